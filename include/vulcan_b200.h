@@ -1,0 +1,177 @@
+/* vulcan_b200 — C ABI of the B200-native Ros2 hot path of VULCAN (exoclime/VULCAN).
+ *
+ * Drop-in boundary: the reference has no native interface for this path — the solver is a Python
+ * class looked up by name (`getattr(op, vulcan_cfg.ode_solver)()`, vulcan.py:162-163) whose methods call the
+ * sympy-generated chem_funs.py and scipy.linalg.solve_banded.  The entry points below are what a ctypes binding
+ * of that class needs; each one cites the reference routine it replaces.  All pointers are HOST pointers unless the
+ * name ends in `_dev`; all arrays are C-order fp64 (or int32 where stated); nothing is thrown across the ABI: every
+ * function returns 0 on success or a negative vk_status, and vk_last_error() returns a message for the calling thread.
+ * A handle is bound to one CUDA device and one stream and is not thread-safe.
+ *
+ * Layouts:  y, ymix, sol ...  [ncol][nz][ni]      k  [ncol][nz][nr+1]  (layer-major; slot 0 unused; the reference's
+ * var.k is a dict {1..nr -> (nz,)} (store.py:25, op.py:166-186) — the Python host packs it)
+ */
+#ifndef VULCAN_B200_H
+#define VULCAN_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VK_ABI_VERSION 1
+
+typedef enum {
+    VK_OK = 0,
+    VK_ERR_INVALID = -1,    /* bad argument */
+    VK_ERR_CUDA = -2,       /* CUDA runtime error (no device, launch failure, out of memory) */
+    VK_ERR_UNSUPPORTED = -3,/* network too large for the compiled kernel set / flag combination not built */
+    VK_ERR_SINGULAR = -4    /* a diagonal block was exactly singular during factorisation */
+} vk_status;
+
+typedef struct vk_network vk_network; /* compiled reaction network on one device */
+typedef struct vk_column vk_column;   /* a batch of ncol independent columns (ncol = 1: the drop-in case) */
+
+int vk_abi_version(void);
+const char *vk_last_error(void);
+/* number of CUDA devices visible; <0 on error.  The product has NO CPU fallback: every compute entry point fails
+ * with VK_ERR_CUDA when there is no device. */
+int vk_device_count(void);
+
+/* ---- network: replaces the generated chem_funs.py (make_chem_funs.py:113-717) --------------------------------
+ * Tables come from vulcan_b200/network.py::Network.tables(): the rate-of-progress monomials, the per-species
+ * production/loss lists in reference summation order, and the analytic Jacobian term lists. */
+typedef struct {
+    int ni, nr;               /* species, reactions (forward+reverse) */
+    int maxf, maxjf;          /* factor slots per rate term / per Jacobian term */
+    int n_rhs, n_ent, n_term; /* lengths of rhs_pair, jac_row, jac_k */
+    const int *rate_fac;      /* [nr+1][maxf]  species index | ni = third body M | ni+1 = 1.0 */
+    const int *rate_pow;      /* [nr+1][maxf] */
+    const int *rhs_ptr;       /* [ni+1] */
+    const int *rhs_pair;      /* [n_rhs] forward reaction id j (odd): term = coef*(rate[j]-rate[j+1]) */
+    const double *rhs_coef;   /* [n_rhs] */
+    const int *jac_ptr;       /* [n_ent+1] */
+    const int *jac_row;       /* [n_ent] */
+    const int *jac_col;       /* [n_ent] */
+    const int *jac_k;         /* [n_term] */
+    const double *jac_coef;   /* [n_term] */
+    const int *jac_fac;       /* [n_term][maxjf] */
+} vk_network_desc;
+
+int vk_network_create(const vk_network_desc *desc, int device, vk_network **out);
+void vk_network_destroy(vk_network *net);
+
+/* ---- columns --------------------------------------------------------------------------------------------- */
+int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out);
+void vk_column_destroy(vk_column *col);
+
+/* Transport / boundary-condition view: the store.AtmData fields read by ODESolver.diffdf* and lhs_jac_*
+ * (op.py:1438-2444).  Arrays are per column ([ncol][...]) unless `shared` is non-zero (then one copy serves all). */
+typedef struct {
+    int shared;
+    int use_moldiff, use_settling, use_topflux, use_botflux; /* vulcan_cfg flags (op.py:2869-2888, 1589-1595) */
+    int n_gas;               /* species summed into ysum for diffdf / ymix (0 = all)  op.py:1505-1507, 2990-2993 */
+    const int *gas_indx;     /* [n_gas] */
+    int n_gas_lhs;           /* same list as used by the lhs variant (op.py:1981-1984) */
+    const int *gas_indx_lhs;
+    const double *Kzz, *vz, *dzi;  /* [nz-1] */
+    const double *Dzz, *vs;        /* [nz-1][ni] */
+    const double *Tco, *g, *M;     /* [nz] */
+    const double *Ti, *Hpi;        /* [nz-1] */
+    const double *ms, *alpha, *top_flux, *bot_flux, *bot_vdep; /* [ni] */
+} vk_atm_view;
+int vk_set_atm(vk_column *col, const vk_atm_view *atm);
+
+/* rate coefficients: var.k packed [ncol][nz][nr+1] (or one copy when shared != 0) */
+int vk_set_k(vk_column *col, const double *k, int shared);
+/* overwrite whole reactions (e.g. the photolysis J rows after compute_J, op.py:2785-2786):
+ * rows[n_rows] reaction ids, vals [ncol][n_rows][nz] */
+int vk_set_k_rows(vk_column *col, int n_rows, const int *rows, const double *vals);
+
+/* step options: the vulcan_cfg / para state consulted inside Ros2.solver (op.py:2896-2970) */
+typedef struct {
+    double mtol, atol;               /* vulcan_cfg.mtol / atol (op.py:2949-2950) */
+    int refine;                      /* fp64 iterative-refinement passes per linear solve (0 = none) */
+    int zero_delta_row0;             /* use_botflux or use_fix_sp_bot: delta[0] = 0 (op.py:2953) */
+    int n_fix_bot;                   /* use_fix_sp_bot (op.py:2945-2946) */
+    const int *fix_bot_idx;          /* [n_fix_bot] species */
+    const double *fix_bot_val;       /* [ncol][n_fix_bot] = mix * n_0[0] */
+    const unsigned char *delta_zero_sp; /* [ni] species whose delta is ignored (op.py:2956-2970) or NULL */
+    const unsigned char *fix_mask;   /* [ncol][nz][ni] rows pinned to identity (fix_species / electrons) or NULL */
+    const double *fix_y;             /* [ncol][nz][ni] values re-imposed where fix_mask (op.py:2960-2968) or NULL */
+} vk_step_opts;
+int vk_set_step_opts(vk_column *col, const vk_step_opts *opts);
+
+/* ---- the hot path -------------------------------------------------------------------------------------------
+ * vk_ros2_solve  ≙  Ros2.solver (op.py:2860-3007): one ATTEMPTED step of every column in the batch.
+ *   in : y, ymix [ncol][nz][ni], dt[ncol]
+ *   out: sol, ymix_out [ncol][nz][ni], delta[ncol] (para.delta), status[ncol] (0 or VK_ERR_SINGULAR)
+ * Host buffers; H2D/D2H copies are part of the call (the reference's Integration reads var.y every step). */
+int vk_ros2_solve(vk_column *col, const double *y, const double *ymix, const double *dt, double *sol,
+                  double *ymix_out, double *delta, int *status);
+
+/* ODESolver.clip + loss (op.py:2447-2487) on host arrays.  compo [ni][na]; atom_sum out [ncol][na];
+ * small_y / nega_y [ncol] are ACCUMULATED like para.small_y / para.nega_y. */
+int vk_clip_loss(vk_column *col, double *y, const double *ymix_in, double *ymix_out, int na, const double *compo,
+                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double *atom_sum, double *small_y,
+                 double *nega_y, int *any_negative);
+
+/* ---- component entry points (parity tests, diagnostics) ---------------------------------------------------- */
+/* chem_funs.chemdf (chem_funs.py:931) + ODESolver.diffdf* (op.py:1438-1898): out_chem/out_diff [ncol][nz][ni],
+ * either may be NULL */
+int vk_eval_rhs(vk_column *col, const double *y, double *out_chem, double *out_diff);
+/* lhs_jac_* (op.py:1973-2444): D [ncol][nz][ni][ni] diagonal blocks, up/dn [ncol][nz][ni] diagonal couplings */
+int vk_eval_lhs(vk_column *col, const double *y, const double *dt, double *D, double *up, double *dn);
+/* block-tridiagonal factor + solve of a caller-supplied system (replaces store_bandM + solve_banded,
+ * op.py:2833-2858, 2914): D [ncol][nz][ni][ni], up/dn/rhs/x [ncol][nz][ni] */
+int vk_blocktri_solve(vk_column *col, const double *D, const double *up, const double *dn, const double *rhs,
+                      double *x, int refine, int *status);
+
+/* ---- photolysis: compute_tau / compute_flux / compute_J (op.py:2580-2786) ---------------------------------- */
+typedef struct {
+    int nbin, i12;                 /* var.nbin, var.sflux_din12_indx */
+    double dbin1, dbin2;           /* trapezoid weights */
+    double sl_angle, edd, flux_atol, f_diurnal; /* vulcan_cfg */
+    const double *bins;            /* [nbin] wavelengths (nm) */
+    const double *sflux_top;       /* [nbin] */
+    int n_abs;  const int *abs_idx;  const double *cross_abs;   /* tau absorbers (photo ∪ ion species): [n_abs][nbin] */
+    const unsigned char *abs_is_T; const double *cross_abs_T;   /* optional T-dependent: [n_abs][nz][nbin] */
+    int n_photo; const int *photo_idx; const double *cross_photo; /* omega0 absorbers (photo_sp): [n_photo][nbin] */
+    int n_scat; const int *scat_idx; const double *cross_scat;  /* Rayleigh: [n_scat][nbin] */
+    int n_br;   const double *cross_J; const int *br_rate_index; /* [n_br][nbin], reaction id per branch (0 = skip) */
+    const unsigned char *br_is_T; const double *cross_J_T;      /* optional [n_br][nz][nbin] */
+} vk_photo_view;
+int vk_photo_setup(vk_column *col, const vk_photo_view *pv);
+/* one photolysis update of every column: y, ymix [ncol][nz][ni], dz [ncol][nz] ->
+ * J [ncol][n_br][nz] (also written into the device copy of k as J*f_diurnal), aflux_change [ncol].
+ * The diffuse-flux state (var.dflux_u of the previous call, op.py:2692) lives on the device between calls. */
+int vk_photo_update(vk_column *col, const double *y, const double *ymix, const double *dz, double *J,
+                    double *aflux_change);
+/* optional read-back of the photolysis fields (debug / parity): any pointer may be NULL.
+ * tau, sflux, dflux_u, dflux_d [ncol][nz+1][nbin]; aflux [ncol][nz][nbin] */
+int vk_photo_read(vk_column *col, double *tau, double *sflux, double *dflux_u, double *dflux_d, double *aflux);
+int vk_photo_reset(vk_column *col);
+
+/* ---- device-resident ensemble driver (Integration.__call__ / one_step / step_size batched) -- */
+typedef struct {
+    double rtol, loss_eps, dt_min, dt_max, dt_var_min, dt_var_max; /* op.py:2489-2534, 3105-3125 */
+    double pos_cut, nega_cut;
+    int na; const double *compo; const double *atom_ini;          /* [ni][na], [ncol][na] */
+    const double *n_0;                                            /* [ncol][nz] hydrostatic rescale (op.py:909-914) */
+} vk_ens_opts;
+int vk_ens_setup(vk_column *col, const vk_ens_opts *o);
+int vk_ens_set_state(vk_column *col, const double *y, const double *dt);
+/* n_steps loop iterations of every column entirely on the device: solver -> clip -> accept/reject(+retry next
+ * iteration with dt/2) -> rescale -> step_size.  No host round trip inside. */
+int vk_ens_run(vk_column *col, int n_steps);
+/* accepted / rejected counters [ncol], model time t [ncol], dt [ncol], y [ncol][nz][ni]; any may be NULL */
+int vk_ens_get_state(vk_column *col, double *y, double *t, double *dt, int *n_accept, int *n_reject);
+
+/* timing of the last vk_ros2_solve / vk_ens_run on the handle's stream, measured with CUDA events (ms) */
+int vk_last_kernel_ms(vk_column *col, float *ms_total, float *ms_factor);
+/* raw device pointers for callers that keep state resident (torch tensors): y/ymix/sol [ncol][nz][ni] */
+int vk_device_buffers(vk_column *col, void **y_dev, void **ymix_dev, void **sol_dev, void **k_dev);
+int vk_stream(vk_column *col, void **cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,165 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, vulcan_b200/_abi.py) against the CPU oracle on the same
+inputs and against the golden fixtures produced by the unmodified reference.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from helpers import Case, GOLD, have, ulp_diff
+
+pytestmark = pytest.mark.gpu
+
+STEPS = [0, 10, 100, 300]
+R = 1. + 1. / 2. ** 0.5
+
+
+def _columns(case, ncol=1, refine=0):
+    from vulcan_b200 import _abi
+    kw = case.atm_kwargs()
+    net = _abi.DeviceNetwork(case.net)
+    col = _abi.Columns(net, case.nz, ncol)
+    col.set_atm(Kzz=kw["Kzz"], vz=kw["vz"], dzi=kw["dzi"], Dzz=kw["Dzz"], vs=kw["vs"], Tco=kw["Tco"], g=kw["g"], M=kw["M"],
+                Ti=kw["Ti"], Hpi=kw["Hpi"], ms=kw["ms"], alpha=kw["alpha"], top_flux=kw["top_flux"], bot_flux=kw["bot_flux"],
+                bot_vdep=kw["bot_vdep"], use_moldiff=kw["use_moldiff"], use_settling=kw["use_settling"],
+                use_topflux=kw["use_topflux"], use_botflux=kw["use_botflux"], gas_indx=kw["gas_indx"],
+                gas_indx_lhs=kw["gas_indx_lhs"], shared=True)
+    col.set_k(case.k)
+    col.set_step_opts(case.cfg["mtol"], case.cfg["atol"], refine=refine)
+    return col
+
+
+@pytest.fixture(scope="module", params=STEPS)
+def case(request):
+    if not have("HD189", "step%04d.npz" % request.param):
+        pytest.skip("fixture missing")
+    from oracle import Oracle
+    c = Case("HD189", request.param)
+    c.oracle = Oracle(c.net)
+    c.atm = c.oracle.make_atm(**c.atm_kwargs())
+    c.col = _columns(c)
+    return c
+
+
+def test_rhs_bit_exact(case):
+    """chemdf + diffdf: bit-identical to the oracle AND to the reference fixture (make_chem_funs.py:113-430, op.py:1496-1597)."""
+    chem, diff = case.col.eval_rhs(case.y)
+    assert np.array_equal(chem[0], case.oracle.chemdf(case.y, case.st["M"], case.k))
+    assert np.array_equal(chem[0], case.fx["chemdf"])
+    assert np.array_equal(diff[0], case.oracle.diffdf(case.atm, case.y))
+    assert np.array_equal(diff[0], case.fx["diffdf"])
+
+
+def test_lhs_blocks(case):
+    """lhs_jac_tot (op.py:1973-2042): couplings bit-identical to the reference; blocks identical to the oracle
+    (same term order) and within Jacobian rounding of the reference's sympy ordering."""
+    D, up, dn = case.col.eval_lhs(case.y, case.dt)
+    Do, upo, dno = case.oracle.lhs(case.atm, case.y, case.k, case.dt)
+    assert np.array_equal(up[0], case.fx["lhs_up"]) and np.array_equal(dn[0], case.fx["lhs_dn"])
+    assert np.array_equal(up[0], upo) and np.array_equal(dn[0], dno)
+    assert np.array_equal(D[0], Do)
+    for i, j in enumerate(case.fx["layers"]):
+        ref = case.fx["lhs_blocks"][i]
+        assert np.max(np.abs(D[0, j] - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 4e-15
+
+
+def test_blocktri_solve_vs_truth(case):
+    """the GPU block-tridiagonal solve is at least as close to the extended-precision solution as LAPACK's (reference)."""
+    o = case.oracle
+    D, up, dn = o.lhs(case.atm, case.y, case.k, case.dt)
+    rhs = case.fx["chemdf"] + case.fx["diffdf"]
+    xt = o.blocktri_truth(D, up, dn, rhs, 3)
+    ykt = case.y + xt / R
+    mask = np.abs(ykt) > case.cfg["atol"]
+
+    def err(x):
+        yk = case.y + x / R
+        return np.max(np.abs(yk - ykt)[mask] / np.abs(ykt)[mask])
+    x0, st0 = case.col.blocktri_solve(D, up, dn, rhs, refine=0)
+    x1, st1 = case.col.blocktri_solve(D, up, dn, rhs, refine=1)
+    assert st0[0] == 0 and st1[0] == 0
+    e_ref, e0, e1 = err(case.fx["k1"]), err(x0[0]), err(x1[0])
+    print("step %d dt %.2e: err vs truth  reference(LAPACK) %.2e  gpu %.2e  gpu+refine %.2e" % (case.step, case.dt, e_ref, e0, e1))
+    assert e0 <= max(10 * e_ref, 1e-12)
+    assert e1 <= max(e_ref, 1e-13)
+    # backward error of the plain solve
+    res = rhs - o.blocktri_matvec(D, up, dn, x1[0])
+    assert np.abs(res).max() <= 1e-9 * np.abs(rhs).max()
+
+
+def test_ros2_step(case):
+    """one attempted step through vk_ros2_solve vs the reference's Ros2.solver output.
+    Small dt: BASELINE's 1e-10 on every n > 1e-30.  Production dt: conditioning-limited, so the comparison is made under
+    the reference's own significance mask and delta must agree to 1e-6 relative."""
+    cfg = case.cfg
+    col = _columns(case, refine=1)
+    sol, ymix, delta, status = col.ros2_solve(case.y, case.ymix, case.dt)
+    assert status[0] == 0
+    ref = case.fx["sol"]
+    if case.dt <= 1e-6:
+        m = ref > 1e-30
+        assert np.max(np.abs(sol[0] - ref)[m] / ref[m]) < 1e-10
+        assert abs(delta[0] - float(case.fx["delta"])) <= 1e-10 * float(case.fx["delta"])
+        m = case.fx["sol_ymix"] > 1e-30
+        assert np.max(np.abs(ymix[0] - case.fx["sol_ymix"])[m] / case.fx["sol_ymix"][m]) < 1e-10
+    else:
+        assert abs(delta[0] - float(case.fx["delta"])) <= 1e-6 * float(case.fx["delta"])
+        m = ref > 1e5
+        assert np.max(np.abs(sol[0] - ref)[m] / ref[m]) < 1e-3
+    # against the oracle running the same algorithm (refine=1): tight everywhere that matters
+    res = case.oracle.ros2_solver(case.atm, case.y, case.ymix, case.k, case.dt, cfg["mtol"], cfg["atol"], refine=1)
+    m = (res["sol"] > cfg["atol"]) & (res["ymix"] > cfg["mtol"])
+    tol = 1e-10 if case.dt <= 1e-6 else 1e-5
+    assert np.max(np.abs(sol[0] - res["sol"])[m] / res["sol"][m]) < tol
+    assert abs(delta[0] - res["delta"]) <= 1e-7 * res["delta"]
+
+
+def test_clip_loss(case):
+    cfg = case.cfg
+    res = case.col.clip_loss(case.fx["sol"], case.fx["sol_ymix"], case.st["compo"], cfg["pos_cut"], cfg["nega_cut"])
+    assert np.array_equal(res["y"][0], case.fx["clip_y"])
+    assert np.array_equal(res["ymix"][0], case.fx["clip_ymix"])
+    assert np.allclose(res["atom_sum"][0], case.fx["atom_sum"], rtol=1e-13, atol=0)
+    assert int(res["any_negative"][0]) == int(np.any(case.fx["clip_y"] < 0))
+
+
+def test_batched_columns_identical():
+    """ncol > 1: every column of a batch of identical inputs gives the single-column answer bit for bit."""
+    c = Case("HD189", 10)
+    col1 = _columns(c, 1)
+    col4 = _columns(c, 4)
+    s1, m1, d1, _ = col1.ros2_solve(c.y, c.ymix, c.dt)
+    y4 = np.repeat(c.y[None], 4, axis=0)
+    m4 = np.repeat(c.ymix[None], 4, axis=0)
+    s4, mm4, d4, st4 = col4.ros2_solve(y4, m4, np.full(4, c.dt))
+    for i in range(4):
+        assert np.array_equal(s4[i], s1[0]) and np.array_equal(mm4[i], m1[0]) and d4[i] == d1[0] and st4[i] == 0
+
+
+@pytest.mark.parametrize("step", [0, 300])
+def test_photolysis(step):
+    """compute_tau / compute_flux / compute_J on the GPU vs reference fixture (two consecutive updates)."""
+    if not have("HD189", "photo%04d.npz" % step):
+        pytest.skip("fixture missing")
+    c = Case("HD189", step)
+    st, cfg = c.st, c.cfg
+    px = np.load("%s/HD189_photo%04d.npz" % (GOLD, step))
+    col = _columns(c)
+    col.photo_setup(st["bins"], st["sflux_top"], int(st["sflux_din12_indx"]), float(st["dbin1"]), float(st["dbin2"]),
+                    cfg["sl_angle"], cfg["edd"], cfg["flux_atol"], cfg["f_diurnal"], st["photo_sp_idx"], st["cross"],
+                    st["photo_sp_idx"], st["cross"], st["scat_sp_idx"], st["cross_scat"], st["cross_J"],
+                    st["branch_rate_index"])
+    sel = px["bin_sel"]
+    for it in (1, 2):
+        J, ch = col.photo_update(px["y"], px["ymix"], px["dz"])
+        f = col.photo_read()
+        ref = px["tau%d" % it]
+        assert np.max(np.abs(f["tau"][0][:, sel] - ref) / np.maximum(np.abs(ref), 1e-300)) < 1e-13
+        for name in ("sflux", "dflux_u", "dflux_d", "aflux"):
+            ref = px["%s%d" % (name, it)]
+            got = f[name][0][:, sel]
+            if name.startswith("dflux"):
+                scale = np.maximum(np.maximum(np.abs(ref).max(axis=0), np.abs(px["sflux%d" % it]).max(axis=0)), 1e-300)[None, :]
+            else:
+                scale = np.maximum(np.abs(ref), 1e-30 * np.abs(ref).max())
+            assert np.max(np.abs(got - ref) / scale) < 1e-9, name
+        assert abs(ch[0] - float(px["aflux_change%d" % it])) < 1e-9
+        ref = px["J%d" % it]
+        assert np.max(np.abs(J[0] - ref) / np.maximum(np.abs(ref), 1e-300 + 1e-12 * np.abs(ref).max(axis=1, keepdims=True))) < 1e-9

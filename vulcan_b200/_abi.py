@@ -1,0 +1,360 @@
+"""ctypes binding of include/vulcan_b200.h (libvulcan_b200.so, hand-written sm_100a CUDA).
+
+There is NO CPU fallback: if the shared library is missing or no CUDA device is visible, every compute
+entry point raises.  (Loading the library and listing its symbols works without a GPU.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_lib", "libvulcan_b200.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_bp = C.POINTER(C.c_ubyte)
+_vp = C.c_void_p
+
+VK_OK, VK_ERR_INVALID, VK_ERR_CUDA, VK_ERR_UNSUPPORTED, VK_ERR_SINGULAR = 0, -1, -2, -3, -4
+
+# every symbol include/vulcan_b200.h declares (tests/test_abi.py checks the header against this list and the .so)
+SYMBOLS = [
+    "vk_abi_version", "vk_last_error", "vk_device_count", "vk_network_create", "vk_network_destroy",
+    "vk_column_create", "vk_column_destroy", "vk_set_atm", "vk_set_k", "vk_set_k_rows", "vk_set_step_opts",
+    "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
+    "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
+    "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream",
+]
+
+
+class VulcanB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "vulcan_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class NetworkDesc(C.Structure):
+    _fields_ = [("ni", C.c_int), ("nr", C.c_int), ("maxf", C.c_int), ("maxjf", C.c_int), ("n_rhs", C.c_int),
+                ("n_ent", C.c_int), ("n_term", C.c_int), ("rate_fac", _ip), ("rate_pow", _ip), ("rhs_ptr", _ip),
+                ("rhs_pair", _ip), ("rhs_coef", _dp), ("jac_ptr", _ip), ("jac_row", _ip), ("jac_col", _ip),
+                ("jac_k", _ip), ("jac_coef", _dp), ("jac_fac", _ip)]
+
+
+class AtmView(C.Structure):
+    _fields_ = [("shared", C.c_int), ("use_moldiff", C.c_int), ("use_settling", C.c_int), ("use_topflux", C.c_int),
+                ("use_botflux", C.c_int), ("n_gas", C.c_int), ("gas_indx", _ip), ("n_gas_lhs", C.c_int),
+                ("gas_indx_lhs", _ip), ("Kzz", _dp), ("vz", _dp), ("dzi", _dp), ("Dzz", _dp), ("vs", _dp),
+                ("Tco", _dp), ("g", _dp), ("M", _dp), ("Ti", _dp), ("Hpi", _dp), ("ms", _dp), ("alpha", _dp),
+                ("top_flux", _dp), ("bot_flux", _dp), ("bot_vdep", _dp)]
+
+
+class StepOpts(C.Structure):
+    _fields_ = [("mtol", C.c_double), ("atol", C.c_double), ("refine", C.c_int), ("zero_delta_row0", C.c_int),
+                ("n_fix_bot", C.c_int), ("fix_bot_idx", _ip), ("fix_bot_val", _dp), ("delta_zero_sp", _bp),
+                ("fix_mask", _bp), ("fix_y", _dp)]
+
+
+class PhotoView(C.Structure):
+    _fields_ = [("nbin", C.c_int), ("i12", C.c_int), ("dbin1", C.c_double), ("dbin2", C.c_double),
+                ("sl_angle", C.c_double), ("edd", C.c_double), ("flux_atol", C.c_double), ("f_diurnal", C.c_double),
+                ("bins", _dp), ("sflux_top", _dp),
+                ("n_abs", C.c_int), ("abs_idx", _ip), ("cross_abs", _dp), ("abs_is_T", _bp), ("cross_abs_T", _dp),
+                ("n_photo", C.c_int), ("photo_idx", _ip), ("cross_photo", _dp),
+                ("n_scat", C.c_int), ("scat_idx", _ip), ("cross_scat", _dp),
+                ("n_br", C.c_int), ("cross_J", _dp), ("br_rate_index", _ip), ("br_is_T", _bp), ("cross_J_T", _dp)]
+
+
+class EnsOpts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("loss_eps", C.c_double), ("dt_min", C.c_double), ("dt_max", C.c_double),
+                ("dt_var_min", C.c_double), ("dt_var_max", C.c_double), ("pos_cut", C.c_double), ("nega_cut", C.c_double),
+                ("na", C.c_int), ("compo", _dp), ("atom_ini", _dp), ("n_0", _dp)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library (built by vulcan_b200/build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VulcanB200Error(VK_ERR_CUDA, "%s not built: run `python -m vulcan_b200.build` (no CPU fallback exists)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.vk_last_error.restype = C.c_char_p
+    for name in SYMBOLS:
+        getattr(lib, name)
+    lib.vk_network_create.argtypes = [C.POINTER(NetworkDesc), C.c_int, C.POINTER(_vp)]
+    lib.vk_network_destroy.argtypes = [_vp]
+    lib.vk_network_destroy.restype = None
+    lib.vk_column_create.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(_vp)]
+    lib.vk_column_destroy.argtypes = [_vp]
+    lib.vk_column_destroy.restype = None
+    lib.vk_set_atm.argtypes = [_vp, C.POINTER(AtmView)]
+    lib.vk_set_k.argtypes = [_vp, _dp, C.c_int]
+    lib.vk_set_k_rows.argtypes = [_vp, C.c_int, _ip, _dp]
+    lib.vk_set_step_opts.argtypes = [_vp, C.POINTER(StepOpts)]
+    lib.vk_ros2_solve.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
+    lib.vk_clip_loss.argtypes = [_vp, _dp, _dp, _dp, C.c_int, _dp, _bp, C.c_double, C.c_double, _dp, _dp, _dp, _ip]
+    lib.vk_eval_rhs.argtypes = [_vp, _dp, _dp, _dp]
+    lib.vk_eval_lhs.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
+    lib.vk_blocktri_solve.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int, _ip]
+    lib.vk_photo_setup.argtypes = [_vp, C.POINTER(PhotoView)]
+    lib.vk_photo_update.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
+    lib.vk_photo_read.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
+    lib.vk_photo_reset.argtypes = [_vp]
+    lib.vk_ens_setup.argtypes = [_vp, C.POINTER(EnsOpts)]
+    lib.vk_ens_set_state.argtypes = [_vp, _dp, _dp]
+    lib.vk_ens_run.argtypes = [_vp, C.c_int]
+    lib.vk_ens_get_state.argtypes = [_vp, _dp, _dp, _dp, _ip, _ip]
+    lib.vk_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.vk_device_buffers.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
+    lib.vk_stream.argtypes = [_vp, C.POINTER(_vp)]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise VulcanB200Error(rc, load().vk_last_error().decode("utf-8", "replace"))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def dptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def iptr(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def bptr(a):
+    return None if a is None else a.ctypes.data_as(_bp)
+
+
+class DeviceNetwork(object):
+    """vk_network handle: the compiled reaction network resident on one GPU."""
+
+    def __init__(self, network, device=0):
+        self.lib = load()
+        n = self.lib.vk_device_count()
+        if n <= 0:
+            raise VulcanB200Error(VK_ERR_CUDA, "no CUDA device visible (vulcan_b200 has no CPU fallback)")
+        self.network = network
+        t = network.tables()
+        self._keep = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in t.items()}
+        k = self._keep
+        d = NetworkDesc(t["ni"], t["nr"], t["maxf"], t["maxjf"], len(k["rhs_pair"]), len(k["jac_row"]), len(k["jac_k"]),
+                        iptr(k["rate_fac"]), iptr(k["rate_pow"]), iptr(k["rhs_ptr"]), iptr(k["rhs_pair"]),
+                        dptr(k["rhs_coef"]), iptr(k["jac_ptr"]), iptr(k["jac_row"]), iptr(k["jac_col"]), iptr(k["jac_k"]),
+                        dptr(k["jac_coef"]), iptr(k["jac_fac"]))
+        h = _vp()
+        check(self.lib.vk_network_create(C.byref(d), int(device), C.byref(h)))
+        self.handle = h
+        self.ni, self.nr, self.device = t["ni"], t["nr"], device
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vk_network_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Columns(object):
+    """vk_column handle: `ncol` independent columns of `nz` layers on the network's device."""
+
+    def __init__(self, devnet, nz, ncol=1):
+        self.lib = devnet.lib
+        self.devnet = devnet
+        self.nz, self.ncol, self.ni, self.nr = int(nz), int(ncol), devnet.ni, devnet.nr
+        h = _vp()
+        check(self.lib.vk_column_create(devnet.handle, self.nz, self.ncol, C.byref(h)))
+        self.handle = h
+        self._photo_nbr = 0
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.vk_column_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape(self, a, tail):
+        a = f64(a)
+        want = (self.ncol,) + tail
+        if a.shape == tail and self.ncol == 1:
+            a = a.reshape(want)
+        if a.shape != want:
+            raise ValueError("expected shape %s, got %s" % (want, a.shape))
+        return a
+
+    # ---------------------------------------------------------------- inputs
+    def set_atm(self, Kzz, vz, dzi, Dzz, vs, Tco, g, M, Ti, Hpi, ms, alpha, top_flux, bot_flux, bot_vdep,
+                use_moldiff=True, use_settling=False, use_topflux=False, use_botflux=False, gas_indx=None,
+                gas_indx_lhs=None, shared=True):
+        nz, ni = self.nz, self.ni
+        rep = () if shared else (self.ncol,)
+
+        def arr(a, tail):
+            a = f64(a)
+            if a.shape != rep + tail:
+                raise ValueError("atm array: expected %s, got %s" % (rep + tail, a.shape))
+            return a
+        keep = dict(Kzz=arr(Kzz, (nz - 1,)), vz=arr(vz, (nz - 1,)), dzi=arr(dzi, (nz - 1,)), Dzz=arr(Dzz, (nz - 1, ni)),
+                    vs=arr(vs, (nz - 1, ni)), Tco=arr(Tco, (nz,)), g=arr(g, (nz,)), M=arr(M, (nz,)), Ti=arr(Ti, (nz - 1,)),
+                    Hpi=arr(Hpi, (nz - 1,)), ms=arr(ms, (ni,)), alpha=arr(alpha, (ni,)), top_flux=arr(top_flux, (ni,)),
+                    bot_flux=arr(bot_flux, (ni,)), bot_vdep=arr(bot_vdep, (ni,)))
+        gi = None if gas_indx is None or len(gas_indx) == ni else i32(gas_indx)
+        gl = None if gas_indx_lhs is None or len(gas_indx_lhs) == ni else i32(gas_indx_lhs)
+        v = AtmView(int(shared), int(use_moldiff), int(use_settling), int(use_topflux), int(use_botflux),
+                    0 if gi is None else len(gi), iptr(gi), 0 if gl is None else len(gl), iptr(gl),
+                    dptr(keep["Kzz"]), dptr(keep["vz"]), dptr(keep["dzi"]), dptr(keep["Dzz"]), dptr(keep["vs"]),
+                    dptr(keep["Tco"]), dptr(keep["g"]), dptr(keep["M"]), dptr(keep["Ti"]), dptr(keep["Hpi"]),
+                    dptr(keep["ms"]), dptr(keep["alpha"]), dptr(keep["top_flux"]), dptr(keep["bot_flux"]),
+                    dptr(keep["bot_vdep"]))
+        check(self.lib.vk_set_atm(self.handle, C.byref(v)))
+
+    def set_k(self, k, shared=None):
+        """k: [nz, nr+1] (shared by all columns) or [ncol, nz, nr+1]."""
+        k = f64(k)
+        if shared is None:
+            shared = (k.ndim == 2)
+        want = (self.nz, self.nr + 1) if shared else (self.ncol, self.nz, self.nr + 1)
+        if k.shape != want:
+            raise ValueError("k: expected %s, got %s" % (want, k.shape))
+        check(self.lib.vk_set_k(self.handle, dptr(k), int(shared)))
+        self._k_shared = bool(shared)
+
+    def set_k_rows(self, rows, vals):
+        rows, vals = i32(rows), f64(vals)
+        check(self.lib.vk_set_k_rows(self.handle, len(rows), iptr(rows), dptr(vals)))
+
+    def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None,
+                      delta_zero_sp=None, fix_mask=None, fix_y=None):
+        fbi = i32(fix_bot_idx)
+        fbv = None if len(fbi) == 0 else f64(fix_bot_val).reshape(self.ncol, len(fbi))
+        dz = None if delta_zero_sp is None else u8(delta_zero_sp)
+        fm = None if fix_mask is None else u8(fix_mask).reshape(self.ncol, self.nz, self.ni)
+        fy = None if fix_y is None else f64(fix_y).reshape(self.ncol, self.nz, self.ni)
+        o = StepOpts(float(mtol), float(atol), int(refine), int(zero_delta_row0), len(fbi), iptr(fbi) if len(fbi) else None,
+                     dptr(fbv), bptr(dz), bptr(fm), dptr(fy))
+        check(self.lib.vk_set_step_opts(self.handle, C.byref(o)))
+
+    # ---------------------------------------------------------------- hot path
+    def ros2_solve(self, y, ymix, dt):
+        """≙ Ros2.solver (op.py:2860-3007) for every column.  Returns sol, ymix, delta[ncol], status[ncol]."""
+        y = self._shape(y, (self.nz, self.ni))
+        ymix = self._shape(ymix, (self.nz, self.ni))
+        dt = f64(np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,)))
+        sol, ymo = np.empty_like(y), np.empty_like(y)
+        delta = np.empty(self.ncol)
+        status = np.zeros(self.ncol, dtype=np.int32)
+        check(self.lib.vk_ros2_solve(self.handle, dptr(y), dptr(ymix), dptr(dt), dptr(sol), dptr(ymo), dptr(delta), iptr(status)))
+        return sol, ymo, delta, status
+
+    def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None):
+        y = self._shape(y, (self.nz, self.ni)).copy()
+        ymix_in = self._shape(ymix_in, (self.nz, self.ni))
+        compo = f64(compo)
+        na = compo.shape[1]
+        ymo = np.empty_like(y)
+        asum = np.zeros((self.ncol, na)) if atom_sum is None else f64(atom_sum).reshape(self.ncol, na).copy()
+        sm = np.zeros(self.ncol) if small_y is None else f64(small_y).reshape(self.ncol).copy()
+        ng = np.zeros(self.ncol) if nega_y is None else f64(nega_y).reshape(self.ncol).copy()
+        anyneg = np.zeros(self.ncol, dtype=np.int32)
+        sk = None if atom_skip is None else u8(atom_skip)
+        check(self.lib.vk_clip_loss(self.handle, dptr(y), dptr(ymix_in), dptr(ymo), na, dptr(compo), bptr(sk),
+                                    float(pos_cut), float(nega_cut), dptr(asum), dptr(sm), dptr(ng), iptr(anyneg)))
+        return dict(y=y, ymix=ymo, atom_sum=asum, small_y=sm, nega_y=ng, any_negative=anyneg)
+
+    # ---------------------------------------------------------------- components
+    def eval_rhs(self, y):
+        y = self._shape(y, (self.nz, self.ni))
+        chem, diff = np.empty_like(y), np.empty_like(y)
+        check(self.lib.vk_eval_rhs(self.handle, dptr(y), dptr(chem), dptr(diff)))
+        return chem, diff
+
+    def eval_lhs(self, y, dt):
+        y = self._shape(y, (self.nz, self.ni))
+        dt = f64(np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,)))
+        D = np.empty((self.ncol, self.nz, self.ni, self.ni))
+        up, dn = np.empty_like(y), np.empty_like(y)
+        check(self.lib.vk_eval_lhs(self.handle, dptr(y), dptr(dt), dptr(D), dptr(up), dptr(dn)))
+        return D, up, dn
+
+    def blocktri_solve(self, D, up, dn, rhs, refine=0):
+        D = self._shape(D, (self.nz, self.ni, self.ni))
+        up, dn, rhs = (self._shape(a, (self.nz, self.ni)) for a in (up, dn, rhs))
+        x = np.empty_like(rhs)
+        status = np.zeros(self.ncol, dtype=np.int32)
+        check(self.lib.vk_blocktri_solve(self.handle, dptr(D), dptr(up), dptr(dn), dptr(rhs), dptr(x), int(refine), iptr(status)))
+        return x, status
+
+    # ---------------------------------------------------------------- photolysis
+    def photo_setup(self, bins, sflux_top, i12, dbin1, dbin2, sl_angle, edd, flux_atol, f_diurnal, abs_idx, cross_abs,
+                    photo_idx, cross_photo, scat_idx, cross_scat, cross_J, br_rate_index, abs_is_T=None, cross_abs_T=None,
+                    br_is_T=None, cross_J_T=None):
+        bins, sflux_top = f64(bins), f64(sflux_top)
+        nbin = bins.size
+        keep = [bins, sflux_top, i32(abs_idx), f64(cross_abs).reshape(-1, nbin), i32(photo_idx),
+                f64(cross_photo).reshape(-1, nbin), i32(scat_idx), f64(cross_scat).reshape(-1, nbin),
+                f64(cross_J).reshape(-1, nbin), i32(br_rate_index)]
+        aT = None if abs_is_T is None else u8(abs_is_T)
+        cT = None if cross_abs_T is None else f64(cross_abs_T)
+        bT = None if br_is_T is None else u8(br_is_T)
+        jT = None if cross_J_T is None else f64(cross_J_T)
+        v = PhotoView(nbin, int(i12), float(dbin1), float(dbin2), float(sl_angle), float(edd), float(flux_atol),
+                      float(f_diurnal), dptr(keep[0]), dptr(keep[1]),
+                      len(keep[2]), iptr(keep[2]), dptr(keep[3]), bptr(aT), dptr(cT),
+                      len(keep[4]), iptr(keep[4]), dptr(keep[5]),
+                      len(keep[6]), iptr(keep[6]), dptr(keep[7]),
+                      keep[8].shape[0], dptr(keep[8]), iptr(keep[9]), bptr(bT), dptr(jT))
+        check(self.lib.vk_photo_setup(self.handle, C.byref(v)))
+        self._photo_nbr, self._photo_nbin = keep[8].shape[0], nbin
+
+    def photo_update(self, y, ymix, dz):
+        y = self._shape(y, (self.nz, self.ni))
+        ymix = self._shape(ymix, (self.nz, self.ni))
+        dz = self._shape(dz, (self.nz,))
+        J = np.empty((self.ncol, self._photo_nbr, self.nz))
+        ch = np.empty(self.ncol)
+        check(self.lib.vk_photo_update(self.handle, dptr(y), dptr(ymix), dptr(dz), dptr(J), dptr(ch)))
+        return J, ch
+
+    def photo_read(self, names=("tau", "sflux", "dflux_u", "dflux_d", "aflux")):
+        nb = self._photo_nbin
+        out = {}
+        for n in names:
+            out[n] = np.empty((self.ncol, self.nz + (0 if n == "aflux" else 1), nb))
+        args = [dptr(out.get(n)) for n in ("tau", "sflux", "dflux_u", "dflux_d", "aflux")]
+        check(self.lib.vk_photo_read(self.handle, *args))
+        return out
+
+    def photo_reset(self):
+        check(self.lib.vk_photo_reset(self.handle))
+
+    def last_kernel_ms(self):
+        a, b = C.c_float(0), C.c_float(0)
+        check(self.lib.vk_last_kernel_ms(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value

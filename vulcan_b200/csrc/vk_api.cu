@@ -1,0 +1,524 @@
+// C ABI glue (include/vulcan_b200.h): handles, host<->device staging, kernel sequencing for one attempted Ros2 step.
+#include <cstdio>
+#include <cstring>
+
+#include "vk_internal.cuh"
+
+namespace vk {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return VK_ERR_CUDA;
+}
+
+int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *ymix_out_dev, int na, const double *compo_dev,
+                const unsigned char *skip_dev, double pos_cut, double nega_cut, double *atom_sum_dev, double *small_dev,
+                double *nega_dev, int *anyneg_dev);
+void photo_destroy(vk_column *c);
+void ens_destroy(vk_column *c);
+
+template <typename T>
+static int dev_copy(std::vector<void *> &allocs, const T *host, size_t n, const T **out)
+{
+    void *p = nullptr;
+    VK_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+    allocs.push_back(p);
+    if (n) VK_CUDA(cudaMemcpy(p, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(p);
+    return VK_OK;
+}
+
+static int pad_block(int ni)
+{
+    if (ni <= 48) return 48;
+    return 24 * ((ni + 23) / 24);
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+int vk_abi_version(void) { return VK_ABI_VERSION; }
+const char *vk_last_error(void) { return g_err.c_str(); }
+int vk_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDeviceCount"); return VK_ERR_CUDA; }
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
+{
+    if (!d || !out) { set_error("null argument"); return VK_ERR_INVALID; }
+    if (d->ni < 1 || d->ni > 253 || d->nr < 2 || d->nr > 65534) { set_error("network size out of range (ni <= 253, nr <= 65534)"); return VK_ERR_UNSUPPORTED; }
+    if (d->maxf > 4 || d->maxjf > 3) { set_error("more than 4 factors per rate term / 3 per Jacobian term"); return VK_ERR_UNSUPPORTED; }
+    if (pad_block(d->ni) > 120) { set_error("ni > 120: no factor kernel instantiated"); return VK_ERR_UNSUPPORTED; }
+    VK_CUDA(cudaSetDevice(device));
+    vk_network *n = new vk_network();
+    n->device = device;
+    const int ni = d->ni, nr = d->nr;
+    std::vector<uchar4> rf(nr + 1), rp(nr + 1);
+    int has_pow = 0;
+    for (int i = 0; i <= nr; i++) {
+        unsigned char f[4], p[4];
+        for (int q = 0; q < 4; q++) {
+            int slot = (q < d->maxf) ? d->rate_fac[i * d->maxf + q] : ni + 1;
+            int pw = (q < d->maxf) ? d->rate_pow[i * d->maxf + q] : 1;
+            if (i == 0) { slot = ni + 1; pw = 1; }
+            if (slot < 0 || slot > ni + 1 || pw < 1 || pw > 255) { delete n; set_error("bad rate table entry"); return VK_ERR_INVALID; }
+            if (pw != 1) has_pow = 1;
+            f[q] = (unsigned char)slot; p[q] = (unsigned char)pw;
+        }
+        rf[i] = make_uchar4(f[0], f[1], f[2], f[3]);
+        rp[i] = make_uchar4(p[0], p[1], p[2], p[3]);
+    }
+    std::vector<int> rt(d->n_rhs);
+    int max_len = 0;
+    for (int s = 0; s < ni; s++) max_len = std::max(max_len, d->rhs_ptr[s + 1] - d->rhs_ptr[s]);
+    for (int q = 0; q < d->n_rhs; q++) {
+        double c = d->rhs_coef[q];
+        int ci = (int)c;
+        if ((double)ci != c || ci < -127 || ci > 127) { delete n; set_error("non-integer stoichiometric coefficient"); return VK_ERR_UNSUPPORTED; }
+        rt[q] = (d->rhs_pair[q] << 8) | (ci & 0xff);
+    }
+    std::vector<ushort2> rc(d->n_ent);
+    for (int e = 0; e < d->n_ent; e++) rc[e] = make_ushort2((unsigned short)d->jac_row[e], (unsigned short)d->jac_col[e]);
+    std::vector<uint2> jt(d->n_term);
+    for (int q = 0; q < d->n_term; q++) {
+        double c = d->jac_coef[q];
+        int ci = (int)c;
+        if ((double)ci != c || ci < -127 || ci > 127) { delete n; set_error("Jacobian coefficient out of range"); return VK_ERR_UNSUPPORTED; }
+        unsigned f[3];
+        for (int x = 0; x < 3; x++) f[x] = (x < d->maxjf) ? (unsigned)d->jac_fac[q * d->maxjf + x] : (unsigned)(ni + 1);
+        jt[q] = make_uint2((unsigned)d->jac_k[q] | ((unsigned)(ci & 0xff) << 16), f[0] | (f[1] << 8) | (f[2] << 16));
+    }
+    NetDev &nd = n->d;
+    nd.ni = ni; nd.nr = nr; nd.nip = pad_block(ni);
+    nd.n_ent = d->n_ent; nd.n_term = d->n_term; nd.n_rhs = d->n_rhs; nd.max_rhs_len = max_len; nd.has_pow = has_pow;
+    int rcode = VK_OK;
+#define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
+    CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term);
+#undef CP
+    if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);
+    if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->jac_ptr, (size_t)d->n_ent + 1, &nd.jac_ptr);
+    if (rcode != VK_OK) { vk_network_destroy(n); return rcode; }
+    *out = n;
+    return VK_OK;
+}
+
+void vk_network_destroy(vk_network *n)
+{
+    if (!n) return;
+    for (void *p : n->allocs) cudaFree(p);
+    delete n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static void free_list(std::vector<void *> &v)
+{
+    for (void *p : v) cudaFree(p);
+    v.clear();
+}
+
+int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
+{
+    if (!net || !out || nz < 3 || ncol < 1) { set_error("bad argument"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(net->device));
+    vk_column *c = new vk_column();
+    memset(static_cast<void *>(c), 0, sizeof(vk_column));
+    new (&c->atm_allocs) std::vector<void *>();
+    new (&c->opt_allocs) std::vector<void *>();
+    c->net = net; c->nz = nz; c->ncol = ncol; c->ni = net->d.ni; c->nr = net->d.nr; c->nip = net->d.nip;
+    const size_t nv = (size_t)ncol * nz * c->ni, nb = (size_t)ncol * nz * c->nip * c->nip, np = (size_t)ncol * nz * c->nip;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev2);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev3);
+    double **vecs[] = {&c->y, &c->ymix, &c->sol, &c->ymix_out, &c->f, &c->k1, &c->k2, &c->yk2, &c->rhs, &c->res, &c->dx};
+    for (double **v : vecs)
+        if (e == cudaSuccess) e = cudaMalloc((void **)v, sizeof(double) * nv);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->z, sizeof(double) * np);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->up, sizeof(double) * np);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->dn, sizeof(double) * np);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->D, sizeof(double) * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->W, sizeof(double) * nb);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->dt, sizeof(double) * ncol);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->delta, sizeof(double) * ncol);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->status, sizeof(int) * ncol);
+    c->h_pin_bytes = sizeof(double) * (4 * nv + 4 * (size_t)ncol) + 64;
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
+    if (e != cudaSuccess) { cuda_fail(e, "vk_column_create allocation"); vk_column_destroy(c); return VK_ERR_CUDA; }
+    c->opts.mtol = 0; c->opts.atol = 0;
+    *out = c;
+    return VK_OK;
+}
+
+void vk_column_destroy(vk_column *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->net->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    photo_destroy(c);
+    ens_destroy(c);
+    double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->z, c->up, c->dn,
+                      c->D, c->W, c->dt, c->delta, c->k};
+    for (double *v : vecs) if (v) cudaFree(v);
+    if (c->status) cudaFree(c->status);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    free_list(c->atm_allocs);
+    free_list(c->opt_allocs);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    c->atm_allocs.~vector();
+    c->opt_allocs.~vector();
+    ::operator delete(c);
+}
+
+int vk_set_atm(vk_column *c, const vk_atm_view *v)
+{
+    if (!c || !v) { set_error("null argument"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    free_list(c->atm_allocs);
+    const int nz = c->nz, ni = c->ni;
+    const size_t rep = v->shared ? 1 : (size_t)c->ncol;
+    AtmDev &a = c->atm;
+    a.nz = nz; a.ni = ni;
+    a.use_moldiff = v->use_moldiff; a.use_settling = v->use_settling; a.use_topflux = v->use_topflux; a.use_botflux = v->use_botflux;
+    a.n_gas = (v->n_gas == ni) ? 0 : v->n_gas;
+    a.n_gas_lhs = (v->n_gas_lhs == ni) ? 0 : v->n_gas_lhs;
+    a.cs1 = v->shared ? 0 : (size_t)(nz - 1);
+    a.csn = v->shared ? 0 : (size_t)(nz - 1) * ni;
+    a.csz = v->shared ? 0 : (size_t)nz;
+    a.csi = v->shared ? 0 : (size_t)ni;
+    int rc = VK_OK;
+    a.gas_indx = nullptr; a.gas_indx_lhs = nullptr;
+    if (a.n_gas > 0) rc = dev_copy(c->atm_allocs, v->gas_indx, (size_t)a.n_gas, &a.gas_indx);
+    if (rc == VK_OK && a.n_gas_lhs > 0) rc = dev_copy(c->atm_allocs, v->gas_indx_lhs, (size_t)a.n_gas_lhs, &a.gas_indx_lhs);
+    std::vector<double> zeros((size_t)rep * (size_t)(nz) * ni, 0.0);
+#define CPA(field, n) if (rc == VK_OK) rc = dev_copy(c->atm_allocs, v->field ? v->field : zeros.data(), rep * (size_t)(n), &a.field)
+    CPA(Kzz, nz - 1); CPA(vz, nz - 1); CPA(dzi, nz - 1); CPA(Ti, nz - 1); CPA(Hpi, nz - 1);
+    CPA(Dzz, (size_t)(nz - 1) * ni); CPA(vs, (size_t)(nz - 1) * ni);
+    CPA(Tco, nz); CPA(g, nz); CPA(M, nz);
+    CPA(ms, ni); CPA(alpha, ni); CPA(top_flux, ni); CPA(bot_flux, ni); CPA(bot_vdep, ni);
+#undef CPA
+    if (rc != VK_OK) return rc;
+    c->atm_set = true;
+    return VK_OK;
+}
+
+int vk_set_k(vk_column *c, const double *k, int shared)
+{
+    if (!c || !k) { set_error("null argument"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    const size_t per = (size_t)c->nz * (c->nr + 1);
+    const size_t want_cs = shared ? 0 : per;
+    if (!c->k || c->k_cs != want_cs || !c->k_set) {
+        VK_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->k) cudaFree(c->k);
+        c->k = nullptr;
+        VK_CUDA(cudaMalloc((void **)&c->k, sizeof(double) * per * (shared ? 1 : c->ncol)));
+        c->k_cs = want_cs;
+    }
+    VK_CUDA(cudaMemcpyAsync(c->k, k, sizeof(double) * per * (shared ? 1 : c->ncol), cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    c->k_set = true;
+    return VK_OK;
+}
+
+__global__ void scatter_k_rows(double *k, size_t k_cs, int nz, int nr, int ncol_k, int n_rows, const int *rows, const double *vals)
+{
+    // vals [ncol_k][n_rows][nz]
+    size_t n = (size_t)ncol_k * n_rows * nz;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        int j = (int)(q % nz);
+        int r = (int)((q / nz) % n_rows);
+        size_t col = q / ((size_t)nz * n_rows);
+        k[col * k_cs + (size_t)j * (nr + 1) + rows[r]] = vals[q];
+    }
+}
+
+int vk_set_k_rows(vk_column *c, int n_rows, const int *rows, const double *vals)
+{
+    if (!c || !c->k_set || n_rows < 0 || (n_rows && (!rows || !vals))) { set_error("bad argument / k not set"); return VK_ERR_INVALID; }
+    if (n_rows == 0) return VK_OK;
+    VK_CUDA(cudaSetDevice(c->net->device));
+    for (int r = 0; r < n_rows; r++)
+        if (rows[r] < 1 || rows[r] > c->nr) { set_error("reaction id out of range"); return VK_ERR_INVALID; }
+    const int ncol_k = c->k_cs ? c->ncol : 1;
+    const size_t n = (size_t)ncol_k * n_rows * c->nz;
+    int *drows = nullptr; double *dvals = nullptr;
+    VK_CUDA(cudaMalloc((void **)&drows, sizeof(int) * n_rows));
+    cudaError_t e = cudaMalloc((void **)&dvals, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(drows, rows, sizeof(int) * n_rows, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dvals, vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        scatter_k_rows<<<(int)std::min<size_t>((n + 255) / 256, 1184), 256, 0, c->stream>>>(c->k, c->k_cs, c->nz, c->nr, ncol_k, n_rows, drows, dvals);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(drows); if (dvals) cudaFree(dvals);
+    if (e != cudaSuccess) return cuda_fail(e, "vk_set_k_rows");
+    return VK_OK;
+}
+
+int vk_set_step_opts(vk_column *c, const vk_step_opts *o)
+{
+    if (!c || !o) { set_error("null argument"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    free_list(c->opt_allocs);
+    StepOptsDev &d = c->opts;
+    memset(&d, 0, sizeof(d));
+    d.mtol = o->mtol; d.atol = o->atol; d.refine = o->refine; d.zero_delta_row0 = o->zero_delta_row0; d.n_fix_bot = o->n_fix_bot;
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    int rc = VK_OK;
+    if (o->n_fix_bot > 0) {
+        rc = dev_copy(c->opt_allocs, o->fix_bot_idx, (size_t)o->n_fix_bot, &d.fix_bot_idx);
+        if (rc == VK_OK) rc = dev_copy(c->opt_allocs, o->fix_bot_val, (size_t)c->ncol * o->n_fix_bot, &d.fix_bot_val);
+    }
+    if (rc == VK_OK && o->delta_zero_sp) rc = dev_copy(c->opt_allocs, o->delta_zero_sp, (size_t)c->ni, &d.delta_zero_sp);
+    if (rc == VK_OK && o->fix_mask) rc = dev_copy(c->opt_allocs, o->fix_mask, nv, &d.fix_mask);
+    if (rc == VK_OK && o->fix_y) rc = dev_copy(c->opt_allocs, o->fix_y, nv, &d.fix_y);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static int ready(vk_column *c)
+{
+    if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
+    if (!c->atm_set || !c->k_set) { set_error("vk_set_atm / vk_set_k must be called first"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    return VK_OK;
+}
+
+// device-side sequence of one attempted step; y, ymix, dt already resident
+int vk_step_device(vk_column *c)
+{
+    int rc;
+    VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
+    VK_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
+    if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
+    VK_CUDA(cudaEventRecord(c->ev1, c->stream));
+    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc;
+    VK_CUDA(cudaEventRecord(c->ev2, c->stream));
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
+    for (int it = 0; it < c->opts.refine; it++) {
+        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res))) return rc;
+        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
+        if ((rc = launch_axpy(c, c->k1, c->dx))) return rc;
+    }
+    if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z))) return rc;                 // k2                op.py:2929
+    for (int it = 0; it < c->opts.refine; it++) {
+        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->rhs, c->k2, c->res))) return rc;
+        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
+        if ((rc = launch_axpy(c, c->k2, c->dx))) return rc;
+    }
+    if ((rc = launch_epilogue(c))) return rc;                                                       // sol, delta, ymix  op.py:2932-2993
+    VK_CUDA(cudaEventRecord(c->ev3, c->stream));
+    return VK_OK;
+}
+
+int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const double *dt, double *sol, double *ymix_out,
+                  double *delta, int *status)
+{
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!y || !ymix || !dt || !sol || !ymix_out || !delta) { set_error("null buffer"); return VK_ERR_INVALID; }
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    // stage through pinned memory so the copies are truly asynchronous DMA
+    double *hy = c->h_pin, *hm = hy + nv, *hs = hm + nv, *ho = hs + nv, *hdt = ho + nv, *hdl = hdt + c->ncol;
+    int *hst = reinterpret_cast<int *>(hdl + c->ncol);
+    memcpy(hy, y, sizeof(double) * nv);
+    memcpy(hm, ymix, sizeof(double) * nv);
+    memcpy(hdt, dt, sizeof(double) * c->ncol);
+    VK_CUDA(cudaMemcpyAsync(c->y, hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->ymix, hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->dt, hdt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = vk_step_device(c))) return rc;
+    VK_CUDA(cudaMemcpyAsync(hs, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(ho, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(hdl, c->delta, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(hst, c->status, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(sol, hs, sizeof(double) * nv);
+    memcpy(ymix_out, ho, sizeof(double) * nv);
+    memcpy(delta, hdl, sizeof(double) * c->ncol);
+    if (status) memcpy(status, hst, sizeof(int) * c->ncol);
+    cudaEventElapsedTime(&c->last_ms_total, c->ev0, c->ev3);
+    cudaEventElapsedTime(&c->last_ms_factor, c->ev1, c->ev2);
+    return VK_OK;
+}
+
+int vk_clip_loss(vk_column *c, double *y, const double *ymix_in, double *ymix_out, int na, const double *compo,
+                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double *atom_sum, double *small_y,
+                 double *nega_y, int *any_negative)
+{
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!y || !ymix_in || !ymix_out || !compo || !atom_sum || !small_y || !nega_y || !any_negative || na < 1) { set_error("null buffer"); return VK_ERR_INVALID; }
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    std::vector<void *> tmp;
+    const double *dcompo = nullptr, *dsmall = nullptr, *dnega = nullptr;
+    const unsigned char *dskip = nullptr;
+    double *dasum = nullptr; int *dneg = nullptr;
+    rc = dev_copy(tmp, compo, (size_t)c->ni * na, &dcompo);
+    if (rc == VK_OK && atom_skip) rc = dev_copy(tmp, atom_skip, (size_t)na, &dskip);
+    if (rc == VK_OK) rc = dev_copy(tmp, small_y, (size_t)c->ncol, &dsmall);
+    if (rc == VK_OK) rc = dev_copy(tmp, nega_y, (size_t)c->ncol, &dnega);
+    cudaError_t e = cudaSuccess;
+    if (rc == VK_OK) {
+        e = cudaMalloc((void **)&dasum, sizeof(double) * c->ncol * na);
+        if (e == cudaSuccess) { tmp.push_back(dasum); e = cudaMemcpy(dasum, atom_sum, sizeof(double) * c->ncol * na, cudaMemcpyHostToDevice); }
+        if (e == cudaSuccess) e = cudaMalloc((void **)&dneg, sizeof(int) * c->ncol);
+        if (e == cudaSuccess) tmp.push_back(dneg);
+        // sol / ymix buffers double as staging for the clip
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->sol, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(c->ymix, ymix_in, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vk_clip_loss staging");
+    }
+    if (rc == VK_OK)
+        rc = launch_clip(c, c->sol, c->ymix, c->ymix_out, na, dcompo, dskip, pos_cut, nega_cut, dasum, const_cast<double *>(dsmall),
+                         const_cast<double *>(dnega), dneg);
+    if (rc == VK_OK) {
+        e = cudaMemcpyAsync(y, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ymix_out, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(atom_sum, dasum, sizeof(double) * c->ncol * na, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(small_y, dsmall, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nega_y, dnega, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(any_negative, dneg, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vk_clip_loss readback");
+    }
+    for (void *p : tmp) cudaFree(p);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+int vk_eval_rhs(vk_column *c, const double *y, double *out_chem, double *out_diff)
+{
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!y) { set_error("null buffer"); return VK_ERR_INVALID; }
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = launch_rhs(c, c->y, nullptr, out_chem ? c->k1 : nullptr, out_diff ? c->k2 : nullptr, nullptr, nullptr))) return rc;
+    if (out_chem) VK_CUDA(cudaMemcpyAsync(out_chem, c->k1, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    if (out_diff) VK_CUDA(cudaMemcpyAsync(out_diff, c->k2, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    return VK_OK;
+}
+
+int vk_eval_lhs(vk_column *c, const double *y, const double *dt, double *D, double *up, double *dn)
+{
+    int rc = ready(c);
+    if (rc) return rc;
+    if (!y || !dt || !D || !up || !dn) { set_error("null buffer"); return VK_ERR_INVALID; }
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->dt, dt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
+    // dense (unpadded) output layout: ld = ni; D / up / dn buffers are large enough (nip >= ni)
+    if ((rc = launch_lhs(c, c->y, c->dt, c->ni, c->D, c->up, c->dn))) return rc;
+    VK_CUDA(cudaMemcpyAsync(D, c->D, sizeof(double) * nv * c->ni, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(up, c->up, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(dn, c->dn, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    return VK_OK;
+}
+
+__global__ void pad_system(int nz, int ni, int nip, size_t nblk, const double *Dd, const double *upd, const double *dnd, double *D,
+                           double *up, double *dn)
+{
+    // dense [nblk][ni][ni] -> padded [nblk][nip][nip] with identity padding
+    const size_t blk = blockIdx.x;
+    if (blk >= nblk) return;
+    for (int q = threadIdx.x; q < nip * nip; q += blockDim.x) {
+        int r = q / nip, cc = q % nip;
+        double v = (r < ni && cc < ni) ? Dd[blk * ni * ni + (size_t)r * ni + cc] : ((r == cc) ? 1.0 : 0.0);
+        D[blk * nip * nip + q] = v;
+    }
+    for (int i = threadIdx.x; i < nip; i += blockDim.x) {
+        up[blk * nip + i] = (i < ni) ? upd[blk * ni + i] : 0.0;
+        dn[blk * nip + i] = (i < ni) ? dnd[blk * ni + i] : 0.0;
+    }
+}
+
+int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, double *x,
+                      int refine, int *status)
+{
+    if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
+    if (!D || !up || !dn || !rhs || !x) { set_error("null buffer"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    const size_t nblk = (size_t)c->ncol * c->nz, nv = nblk * c->ni;
+    double *Dd = nullptr, *upd = nullptr, *dnd = nullptr;
+    VK_CUDA(cudaMalloc((void **)&Dd, sizeof(double) * nv * c->ni));
+    cudaError_t e = cudaMalloc((void **)&upd, sizeof(double) * nv);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dnd, sizeof(double) * nv);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Dd, D, sizeof(double) * nv * c->ni, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(upd, up, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dnd, dn, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->f, rhs, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream);
+    int rc = VK_OK;
+    if (e == cudaSuccess) {
+        pad_system<<<(unsigned)nblk, 256, 0, c->stream>>>(c->nz, c->ni, c->nip, nblk, Dd, upd, dnd, c->D, c->up, c->dn);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) rc = cuda_fail(e, "vk_blocktri_solve staging");
+    if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+    if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
+    for (int it = 0; rc == VK_OK && it < refine; it++) {
+        rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res);
+        if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z);
+        if (rc == VK_OK) rc = launch_axpy(c, c->k1, c->dx);
+    }
+    if (rc == VK_OK) {
+        e = cudaMemcpyAsync(x, c->k1, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, c->status, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "vk_blocktri_solve readback");
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(Dd); if (upd) cudaFree(upd); if (dnd) cudaFree(dnd);
+    return rc;
+}
+
+int vk_last_kernel_ms(vk_column *c, float *ms_total, float *ms_factor)
+{
+    if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
+    if (ms_total) *ms_total = c->last_ms_total;
+    if (ms_factor) *ms_factor = c->last_ms_factor;
+    return VK_OK;
+}
+
+int vk_device_buffers(vk_column *c, void **y_dev, void **ymix_dev, void **sol_dev, void **k_dev)
+{
+    if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
+    if (y_dev) *y_dev = c->y;
+    if (ymix_dev) *ymix_dev = c->ymix;
+    if (sol_dev) *sol_dev = c->sol;
+    if (k_dev) *k_dev = c->k;
+    return VK_OK;
+}
+
+int vk_stream(vk_column *c, void **cuda_stream)
+{
+    if (!c || !cuda_stream) { set_error("null argument"); return VK_ERR_INVALID; }
+    *cuda_stream = (void *)c->stream;
+    return VK_OK;
+}
+
+}  // extern "C"

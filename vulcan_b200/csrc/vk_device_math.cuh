@@ -1,0 +1,46 @@
+// Device helpers shared by the -fmad=false translation units (vk_chem.cu, vk_step.cu).
+#pragma once
+
+namespace vk {
+
+// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src) for n <= 128 contiguous doubles;
+// np.sum(y, axis=1) at op.py:1505-1507, 2990-2993 reduces each row of ni species this way.
+static __device__ __forceinline__ double np_pairwise_le128(const double *a, int n)
+{
+    if (n < 8) {
+        double res = 0.;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    double r0 = a[0], r1 = a[1], r2 = a[2], r3 = a[3], r4 = a[4], r5 = a[5], r6 = a[6], r7 = a[7];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 += a[i]; r1 += a[i + 1]; r2 += a[i + 2]; r3 += a[i + 3];
+        r4 += a[i + 4]; r5 += a[i + 5]; r6 += a[i + 6]; r7 += a[i + 7];
+    }
+    double res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+// n <= 256 (one level of numpy's recursion); vk_network_create rejects ni > 253
+static __device__ __forceinline__ double np_pairwise(const double *a, int n)
+{
+    if (n <= 128) return np_pairwise_le128(a, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_le128(a, n2) + np_pairwise_le128(a + n2, n - n2);
+}
+// row sum over the gas species (compacted through `tmp` like the fancy-index copy y[:,gas_indx]) or over all species
+static __device__ __forceinline__ double row_sum(const double *yrow, int ni, int n_gas, const int *gas, double *tmp)
+{
+    if (n_gas > 0) {
+        for (int i = 0; i < n_gas; i++) tmp[i] = yrow[gas[i]];
+        return np_pairwise(tmp, n_gas);
+    }
+    return np_pairwise(yrow, ni);
+}
+
+static __device__ __forceinline__ double posv(double v) { return (v > 0) ? v : 0.0 * v; }  // (v>0)*v
+static __device__ __forceinline__ double negv(double v) { return (v < 0) ? v : 0.0 * v; }  // (v<0)*v
+
+}  // namespace vk

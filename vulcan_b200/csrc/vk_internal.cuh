@@ -1,0 +1,111 @@
+// vulcan_b200 internal device structures (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/vulcan_b200.h"
+
+#define VK_KB 1.38064852e-16   // phy_const.py:3
+#define VK_NAVO 6.02214086e23  // phy_const.py:4
+#define VK_HC 1.98644582e-9    // phy_const.py:8
+
+namespace vk {
+
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what);
+#define VK_CUDA(call)                                              \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return vk::cuda_fail(_e, #call);    \
+    } while (0)
+
+// ---- compiled network on the device ---------------------------------------------------------------------------
+// factor slots are bytes: species index (< 254), ni = third body M, ni+1 = constant 1.0
+struct NetDev {
+    int ni, nr, nip;            // nip = padded block size (multiple of 24)
+    int n_ent, n_term, n_rhs, max_rhs_len;
+    int has_pow;                // any exponent != 1 in the network (rare `n*X` syntax)
+    const uchar4 *rate_fac;     // [nr+1] four ordered factor slots
+    const uchar4 *rate_pow;     // [nr+1]
+    const int *rhs_ptr;         // [ni+1]
+    const int *rhs_term;        // [n_rhs]  (forward id << 8) | (coef & 0xff), coef signed 8 bit
+    const int *jac_ptr;         // [n_ent+1]
+    const ushort2 *jac_rc;      // [n_ent] (row, col)
+    const uint2 *jac_term;      // [n_term] .x = k index | (coef8 << 16), .y = 3 factor bytes
+};
+
+// ---- transport view on the device -------------------------------------------------------------------------------
+struct AtmDev {
+    int nz, ni;
+    int use_moldiff, use_settling, use_topflux, use_botflux;
+    int n_gas, n_gas_lhs;
+    const int *gas_indx, *gas_indx_lhs;
+    size_t cs1, csn, csz;       // column strides (elements) of [nz-1], [nz-1][ni] and [nz] arrays; cs_i for [ni]; 0 when shared
+    size_t csi;
+    const double *Kzz, *vz, *dzi, *Dzz, *vs, *Tco, *g, *M, *Ti, *Hpi, *ms, *alpha, *top_flux, *bot_flux, *bot_vdep;
+};
+
+struct StepOptsDev {
+    double mtol, atol;
+    int refine, zero_delta_row0, n_fix_bot;
+    const int *fix_bot_idx;
+    const double *fix_bot_val;        // [ncol][n_fix_bot]
+    const unsigned char *delta_zero_sp;
+    const unsigned char *fix_mask;    // [ncol][nz][ni]
+    const double *fix_y;
+};
+
+}  // namespace vk
+
+struct vk_network {
+    int device;
+    vk::NetDev d;
+    std::vector<void *> allocs;
+};
+
+struct PhotoState;
+struct EnsState;
+
+struct vk_column {
+    vk_network *net;
+    int nz, ncol, ni, nr, nip;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1, ev2, ev3;
+    float last_ms_total, last_ms_factor;
+    // state
+    double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
+    size_t k_cs;                              // column stride of k (0 = shared)
+    double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx;  // work vectors [ncol][nz][ni]
+    double *D, *W;                            // [ncol][nz][nip][nip]  lhs diagonal blocks / inverse Schur blocks
+    double *up, *dn;                          // [ncol][nz][nip]
+    double *dt, *delta;                       // [ncol]
+    int *status;                              // [ncol]
+    vk::AtmDev atm;
+    bool atm_set, k_set;
+    vk::StepOptsDev opts;
+    std::vector<void *> atm_allocs, opt_allocs;
+    // pinned host staging
+    double *h_pin;
+    size_t h_pin_bytes;
+    PhotoState *photo;
+    EnsState *ens;
+};
+
+namespace vk {
+// kernels (vk_chem.cu)
+int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_chem, double *out_diff,
+               const double *k1_for_rhs2, const double *dt_dev);
+int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dense_out_ni, double *D_out, double *up_out,
+               double *dn_out);
+// kernels (vk_solve.cu)
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status);
+int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z);
+int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
+                    double *res);
+// kernels (vk_step.cu)
+int launch_epilogue(vk_column *c);
+int launch_axpy(vk_column *c, double *x, const double *dx);
+}  // namespace vk

@@ -1,0 +1,330 @@
+// Photolysis update: ODESolver.compute_tau / compute_flux / compute_J (op.py:2580-2786).
+//
+// Wavelength-parallel: one thread per (column, wavelength bin) marches along z.
+//   pass 1 (top -> bottom): optical depth suffix sum (op.py:2588-2599), Beer direct beam, two-stream coefficients
+//                           (op.py:2612-2677) and the downward diffuse sweep (op.py:2691-2692) which uses the upward flux
+//                           LEFT BY THE PREVIOUS CALL (lagged fixed point, state lives on the device);
+//   pass 2 (bottom -> top): upward sweep (op.py:2693-2694), coefficients recomputed instead of stored;
+//   pass 3               : actinic flux and its relative change (op.py:2709-2737).
+// J rates: one warp per (column, branch, layer) contracts aflux[z,:] with the branch cross section (trapezoid on the two
+// uniform grids, op.py:2766-2786) and writes J*f_diurnal straight into the device copy of k.
+// Compiled with -fmad=false (same expression order as the reference; exp() is the only non-identical primitive).
+#include "vk_internal.cuh"
+
+struct PhotoState {
+    int nbin, i12, n_abs, n_photo, n_scat, n_br;
+    double dbin1, dbin2, sl_angle, edd, flux_atol, f_diurnal;
+    double *bins, *sflux_top, *cross_abs, *cross_abs_T, *cross_photo, *cross_scat, *cross_J, *cross_J_T;
+    int *abs_idx, *photo_idx, *scat_idx, *br_rate_index;
+    unsigned char *abs_is_T, *br_is_T;
+    // per column state
+    double *tau, *sflux, *dflux_u, *dflux_d;   // [ncol][nz+1][nbin]
+    double *aflux;                             // [ncol][nz][nbin]
+    double *dz, *J;                            // [ncol][nz], [ncol][n_br][nz]
+    unsigned long long *change_bits;           // [ncol]
+    std::vector<void *> allocs;
+};
+
+namespace vk {
+
+struct FluxArgs {
+    int nz, ni, nbin, ncol;
+    int n_abs, n_photo, n_scat;
+    const int *abs_idx, *photo_idx, *scat_idx;
+    const double *cross_abs, *cross_abs_T, *cross_photo, *cross_scat;
+    const unsigned char *abs_is_T;
+    const double *y, *ymix, *dz, *sflux_top, *bins;
+    double sl_angle, edd, flux_atol;
+    double *tau, *sflux, *dflux_u, *dflux_d, *aflux;
+    unsigned long long *change_bits;
+};
+
+struct Coef { double chi, xi, phi, i_u, i_d; };
+
+__device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double *ymj, int b, double tau_j, double tau_jp,
+                                                double dir_j, double dir_jp, double mu_ang)
+{
+    // single-scattering albedo (op.py:2621-2636)
+    double tot_abs = 0.0, tot_scat = 0.0;
+    for (int s = 0; s < a.n_photo; s++) tot_abs += ymj[a.photo_idx[s]] * a.cross_photo[(size_t)s * a.nbin + b];
+    for (int s = 0; s < a.n_scat; s++) tot_scat += ymj[a.scat_idx[s]] * a.cross_scat[(size_t)s * a.nbin + b];
+    double w0 = tot_scat / (tot_abs + tot_scat);
+    if (w0 != w0) w0 = 0.0;                                   // np.nan_to_num
+    else if (isinf(w0)) w0 = (w0 > 0) ? 1.7976931348623157e308 : -1.7976931348623157e308;
+    w0 = fmin(w0, 1. - 1.E-8);
+    const double edd = a.edd;
+    double dtau = tau_j - tau_jp;
+    double sq = sqrt(1. - w0);
+    double tran = exp(-1. / edd * sq * dtau);
+    double zp = 0.5 * (1. + sq), zm = 0.5 * (1. - sq);
+    double ll = -1. * w0 / (1. / (mu_ang * mu_ang) - 1. / (edd * edd) * (1. - w0));
+    double g_p = 0.5 * (ll * (1. / edd + 1. / mu_ang));
+    double g_m = 0.5 * (ll * (1. / edd - 1. / mu_ang));
+    double t2 = tran * tran;
+    Coef c;
+    c.chi = zm * zm * t2 - zp * zp;
+    c.xi = zp * zm * (1. - t2);
+    c.phi = (zm * zm - zp * zp) * tran;
+    c.i_u = c.phi * g_p * dir_j - (c.xi * g_m + c.chi * g_p) * dir_jp;
+    c.i_d = c.phi * g_m * dir_jp - (c.chi * g_m + c.xi * g_p) * dir_j;
+    return c;
+}
+
+__global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
+{
+    const int nz = a.nz, ni = a.ni, nbin = a.nbin;
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const bool live = gid < (size_t)a.ncol * nbin;
+    double change = 0.0;
+    bool has = false;
+    if (live) {
+        const int col = (int)(gid / nbin), b = (int)(gid % nbin);
+        const double *yc = a.y + (size_t)col * nz * ni, *ymc = a.ymix + (size_t)col * nz * ni, *dzc = a.dz + (size_t)col * nz;
+        double *tau = a.tau + (size_t)col * (nz + 1) * nbin + b;
+        double *sfl = a.sflux + (size_t)col * (nz + 1) * nbin + b;
+        double *du = a.dflux_u + (size_t)col * (nz + 1) * nbin + b;
+        double *dd = a.dflux_d + (size_t)col * (nz + 1) * nbin + b;
+        double *af = a.aflux + (size_t)col * nz * nbin + b;
+        const double cosz = cos(a.sl_angle), mu_ang = -1. * cos(a.sl_angle);
+        const double top = a.sflux_top[b];
+        // ---- pass 1: top -> bottom
+        double tau_above = 0.0;
+        tau[(size_t)nz * nbin] = 0.0;
+        double s_above = top * exp(-1. * tau_above / cosz);
+        sfl[(size_t)nz * nbin] = s_above;
+        double dd_above = dd[(size_t)nz * nbin];          // stays as left by the caller (zero): dflux_d[nz] is never written
+        for (int j = nz - 1; j >= 0; j--) {
+            const double *yj = yc + (size_t)j * ni;
+            double tj = 0.0;
+            for (int s = 0; s < a.n_abs; s++) {
+                double f = yj[a.abs_idx[s]] * dzc[j];
+                double cs = (a.abs_is_T && a.abs_is_T[s]) ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : a.cross_abs[(size_t)s * nbin + b];
+                tj += f * cs;
+            }
+            for (int s = 0; s < a.n_scat; s++) tj += yj[a.scat_idx[s]] * dzc[j] * a.cross_scat[(size_t)s * nbin + b];
+            tj += tau_above;
+            tau[(size_t)j * nbin] = tj;
+            double sj = top * exp(-1. * tj / cosz);
+            sfl[(size_t)j * nbin] = sj;
+            Coef c = two_stream_coef(a, ymc + (size_t)j * ni, b, tj, tau_above, sj * cosz, s_above * cosz, mu_ang);
+            double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du[(size_t)j * nbin] + c.i_d / mu_ang);   // op.py:2692
+            dd[(size_t)j * nbin] = ddj;
+            dd_above = ddj; tau_above = tj; s_above = sj;
+        }
+        // ---- pass 2: bottom -> top (dflux_u[0] keeps its value: zero upward flux at the bottom)
+        double du_below = du[0];
+        for (int j = 1; j <= nz; j++) {
+            const int m = j - 1;
+            double t_m = tau[(size_t)m * nbin], t_j = tau[(size_t)j * nbin];
+            double s_m = sfl[(size_t)m * nbin], s_j = sfl[(size_t)j * nbin];
+            Coef c = two_stream_coef(a, ymc + (size_t)m * ni, b, t_m, t_j, s_m * cosz, s_j * cosz, mu_ang);
+            double duj = 1. / c.chi * (c.phi * du_below - c.xi * dd[(size_t)j * nbin] + c.i_u / mu_ang);   // op.py:2694
+            du[(size_t)j * nbin] = duj;
+            du_below = duj;
+        }
+        // ---- pass 3: actinic flux (op.py:2709-2737)
+        const double hcl = VK_HC / a.bins[b];
+        for (int j = 0; j < nz; j++) {
+            double ave_dir = 0.5 * (sfl[(size_t)j * nbin] + sfl[(size_t)(j + 1) * nbin]);
+            double tot = ave_dir + 0.5 * (du[(size_t)j * nbin] + du[(size_t)(j + 1) * nbin] + dd[(size_t)(j + 1) * nbin] + dd[(size_t)j * nbin]) / a.edd;
+            double prev = af[(size_t)j * nbin];
+            double cur = tot / hcl;
+            af[(size_t)j * nbin] = cur;
+            if (cur > a.flux_atol) {
+                double ch = fabs(cur - prev) / cur;
+                if (ch == ch && (!has || ch > change)) { change = ch; has = true; }   // np.nanmax
+            }
+        }
+    }
+    unsigned long long bits = has ? (unsigned long long)__double_as_longlong(change) : 0ull;
+    // threads of one warp may straddle two columns only when nbin is not a multiple of 32: reduce per thread instead
+    if (live && bits) atomicMax(a.change_bits + (gid / nbin), bits);
+}
+
+struct JArgs {
+    int nz, nbin, i12, n_br, ncol, nr;
+    double dbin1, dbin2, f_diurnal;
+    const double *aflux, *cross_J, *cross_J_T;
+    const unsigned char *br_is_T;
+    const int *br_rate_index;
+    double *J;       // [ncol][n_br][nz]
+    double *k;       // device k
+    size_t k_cs;
+};
+
+__global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t nw = (size_t)a.ncol * a.n_br * a.nz;
+    if (w >= nw) return;
+    const int j = (int)(w % a.nz), br = (int)((w / a.nz) % a.n_br), col = (int)(w / ((size_t)a.nz * a.n_br));
+    const double *f = a.aflux + ((size_t)col * a.nz + j) * a.nbin;
+    const double *c = (a.br_is_T && a.br_is_T[br]) ? a.cross_J_T + ((size_t)br * a.nz + j) * a.nbin : a.cross_J + (size_t)br * a.nbin;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = lane; b < a.i12; b += 32) s1 += f[b] * c[b] * a.dbin1;
+    for (int b = a.i12 + lane; b < a.nbin; b += 32) s2 += f[b] * c[b] * a.dbin2;
+    for (int off = 16; off > 0; off >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+    }
+    if (lane == 0) {
+        double v = s1;
+        v -= 0.5 * (f[0] * c[0] + f[a.i12 - 1] * c[a.i12 - 1]) * a.dbin1;
+        v += s2;
+        v -= 0.5 * (f[a.i12] * c[a.i12] + f[a.nbin - 1] * c[a.nbin - 1]) * a.dbin2;
+        a.J[((size_t)col * a.n_br + br) * a.nz + j] = v;
+        const int rid = a.br_rate_index[br];
+        if (rid > 0) a.k[(size_t)col * a.k_cs + (size_t)j * (a.nr + 1) + rid] = v * a.f_diurnal;   // op.py:2785-2786
+    }
+}
+
+void photo_destroy(vk_column *c)
+{
+    if (!c->photo) return;
+    for (void *p : c->photo->allocs) cudaFree(p);
+    delete c->photo;
+    c->photo = nullptr;
+}
+
+template <typename T>
+static int pcopy(PhotoState *p, const T *host, size_t n, T **out)
+{
+    void *d = nullptr;
+    VK_CUDA(cudaMalloc(&d, sizeof(T) * (n ? n : 1)));
+    p->allocs.push_back(d);
+    if (host && n) VK_CUDA(cudaMemcpy(d, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+    else VK_CUDA(cudaMemset(d, 0, sizeof(T) * (n ? n : 1)));
+    *out = reinterpret_cast<T *>(d);
+    return VK_OK;
+}
+
+}  // namespace vk
+
+using namespace vk;
+
+extern "C" {
+
+int vk_photo_setup(vk_column *c, const vk_photo_view *v)
+{
+    if (!c || !v || v->nbin < 4 || v->i12 < 2 || v->i12 > v->nbin - 2) { set_error("bad photo view"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    photo_destroy(c);
+    PhotoState *p = new PhotoState();
+    c->photo = p;
+    p->nbin = v->nbin; p->i12 = v->i12; p->dbin1 = v->dbin1; p->dbin2 = v->dbin2; p->sl_angle = v->sl_angle; p->edd = v->edd;
+    p->flux_atol = v->flux_atol; p->f_diurnal = v->f_diurnal;
+    p->n_abs = v->n_abs; p->n_photo = v->n_photo; p->n_scat = v->n_scat; p->n_br = v->n_br;
+    const size_t nb = v->nbin, nz = c->nz, ncol = c->ncol;
+    int rc = VK_OK;
+#define PC(field, n) if (rc == VK_OK) rc = pcopy(p, v->field, (size_t)(n), &p->field)
+    PC(bins, nb); PC(sflux_top, nb);
+    PC(abs_idx, v->n_abs); PC(cross_abs, v->n_abs * nb);
+    PC(photo_idx, v->n_photo); PC(cross_photo, v->n_photo * nb);
+    PC(scat_idx, v->n_scat); PC(cross_scat, v->n_scat * nb);
+    PC(cross_J, v->n_br * nb); PC(br_rate_index, v->n_br);
+#undef PC
+    p->abs_is_T = nullptr; p->cross_abs_T = nullptr; p->br_is_T = nullptr; p->cross_J_T = nullptr;
+    if (rc == VK_OK && v->abs_is_T && v->cross_abs_T) {
+        rc = pcopy(p, v->abs_is_T, (size_t)v->n_abs, &p->abs_is_T);
+        if (rc == VK_OK) rc = pcopy(p, v->cross_abs_T, (size_t)v->n_abs * nz * nb, &p->cross_abs_T);
+    }
+    if (rc == VK_OK && v->br_is_T && v->cross_J_T) {
+        rc = pcopy(p, v->br_is_T, (size_t)v->n_br, &p->br_is_T);
+        if (rc == VK_OK) rc = pcopy(p, v->cross_J_T, (size_t)v->n_br * nz * nb, &p->cross_J_T);
+    }
+    const double *nul = nullptr;
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * (nz + 1) * nb, &p->tau);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * (nz + 1) * nb, &p->sflux);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * (nz + 1) * nb, &p->dflux_u);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * (nz + 1) * nb, &p->dflux_d);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * nz * nb, &p->aflux);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * nz, &p->dz);
+    if (rc == VK_OK) rc = pcopy(p, nul, ncol * (size_t)v->n_br * nz, &p->J);
+    const unsigned long long *nulu = nullptr;
+    if (rc == VK_OK) rc = pcopy(p, nulu, ncol, &p->change_bits);
+    if (rc != VK_OK) photo_destroy(c);
+    return rc;
+}
+
+int vk_photo_reset(vk_column *c)
+{
+    if (!c || !c->photo) { set_error("photo not set up"); return VK_ERR_INVALID; }
+    PhotoState *p = c->photo;
+    VK_CUDA(cudaSetDevice(c->net->device));
+    const size_t n1 = (size_t)c->ncol * (c->nz + 1) * p->nbin;
+    VK_CUDA(cudaMemsetAsync(p->dflux_u, 0, sizeof(double) * n1, c->stream));
+    VK_CUDA(cudaMemsetAsync(p->dflux_d, 0, sizeof(double) * n1, c->stream));
+    VK_CUDA(cudaMemsetAsync(p->aflux, 0, sizeof(double) * (size_t)c->ncol * c->nz * p->nbin, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    return VK_OK;
+}
+
+// device-resident update (y, ymix already in c->y / c->ymix, dz in photo->dz)
+int vk_photo_update_device(vk_column *c, const double *y_dev, const double *ymix_dev)
+{
+    PhotoState *p = c->photo;
+    FluxArgs a;
+    a.nz = c->nz; a.ni = c->ni; a.nbin = p->nbin; a.ncol = c->ncol;
+    a.n_abs = p->n_abs; a.n_photo = p->n_photo; a.n_scat = p->n_scat;
+    a.abs_idx = p->abs_idx; a.photo_idx = p->photo_idx; a.scat_idx = p->scat_idx;
+    a.cross_abs = p->cross_abs; a.cross_abs_T = p->cross_abs_T; a.cross_photo = p->cross_photo; a.cross_scat = p->cross_scat;
+    a.abs_is_T = p->abs_is_T;
+    a.y = y_dev; a.ymix = ymix_dev; a.dz = p->dz; a.sflux_top = p->sflux_top; a.bins = p->bins;
+    a.sl_angle = p->sl_angle; a.edd = p->edd; a.flux_atol = p->flux_atol;
+    a.tau = p->tau; a.sflux = p->sflux; a.dflux_u = p->dflux_u; a.dflux_d = p->dflux_d; a.aflux = p->aflux;
+    a.change_bits = p->change_bits;
+    VK_CUDA(cudaMemsetAsync(p->change_bits, 0, sizeof(unsigned long long) * c->ncol, c->stream));
+    const size_t nthr = (size_t)c->ncol * p->nbin;
+    flux_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, c->stream>>>(a);
+    VK_CUDA(cudaGetLastError());
+    JArgs ja;
+    ja.nz = c->nz; ja.nbin = p->nbin; ja.i12 = p->i12; ja.n_br = p->n_br; ja.ncol = c->ncol; ja.nr = c->nr;
+    ja.dbin1 = p->dbin1; ja.dbin2 = p->dbin2; ja.f_diurnal = p->f_diurnal;
+    ja.aflux = p->aflux; ja.cross_J = p->cross_J; ja.cross_J_T = p->cross_J_T; ja.br_is_T = p->br_is_T;
+    ja.br_rate_index = p->br_rate_index; ja.J = p->J; ja.k = c->k; ja.k_cs = c->k_cs;
+    const size_t nwarp = (size_t)c->ncol * p->n_br * c->nz;
+    jrate_kernel<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, c->stream>>>(ja);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+
+int vk_photo_update(vk_column *c, const double *y, const double *ymix, const double *dz, double *J, double *aflux_change)
+{
+    if (!c || !c->photo || !y || !ymix || !dz) { set_error("photo not set up / null buffer"); return VK_ERR_INVALID; }
+    if (!c->k_set) { set_error("vk_set_k must be called first"); return VK_ERR_INVALID; }
+    if (c->k_cs == 0 && c->ncol > 1) { set_error("photolysis writes J into k: k must be per column"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    PhotoState *p = c->photo;
+    const size_t nv = (size_t)c->ncol * c->nz * c->ni;
+    VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->ymix, ymix, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(p->dz, dz, sizeof(double) * c->ncol * c->nz, cudaMemcpyHostToDevice, c->stream));
+    int rc = vk_photo_update_device(c, c->y, c->ymix);
+    if (rc) return rc;
+    if (J) VK_CUDA(cudaMemcpyAsync(J, p->J, sizeof(double) * (size_t)c->ncol * p->n_br * c->nz, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<unsigned long long> bits(c->ncol);
+    VK_CUDA(cudaMemcpyAsync(bits.data(), p->change_bits, sizeof(unsigned long long) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    if (aflux_change)
+        for (int i = 0; i < c->ncol; i++) memcpy(&aflux_change[i], &bits[i], sizeof(double));
+    return VK_OK;
+}
+
+int vk_photo_read(vk_column *c, double *tau, double *sflux, double *dflux_u, double *dflux_d, double *aflux)
+{
+    if (!c || !c->photo) { set_error("photo not set up"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    PhotoState *p = c->photo;
+    const size_t n1 = sizeof(double) * (size_t)c->ncol * (c->nz + 1) * p->nbin, n0 = sizeof(double) * (size_t)c->ncol * c->nz * p->nbin;
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    if (tau) VK_CUDA(cudaMemcpy(tau, p->tau, n1, cudaMemcpyDeviceToHost));
+    if (sflux) VK_CUDA(cudaMemcpy(sflux, p->sflux, n1, cudaMemcpyDeviceToHost));
+    if (dflux_u) VK_CUDA(cudaMemcpy(dflux_u, p->dflux_u, n1, cudaMemcpyDeviceToHost));
+    if (dflux_d) VK_CUDA(cudaMemcpy(dflux_d, p->dflux_d, n1, cudaMemcpyDeviceToHost));
+    if (aflux) VK_CUDA(cudaMemcpy(aflux, p->aflux, n0, cudaMemcpyDeviceToHost));
+    return VK_OK;
+}
+
+}  // extern "C"

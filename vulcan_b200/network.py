@@ -20,8 +20,8 @@ The Jacobian tables are derived analytically here (product rule on the monomials
 symbolic differentiation of generated source (make_chem_funs.py:653-717).
 
 Outputs are plain numpy arrays (see `Network.tables()`), consumed by
-  - vulcan_b200/codegen.py  (emits the per-network CUDA translation unit)
-  - oracle/vk_oracle.c      (CPU restatement used only by tests / bench cpu_baseline)
+  - vulcan_b200/_abi.py     (uploaded to the GPU through vk_network_create)
+  - the CPU checker under tests/ (test infrastructure only, never imported from here)
 """
 import json
 import re
