@@ -163,3 +163,38 @@ def test_photolysis(step):
         assert abs(ch[0] - float(px["aflux_change%d" % it])) < 1e-9
         ref = px["J%d" % it]
         assert np.max(np.abs(J[0] - ref) / np.maximum(np.abs(ref), 1e-300 + 1e-12 * np.abs(ref).max(axis=1, keepdims=True))) < 1e-9
+
+
+def test_device_resident_loop_vs_reference_trajectory():
+    """vk_ens_run (solver -> clip -> accept/reject -> rescale -> step_size entirely on the device) started from the
+    reference state at step 10 must reproduce the reference's own (dt, delta) trajectory of steps 10..99 (same photolysis
+    rates, same atmosphere between the updates at count 0 and 100)."""
+    if not have("HD189", "full.npz"):
+        pytest.skip("fixture missing")
+    c = Case("HD189", 10)
+    cfg = c.cfg
+    full = np.load("%s/HD189_full.npz" % GOLD)
+    tr = full["traj"]
+    col = _columns(c, 1, refine=1)
+    col.ens_setup(cfg["rtol"], cfg["loss_eps"], cfg["dt_min"], cfg["dt_max"], cfg["dt_var_min"], cfg["dt_var_max"],
+                  cfg["pos_cut"], cfg["nega_cut"], c.st["compo"], c.st["atom_ini"], c.st["n_0"])
+    col.ens_set_state(c.y, c.dt)
+    worst_dt = 0.0
+    prev_acc, n_rej_seen = 0, 0
+    while prev_acc < 89:
+        col.ens_run(1)
+        s = col.ens_get_state(want_y=False)
+        acc = int(s["n_accept"][0])
+        if acc == prev_acc:            # the attempt was rejected (the reference rejects the same attempts: its dt_try/dt_used differ)
+            n_rej_seen += 1
+            assert n_rej_seen < 20
+            continue
+        prev_acc = acc
+        row = 10 + acc                 # reference row of the NEXT accepted step: t_before, dt_try
+        worst_dt = max(worst_dt, abs(s["dt"][0] - tr[row, 2]) / tr[row, 2])
+        assert abs(s["t"][0] - (tr[row, 1] - tr[10, 1])) <= 1e-9 * tr[row, 1]
+    ref_rej = int(np.sum(tr[10:99, 2] != tr[10:99, 3]))
+    print("device-resident loop vs reference over steps 10..99: max rel dt deviation %.2e, rejected attempts %d (reference %d)"
+          % (worst_dt, n_rej_seen, ref_rej))
+    assert n_rej_seen == ref_rej
+    assert worst_dt < 1e-6

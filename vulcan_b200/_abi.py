@@ -358,3 +358,28 @@ class Columns(object):
         a, b = C.c_float(0), C.c_float(0)
         check(self.lib.vk_last_kernel_ms(self.handle, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    # ---------------------------------------------------------------- device-resident ensemble driver
+    def ens_setup(self, rtol, loss_eps, dt_min, dt_max, dt_var_min, dt_var_max, pos_cut, nega_cut, compo, atom_ini, n_0):
+        compo = f64(compo)
+        na = compo.shape[1]
+        atom_ini = f64(np.broadcast_to(f64(atom_ini), (self.ncol, na)))
+        n_0 = f64(np.broadcast_to(f64(n_0), (self.ncol, self.nz)))
+        o = EnsOpts(float(rtol), float(loss_eps), float(dt_min), float(dt_max), float(dt_var_min), float(dt_var_max),
+                    float(pos_cut), float(nega_cut), na, dptr(compo), dptr(atom_ini), dptr(n_0))
+        check(self.lib.vk_ens_setup(self.handle, C.byref(o)))
+
+    def ens_set_state(self, y, dt):
+        y = self._shape(y, (self.nz, self.ni))
+        dt = f64(np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,)))
+        check(self.lib.vk_ens_set_state(self.handle, dptr(y), dptr(dt)))
+
+    def ens_run(self, n_steps):
+        check(self.lib.vk_ens_run(self.handle, int(n_steps)))
+
+    def ens_get_state(self, want_y=True):
+        y = np.empty((self.ncol, self.nz, self.ni)) if want_y else None
+        t, dt = np.empty(self.ncol), np.empty(self.ncol)
+        na, nrj = np.zeros(self.ncol, dtype=np.int32), np.zeros(self.ncol, dtype=np.int32)
+        check(self.lib.vk_ens_get_state(self.handle, dptr(y), dptr(t), dptr(dt), iptr(na), iptr(nrj)))
+        return dict(y=y, t=t, dt=dt, n_accept=na, n_reject=nrj)

@@ -37,6 +37,36 @@ static int pad_block(int ni)
     return 24 * ((ni + 23) / 24);
 }
 
+// device-side sequence of one attempted step; y, ymix, dt already resident
+int vk_step_device_impl(vk_column *c)
+{
+    int rc;
+    VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
+    VK_CUDA(cudaEventRecord(c->ev0, c->stream));
+    if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
+    if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
+    VK_CUDA(cudaEventRecord(c->ev1, c->stream));
+    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f, c->z))) return rc;      // W_j and z = forward-eliminated f
+    VK_CUDA(cudaEventRecord(c->ev2, c->stream));
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 1))) return rc;                // k1 (backward sweep)  op.py:2914
+    for (int it = 0; it < c->opts.refine; it++) {
+        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res))) return rc;
+        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
+        if ((rc = launch_axpy(c, c->k1, c->dx))) return rc;
+    }
+    if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z))) return rc;                 // k2                op.py:2929
+    for (int it = 0; it < c->opts.refine; it++) {
+        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->rhs, c->k2, c->res))) return rc;
+        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
+        if ((rc = launch_axpy(c, c->k2, c->dx))) return rc;
+    }
+    if ((rc = launch_epilogue(c))) return rc;                                                       // sol, delta, ymix  op.py:2932-2993
+    VK_CUDA(cudaEventRecord(c->ev3, c->stream));
+    return VK_OK;
+}
+
+
 }  // namespace vk
 
 using namespace vk;
@@ -303,35 +333,6 @@ static int ready(vk_column *c)
     return VK_OK;
 }
 
-// device-side sequence of one attempted step; y, ymix, dt already resident
-int vk_step_device(vk_column *c)
-{
-    int rc;
-    VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
-    VK_CUDA(cudaEventRecord(c->ev0, c->stream));
-    if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
-    if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
-    VK_CUDA(cudaEventRecord(c->ev1, c->stream));
-    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc;
-    VK_CUDA(cudaEventRecord(c->ev2, c->stream));
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
-    for (int it = 0; it < c->opts.refine; it++) {
-        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res))) return rc;
-        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
-        if ((rc = launch_axpy(c, c->k1, c->dx))) return rc;
-    }
-    if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z))) return rc;                 // k2                op.py:2929
-    for (int it = 0; it < c->opts.refine; it++) {
-        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->rhs, c->k2, c->res))) return rc;
-        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
-        if ((rc = launch_axpy(c, c->k2, c->dx))) return rc;
-    }
-    if ((rc = launch_epilogue(c))) return rc;                                                       // sol, delta, ymix  op.py:2932-2993
-    VK_CUDA(cudaEventRecord(c->ev3, c->stream));
-    return VK_OK;
-}
-
 int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const double *dt, double *sol, double *ymix_out,
                   double *delta, int *status)
 {
@@ -348,7 +349,7 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
     VK_CUDA(cudaMemcpyAsync(c->y, hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->ymix, hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, hdt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = vk_step_device(c))) return rc;
+    if ((rc = vk_step_device_impl(c))) return rc;
     VK_CUDA(cudaMemcpyAsync(hs, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(ho, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(hdl, c->delta, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
@@ -478,7 +479,7 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) rc = cuda_fail(e, "vk_blocktri_solve staging");
-    if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+    if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr);
     if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
     for (int it = 0; rc == VK_OK && it < refine; it++) {
         rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res);

@@ -101,8 +101,10 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
 int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dense_out_ni, double *D_out, double *up_out,
                double *dn_out);
 // kernels (vk_solve.cu)
-int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status);
-int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z);
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status, const double *rhs,
+                  double *z);
+int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z,
+                 int skip_fwd = 0);
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
                     double *res);
 // kernels (vk_step.cu)

@@ -15,13 +15,43 @@ namespace vk {
 
 __device__ __forceinline__ unsigned long long abs_bits(double v) { return (unsigned long long)__double_as_longlong(fabs(v)); }
 
-template <int TR, int WR>
+// Register layout: warp w owns the 8 columns [8w, 8w+8) of the block and ALL its rows, in the m8n8 accumulator-fragment
+// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1.
+// One pivot step k:
+//   owner warp (k/8): pivot search on its own column with ONE warp REDUX over packed keys {|a| high word, row} (the
+//   maximum is taken on the top 13 mantissa bits: threshold partial pivoting with threshold 1 - 2^-13), reciprocal of
+//   each lane's local best computed while the REDUX is in flight, multipliers l_r = a_rk / pivot published to shared memory;
+//   __syncthreads (the only block barrier of the step);
+//   every warp: rank-1 update of its own 8 columns; the pivot-row values it needs are its own (warp shuffle).
+// dst = A[idx][e] with a block-uniform runtime idx: a uniform switch keeps A in registers (no local-memory indexing)
+#define VK_SELECT_ROW(idx, e, dst)                                                     \
+    switch (idx) {                                                                     \
+        case 0: dst = A[0][e]; break;                                                  \
+        case 1: if (NR > 1) dst = A[1 < NR ? 1 : 0][e]; break;                         \
+        case 2: if (NR > 2) dst = A[2 < NR ? 2 : 0][e]; break;                         \
+        case 3: if (NR > 3) dst = A[3 < NR ? 3 : 0][e]; break;                         \
+        case 4: if (NR > 4) dst = A[4 < NR ? 4 : 0][e]; break;                         \
+        case 5: if (NR > 5) dst = A[5 < NR ? 5 : 0][e]; break;                         \
+        case 6: if (NR > 6) dst = A[6 < NR ? 6 : 0][e]; break;                         \
+        case 7: if (NR > 7) dst = A[7 < NR ? 7 : 0][e]; break;                         \
+        case 8: if (NR > 8) dst = A[8 < NR ? 8 : 0][e]; break;                         \
+        case 9: if (NR > 9) dst = A[9 < NR ? 9 : 0][e]; break;                         \
+        case 10: if (NR > 10) dst = A[10 < NR ? 10 : 0][e]; break;                     \
+        case 11: if (NR > 11) dst = A[11 < NR ? 11 : 0][e]; break;                     \
+        case 12: if (NR > 12) dst = A[12 < NR ? 12 : 0][e]; break;                     \
+        case 13: if (NR > 13) dst = A[13 < NR ? 13 : 0][e]; break;                     \
+        case 14: if (NR > 14) dst = A[14 < NR ? 14 : 0][e]; break;                     \
+        default: break;                                                                \
+    }
+
+template <int NIP>
 struct FactorCfg {
-    static constexpr int NIP = 8 * TR * WR;
-    static constexpr int NW = WR * WR;
+    static constexpr int NW = NIP / 8;
+    static constexpr int NR = NIP / 8;
     static constexpr int NT = NW * 32;
     static constexpr int LD = NIP + 2;
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * LD + 3 * NIP) + sizeof(int) * 2 * NIP;
+    // Wsm + lbuf[2] + tvec + zprev (doubles), pinv[2] (double), piv_p, piv_q, pidx[2] (ints)
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * LD + 5 * NIP) + sizeof(int) * (2 * NIP + 4);
 };
 
 struct FactorArgs {
@@ -31,173 +61,170 @@ struct FactorArgs {
     const double *dn;
     double *W;           // [ncol][nz][NIP][NIP]
     int *status;         // [ncol]
+    const double *rhs;   // optional [ncol][nz][ni]: forward elimination fused into the factorisation
+    double *z;           // [ncol][nz][NIP]
 };
 
-template <int TR, int WR>
-__global__ void __launch_bounds__(FactorCfg<TR, WR>::NT, 1) factor_kernel(FactorArgs a)
+template <int NIP, int MINB>
+__global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
 {
-    using C = FactorCfg<TR, WR>;
-    constexpr int NIP = C::NIP, LD = C::LD, NT = C::NT;
-    extern __shared__ double smem[];
-    double *Wsm = smem;                 // NIP x LD   natural-layout inverse of the previous layer
-    double *colk = Wsm + NIP * LD;      // 2 x NIP    pivot column (double buffered)
-    double *rowk = colk + 2 * NIP;      // NIP        pivot row
-    int *piv_p = (int *)(rowk + NIP);   // p[k]: physical row chosen at step k
-    int *piv_q = piv_p + NIP;           // q[r]: step at which physical row r was the pivot
+    using C = FactorCfg<NIP>;
+    constexpr int NR = C::NR, LD = C::LD, NT = C::NT;
+    extern __shared__ __align__(16) double smem[];
+    double *Wsm = smem;                  // NIP x LD   natural-layout inverse of the current / previous layer
+    double *lbuf = Wsm + NIP * LD;       // 2 x NIP    multipliers of step k (double buffered)
+    double *tvec = lbuf + 2 * NIP;       // NIP
+    double *zprev = tvec + NIP;          // NIP
+    double *rscale = zprev + NIP;        // NIP  1/pivot of each physical row (deferred row scaling)
+    int *piv_p = (int *)(rscale + NIP);  // p[k]: physical row chosen at step k
+    int *piv_q = piv_p + NIP;            // q[r]: step at which physical row r was the pivot
+    int *pidx = piv_q + NIP;             // 2
 
     const int col = blockIdx.x;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int wr = warp / WR, wc = warp % WR;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ni = a.ni, nz = a.nz;
-    // my rows: R(aa) = 8*(wr*TR+aa)+g ; my columns: Cc(bb,e) = 8*(wc*TR+bb)+2t+e
-    const int row0 = 8 * wr * TR + g, col0 = 8 * wc * TR + 2 * t;
+    const int c0 = 8 * w + 2 * t;        // my columns c0, c0+1 ; my rows 8*i + g
 
-    double A[TR][TR][2];
+    double A[NR][2];
     const double *Dc = a.D + (size_t)col * nz * NIP * NIP;
     const double *upc = a.up + (size_t)col * nz * NIP;
     const double *dnc = a.dn + (size_t)col * nz * NIP;
     double *Wc = a.W + (size_t)col * nz * NIP * NIP;
+    const bool fuse = a.rhs != nullptr;
+    const double *rc = fuse ? a.rhs + (size_t)col * nz * ni : nullptr;
+    double *zc = fuse ? a.z + (size_t)col * nz * NIP : nullptr;
+    if (tid < NIP) zprev[tid] = 0.0;
 
     for (int j = 0; j < nz; j++) {
-        // ---- S_j into registers
+        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}) into registers
         const double *Dj = Dc + (size_t)j * NIP * NIP;
+        {
+            double u0 = 0.0, u1 = 0.0;
+            if (j > 0) { u0 = upc[(size_t)(j - 1) * NIP + c0]; u1 = upc[(size_t)(j - 1) * NIP + c0 + 1]; }
 #pragma unroll
-        for (int aa = 0; aa < TR; aa++)
-#pragma unroll
-            for (int bb = 0; bb < TR; bb++) {
-                const int r = row0 + 8 * aa, c = col0 + 8 * bb;
-                double2 d = *reinterpret_cast<const double2 *>(Dj + (size_t)r * NIP + c);
+            for (int i = 0; i < NR; i++) {
+                const int r = 8 * i + g;
+                double2 d = *reinterpret_cast<const double2 *>(Dj + (size_t)r * NIP + c0);
                 if (j > 0) {
                     const double l = dnc[(size_t)j * NIP + r];
-                    const double u0 = upc[(size_t)(j - 1) * NIP + c], u1 = upc[(size_t)(j - 1) * NIP + c + 1];
-                    d.x = d.x - (l * Wsm[r * LD + c]) * u0;
-                    d.y = d.y - (l * Wsm[r * LD + c + 1]) * u1;
+                    const double2 wv = *reinterpret_cast<const double2 *>(Wsm + r * LD + c0);
+                    d.x = d.x - (l * wv.x) * u0;
+                    d.y = d.y - (l * wv.y) * u1;
                 }
-                A[aa][bb][0] = d.x;
-                A[aa][bb][1] = d.y;
+                A[i][0] = d.x;
+                A[i][1] = d.y;
             }
-        __syncthreads();   // everyone is done reading Wsm of layer j-1
-        // ---- Gauss-Jordan with implicit row pivoting
-        bool used[(NIP + 31) / 32];
-#pragma unroll
-        for (int m = 0; m < (NIP + 31) / 32; m++) used[m] = false;
-        if (tid < NIP) { piv_p[tid] = tid; piv_q[tid] = tid; }
-        // publish column 0
-        if (wc == 0 && t == 0) {
-#pragma unroll
-            for (int aa = 0; aa < TR; aa++) colk[row0 + 8 * aa] = A[aa][0][0];
         }
+        if (tid < NIP) { piv_p[tid] = tid; piv_q[tid] = tid; rscale[tid] = 1.0; }
+        __syncthreads();   // everyone is done reading Wsm of layer j-1
+        unsigned avail = (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u);   // bit i: my row 8i+g has not been a pivot yet
         bool singular = false;
         for (int k = 0; k < ni; k++) {
-            const int cb = (k & 1) * NIP;
-            __syncthreads();   // S1: column k published, update k-1 finished everywhere
-            // pivot search (every warp redundantly): max |colk[r]| over unused rows, smallest row on ties
-            unsigned long long best = 0ull;
-            int brow = 0x7fffffff;
+            const int cb = k & 1;
+            const int kc = k & 7;
+            if (w == (k >> 3)) {
+                // ---- owner warp: pivot search on column k (held by the 8 lanes with t == kc/2)
+                const bool holder = (t == (kc >> 1));
+                unsigned key[NR];
 #pragma unroll
-            for (int m = 0; m < (NIP + 31) / 32; m++) {
-                const int r = lane + 32 * m;
-                if (r < NIP && !used[m]) {
-                    unsigned long long v = abs_bits(colk[cb + r]);
-                    if (v > best) { best = v; brow = r; }
+                for (int i = 0; i < NR; i++) {
+                    const int hi = (kc & 1) ? __double2hiint(A[i][1]) : __double2hiint(A[i][0]);
+                    key[i] = (((unsigned)hi & 0x7fffff80u) | (unsigned)(127 - (8 * i + g))) & (0u - ((avail >> i) & 1u));
                 }
-            }
-            unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
-            unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
-            unsigned mlo = __reduce_max_sync(0xffffffffu, (hi == mhi) ? lo : 0u);
-            unsigned prow = __reduce_min_sync(0xffffffffu, (hi == mhi && lo == mlo) ? (unsigned)brow : 0x7fffffffu);
-            if ((mhi | mlo) == 0u) { singular = true; break; }
-            const int p = (int)prow;
 #pragma unroll
-            for (int m = 0; m < (NIP + 31) / 32; m++)
-                if (p == lane + 32 * m) used[m] = true;
-            const double piv = colk[cb + p];
-            const double inv = 1.0 / piv;
-            if (tid == 0) { piv_p[k] = p; piv_q[p] = k; }
-            // owners of row p publish it (with 1.0 in column k); owners of column k clear it
-            const int kb = k >> 3;                  // tile column of k
-            const bool own_colk = (kb / TR == wc) && (((k & 7) >> 1) == t);
-            const int kbb = kb % TR, ke = k & 1;
-            const int pa = (p >> 3);                // tile row of p
-            const bool own_rowp = (pa / TR == wr) && ((p & 7) == g);
-            const int paa = pa % TR;
-            if (own_colk) {
+                for (int st = 1; st < NR; st <<= 1)
 #pragma unroll
-                for (int aa = 0; aa < TR; aa++)
+                    for (int i = 0; i + st < NR; i += 2 * st) key[i] = max(key[i], key[i + st]);
+                const unsigned mk = __reduce_max_sync(0xffffffffu, holder ? key[0] : 0u);
+                const int p = 127 - (int)(mk & 0x7fu);
+                const int pi = p >> 3;
+                double pv0 = 1.0, pv1 = 1.0;
+                VK_SELECT_ROW(pi, 0, pv0);
+                VK_SELECT_ROW(pi, 1, pv1);
+                double pv = (kc & 1) ? pv1 : pv0;
+                pv = __shfl_sync(0xffffffffu, pv, ((p & 7) << 2) | (kc >> 1));
+                const double inv = 1.0 / pv;
+                if (holder) {
 #pragma unroll
-                    for (int bb = 0; bb < TR; bb++)
-#pragma unroll
-                        for (int e = 0; e < 2; e++)
-                            if (bb == kbb && e == ke) A[aa][bb][e] = (own_rowp && aa == paa) ? 1.0 : 0.0;
-            }
-            if (own_rowp) {
-#pragma unroll
-                for (int aa = 0; aa < TR; aa++)
-                    if (aa == paa) {
-#pragma unroll
-                        for (int bb = 0; bb < TR; bb++) {
-                            rowk[col0 + 8 * bb] = A[aa][bb][0];
-                            rowk[col0 + 8 * bb + 1] = A[aa][bb][1];
-                        }
+                    for (int i = 0; i < NR; i++) {
+                        const int r = 8 * i + g;
+                        const double v = (kc & 1) ? A[i][1] : A[i][0];
+                        const double l = (r == p) ? 0.0 : v * inv;
+                        lbuf[cb * NIP + r] = l;
+                        // column k of the transformed block; the pivot row is kept UNSCALED (its factor 1/pivot is applied
+                        // once, when the block is written out), so its own entry in column k is pivot * (1/pivot) = 1
+                        const double nv = (r == p) ? 1.0 : -l;
+                        if (kc & 1) A[i][1] = nv; else A[i][0] = nv;
                     }
-            }
-            __syncthreads();   // S2: pivot row published
-            double rs[TR][2], mm[TR];
-#pragma unroll
-            for (int bb = 0; bb < TR; bb++) {
-                rs[bb][0] = rowk[col0 + 8 * bb] * inv;
-                rs[bb][1] = rowk[col0 + 8 * bb + 1] * inv;
-            }
-#pragma unroll
-            for (int aa = 0; aa < TR; aa++) mm[aa] = colk[cb + row0 + 8 * aa];
-#pragma unroll
-            for (int aa = 0; aa < TR; aa++) {
-                const bool isp = own_rowp && (aa == paa);
-#pragma unroll
-                for (int bb = 0; bb < TR; bb++) {
-                    A[aa][bb][0] = isp ? rs[bb][0] : fma(-mm[aa], rs[bb][0], A[aa][bb][0]);
-                    A[aa][bb][1] = isp ? rs[bb][1] : fma(-mm[aa], rs[bb][1], A[aa][bb][1]);
+                }
+                if (lane == 0) {
+                    const bool ok = (mk >> 7) != 0u;
+                    pidx[cb] = ok ? p : -1;
+                    if (ok) { piv_p[k] = p; piv_q[p] = k; rscale[p] = inv; }
                 }
             }
-            // publish column k+1 into the other buffer
-            if (k + 1 < ni) {
-                const int k1 = k + 1, k1b = k1 >> 3;
-                if ((k1b / TR == wc) && (((k1 & 7) >> 1) == t)) {
-                    const int nb = ((k1 & 1) * NIP);
-                    const int bb1 = k1b % TR, e1 = k1 & 1;
+            __syncthreads();
+            const int p = pidx[cb];
+            if (p < 0) { singular = true; break; }
+            const int pi = p >> 3, pg = p & 7;
+            if (pg == g) avail &= ~(1u << pi);
+            // pivot-row values of my two columns (held by lane 4*pg + t of this warp)
+            double pr0 = 0.0, pr1 = 0.0;
+            VK_SELECT_ROW(pi, 0, pr0);
+            VK_SELECT_ROW(pi, 1, pr1);
+            pr0 = __shfl_sync(0xffffffffu, pr0, (pg << 2) | t);
+            pr1 = __shfl_sync(0xffffffffu, pr1, (pg << 2) | t);
+            if (w == (k >> 3) && t == (kc >> 1)) {   // column k itself is already final: eliminate with 0
+                if (kc & 1) pr1 = 0.0; else pr0 = 0.0;
+            }
 #pragma unroll
-                    for (int aa = 0; aa < TR; aa++)
-#pragma unroll
-                        for (int bb = 0; bb < TR; bb++)
-#pragma unroll
-                            for (int e = 0; e < 2; e++)
-                                if (bb == bb1 && e == e1) colk[nb + row0 + 8 * aa] = A[aa][bb][e];
-                }
+            for (int i = 0; i < NR; i++) {
+                const double l = lbuf[cb * NIP + 8 * i + g];    // 0 for the pivot row
+                A[i][0] = fma(-l, pr0, A[i][0]);
+                A[i][1] = fma(-l, pr1, A[i][1]);
             }
         }
         if (singular) {
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
-            return;   // uniform: every warp saw the same zero column
+            return;   // uniform: every thread read the same flag
         }
-        __syncthreads();   // permutation tables complete
-        // ---- un-permute into shared memory:  W[q(r)][p(c)] = A[r][c]
+        // ---- un-permute into shared memory, applying the deferred pivot-row scaling:  W[q(r)][p(c)] = A[r][c] / pivot(r)
+        {
+            const int pc0 = piv_p[c0], pc1 = piv_p[c0 + 1];
 #pragma unroll
-        for (int aa = 0; aa < TR; aa++) {
-            const int qr = piv_q[row0 + 8 * aa];
-#pragma unroll
-            for (int bb = 0; bb < TR; bb++) {
-                Wsm[qr * LD + piv_p[col0 + 8 * bb]] = A[aa][bb][0];
-                Wsm[qr * LD + piv_p[col0 + 8 * bb + 1]] = A[aa][bb][1];
+            for (int i = 0; i < NR; i++) {
+                const int qr = piv_q[8 * i + g];
+                const double sc = rscale[8 * i + g];
+                Wsm[qr * LD + pc0] = A[i][0] * sc;
+                Wsm[qr * LD + pc1] = A[i][1] * sc;
             }
+        }
+        if (fuse && tid < NIP) {
+            const double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
+            tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zprev[tid];
         }
         __syncthreads();
         double *Wj = Wc + (size_t)j * NIP * NIP;
         for (int q = tid; q < NIP * NIP / 2; q += NT) {
             const int r = (2 * q) / NIP, c = (2 * q) % NIP;
-            double2 v = make_double2(Wsm[r * LD + c], Wsm[r * LD + c + 1]);
-            *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c) = v;
+            *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c) = *reinterpret_cast<const double2 *>(Wsm + r * LD + c);
         }
-        // the next iteration reads Wsm for its Schur update and syncs before overwriting it
+        if (fuse) {   // z_j = W_j (r_j - dn_j * z_{j-1}) : 4 threads per row
+            const int row = tid >> 2, part = tid & 3;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NIP / 8; i++) {
+                const double2 wv = *reinterpret_cast<const double2 *>(Wsm + row * LD + i * 8 + part * 2);
+                const double2 tv = *reinterpret_cast<const double2 *>(tvec + i * 8 + part * 2);
+                acc0 = fma(wv.x, tv.x, acc0);
+                acc1 = fma(wv.y, tv.y, acc1);
+            }
+            double acc = acc0 + acc1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (part == 0) { zprev[row] = acc; zc[(size_t)j * NIP + row] = acc; }
+        }
+        // the next iteration reads Wsm / zprev after its own __syncthreads-protected section
     }
 }
 
@@ -209,6 +236,7 @@ struct SolveArgs {
     const double *rhs;           // [ncol][nz][ni]
     double *x;                   // [ncol][nz][ni]
     double *z;                   // [ncol][nz][nip] scratch
+    int skip_fwd;                // z already holds the forward-eliminated vector (fused into the factorisation)
 };
 
 template <int NIP>
@@ -247,9 +275,9 @@ __global__ void __launch_bounds__(NIP * 4, 1) solve_kernel(SolveArgs a)
         return acc;
     };
     // ---- forward: z_j = W_j (r_j - dn_j * z_{j-1})
-    if (tid < NIP) zprev[tid] = 0.0;
-    load_w(0);
-    for (int j = 0; j < nz; j++) {
+    if (tid < NIP) zprev[tid] = a.skip_fwd ? zc[(size_t)(nz - 1) * NIP + tid] : 0.0;
+    if (!a.skip_fwd) load_w(0);
+    for (int j = 0; j < nz && !a.skip_fwd; j++) {
         __syncthreads();
         if (tid < NIP) {
             double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
@@ -314,35 +342,37 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <int TR, int WR>
-static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status)
+template <int NIP, int MINB>
+static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status,
+                           const double *rhs, double *z)
 {
-    using C = FactorCfg<TR, WR>;
+    using C = FactorCfg<NIP>;
     static bool configured = false;
     if (!configured) {
-        VK_CUDA(cudaFuncSetAttribute(factor_kernel<TR, WR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
         configured = true;
     }
-    FactorArgs a{c->nz, c->ni, D, up, dn, W, status};
-    factor_kernel<TR, WR><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
+    FactorArgs a{c->nz, c->ni, D, up, dn, W, status, rhs, z};
+    factor_kernel<NIP, MINB><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
 
-int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status)
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status, const double *rhs,
+                  double *z)
 {
     switch (c->nip) {
-        case 48: return launch_factor_t<2, 3>(c, D, up, dn, W, status);
-        case 72: return launch_factor_t<3, 3>(c, D, up, dn, W, status);
-        case 96: return launch_factor_t<4, 3>(c, D, up, dn, W, status);
-        case 120: return launch_factor_t<5, 3>(c, D, up, dn, W, status);
+        case 48: return launch_factor_t<48, 2>(c, D, up, dn, W, status, rhs, z);
+        case 72: return launch_factor_t<72, 2>(c, D, up, dn, W, status, rhs, z);
+        case 96: return launch_factor_t<96, 1>(c, D, up, dn, W, status, rhs, z);
+        case 120: return launch_factor_t<120, 1>(c, D, up, dn, W, status, rhs, z);
         default: set_error("no factor kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
     }
 }
 
-int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z)
+int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z, int skip_fwd)
 {
-    SolveArgs a{c->nz, c->ni, c->nip, W, up, dn, rhs, x, z};
+    SolveArgs a{c->nz, c->ni, c->nip, W, up, dn, rhs, x, z, skip_fwd};
     switch (c->nip) {
         case 48: solve_kernel<48><<<c->ncol, 48 * 4, 0, c->stream>>>(a); break;
         case 72: solve_kernel<72><<<c->ncol, 72 * 4, 0, c->stream>>>(a); break;
