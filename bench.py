@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the B200-native Ros2 hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference [--gpus N] ...                CPU arm: the oracle port of the reference path on host cores
+
+Workload (config.workload): BASELINE config "ensemble sweep: 4096 HD189-like columns over a Kzz x metallicity x C/O grid"
+(NCHO_photo_network: ni=69, nr=878, nz=150), STRONG scaling: the 4096 columns are partitioned across the N ranks, no
+collective inside the step, one final gather.  A "step" is one ATTEMPTED Ros2 step of every column through the whole
+hot path (rhs -> lhs -> block-tridiagonal factor -> 2 solves (+refinement) -> epilogue -> clip -> accept/reject ->
+rescale -> step size), inputs resident in HBM.  The per-step working set (D and W blocks: 2 x 6.2 MB per column) is far
+larger than the 126 MB L2, so no explicit L2 flush is needed between timed steps.
+`value`  = column-steps/s of the device-resident loop (vk_ens_run), CUDA-event timed, max over ranks.
+`e2e`    = the same metric through the reference-facing call vk_ros2_solve with PINNED HOST buffers: H2D of y, ymix, dt and
+           D2H of sol, ymix, delta inside the timed region every step.
+Synthetic data: the reference's own HD189 state at step 100 (tests/golden fixture, produced by running the unmodified
+reference) re-weighted per column (vulcan_b200/ensemble.py).  /root/reference is never read at run time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "tests"))
+
+N_COLUMNS = 4096
+BASE_STEP = 100          # fixture state the synthetic columns are derived from (dt = 4.84 s)
+FLOP_FACTOR = lambda nz, ni: nz * (2.0 * ni ** 3 + ni ** 2)                 # getrf+getri count + scaled Schur update
+FLOP_SOLVES = lambda nz, ni, nrhs: nrhs * nz * (2.0 * ni ** 2 + 2.0 * ni)   # forward/backward sweeps
+
+
+def load_case():
+    from helpers import Case
+    return Case("HD189", BASE_STEP)
+
+
+def build_columns(case, lo, hi):
+    from vulcan_b200 import ensemble
+    kz, met, co = ensemble.sweep_grid()
+    kz, met, co = kz[lo:hi], met[lo:hi], co[lo:hi]
+    st, cfg = case.st, case.cfg
+    y, atom_ini = ensemble.synthetic_columns(case.y, st["n_0"], st["compo"], cfg["atom_list"], kz, met, co)
+    kw = case.atm_kwargs()
+    kzz = kz[:, None] * np.asarray(kw["Kzz"])[None, :]
+    return y, atom_ini, kzz, kw
+
+
+class ClockSampler(object):
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_fp64_peak(device):
+    """MEASURED_PEAKS.json has no FP64 entry: time cuBLAS DGEMM 6144^3 in this run, best of 5."""
+    import torch
+    n = 6144
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def cpu_port_rate(case, n_sample, threads):
+    """column-steps/s of the CPU oracle port (oracle/vk_oracle.c, one attempted step + clip per column) on `threads`
+    host threads; the ctypes calls release the GIL."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import Oracle
+    y, atom_ini, kzz, kw = build_columns(case, 0, n_sample)
+    cfg = case.cfg
+    o = Oracle(case.net)
+    atms = []
+    for i in range(n_sample):
+        k2 = dict(kw); k2["Kzz"] = kzz[i]
+        atms.append(o.make_atm(**k2))
+    ymix = y / y.sum(axis=2, keepdims=True)
+
+    def one(i):
+        res = o.ros2_solver(atms[i], y[i], ymix[i], case.k, case.dt, cfg["mtol"], cfg["atol"], refine=1)
+        o.clip_loss(res["sol"], res["ymix"], case.st["compo"], cfg["pos_cut"], cfg["nega_cut"], cfg["mtol"])
+        return res["delta"]
+    one(0)
+    t0 = time.time()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, range(n_sample)))
+    return n_sample / (time.time() - t0)
+
+
+def host_threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    case = load_case()
+    threads = host_threads()
+    n_sample = max(2 * threads, 16)
+    rates = []
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_port_rate(case, min(n_sample, threads), threads)
+    t0 = time.time()
+    for _ in range(args.steps):
+        rates.append(cpu_port_rate(case, n_sample, threads))
+        if time.time() - t0 > 150:
+            break
+    v = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "ensemble column-steps/s", "value": v, "unit": "column-steps/s", "n_gpus": args.gpus,
+        "steps": len(rates), "warmup": args.warmup, "ms_per_step": 1e3 * N_COLUMNS / v, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ensemble sweep: 4096 HD189-like columns (NCHO_photo_network ni=69 nr=878 nz=150), Kzz x metallicity x C/O",
+                   "sample_columns_per_step": n_sample},
+        "cpu_baseline": {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port",
+                         "sample": "%d column-steps per bench step on %d host threads with the C oracle port (oracle/vk_oracle.c: same "
+                                   "algorithm as the GPU path incl. 1 refinement pass); the UNMODIFIED numpy/scipy reference measured in the "
+                                   "build container is 0.42-0.50 s per solver call on 1 core (BASELINE.md), i.e. ~4x slower than this port" % (n_sample, threads)},
+        "e2e": {"value": v, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--columns", type=int, default=N_COLUMNS)
+    ap.add_argument("--refine", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vulcan_b200 import _abi, ensemble
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
+    args.warmup = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    case = load_case()
+    cfg, st = case.cfg, case.st
+    ncols_total = args.columns
+    lo, hi = ensemble.partition(ncols_total, world, rank)
+    y, atom_ini, kzz, kw = build_columns(case, lo, hi)
+    atm_common = dict(kw)
+    runner = ensemble.EnsembleRunner(case.net, case.nz, y, np.full(hi - lo, case.dt), atm_common, kzz, case.k, cfg, st["compo"],
+                                     atom_ini, st["n_0"], device=local_rank, refine=args.refine)
+    ncol = hi - lo
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident loop ------------------------------------------------------------------------------------
+    runner.run(args.warmup)
+    runner.col.ens_set_state(y, np.full(ncol, case.dt))     # every timed run starts from the same state
+    runner.run(1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.time()
+    ms = runner.run(args.steps)                              # CUDA events on the handle's stream bracket exactly K steps
+    barrier()
+    wall = time.time() - t_wall0
+    clocks = sampler.stop()
+    tms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    value = ncols_total * args.steps / (ms_max * 1e-3)
+    s = runner.state(want_y=False)
+
+    # ---- per-kernel time of the dominant kernel (factor) for the roofline: CUDA events inside the step ---------------
+    fac_ms, tot_ms = [], []
+    for _ in range(3):
+        runner.run(1)
+        a, b = runner.col.last_kernel_ms()
+        tot_ms.append(a)
+    # ev1..ev2 of the last step bracket the factor kernel
+    import ctypes
+    fa, fb = ctypes.c_float(0), ctypes.c_float(0)
+    runner.col.lib.vk_last_kernel_ms(runner.col.handle, ctypes.byref(fa), ctypes.byref(fb))
+
+    # ---- e2e through the reference-facing call with pinned host buffers ----------------------------------------------
+    nv = ncol * case.nz * case.net.ni
+    pin = [torch.empty(nv, dtype=torch.float64).pin_memory() for _ in range(4)]
+    hy, hm, hs, ho = [p.numpy() for p in pin]
+    hy[:] = y.ravel()
+    hm[:] = (y / y.sum(axis=2, keepdims=True)).ravel()
+    hdt = np.full(ncol, case.dt); hdelta = np.empty(ncol); hstat = np.zeros(ncol, dtype=np.int32)
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        runner.col.ros2_solve_into(hy, hm, hdt, hs, ho, hdelta, hstat)
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        runner.col.ros2_solve_into(hy, hm, hdt, hs, ho, hdelta, hstat)
+    barrier()
+    t_e2e = torch.tensor([time.time() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = ncols_total * e2e_steps / float(t_e2e.item())
+
+    # ---- the one collective: final gather of the mixing ratios ----------------------------------------------------------
+    fin = runner.state(want_y=True)
+    ymix_local = fin["y"] / fin["y"].sum(axis=2, keepdims=True)
+    gathered = ensemble.gather_final(ymix_local, world, rank, device)
+
+    if rank == 0:
+        ni, nz = case.net.ni, case.nz
+        refine = args.refine
+        launches_per_step = 2 + 1 + 1 + (2 + 2 * refine) + 2 * refine + 2 * refine + 1 + 1 + 1 + 1
+        line = {
+            "metric": "ensemble column-steps/s", "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ensemble sweep: %d HD189-like columns (NCHO_photo_network ni=69 nr=878 nz=150), Kzz x metallicity x C/O, "
+                                   "partitioned across %d GPU(s); attempted steps, refine=%d" % (ncols_total, world, refine),
+                       "columns_per_gpu": ncol, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
+                       "accepted_fraction": float(np.sum(s["n_accept"])) / float(np.sum(s["n_accept"]) + np.sum(s["n_reject"]))},
+            "e2e": {"value": e2e_value, "unit": "column-steps/s", "h2d_bytes_per_step": int(2 * nv * 8 * world + 8 * ncols_total),
+                    "d2h_bytes_per_step": int(2 * nv * 8 * world + 12 * ncols_total)},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "wall_s_timed_region": wall,
+            "final_gather_rows": None if gathered is None else int(gathered.shape[0]),
+        }
+        # roofline of the dominant kernel (block-tridiagonal factorisation: FP64 pipe bound)
+        peak = measured_fp64_peak(device)
+        fms = float(fb.value)
+        flops = ncol * FLOP_FACTOR(nz, ni)
+        traffic = None
+        prof = os.path.join(REPO, "profiles", "r01_factor_traffic.json")
+        if os.path.exists(prof):
+            try:
+                traffic = json.load(open(prof)).get("dram_bytes_per_column", None)
+                traffic = None if traffic is None else traffic * ncol
+            except Exception:
+                traffic = None
+        line["roofline"] = {"bound": "tensor", "kernel": "factor_kernel (per-layer Gauss-Jordan inverse + Schur update)",
+                            "achieved": flops / (fms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                            "frac": flops / (fms * 1e-3) / 1e12 / peak, "traffic": traffic,
+                            "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
+                            "flops_per_column_step": FLOP_FACTOR(nz, ni), "kernel_ms": fms,
+                            "share_of_step": fms / float(np.mean(tot_ms))}
+        # single-column numbers (BASELINE metric part 1)
+        one = ensemble.EnsembleRunner(case.net, case.nz, case.y[None], np.array([case.dt]), atm_common, np.asarray(kw["Kzz"])[None],
+                                      case.k, cfg, st["compo"], st["atom_ini"][None], st["n_0"], device=local_rank, refine=refine)
+        one.run(5)
+        ms1 = one.run(30)
+        col1 = one.col
+        y1 = case.y[None].copy(); m1 = case.ymix[None].copy()
+        for _ in range(3):
+            col1.ros2_solve(y1, m1, case.dt)
+        t0 = time.time()
+        for _ in range(20):
+            col1.ros2_solve(y1, m1, case.dt)
+        e2e1 = 20 / (time.time() - t0)
+        line["single_column"] = {"steps_per_s": 30 / (ms1 * 1e-3), "ms_per_step": ms1 / 30, "e2e_steps_per_s": e2e1,
+                                 "note": "attempted Ros2 steps of ONE HD189 column (latency-bound: one SM runs the block-Thomas recurrence)"}
+        if not args.no_cpu_baseline:
+            threads = host_threads()
+            n_sample = max(2 * threads, 16)
+            v = cpu_port_rate(case, n_sample, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port",
+                                    "sample": "%d column-steps of the same workload on %d host threads, C oracle port (oracle/vk_oracle.c); the "
+                                              "unmodified numpy/scipy reference is ~4x slower per step (0.42-0.50 s, BASELINE.md)" % (n_sample, threads)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

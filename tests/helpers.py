@@ -29,8 +29,8 @@ class Case(object):
 
     def __init__(self, tag, step):
         self.tag, self.step = tag, step
-        self.st = np.load(os.path.join(GOLD, "%s_static.npz" % tag), allow_pickle=False)
-        self.fx = np.load(os.path.join(GOLD, "%s_step%04d.npz" % (tag, step)), allow_pickle=False)
+        self.st = dict(np.load(os.path.join(GOLD, "%s_static.npz" % tag), allow_pickle=False))   # eager: NpzFile is not thread-safe
+        self.fx = dict(np.load(os.path.join(GOLD, "%s_step%04d.npz" % (tag, step)), allow_pickle=False))
         self.cfg = json.loads(str(self.st["cfg_json"]))
         self.net = load_network(tag)
         st, fx = self.st, self.fx

@@ -273,6 +273,13 @@ class Columns(object):
         check(self.lib.vk_ros2_solve(self.handle, dptr(y), dptr(ymix), dptr(dt), dptr(sol), dptr(ymo), dptr(delta), iptr(status)))
         return sol, ymo, delta, status
 
+    def ros2_solve_into(self, y, ymix, dt, sol, ymix_out, delta, status):
+        """same call on caller-owned C-contiguous float64 arrays (e.g. numpy views of pinned torch tensors): no allocation,
+        and page-locked buffers are DMA'd directly."""
+        for a in (y, ymix, sol, ymix_out):
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == self.ncol * self.nz * self.ni
+        check(self.lib.vk_ros2_solve(self.handle, dptr(y), dptr(ymix), dptr(dt), dptr(sol), dptr(ymix_out), dptr(delta), iptr(status)))
+
     def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None):
         y = self._shape(y, (self.nz, self.ni)).copy()
         ymix_in = self._shape(ymix_in, (self.nz, self.ni))

@@ -340,23 +340,34 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
     if (rc) return rc;
     if (!y || !ymix || !dt || !sol || !ymix_out || !delta) { set_error("null buffer"); return VK_ERR_INVALID; }
     const size_t nv = (size_t)c->ncol * c->nz * c->ni;
-    // stage through pinned memory so the copies are truly asynchronous DMA
+    // caller buffers that are already page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used directly;
+    // pageable buffers are staged through the handle's pinned area so that the copies are real asynchronous DMA
+    auto pinned = [](const void *p) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+        return at.type == cudaMemoryTypeHost;
+    };
+    const bool direct = pinned(y) && pinned(ymix) && pinned(sol) && pinned(ymix_out);
     double *hy = c->h_pin, *hm = hy + nv, *hs = hm + nv, *ho = hs + nv, *hdt = ho + nv, *hdl = hdt + c->ncol;
     int *hst = reinterpret_cast<int *>(hdl + c->ncol);
-    memcpy(hy, y, sizeof(double) * nv);
-    memcpy(hm, ymix, sizeof(double) * nv);
+    if (!direct) {
+        memcpy(hy, y, sizeof(double) * nv);
+        memcpy(hm, ymix, sizeof(double) * nv);
+    }
     memcpy(hdt, dt, sizeof(double) * c->ncol);
-    VK_CUDA(cudaMemcpyAsync(c->y, hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
-    VK_CUDA(cudaMemcpyAsync(c->ymix, hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->y, direct ? y : hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->ymix, direct ? ymix : hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, hdt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
     if ((rc = vk_step_device_impl(c))) return rc;
-    VK_CUDA(cudaMemcpyAsync(hs, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
-    VK_CUDA(cudaMemcpyAsync(ho, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(direct ? sol : hs, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(direct ? ymix_out : ho, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(hdl, c->delta, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(hst, c->status, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(sol, hs, sizeof(double) * nv);
-    memcpy(ymix_out, ho, sizeof(double) * nv);
+    if (!direct) {
+        memcpy(sol, hs, sizeof(double) * nv);
+        memcpy(ymix_out, ho, sizeof(double) * nv);
+    }
     memcpy(delta, hdl, sizeof(double) * c->ncol);
     if (status) memcpy(status, hst, sizeof(int) * c->ncol);
     cudaEventElapsedTime(&c->last_ms_total, c->ev0, c->ev3);
