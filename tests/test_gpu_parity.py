@@ -54,7 +54,10 @@ def test_lhs_blocks(case):
     Do, upo, dno = case.oracle.lhs(case.atm, case.y, case.k, case.dt)
     assert np.array_equal(up[0], case.fx["lhs_up"]) and np.array_equal(dn[0], case.fx["lhs_dn"])
     assert np.array_equal(up[0], upo) and np.array_equal(dn[0], dno)
-    assert np.array_equal(D[0], Do)
+    # entries longer than 16 terms are summed in 16-term segments on the GPU (balanced warps): rounding-level vs the oracle
+    scale = np.abs(Do).max(axis=2, keepdims=True)
+    assert np.max(np.abs(D[0] - Do) / scale) < 4e-15
+    assert np.array_equal(D[0] != 0, Do != 0)
     for i, j in enumerate(case.fx["layers"]):
         ref = case.fx["lhs_blocks"][i]
         assert np.max(np.abs(D[0, j] - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 4e-15

@@ -129,12 +129,39 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
         for (int x = 0; x < 3; x++) f[x] = (x < d->maxjf) ? (unsigned)d->jac_fac[q * d->maxjf + x] : (unsigned)(ni + 1);
         jt[q] = make_uint2((unsigned)d->jac_k[q] | ((unsigned)(ci & 0xff) << 16), f[0] | (f[1] << 8) | (f[2] << 16));
     }
+    // work schedule of the Jacobian kernel: segments of <= 16 terms sorted by decreasing length
+    struct Seg { unsigned rc; int q0; int len; int ent; };
+    std::vector<Seg> segs;
+    std::vector<uint2> multi;
+    std::vector<int> ent_slot0(d->n_ent, -1);
+    int n_part = 0;
+    const int SEGLEN = 16;
+    for (int e = 0; e < d->n_ent; e++) {
+        const int q0 = d->jac_ptr[e], q1 = d->jac_ptr[e + 1];
+        const unsigned rcw = (unsigned)d->jac_row[e] | ((unsigned)d->jac_col[e] << 16);
+        const int nseg = std::max(1, (q1 - q0 + SEGLEN - 1) / SEGLEN);
+        if (nseg > 1) {
+            ent_slot0[e] = n_part;
+            multi.push_back(make_uint2(rcw, (unsigned)n_part | ((unsigned)nseg << 16)));
+            n_part += nseg;
+        }
+        for (int sI = 0; sI < nseg; sI++) {
+            const int a0 = q0 + sI * SEGLEN, a1 = std::min(q1, a0 + SEGLEN);
+            segs.push_back(Seg{rcw, a0, a1 - a0, (nseg > 1) ? (ent_slot0[e] + sI) : 0xffff});
+        }
+    }
+    if (n_part >= 0xffff) { delete n; set_error("too many split Jacobian entries"); return VK_ERR_UNSUPPORTED; }
+    std::stable_sort(segs.begin(), segs.end(), [](const Seg &a, const Seg &b) { return a.len > b.len; });
+    std::vector<uint4> segw(segs.size());
+    for (size_t q = 0; q < segs.size(); q++)
+        segw[q] = make_uint4(segs[q].rc, (unsigned)segs[q].q0, (unsigned)segs[q].len | ((unsigned)segs[q].ent << 16), 0u);
     NetDev &nd = n->d;
     nd.ni = ni; nd.nr = nr; nd.nip = pad_block(ni);
+    nd.n_seg = (int)segw.size(); nd.n_multi = (int)multi.size(); nd.n_part = n_part;
     nd.n_ent = d->n_ent; nd.n_term = d->n_term; nd.n_rhs = d->n_rhs; nd.max_rhs_len = max_len; nd.has_pow = has_pow;
     int rcode = VK_OK;
 #define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
-    CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term);
+    CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term); CP(segw, jac_seg); CP(multi, jac_multi);
 #undef CP
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->jac_ptr, (size_t)d->n_ent + 1, &nd.jac_ptr);
@@ -244,6 +271,20 @@ int vk_set_atm(vk_column *c, const vk_atm_view *v)
     CPA(ms, ni); CPA(alpha, ni); CPA(top_flux, ni); CPA(bot_flux, ni); CPA(bot_vdep, ni);
 #undef CPA
     if (rc != VK_OK) return rc;
+    // atmosphere-only stencil pieces (evaluated once per vk_set_atm)
+    {
+        const size_t npre = rep * (size_t)nz * ni;
+        double **pp[] = {&a.pre.Q, &a.pre.QB, &a.pre.QC, &a.pre.TA, &a.pre.TB, &a.pre.TC, &a.pre.SA, &a.pre.SB, &a.pre.SC};
+        for (double **q : pp) {
+            void *ptr = nullptr;
+            VK_CUDA(cudaMalloc(&ptr, sizeof(double) * npre));
+            c->atm_allocs.push_back(ptr);
+            *q = reinterpret_cast<double *>(ptr);
+        }
+        a.pre_cs = v->shared ? 0 : (size_t)nz * ni;
+        if ((rc = launch_atm_pre(c, (int)rep))) return rc;
+        VK_CUDA(cudaStreamSynchronize(c->stream));
+    }
     c->atm_set = true;
     return VK_OK;
 }

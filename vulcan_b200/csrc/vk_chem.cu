@@ -4,10 +4,13 @@
 //                (op.py:1438-1791), optionally the Ros2 stage-2 right-hand side  f(y+k1/r) - 2/(r h) k1 (op.py:2917-2928)
 //   lhs_kernel : chem_funs.neg_symjac block (make_chem_funs.py:653-717) + lhs_jac_tot / _settling / _no_mol
 //                (op.py:1973-2364):  D = 1/(r h) I - J_chem - J_transport, up/dn = the diagonal couplings
+//   atm_pre_kernel : the parts of the transport stencil that depend on the atmosphere only (molecular-diffusion quotients,
+//                thermal/gravity brackets, settling terms) evaluated ONCE per vk_set_atm with the reference's operation
+//                order, so that the per-step kernels reproduce the reference bit for bit without re-doing ~25 divisions
+//                per species and layer.
 //
-// This translation unit is compiled with -fmad=false: every expression below is evaluated with one IEEE rounding per
-// operation in the reference's order, so chemdf and diffdf are bit-identical to the numpy reference (tests/test_gpu_parity.py).
-// The reaction tables are staged per block in shared memory next to the layer's y and k vectors.
+// This translation unit is compiled with -fmad=false: every expression is evaluated with one IEEE rounding per operation in
+// the reference's order, so chemdf and diffdf are bit-identical to the numpy reference (tests/test_gpu_parity.py).
 #include "vk_internal.cuh"
 #include "vk_device_math.cuh"
 
@@ -33,6 +36,76 @@ __device__ __forceinline__ double phi_br(const AtmLayer &L, int m, int i, double
     return -1. / L.Hpi[m] + L.ms[i] * gx / (VK_NAVO * VK_KB * L.Ti[m]) + L.alpha[i] / L.Ti[m] * (L.Tco[m + 1] - L.Tco[m]) / L.dzi[m];
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// atmosphere-only pieces, arrays [ncol_atm][nz][ni]:
+//   Q  : Dzz[m]/dzi[m] at interface m = j (row nz-1 unused)
+//   QB : interior 1./dz_ave*Dzz[j]/dzi[j]      ; j=0: 1./dzi0*(D0/dzi0)            ; top: -1./dzi_m*(Dm/dzi_m)   (the A quotient)
+//   QC : interior 1./dz_ave*Dzz[j-1]/dzi[j-1]  ; j=0: -1./dzi0*(D0/dzi0) (A quot.) ; top:  1./dzi_m*(Dm/dzi_m)
+//   TA/TB/TC : thermal-gravity terms; SA/SB/SC : settling terms (signs applied by the consumer exactly as op.py does)
+__global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p)
+{
+    const int nz = a.nz, ni = a.ni;
+    const int col = blockIdx.x / nz, j = blockIdx.x % nz;
+    if (col >= ncol_atm) return;
+    const AtmLayer L = atm_at(a, col);
+    const double *dzi = L.dzi, *Dzz = L.Dzz, *vs = L.vs, *g = L.g;
+    const size_t base = ((size_t)col * nz + j) * ni;
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) {
+        double Q = 0, QB = 0, QC = 0, TA = 0, TB = 0, TC = 0, SA = 0, SB = 0, SC = 0;
+        if (j < nz - 1) Q = Dzz[(size_t)j * ni + i] / dzi[j];
+        if (j == 0) {
+            double D0 = Dzz[i];
+            QB = 1. / (dzi[0]) * (D0 / dzi[0]);
+            QC = -1. / (dzi[0]) * (D0 / dzi[0]);
+            double br = phi_br(L, 0, i, g[0]);
+            TA = 1. / (dzi[0]) * D0 / 2. * br;
+            TB = TA;
+            SA = (posv(vs[i])) / dzi[0];
+            SB = (negv(vs[i])) / dzi[0];
+        } else if (j == nz - 1) {
+            const int m = nz - 2;
+            double Dm = Dzz[(size_t)m * ni + i];
+            QB = -1. / (dzi[m]) * (Dm / dzi[m]);
+            QC = 1. / (dzi[m]) * (Dm / dzi[m]);
+            double br = phi_br(L, m, i, g[nz - 1]);
+            TA = 1. / (dzi[m]) * Dm / 2. * br;
+            TC = TA;
+            SA = (negv(vs[(size_t)m * ni + i])) / dzi[m];
+            SC = (posv(vs[(size_t)m * ni + i])) / dzi[m];
+        } else {
+            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
+            double Dj = Dzz[(size_t)j * ni + i], Dm = Dzz[(size_t)(j - 1) * ni + i];
+            QB = 1. / dz_ave * Dj / dzi[j];
+            QC = 1. / dz_ave * Dm / dzi[j - 1];
+            TA = 1. / (2. * dz_ave) * (Dj * phi_br(L, j, i, g[j]) - Dm * phi_br(L, j - 1, i, g[j]));
+            TB = 1. / (2. * dz_ave) * Dj * phi_br(L, j, i, g[j + 1]);
+            TC = 1. / (2. * dz_ave) * Dm * phi_br(L, j - 1, i, g[j - 1]);
+            double vj = vs[(size_t)j * ni + i], vm = vs[(size_t)(j - 1) * ni + i];
+            SA = (posv(vj) - negv(vm)) / dz_ave;
+            SB = (negv(vj)) / dz_ave;
+            SC = (posv(vm)) / dz_ave;
+        }
+        p.Q[base + i] = Q; p.QB[base + i] = QB; p.QC[base + i] = QC;
+        p.TA[base + i] = TA; p.TB[base + i] = TB; p.TC[base + i] = TC;
+        p.SA[base + i] = SA; p.SB[base + i] = SB; p.SC[base + i] = SC;
+    }
+}
+
+int launch_atm_pre(vk_column *c, int ncol_atm)
+{
+    atm_pre_kernel<<<ncol_atm * c->nz, 96, 0, c->stream>>>(c->atm, ncol_atm, c->atm.pre);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+
+// per-layer scalars that depend on the layer sums (one thread per block computes them)
+struct LayerScal {
+    double Aa, Bb, Cc;        // eddy + advection parts (diffdf form)
+    double m1;                // -1./dz_ave (interior)
+    double sp, sm;            // (ysp+ys0), (ys0+ysm)
+    double ys0, ysp, ysm;
+};
+
 struct RhsArgs {
     NetDev net;
     AtmDev atm;
@@ -47,20 +120,24 @@ struct RhsArgs {
     const unsigned char *fix_mask;          // rows forced to zero (op.py:2896-2925)
 };
 
-__global__ void __launch_bounds__(256) rhs_kernel(RhsArgs A)
+#define RHS_NT 256
+#define RHS_TR0 128      // first thread of the transport group
+
+__global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
 {
     extern __shared__ double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz;
     const int col = blockIdx.x / nz, j = blockIdx.x % nz;
     const int tid = threadIdx.x, nt = blockDim.x;
-    // shared layout
     double *ym = sm;                    // y[j-1]  (ni+2)
     double *y0 = ym + (ni + 2);         // y[j]    yx: [ni] = M, [ni+1] = 1.0
     double *yp = y0 + (ni + 2);         // y[j+1]
     double *kz = yp + (ni + 2);         // k[j][0..nr]
-    double *rate = kz + (nr + 2);       // rate[0..nr]
+    double *rate = kz + (nr + 2);       // rate[0..nr]  (phase 2: rate[odd j] <- rate[j] - rate[j+1])
     double *tmp = rate + (nr + 2);      // 3*ni scratch for gas-compacted sums
-    double *ysum = tmp + 3 * ni;        // [3]
+    double *ysum = tmp + 3 * ni;        // [4]
+    double *dsp = ysum + 4;             // [ni] transport tendency per species
+    LayerScal *S = reinterpret_cast<LayerScal *>(dsp + ni + (ni & 1));
 
     const size_t base = ((size_t)col * nz + j) * ni;
     const double rr = 1. + 1. / sqrt(2.);
@@ -81,7 +158,7 @@ __global__ void __launch_bounds__(256) rhs_kernel(RhsArgs A)
     for (int i = tid; i <= nr; i += nt) kz[i] = kg[i];
     __syncthreads();
 
-    // ---- rates of progress: rate[i] = k[i] * f0 * f1 * f2 * f3 (written order)
+    // ---- phase 1: rates of progress rate[i] = k[i]*f0*f1*f2*f3 (written order); layer sums (numpy pairwise order)
     for (int i = tid + 1; i <= nr; i += nt) {
         uchar4 f = A.net.rate_fac[i];
         double v = kz[i];
@@ -98,111 +175,126 @@ __global__ void __launch_bounds__(256) rhs_kernel(RhsArgs A)
         }
         rate[i] = v;
     }
-    // ---- layer sums for the diffusion stencil (three threads, numpy pairwise order)
-    if (tid < 3) {
-        int jj = j - 1 + tid;
+    if (tid >= RHS_NT - 3) {
+        const int q = tid - (RHS_NT - 3);
+        const int jj = j - 1 + q;
         if (jj >= 0 && jj < nz) {
-            const double *row = (tid == 0) ? ym : ((tid == 1) ? y0 : yp);
-            ysum[tid] = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, tmp + tid * ni);
+            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+            ysum[q] = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, tmp + q * ni);
         }
     }
     __syncthreads();
 
+    // ---- phase 2: v_j = rate[j] - rate[j+1] for every pair; one thread: the layer scalars of the stencil
+    for (int p = tid; 2 * p + 1 <= nr; p += nt) rate[2 * p + 1] = rate[2 * p + 1] - rate[2 * p + 2];
     const AtmLayer L = atm_at(A.atm, col);
-    const double *dzi = L.dzi, *Kzz = L.Kzz, *vz = L.vz;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
-    for (int i = tid; i < ni; i += nt) {
-        // ---- chemistry: left-to-right sum of coef * (rate[j] - rate[j+1]) in network order
-        double chem = 0.0;
-        {
-            int q0 = A.net.rhs_ptr[i], q1 = A.net.rhs_ptr[i + 1];
-            for (int q = q0; q < q1; q++) {
-                int t = A.net.rhs_term[q];
-                int jf = t >> 8;
-                double coef = (double)((signed char)(t & 0xff));
-                double v = rate[jf] - rate[jf + 1];
-                double term = coef * v;
-                chem = (q == q0) ? term : chem + term;
-            }
-        }
-        // ---- transport
-        double diff;
+    if (tid == RHS_NT - 1) {
+        const double *dzi = L.dzi, *Kzz = L.Kzz, *vz = L.vz;
         const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+        LayerScal s;
+        s.ys0 = ys0; s.ysp = ysp; s.ysm = ysm; s.sp = ysp + ys0; s.sm = ys0 + ysm; s.m1 = 0; s.Aa = s.Bb = s.Cc = 0;
         if (j == 0) {
-            double Aa = -1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ys0;
-            double Bb = 1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ysp;
-            Aa += -(posv(vz[0])) / dzi[0];
-            Bb += -(negv(vz[0])) / dzi[0];
+            s.Aa = -1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ys0;
+            s.Bb = 1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ysp;
+            s.Aa += -(posv(vz[0])) / dzi[0];
+            s.Bb += -(negv(vz[0])) / dzi[0];
+        } else if (j == nz - 1) {
+            const int m = nz - 2;
+            s.Aa = -1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ys0;
+            s.Cc = 1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ysm;
+            s.Aa += (negv(vz[m])) / dzi[m];
+            s.Cc += (posv(vz[m])) / dzi[m];
+        } else {
+            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
             if (md) {
-                double D0 = L.Dzz[i];
-                double br = phi_br(L, 0, i, L.g[0]);
-                double Ai = -1. / (dzi[0]) * (D0 / dzi[0]) * (ysp + ys0) / 2. / ys0 + 1. / (dzi[0]) * D0 / 2. * br;
-                double Bi = 1. / (dzi[0]) * (D0 / dzi[0]) * (ysp + ys0) / 2. / ysp + 1. / (dzi[0]) * D0 / 2. * br;
+                s.Aa = -1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
+                s.Bb = 1. / dz_ave * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
+                s.Cc = 1. / dz_ave * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
+            } else {   // diffdf_no_mol writes 2./(dzi[j-1]+dzi[j]) (op.py:1474-1476)
+                s.Aa = -2. / (dzi[j - 1] + dzi[j]) * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
+                s.Bb = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
+                s.Cc = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
+            }
+            s.Aa += -(posv(vz[j]) - negv(vz[j - 1])) / dz_ave;
+            s.Bb += -(negv(vz[j])) / dz_ave;
+            s.Cc += (posv(vz[j - 1])) / dz_ave;
+            s.m1 = -1. / dz_ave;
+        }
+        *S = s;
+    }
+    __syncthreads();
+
+    // ---- phase 3: chemistry sums (threads 0..ni-1) run beside the transport stencil (threads RHS_TR0..RHS_TR0+ni-1)
+    double chem = 0.0;
+    if (tid < ni) {
+        // left-to-right sum of coef * v_j in network order (make_chem_funs.py:258-285)
+        const int q0 = A.net.rhs_ptr[tid], q1 = A.net.rhs_ptr[tid + 1];
+        for (int q = q0; q < q1; q++) {
+            const int t = A.net.rhs_term[q];
+            const double coef = (double)((signed char)(t & 0xff));
+            const double term = coef * rate[t >> 8];
+            chem = (q == q0) ? term : chem + term;
+        }
+    } else if (tid >= RHS_TR0 && tid < RHS_TR0 + ni) {
+        const int i = tid - RHS_TR0;
+        const LayerScal s = *S;
+        const double *dzi = L.dzi;
+        const AtmPre &P = A.atm.pre;
+        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+        double diff;
+        if (j == 0) {
+            if (md) {
+                double Ai = P.QC[pb] * s.sp / 2. / s.ys0 + P.TA[pb];
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp + P.TB[pb];
                 if (st) {
-                    Ai = Ai - (posv(L.vs[i])) / dzi[0];
-                    Bi = Bi - (negv(L.vs[i])) / dzi[0];
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
                 }
-                diff = (Aa + Ai) * y0[i] + (Bb + Bi) * yp[i];
+                diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
             } else {
-                diff = Aa * y0[i] + Bb * yp[i];
+                diff = s.Aa * y0[i] + s.Bb * yp[i];
             }
             if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
         } else if (j == nz - 1) {
-            const int m = nz - 2;
-            double Aa = -1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ys0;
-            double Cc = 1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ysm;
-            Aa += (negv(vz[m])) / dzi[m];
-            Cc += (posv(vz[m])) / dzi[m];
             if (md) {
-                double Dm = L.Dzz[(size_t)m * ni + i];
-                double br = phi_br(L, m, i, L.g[nz - 1]);
-                double Ai = -1. / (dzi[m]) * (Dm / dzi[m]) * (ys0 + ysm) / 2. / ys0 - 1. / (dzi[m]) * Dm / 2. * br;
-                double Ci = 1. / (dzi[m]) * (Dm / dzi[m]) * (ys0 + ysm) / 2. / ysm - 1. / (dzi[m]) * Dm / 2. * br;
+                double Ai = P.QB[pb] * s.sm / 2. / s.ys0 - P.TA[pb];
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm - P.TC[pb];
                 if (st) {
-                    Ai = Ai + (negv(L.vs[(size_t)m * ni + i])) / dzi[m];
-                    Ci = Ci + (posv(L.vs[(size_t)m * ni + i])) / dzi[m];
+                    Ai = Ai + P.SA[pb];
+                    Ci = Ci + P.SC[pb];
                 }
-                diff = (Aa + Ai) * y0[i] + (Cc + Ci) * ym[i];
+                diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
             } else {
-                diff = Aa * y0[i] + Cc * ym[i];
+                diff = s.Aa * y0[i] + s.Cc * ym[i];
             }
-            if (A.atm.use_topflux) diff += L.top_flux[i] / dzi[m];
+            if (A.atm.use_topflux) diff += L.top_flux[i] / dzi[nz - 2];
         } else {
-            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
-            double Aa, Bb, Cc;
+            double t1 = s.Aa * y0[i] + s.Bb * yp[i] + s.Cc * ym[i];
             if (md) {
-                Aa = -1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
-                Bb = 1. / dz_ave * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
-                Cc = 1. / dz_ave * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
-            } else {   // diffdf_no_mol writes 2./(dzi[j-1]+dzi[j]) (op.py:1474-1476)
-                Aa = -2. / (dzi[j - 1] + dzi[j]) * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
-                Bb = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
-                Cc = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
-            }
-            Aa += -(posv(vz[j]) - negv(vz[j - 1])) / dz_ave;
-            Bb += -(negv(vz[j])) / dz_ave;
-            Cc += (posv(vz[j - 1])) / dz_ave;
-            double t1 = Aa * y0[i] + Bb * yp[i] + Cc * ym[i];
-            if (md) {
-                double Dj = L.Dzz[(size_t)j * ni + i], Dm = L.Dzz[(size_t)(j - 1) * ni + i];
-                double Ai = -1. / dz_ave * (Dj / dzi[j] * (ysp + ys0) / 2. + Dm / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
-                double Bi = 1. / dz_ave * Dj / dzi[j] * (ysp + ys0) / 2. / ysp;
-                double Ci = 1. / dz_ave * Dm / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
+                double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
                 if (st) {
-                    double vj = L.vs[(size_t)j * ni + i], vm = L.vs[(size_t)(j - 1) * ni + i];
-                    Ai = Ai - (posv(vj) - negv(vm)) / dz_ave;
-                    Bi = Bi - (negv(vj)) / dz_ave;
-                    Ci = Ci + (posv(vm)) / dz_ave;
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
+                    Ci = Ci + P.SC[pb];
                 }
-                Ai += 1. / (2. * dz_ave) * (Dj * phi_br(L, j, i, L.g[j]) - Dm * phi_br(L, j - 1, i, L.g[j]));
-                Bi += 1. / (2. * dz_ave) * Dj * phi_br(L, j, i, L.g[j + 1]);
-                Ci += -1. / (2. * dz_ave) * Dm * phi_br(L, j - 1, i, L.g[j - 1]);
+                Ai += P.TA[pb];
+                Bi += P.TB[pb];
+                Ci += -P.TC[pb];
                 double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
                 diff = t1 + t2;
             } else {
                 diff = t1;
             }
         }
+        dsp[i] = diff;
+    }
+    __syncthreads();
+    if (tid < ni) {
+        const int i = tid;
+        const double diff = dsp[i];
         if (A.out_chem) A.out_chem[base + i] = chem;
         if (A.out_diff) A.out_diff[base + i] = diff;
         if (A.out_sum) {
@@ -244,7 +336,8 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     double *kz = yp + (ni + 2);
     double *tmp = kz + (nr + 2);
     double *ysum = tmp + 3 * ni;
-    double *blk = ysum + 4;            // ld*ld block
+    double *part = ysum + 4;                                   // partial sums of split Jacobian entries
+    double *blk = part + A.net.n_part + (A.net.n_part & 1);    // ld*ld block
 
     const size_t base = ((size_t)col * nz + j) * ni;
     for (int i = tid; i < ni; i += nt) {
@@ -257,28 +350,39 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     for (int i = tid; i <= nr; i += nt) kz[i] = kg[i];
     for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
     __syncthreads();
-    if (tid < 3) {
-        int jj = j - 1 + tid;
+    if (tid >= 253) {
+        const int q = tid - 253;
+        const int jj = j - 1 + q;
         if (jj >= 0 && jj < nz) {
-            const double *row = (tid == 0) ? ym : ((tid == 1) ? y0 : yp);
-            ysum[tid] = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, tmp + tid * ni);
+            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+            ysum[q] = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, tmp + q * ni);
         }
     }
-    // ---- chemical Jacobian entries: blk[s][t] = -(d f_s / d y_t)
-    for (int e = tid; e < A.net.n_ent; e += nt) {
-        int q0 = A.net.jac_ptr[e], q1 = A.net.jac_ptr[e + 1];
+    // ---- chemical Jacobian: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work
+    for (int s = tid; s < A.net.n_seg; s += nt) {
+        const uint4 sg = A.net.jac_seg[s];     // x = row | col << 16, y = first term, z = n terms | slot << 16
+        const int q0 = (int)sg.y, q1 = q0 + (int)(sg.z & 0xffff);
         double acc = 0.0;
         for (int q = q0; q < q1; q++) {
-            uint2 t = A.net.jac_term[q];
-            double coef = (double)((signed char)((t.x >> 16) & 0xff));
+            const uint2 t = A.net.jac_term[q];
+            const double coef = (double)((signed char)((t.x >> 16) & 0xff));
             double term = coef * kz[t.x & 0xffff];
             term = term * y0[t.y & 0xff];
             term = term * y0[(t.y >> 8) & 0xff];
             term = term * y0[(t.y >> 16) & 0xff];
             acc += term;
         }
-        ushort2 rc = A.net.jac_rc[e];
-        blk[rc.x * ld + rc.y] = -acc;
+        const unsigned slot = sg.z >> 16;
+        if (slot == 0xffffu) blk[(sg.x & 0xffff) * ld + (sg.x >> 16)] = -acc;
+        else part[slot] = acc;
+    }
+    __syncthreads();
+    for (int m = tid; m < A.net.n_multi; m += nt) {          // entries that were split: fixed-order sum of their partials
+        const uint2 me = A.net.jac_multi[m];                 // x = row | col << 16, y = first slot | n << 16
+        const int s0 = (int)(me.y & 0xffff), n = (int)(me.y >> 16);
+        double acc = 0.0;
+        for (int q = 0; q < n; q++) acc += part[s0 + q];
+        blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
     }
     __syncthreads();
     // ---- diagonal: c0 + negJ_ss - transport;  couplings up/dn   (op.py:1998-2040)
@@ -289,6 +393,7 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     const double c0 = 1. / (rr * A.dt[col]);
     const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
     const size_t vbase = ((size_t)col * nz + j) * ld;
+    const AtmPre &P = A.atm.pre;
     for (int i = tid; i < ld; i += nt) {
         if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
             blk[i * ld + i] = 1.0;
@@ -296,19 +401,18 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
             A.dn[vbase + i] = 0.0;
             continue;
         }
+        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
         double d = c0 + blk[i * ld + i];
         double u = 0.0, l = 0.0;
         if (j == 0) {
             d -= -1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / (2. * ys0) - (posv(vz[0])) / dzi[0];
             u -= 1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / (2. * ysp) - (negv(vz[0])) / dzi[0];
             if (md) {
-                double D0 = L.Dzz[i];
-                double br = phi_br(L, 0, i, L.g[0]);
-                double ta = -1. / (dzi[0]) * (D0 / dzi[0]) * (ysp + ys0) / (2. * ys0) + 1. / (dzi[0]) * D0 / 2. * br;
-                double tb = 1. / (dzi[0]) * (D0 / dzi[0]) * (ysp + ys0) / (2. * ysp) + 1. / (dzi[0]) * D0 / 2. * br;
+                double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
+                double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
                 if (st) {
-                    ta = ta - (posv(L.vs[i])) / dzi[0];
-                    tb = tb - (negv(L.vs[i])) / dzi[0];
+                    ta = ta - P.SA[pb];
+                    tb = tb - P.SB[pb];
                 }
                 d -= ta;
                 if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
@@ -321,13 +425,11 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
             d -= -1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ysm + ys0) / (2. * ys0) + (negv(vz[m])) / dzi[m];
             l -= 1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ysm + ys0) / (2. * ysm) + (posv(vz[m])) / dzi[m];
             if (md) {
-                double Dm = L.Dzz[(size_t)m * ni + i];
-                double br = phi_br(L, m, i, L.g[nz - 1]);
-                double ta = -1. / (dzi[m]) * (Dm / dzi[m]) * (ys0 + ysm) / (2. * ys0) - 1. / (dzi[m]) * Dm / 2. * br;
-                double tc = 1. / (dzi[m]) * (Dm / dzi[m]) * (ys0 + ysm) / (2. * ysm) - 1. / (dzi[m]) * Dm / 2. * br;
+                double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
+                double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
                 if (st) {
-                    ta = ta + (negv(L.vs[(size_t)m * ni + i])) / dzi[m];
-                    tc = tc + (posv(L.vs[(size_t)m * ni + i])) / dzi[m];
+                    ta = ta + P.SA[pb];
+                    tc = tc + P.SC[pb];
                 }
                 d -= ta;
                 l -= tc;
@@ -339,16 +441,13 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
             u -= 1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / (2. * ysp)) - (negv(vz[j])) / dz_ave;
             l -= 1. / dz_ave * (Kzz[j - 1] / dzi[j - 1] * (ysm + ys0) / (2. * ysm)) + (posv(vz[j - 1])) / dz_ave;
             if (md) {
-                double Dj = L.Dzz[(size_t)j * ni + i], Dm = L.Dzz[(size_t)(j - 1) * ni + i];
-                double ta = -1. / dz_ave * (Dj / dzi[j] * (ysp + ys0) / 2. + Dm / dzi[j - 1] * (ysm + ys0) / 2.) / ys0 +
-                            1. / (2. * dz_ave) * (Dj * phi_br(L, j, i, L.g[j]) - Dm * phi_br(L, j - 1, i, L.g[j]));
-                double tb = 1. / dz_ave * (Dj / dzi[j] * (ysp + ys0) / (2. * ysp)) + 1. / (2. * dz_ave) * Dj * phi_br(L, j, i, L.g[j + 1]);
-                double tc = 1. / dz_ave * (Dm / dzi[j - 1] * (ysm + ys0) / (2. * ysm)) - 1. / (2. * dz_ave) * Dm * phi_br(L, j - 1, i, L.g[j - 1]);
+                double ta = -1. / dz_ave * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
+                double tb = 1. / dz_ave * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
+                double tc = 1. / dz_ave * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
                 if (st) {
-                    double vj = L.vs[(size_t)j * ni + i], vm = L.vs[(size_t)(j - 1) * ni + i];
-                    ta = ta - (posv(vj) - negv(vm)) / dz_ave;
-                    tb = tb - (negv(vj)) / dz_ave;
-                    tc = tc + (posv(vm)) / dz_ave;
+                    ta = ta - P.SA[pb];
+                    tb = tb - P.SB[pb];
+                    tc = tc + P.SC[pb];
                 }
                 d -= ta;
                 u -= tb;
@@ -365,20 +464,26 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     }
     __syncthreads();
     double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
-    for (int q = tid; q < ld * ld; q += nt) Dg[q] = blk[q];
+    if ((ld & 1) == 0) {
+        for (int q = tid; q < ld * ld / 2; q += nt)
+            reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
+    } else {
+        for (int q = tid; q < ld * ld; q += nt) Dg[q] = blk[q];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_chem, double *out_diff,
                const double *k1_for_rhs2, const double *dt_dev)
 {
+    if (c->ni > RHS_NT - RHS_TR0 - 3) { set_error("ni too large for rhs_kernel thread layout"); return VK_ERR_UNSUPPORTED; }
     RhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs;
     a.k1 = k1_for_rhs2; a.dt = dt_dev; a.yk2_out = k1_for_rhs2 ? c->yk2 : nullptr;
     a.out_sum = out_sum; a.out_chem = out_chem; a.out_diff = out_diff;
     a.fix_mask = c->opts.fix_mask;
-    size_t smem = sizeof(double) * (3 * (c->ni + 2) + 2 * (c->nr + 2) + 3 * c->ni + 4);
-    rhs_kernel<<<c->ncol * c->nz, 256, smem, c->stream>>>(a);
+    size_t smem = sizeof(double) * (3 * (c->ni + 2) + 2 * (c->nr + 2) + 3 * c->ni + 4 + c->ni + 2) + sizeof(LayerScal) + 16;
+    rhs_kernel<<<c->ncol * c->nz, RHS_NT, smem, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
@@ -388,7 +493,8 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     LhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
     a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask;
-    size_t smem = sizeof(double) * (3 * (c->ni + 2) + (c->nr + 2) + 3 * c->ni + 4 + (size_t)ld * ld);
+    const int np = c->net->d.n_part + (c->net->d.n_part & 1);
+    size_t smem = sizeof(double) * (3 * (c->ni + 2) + (c->nr + 2) + 3 * c->ni + 4 + np + (size_t)ld * ld) + 16;
     static size_t configured = 0;
     if (smem > configured) {
         VK_CUDA(cudaFuncSetAttribute(lhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

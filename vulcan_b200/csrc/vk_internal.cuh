@@ -35,6 +35,15 @@ struct NetDev {
     const int *jac_ptr;         // [n_ent+1]
     const ushort2 *jac_rc;      // [n_ent] (row, col)
     const uint2 *jac_term;      // [n_term] .x = k index | (coef8 << 16), .y = 3 factor bytes
+    // Jacobian work schedule: entries cut into segments of <= 16 terms, sorted by length (warp lanes carry equal work)
+    int n_seg, n_multi, n_part;
+    const uint4 *jac_seg;       // [n_seg]   x = row | col << 16, y = first term, z = n terms | slot << 16 (slot 0xffff: whole entry)
+    const uint2 *jac_multi;     // [n_multi] x = row | col << 16, y = first slot | n slots << 16
+};
+
+// atmosphere-only pieces of the transport stencil, [ncol_atm][nz][ni] each (see atm_pre_kernel)
+struct AtmPre {
+    double *Q, *QB, *QC, *TA, *TB, *TC, *SA, *SB, *SC;
 };
 
 // ---- transport view on the device -------------------------------------------------------------------------------
@@ -46,6 +55,8 @@ struct AtmDev {
     size_t cs1, csn, csz;       // column strides (elements) of [nz-1], [nz-1][ni] and [nz] arrays; cs_i for [ni]; 0 when shared
     size_t csi;
     const double *Kzz, *vz, *dzi, *Dzz, *vs, *Tco, *g, *M, *Ti, *Hpi, *ms, *alpha, *top_flux, *bot_flux, *bot_vdep;
+    AtmPre pre;
+    size_t pre_cs;              // column stride of the AtmPre arrays (0 when shared)
 };
 
 struct StepOptsDev {
@@ -100,6 +111,7 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
                const double *k1_for_rhs2, const double *dt_dev);
 int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dense_out_ni, double *D_out, double *up_out,
                double *dn_out);
+int launch_atm_pre(vk_column *c, int ncol_atm);
 // kernels (vk_solve.cu)
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status, const double *rhs,
                   double *z);

@@ -240,7 +240,7 @@ struct SolveArgs {
 };
 
 template <int NIP>
-__global__ void __launch_bounds__(NIP * 4, 1) solve_kernel(SolveArgs a)
+__global__ void __launch_bounds__(NIP * 4, (NIP <= 72) ? 2 : 1) solve_kernel(SolveArgs a)
 {
     constexpr int NCH = NIP / 8;
     __shared__ __align__(16) double tvec[NIP];
