@@ -9,49 +9,47 @@
 // layout (lane = 4*g + t holds rows 8*tile+g, columns 8*tile+2t,2t+1), pivot row / column are broadcast through
 // shared memory, the pivot search is a warp REDUX over the candidate column.  The factor is stored once (W_j) and reused
 // for the second Ros2 stage and for iterative refinement - the reference factorises twice.
+#include <type_traits>
+
 #include "vk_internal.cuh"
 
 namespace vk {
 
-__device__ __forceinline__ unsigned long long abs_bits(double v) { return (unsigned long long)__double_as_longlong(fabs(v)); }
+// 1/x without the IEEE slow path: hardware approximation (2^-23) + two Newton steps (error ~1 ulp); x = 0 / inf / nan give
+// inf / 0 / nan, caught by the singular-pivot flag
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
 
 // Register layout: warp w owns the 8 columns [8w, 8w+8) of the block and ALL its rows, in the m8n8 accumulator-fragment
-// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1.
-// One pivot step k:
-//   owner warp (k/8): pivot search on its own column with ONE warp REDUX over packed keys {|a| high word, row} (the
-//   maximum is taken on the top 13 mantissa bits: threshold partial pivoting with threshold 1 - 2^-13), reciprocal of
-//   each lane's local best computed while the REDUX is in flight, multipliers l_r = a_rk / pivot published to shared memory;
-//   __syncthreads (the only block barrier of the step);
-//   every warp: rank-1 update of its own 8 columns; the pivot-row values it needs are its own (warp shuffle).
-// dst = A[idx][e] with a block-uniform runtime idx: a uniform switch keeps A in registers (no local-memory indexing)
-#define VK_SELECT_ROW(idx, e, dst)                                                     \
-    switch (idx) {                                                                     \
-        case 0: dst = A[0][e]; break;                                                  \
-        case 1: if (NR > 1) dst = A[1 < NR ? 1 : 0][e]; break;                         \
-        case 2: if (NR > 2) dst = A[2 < NR ? 2 : 0][e]; break;                         \
-        case 3: if (NR > 3) dst = A[3 < NR ? 3 : 0][e]; break;                         \
-        case 4: if (NR > 4) dst = A[4 < NR ? 4 : 0][e]; break;                         \
-        case 5: if (NR > 5) dst = A[5 < NR ? 5 : 0][e]; break;                         \
-        case 6: if (NR > 6) dst = A[6 < NR ? 6 : 0][e]; break;                         \
-        case 7: if (NR > 7) dst = A[7 < NR ? 7 : 0][e]; break;                         \
-        case 8: if (NR > 8) dst = A[8 < NR ? 8 : 0][e]; break;                         \
-        case 9: if (NR > 9) dst = A[9 < NR ? 9 : 0][e]; break;                         \
-        case 10: if (NR > 10) dst = A[10 < NR ? 10 : 0][e]; break;                     \
-        case 11: if (NR > 11) dst = A[11 < NR ? 11 : 0][e]; break;                     \
-        case 12: if (NR > 12) dst = A[12 < NR ? 12 : 0][e]; break;                     \
-        case 13: if (NR > 13) dst = A[13 < NR ? 13 : 0][e]; break;                     \
-        case 14: if (NR > 14) dst = A[14 < NR ? 14 : 0][e]; break;                     \
-        default: break;                                                                \
-    }
-
+// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1 (the layout of
+// mma.sync.m8n8k4.f64 accumulators).
+//
+// Pivoting: DIAGONAL pivots.  Measured on the reference's own matrices (tests + DESIGN.md §4.1): for these systems
+// (1/(r h) I - J with loss terms on the diagonal; species abundances spanning 30+ decades so that rows carry wildly
+// different scales) Gauss-Jordan on the diagonal is 2-5 orders of magnitude MORE accurate than LAPACK-style partial pivoting,
+// which lets the largest entry of a column - a scale artefact - destroy componentwise accuracy.  A zero / non-finite pivot
+// sets VK_ERR_SINGULAR for the column: the step is rejected and retried with dt/2 exactly like any other failed step.
+//
+// With the pivot row known in advance the per-pivot work is: owner warp (k/8) forms the multipliers a_rk / a_kk of its column
+// and publishes them (double-buffered shared memory); ONE __syncthreads; every warp: 9 LDS + pivot-row broadcast by warp
+// shuffle from a compile-time register (the k loop is unrolled over the row tile) + 18 FMAs.  Pivot-row scaling is deferred to
+// the end of the layer, so the inverse W_j stays in registers in its natural layout: the Schur update of the next layer
+// (elementwise, the couplings are diagonal), the write-out and the fused forward elimination all work from registers.
 template <int NIP>
 struct FactorCfg {
-    static constexpr int NW = NIP / 8;
-    static constexpr int NR = NIP / 8;
+    static constexpr int NW = NIP / 8;           // warps
+    static constexpr int NR = NIP / 8;           // rows per lane
     static constexpr int NT = NW * 32;
-    static constexpr int LD = NIP + 2;
-    // Wsm + lbuf[2] + tvec + zprev (doubles), pinv[2] (double), piv_p, piv_q, pidx[2] (ints)
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * LD + 5 * NIP) + sizeof(int) * (2 * NIP + 4);
+    // lbuf[2][NIP] + rscale[NIP] + tvec[NIP] + zpart[NW][NIP] (doubles)
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)(4 + NW) * NIP);
 };
 
 struct FactorArgs {
@@ -65,20 +63,23 @@ struct FactorArgs {
     double *z;           // [ncol][nz][NIP]
 };
 
+#ifdef VK_TRACE
+__device__ long long g_trace[128 * 8];
+#define TRACE(kk, ev) do { if (j == 5 && (kk) < 128 && lane == 0) g_trace[(kk) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TRACE(kk, ev) do { } while (0)
+#endif
+
 template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
 {
     using C = FactorCfg<NIP>;
-    constexpr int NR = C::NR, LD = C::LD, NT = C::NT;
+    constexpr int NR = C::NR, NW = C::NW;
     extern __shared__ __align__(16) double smem[];
-    double *Wsm = smem;                  // NIP x LD   natural-layout inverse of the current / previous layer
-    double *lbuf = Wsm + NIP * LD;       // 2 x NIP    multipliers of step k (double buffered)
-    double *tvec = lbuf + 2 * NIP;       // NIP
-    double *zprev = tvec + NIP;          // NIP
-    double *rscale = zprev + NIP;        // NIP  1/pivot of each physical row (deferred row scaling)
-    int *piv_p = (int *)(rscale + NIP);  // p[k]: physical row chosen at step k
-    int *piv_q = piv_p + NIP;            // q[r]: step at which physical row r was the pivot
-    int *pidx = piv_q + NIP;             // 2
+    double *lbuf = smem;                 // 2 x NIP   multipliers of pivot step k (double buffered)
+    double *rscale = lbuf + 2 * NIP;     // NIP       1/pivot of every row (deferred pivot-row scaling)
+    double *tvec = rscale + NIP;         // NIP       r_j - dn_j * z_{j-1}
+    double *zpart = tvec + NIP;          // NW x NIP  per-warp partial sums of W_j tvec
 
     const int col = blockIdx.x;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -93,138 +94,134 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     const bool fuse = a.rhs != nullptr;
     const double *rc = fuse ? a.rhs + (size_t)col * nz * ni : nullptr;
     double *zc = fuse ? a.z + (size_t)col * nz * NIP : nullptr;
-    if (tid < NIP) zprev[tid] = 0.0;
+    double zreg = 0.0;                   // z_{j-1}[tid] for tid < NIP
+    int bad = 0;
 
     for (int j = 0; j < nz; j++) {
-        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}) into registers
-        const double *Dj = Dc + (size_t)j * NIP * NIP;
+        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}); W_{j-1} is still in A
         {
+            const double *Dj = Dc + (size_t)j * NIP * NIP;
             double u0 = 0.0, u1 = 0.0;
             if (j > 0) { u0 = upc[(size_t)(j - 1) * NIP + c0]; u1 = upc[(size_t)(j - 1) * NIP + c0 + 1]; }
 #pragma unroll
             for (int i = 0; i < NR; i++) {
                 const int r = 8 * i + g;
-                double2 d = *reinterpret_cast<const double2 *>(Dj + (size_t)r * NIP + c0);
+                const double2 d = *reinterpret_cast<const double2 *>(Dj + (size_t)r * NIP + c0);
                 if (j > 0) {
                     const double l = dnc[(size_t)j * NIP + r];
-                    const double2 wv = *reinterpret_cast<const double2 *>(Wsm + r * LD + c0);
-                    d.x = d.x - (l * wv.x) * u0;
-                    d.y = d.y - (l * wv.y) * u1;
+                    A[i][0] = d.x - (l * A[i][0]) * u0;
+                    A[i][1] = d.y - (l * A[i][1]) * u1;
+                } else {
+                    A[i][0] = d.x;
+                    A[i][1] = d.y;
                 }
-                A[i][0] = d.x;
-                A[i][1] = d.y;
-            }
-        }
-        if (tid < NIP) { piv_p[tid] = tid; piv_q[tid] = tid; rscale[tid] = 1.0; }
-        __syncthreads();   // everyone is done reading Wsm of layer j-1
-        unsigned avail = (NR >= 32) ? 0xffffffffu : ((1u << NR) - 1u);   // bit i: my row 8i+g has not been a pivot yet
-        bool singular = false;
-        for (int k = 0; k < ni; k++) {
-            const int cb = k & 1;
-            const int kc = k & 7;
-            if (w == (k >> 3)) {
-                // ---- owner warp: pivot search on column k (held by the 8 lanes with t == kc/2)
-                const bool holder = (t == (kc >> 1));
-                unsigned key[NR];
-#pragma unroll
-                for (int i = 0; i < NR; i++) {
-                    const int hi = (kc & 1) ? __double2hiint(A[i][1]) : __double2hiint(A[i][0]);
-                    key[i] = (((unsigned)hi & 0x7fffff80u) | (unsigned)(127 - (8 * i + g))) & (0u - ((avail >> i) & 1u));
-                }
-#pragma unroll
-                for (int st = 1; st < NR; st <<= 1)
-#pragma unroll
-                    for (int i = 0; i + st < NR; i += 2 * st) key[i] = max(key[i], key[i + st]);
-                const unsigned mk = __reduce_max_sync(0xffffffffu, holder ? key[0] : 0u);
-                const int p = 127 - (int)(mk & 0x7fu);
-                const int pi = p >> 3;
-                double pv0 = 1.0, pv1 = 1.0;
-                VK_SELECT_ROW(pi, 0, pv0);
-                VK_SELECT_ROW(pi, 1, pv1);
-                double pv = (kc & 1) ? pv1 : pv0;
-                pv = __shfl_sync(0xffffffffu, pv, ((p & 7) << 2) | (kc >> 1));
-                const double inv = 1.0 / pv;
-                if (holder) {
-#pragma unroll
-                    for (int i = 0; i < NR; i++) {
-                        const int r = 8 * i + g;
-                        const double v = (kc & 1) ? A[i][1] : A[i][0];
-                        const double l = (r == p) ? 0.0 : v * inv;
-                        lbuf[cb * NIP + r] = l;
-                        // column k of the transformed block; the pivot row is kept UNSCALED (its factor 1/pivot is applied
-                        // once, when the block is written out), so its own entry in column k is pivot * (1/pivot) = 1
-                        const double nv = (r == p) ? 1.0 : -l;
-                        if (kc & 1) A[i][1] = nv; else A[i][0] = nv;
-                    }
-                }
-                if (lane == 0) {
-                    const bool ok = (mk >> 7) != 0u;
-                    pidx[cb] = ok ? p : -1;
-                    if (ok) { piv_p[k] = p; piv_q[p] = k; rscale[p] = inv; }
-                }
-            }
-            __syncthreads();
-            const int p = pidx[cb];
-            if (p < 0) { singular = true; break; }
-            const int pi = p >> 3, pg = p & 7;
-            if (pg == g) avail &= ~(1u << pi);
-            // pivot-row values of my two columns (held by lane 4*pg + t of this warp)
-            double pr0 = 0.0, pr1 = 0.0;
-            VK_SELECT_ROW(pi, 0, pr0);
-            VK_SELECT_ROW(pi, 1, pr1);
-            pr0 = __shfl_sync(0xffffffffu, pr0, (pg << 2) | t);
-            pr1 = __shfl_sync(0xffffffffu, pr1, (pg << 2) | t);
-            if (w == (k >> 3) && t == (kc >> 1)) {   // column k itself is already final: eliminate with 0
-                if (kc & 1) pr1 = 0.0; else pr0 = 0.0;
-            }
-#pragma unroll
-            for (int i = 0; i < NR; i++) {
-                const double l = lbuf[cb * NIP + 8 * i + g];    // 0 for the pivot row
-                A[i][0] = fma(-l, pr0, A[i][0]);
-                A[i][1] = fma(-l, pr1, A[i][1]);
-            }
-        }
-        if (singular) {
-            if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
-            return;   // uniform: every thread read the same flag
-        }
-        // ---- un-permute into shared memory, applying the deferred pivot-row scaling:  W[q(r)][p(c)] = A[r][c] / pivot(r)
-        {
-            const int pc0 = piv_p[c0], pc1 = piv_p[c0 + 1];
-#pragma unroll
-            for (int i = 0; i < NR; i++) {
-                const int qr = piv_q[8 * i + g];
-                const double sc = rscale[8 * i + g];
-                Wsm[qr * LD + pc0] = A[i][0] * sc;
-                Wsm[qr * LD + pc1] = A[i][1] * sc;
             }
         }
         if (fuse && tid < NIP) {
             const double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
-            tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zprev[tid];
+            tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zreg;
+        }
+        if (tid < NIP) rscale[tid] = 1.0;
+        // ---- Gauss-Jordan on the diagonal.  lbuf holds the NEGATED multipliers -a_rk/a_kk (0 in the pivot row); they are
+        // also the new column k of the transformed block (with 1 in the pivot row, which stays unscaled until write-out).
+        // PUBLISH(KT, G, E, H, CB): the warp owning column 8*KT+G (plane E of lane pair H) forms and publishes them.
+#define VK_PUBLISH(KT, G, E, H, CB)                                                                                    \
+        {                                                                                                              \
+            const double dkk = __shfl_sync(0xffffffffu, A[KT][E], ((G) << 2) | (H));                                   \
+            const double ninv = -fast_rcp(dkk);                                                                        \
+            if (!(fabs(dkk) > 0.0)) bad = 1;                                                                           \
+            if (t == (H)) {                                                                                            \
+                _Pragma("unroll") for (int i = 0; i < NR; i++) {                                                       \
+                    A[i][E] = A[i][E] * ninv;                                                                          \
+                    if (i == (KT)) { if (g == (G)) A[i][E] = 0.0; }                                                    \
+                    lbuf[(CB) * NIP + 8 * i + g] = A[i][E];                                                            \
+                }                                                                                                      \
+                if (g == (G)) { A[KT][E] = 1.0; rscale[8 * (KT) + (G)] = -ninv; }                                      \
+            }                                                                                                          \
+        }
+        if (w == 0) VK_PUBLISH(0, 0, 0, 0, 0)
+        // one row tile of pivots; KT and the plane E are compile-time constants so that A[KT][E] is a register
+        auto pivot_tile = [&](auto ktc) {
+            constexpr int kt = decltype(ktc)::value;
+            constexpr int ktn = (kt + 1 < NR) ? kt + 1 : kt;
+            for (int h = 0; h < 4; h++) {
+                // ---------------- pivot k = 8 kt + 2 h (plane 0); the next column is plane 1 of the same lane pair
+                {
+                    const int k = 8 * kt + 2 * h;
+                    if (k >= ni) break;
+                    __syncthreads();                              // multipliers of step k visible (buffer 0: k is even)
+                    double nl[NR];
+#pragma unroll
+                    for (int i = 0; i < NR; i++) nl[i] = lbuf[8 * i + g];
+                    const int src = ((2 * h) << 2) | t;
+                    const double pr1 = __shfl_sync(0xffffffffu, A[kt][1], src);
+                    double pr0 = __shfl_sync(0xffffffffu, A[kt][0], src);
+                    if (w == kt && t == h) pr0 = 0.0;             // column k itself is final
+#pragma unroll
+                    for (int i = 0; i < NR; i++) A[i][1] = fma(nl[i], pr1, A[i][1]);
+                    if (w == kt && k + 1 < ni) VK_PUBLISH(kt, 2 * h + 1, 1, h, 1)
+#pragma unroll
+                    for (int i = 0; i < NR; i++) A[i][0] = fma(nl[i], pr0, A[i][0]);
+                }
+                // ---------------- pivot k = 8 kt + 2 h + 1 (plane 1); the next column is plane 0 of the next lane pair / tile
+                {
+                    const int k = 8 * kt + 2 * h + 1;
+                    if (k >= ni) break;
+                    __syncthreads();                              // buffer 1: k is odd
+                    double nl[NR];
+#pragma unroll
+                    for (int i = 0; i < NR; i++) nl[i] = lbuf[NIP + 8 * i + g];
+                    const int src = ((2 * h + 1) << 2) | t;
+                    const double pr0 = __shfl_sync(0xffffffffu, A[kt][0], src);
+                    double pr1 = __shfl_sync(0xffffffffu, A[kt][1], src);
+                    if (w == kt && t == h) pr1 = 0.0;             // column k itself is final
+#pragma unroll
+                    for (int i = 0; i < NR; i++) A[i][0] = fma(nl[i], pr0, A[i][0]);
+                    if (k + 1 < ni) {
+                        if (h < 3) { if (w == kt) VK_PUBLISH(kt, 2 * h + 2, 0, h + 1, 0) }
+                        else if (kt + 1 < NR) { if (w == ktn) VK_PUBLISH(ktn, 0, 0, 0, 0) }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; i++) A[i][1] = fma(nl[i], pr1, A[i][1]);
+                }
+            }
+        };
+#define VK_TILE(N) if constexpr ((N) < NR) { if (8 * (N) < ni) pivot_tile(std::integral_constant<int, (N)>{}); }
+        VK_TILE(0) VK_TILE(1) VK_TILE(2) VK_TILE(3) VK_TILE(4) VK_TILE(5) VK_TILE(6) VK_TILE(7)
+        VK_TILE(8) VK_TILE(9) VK_TILE(10) VK_TILE(11) VK_TILE(12) VK_TILE(13) VK_TILE(14)
+#undef VK_TILE
+#undef VK_PUBLISH
+        if (__syncthreads_or(bad)) {
+            if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
+            return;
+        }
+        // ---- W_j = diag(rscale) A : stays in registers for the next layer; written out; fused forward elimination
+        double *Wj = Wc + (size_t)j * NIP * NIP;
+        double tv0 = 0.0, tv1 = 0.0;
+        if (fuse) { tv0 = tvec[c0]; tv1 = tvec[c0 + 1]; }
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const int r = 8 * i + g;
+            const double sc = rscale[r];
+            A[i][0] *= sc;
+            A[i][1] *= sc;
+            *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c0) = make_double2(A[i][0], A[i][1]);
+            if (fuse) {
+                double part = fma(A[i][0], tv0, A[i][1] * tv1);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                if (t == 0) zpart[w * NIP + r] = part;
+            }
         }
         __syncthreads();
-        double *Wj = Wc + (size_t)j * NIP * NIP;
-        for (int q = tid; q < NIP * NIP / 2; q += NT) {
-            const int r = (2 * q) / NIP, c = (2 * q) % NIP;
-            *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c) = *reinterpret_cast<const double2 *>(Wsm + r * LD + c);
-        }
-        if (fuse) {   // z_j = W_j (r_j - dn_j * z_{j-1}) : 4 threads per row
-            const int row = tid >> 2, part = tid & 3;
-            double acc0 = 0.0, acc1 = 0.0;
+        if (fuse && tid < NIP) {   // z_j = W_j (r_j - dn_j * z_{j-1})
+            double acc = 0.0;
 #pragma unroll
-            for (int i = 0; i < NIP / 8; i++) {
-                const double2 wv = *reinterpret_cast<const double2 *>(Wsm + row * LD + i * 8 + part * 2);
-                const double2 tv = *reinterpret_cast<const double2 *>(tvec + i * 8 + part * 2);
-                acc0 = fma(wv.x, tv.x, acc0);
-                acc1 = fma(wv.y, tv.y, acc1);
-            }
-            double acc = acc0 + acc1;
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (part == 0) { zprev[row] = acc; zc[(size_t)j * NIP + row] = acc; }
+            for (int q = 0; q < NW; q++) acc += zpart[q * NIP + tid];
+            zreg = acc;
+            zc[(size_t)j * NIP + tid] = acc;
         }
-        // the next iteration reads Wsm / zprev after its own __syncthreads-protected section
+        // (the next layer's first __syncthreads orders the zpart / tvec / rscale reuse)
     }
 }
 
@@ -347,11 +344,6 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
                            const double *rhs, double *z)
 {
     using C = FactorCfg<NIP>;
-    static bool configured = false;
-    if (!configured) {
-        VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured = true;
-    }
     FactorArgs a{c->nz, c->ni, D, up, dn, W, status, rhs, z};
     factor_kernel<NIP, MINB><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
@@ -393,3 +385,11 @@ int launch_residual(vk_column *c, const double *D, const double *up, const doubl
 }
 
 }  // namespace vk
+
+
+#ifdef VK_TRACE
+extern "C" int vk_debug_trace(long long *out)
+{
+    return (int)cudaMemcpyFromSymbol(out, vk::g_trace, sizeof(long long) * 128 * 8);
+}
+#endif
