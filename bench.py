@@ -123,7 +123,7 @@ def cpu_port_rate(case, n_sample, threads):
     ymix = y / y.sum(axis=2, keepdims=True)
 
     def one(i):
-        res = o.ros2_solver(atms[i], y[i], ymix[i], case.k, case.dt, cfg["mtol"], cfg["atol"], refine=1)
+        res = o.ros2_solver(atms[i], y[i], ymix[i], case.k, case.dt, cfg["mtol"], cfg["atol"], refine=0)
         o.clip_loss(res["sol"], res["ymix"], case.st["compo"], cfg["pos_cut"], cfg["nega_cut"], cfg["mtol"])
         return res["delta"]
     one(0)
@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--columns", type=int, default=N_COLUMNS)
-    ap.add_argument("--refine", type=int, default=1)
+    ap.add_argument("--refine", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

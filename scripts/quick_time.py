@@ -18,7 +18,7 @@ def make(case, ncol, refine):
 
 if __name__ == "__main__":
   c = Case("HD189", 100)
-  for ncol in [1, 148, 592]:
+  for ncol in [1, 592, 888]:
       for refine in (0, 1):
           col = make(c, ncol, refine)
           y = np.repeat(c.y[None], ncol, 0); ym = np.repeat(c.ymix[None], ncol, 0); dt = np.full(ncol, c.dt)

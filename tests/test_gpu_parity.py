@@ -178,7 +178,7 @@ def test_device_resident_loop_vs_reference_trajectory():
     cfg = c.cfg
     full = np.load("%s/HD189_full.npz" % GOLD)
     tr = full["traj"]
-    col = _columns(c, 1, refine=1)
+    col = _columns(c, 1, refine=0)
     col.ens_setup(cfg["rtol"], cfg["loss_eps"], cfg["dt_min"], cfg["dt_max"], cfg["dt_var_min"], cfg["dt_var_max"],
                   cfg["pos_cut"], cfg["nega_cut"], c.st["compo"], c.st["atom_ini"], c.st["n_0"])
     col.ens_set_state(c.y, c.dt)

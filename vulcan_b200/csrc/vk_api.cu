@@ -281,6 +281,12 @@ int vk_set_atm(vk_column *c, const vk_atm_view *v)
             c->atm_allocs.push_back(ptr);
             *q = reinterpret_cast<double *>(ptr);
         }
+        {
+            void *ptr = nullptr;
+            VK_CUDA(cudaMalloc(&ptr, sizeof(double) * rep * (size_t)nz * 10));
+            c->atm_allocs.push_back(ptr);
+            a.pre.LS = reinterpret_cast<double *>(ptr);
+        }
         a.pre_cs = v->shared ? 0 : (size_t)nz * ni;
         if ((rc = launch_atm_pre(c, (int)rep))) return rc;
         VK_CUDA(cudaStreamSynchronize(c->stream));

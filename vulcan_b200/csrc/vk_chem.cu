@@ -89,6 +89,43 @@ __global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p)
         p.TA[base + i] = TA; p.TB[base + i] = TB; p.TC[base + i] = TC;
         p.SA[base + i] = SA; p.SB[base + i] = SB; p.SC[base + i] = SC;
     }
+    if (threadIdx.x == 0) {
+        // per-layer scalars: [0] A prefactor (rhs form), [1] Kzz[j]/dzi[j], [2] Kzz[j-1]/dzi[j-1], [3] B prefactor (rhs form),
+        // [4] C prefactor (rhs form), [5..7] advection terms added to A, B, C, [8] -1/dz_ave, [9] 1/dz_ave
+        const double *Kzz = L.Kzz, *vz = L.vz;
+        double s[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        if (j == 0) {
+            s[0] = -1. / (dzi[0]) * (Kzz[0] / dzi[0]);
+            s[3] = 1. / (dzi[0]) * (Kzz[0] / dzi[0]);
+            s[5] = -(posv(vz[0])) / dzi[0];
+            s[6] = -(negv(vz[0])) / dzi[0];
+        } else if (j == nz - 1) {
+            const int m = nz - 2;
+            s[0] = -1. / (dzi[m]) * (Kzz[m] / dzi[m]);
+            s[4] = 1. / (dzi[m]) * (Kzz[m] / dzi[m]);
+            s[5] = (negv(vz[m])) / dzi[m];
+            s[7] = (posv(vz[m])) / dzi[m];
+        } else {
+            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
+            s[1] = Kzz[j] / dzi[j];
+            s[2] = Kzz[j - 1] / dzi[j - 1];
+            if (a.use_moldiff) {
+                s[0] = -1. / dz_ave;
+                s[3] = 1. / dz_ave * Kzz[j] / dzi[j];
+                s[4] = 1. / dz_ave * Kzz[j - 1] / dzi[j - 1];
+            } else {   // diffdf_no_mol writes 2./(dzi[j-1]+dzi[j]) (op.py:1474-1476)
+                s[0] = -2. / (dzi[j - 1] + dzi[j]);
+                s[3] = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j] / dzi[j];
+                s[4] = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j - 1] / dzi[j - 1];
+            }
+            s[5] = -(posv(vz[j]) - negv(vz[j - 1])) / dz_ave;
+            s[6] = -(negv(vz[j])) / dz_ave;
+            s[7] = (posv(vz[j - 1])) / dz_ave;
+            s[8] = -1. / dz_ave;
+            s[9] = 1. / dz_ave;
+        }
+        for (int q = 0; q < 10; q++) p.LS[((size_t)col * nz + j) * 10 + q] = s[q];
+    }
 }
 
 int launch_atm_pre(vk_column *c, int ncol_atm)
@@ -175,13 +212,20 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
         }
         rate[i] = v;
     }
-    if (tid >= RHS_NT - 3) {
-        const int q = tid - (RHS_NT - 3);
+    if (tid >= RHS_NT - 32) {      // last warp: the three layer sums, 8 lanes each, numpy association (vk_device_math.cuh)
+        const int lane_ = tid - (RHS_NT - 32), q = lane_ >> 3;
         const int jj = j - 1 + q;
-        if (jj >= 0 && jj < nz) {
-            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-            ysum[q] = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, tmp + q * ni);
+        const bool act = (q < 3) && jj >= 0 && jj < nz;
+        const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+        int n = ni;
+        if (A.atm.n_gas > 0) {     // compact the gas species like the fancy-index copy y[:,gas_indx]
+            n = A.atm.n_gas;
+            if (act) for (int i = (lane_ & 7); i < n; i += 8) tmp[q * ni + i] = row[A.atm.gas_indx[i]];
+            row = tmp + q * ni;
+            __syncwarp();
         }
+        const double sres = np_pairwise_group8(row, n, act);
+        if (act && (lane_ & 7) == 0) ysum[q] = sres;
     }
     __syncthreads();
 
@@ -189,52 +233,53 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
     for (int p = tid; 2 * p + 1 <= nr; p += nt) rate[2 * p + 1] = rate[2 * p + 1] - rate[2 * p + 2];
     const AtmLayer L = atm_at(A.atm, col);
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
-    if (tid == RHS_NT - 1) {
-        const double *dzi = L.dzi, *Kzz = L.Kzz, *vz = L.vz;
+    if (tid >= RHS_NT - 3) {       // three threads: A, B, C of the eddy + advection stencil from the precomputed prefactors
+        const int q = tid - (RHS_NT - 3);
+        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
         const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-        LayerScal s;
-        s.ys0 = ys0; s.ysp = ysp; s.ysm = ysm; s.sp = ysp + ys0; s.sm = ys0 + ysm; s.m1 = 0; s.Aa = s.Bb = s.Cc = 0;
-        if (j == 0) {
-            s.Aa = -1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ys0;
-            s.Bb = 1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / 2. / ysp;
-            s.Aa += -(posv(vz[0])) / dzi[0];
-            s.Bb += -(negv(vz[0])) / dzi[0];
-        } else if (j == nz - 1) {
-            const int m = nz - 2;
-            s.Aa = -1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ys0;
-            s.Cc = 1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ys0 + ysm) / 2. / ysm;
-            s.Aa += (negv(vz[m])) / dzi[m];
-            s.Cc += (posv(vz[m])) / dzi[m];
+        const double sp = ysp + ys0, smm = ys0 + ysm;
+        if (q == 0) {
+            double v;
+            if (j == 0) v = ls[0] * sp / 2. / ys0;
+            else if (j == nz - 1) v = ls[0] * smm / 2. / ys0;
+            else v = ls[0] * (ls[1] * sp / 2. + ls[2] * smm / 2.) / ys0;
+            v += ls[5];
+            S->Aa = v; S->m1 = ls[8]; S->sp = sp; S->sm = smm; S->ys0 = ys0; S->ysp = ysp; S->ysm = ysm;
+        } else if (q == 1) {
+            double v = 0.0;
+            if (j < nz - 1) { v = ls[3] * sp / 2. / ysp; v += ls[6]; }
+            S->Bb = v;
         } else {
-            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
-            if (md) {
-                s.Aa = -1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
-                s.Bb = 1. / dz_ave * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
-                s.Cc = 1. / dz_ave * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
-            } else {   // diffdf_no_mol writes 2./(dzi[j-1]+dzi[j]) (op.py:1474-1476)
-                s.Aa = -2. / (dzi[j - 1] + dzi[j]) * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2.) / ys0;
-                s.Bb = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j] / dzi[j] * (ysp + ys0) / 2. / ysp;
-                s.Cc = 2. / (dzi[j - 1] + dzi[j]) * Kzz[j - 1] / dzi[j - 1] * (ys0 + ysm) / 2. / ysm;
-            }
-            s.Aa += -(posv(vz[j]) - negv(vz[j - 1])) / dz_ave;
-            s.Bb += -(negv(vz[j])) / dz_ave;
-            s.Cc += (posv(vz[j - 1])) / dz_ave;
-            s.m1 = -1. / dz_ave;
+            double v = 0.0;
+            if (j > 0) { v = ls[4] * smm / 2. / ysm; v += ls[7]; }
+            S->Cc = v;
         }
-        *S = s;
     }
     __syncthreads();
 
     // ---- phase 3: chemistry sums (threads 0..ni-1) run beside the transport stencil (threads RHS_TR0..RHS_TR0+ni-1)
     double chem = 0.0;
     if (tid < ni) {
-        // left-to-right sum of coef * v_j in network order (make_chem_funs.py:258-285)
+        // left-to-right sum of coef * v_j in network order (make_chem_funs.py:258-285).  The additions form one dependent
+        // chain (order = parity); descriptors and rates are fetched four terms ahead so that only the DADD latency remains.
         const int q0 = A.net.rhs_ptr[tid], q1 = A.net.rhs_ptr[tid + 1];
-        for (int q = q0; q < q1; q++) {
+        int q = q0;
+        if (q < q1) {
             const int t = A.net.rhs_term[q];
-            const double coef = (double)((signed char)(t & 0xff));
-            const double term = coef * rate[t >> 8];
-            chem = (q == q0) ? term : chem + term;
+            chem = (double)((signed char)(t & 0xff)) * rate[t >> 8];
+            q++;
+        }
+        for (; q + 4 <= q1; q += 4) {
+            const int t0 = A.net.rhs_term[q], t1 = A.net.rhs_term[q + 1], t2 = A.net.rhs_term[q + 2], t3 = A.net.rhs_term[q + 3];
+            const double a0 = (double)((signed char)(t0 & 0xff)) * rate[t0 >> 8];
+            const double a1 = (double)((signed char)(t1 & 0xff)) * rate[t1 >> 8];
+            const double a2 = (double)((signed char)(t2 & 0xff)) * rate[t2 >> 8];
+            const double a3 = (double)((signed char)(t3 & 0xff)) * rate[t3 >> 8];
+            chem = chem + a0; chem = chem + a1; chem = chem + a2; chem = chem + a3;
+        }
+        for (; q < q1; q++) {
+            const int t = A.net.rhs_term[q];
+            chem = chem + (double)((signed char)(t & 0xff)) * rate[t >> 8];
         }
     } else if (tid >= RHS_TR0 && tid < RHS_TR0 + ni) {
         const int i = tid - RHS_TR0;
@@ -324,7 +369,7 @@ struct LhsArgs {
     const unsigned char *fix_mask;
 };
 
-__global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
+__global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
 {
     extern __shared__ double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
@@ -350,13 +395,20 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     for (int i = tid; i <= nr; i += nt) kz[i] = kg[i];
     for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
     __syncthreads();
-    if (tid >= 253) {
-        const int q = tid - 253;
+    if (tid >= 224) {              // last warp: the three layer sums, 8 lanes each, numpy association
+        const int lane_ = tid - 224, q = lane_ >> 3;
         const int jj = j - 1 + q;
-        if (jj >= 0 && jj < nz) {
-            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-            ysum[q] = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, tmp + q * ni);
+        const bool act = (q < 3) && jj >= 0 && jj < nz;
+        const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+        int n = ni;
+        if (A.atm.n_gas_lhs > 0) {
+            n = A.atm.n_gas_lhs;
+            if (act) for (int i = (lane_ & 7); i < n; i += 8) tmp[q * ni + i] = row[A.atm.gas_indx_lhs[i]];
+            row = tmp + q * ni;
+            __syncwarp();
         }
+        const double sres = np_pairwise_group8(row, n, act);
+        if (act && (lane_ & 7) == 0) ysum[q] = sres;
     }
     // ---- chemical Jacobian: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work
     for (int s = tid; s < A.net.n_seg; s += nt) {
@@ -387,11 +439,30 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
     __syncthreads();
     // ---- diagonal: c0 + negJ_ss - transport;  couplings up/dn   (op.py:1998-2040)
     const AtmLayer L = atm_at(A.atm, col);
-    const double *dzi = L.dzi, *Kzz = L.Kzz, *vz = L.vz;
+    const double *dzi = L.dzi;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
     const double rr = 1. + 1. / sqrt(2.);
     const double c0 = 1. / (rr * A.dt[col]);
     const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+    const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+    // species-independent eddy + advection parts (three threads, one division each)
+    if (tid < 3) {
+        double v = 0.0;
+        if (j == 0) {
+            if (tid == 0) v = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
+            if (tid == 1) v = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+        } else if (j == nz - 1) {
+            if (tid == 0) v = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
+            if (tid == 2) v = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+        } else {
+            if (tid == 0) v = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
+            if (tid == 1) v = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
+            if (tid == 2) v = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+        }
+        tmp[tid] = v;
+    }
+    __syncthreads();
+    const double eA = tmp[0], eB = tmp[1], eC = tmp[2];
     const size_t vbase = ((size_t)col * nz + j) * ld;
     const AtmPre &P = A.atm.pre;
     for (int i = tid; i < ld; i += nt) {
@@ -405,8 +476,8 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
         double d = c0 + blk[i * ld + i];
         double u = 0.0, l = 0.0;
         if (j == 0) {
-            d -= -1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / (2. * ys0) - (posv(vz[0])) / dzi[0];
-            u -= 1. / (dzi[0]) * (Kzz[0] / dzi[0]) * (ysp + ys0) / (2. * ysp) - (negv(vz[0])) / dzi[0];
+            d -= eA;
+            u -= eB;
             if (md) {
                 double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
                 double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
@@ -421,9 +492,8 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
                 if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
             }
         } else if (j == nz - 1) {
-            const int m = nz - 2;
-            d -= -1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ysm + ys0) / (2. * ys0) + (negv(vz[m])) / dzi[m];
-            l -= 1. / (dzi[m]) * (Kzz[m] / dzi[m]) * (ysm + ys0) / (2. * ysm) + (posv(vz[m])) / dzi[m];
+            d -= eA;
+            l -= eC;
             if (md) {
                 double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
                 double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
@@ -435,15 +505,13 @@ __global__ void __launch_bounds__(256) lhs_kernel(LhsArgs A)
                 l -= tc;
             }
         } else {
-            double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
-            d -= -1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / 2. + Kzz[j - 1] / dzi[j - 1] * (ysm + ys0) / 2.) / ys0 -
-                 (posv(vz[j]) - negv(vz[j - 1])) / dz_ave;
-            u -= 1. / dz_ave * (Kzz[j] / dzi[j] * (ysp + ys0) / (2. * ysp)) - (negv(vz[j])) / dz_ave;
-            l -= 1. / dz_ave * (Kzz[j - 1] / dzi[j - 1] * (ysm + ys0) / (2. * ysm)) + (posv(vz[j - 1])) / dz_ave;
+            d -= eA;
+            u -= eB;
+            l -= eC;
             if (md) {
-                double ta = -1. / dz_ave * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
-                double tb = 1. / dz_ave * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
-                double tc = 1. / dz_ave * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
+                double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
+                double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
+                double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
                 if (st) {
                     ta = ta - P.SA[pb];
                     tb = tb - P.SB[pb];

@@ -40,6 +40,32 @@ static __device__ __forceinline__ double row_sum(const double *yrow, int ni, int
     return np_pairwise(yrow, ni);
 }
 
+// warp-cooperative version of row_sum for up to 4 rows at once: lanes 8*q .. 8*q+7 reduce row q with numpy's 8 accumulators
+// (identical association: r_m = a[m] + a[8+m] + ..., ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail sequentially).
+// n <= 128.  Call with all 32 lanes; returns the sum of row (lane >> 3) in every lane of that group.
+static __device__ __forceinline__ double np_pairwise_group8(const double *a, int n, bool active)
+{
+    const int m = threadIdx.x & 7;
+    double r = 0.0, res;
+    if (n < 8) {
+        res = 0.;
+        if (active) for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    const int nb = n - (n % 8);
+    if (active) {
+        r = a[m];
+        for (int i = 8; i < nb; i += 8) r += a[i + m];
+    }
+    // ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) : butterfly over the 8 lanes of the group keeps exactly this association
+    r = r + __shfl_xor_sync(0xffffffffu, r, 1);
+    r = r + __shfl_xor_sync(0xffffffffu, r, 2);
+    r = r + __shfl_xor_sync(0xffffffffu, r, 4);
+    res = r;
+    if (active) for (int i = nb; i < n; i++) res += a[i];
+    return res;
+}
+
 static __device__ __forceinline__ double posv(double v) { return (v > 0) ? v : 0.0 * v; }  // (v>0)*v
 static __device__ __forceinline__ double negv(double v) { return (v < 0) ? v : 0.0 * v; }  // (v<0)*v
 

@@ -44,6 +44,7 @@ struct NetDev {
 // atmosphere-only pieces of the transport stencil, [ncol_atm][nz][ni] each (see atm_pre_kernel)
 struct AtmPre {
     double *Q, *QB, *QC, *TA, *TB, *TC, *SA, *SB, *SC;
+    double *LS;                 // [ncol_atm][nz][10] per-layer scalars (eddy / advection prefactors)
 };
 
 // ---- transport view on the device -------------------------------------------------------------------------------

@@ -54,7 +54,7 @@ def synthetic_columns(y_base, n_0, compo, atom_names, kzz_scale, met_scale, c_to
 class EnsembleRunner(object):
     """The columns [lo, hi) of an ensemble resident on one GPU, advanced by the device-resident controller."""
 
-    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=1):
+    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=0):
         self.ncol = y.shape[0]
         self.devnet = _abi.DeviceNetwork(network, device)
         self.col = _abi.Columns(self.devnet, nz, self.ncol)

@@ -17,7 +17,7 @@ _DYN_ATM = ("Kzz", "vz", "dzi", "Dzz", "vs", "Tco", "g", "M", "Ti", "Hpi", "ms",
 
 
 class Ros2(object):
-    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=1, network=None):
+    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=0, network=None):
         """cfg: the vulcan_cfg module (imported like the reference does when omitted); species: chem_funs.spec_list
         (only used to cross-check the network compiler's species order); compo: {species: {atom: n}} or an
         [ni][na] array for `loss` (read from cfg.com_file when omitted)."""
