@@ -29,27 +29,35 @@ __device__ __forceinline__ double fast_rcp(double x)
 }
 
 // Register layout: warp w owns the 8 columns [8w, 8w+8) of the block and ALL its rows, in the m8n8 accumulator-fragment
-// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1 (the layout of
-// mma.sync.m8n8k4.f64 accumulators).
+// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1 - the C/D layout
+// of mma.sync.m8n8k4.f64 (DMMA), so a tile of the matrix is directly a DMMA accumulator.
 //
-// Pivoting: DIAGONAL pivots.  Measured on the reference's own matrices (tests + DESIGN.md §4.1): for these systems
-// (1/(r h) I - J with loss terms on the diagonal; species abundances spanning 30+ decades so that rows carry wildly
-// different scales) Gauss-Jordan on the diagonal is 2-5 orders of magnitude MORE accurate than LAPACK-style partial pivoting,
-// which lets the largest entry of a column - a scale artefact - destroy componentwise accuracy.  A zero / non-finite pivot
-// sets VK_ERR_SINGULAR for the column: the step is rejected and retried with dt/2 exactly like any other failed step.
+// Algorithm: BLOCKED in-place Gauss-Jordan inversion with 8-wide panels on the FP64 tensor pipe.  For panel K (rows and
+// columns 8kt .. 8kt+7), with P = A_KK^{-1}:
+//     columns outside the panel (warp w != kt):   V = P A_Kw ;  A_Kw <- V ;  A_iw <- A_iw - A_iK V     (i != kt)
+//     panel columns (owner warp kt):              A_iK <- -A_iK P  (i != kt) ;  A_KK <- P
+// i.e. per panel and warp 2 + 2(NR-1) DMMAs instead of 8 x 2 NR DFMAs, ONE __syncthreads per 8 pivots instead of 8, and
+// NR 16-byte shared-memory loads instead of 8 NR.  Only two things cross warps: the RAW panel columns A_iK (published by
+// the owner right after its own update of the previous panel - before the inversion, so off the critical path) and the
+// 8 x 8 inverse P.  The k index of the m8n8k4 shape is mapped slot t <-> panel index 2t+s (s = which of the two k4 steps), so
+// that the A operand of every product is exactly the (x, y) pair a lane already holds / loads with one LDS.128.
 //
-// With the pivot row known in advance the per-pivot work is: owner warp (k/8) forms the multipliers a_rk / a_kk of its column
-// and publishes them (double-buffered shared memory); ONE __syncthreads; every warp: 9 LDS + pivot-row broadcast by warp
-// shuffle from a compile-time register (the k loop is unrolled over the row tile) + 18 FMAs.  Pivot-row scaling is deferred to
-// the end of the layer, so the inverse W_j stays in registers in its natural layout: the Schur update of the next layer
-// (elementwise, the couplings are diagonal), the write-out and the fused forward elimination all work from registers.
+// Pivoting: DIAGONAL pivots inside the 8 x 8 panel inverse (in-warp Gauss-Jordan with shuffles).  Measured on the
+// reference's own matrices (tests + DESIGN.md §4.1): for these systems (1/(r h) I - J with the loss terms on the diagonal;
+// abundances spanning 30+ decades so that rows carry wildly different scales) elimination on the diagonal is 2-5 orders of
+// magnitude MORE accurate than LAPACK-style partial pivoting, which lets the largest entry of a column - a scale artefact -
+// destroy componentwise accuracy.  A zero / non-finite pivot sets VK_ERR_SINGULAR for the column: the step is rejected and
+// retried with dt/2 exactly like any other failed step.
+//
+// Look-ahead: the NEXT owner (warp kt+1) updates its diagonal tile first and then interleaves the 8 dependent pivot steps
+// of the 8 x 8 inverse (shuffle -> 1/x -> multiply -> FMA, ~115 clk each) with the DMMAs of its remaining tiles.
 template <int NIP>
 struct FactorCfg {
     static constexpr int NW = NIP / 8;           // warps
-    static constexpr int NR = NIP / 8;           // rows per lane
+    static constexpr int NR = NIP / 8;           // row tiles per lane
     static constexpr int NT = NW * 32;
-    // lbuf[2][NIP] + rscale[NIP] + tvec[NIP] + zpart[NW][NIP] (doubles)
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)(4 + NW) * NIP);
+    // mraw[2][NIP][8] + pbuf[2][64] + tvec[NIP] + zpart[NW][NIP] (doubles)
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)16 * NIP + 128 + NIP + (size_t)NW * NIP);
 };
 
 struct FactorArgs {
@@ -63,12 +71,47 @@ struct FactorArgs {
     double *z;           // [ncol][nz][NIP]
 };
 
-#ifdef VK_TRACE
-__device__ long long g_trace[128 * 8];
-#define TRACE(kk, ev) do { if (j == 5 && (kk) < 128 && lane == 0) g_trace[(kk) * 8 + (ev)] = clock64(); } while (0)
-#else
-#define TRACE(kk, ev) do { } while (0)
-#endif
+// D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor pipe: lane 4g+t supplies A[g][t], B[t][g], C[g][2t..2t+1]
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b, double c0, double c1)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// tile in accumulator layout (x0 = T[g][2t], x1 = T[g][2t+1])  ->  B fragments of the two k4 steps, b_s = T[2t+s][g]
+__device__ __forceinline__ void to_bfrag(double x0, double x1, int g, int t, double &b0, double &b1)
+{
+    const int s0 = (t << 3) | (g >> 1), s1 = s0 + 4;      // lanes (2t, g>>1) and (2t+1, g>>1)
+    const double p0 = __shfl_sync(0xffffffffu, x0, s0), p1 = __shfl_sync(0xffffffffu, x1, s0);
+    const double q0 = __shfl_sync(0xffffffffu, x0, s1), q1 = __shfl_sync(0xffffffffu, x1, s1);
+    b0 = (g & 1) ? p1 : p0;
+    b1 = (g & 1) ? q1 : q0;
+}
+
+// one pivot step P (compile time) of the in-warp 8 x 8 Gauss-Jordan inverse on an accumulator-layout tile
+template <int P>
+__device__ __forceinline__ void gj8_step(double &x0, double &x1, int g, int t, int &bad)
+{
+    constexpr int HP = P >> 1, E = P & 1;
+    const double mine = E ? x1 : x0;
+    const double piv = __shfl_sync(0xffffffffu, mine, (P << 2) | HP);     // a[P][P]
+    const double cp = __shfl_sync(0xffffffffu, mine, (g << 2) | HP);      // a[g][P]
+    const double r0 = __shfl_sync(0xffffffffu, x0, (P << 2) | t);         // a[P][2t]
+    const double r1 = __shfl_sync(0xffffffffu, x1, (P << 2) | t);         // a[P][2t+1]
+    const double rinv = fast_rcp(piv);
+    if (!(fabs(piv) > 0.0) || !(fabs(piv) < 1.0e300)) bad = 1;
+    if (g == P) {
+        x0 = r0 * rinv;
+        x1 = r1 * rinv;
+        if (t == HP) { if (E) x1 = rinv; else x0 = rinv; }
+    } else {
+        const double m = -cp * rinv;
+        x0 = fma(m, r0, x0);
+        x1 = fma(m, r1, x1);
+        if (t == HP) { if (E) x1 = m; else x0 = m; }
+    }
+}
 
 template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
@@ -76,10 +119,10 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     using C = FactorCfg<NIP>;
     constexpr int NR = C::NR, NW = C::NW;
     extern __shared__ __align__(16) double smem[];
-    double *lbuf = smem;                 // 2 x NIP   multipliers of pivot step k (double buffered)
-    double *rscale = lbuf + 2 * NIP;     // NIP       1/pivot of every row (deferred pivot-row scaling)
-    double *tvec = rscale + NIP;         // NIP       r_j - dn_j * z_{j-1}
-    double *zpart = tvec + NIP;          // NW x NIP  per-warp partial sums of W_j tvec
+    double *mraw = smem;                 // 2 x NIP x 8   raw panel columns A_iK (double buffered by panel parity)
+    double *pbuf = mraw + 16 * NIP;      // 2 x 64        P = A_KK^{-1}
+    double *tvec = pbuf + 128;           // NIP           r_j - dn_j * z_{j-1}
+    double *zpart = tvec + NIP;          // NW x NIP      per-warp partial sums of W_j tvec
 
     const int col = blockIdx.x;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -96,6 +139,17 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     double *zc = fuse ? a.z + (size_t)col * nz * NIP : nullptr;
     double zreg = 0.0;                   // z_{j-1}[tid] for tid < NIP
     int bad = 0;
+    double px0 = 0.0, px1 = 0.0;         // the panel inverse held by its owner across the barrier
+
+    // owner of panel KT: publish the raw panel columns, invert the diagonal tile, publish P
+    auto publish_raw = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < NR; i++)
+            *reinterpret_cast<double2 *>(mraw + ((size_t)buf * NIP + 8 * i + g) * 8 + 2 * t) = make_double2(A[i][0], A[i][1]);
+    };
+    auto publish_p = [&](int buf) {
+        *reinterpret_cast<double2 *>(pbuf + buf * 64 + g * 8 + 2 * t) = make_double2(px0, px1);
+    };
 
     for (int j = 0; j < nz; j++) {
         // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}); W_{j-1} is still in A
@@ -121,90 +175,105 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             const double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
             tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zreg;
         }
-        if (tid < NIP) rscale[tid] = 1.0;
-        // ---- Gauss-Jordan on the diagonal.  lbuf holds the NEGATED multipliers -a_rk/a_kk (0 in the pivot row); they are
-        // also the new column k of the transformed block (with 1 in the pivot row, which stays unscaled until write-out).
-        // PUBLISH(KT, G, E, H, CB): the warp owning column 8*KT+G (plane E of lane pair H) forms and publishes them.
-#define VK_PUBLISH(KT, G, E, H, CB)                                                                                    \
-        {                                                                                                              \
-            const double dkk = __shfl_sync(0xffffffffu, A[KT][E], ((G) << 2) | (H));                                   \
-            const double ninv = -fast_rcp(dkk);                                                                        \
-            if (!(fabs(dkk) > 0.0)) bad = 1;                                                                           \
-            if (t == (H)) {                                                                                            \
-                _Pragma("unroll") for (int i = 0; i < NR; i++) {                                                       \
-                    A[i][E] = A[i][E] * ninv;                                                                          \
-                    if (i == (KT)) { if (g == (G)) A[i][E] = 0.0; }                                                    \
-                    lbuf[(CB) * NIP + 8 * i + g] = A[i][E];                                                            \
-                }                                                                                                      \
-                if (g == (G)) { A[KT][E] = 1.0; rscale[8 * (KT) + (G)] = -ninv; }                                      \
-            }                                                                                                          \
+        if (w == 0) {
+            publish_raw(0);
+            px0 = A[0][0]; px1 = A[0][1];
+            gj8_step<0>(px0, px1, g, t, bad); gj8_step<1>(px0, px1, g, t, bad); gj8_step<2>(px0, px1, g, t, bad);
+            gj8_step<3>(px0, px1, g, t, bad); gj8_step<4>(px0, px1, g, t, bad); gj8_step<5>(px0, px1, g, t, bad);
+            gj8_step<6>(px0, px1, g, t, bad); gj8_step<7>(px0, px1, g, t, bad);
+            publish_p(0);
         }
-        if (w == 0) VK_PUBLISH(0, 0, 0, 0, 0)
-        // one row tile of pivots; KT and the plane E are compile-time constants so that A[KT][E] is a register
-        auto pivot_tile = [&](auto ktc) {
+        auto panel = [&](auto ktc) {
             constexpr int kt = decltype(ktc)::value;
-            constexpr int ktn = (kt + 1 < NR) ? kt + 1 : kt;
-            for (int h = 0; h < 4; h++) {
-                // ---------------- pivot k = 8 kt + 2 h (plane 0); the next column is plane 1 of the same lane pair
-                {
-                    const int k = 8 * kt + 2 * h;
-                    if (k >= ni) break;
-                    __syncthreads();                              // multipliers of step k visible (buffer 0: k is even)
-                    double nl[NR];
+            constexpr int buf = kt & 1;
+            __syncthreads();                              // raw panel columns + P of panel kt visible
+            if (w == kt) {
+                // ---- panel columns: A_iK <- -A_iK P, A_KK <- P.  A operand = my own (x, y) pair, B operand = -P
+                double b0, b1;
+                to_bfrag(px0, px1, g, t, b0, b1);
+                b0 = -b0; b1 = -b1;
 #pragma unroll
-                    for (int i = 0; i < NR; i++) nl[i] = lbuf[8 * i + g];
-                    const int src = ((2 * h) << 2) | t;
-                    const double pr1 = __shfl_sync(0xffffffffu, A[kt][1], src);
-                    double pr0 = __shfl_sync(0xffffffffu, A[kt][0], src);
-                    if (w == kt && t == h) pr0 = 0.0;             // column k itself is final
-#pragma unroll
-                    for (int i = 0; i < NR; i++) A[i][1] = fma(nl[i], pr1, A[i][1]);
-                    if (w == kt && k + 1 < ni) VK_PUBLISH(kt, 2 * h + 1, 1, h, 1)
-#pragma unroll
-                    for (int i = 0; i < NR; i++) A[i][0] = fma(nl[i], pr0, A[i][0]);
+                for (int i = 0; i < NR; i++) {
+                    if (i == kt) continue;
+                    double d0, d1;
+                    dmma(d0, d1, A[i][0], b0, 0.0, 0.0);
+                    dmma(A[i][0], A[i][1], A[i][1], b1, d0, d1);
                 }
-                // ---------------- pivot k = 8 kt + 2 h + 1 (plane 1); the next column is plane 0 of the next lane pair / tile
-                {
-                    const int k = 8 * kt + 2 * h + 1;
-                    if (k >= ni) break;
-                    __syncthreads();                              // buffer 1: k is odd
-                    double nl[NR];
+                A[kt][0] = px0; A[kt][1] = px1;
+            } else {
+                // ---- V = P A_Kw (new pivot rows of my columns)
+                double u0, u1;
+                to_bfrag(A[kt][0], A[kt][1], g, t, u0, u1);
+                const double2 pa = *reinterpret_cast<const double2 *>(pbuf + buf * 64 + g * 8 + 2 * t);
+                double v0, v1;
+                dmma(v0, v1, pa.x, u0, 0.0, 0.0);
+                dmma(v0, v1, pa.y, u1, v0, v1);
+                A[kt][0] = v0; A[kt][1] = v1;
+                double nv0, nv1;
+                to_bfrag(v0, v1, g, t, nv0, nv1);
+                nv0 = -nv0; nv1 = -nv1;
+                const double *mr = mraw + ((size_t)buf * NIP + g) * 8 + 2 * t;
+                auto upd = [&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
+                    dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
+                    dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
+                };
+                auto generic = [&]() {
 #pragma unroll
-                    for (int i = 0; i < NR; i++) nl[i] = lbuf[NIP + 8 * i + g];
-                    const int src = ((2 * h + 1) << 2) | t;
-                    const double pr0 = __shfl_sync(0xffffffffu, A[kt][0], src);
-                    double pr1 = __shfl_sync(0xffffffffu, A[kt][1], src);
-                    if (w == kt && t == h) pr1 = 0.0;             // column k itself is final
-#pragma unroll
-                    for (int i = 0; i < NR; i++) A[i][0] = fma(nl[i], pr0, A[i][0]);
-                    if (k + 1 < ni) {
-                        if (h < 3) { if (w == kt) VK_PUBLISH(kt, 2 * h + 2, 0, h + 1, 0) }
-                        else if (kt + 1 < NR) { if (w == ktn) VK_PUBLISH(ktn, 0, 0, 0, 0) }
+                    for (int i = 0; i < NR; i++) {
+                        if (i == kt) continue;
+                        const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
+                        dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
+                        dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
                     }
-#pragma unroll
-                    for (int i = 0; i < NR; i++) A[i][1] = fma(nl[i], pr1, A[i][1]);
+                };
+                if constexpr (kt + 1 < NR) {
+                    if (w == kt + 1) {
+                        // ---- next owner: diagonal tile first, then the 8 dependent pivot steps interleaved with the other tiles
+                        constexpr int kn = kt + 1;
+                        upd(std::integral_constant<int, kn>{});
+                        px0 = A[kn][0]; px1 = A[kn][1];
+                        constexpr int NO = NR - 2;              // tiles other than kt and kn, in a fixed order
+                        static_assert(NO <= 16, "panel look-ahead schedule covers at most 18 row tiles");
+                        auto other = [&](auto qc) {
+                            constexpr int q = decltype(qc)::value;
+                            if constexpr (q < NO) {
+                                constexpr int i = (q < kt) ? q : q + 2;
+                                upd(std::integral_constant<int, i>{});
+                            }
+                        };
+#define VK_GJ(PP)                                                                                                      \
+                        gj8_step<PP>(px0, px1, g, t, bad);                                                             \
+                        other(std::integral_constant<int, 2 * (PP)>{});                                                \
+                        other(std::integral_constant<int, 2 * (PP) + 1>{});
+                        VK_GJ(0) VK_GJ(1) VK_GJ(2) VK_GJ(3) VK_GJ(4) VK_GJ(5) VK_GJ(6) VK_GJ(7)
+#undef VK_GJ
+                        publish_raw(kn & 1);
+                        publish_p(kn & 1);
+                    } else {
+                        generic();
+                    }
+                } else {
+                    generic();
                 }
             }
         };
-#define VK_TILE(N) if constexpr ((N) < NR) { if (8 * (N) < ni) pivot_tile(std::integral_constant<int, (N)>{}); }
-        VK_TILE(0) VK_TILE(1) VK_TILE(2) VK_TILE(3) VK_TILE(4) VK_TILE(5) VK_TILE(6) VK_TILE(7)
-        VK_TILE(8) VK_TILE(9) VK_TILE(10) VK_TILE(11) VK_TILE(12) VK_TILE(13) VK_TILE(14)
-#undef VK_TILE
-#undef VK_PUBLISH
+#define VK_PANEL(N) if constexpr ((N) < NR) panel(std::integral_constant<int, (N)>{});
+        VK_PANEL(0) VK_PANEL(1) VK_PANEL(2) VK_PANEL(3) VK_PANEL(4) VK_PANEL(5) VK_PANEL(6) VK_PANEL(7)
+        VK_PANEL(8) VK_PANEL(9) VK_PANEL(10) VK_PANEL(11) VK_PANEL(12) VK_PANEL(13) VK_PANEL(14)
+#undef VK_PANEL
         if (__syncthreads_or(bad)) {
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
             return;
         }
-        // ---- W_j = diag(rscale) A : stays in registers for the next layer; written out; fused forward elimination
+        // ---- W_j = A : stays in registers for the next layer; written out; fused forward elimination
         double *Wj = Wc + (size_t)j * NIP * NIP;
         double tv0 = 0.0, tv1 = 0.0;
         if (fuse) { tv0 = tvec[c0]; tv1 = tvec[c0 + 1]; }
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int r = 8 * i + g;
-            const double sc = rscale[r];
-            A[i][0] *= sc;
-            A[i][1] *= sc;
             *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c0) = make_double2(A[i][0], A[i][1]);
             if (fuse) {
                 double part = fma(A[i][0], tv0, A[i][1] * tv1);
@@ -221,7 +290,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             zreg = acc;
             zc[(size_t)j * NIP + tid] = acc;
         }
-        // (the next layer's first __syncthreads orders the zpart / tvec / rscale reuse)
+        // (the next layer's first __syncthreads orders the zpart / tvec reuse)
     }
 }
 
