@@ -1,4 +1,4 @@
-"""VK_TRACE=1 python scripts/trace_factor.py : per-pivot-step timeline (clock64) of layer 5 of a single-column factorisation."""
+"""VK_TRACE=1 python scripts/trace_factor.py : per-panel timeline (clock64) of layer 5 of a single-column factorisation."""
 import os, sys, ctypes
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
@@ -13,9 +13,10 @@ for _ in range(2):
 buf = (ctypes.c_longlong * (128 * 8))()
 _abi.load().vk_debug_trace(buf)
 t = np.array(buf[:], dtype=np.int64).reshape(128, 8)
-names = ["own:after_bar", "own:fma_done", "own:inv_ready", "own:published", "w8:step_done"]
-print("step  " + "  ".join("%-16s" % n for n in names) + "  step_total")
-for k in range(20, 44):
+L = t[100]
+print("layer: start 0 | schur done %d | P0 published %d | panels done %d | layer end %d" % tuple(L[1:5] - L[0]))
+names = ["next:after_bar", "next:V+bfrag", "next:diag_upd", "next:gj_done", "next:published", "generic:done", "owner:done"]
+print("panel " + "  ".join("%-15s" % n for n in names) + "  panel_total")
+for k in range(9):
     base = t[k, 0]
-    print("%4d  " % k + "  ".join("%-16d" % (t[k, e] - base) for e in range(5)) + "  %d" % (t[k + 1, 0] - t[k, 0]))
-d = np.diff(t[8:64, 0]); print("mean cycles/step", d.mean(), "min", d.min(), "max", d.max())
+    print("%4d  " % k + "  ".join("%-15d" % (t[k, e] - base) for e in range(7)) + "  %d" % ((t[k + 1, 0] if k < 8 else L[3]) - t[k, 0]))

@@ -4,11 +4,9 @@
 // scaling of the previous inverse:
 //     S_0 = D_0,   S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}),   W_j = S_j^{-1}
 //     z_j = W_j (r_j - dn_j * z_{j-1}),   x_{nz-1} = z_{nz-1},   x_j = z_j - W_j (up_j * x_{j+1})
-// One thread block per column marches over the layers.  W_j is formed by in-register Gauss-Jordan elimination with
-// partial (row) pivoting inside the block: the NIP x NIP matrix lives in registers in the m8n8 accumulator-fragment
-// layout (lane = 4*g + t holds rows 8*tile+g, columns 8*tile+2t,2t+1), pivot row / column are broadcast through
-// shared memory, the pivot search is a warp REDUX over the candidate column.  The factor is stored once (W_j) and reused
-// for the second Ros2 stage and for iterative refinement - the reference factorises twice.
+// One thread block per column marches over the layers.  W_j is formed by blocked in-register Gauss-Jordan inversion on the
+// FP64 tensor pipe (see factor_kernel).  The factor is stored once (W_j) and reused for the second Ros2 stage and for
+// iterative refinement - the reference factorises twice.
 #include <type_traits>
 
 #include "vk_internal.cuh"
@@ -28,36 +26,40 @@ __device__ __forceinline__ double fast_rcp(double x)
     return r;
 }
 
-// Register layout: warp w owns the 8 columns [8w, 8w+8) of the block and ALL its rows, in the m8n8 accumulator-fragment
-// pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1 - the C/D layout
-// of mma.sync.m8n8k4.f64 (DMMA), so a tile of the matrix is directly a DMMA accumulator.
+// Register layout: column warp w (< NW) owns the 8 columns [8w, 8w+8) of the block and ALL its rows, in the m8n8
+// accumulator-fragment pattern stacked vertically: lane = 4*g + t holds rows 8*i + g (i < NIP/8) and columns 8w + 2t, 8w + 2t + 1
+// - the C/D layout of mma.sync.m8n8k4.f64 (DMMA), so a tile of the matrix is directly a DMMA accumulator.
 //
 // Algorithm: BLOCKED in-place Gauss-Jordan inversion with 8-wide panels on the FP64 tensor pipe.  For panel K (rows and
 // columns 8kt .. 8kt+7), with P = A_KK^{-1}:
 //     columns outside the panel (warp w != kt):   V = P A_Kw ;  A_Kw <- V ;  A_iw <- A_iw - A_iK V     (i != kt)
-//     panel columns (owner warp kt):              A_iK <- -A_iK P  (i != kt) ;  A_KK <- P
-// i.e. per panel and warp 2 + 2(NR-1) DMMAs instead of 8 x 2 NR DFMAs, ONE __syncthreads per 8 pivots instead of 8, and
-// NR 16-byte shared-memory loads instead of 8 NR.  Only two things cross warps: the RAW panel columns A_iK (published by
-// the owner right after its own update of the previous panel - before the inversion, so off the critical path) and the
-// 8 x 8 inverse P.  The k index of the m8n8k4 shape is mapped slot t <-> panel index 2t+s (s = which of the two k4 steps), so
-// that the A operand of every product is exactly the (x, y) pair a lane already holds / loads with one LDS.128.
+//     panel columns (warp kt):                    A_iK <- -A_iK P  (i != kt) ;  A_KK <- P
+// i.e. per panel and warp 2 + 2(NR-1) DMMAs instead of 8 x 2 NR DFMAs, one barrier per 8 pivots instead of 8, and NR 16-byte
+// shared-memory loads instead of 8 NR.  Only two things cross warps: the RAW panel columns A_iK and the 8 x 8 inverse P.
+// The k index of the m8n8k4 shape is mapped slot t <-> panel index 2t+s (s = which of the two k4 steps), so that the A
+// operand of every product is exactly the (x, y) pair a lane already holds / loads with one LDS.128.
 //
-// Pivoting: DIAGONAL pivots inside the 8 x 8 panel inverse (in-warp Gauss-Jordan with shuffles).  Measured on the
-// reference's own matrices (tests + DESIGN.md §4.1): for these systems (1/(r h) I - J with the loss terms on the diagonal;
-// abundances spanning 30+ decades so that rows carry wildly different scales) elimination on the diagonal is 2-5 orders of
-// magnitude MORE accurate than LAPACK-style partial pivoting, which lets the largest entry of a column - a scale artefact -
-// destroy componentwise accuracy.  A zero / non-finite pivot sets VK_ERR_SINGULAR for the column: the step is rejected and
-// retried with dt/2 exactly like any other failed step.
+// Warp specialisation: the 8 dependent pivot steps of the 8 x 8 inverse (shuffle -> 1/x -> multiply -> FMA, ~115 clk each) are
+// the critical chain of a panel.  A warp that also carries DMMAs issues in order and is held up whenever the tensor pipe of
+// its sub-partition is busy with the other warps' updates, so the inverse runs on a DEDICATED warp (warp NW) that owns no
+// columns: warp kt+1 updates its diagonal tile first, hands it over through shared memory (named barrier, 64 threads), goes on
+// with its other tiles and publishes its raw columns; the inverse warp publishes P and ARRIVES on the panel barrier that the
+// column warps wait on.  The next layer's D block and couplings are prefetched into shared memory by 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier) issued one panel into the current layer.
 //
-// Look-ahead: the NEXT owner (warp kt+1) updates its diagonal tile first and then interleaves the 8 dependent pivot steps
-// of the 8 x 8 inverse (shuffle -> 1/x -> multiply -> FMA, ~115 clk each) with the DMMAs of its remaining tiles.
+// Pivoting: DIAGONAL pivots inside the 8 x 8 panel inverse.  Measured on the reference's own matrices (tests + DESIGN.md
+// §4.1): for these systems (1/(r h) I - J with the loss terms on the diagonal; abundances spanning 30+ decades so that rows
+// carry wildly different scales) elimination on the diagonal is 2-5 orders of magnitude MORE accurate than LAPACK-style
+// partial pivoting, which lets the largest entry of a column - a scale artefact - destroy componentwise accuracy.  A zero /
+// non-finite pivot sets VK_ERR_SINGULAR for the column: the step is rejected and retried with dt/2 like any failed step.
 template <int NIP>
 struct FactorCfg {
-    static constexpr int NW = NIP / 8;           // warps
+    static constexpr int NW = NIP / 8;           // column warps
     static constexpr int NR = NIP / 8;           // row tiles per lane
-    static constexpr int NT = NW * 32;
-    // mraw[2][NIP][8] + pbuf[2][64] + tvec[NIP] + zpart[NW][NIP] (doubles)
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)16 * NIP + 128 + NIP + (size_t)NW * NIP);
+    static constexpr int NT = (NW + 1) * 32;     // + the panel-inverse warp
+    // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[2][64] + dtile[2][64] + tvec[NIP] + zpart[NW][NIP] + mbarrier
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 256 + NIP + (size_t)NW * NIP + 2);
+    static constexpr unsigned TX_BYTES = (unsigned)(sizeof(double) * ((size_t)NIP * NIP + 2 * NIP));
 };
 
 struct FactorArgs {
@@ -113,56 +115,136 @@ __device__ __forceinline__ void gj8_step(double &x0, double &x1, int g, int t, i
     }
 }
 
+// named barriers (id 0 is __syncthreads): producer/consumer hand-offs between the column warps and the inverse warp
+template <int ID, int NTHREADS>
+__device__ __forceinline__ void bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
+template <int ID, int NTHREADS>
+__device__ __forceinline__ void bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "VK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra VK_DONE_%=;\n"
+        "bra VK_WAIT_%=;\n"
+        "VK_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, void *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#ifdef VK_TRACE
+__device__ long long g_trace[128 * 8];
+#define TRACE(kk, ev, dep) do { if (j == 5 && lane == 0) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "d"(dep)); g_trace[(kk) * 8 + (ev)] = c_; } } while (0)
+#else
+#define TRACE(kk, ev, dep) do { } while (0)
+#endif
+
+enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3 };   // + panel parity
+
 template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
 {
     using C = FactorCfg<NIP>;
-    constexpr int NR = C::NR, NW = C::NW;
-    extern __shared__ __align__(16) double smem[];
-    double *mraw = smem;                 // 2 x NIP x 8   raw panel columns A_iK (double buffered by panel parity)
+    constexpr int NR = C::NR, NW = C::NW, NT = C::NT;
+    extern __shared__ __align__(128) double smem[];
+    double *dbuf = smem;                 // NIP x NIP     D_j (TMA destination)
+    double *updn = dbuf + NIP * NIP;     // 2 x NIP       up_{j-1}, dn_j (TMA destination)
+    double *mraw = updn + 2 * NIP;       // 2 x NIP x 8   raw panel columns A_iK (double buffered by panel parity)
     double *pbuf = mraw + 16 * NIP;      // 2 x 64        P = A_KK^{-1}
-    double *tvec = pbuf + 128;           // NIP           r_j - dn_j * z_{j-1}
+    double *dtile = pbuf + 128;          // 2 x 64        diagonal tile handed to the inverse warp
+    double *tvec = dtile + 128;          // NIP           r_j - dn_j * z_{j-1}
     double *zpart = tvec + NIP;          // NW x NIP      per-warp partial sums of W_j tvec
+    void *mbar = zpart + NW * NIP;       // mbarrier of the TMA prefetch
 
     const int col = blockIdx.x;
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int ni = a.ni, nz = a.nz;
-    const int c0 = 8 * w + 2 * t;        // my columns c0, c0+1 ; my rows 8*i + g
-
-    double A[NR][2];
-    const double *Dc = a.D + (size_t)col * nz * NIP * NIP;
-    const double *upc = a.up + (size_t)col * nz * NIP;
-    const double *dnc = a.dn + (size_t)col * nz * NIP;
-    double *Wc = a.W + (size_t)col * nz * NIP * NIP;
+    const size_t cbase = (size_t)col * nz;
     const bool fuse = a.rhs != nullptr;
-    const double *rc = fuse ? a.rhs + (size_t)col * nz * ni : nullptr;
-    double *zc = fuse ? a.z + (size_t)col * nz * NIP : nullptr;
-    double zreg = 0.0;                   // z_{j-1}[tid] for tid < NIP
     int bad = 0;
-    double px0 = 0.0, px1 = 0.0;         // the panel inverse held by its owner across the barrier
 
-    // owner of panel KT: publish the raw panel columns, invert the diagonal tile, publish P
+    auto prefetch = [&](int j) {         // one thread: D_j, up_{j-1}, dn_j -> shared memory
+        mbar_expect_tx(mbar, (j > 0) ? C::TX_BYTES : (unsigned)(sizeof(double) * NIP * NIP));
+        tma_load_1d(dbuf, a.D + (cbase + j) * NIP * NIP, (unsigned)(sizeof(double) * NIP * NIP), mbar);
+        if (j > 0) {
+            tma_load_1d(updn, a.up + (cbase + j - 1) * NIP, (unsigned)(sizeof(double) * NIP), mbar);
+            tma_load_1d(updn + NIP, a.dn + (cbase + j) * NIP, (unsigned)(sizeof(double) * NIP), mbar);
+        }
+    };
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) prefetch(0);
+
+    if (w == NW) {
+        // ================= panel-inverse warp =================
+        for (int j = 0; j < nz; j++) {
+            auto invert = [&](auto bufc) {
+                constexpr int buf = decltype(bufc)::value;
+                bar_sync<VK_BAR_TILE + buf, 64>();                     // diagonal tile of the panel is in dtile[buf]
+                const double2 x = *reinterpret_cast<const double2 *>(dtile + buf * 64 + g * 8 + 2 * t);
+                double x0 = x.x, x1 = x.y;
+                gj8_step<0>(x0, x1, g, t, bad); gj8_step<1>(x0, x1, g, t, bad); gj8_step<2>(x0, x1, g, t, bad);
+                gj8_step<3>(x0, x1, g, t, bad); gj8_step<4>(x0, x1, g, t, bad); gj8_step<5>(x0, x1, g, t, bad);
+                gj8_step<6>(x0, x1, g, t, bad); gj8_step<7>(x0, x1, g, t, bad);
+                *reinterpret_cast<double2 *>(pbuf + buf * 64 + g * 8 + 2 * t) = make_double2(x0, x1);
+                __threadfence_block();
+                bar_arrive<VK_BAR_PANEL + buf, NT>();                  // P of the panel published
+            };
+            for (int kt = 0; kt < NR; kt += 2) {
+                invert(std::integral_constant<int, 0>{});
+                if (kt + 1 < NR) invert(std::integral_constant<int, 1>{});
+            }
+            if (__syncthreads_or(bad)) return;
+            __syncthreads();
+        }
+        return;
+    }
+
+    // ================= column warps =================
+    const int c0 = 8 * w + 2 * t;        // my columns c0, c0+1 ; my rows 8*i + g
+    double A[NR][2];
+    double zreg = 0.0;                   // z_{j-1}[tid] for tid < NIP
     auto publish_raw = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < NR; i++)
             *reinterpret_cast<double2 *>(mraw + ((size_t)buf * NIP + 8 * i + g) * 8 + 2 * t) = make_double2(A[i][0], A[i][1]);
     };
-    auto publish_p = [&](int buf) {
-        *reinterpret_cast<double2 *>(pbuf + buf * 64 + g * 8 + 2 * t) = make_double2(px0, px1);
-    };
 
     for (int j = 0; j < nz; j++) {
-        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}); W_{j-1} is still in A
+        if (w == 0) TRACE(100, 0, zreg);
+        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}); W_{j-1} is still in A; D_j, up, dn arrive by TMA
+        double rj = 0.0;
+        if (fuse && tid < ni) rj = a.rhs[(cbase + j) * ni + tid];
+        mbar_wait(mbar, j & 1);
         {
-            const double *Dj = Dc + (size_t)j * NIP * NIP;
             double u0 = 0.0, u1 = 0.0;
-            if (j > 0) { u0 = upc[(size_t)(j - 1) * NIP + c0]; u1 = upc[(size_t)(j - 1) * NIP + c0 + 1]; }
+            if (j > 0) { u0 = updn[c0]; u1 = updn[c0 + 1]; }
 #pragma unroll
             for (int i = 0; i < NR; i++) {
                 const int r = 8 * i + g;
-                const double2 d = *reinterpret_cast<const double2 *>(Dj + (size_t)r * NIP + c0);
+                const double2 d = *reinterpret_cast<const double2 *>(dbuf + r * NIP + c0);
                 if (j > 0) {
-                    const double l = dnc[(size_t)j * NIP + r];
+                    const double l = updn[NIP + r];
                     A[i][0] = d.x - (l * A[i][0]) * u0;
                     A[i][1] = d.y - (l * A[i][1]) * u1;
                 } else {
@@ -171,27 +253,25 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 }
             }
         }
-        if (fuse && tid < NIP) {
-            const double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
-            tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zreg;
-        }
+        if (fuse && tid < NIP) tvec[tid] = (j == 0) ? rj : rj - updn[NIP + tid] * zreg;
         if (w == 0) {
+            TRACE(100, 1, A[0][0]);
+            *reinterpret_cast<double2 *>(dtile + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
+            __threadfence_block();
+            bar_arrive<VK_BAR_TILE, 64>();
             publish_raw(0);
-            px0 = A[0][0]; px1 = A[0][1];
-            gj8_step<0>(px0, px1, g, t, bad); gj8_step<1>(px0, px1, g, t, bad); gj8_step<2>(px0, px1, g, t, bad);
-            gj8_step<3>(px0, px1, g, t, bad); gj8_step<4>(px0, px1, g, t, bad); gj8_step<5>(px0, px1, g, t, bad);
-            gj8_step<6>(px0, px1, g, t, bad); gj8_step<7>(px0, px1, g, t, bad);
-            publish_p(0);
         }
+        double u0 = 0.0, u1 = 0.0;       // B fragments of my pivot-row tile of the coming panel
+        if (w != 0) to_bfrag(A[0][0], A[0][1], g, t, u0, u1);
         auto panel = [&](auto ktc) {
             constexpr int kt = decltype(ktc)::value;
             constexpr int buf = kt & 1;
-            __syncthreads();                              // raw panel columns + P of panel kt visible
+            bar_sync<VK_BAR_PANEL + buf, NT>();             // raw panel columns + P of panel kt visible
+            if (kt == 1 && tid == 0 && j + 1 < nz) prefetch(j + 1);   // every column warp has consumed dbuf / updn by now
+            if (w == (kt + 1) % NW) TRACE(kt, 0, u0);
             if (w == kt) {
                 // ---- panel columns: A_iK <- -A_iK P, A_KK <- P.  A operand = my own (x, y) pair, B operand = -P
-                double b0, b1;
-                to_bfrag(px0, px1, g, t, b0, b1);
-                b0 = -b0; b1 = -b1;
+                const double b0 = -pbuf[buf * 64 + (2 * t) * 8 + g], b1 = -pbuf[buf * 64 + (2 * t + 1) * 8 + g];
 #pragma unroll
                 for (int i = 0; i < NR; i++) {
                     if (i == kt) continue;
@@ -199,11 +279,12 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                     dmma(d0, d1, A[i][0], b0, 0.0, 0.0);
                     dmma(A[i][0], A[i][1], A[i][1], b1, d0, d1);
                 }
-                A[kt][0] = px0; A[kt][1] = px1;
+                const double2 pc = *reinterpret_cast<const double2 *>(pbuf + buf * 64 + g * 8 + 2 * t);
+                A[kt][0] = pc.x; A[kt][1] = pc.y;
+                if constexpr (kt + 1 < NR) to_bfrag(A[kt + 1][0], A[kt + 1][1], g, t, u0, u1);
+                TRACE(kt, 6, A[0][0]);
             } else {
                 // ---- V = P A_Kw (new pivot rows of my columns)
-                double u0, u1;
-                to_bfrag(A[kt][0], A[kt][1], g, t, u0, u1);
                 const double2 pa = *reinterpret_cast<const double2 *>(pbuf + buf * 64 + g * 8 + 2 * t);
                 double v0, v1;
                 dmma(v0, v1, pa.x, u0, 0.0, 0.0);
@@ -219,7 +300,28 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                     dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
                     dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
                 };
-                auto generic = [&]() {
+                if constexpr (kt + 1 < NR) {
+                    constexpr int kn = kt + 1;
+                    upd(std::integral_constant<int, kn>{});           // the next panel's pivot-row tile first
+                    if (w == kn) {
+                        // ---- next panel's columns are mine: hand the diagonal tile to the inverse warp, then the other tiles
+                        TRACE(kt, 1, A[kn][0]);
+                        *reinterpret_cast<double2 *>(dtile + (kn & 1) * 64 + g * 8 + 2 * t) = make_double2(A[kn][0], A[kn][1]);
+                        __threadfence_block();
+                        bar_arrive<VK_BAR_TILE + (kn & 1), 64>();
+                    } else {
+                        to_bfrag(A[kn][0], A[kn][1], g, t, u0, u1);
+                    }
+#pragma unroll
+                    for (int i = 0; i < NR; i++) {
+                        if (i == kt || i == kn) continue;
+                        const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
+                        dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
+                        dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
+                    }
+                    if (w == kn) { publish_raw(kn & 1); TRACE(kt, 4, A[0][0]); }
+                    if (w == (kt + 3) % NW) TRACE(kt, 5, A[0][0]);
+                } else {
 #pragma unroll
                     for (int i = 0; i < NR; i++) {
                         if (i == kt) continue;
@@ -227,35 +329,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                         dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
                         dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
                     }
-                };
-                if constexpr (kt + 1 < NR) {
-                    if (w == kt + 1) {
-                        // ---- next owner: diagonal tile first, then the 8 dependent pivot steps interleaved with the other tiles
-                        constexpr int kn = kt + 1;
-                        upd(std::integral_constant<int, kn>{});
-                        px0 = A[kn][0]; px1 = A[kn][1];
-                        constexpr int NO = NR - 2;              // tiles other than kt and kn, in a fixed order
-                        static_assert(NO <= 16, "panel look-ahead schedule covers at most 18 row tiles");
-                        auto other = [&](auto qc) {
-                            constexpr int q = decltype(qc)::value;
-                            if constexpr (q < NO) {
-                                constexpr int i = (q < kt) ? q : q + 2;
-                                upd(std::integral_constant<int, i>{});
-                            }
-                        };
-#define VK_GJ(PP)                                                                                                      \
-                        gj8_step<PP>(px0, px1, g, t, bad);                                                             \
-                        other(std::integral_constant<int, 2 * (PP)>{});                                                \
-                        other(std::integral_constant<int, 2 * (PP) + 1>{});
-                        VK_GJ(0) VK_GJ(1) VK_GJ(2) VK_GJ(3) VK_GJ(4) VK_GJ(5) VK_GJ(6) VK_GJ(7)
-#undef VK_GJ
-                        publish_raw(kn & 1);
-                        publish_p(kn & 1);
-                    } else {
-                        generic();
-                    }
-                } else {
-                    generic();
                 }
             }
         };
@@ -263,12 +336,13 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         VK_PANEL(0) VK_PANEL(1) VK_PANEL(2) VK_PANEL(3) VK_PANEL(4) VK_PANEL(5) VK_PANEL(6) VK_PANEL(7)
         VK_PANEL(8) VK_PANEL(9) VK_PANEL(10) VK_PANEL(11) VK_PANEL(12) VK_PANEL(13) VK_PANEL(14)
 #undef VK_PANEL
+        if (w == 0) TRACE(100, 3, A[0][0]);
         if (__syncthreads_or(bad)) {
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
             return;
         }
         // ---- W_j = A : stays in registers for the next layer; written out; fused forward elimination
-        double *Wj = Wc + (size_t)j * NIP * NIP;
+        double *Wj = a.W + (cbase + j) * NIP * NIP;
         double tv0 = 0.0, tv1 = 0.0;
         if (fuse) { tv0 = tvec[c0]; tv1 = tvec[c0 + 1]; }
 #pragma unroll
@@ -288,9 +362,10 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 #pragma unroll
             for (int q = 0; q < NW; q++) acc += zpart[q * NIP + tid];
             zreg = acc;
-            zc[(size_t)j * NIP + tid] = acc;
+            a.z[(cbase + j) * NIP + tid] = acc;
         }
-        // (the next layer's first __syncthreads orders the zpart / tvec reuse)
+        if (w == 0) TRACE(100, 4, zreg);
+        // (the panel barriers of the next layer order the zpart / tvec reuse)
     }
 }
 
@@ -414,6 +489,11 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
 {
     using C = FactorCfg<NIP>;
     FactorArgs a{c->nz, c->ni, D, up, dn, W, status, rhs, z};
+    static bool attr_set = false;
+    if (!attr_set) {
+        VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set = true;
+    }
     factor_kernel<NIP, MINB><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
