@@ -20,3 +20,6 @@ print("panel " + "  ".join("%-15s" % n for n in names) + "  panel_total")
 for k in range(9):
     base = t[k, 0]
     print("%4d  " % k + "  ".join("%-15d" % (t[k, e] - base) for e in range(7)) + "  %d" % ((t[k + 1, 0] if k < 8 else L[3]) - t[k, 0]))
+
+f = t[64]
+print("warp 4, panel 3: after_bar 0 | pa loaded %d | V done %d | nv frags %d | tile0 %d | tile1 %d | tile2 %d | tile8 %d" % tuple(f[1:8] - f[0]))

@@ -57,8 +57,8 @@ struct FactorCfg {
     static constexpr int NW = NIP / 8;           // column warps
     static constexpr int NR = NIP / 8;           // row tiles per lane
     static constexpr int NT = (NW + 1) * 32;     // + the panel-inverse warp
-    // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[2][64] + dtile[2][64] + tvec[NIP] + zpart[NW][NIP] + mbarrier
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 256 + NIP + (size_t)NW * NIP + 2);
+    // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[3][64] + hbuf[2][2][64] + tvec[NIP] + zpart[NW][NIP] + mbarrier
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 192 + 256 + NIP + (size_t)NW * NIP + 2);
     static constexpr unsigned TX_BYTES = (unsigned)(sizeof(double) * ((size_t)NIP * NIP + 2 * NIP));
 };
 
@@ -156,7 +156,7 @@ __device__ long long g_trace[128 * 8];
 #define TRACE(kk, ev, dep) do { } while (0)
 #endif
 
-enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3 };   // + panel parity
+enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3, VK_BAR_RAW = 5 };   // + panel parity
 
 template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
@@ -167,9 +167,9 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     double *dbuf = smem;                 // NIP x NIP     D_j (TMA destination)
     double *updn = dbuf + NIP * NIP;     // 2 x NIP       up_{j-1}, dn_j (TMA destination)
     double *mraw = updn + 2 * NIP;       // 2 x NIP x 8   raw panel columns A_iK (double buffered by panel parity)
-    double *pbuf = mraw + 16 * NIP;      // 2 x 64        P = A_KK^{-1}
-    double *dtile = pbuf + 128;          // 2 x 64        diagonal tile handed to the inverse warp
-    double *tvec = dtile + 128;          // NIP           r_j - dn_j * z_{j-1}
+    double *pbuf = mraw + 16 * NIP;      // 3 x 64        P = A_KK^{-1} (the inverse warp runs up to two panels ahead)
+    double *hbuf = pbuf + 192;           // 2 x 2 x 64    tiles handed to the inverse warp: [parity][0] = A_{K-1,K}, [parity][1] = A_KK
+    double *tvec = hbuf + 256;           // NIP           r_j - dn_j * z_{j-1}
     double *zpart = tvec + NIP;          // NW x NIP      per-warp partial sums of W_j tvec
     void *mbar = zpart + NW * NIP;       // mbarrier of the TMA prefetch
 
@@ -197,22 +197,41 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 
     if (w == NW) {
         // ================= panel-inverse warp =================
+        // P_m = (A_mm - A_mK P_{m-1} A_Km)^{-1} with K = panel m-1 and all three tiles as they are after the update of panel m-2:
+        // the whole chain P_{m-1} -> P_m stays inside this warp, the column warps only feed it tiles one panel ahead of time.
         for (int j = 0; j < nz; j++) {
-            auto invert = [&](auto bufc) {
-                constexpr int buf = decltype(bufc)::value;
-                bar_sync<VK_BAR_TILE + buf, 64>();                     // diagonal tile of the panel is in dtile[buf]
-                const double2 x = *reinterpret_cast<const double2 *>(dtile + buf * 64 + g * 8 + 2 * t);
-                double x0 = x.x, x1 = x.y;
+            double x0 = 0.0, x1 = 0.0;       // P_{m-1} in accumulator layout = A fragments of the next product
+            auto step = [&](auto parc, int m) {
+                constexpr int par = decltype(parc)::value;
+                bar_sync<VK_BAR_TILE + par, 64>();                     // tiles of panel m are in hbuf[par]
+                const double *hb = hbuf + par * 128;
+                const double2 dg = *reinterpret_cast<const double2 *>(hb + 64 + g * 8 + 2 * t);
+                double s0 = dg.x, s1 = dg.y;
+                if (m > 0) {
+                    const double ub0 = hb[(2 * t) * 8 + g], ub1 = hb[(2 * t + 1) * 8 + g];
+                    double ta0, ta1, tb0, tb1;
+                    dmma(ta0, ta1, x0, ub0, 0.0, 0.0);
+                    dmma(tb0, tb1, x1, ub1, 0.0, 0.0);
+                    ta0 += tb0; ta1 += tb1;                            // T = P_{m-1} A_Km
+                    double nb0, nb1;
+                    to_bfrag(ta0, ta1, g, t, nb0, nb1);
+                    bar_sync<VK_BAR_RAW + (par ^ 1), 64>();            // raw columns of panel m-1 are in mraw[par ^ 1]
+                    const double2 mr = *reinterpret_cast<const double2 *>(mraw + ((size_t)(par ^ 1) * NIP + 8 * m + g) * 8 + 2 * t);
+                    double sa0, sa1, sb0, sb1;
+                    dmma(sa0, sa1, mr.x, -nb0, s0, s1);
+                    dmma(sb0, sb1, mr.y, -nb1, 0.0, 0.0);
+                    s0 = sa0 + sb0; s1 = sa1 + sb1;
+                }
+                x0 = s0; x1 = s1;
                 gj8_step<0>(x0, x1, g, t, bad); gj8_step<1>(x0, x1, g, t, bad); gj8_step<2>(x0, x1, g, t, bad);
                 gj8_step<3>(x0, x1, g, t, bad); gj8_step<4>(x0, x1, g, t, bad); gj8_step<5>(x0, x1, g, t, bad);
                 gj8_step<6>(x0, x1, g, t, bad); gj8_step<7>(x0, x1, g, t, bad);
-                *reinterpret_cast<double2 *>(pbuf + buf * 64 + g * 8 + 2 * t) = make_double2(x0, x1);
-                __threadfence_block();
-                bar_arrive<VK_BAR_PANEL + buf, NT>();                  // P of the panel published
+                *reinterpret_cast<double2 *>(pbuf + (m % 3) * 64 + g * 8 + 2 * t) = make_double2(x0, x1);
+                bar_arrive<VK_BAR_PANEL + par, NT>();                  // P_m published
             };
-            for (int kt = 0; kt < NR; kt += 2) {
-                invert(std::integral_constant<int, 0>{});
-                if (kt + 1 < NR) invert(std::integral_constant<int, 1>{});
+            for (int m = 0; m < NR; m += 2) {
+                step(std::integral_constant<int, 0>{}, m);
+                if (m + 1 < NR) step(std::integral_constant<int, 1>{}, m + 1);
             }
             if (__syncthreads_or(bad)) return;
             __syncthreads();
@@ -256,22 +275,27 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         if (fuse && tid < NIP) tvec[tid] = (j == 0) ? rj : rj - updn[NIP + tid] * zreg;
         if (w == 0) {
             TRACE(100, 1, A[0][0]);
-            *reinterpret_cast<double2 *>(dtile + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
-            __threadfence_block();
+            *reinterpret_cast<double2 *>(hbuf + 64 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
             bar_arrive<VK_BAR_TILE, 64>();
             publish_raw(0);
+            bar_arrive<VK_BAR_RAW, 64>();
+        } else if (w == 1) {
+            *reinterpret_cast<double2 *>(hbuf + 128 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
+            *reinterpret_cast<double2 *>(hbuf + 128 + 64 + g * 8 + 2 * t) = make_double2(A[1][0], A[1][1]);
+            bar_arrive<VK_BAR_TILE + 1, 64>();
         }
         double u0 = 0.0, u1 = 0.0;       // B fragments of my pivot-row tile of the coming panel
         if (w != 0) to_bfrag(A[0][0], A[0][1], g, t, u0, u1);
         auto panel = [&](auto ktc) {
             constexpr int kt = decltype(ktc)::value;
-            constexpr int buf = kt & 1;
-            bar_sync<VK_BAR_PANEL + buf, NT>();             // raw panel columns + P of panel kt visible
+            constexpr int par = kt & 1;
+            const double *pb = pbuf + (kt % 3) * 64;
+            bar_sync<VK_BAR_PANEL + par, NT>();           // raw panel columns + P of panel kt visible
             if (kt == 1 && tid == 0 && j + 1 < nz) prefetch(j + 1);   // every column warp has consumed dbuf / updn by now
             if (w == (kt + 1) % NW) TRACE(kt, 0, u0);
             if (w == kt) {
                 // ---- panel columns: A_iK <- -A_iK P, A_KK <- P.  A operand = my own (x, y) pair, B operand = -P
-                const double b0 = -pbuf[buf * 64 + (2 * t) * 8 + g], b1 = -pbuf[buf * 64 + (2 * t + 1) * 8 + g];
+                const double b0 = -pb[(2 * t) * 8 + g], b1 = -pb[(2 * t + 1) * 8 + g];
 #pragma unroll
                 for (int i = 0; i < NR; i++) {
                     if (i == kt) continue;
@@ -279,57 +303,66 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                     dmma(d0, d1, A[i][0], b0, 0.0, 0.0);
                     dmma(A[i][0], A[i][1], A[i][1], b1, d0, d1);
                 }
-                const double2 pc = *reinterpret_cast<const double2 *>(pbuf + buf * 64 + g * 8 + 2 * t);
+                const double2 pc = *reinterpret_cast<const double2 *>(pb + g * 8 + 2 * t);
                 A[kt][0] = pc.x; A[kt][1] = pc.y;
                 if constexpr (kt + 1 < NR) to_bfrag(A[kt + 1][0], A[kt + 1][1], g, t, u0, u1);
                 TRACE(kt, 6, A[0][0]);
             } else {
                 // ---- V = P A_Kw (new pivot rows of my columns)
-                const double2 pa = *reinterpret_cast<const double2 *>(pbuf + buf * 64 + g * 8 + 2 * t);
+                if (kt == 3 && w == 4) TRACE(64, 0, u0);
+                const double2 pa = *reinterpret_cast<const double2 *>(pb + g * 8 + 2 * t);
+                if (kt == 3 && w == 4) TRACE(64, 1, pa.x);
                 double v0, v1;
                 dmma(v0, v1, pa.x, u0, 0.0, 0.0);
                 dmma(v0, v1, pa.y, u1, v0, v1);
                 A[kt][0] = v0; A[kt][1] = v1;
+                if (kt == 3 && w == 4) TRACE(64, 2, v0);
                 double nv0, nv1;
                 to_bfrag(v0, v1, g, t, nv0, nv1);
                 nv0 = -nv0; nv1 = -nv1;
-                const double *mr = mraw + ((size_t)buf * NIP + g) * 8 + 2 * t;
+                if (kt == 3 && w == 4) TRACE(64, 3, nv1);
+                const double *mr = mraw + ((size_t)par * NIP + g) * 8 + 2 * t;
                 auto upd = [&](auto ic) {
                     constexpr int i = decltype(ic)::value;
                     const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
                     dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
                     dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
                 };
+                // the tiles the inverse warp is waiting for first: pivot rows of the next panel, diagonal tile of the one after
                 if constexpr (kt + 1 < NR) {
-                    constexpr int kn = kt + 1;
-                    upd(std::integral_constant<int, kn>{});           // the next panel's pivot-row tile first
-                    if (w == kn) {
-                        // ---- next panel's columns are mine: hand the diagonal tile to the inverse warp, then the other tiles
-                        TRACE(kt, 1, A[kn][0]);
-                        *reinterpret_cast<double2 *>(dtile + (kn & 1) * 64 + g * 8 + 2 * t) = make_double2(A[kn][0], A[kn][1]);
-                        __threadfence_block();
-                        bar_arrive<VK_BAR_TILE + (kn & 1), 64>();
-                    } else {
-                        to_bfrag(A[kn][0], A[kn][1], g, t, u0, u1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < NR; i++) {
-                        if (i == kt || i == kn) continue;
-                        const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
-                        dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
-                        dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
-                    }
-                    if (w == kn) { publish_raw(kn & 1); TRACE(kt, 4, A[0][0]); }
-                    if (w == (kt + 3) % NW) TRACE(kt, 5, A[0][0]);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NR; i++) {
-                        if (i == kt) continue;
-                        const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
-                        dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
-                        dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
+                    upd(std::integral_constant<int, kt + 1>{});
+                    if (w != kt + 1) to_bfrag(A[kt + 1][0], A[kt + 1][1], g, t, u0, u1);
+                }
+                if constexpr (kt + 2 < NR) {
+                    upd(std::integral_constant<int, kt + 2>{});
+                    if (w == kt + 2) {
+                        constexpr int hp = (kt + 2) & 1;
+                        *reinterpret_cast<double2 *>(hbuf + hp * 128 + g * 8 + 2 * t) = make_double2(A[kt + 1][0], A[kt + 1][1]);
+                        *reinterpret_cast<double2 *>(hbuf + hp * 128 + 64 + g * 8 + 2 * t) = make_double2(A[kt + 2][0], A[kt + 2][1]);
+                        bar_arrive<VK_BAR_TILE + hp, 64>();
+                        TRACE(kt, 1, A[kt + 2][0]);
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < NR; i++) {
+                    if (i == kt || i == kt + 1 || i == kt + 2) continue;
+                    const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
+                    dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
+                    dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
+                    if (kt == 3 && w == 4 && i == 0) TRACE(64, 4, A[i][0]);
+                    if (kt == 3 && w == 4 && i == 1) TRACE(64, 5, A[i][0]);
+                    if (kt == 3 && w == 4 && i == 2) TRACE(64, 6, A[i][0]);
+                    if (kt == 3 && w == 4 && i == 8) TRACE(64, 7, A[i][0]);
+                }
+                if constexpr (kt + 1 < NR) {
+                    if (w == kt + 1) {
+                        publish_raw((kt + 1) & 1);
+                        // consumed by the inverse warp for panel kt+2 (an arrival nobody waits for would corrupt the next phase)
+                        if constexpr (kt + 2 < NR) bar_arrive<VK_BAR_RAW + ((kt + 1) & 1), 64>();
+                        TRACE(kt, 4, A[0][0]);
+                    }
+                }
+                if (w == (kt + 3) % NW) TRACE(kt, 5, A[0][0]);
             }
         };
 #define VK_PANEL(N) if constexpr ((N) < NR) panel(std::integral_constant<int, (N)>{});
