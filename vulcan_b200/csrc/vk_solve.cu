@@ -56,9 +56,16 @@ template <int NIP>
 struct FactorCfg {
     static constexpr int NW = NIP / 8;           // column warps
     static constexpr int NR = NIP / 8;           // row tiles per lane
-    static constexpr int NT = (NW + 1) * 32;     // + the panel-inverse warp
+    // Warp -> sub-partition is warp id % 4 (scripts/ubench/dmma_warps.cu).  DFMA/DMUL of the panel-inverse chain share the FP64
+    // pipe with DMMA, so the inverse warp gets a sub-partition of its own: warp 3 inverts, warps 7, 11, .. only keep the block
+    // barriers company, and the column warps fill sub-partitions 0-2 evenly (NW is a multiple of 3).
+    static constexpr bool SPREAD = (NW % 3 == 0) && (NW / 3) * 4 * 32 <= 512;
+    static constexpr int NWARPS = SPREAD ? (NW / 3) * 4 : NW + 1;
+    static constexpr int HELPER = SPREAD ? 3 : NW;
+    static constexpr int NT = NWARPS * 32;
+    static constexpr int NSYNC = (NW + 1) * 32;  // threads on the panel barrier: column warps + the inverse warp
     // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[3][64] + hbuf[2][2][64] + tvec[NIP] + zpart[NW][NIP] + mbarrier
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 192 + 256 + NIP + (size_t)NW * NIP + 2);
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 192 + 256 + 128 + NIP + (size_t)NW * NIP + 2);
     static constexpr unsigned TX_BYTES = (unsigned)(sizeof(double) * ((size_t)NIP * NIP + 2 * NIP));
 };
 
@@ -162,19 +169,22 @@ template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
 {
     using C = FactorCfg<NIP>;
-    constexpr int NR = C::NR, NW = C::NW, NT = C::NT;
+    constexpr int NR = C::NR, NW = C::NW, NT = C::NSYNC;
     extern __shared__ __align__(128) double smem[];
     double *dbuf = smem;                 // NIP x NIP     D_j (TMA destination)
     double *updn = dbuf + NIP * NIP;     // 2 x NIP       up_{j-1}, dn_j (TMA destination)
     double *mraw = updn + 2 * NIP;       // 2 x NIP x 8   raw panel columns A_iK (double buffered by panel parity)
     double *pbuf = mraw + 16 * NIP;      // 3 x 64        P = A_KK^{-1} (the inverse warp runs up to two panels ahead)
     double *hbuf = pbuf + 192;           // 2 x 2 x 64    tiles handed to the inverse warp: [parity][0] = A_{K-1,K}, [parity][1] = A_KK
-    double *tvec = hbuf + 256;           // NIP           r_j - dn_j * z_{j-1}
+    double *hraw = hbuf + 256;           // 2 x 64        [parity of m] = A_mK, K = panel m-1 (from warp m-1)
+    double *tvec = hraw + 128;           // NIP           r_j - dn_j * z_{j-1}
     double *zpart = tvec + NIP;          // NW x NIP      per-warp partial sums of W_j tvec
     void *mbar = zpart + NW * NIP;       // mbarrier of the TMA prefetch
 
     const int col = blockIdx.x;
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int w = C::SPREAD ? wid - (wid >> 2) : wid;     // column-warp index (meaningless for the other warps)
+    const int tid = w * 32 + lane;                         // thread index among the column warps
     const int ni = a.ni, nz = a.nz;
     const size_t cbase = (size_t)col * nz;
     const bool fuse = a.rhs != nullptr;
@@ -188,14 +198,22 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             tma_load_1d(updn + NIP, a.dn + (cbase + j) * NIP, (unsigned)(sizeof(double) * NIP), mbar);
         }
     };
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) prefetch(0);
+    if (threadIdx.x == 0) prefetch(0);
 
-    if (w == NW) {
+    if (C::SPREAD && (wid & 3) == 3 && wid != C::HELPER) {
+        // idle warps of the spread layout: only the two block-wide barriers of every layer
+        for (int j = 0; j < nz; j++) {
+            if (__syncthreads_or(0)) return;
+            __syncthreads();
+        }
+        return;
+    }
+    if (wid == C::HELPER) {
         // ================= panel-inverse warp =================
         // P_m = (A_mm - A_mK P_{m-1} A_Km)^{-1} with K = panel m-1 and all three tiles as they are after the update of panel m-2:
         // the whole chain P_{m-1} -> P_m stays inside this warp, the column warps only feed it tiles one panel ahead of time.
@@ -215,8 +233,8 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                     ta0 += tb0; ta1 += tb1;                            // T = P_{m-1} A_Km
                     double nb0, nb1;
                     to_bfrag(ta0, ta1, g, t, nb0, nb1);
-                    bar_sync<VK_BAR_RAW + (par ^ 1), 64>();            // raw columns of panel m-1 are in mraw[par ^ 1]
-                    const double2 mr = *reinterpret_cast<const double2 *>(mraw + ((size_t)(par ^ 1) * NIP + 8 * m + g) * 8 + 2 * t);
+                    bar_sync<VK_BAR_RAW + par, 64>();                  // A_mK (K = panel m-1), handed over by warp m-1
+                    const double2 mr = *reinterpret_cast<const double2 *>(hraw + par * 64 + g * 8 + 2 * t);
                     double sa0, sa1, sb0, sb1;
                     dmma(sa0, sa1, mr.x, -nb0, s0, s1);
                     dmma(sb0, sb1, mr.y, -nb1, 0.0, 0.0);
@@ -277,8 +295,9 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             TRACE(100, 1, A[0][0]);
             *reinterpret_cast<double2 *>(hbuf + 64 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
             bar_arrive<VK_BAR_TILE, 64>();
+            *reinterpret_cast<double2 *>(hraw + 64 + g * 8 + 2 * t) = make_double2(A[1][0], A[1][1]);
+            bar_arrive<VK_BAR_RAW + 1, 64>();
             publish_raw(0);
-            bar_arrive<VK_BAR_RAW, 64>();
         } else if (w == 1) {
             *reinterpret_cast<double2 *>(hbuf + 128 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
             *reinterpret_cast<double2 *>(hbuf + 128 + 64 + g * 8 + 2 * t) = make_double2(A[1][0], A[1][1]);
@@ -335,6 +354,11 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 }
                 if constexpr (kt + 2 < NR) {
                     upd(std::integral_constant<int, kt + 2>{});
+                    if (w == kt + 1) {                    // A_{kt+2,K'} (K' = panel kt+1) for P_{kt+2}
+                        constexpr int hq = (kt + 2) & 1;
+                        *reinterpret_cast<double2 *>(hraw + hq * 64 + g * 8 + 2 * t) = make_double2(A[kt + 2][0], A[kt + 2][1]);
+                        bar_arrive<VK_BAR_RAW + hq, 64>();
+                    }
                     if (w == kt + 2) {
                         constexpr int hp = (kt + 2) & 1;
                         *reinterpret_cast<double2 *>(hbuf + hp * 128 + g * 8 + 2 * t) = make_double2(A[kt + 1][0], A[kt + 1][1]);
@@ -357,8 +381,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 if constexpr (kt + 1 < NR) {
                     if (w == kt + 1) {
                         publish_raw((kt + 1) & 1);
-                        // consumed by the inverse warp for panel kt+2 (an arrival nobody waits for would corrupt the next phase)
-                        if constexpr (kt + 2 < NR) bar_arrive<VK_BAR_RAW + ((kt + 1) & 1), 64>();
                         TRACE(kt, 4, A[0][0]);
                     }
                 }
