@@ -217,14 +217,13 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
         const int jj = j - 1 + q;
         const bool act = (q < 3) && jj >= 0 && jj < nz;
         const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-        int n = ni;
-        if (A.atm.n_gas > 0) {     // compact the gas species like the fancy-index copy y[:,gas_indx]
-            n = A.atm.n_gas;
-            if (act) for (int i = (lane_ & 7); i < n; i += 8) tmp[q * ni + i] = row[A.atm.gas_indx[i]];
-            row = tmp + q * ni;
-            __syncwarp();
+        double sres;
+        if (A.atm.n_gas > 0) {     // np.sum(y[:,gas_indx], axis=1) is a plain left-to-right sum (see row_sum)
+            sres = 0.0;
+            if (act && (lane_ & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, tmp);
+        } else {
+            sres = np_pairwise_group8(row, ni, act);
         }
-        const double sres = np_pairwise_group8(row, n, act);
         if (act && (lane_ & 7) == 0) ysum[q] = sres;
     }
     __syncthreads();
@@ -400,14 +399,13 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
         const int jj = j - 1 + q;
         const bool act = (q < 3) && jj >= 0 && jj < nz;
         const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-        int n = ni;
+        double sres;
         if (A.atm.n_gas_lhs > 0) {
-            n = A.atm.n_gas_lhs;
-            if (act) for (int i = (lane_ & 7); i < n; i += 8) tmp[q * ni + i] = row[A.atm.gas_indx_lhs[i]];
-            row = tmp + q * ni;
-            __syncwarp();
+            sres = 0.0;
+            if (act && (lane_ & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, tmp);
+        } else {
+            sres = np_pairwise_group8(row, ni, act);
         }
-        const double sres = np_pairwise_group8(row, n, act);
         if (act && (lane_ & 7) == 0) ysum[q] = sres;
     }
     // ---- chemical Jacobian: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work

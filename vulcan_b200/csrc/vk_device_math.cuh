@@ -30,12 +30,15 @@ static __device__ __forceinline__ double np_pairwise(const double *a, int n)
     n2 -= n2 % 8;
     return np_pairwise_le128(a, n2) + np_pairwise_le128(a + n2, n - n2);
 }
-// row sum over the gas species (compacted through `tmp` like the fancy-index copy y[:,gas_indx]) or over all species
+// row sum over the gas species or over all species (`tmp` unused, kept for the call sites)
 static __device__ __forceinline__ double row_sum(const double *yrow, int ni, int n_gas, const int *gas, double *tmp)
 {
     if (n_gas > 0) {
-        for (int i = 0; i < n_gas; i++) tmp[i] = yrow[gas[i]];
-        return np_pairwise(tmp, n_gas);
+        // np.sum(y[:, gas_indx], axis=1): the fancy-indexed copy is F-ordered, numpy reduces it column by column, i.e. a plain
+        // left-to-right sum in gas_indx order (NOT pairwise) - pinned by the Jupiter / Earth fixtures
+        double acc = yrow[gas[0]];
+        for (int i = 1; i < n_gas; i++) acc += yrow[gas[i]];
+        return acc;
     }
     return np_pairwise(yrow, ni);
 }
