@@ -207,7 +207,9 @@ def main():
     lo, hi = ensemble.partition(ncols_total, world, rank)
     y, atom_ini, kzz, kw = build_columns(case, lo, hi)
     atm_common = dict(kw)
-    runner = ensemble.EnsembleRunner(case.net, case.nz, y, np.full(hi - lo, case.dt), atm_common, kzz, case.k, cfg, st["compo"],
+    # every column starts like a fresh reference run: its own (re-weighted) state with dt = dttry (vulcan_cfg.dttry, store.py:32)
+    dt0 = float(cfg["dttry"])
+    runner = ensemble.EnsembleRunner(case.net, case.nz, y, np.full(hi - lo, dt0), atm_common, kzz, case.k, cfg, st["compo"],
                                      atom_ini, st["n_0"], device=local_rank, refine=args.refine)
     ncol = hi - lo
 
@@ -218,7 +220,7 @@ def main():
 
     # ---- device-resident loop ------------------------------------------------------------------------------------
     runner.run(args.warmup)
-    runner.col.ens_set_state(y, np.full(ncol, case.dt))     # every timed run starts from the same state
+    runner.col.ens_set_state(y, np.full(ncol, dt0))         # every timed run starts from the same state
     runner.run(1)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -252,7 +254,7 @@ def main():
     hy, hm, hs, ho = [p.numpy() for p in pin]
     hy[:] = y.ravel()
     hm[:] = (y / y.sum(axis=2, keepdims=True)).ravel()
-    hdt = np.full(ncol, case.dt); hdelta = np.empty(ncol); hstat = np.zeros(ncol, dtype=np.int32)
+    hdt = np.full(ncol, dt0); hdelta = np.empty(ncol); hstat = np.zeros(ncol, dtype=np.int32)
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
         runner.col.ros2_solve_into(hy, hm, hdt, hs, ho, hdelta, hstat)
@@ -322,6 +324,24 @@ def main():
         e2e1 = 20 / (time.time() - t0)
         line["single_column"] = {"steps_per_s": 30 / (ms1 * 1e-3), "ms_per_step": ms1 / 30, "e2e_steps_per_s": e2e1,
                                  "note": "attempted Ros2 steps of ONE HD189 column (latency-bound: one SM runs the block-Thomas recurrence)"}
+        # time-to-steady-state: the reference's own initial state through the drop-in solver object + Integration mirror
+        # (same convergence criterion, photolysis updates included); reference numbers from tests/golden/HD189_full.npz
+        try:
+            from test_gpu_steady_state import run_hd189
+            from helpers import GOLD
+            c0, var, atm, para, integ, wall_ss = run_hd189(refine=refine)
+            ref = np.load(os.path.join(GOLD, "HD189_full.npz"))
+            n_rej = para.delta_count + para.nega_count + para.loss_count
+            line["single_column"]["time_to_steady_state"] = {
+                "wall_s": wall_ss, "accepted_steps": int(para.count), "rejected_attempts": int(n_rej), "model_time_s": float(var.t),
+                "converged": bool(para.end_case == 1), "photolysis_updates": int(integ.n_photo_updates),
+                "attempts_per_s": (para.count + n_rej) / wall_ss,
+                "reference_cpu": {"wall_s": float(ref["wall_s"]), "accepted_steps": int(ref["count"]),
+                                  "rejected_attempts": int(ref["delta_count"]) + int(ref["nega_count"]) + int(ref["loss_count"]),
+                                  "model_time_s": float(ref["t"]), "where": "unmodified numpy/scipy reference, 1 core, build container"},
+                "speedup_vs_reference_cpu": float(ref["wall_s"]) / wall_ss}
+        except Exception as e:      # never lose the bench line over the auxiliary number
+            line["single_column"]["time_to_steady_state"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             threads = host_threads()
             n_sample = max(2 * threads, 16)

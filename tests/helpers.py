@@ -134,6 +134,57 @@ def photo_tables(st):
                 br_is_T=br_is_T if br_is_T.any() else None, cross_J_T=cross_J_T)
 
 
+def mock_objects(case, with_photo=True):
+    """Stand-ins for the reference's vulcan_cfg module and store.Variables / AtmData / Parameters containers (store.py:21-209)
+    filled from a fixture: the GPU box has no /root/reference, and the drop-in class only reads attributes."""
+    from types import SimpleNamespace
+    st, fx, cfgd = case.st, case.fx, case.cfg
+    cfg = SimpleNamespace(**cfgd)
+    cfg.use_fix_sp_bot = {} if not isinstance(cfgd.get("use_fix_sp_bot"), dict) else cfgd["use_fix_sp_bot"]
+    for name, default in (("non_gas_sp", []), ("condense_sp", []), ("fix_species", []), ("remove_list", []), ("T_cross_sp", []),
+                          ("diff_esc", []), ("use_relax", [])):
+        if not isinstance(getattr(cfg, name, None), list):
+            setattr(cfg, name, default)
+    atoms = cfg.atom_list
+    var = SimpleNamespace(y=case.y.copy(), ymix=case.ymix.copy(), dt=case.dt, t=float(fx["t"]), y_prev=case.y.copy(),
+                          k={i: case.k_rz[i].copy() for i in range(1, case.nr + 1)},
+                          atom_ini={a: float(st["atom_ini"][q]) for q, a in enumerate(atoms)}, atom_sum={},
+                          atom_loss={a: float(fx["atom_loss_in"][q]) for q, a in enumerate(atoms)},
+                          atom_loss_prev={a: float(fx["atom_loss_prev"][q]) for q, a in enumerate(atoms)},
+                          dy=1., dydt=1., dy_prev=1., longdy=1., longdydt=1., aflux_change=0., y_time=[], t_time=[],
+                          atom_loss_time=[])
+    atm = SimpleNamespace(Kzz=st["Kzz"].copy(), vz=st["vz"].copy(), dzi=fx["dzi"].copy(), Dzz=st["Dzz"].copy(), vs=fx["vs_dyn"].copy(),
+                          Tco=st["Tco"].copy(), g=fx["g"].copy(), M=st["M"].copy(), Ti=fx["Ti"].copy(), Hpi=fx["Hpi"].copy(),
+                          ms=st["ms"].copy(), alpha=st["alpha"].copy(), top_flux=fx["top_flux_dyn"].copy(), bot_flux=st["bot_flux"].copy(),
+                          bot_vdep=st["bot_vdep"].copy(), gas_indx=list(st["gas_indx"]), n_0=st["n_0"].copy(), dz=fx["dz"].copy(),
+                          pico=st["pico"].copy(), pco=st["pco"].copy(), pref_indx=int(st["pref_indx"]), gs=float(cfgd["gs"]),
+                          Hp=fx["Hp"].copy(), zco=fx["zco"].copy(), mu=fx["mu"].copy())
+    para = SimpleNamespace(delta=0.0, small_y=0.0, nega_y=0.0, delta_count=0, nega_count=0, loss_count=0, count=int(fx["count"]),
+                           fix_species_start=False, solver_str="", end_case=0, switch_final_photo_frq=False)
+    if with_photo and cfgd.get("use_photo") and "photo_sp" in st:
+        psp = [str(s) for s in st["photo_sp"]]
+        var.photo_sp = set(psp)
+        var.ion_sp = set()
+        var.bins, var.sflux_top = st["bins"], st["sflux_top"]
+        var.sflux_din12_indx, var.dbin1, var.dbin2 = int(st["sflux_din12_indx"]), float(st["dbin1"]), float(st["dbin2"])
+        var.cross = {s: st["cross"][i] for i, s in enumerate(psp)}
+        var.cross_scat = {s: st["cross_scat"][i] for i, s in enumerate(cfg.scat_sp)}
+        var.n_branch, var.cross_J, var.pho_rate_index = {}, {}, {}
+        for q in range(len(st["branch_sp"])):
+            s, b = psp[int(st["branch_sp"][q])], int(st["branch_no"][q])
+            var.n_branch[s] = max(var.n_branch.get(s, 0), b)
+            var.cross_J[(s, b)] = st["cross_J"][q]
+            var.pho_rate_index[(s, b)] = int(st["branch_rate_index"][q])
+        if "T_cross_sp" in st:
+            tsp = [str(x) for x in st["T_cross_sp"]]
+            var.cross_T = {s: st["cross_T"][q] for q, s in enumerate(tsp)}
+            var.cross_J_T = {}
+            for q, b in enumerate(st["cross_J_T_branch"]):
+                b = int(b)
+                var.cross_J_T[(psp[int(st["branch_sp"][b])], int(st["branch_no"][b]))] = st["cross_J_T"][q]
+    return cfg, var, atm, para
+
+
 def ulp_diff(a, b):
     """max distance in units in the last place between two float64 arrays (same sign assumed where it matters)."""
     a = np.ascontiguousarray(a, dtype=np.float64)

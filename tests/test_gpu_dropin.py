@@ -6,29 +6,13 @@ from types import SimpleNamespace
 import numpy as np
 import pytest
 
-from helpers import Case, GOLD, have
+from helpers import Case, GOLD, have, mock_objects
 
 pytestmark = pytest.mark.gpu
 
 
 def _mock(case):
-    st, fx, cfgd = case.st, case.fx, case.cfg
-    cfg = SimpleNamespace(**cfgd)
-    cfg.use_fix_sp_bot = {} if not isinstance(cfgd.get("use_fix_sp_bot"), dict) else cfgd["use_fix_sp_bot"]
-    for name, default in (("non_gas_sp", []), ("condense_sp", []), ("fix_species", []), ("remove_list", []), ("T_cross_sp", [])):
-        if not isinstance(getattr(cfg, name, None), list):
-            setattr(cfg, name, default)
-    atoms = cfg.atom_list
-    var = SimpleNamespace(y=case.y.copy(), ymix=case.ymix.copy(), dt=case.dt, t=float(fx["t"]), y_prev=case.y.copy(),
-                          k={i: case.k_rz[i].copy() for i in range(1, case.nr + 1)},
-                          atom_ini={a: float(st["atom_ini"][q]) for q, a in enumerate(atoms)}, atom_sum={}, atom_loss={},
-                          atom_loss_prev={a: float(fx["atom_loss_prev"][q]) for q, a in enumerate(atoms)})
-    atm = SimpleNamespace(Kzz=st["Kzz"], vz=st["vz"], dzi=fx["dzi"], Dzz=st["Dzz"], vs=fx["vs_dyn"], Tco=st["Tco"], g=fx["g"],
-                          M=st["M"], Ti=fx["Ti"], Hpi=fx["Hpi"], ms=st["ms"], alpha=st["alpha"], top_flux=fx["top_flux_dyn"],
-                          bot_flux=st["bot_flux"], bot_vdep=st["bot_vdep"], gas_indx=list(st["gas_indx"]), n_0=st["n_0"], dz=fx["dz"])
-    para = SimpleNamespace(delta=0.0, small_y=0.0, nega_y=0.0, delta_count=0, nega_count=0, loss_count=0, count=int(fx["count"]),
-                           fix_species_start=False, solver_str="")
-    return cfg, var, atm, para
+    return mock_objects(case, with_photo=False)
 
 
 @pytest.mark.parametrize("step", [0, 100])

@@ -46,6 +46,7 @@ class Ros2(object):
         self._devnet = _abi.DeviceNetwork(self.network, device)
         self._col = None
         self._k_cache = None
+        self._k_ids = None
         self._atm_cache = None
         self._opts_key = None
         self._photo_ready = False
@@ -93,12 +94,20 @@ class Ros2(object):
         self._atm_cache = (flags, {n: v.copy() for n, v in vals.items()})
 
     def _sync_k(self, var, nz):
+        """var.k is a dict {1..nr -> (nz,) array} (store.py:25).  During integration the reference only REBINDS entries
+        (compute_J op.py:2785, conden op.py:1122-1176), so the identity of the value objects is a sufficient change detector;
+        a full comparison is still made every 64 calls."""
+        ids = tuple(map(id, var.k.values()))
+        self._k_calls = getattr(self, "_k_calls", 0) + 1
+        if self._k_cache is not None and ids == self._k_ids and self._k_calls % 64:
+            return
         k = np.zeros((nz, self.nr + 1))
         for i in range(1, self.nr + 1):
             k[:, i] = var.k[i]
         if self._k_cache is None or not np.array_equal(self._k_cache, k):
             self._columns(nz).set_k(k)
             self._k_cache = k
+        self._k_ids = ids
 
     def _sync_opts(self, var, atm, para, nz):
         cfg, ni = self.cfg, self.ni
@@ -297,6 +306,7 @@ class Ros2(object):
             if var.pho_rate_index[(s, b)] not in self.cfg.remove_list:
                 var.k[var.pho_rate_index[(s, b)]] = var.J_sp[(s, b)] * self.cfg.f_diurnal
         self._k_cache = None          # the device copy of k already holds the new J rows; re-verified on the next solver call
+        self._k_ids = None
         self._photo_cache = None
 
     def compute_Jion(self, var, atm):
