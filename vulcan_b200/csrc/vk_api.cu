@@ -129,6 +129,29 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
         for (int x = 0; x < 3; x++) f[x] = (x < d->maxjf) ? (unsigned)d->jac_fac[q * d->maxjf + x] : (unsigned)(ni + 1);
         jt[q] = make_uint2((unsigned)d->jac_k[q] | ((unsigned)(ci & 0xff) << 16), f[0] | (f[1] << 8) | (f[2] << 16));
     }
+    // warp-per-layer rhs kernel tables
+    std::vector<unsigned short> rd16(d->n_rhs);
+    int rhs_unit = (nr / 2 < 32768) ? 1 : 0;
+    for (int q = 0; q < d->n_rhs; q++) {
+        const int ci = (int)d->rhs_coef[q];
+        if (ci != 1 && ci != -1) rhs_unit = 0;
+        rd16[q] = (unsigned short)((((d->rhs_pair[q] - 1) / 2) & 0x7fff) | (ci < 0 ? 0x8000 : 0));
+    }
+    std::vector<int> lane_sp(32 * VK_RHS_SPL, -1);
+    {
+        std::vector<int> order(ni), load(32, 0), cnt(32, 0);
+        for (int s = 0; s < ni; s++) order[s] = s;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return d->rhs_ptr[a + 1] - d->rhs_ptr[a] > d->rhs_ptr[b + 1] - d->rhs_ptr[b]; });
+        for (int s : order) {
+            int best = -1;
+            for (int l = 0; l < 32; l++)
+                if (cnt[l] < VK_RHS_SPL && (best < 0 || load[l] < load[best])) best = l;
+            if (best < 0) { delete n; set_error("too many species for the rhs lane schedule"); return VK_ERR_UNSUPPORTED; }
+            lane_sp[best * VK_RHS_SPL + cnt[best]++] = s;
+            load[best] += d->rhs_ptr[s + 1] - d->rhs_ptr[s] + 4;     // + a little per-species overhead
+        }
+    }
     // work schedule of the Jacobian kernel: segments of <= 16 terms sorted by decreasing length
     struct Seg { unsigned rc; int q0; int len; int ent; };
     std::vector<Seg> segs;
@@ -162,6 +185,8 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
     int rcode = VK_OK;
 #define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
     CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term); CP(segw, jac_seg); CP(multi, jac_multi);
+    CP(rd16, rhs_desc16); CP(lane_sp, rhs_lane_sp);
+    nd.rhs_unit = rhs_unit;
 #undef CP
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->jac_ptr, (size_t)d->n_ent + 1, &nd.jac_ptr);

@@ -354,6 +354,233 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// rhs_warp_kernel: ONE WARP per (column, layer), RHS_WPB layers per block, no block-wide barrier after the tables are staged.
+// The per-species production-loss sum must be added left to right in the reference's order (bit-identical RHS is the first parity
+// gate), so the longest chain (H: 170 terms in NCHO) bounds the latency of a layer whatever the thread count; what matters is how
+// many layers are in flight per SM and how few instructions a term costs.  Per warp: the three y rows, the 439 pair rates
+// v_p = k_f prod(y) - k_r prod(y) (each lane forms whole pairs, so the separate differencing pass disappears) and the layer scalars
+// live in 5.5 KB of shared memory; term descriptors are 16 bit (pair index + sign; all coefficients of the shipped networks are
+// +-1, otherwise the general 32-bit descriptors are used) and are staged once per block; species are dealt to lanes longest
+// chain first (vk_network_create).
+#define RHS_WPB 8
+struct RhsWarpSmem {    // offsets in doubles inside one warp's slab
+    int ym, y0, yp, v, chem, scal, total;
+};
+__host__ __device__ inline RhsWarpSmem rhs_warp_layout(int ni, int nr)
+{
+    RhsWarpSmem L;
+    L.ym = 0; L.y0 = L.ym + (ni + 2); L.yp = L.y0 + (ni + 2);
+    L.v = L.yp + (ni + 2);                    // [nr/2 + 1]
+    L.chem = L.v + (nr / 2 + 2);              // [ni]
+    L.scal = L.chem + ni + (ni & 1);          // LayerScal + ysum[4]
+    L.total = L.scal + 16;
+    return L;
+}
+
+__global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n_layers_total)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, npair = nr / 2;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const RhsWarpSmem SL = rhs_warp_layout(ni, nr);
+    // block-shared tables: rate factors [nr+1] (uchar4), 16-bit descriptors [n_rhs]
+    uchar4 *rfac = reinterpret_cast<uchar4 *>(sm + (size_t)RHS_WPB * SL.total);
+    unsigned short *td = reinterpret_cast<unsigned short *>(rfac + (nr + 2));
+    for (int i = tid; i <= nr; i += blockDim.x) rfac[i] = A.net.rate_fac[i];
+    if (A.net.rhs_unit) for (int i = tid; i < A.net.n_rhs; i += blockDim.x) td[i] = A.net.rhs_desc16[i];
+    __syncthreads();
+
+    const int lay = blockIdx.x * RHS_WPB + w;
+    if (lay >= n_layers_total) return;
+    const int col = lay / nz, j = lay % nz;
+    double *ws = sm + (size_t)w * SL.total;
+    double *ym = ws + SL.ym, *y0 = ws + SL.y0, *yp = ws + SL.yp, *v = ws + SL.v, *chem_s = ws + SL.chem;
+    LayerScal *S = reinterpret_cast<LayerScal *>(ws + SL.scal);
+    double *ysum = ws + SL.scal + 10;         // [4] behind the 10 doubles of LayerScal
+
+    const size_t base = ((size_t)col * nz + j) * ni;
+    const double rr = 1. + 1. / sqrt(2.);
+    for (int i = lane; i < ni; i += 32) {
+        double v0 = A.y[base + i];
+        double vm = (j > 0) ? A.y[base - ni + i] : 0.0;
+        double vp = (j < nz - 1) ? A.y[base + ni + i] : 0.0;
+        if (A.k1) {   // yk2 = y + k1/r   (op.py:2917)
+            v0 = v0 + A.k1[base + i] / rr;
+            if (j > 0) vm = vm + A.k1[base - ni + i] / rr;
+            if (j < nz - 1) vp = vp + A.k1[base + ni + i] / rr;
+            if (A.yk2_out) A.yk2_out[base + i] = v0;
+        }
+        y0[i] = v0; ym[i] = vm; yp[i] = vp;
+    }
+    if (lane == 0) { y0[ni] = A.atm.M[col * A.atm.csz + j]; y0[ni + 1] = 1.0; }
+    __syncwarp();
+
+    // ---- pair rates v_p = rate[2p+1] - rate[2p+2], rate[i] = k[i]*f0*f1*f2*f3 in written order (padding slots multiply by 1.0)
+    const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
+    for (int p = lane; p < npair; p += 32) {
+        double r2[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = 2 * p + 1 + h;
+            const uchar4 f = rfac[i];
+            double x = kg[i];
+            if (!A.net.has_pow) {
+                x = x * y0[f.x]; x = x * y0[f.y]; x = x * y0[f.z]; x = x * y0[f.w];
+            } else {
+                const uchar4 pw = A.net.rate_pow[i];
+                const unsigned char ff[4] = {f.x, f.y, f.z, f.w}, pp[4] = {pw.x, pw.y, pw.z, pw.w};
+                for (int q = 0; q < 4; q++) {
+                    const double b = y0[ff[q]];
+                    const double tt = (pp[q] == 1) ? b : ((pp[q] == 2) ? b * b : pow(b, (double)pp[q]));
+                    x = x * tt;
+                }
+            }
+            r2[h] = x;
+        }
+        v[p] = r2[0] - r2[1];
+    }
+    // ---- the three layer sums (numpy association) and the layer scalars of the stencil
+    {
+        const int q = lane >> 3;
+        const int jj = j - 1 + q;
+        const bool act = (q < 3) && jj >= 0 && jj < nz;
+        const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+        double sres;
+        if (A.atm.n_gas > 0) {     // np.sum(y[:,gas_indx], axis=1) is a plain left-to-right sum (see row_sum)
+            sres = 0.0;
+            if (act && (lane & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, nullptr);
+        } else {
+            sres = np_pairwise_group8(row, ni, act);
+        }
+        if (act && (lane & 7) == 0) ysum[q] = sres;
+    }
+    __syncwarp();
+    const AtmLayer L = atm_at(A.atm, col);
+    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    if (lane < 3) {
+        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+        const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+        const double sp = ysp + ys0, smm = ys0 + ysm;
+        if (lane == 0) {
+            double x;
+            if (j == 0) x = ls[0] * sp / 2. / ys0;
+            else if (j == nz - 1) x = ls[0] * smm / 2. / ys0;
+            else x = ls[0] * (ls[1] * sp / 2. + ls[2] * smm / 2.) / ys0;
+            x += ls[5];
+            S->Aa = x; S->m1 = ls[8]; S->sp = sp; S->sm = smm; S->ys0 = ys0; S->ysp = ysp; S->ysm = ysm;
+        } else if (lane == 1) {
+            double x = 0.0;
+            if (j < nz - 1) { x = ls[3] * sp / 2. / ysp; x += ls[6]; }
+            S->Bb = x;
+        } else {
+            double x = 0.0;
+            if (j > 0) { x = ls[4] * smm / 2. / ysm; x += ls[7]; }
+            S->Cc = x;
+        }
+    }
+    __syncwarp();
+
+    // ---- chemistry: left-to-right sum of coef * v_p per species in network order (make_chem_funs.py:258-285)
+    const int *my_sp = A.net.rhs_lane_sp + lane * VK_RHS_SPL;
+    for (int slot = 0; slot < VK_RHS_SPL; slot++) {
+        const int s = my_sp[slot];
+        if (s < 0) break;
+        const int q0 = A.net.rhs_ptr[s], q1 = A.net.rhs_ptr[s + 1];
+        double chem = 0.0;
+        if (A.net.rhs_unit) {
+            // x - v is exactly x + (-1.0 * v): the sign is applied by flipping the sign bit of v
+            auto term = [&](int q) -> double {
+                const unsigned d = td[q];
+                const double x = v[d & 0x7fffu];
+                return __hiloint2double(__double2hiint(x) ^ (int)((d & 0x8000u) << 16), __double2loint(x));
+            };
+            int q = q0;
+            if (q < q1) { chem = term(q); q++; }
+            for (; q + 4 <= q1; q += 4) {
+                const double a0 = term(q), a1 = term(q + 1), a2 = term(q + 2), a3 = term(q + 3);
+                chem = chem + a0; chem = chem + a1; chem = chem + a2; chem = chem + a3;
+            }
+            for (; q < q1; q++) chem = chem + term(q);
+        } else {
+            for (int q = q0; q < q1; q++) {
+                const int t = A.net.rhs_term[q];
+                const double x = (double)((signed char)(t & 0xff)) * v[((t >> 8) - 1) >> 1];
+                chem = (q == q0) ? x : chem + x;
+            }
+        }
+        chem_s[s] = chem;
+    }
+    __syncwarp();
+
+    // ---- transport stencil + output, species i = lane, lane + 32, ...
+    const LayerScal s = *S;
+    const double *dzi = L.dzi;
+    const AtmPre &P = A.atm.pre;
+    for (int i = lane; i < ni; i += 32) {
+        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+        double diff;
+        if (j == 0) {
+            if (md) {
+                double Ai = P.QC[pb] * s.sp / 2. / s.ys0 + P.TA[pb];
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp + P.TB[pb];
+                if (st) {
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
+                }
+                diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
+            } else {
+                diff = s.Aa * y0[i] + s.Bb * yp[i];
+            }
+            if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
+        } else if (j == nz - 1) {
+            if (md) {
+                double Ai = P.QB[pb] * s.sm / 2. / s.ys0 - P.TA[pb];
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm - P.TC[pb];
+                if (st) {
+                    Ai = Ai + P.SA[pb];
+                    Ci = Ci + P.SC[pb];
+                }
+                diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
+            } else {
+                diff = s.Aa * y0[i] + s.Cc * ym[i];
+            }
+            if (A.atm.use_topflux) diff += L.top_flux[i] / dzi[nz - 2];
+        } else {
+            double t1 = s.Aa * y0[i] + s.Bb * yp[i] + s.Cc * ym[i];
+            if (md) {
+                double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
+                if (st) {
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
+                    Ci = Ci + P.SC[pb];
+                }
+                Ai += P.TA[pb];
+                Bi += P.TB[pb];
+                Ci += -P.TC[pb];
+                double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
+                diff = t1 + t2;
+            } else {
+                diff = t1;
+            }
+        }
+        const double chem = chem_s[i];
+        if (A.out_chem) A.out_chem[base + i] = chem;
+        if (A.out_diff) A.out_diff[base + i] = diff;
+        if (A.out_sum) {
+            double f = chem + diff;                                   // op.py:2892 / 2918
+            if (A.fix_mask && A.fix_mask[base + i]) f = 0.0;          // op.py:2904, 2924
+            if (A.k1) {
+                double c = 2. / (rr * A.dt[col]);
+                f = f - c * A.k1[base + i];                           // op.py:2928
+            }
+            A.out_sum[base + i] = f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 struct LhsArgs {
     NetDev net;
     AtmDev atm;
@@ -542,14 +769,21 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
 int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_chem, double *out_diff,
                const double *k1_for_rhs2, const double *dt_dev)
 {
-    if (c->ni > RHS_NT - RHS_TR0 - 3) { set_error("ni too large for rhs_kernel thread layout"); return VK_ERR_UNSUPPORTED; }
     RhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs;
     a.k1 = k1_for_rhs2; a.dt = dt_dev; a.yk2_out = k1_for_rhs2 ? c->yk2 : nullptr;
     a.out_sum = out_sum; a.out_chem = out_chem; a.out_diff = out_diff;
     a.fix_mask = c->opts.fix_mask;
-    size_t smem = sizeof(double) * (3 * (c->ni + 2) + 2 * (c->nr + 2) + 3 * c->ni + 4 + c->ni + 2) + sizeof(LayerScal) + 16;
-    rhs_kernel<<<c->ncol * c->nz, RHS_NT, smem, c->stream>>>(a);
+    const RhsWarpSmem SL = rhs_warp_layout(c->ni, c->nr);
+    const size_t smem = sizeof(double) * (size_t)RHS_WPB * SL.total + sizeof(uchar4) * (c->nr + 2) +
+                        sizeof(unsigned short) * (a.net.n_rhs + 8) + 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        VK_CUDA(cudaFuncSetAttribute(rhs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int n_layers = c->ncol * c->nz;
+    rhs_warp_kernel<<<(n_layers + RHS_WPB - 1) / RHS_WPB, RHS_WPB * 32, smem, c->stream>>>(a, n_layers);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }

@@ -11,6 +11,7 @@
 #define VK_KB 1.38064852e-16   // phy_const.py:3
 #define VK_NAVO 6.02214086e23  // phy_const.py:4
 #define VK_HC 1.98644582e-9    // phy_const.py:8
+#define VK_RHS_SPL 8            // species slots per lane in the warp-per-layer rhs kernel (ni <= 256)
 
 namespace vk {
 
@@ -35,6 +36,12 @@ struct NetDev {
     const int *jac_ptr;         // [n_ent+1]
     const ushort2 *jac_rc;      // [n_ent] (row, col)
     const uint2 *jac_term;      // [n_term] .x = k index | (coef8 << 16), .y = 3 factor bytes
+    // warp-per-layer rhs kernel: 16-bit term descriptors (bit 15 = minus, bits 0..14 = reaction pair (id-1)/2) when every
+    // stoichiometric coefficient is +-1 (rhs_unit), and the species each of the 32 lanes sums (longest chains first, then
+    // greedily balanced): rhs_lane_sp[lane][VK_RHS_SPL], -1 = none
+    int rhs_unit;
+    const unsigned short *rhs_desc16;   // [n_rhs]
+    const int *rhs_lane_sp;             // [32][VK_RHS_SPL]
     // Jacobian work schedule: entries cut into segments of <= 16 terms, sorted by length (warp lanes carry equal work)
     int n_seg, n_multi, n_part;
     const uint4 *jac_seg;       // [n_seg]   x = row | col << 16, y = first term, z = n terms | slot << 16 (slot 0xffff: whole entry)
