@@ -178,7 +178,42 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
     std::vector<uint4> segw(segs.size());
     for (size_t q = 0; q < segs.size(); q++)
         segw[q] = make_uint4(segs[q].rc, (unsigned)segs[q].q0, (unsigned)segs[q].len | ((unsigned)segs[q].ent << 16), 0u);
+    // multi-layer Jacobian kernel tables: distinct products + 16-bit term descriptors (coefficient codes, see lhs_ml_kernel)
+    std::vector<unsigned> uq;
+    std::vector<unsigned short> jt16(d->n_term);
+    std::vector<uint2> seg8(segs.size());
+    int ml_ok = (nr < 2048 && ni + 1 < 128 && d->n_term < 65536 && d->maxjf <= 3) ? 1 : 0;
+    if (ml_ok) {
+        std::vector<std::pair<unsigned, int>> keyed(d->n_term);
+        for (int q = 0; q < d->n_term; q++) {
+            unsigned f[3];
+            for (int x = 0; x < 3; x++) f[x] = (x < d->maxjf) ? (unsigned)d->jac_fac[q * d->maxjf + x] : (unsigned)(ni + 1);
+            keyed[q] = std::make_pair((unsigned)d->jac_k[q] | (f[0] << 11) | (f[1] << 18) | (f[2] << 25), q);
+        }
+        std::vector<std::pair<unsigned, int>> sorted = keyed;
+        std::sort(sorted.begin(), sorted.end());
+        std::vector<int> uidx(d->n_term);
+        for (size_t q = 0; q < sorted.size(); q++) {
+            if (q == 0 || sorted[q].first != sorted[q - 1].first) uq.push_back(sorted[q].first);
+            uidx[sorted[q].second] = (int)uq.size() - 1;
+        }
+        if (uq.size() >= 8192) ml_ok = 0;
+        static const int codes[8] = {1, -1, 2, -2, 4, -4, 3, -3};
+        for (int q = 0; q < d->n_term && ml_ok; q++) {
+            const int ci = (int)d->jac_coef[q];
+            int code = -1;
+            for (int x = 0; x < 8; x++) if (codes[x] == ci) code = x;
+            if (code < 0) { ml_ok = 0; break; }
+            jt16[q] = (unsigned short)(uidx[q] | (code << 13));
+        }
+        for (size_t q = 0; q < segs.size(); q++) {
+            const unsigned row = segs[q].rc & 0xffff, colx = segs[q].rc >> 16;
+            seg8[q] = make_uint2(row | (colx << 8) | ((unsigned)segs[q].len << 16), (unsigned)segs[q].q0 | ((unsigned)segs[q].ent << 16));
+        }
+    }
+    if (uq.empty()) uq.push_back(0);
     NetDev &nd = n->d;
+    nd.n_uniq = ml_ok ? (int)uq.size() : 0; nd.lhs_ml_ok = ml_ok;
     nd.ni = ni; nd.nr = nr; nd.nip = pad_block(ni);
     nd.n_seg = (int)segw.size(); nd.n_multi = (int)multi.size(); nd.n_part = n_part;
     nd.n_ent = d->n_ent; nd.n_term = d->n_term; nd.n_rhs = d->n_rhs; nd.max_rhs_len = max_len; nd.has_pow = has_pow;
@@ -186,6 +221,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
 #define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
     CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term); CP(segw, jac_seg); CP(multi, jac_multi);
     CP(rd16, rhs_desc16); CP(lane_sp, rhs_lane_sp);
+    CP(uq, jac_uniq); CP(jt16, jac_term16); CP(seg8, jac_seg8);
     nd.rhs_unit = rhs_unit;
 #undef CP
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);

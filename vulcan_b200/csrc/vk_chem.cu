@@ -766,6 +766,237 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// lhs_ml_kernel: the same block as lhs_kernel, restructured for throughput.
+//  * One thread block walks LHS_LPB consecutive layers of a column; the network tables (distinct products, 16-bit term descriptors,
+//    segment schedule - 40 KB for NCHO) are staged in shared memory ONCE per block, so the per-term work never waits on L2.
+//  * The 5953 Jacobian terms of NCHO are coefficient x one of only 1603 distinct products k_r y_a y_b y_c: the products are formed
+//    once per layer (phase A), a term is then one 16-bit descriptor, one product load, one multiply by +-1/2/4 (exact) and one add.
+//  * k and the three y rows of the NEXT layer are fetched with cp.async while the current layer is assembled; the finished block is
+//    streamed out with 16-byte stores and zeroed behind the copy.
+#define LHS_LPB 6
+__constant__ double c_jac_coef[8] = {1., -1., 2., -2., 4., -4., 3., -3.};
+
+struct LhsMlSmem {      // offsets in doubles
+    int kz, ym, y0, yp, dprod, part, misc, blk, tab, total_bytes;
+};
+static inline LhsMlSmem lhs_ml_layout(const NetDev &n, int ld)
+{
+    LhsMlSmem L;
+    int o = 0;
+    L.kz = o; o += n.nr + 2;
+    L.ym = o; o += n.ni + 2; L.y0 = o; o += n.ni + 2; L.yp = o; o += n.ni + 2;
+    L.dprod = o; o += n.n_uniq + 2;
+    L.part = o; o += n.n_part + 2;
+    L.misc = o; o += 16;
+    o += o & 1;
+    L.blk = o; o += ld * ld + (ld & 1);
+    L.tab = o;
+    size_t bytes = sizeof(double) * (size_t)o + sizeof(uint2) * (n.n_seg + 1) + sizeof(uint2) * (n.n_multi + 1) +
+                   sizeof(unsigned) * (n.n_uniq + 2) + sizeof(unsigned short) * (n.n_term + 8);
+    L.total_bytes = (int)((bytes + 15) & ~(size_t)15);
+    return L;
+}
+
+__device__ __forceinline__ void cp_async8(double *dst, const double *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col)
+{
+    extern __shared__ __align__(16) double sm[];
+    const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
+    const int col = blockIdx.x / blocks_per_col, j0 = (blockIdx.x % blocks_per_col) * LHS_LPB;
+    const int j1 = min(j0 + LHS_LPB, nz);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
+    double *ysum = sm + SL.misc, *ev = sm + SL.misc + 4, *ctab = sm + SL.misc + 8, *blk = sm + SL.blk;
+    uint2 *seg = reinterpret_cast<uint2 *>(sm + SL.tab);
+    uint2 *multi = seg + (A.net.n_seg + 1);
+    unsigned *uq = reinterpret_cast<unsigned *>(multi + (A.net.n_multi + 1));
+    unsigned short *tt = reinterpret_cast<unsigned short *>(uq + (A.net.n_uniq + 2));
+
+    auto prefetch = [&](int j) {      // k row and the three y rows of layer j -> shared memory (cp.async, 8 bytes each)
+        const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
+        for (int i = tid; i <= nr; i += nt) cp_async8(kz + i, kg + i);
+        const size_t base = ((size_t)col * nz + j) * ni;
+        for (int i = tid; i < ni; i += nt) {
+            cp_async8(y0 + i, A.y + base + i);
+            if (j > 0) cp_async8(ym + i, A.y + base - ni + i);
+            if (j < nz - 1) cp_async8(yp + i, A.y + base + ni + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(j0);
+    for (int i = tid; i < A.net.n_seg; i += nt) seg[i] = A.net.jac_seg8[i];
+    for (int i = tid; i < A.net.n_multi; i += nt) multi[i] = A.net.jac_multi[i];
+    for (int i = tid; i < A.net.n_uniq; i += nt) uq[i] = A.net.jac_uniq[i];
+    for (int i = tid; i < A.net.n_term; i += nt) tt[i] = A.net.jac_term16[i];
+    for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
+    if (tid == 0) { y0[ni + 1] = 1.0; }
+    if (tid < 8) ctab[tid] = c_jac_coef[tid];     // per-lane lookups: shared memory (a constant bank would serialise)
+    const AtmLayer L = atm_at(A.atm, col);
+    const double *dzi = L.dzi;
+    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const double rr = 1. + 1. / sqrt(2.);
+    const double c0 = 1. / (rr * A.dt[col]);
+    const AtmPre &P = A.atm.pre;
+
+    for (int j = j0; j < j1; j++) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tid == 0) y0[ni] = A.atm.M[col * A.atm.csz + j];
+        __syncthreads();
+        // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums
+        for (int u = tid; u < A.net.n_uniq; u += nt) {
+            const unsigned d = uq[u];
+            double x = kz[d & 0x7ffu];
+            x = x * y0[(d >> 11) & 0x7fu];
+            x = x * y0[(d >> 18) & 0x7fu];
+            x = x * y0[(d >> 25) & 0x7fu];
+            dprod[u] = x;
+        }
+        if (tid >= 224) {              // last warp: the three layer sums, 8 lanes each, numpy association
+            const int lane_ = tid - 224, q = lane_ >> 3;
+            const int jj = j - 1 + q;
+            const bool act = (q < 3) && jj >= 0 && jj < nz;
+            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+            double sres;
+            if (A.atm.n_gas_lhs > 0) {
+                sres = 0.0;
+                if (act && (lane_ & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, nullptr);
+            } else {
+                sres = np_pairwise_group8(row, ni, act);
+            }
+            if (act && (lane_ & 7) == 0) ysum[q] = sres;
+        }
+        __syncthreads();
+        if (j + 1 < j1) prefetch(j + 1);           // k / y of this layer are consumed: fetch the next layer behind the assembly
+        // ---- phase B: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work
+        for (int s = tid; s < A.net.n_seg; s += nt) {
+            const uint2 sg = seg[s];
+            const int q0 = (int)(sg.y & 0xffffu), n = (int)(sg.x >> 16);
+            double acc = 0.0;
+            for (int q = 0; q < n; q++) {
+                const unsigned d = tt[q0 + q];
+                acc += ctab[d >> 13] * dprod[d & 0x1fffu];
+            }
+            const unsigned slot = sg.y >> 16;
+            if (slot == 0xffffu) blk[(sg.x & 0xffu) * ld + ((sg.x >> 8) & 0xffu)] = -acc;
+            else part[slot] = acc;
+        }
+        __syncthreads();
+        // ---- phase C: split entries (fixed-order sum of their partials); species-independent eddy + advection parts
+        for (int m = tid; m < A.net.n_multi; m += nt) {
+            const uint2 me = multi[m];                 // x = row | col << 16, y = first slot | n << 16
+            const int s0 = (int)(me.y & 0xffff), n = (int)(me.y >> 16);
+            double acc = 0.0;
+            for (int q = 0; q < n; q++) acc += part[s0 + q];
+            blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
+        }
+        const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+        if (tid >= 224 && tid < 227) {
+            const int q = tid - 224;
+            double x = 0.0;
+            if (j == 0) {
+                if (q == 0) x = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
+                if (q == 1) x = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+            } else if (j == nz - 1) {
+                if (q == 0) x = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
+                if (q == 2) x = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+            } else {
+                if (q == 0) x = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
+                if (q == 1) x = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
+                if (q == 2) x = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+            }
+            ev[q] = x;
+        }
+        __syncthreads();
+        // ---- diagonal: c0 + negJ_ss - transport;  couplings up/dn   (op.py:1998-2040)
+        const double eA = ev[0], eB = ev[1], eC = ev[2];
+        const size_t base = ((size_t)col * nz + j) * ni;
+        const size_t vbase = ((size_t)col * nz + j) * ld;
+        for (int i = tid; i < ld; i += nt) {
+            if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
+                blk[i * ld + i] = 1.0;
+                A.up[vbase + i] = 0.0;
+                A.dn[vbase + i] = 0.0;
+                continue;
+            }
+            const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+            double d = c0 + blk[i * ld + i];
+            double u = 0.0, l = 0.0;
+            if (j == 0) {
+                d -= eA;
+                u -= eB;
+                if (md) {
+                    double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
+                    double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
+                    if (st) {
+                        ta = ta - P.SA[pb];
+                        tb = tb - P.SB[pb];
+                    }
+                    d -= ta;
+                    if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
+                    u -= tb;
+                } else {
+                    if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
+                }
+            } else if (j == nz - 1) {
+                d -= eA;
+                l -= eC;
+                if (md) {
+                    double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
+                    double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
+                    if (st) {
+                        ta = ta + P.SA[pb];
+                        tc = tc + P.SC[pb];
+                    }
+                    d -= ta;
+                    l -= tc;
+                }
+            } else {
+                d -= eA;
+                u -= eB;
+                l -= eC;
+                if (md) {
+                    double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
+                    double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
+                    double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
+                    if (st) {
+                        ta = ta - P.SA[pb];
+                        tb = tb - P.SB[pb];
+                        tc = tc + P.SC[pb];
+                    }
+                    d -= ta;
+                    u -= tb;
+                    l -= tc;
+                }
+            }
+            if (A.fix_mask && A.fix_mask[base + i]) {   // op.py:2903-2906: row -> 1/(r h) e_i
+                for (int t = 0; t < ni; t++) blk[i * ld + t] = 0.0;
+                d = c0; u = 0.0; l = 0.0;
+            }
+            blk[i * ld + i] = d;
+            A.up[vbase + i] = u;
+            A.dn[vbase + i] = l;
+        }
+        __syncthreads();
+        // ---- phase D: stream the block out and zero it behind the copy
+        double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
+        if ((ld & 1) == 0) {
+            for (int q = tid; q < ld * ld / 2; q += nt) {
+                reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
+                reinterpret_cast<double2 *>(blk)[q] = make_double2(0.0, 0.0);
+            }
+        } else {
+            for (int q = tid; q < ld * ld; q += nt) { Dg[q] = blk[q]; blk[q] = 0.0; }
+        }
+        // (the barrier at the top of the next iteration orders the zeroed block and the prefetched rows)
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_chem, double *out_diff,
                const double *k1_for_rhs2, const double *dt_dev)
 {
@@ -793,6 +1024,20 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     LhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
     a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask;
+    if (a.net.lhs_ml_ok) {
+        const LhsMlSmem SL = lhs_ml_layout(a.net, ld);
+        if (SL.total_bytes <= 227 * 1024) {
+            static int configured = 0;
+            if (SL.total_bytes > configured) {
+                VK_CUDA(cudaFuncSetAttribute(lhs_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total_bytes));
+                configured = SL.total_bytes;
+            }
+            const int bpc = (c->nz + LHS_LPB - 1) / LHS_LPB;
+            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc);
+            VK_CUDA(cudaGetLastError());
+            return VK_OK;
+        }
+    }
     const int np = c->net->d.n_part + (c->net->d.n_part & 1);
     size_t smem = sizeof(double) * (3 * (c->ni + 2) + (c->nr + 2) + 3 * c->ni + 4 + np + (size_t)ld * ld) + 16;
     static size_t configured = 0;

@@ -46,6 +46,11 @@ struct NetDev {
     int n_seg, n_multi, n_part;
     const uint4 *jac_seg;       // [n_seg]   x = row | col << 16, y = first term, z = n terms | slot << 16 (slot 0xffff: whole entry)
     const uint2 *jac_multi;     // [n_multi] x = row | col << 16, y = first slot | n slots << 16
+    // multi-layer Jacobian kernel: the 5953 terms of NCHO share 1603 distinct products k_r y_a y_b y_c
+    int n_uniq, lhs_ml_ok;      // lhs_ml_ok: packing limits hold (nr < 2048, ni + 1 < 128, n_uniq < 8192, n_term < 65536, coefficients in the table)
+    const unsigned *jac_uniq;   // [n_uniq]  r | f0 << 11 | f1 << 18 | f2 << 25
+    const unsigned short *jac_term16;   // [n_term] product index | coefficient code << 13
+    const uint2 *jac_seg8;      // [n_seg]   x = row | col << 8 | (n terms) << 16, y = first term | slot << 16
 };
 
 // atmosphere-only pieces of the transport stencil, [ncol_atm][nz][ni] each (see atm_pre_kernel)
