@@ -180,8 +180,9 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
         segw[q] = make_uint4(segs[q].rc, (unsigned)segs[q].q0, (unsigned)segs[q].len | ((unsigned)segs[q].ent << 16), 0u);
     // multi-layer Jacobian kernel tables: distinct products + 16-bit term descriptors (coefficient codes, see lhs_ml_kernel)
     std::vector<unsigned> uq;
-    std::vector<unsigned short> jt16(d->n_term);
-    std::vector<uint2> seg8(segs.size());
+    std::vector<unsigned short> jt16(d->n_term), ttT;
+    std::vector<unsigned> seg4;
+    std::vector<uint2> grp;
     int ml_ok = (nr < 2048 && ni + 1 < 128 && d->n_term < 65536 && d->maxjf <= 3) ? 1 : 0;
     if (ml_ok) {
         std::vector<std::pair<unsigned, int>> keyed(d->n_term);
@@ -197,7 +198,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
             if (q == 0 || sorted[q].first != sorted[q - 1].first) uq.push_back(sorted[q].first);
             uidx[sorted[q].second] = (int)uq.size() - 1;
         }
-        if (uq.size() >= 8192) ml_ok = 0;
+        if (uq.size() >= 8191) ml_ok = 0;
         static const int codes[8] = {1, -1, 2, -2, 4, -4, 3, -3};
         for (int q = 0; q < d->n_term && ml_ok; q++) {
             const int ci = (int)d->jac_coef[q];
@@ -206,14 +207,29 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
             if (code < 0) { ml_ok = 0; break; }
             jt16[q] = (unsigned short)(uidx[q] | (code << 13));
         }
-        for (size_t q = 0; q < segs.size(); q++) {
-            const unsigned row = segs[q].rc & 0xffff, colx = segs[q].rc >> 16;
-            seg8[q] = make_uint2(row | (colx << 8) | ((unsigned)segs[q].len << 16), (unsigned)segs[q].q0 | ((unsigned)segs[q].ent << 16));
+        // groups of 32 segments (already sorted by decreasing length), terms transposed, padded with the zero product
+        const unsigned short pad = (unsigned short)uq.size();          // dprod[n_uniq] = 0.0, code 0 (x 1.0)
+        for (size_t g0 = 0; g0 < segs.size() && ml_ok; g0 += 32) {
+            const int nmax = segs[g0].len;
+            grp.push_back(make_uint2((unsigned)ttT.size(), (unsigned)nmax));
+            const size_t base = ttT.size();
+            ttT.resize(base + (size_t)32 * nmax, pad);
+            for (int l = 0; l < 32; l++) {
+                if (g0 + l < segs.size()) {
+                    const Seg &sg = segs[g0 + l];
+                    for (int q = 0; q < sg.len; q++) ttT[base + (size_t)32 * q + l] = jt16[sg.q0 + q];
+                    seg4.push_back((sg.rc & 0xff) | (((sg.rc >> 16) & 0xff) << 8) | ((unsigned)sg.ent << 16));
+                } else {
+                    seg4.push_back(0xffu | (0xffu << 8) | (0xffffu << 16));
+                }
+            }
         }
     }
+    if (grp.empty()) { grp.push_back(make_uint2(0, 0)); seg4.resize(32, 0xffffffffu); ttT.push_back(0); }
     if (uq.empty()) uq.push_back(0);
     NetDev &nd = n->d;
     nd.n_uniq = ml_ok ? (int)uq.size() : 0; nd.lhs_ml_ok = ml_ok;
+    nd.n_grp = (int)grp.size(); nd.n_tt = (int)ttT.size();
     nd.ni = ni; nd.nr = nr; nd.nip = pad_block(ni);
     nd.n_seg = (int)segw.size(); nd.n_multi = (int)multi.size(); nd.n_part = n_part;
     nd.n_ent = d->n_ent; nd.n_term = d->n_term; nd.n_rhs = d->n_rhs; nd.max_rhs_len = max_len; nd.has_pow = has_pow;
@@ -221,7 +237,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
 #define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
     CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term); CP(segw, jac_seg); CP(multi, jac_multi);
     CP(rd16, rhs_desc16); CP(lane_sp, rhs_lane_sp);
-    CP(uq, jac_uniq); CP(jt16, jac_term16); CP(seg8, jac_seg8);
+    CP(uq, jac_uniq); CP(ttT, jac_tt); CP(seg4, jac_seg4); CP(grp, jac_grp);
     nd.rhs_unit = rhs_unit;
 #undef CP
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);
@@ -642,3 +658,30 @@ int vk_stream(vk_column *c, void **cuda_stream)
 }
 
 }  // extern "C"
+
+// debug / profiling aid (not part of the public header): time `reps` launches of one kernel of the step on the resident state.
+// which: 0 = lhs, 1 = rhs (stage 1), 2 = factor, 3 = solve (backward only), 4 = solve (forward + backward)
+extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms)
+{
+    if (!c || !ms || reps < 1) return VK_ERR_INVALID;
+    VK_CUDA(cudaSetDevice(c->net->device));
+    cudaEvent_t a, b;
+    VK_CUDA(cudaEventCreate(&a));
+    VK_CUDA(cudaEventCreate(&b));
+    int rc = VK_OK;
+    VK_CUDA(cudaEventRecord(a, c->stream));
+    for (int r = 0; r < reps && rc == VK_OK; r++) {
+        if (which == 0) rc = vk::launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
+        else if (which == 1) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);
+        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f, c->z);
+        else if (which == 3) rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 1);
+        else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 0);
+    }
+    VK_CUDA(cudaEventRecord(b, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    VK_CUDA(cudaEventElapsedTime(ms, a, b));
+    *ms /= reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return rc;
+}

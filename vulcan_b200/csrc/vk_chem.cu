@@ -11,6 +11,8 @@
 //
 // This translation unit is compiled with -fmad=false: every expression is evaluated with one IEEE rounding per operation in
 // the reference's order, so chemdf and diffdf are bit-identical to the numpy reference (tests/test_gpu_parity.py).
+#include <cstdlib>
+
 #include "vk_internal.cuh"
 #include "vk_device_math.cuh"
 
@@ -773,7 +775,7 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
 //    once per layer (phase A), a term is then one 16-bit descriptor, one product load, one multiply by +-1/2/4 (exact) and one add.
 //  * k and the three y rows of the NEXT layer are fetched with cp.async while the current layer is assembled; the finished block is
 //    streamed out with 16-byte stores and zeroed behind the copy.
-#define LHS_LPB 6
+#define LHS_LPB 10
 __constant__ double c_jac_coef[8] = {1., -1., 2., -2., 4., -4., 3., -3.};
 
 struct LhsMlSmem {      // offsets in doubles
@@ -791,8 +793,8 @@ static inline LhsMlSmem lhs_ml_layout(const NetDev &n, int ld)
     o += o & 1;
     L.blk = o; o += ld * ld + (ld & 1);
     L.tab = o;
-    size_t bytes = sizeof(double) * (size_t)o + sizeof(uint2) * (n.n_seg + 1) + sizeof(uint2) * (n.n_multi + 1) +
-                   sizeof(unsigned) * (n.n_uniq + 2) + sizeof(unsigned short) * (n.n_term + 8);
+    size_t bytes = sizeof(double) * (size_t)o + sizeof(uint2) * (n.n_grp + 1) + sizeof(uint2) * (n.n_multi + 1) +
+                   sizeof(unsigned) * (n.n_uniq + 2) + sizeof(unsigned) * ((size_t)n.n_grp * 32) + sizeof(unsigned short) * (n.n_tt + 8);
     L.total_bytes = (int)((bytes + 15) & ~(size_t)15);
     return L;
 }
@@ -802,7 +804,7 @@ __device__ __forceinline__ void cp_async8(double *dst, const double *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col)
+__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col, int dbg)
 {
     extern __shared__ __align__(16) double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
@@ -811,10 +813,11 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
     const int tid = threadIdx.x, nt = blockDim.x;
     double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
     double *ysum = sm + SL.misc, *ev = sm + SL.misc + 4, *ctab = sm + SL.misc + 8, *blk = sm + SL.blk;
-    uint2 *seg = reinterpret_cast<uint2 *>(sm + SL.tab);
-    uint2 *multi = seg + (A.net.n_seg + 1);
+    uint2 *grp = reinterpret_cast<uint2 *>(sm + SL.tab);
+    uint2 *multi = grp + (A.net.n_grp + 1);
     unsigned *uq = reinterpret_cast<unsigned *>(multi + (A.net.n_multi + 1));
-    unsigned short *tt = reinterpret_cast<unsigned short *>(uq + (A.net.n_uniq + 2));
+    unsigned *seg = uq + (A.net.n_uniq + 2);
+    unsigned short *tt = reinterpret_cast<unsigned short *>(seg + (size_t)A.net.n_grp * 32);
 
     auto prefetch = [&](int j) {      // k row and the three y rows of layer j -> shared memory (cp.async, 8 bytes each)
         const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
@@ -828,10 +831,16 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(j0);
-    for (int i = tid; i < A.net.n_seg; i += nt) seg[i] = A.net.jac_seg8[i];
+    for (int i = tid; i < A.net.n_grp; i += nt) grp[i] = A.net.jac_grp[i];
+    for (int i = tid; i < A.net.n_grp * 32; i += nt) seg[i] = A.net.jac_seg4[i];
     for (int i = tid; i < A.net.n_multi; i += nt) multi[i] = A.net.jac_multi[i];
     for (int i = tid; i < A.net.n_uniq; i += nt) uq[i] = A.net.jac_uniq[i];
-    for (int i = tid; i < A.net.n_term; i += nt) tt[i] = A.net.jac_term16[i];
+    {   // 16-bit descriptors copied as 32-bit words (the table is 4-byte aligned and padded)
+        const unsigned *src = reinterpret_cast<const unsigned *>(A.net.jac_tt);
+        unsigned *dst = reinterpret_cast<unsigned *>(tt);
+        for (int i = tid; i < (A.net.n_tt + 1) / 2; i += nt) dst[i] = src[i];
+    }
+    if (tid == 0) dprod[A.net.n_uniq] = 0.0;      // the padding product
     for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
     if (tid == 0) { y0[ni + 1] = 1.0; }
     if (tid < 8) ctab[tid] = c_jac_coef[tid];     // per-lane lookups: shared memory (a constant bank would serialise)
@@ -847,7 +856,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         if (tid == 0) y0[ni] = A.atm.M[col * A.atm.csz + j];
         __syncthreads();
         // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums
-        for (int u = tid; u < A.net.n_uniq; u += nt) {
+        if (!(dbg & 4)) for (int u = tid; u < A.net.n_uniq; u += nt) {
             const unsigned d = uq[u];
             double x = kz[d & 0x7ffu];
             x = x * y0[(d >> 11) & 0x7fu];
@@ -871,18 +880,67 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         }
         __syncthreads();
         if (j + 1 < j1) prefetch(j + 1);           // k / y of this layer are consumed: fetch the next layer behind the assembly
-        // ---- phase B: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work
-        for (int s = tid; s < A.net.n_seg; s += nt) {
-            const uint2 sg = seg[s];
-            const int q0 = (int)(sg.y & 0xffffu), n = (int)(sg.x >> 16);
-            double acc = 0.0;
-            for (int q = 0; q < n; q++) {
-                const unsigned d = tt[q0 + q];
-                acc += ctab[d >> 13] * dprod[d & 0x1fffu];
+        // atmosphere-only stencil pieces of my species / the layer scalars: fetched now, consumed after the gather (their L2
+        // latency hides behind phase B instead of sitting between two barriers)
+        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+        double pQ = 0., pQm = 0., pQB = 0., pQC = 0., pTA = 0., pTB = 0., pTC = 0., pSA = 0., pSB = 0., pSC = 0., pvd = 0.;
+        double pl8 = 0., pl9 = 0.;
+        double lsr[10];
+        if (tid < ni) {
+            const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + tid;
+            if (md) {
+                pQ = P.Q[pb]; if (j > 0) pQm = P.Q[pb - ni];
+                pQB = P.QB[pb]; pQC = P.QC[pb]; pTA = P.TA[pb]; pTB = P.TB[pb]; pTC = P.TC[pb];
+                if (st) { pSA = P.SA[pb]; pSB = P.SB[pb]; pSC = P.SC[pb]; }
             }
-            const unsigned slot = sg.y >> 16;
-            if (slot == 0xffffu) blk[(sg.x & 0xffu) * ld + ((sg.x >> 8) & 0xffu)] = -acc;
-            else part[slot] = acc;
+            if (A.atm.use_botflux && j == 0) pvd = L.bot_vdep[tid];
+            if (j > 0 && j < nz - 1) { pl8 = ls[8]; pl9 = ls[9]; }
+        }
+        if (tid >= 224 && tid < 227) {
+#pragma unroll
+            for (int q = 0; q < 10; q++) lsr[q] = ls[q];
+        }
+        // ---- phase B: groups of 32 segments (<= 16 terms each, sorted by length); one warp works on TWO groups at a time (two
+        // independent accumulation chains); term q of lane l at tt[base + 32 q + l]: conflict-free 16-bit loads, warp-uniform trip
+        // counts, no divergence
+        {
+            const int nw = nt >> 5, lane = tid & 31;
+            if (!(dbg & 2)) for (int gI = tid >> 5; gI < A.net.n_grp; gI += 2 * nw) {
+                const int gJ = gI + nw;
+                const bool two = gJ < A.net.n_grp;
+                const uint2 ga = grp[gI], gb = grp[two ? gJ : gI];
+                const unsigned short *ta = tt + ga.x + lane, *tb = tt + gb.x + lane;
+                const int na = (int)ga.y, nb = two ? (int)gb.y : 0;     // na >= nb (sorted by decreasing length)
+                double acc_a = 0.0, acc_b = 0.0;
+                int q = 0;
+#pragma unroll 2
+                for (; q < nb; q++) {
+                    const unsigned da = ta[32 * q], db = tb[32 * q];
+                    acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
+                    acc_b += ctab[db >> 13] * dprod[db & 0x1fffu];
+                }
+#pragma unroll 2
+                for (; q < na; q++) {
+                    const unsigned da = ta[32 * q];
+                    acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
+                }
+                {
+                    const unsigned sg = seg[gI * 32 + lane];
+                    const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+                    if (row != 0xffu) {
+                        if (slot == 0xffffu) blk[row * ld + colx] = -acc_a;
+                        else part[slot] = acc_a;
+                    }
+                }
+                if (two) {
+                    const unsigned sg = seg[gJ * 32 + lane];
+                    const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+                    if (row != 0xffu) {
+                        if (slot == 0xffffu) blk[row * ld + colx] = -acc_b;
+                        else part[slot] = acc_b;
+                    }
+                }
+            }
         }
         __syncthreads();
         // ---- phase C: split entries (fixed-order sum of their partials); species-independent eddy + advection parts
@@ -894,20 +952,19 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
             blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
         }
         const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
         if (tid >= 224 && tid < 227) {
             const int q = tid - 224;
             double x = 0.0;
             if (j == 0) {
-                if (q == 0) x = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
-                if (q == 1) x = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+                if (q == 0) x = lsr[0] * (ysp + ys0) / (2. * ys0) + lsr[5];
+                if (q == 1) x = lsr[3] * (ysp + ys0) / (2. * ysp) + lsr[6];
             } else if (j == nz - 1) {
-                if (q == 0) x = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
-                if (q == 2) x = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+                if (q == 0) x = lsr[0] * (ysm + ys0) / (2. * ys0) + lsr[5];
+                if (q == 2) x = lsr[4] * (ysm + ys0) / (2. * ysm) + lsr[7];
             } else {
-                if (q == 0) x = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
-                if (q == 1) x = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
-                if (q == 2) x = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+                if (q == 0) x = lsr[8] * (lsr[1] * (ysp + ys0) / 2. + lsr[2] * (ysm + ys0) / 2.) / ys0 + lsr[5];
+                if (q == 1) x = lsr[9] * (lsr[1] * (ysp + ys0) / (2. * ysp)) + lsr[6];
+                if (q == 2) x = lsr[9] * (lsr[2] * (ysm + ys0) / (2. * ysm)) + lsr[7];
             }
             ev[q] = x;
         }
@@ -916,41 +973,41 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         const double eA = ev[0], eB = ev[1], eC = ev[2];
         const size_t base = ((size_t)col * nz + j) * ni;
         const size_t vbase = ((size_t)col * nz + j) * ld;
-        for (int i = tid; i < ld; i += nt) {
+        const double ls8 = pl8, ls9 = pl9;
+        if (!(dbg & 8)) for (int i = tid; i < ld; i += nt) {
             if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
                 blk[i * ld + i] = 1.0;
                 A.up[vbase + i] = 0.0;
                 A.dn[vbase + i] = 0.0;
                 continue;
             }
-            const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
             double d = c0 + blk[i * ld + i];
             double u = 0.0, l = 0.0;
             if (j == 0) {
                 d -= eA;
                 u -= eB;
                 if (md) {
-                    double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
-                    double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
+                    double ta = pQC * (ysp + ys0) / (2. * ys0) + pTA;
+                    double tb = pQB * (ysp + ys0) / (2. * ysp) + pTB;
                     if (st) {
-                        ta = ta - P.SA[pb];
-                        tb = tb - P.SB[pb];
+                        ta = ta - pSA;
+                        tb = tb - pSB;
                     }
                     d -= ta;
-                    if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
+                    if (A.atm.use_botflux) d -= -1. * pvd / dzi[0];
                     u -= tb;
                 } else {
-                    if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
+                    if (A.atm.use_botflux) d -= -1. * pvd / dzi[0];
                 }
             } else if (j == nz - 1) {
                 d -= eA;
                 l -= eC;
                 if (md) {
-                    double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
-                    double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
+                    double ta = pQB * (ys0 + ysm) / (2. * ys0) - pTA;
+                    double tc = pQC * (ys0 + ysm) / (2. * ysm) - pTC;
                     if (st) {
-                        ta = ta + P.SA[pb];
-                        tc = tc + P.SC[pb];
+                        ta = ta + pSA;
+                        tc = tc + pSC;
                     }
                     d -= ta;
                     l -= tc;
@@ -960,13 +1017,13 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
                 u -= eB;
                 l -= eC;
                 if (md) {
-                    double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
-                    double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
-                    double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
+                    double ta = ls8 * (pQ * (ysp + ys0) / 2. + pQm * (ysm + ys0) / 2.) / ys0 + pTA;
+                    double tb = ls9 * (pQ * (ysp + ys0) / (2. * ysp)) + pTB;
+                    double tc = ls9 * (pQm * (ysm + ys0) / (2. * ysm)) - pTC;
                     if (st) {
-                        ta = ta - P.SA[pb];
-                        tb = tb - P.SB[pb];
-                        tc = tc + P.SC[pb];
+                        ta = ta - pSA;
+                        tb = tb - pSB;
+                        tc = tc + pSC;
                     }
                     d -= ta;
                     u -= tb;
@@ -984,7 +1041,8 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         __syncthreads();
         // ---- phase D: stream the block out and zero it behind the copy
         double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
-        if ((ld & 1) == 0) {
+        if (dbg & 1) {
+        } else if ((ld & 1) == 0) {
             for (int q = tid; q < ld * ld / 2; q += nt) {
                 reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
                 reinterpret_cast<double2 *>(blk)[q] = make_double2(0.0, 0.0);
@@ -1033,7 +1091,9 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
                 configured = SL.total_bytes;
             }
             const int bpc = (c->nz + LHS_LPB - 1) / LHS_LPB;
-            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc);
+            static int dbg = -1;
+            if (dbg < 0) { const char *e = getenv("VK_LHS_DBG"); dbg = e ? atoi(e) : 0; }
+            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, dbg);
             VK_CUDA(cudaGetLastError());
             return VK_OK;
         }

@@ -49,8 +49,12 @@ struct NetDev {
     // multi-layer Jacobian kernel: the 5953 terms of NCHO share 1603 distinct products k_r y_a y_b y_c
     int n_uniq, lhs_ml_ok;      // lhs_ml_ok: packing limits hold (nr < 2048, ni + 1 < 128, n_uniq < 8192, n_term < 65536, coefficients in the table)
     const unsigned *jac_uniq;   // [n_uniq]  r | f0 << 11 | f1 << 18 | f2 << 25
-    const unsigned short *jac_term16;   // [n_term] product index | coefficient code << 13
-    const uint2 *jac_seg8;      // [n_seg]   x = row | col << 8 | (n terms) << 16, y = first term | slot << 16
+    // segments in groups of 32 (one per lane), terms stored TRANSPOSED inside a group: term q of lane l at jac_tt[base_g + 32 q + l],
+    // padded to the group's longest segment with a descriptor of the always-zero product n_uniq (bank-conflict free, no divergence)
+    int n_grp, n_tt;
+    const unsigned short *jac_tt;       // [n_tt]   product index | coefficient code << 13
+    const unsigned *jac_seg4;           // [n_grp*32] row | col << 8 | slot << 16 (slot 0xffff: whole entry; row 0xff: padding lane)
+    const uint2 *jac_grp;               // [n_grp]  x = base into jac_tt, y = terms per lane
 };
 
 // atmosphere-only pieces of the transport stencil, [ncol_atm][nz][ni] each (see atm_pre_kernel)
