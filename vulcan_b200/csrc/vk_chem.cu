@@ -769,13 +769,12 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
 
 // ------------------------------------------------------------------------------------------------------------------
 // lhs_ml_kernel: the same block as lhs_kernel, restructured for throughput.
-//  * One thread block walks LHS_LPB consecutive layers of a column; the network tables (distinct products, 16-bit term descriptors,
+//  * One thread block walks `lpb` (1..30, chosen by the launcher) consecutive layers of a column; the network tables (distinct products, 16-bit term descriptors,
 //    segment schedule - 40 KB for NCHO) are staged in shared memory ONCE per block, so the per-term work never waits on L2.
 //  * The 5953 Jacobian terms of NCHO are coefficient x one of only 1603 distinct products k_r y_a y_b y_c: the products are formed
 //    once per layer (phase A), a term is then one 16-bit descriptor, one product load, one multiply by +-1/2/4 (exact) and one add.
 //  * k and the three y rows of the NEXT layer are fetched with cp.async while the current layer is assembled; the finished block is
 //    streamed out with 16-byte stores and zeroed behind the copy.
-#define LHS_LPB 10
 __constant__ double c_jac_coef[8] = {1., -1., 2., -2., 4., -4., 3., -3.};
 
 struct LhsMlSmem {      // offsets in doubles
@@ -804,15 +803,16 @@ __device__ __forceinline__ void cp_async8(double *dst, const double *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col, int dbg)
+__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col, int lpb, int dbg)
 {
     extern __shared__ __align__(16) double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
-    const int col = blockIdx.x / blocks_per_col, j0 = (blockIdx.x % blocks_per_col) * LHS_LPB;
-    const int j1 = min(j0 + LHS_LPB, nz);
+    const int col = blockIdx.x / blocks_per_col, j0 = (blockIdx.x % blocks_per_col) * lpb;
+    const int j1 = min(j0 + lpb, nz);
     const int tid = threadIdx.x, nt = blockDim.x;
     double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
-    double *ysum = sm + SL.misc, *ev = sm + SL.misc + 4, *ctab = sm + SL.misc + 8, *blk = sm + SL.blk;
+    double *ysum = sm + SL.misc, *ctab = sm + SL.misc + 8, *blk = sm + SL.blk;
+    int *gctr = reinterpret_cast<int *>(sm + SL.misc + 4);   // group counter of the gather
     uint2 *grp = reinterpret_cast<uint2 *>(sm + SL.tab);
     uint2 *multi = grp + (A.net.n_grp + 1);
     unsigned *uq = reinterpret_cast<unsigned *>(multi + (A.net.n_multi + 1));
@@ -844,6 +844,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
     for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
     if (tid == 0) { y0[ni + 1] = 1.0; }
     if (tid < 8) ctab[tid] = c_jac_coef[tid];     // per-lane lookups: shared memory (a constant bank would serialise)
+    if (tid == 0) *gctr = 0;
     const AtmLayer L = atm_at(A.atm, col);
     const double *dzi = L.dzi;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
@@ -880,33 +881,87 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         }
         __syncthreads();
         if (j + 1 < j1) prefetch(j + 1);           // k / y of this layer are consumed: fetch the next layer behind the assembly
-        // atmosphere-only stencil pieces of my species / the layer scalars: fetched now, consumed after the gather (their L2
-        // latency hides behind phase B instead of sitting between two barriers)
-        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
-        double pQ = 0., pQm = 0., pQB = 0., pQC = 0., pTA = 0., pTB = 0., pTC = 0., pSA = 0., pSB = 0., pSC = 0., pvd = 0.;
-        double pl8 = 0., pl9 = 0.;
-        double lsr[10];
-        if (tid < ni) {
-            const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + tid;
-            if (md) {
-                pQ = P.Q[pb]; if (j > 0) pQm = P.Q[pb - ni];
-                pQB = P.QB[pb]; pQC = P.QC[pb]; pTA = P.TA[pb]; pTB = P.TB[pb]; pTC = P.TC[pb];
-                if (st) { pSA = P.SA[pb]; pSB = P.SB[pb]; pSC = P.SC[pb]; }
+        // ---- transport part of the diagonal and the couplings up/dn (op.py:1998-2040): independent of the chemical Jacobian, so the
+        // threads that own a species do it FIRST (6 true divisions, ~1500 clk of latency) and then join the gather, which hands out
+        // its groups through a shared counter - the other warps start gathering at once.
+        const size_t base = ((size_t)col * nz + j) * ni;
+        const size_t vbase = ((size_t)col * nz + j) * ld;
+        double eA = 0.0, tA = 0.0, tV = 0.0;       // subtracted from the diagonal in this order after the gather
+        if (tid < ld && !(dbg & 8)) {
+            const int i = tid;
+            if (i >= ni) {
+                A.up[vbase + i] = 0.0;
+                A.dn[vbase + i] = 0.0;
+            } else {
+                const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+                const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+                const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+                double eB = 0.0, eC = 0.0, u = 0.0, l = 0.0;
+                if (j == 0) {
+                    eA = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
+                    eB = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+                    u -= eB;
+                    if (md) {
+                        double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
+                        double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
+                        if (st) {
+                            ta = ta - P.SA[pb];
+                            tb = tb - P.SB[pb];
+                        }
+                        tA = ta;
+                        u -= tb;
+                    }
+                    if (A.atm.use_botflux) tV = -1. * L.bot_vdep[i] / dzi[0];
+                } else if (j == nz - 1) {
+                    eA = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
+                    eC = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+                    l -= eC;
+                    if (md) {
+                        double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
+                        double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
+                        if (st) {
+                            ta = ta + P.SA[pb];
+                            tc = tc + P.SC[pb];
+                        }
+                        tA = ta;
+                        l -= tc;
+                    }
+                } else {
+                    eA = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
+                    eB = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
+                    eC = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+                    u -= eB;
+                    l -= eC;
+                    if (md) {
+                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
+                        double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
+                        double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
+                        if (st) {
+                            ta = ta - P.SA[pb];
+                            tb = tb - P.SB[pb];
+                            tc = tc + P.SC[pb];
+                        }
+                        tA = ta;
+                        u -= tb;
+                        l -= tc;
+                    }
+                }
+                if (A.fix_mask && A.fix_mask[base + i]) { u = 0.0; l = 0.0; }
+                A.up[vbase + i] = u;
+                A.dn[vbase + i] = l;
             }
-            if (A.atm.use_botflux && j == 0) pvd = L.bot_vdep[tid];
-            if (j > 0 && j < nz - 1) { pl8 = ls[8]; pl9 = ls[9]; }
         }
-        if (tid >= 224 && tid < 227) {
-#pragma unroll
-            for (int q = 0; q < 10; q++) lsr[q] = ls[q];
-        }
-        // ---- phase B: groups of 32 segments (<= 16 terms each, sorted by length); one warp works on TWO groups at a time (two
+        // ---- phase B: groups of 32 segments (<= 16 terms each, sorted by length), two adjacent groups per warp and turn (two
         // independent accumulation chains); term q of lane l at tt[base + 32 q + l]: conflict-free 16-bit loads, warp-uniform trip
         // counts, no divergence
         {
-            const int nw = nt >> 5, lane = tid & 31;
-            if (!(dbg & 2)) for (int gI = tid >> 5; gI < A.net.n_grp; gI += 2 * nw) {
-                const int gJ = gI + nw;
+            const int lane = tid & 31;
+            while (!(dbg & 2)) {
+                int gI = 0;
+                if (lane == 0) gI = atomicAdd(gctr, 2);
+                gI = __shfl_sync(0xffffffffu, gI, 0);
+                if (gI >= A.net.n_grp) break;
+                const int gJ = gI + 1;
                 const bool two = gJ < A.net.n_grp;
                 const uint2 ga = grp[gI], gb = grp[two ? gJ : gI];
                 const unsigned short *ta = tt + ga.x + lane, *tb = tt + gb.x + lane;
@@ -943,7 +998,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
             }
         }
         __syncthreads();
-        // ---- phase C: split entries (fixed-order sum of their partials); species-independent eddy + advection parts
+        // ---- phase C: split entries (fixed-order sum of their partials)
         for (int m = tid; m < A.net.n_multi; m += nt) {
             const uint2 me = multi[m];                 // x = row | col << 16, y = first slot | n << 16
             const int s0 = (int)(me.y & 0xffff), n = (int)(me.y >> 16);
@@ -951,92 +1006,24 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
             for (int q = 0; q < n; q++) acc += part[s0 + q];
             blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
         }
-        const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-        if (tid >= 224 && tid < 227) {
-            const int q = tid - 224;
-            double x = 0.0;
-            if (j == 0) {
-                if (q == 0) x = lsr[0] * (ysp + ys0) / (2. * ys0) + lsr[5];
-                if (q == 1) x = lsr[3] * (ysp + ys0) / (2. * ysp) + lsr[6];
-            } else if (j == nz - 1) {
-                if (q == 0) x = lsr[0] * (ysm + ys0) / (2. * ys0) + lsr[5];
-                if (q == 2) x = lsr[4] * (ysm + ys0) / (2. * ysm) + lsr[7];
-            } else {
-                if (q == 0) x = lsr[8] * (lsr[1] * (ysp + ys0) / 2. + lsr[2] * (ysm + ys0) / 2.) / ys0 + lsr[5];
-                if (q == 1) x = lsr[9] * (lsr[1] * (ysp + ys0) / (2. * ysp)) + lsr[6];
-                if (q == 2) x = lsr[9] * (lsr[2] * (ysm + ys0) / (2. * ysm)) + lsr[7];
-            }
-            ev[q] = x;
-        }
+        if (tid == 0) *gctr = 0;
         __syncthreads();
-        // ---- diagonal: c0 + negJ_ss - transport;  couplings up/dn   (op.py:1998-2040)
-        const double eA = ev[0], eB = ev[1], eC = ev[2];
-        const size_t base = ((size_t)col * nz + j) * ni;
-        const size_t vbase = ((size_t)col * nz + j) * ld;
-        const double ls8 = pl8, ls9 = pl9;
-        if (!(dbg & 8)) for (int i = tid; i < ld; i += nt) {
+        // ---- diagonal: c0 + negJ_ss - transport
+        if (tid < ld && !(dbg & 8)) {
+            const int i = tid;
             if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
                 blk[i * ld + i] = 1.0;
-                A.up[vbase + i] = 0.0;
-                A.dn[vbase + i] = 0.0;
-                continue;
-            }
-            double d = c0 + blk[i * ld + i];
-            double u = 0.0, l = 0.0;
-            if (j == 0) {
-                d -= eA;
-                u -= eB;
-                if (md) {
-                    double ta = pQC * (ysp + ys0) / (2. * ys0) + pTA;
-                    double tb = pQB * (ysp + ys0) / (2. * ysp) + pTB;
-                    if (st) {
-                        ta = ta - pSA;
-                        tb = tb - pSB;
-                    }
-                    d -= ta;
-                    if (A.atm.use_botflux) d -= -1. * pvd / dzi[0];
-                    u -= tb;
-                } else {
-                    if (A.atm.use_botflux) d -= -1. * pvd / dzi[0];
-                }
-            } else if (j == nz - 1) {
-                d -= eA;
-                l -= eC;
-                if (md) {
-                    double ta = pQB * (ys0 + ysm) / (2. * ys0) - pTA;
-                    double tc = pQC * (ys0 + ysm) / (2. * ysm) - pTC;
-                    if (st) {
-                        ta = ta + pSA;
-                        tc = tc + pSC;
-                    }
-                    d -= ta;
-                    l -= tc;
-                }
             } else {
+                double d = c0 + blk[i * ld + i];
                 d -= eA;
-                u -= eB;
-                l -= eC;
-                if (md) {
-                    double ta = ls8 * (pQ * (ysp + ys0) / 2. + pQm * (ysm + ys0) / 2.) / ys0 + pTA;
-                    double tb = ls9 * (pQ * (ysp + ys0) / (2. * ysp)) + pTB;
-                    double tc = ls9 * (pQm * (ysm + ys0) / (2. * ysm)) - pTC;
-                    if (st) {
-                        ta = ta - pSA;
-                        tb = tb - pSB;
-                        tc = tc + pSC;
-                    }
-                    d -= ta;
-                    u -= tb;
-                    l -= tc;
+                if (md) d -= tA;
+                if (A.atm.use_botflux && j == 0) d -= tV;
+                if (A.fix_mask && A.fix_mask[base + i]) {   // op.py:2903-2906: row -> 1/(r h) e_i
+                    for (int t = 0; t < ni; t++) blk[i * ld + t] = 0.0;
+                    d = c0;
                 }
+                blk[i * ld + i] = d;
             }
-            if (A.fix_mask && A.fix_mask[base + i]) {   // op.py:2903-2906: row -> 1/(r h) e_i
-                for (int t = 0; t < ni; t++) blk[i * ld + t] = 0.0;
-                d = c0; u = 0.0; l = 0.0;
-            }
-            blk[i * ld + i] = d;
-            A.up[vbase + i] = u;
-            A.dn[vbase + i] = l;
         }
         __syncthreads();
         // ---- phase D: stream the block out and zero it behind the copy
@@ -1090,10 +1077,14 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
                 VK_CUDA(cudaFuncSetAttribute(lhs_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total_bytes));
                 configured = SL.total_bytes;
             }
-            const int bpc = (c->nz + LHS_LPB - 1) / LHS_LPB;
+            // layers per block: amortise the table staging (40 KB per block) but keep >= ~8 blocks per SM in the grid
+            int lpb = (int)(((long long)c->ncol * c->nz) / (8 * 148));
+            lpb = std::max(1, std::min(lpb, 30));
+            { const char *e = getenv("VK_LHS_LPB"); if (e) lpb = atoi(e); }
+            const int bpc = (c->nz + lpb - 1) / lpb;
             static int dbg = -1;
             if (dbg < 0) { const char *e = getenv("VK_LHS_DBG"); dbg = e ? atoi(e) : 0; }
-            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, dbg);
+            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
             VK_CUDA(cudaGetLastError());
             return VK_OK;
         }
