@@ -59,6 +59,25 @@ typedef struct {
 int vk_network_create(const vk_network_desc *desc, int device, vk_network **out);
 void vk_network_destroy(vk_network *net);
 
+/* ---- rate coefficients on the device: replaces ReadRate.read_rate / lim_lowT_rates / rev_rate / remove_rate (op.py:63-342)
+ * and the generated chem_funs.Gibbs (make_chem_funs.py:568-580, thermo/gibbs_text.txt).  Tables come from
+ * vulcan_b200/rates.py::RateTable; all arrays are indexed by reaction PAIR p (forward id 2p+1, reverse 2p+2). */
+typedef struct {
+    int npair;
+    const int *kind;            /* [npair] 0 zero (photo/ion/condensation rows), 1 a T^n exp(-E/T), 2 + high-pressure limit, 3 OH+CH3+M */
+    const double *arrhenius;    /* [npair][6] a, n, E, a_inf, n_inf, E_inf (op.py:154-163) */
+    const int *cap_kind;        /* [npair] low-temperature limits (op.py:320-342): 0 none, 1 Lindemann form, 2 constant */
+    const double *cap;          /* [npair][2] threshold temperature, value */
+    const unsigned char *reverse; /* [npair] reverse rate k_f / K_eq (even id < stop_rev_indx, op.py:289-304) */
+    const unsigned char *removed; /* [npair] bit 0: forward id in remove_list, bit 1: reverse id in remove_list (op.py:311-317) */
+    const int *gibbs_ptr;       /* [npair+1] */
+    const int *gibbs_sp;        /* species of every Gibbs term, written order, M skipped */
+    const int *gibbs_nu;        /* -n for reactants, +n for products */
+    const int *dnu;             /* [npair] n_reac - n_prod: K_eq carries (kb T / 1e6)^dnu */
+    const double *nasa9;        /* [ni][20] NASA-9 coefficients, 200-1000 K then 1000-6000 K (thermo/NASA9/<species>.txt) */
+} vk_rate_desc;
+int vk_rates_set(vk_network *net, const vk_rate_desc *desc);
+
 /* ---- columns --------------------------------------------------------------------------------------------- */
 int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out);
 void vk_column_destroy(vk_column *col);
@@ -82,6 +101,11 @@ int vk_set_atm(vk_column *col, const vk_atm_view *atm);
 
 /* rate coefficients: var.k packed [ncol][nz][nr+1] (or one copy when shared != 0) */
 int vk_set_k(vk_column *col, const double *k, int shared);
+/* rate coefficients computed ON the device from temperature and total number density (needs vk_rates_set):
+ * Tco, M [ncol][nz], or [nz] when shared != 0.  Photolysis rows are zero until vk_photo_update fills them. */
+int vk_compute_k(vk_column *col, const double *Tco, const double *M, int shared);
+/* read the device copy of k back: [ncol][nz][nr+1], or [nz][nr+1] when it is shared */
+int vk_get_k(vk_column *col, double *k);
 /* overwrite whole reactions (e.g. the photolysis J rows after compute_J, op.py:2785-2786):
  * rows[n_rows] reaction ids, vals [ncol][n_rows][nz] */
 int vk_set_k_rows(vk_column *col, int n_rows, const int *rows, const double *vals);

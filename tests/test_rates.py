@@ -1,0 +1,80 @@
+"""Rate coefficients: the numpy oracle (oracle/rates_oracle.py) is pinned BIT-IDENTICAL to the reference's own
+var.k (<cfg>_static.npz, written by the unmodified reference: read_rate + lim_lowT_rates + rev_rate + remove_rate, op.py:63-342,
+chem_funs.Gibbs); the device kernel (vk_compute_k) is then checked against the oracle to 1e-12 relative: libm vs CUDA pow / exp / log
+differ by an ulp, and K_eq = exp(-sum nu g/RT) amplifies one ulp of the sum by |sum| (up to ~700 in the cold layers of Jupiter / Earth:
+measured 1.1e-13 there, 2e-14 for the hot Jupiters)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLD, load_network
+
+TAGS = ["HD189", "Jupiter", "Earth", "HD209S"]
+LOW_T = {"Jupiter": True}            # cfg_examples/vulcan_cfg_Jupiter.py:7
+
+
+def _load(tag):
+    net = load_network(tag)
+    st = np.load(os.path.join(GOLD, tag + "_static.npz"))
+    nasa9 = np.load(os.path.join(GOLD, tag + "_nasa9.npz"))["coef"]
+    ci, pi = int(st["conden_indx"]), int(st["photo_indx"])
+    hi = ci if ci > 0 else pi        # rows from here on are condensation / photolysis rows (set elsewhere, zero at set-up)
+    return net, st, nasa9, hi
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_matches_reference_k_bit_for_bit(tag):
+    import rates_oracle
+    net, st, nasa9, hi = _load(tag)
+    with np.errstate(over="ignore"):
+        k = rates_oracle.compute_k(net, st["Tco"], st["M"], nasa9, use_lowT_limit_rates=LOW_T.get(tag, False))
+    assert np.array_equal(k[1:hi], st["k"][1:hi])
+    assert not k[hi:].any()
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_rate_table_structure(tag):
+    from vulcan_b200.rates import RateTable
+    net, st, nasa9, hi = _load(tag)
+    rt = RateTable(net, nasa9, use_lowT_limit_rates=LOW_T.get(tag, False))
+    assert rt.npair * 2 == net.nr and rt.gibbs_ptr[-1] == len(rt.gibbs_sp)
+    # reverse rates exactly where the reference has them (non-zero even rows below stop_rev_indx)
+    ref_rev = np.array([st["k"][2 * p + 2].any() for p in range(rt.npair)])
+    below = np.array([2 * p + 2 < hi for p in range(rt.npair)])
+    assert np.array_equal(ref_rev & below, (rt.reverse == 1) & below & ref_rev)
+    assert (rt.kind[[r.id // 2 for r in net.reactions if r.id >= hi]] == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", TAGS)
+def test_device_rates_vs_oracle(tag):
+    import rates_oracle
+    from vulcan_b200 import _abi
+    from vulcan_b200.rates import RateTable
+    net, st, nasa9, hi = _load(tag)
+    nz = int(st["nz"])
+    with np.errstate(over="ignore"):
+        ref = rates_oracle.compute_k(net, st["Tco"], st["M"], nasa9, use_lowT_limit_rates=LOW_T.get(tag, False))
+    dn = _abi.DeviceNetwork(net)
+    dn.set_rates(RateTable(net, nasa9, use_lowT_limit_rates=LOW_T.get(tag, False)))
+    col = _abi.Columns(dn, nz, 1)
+    col.compute_k(st["Tco"], st["M"])
+    k = col.get_k().T                                  # [nr+1, nz]
+    assert k.shape == ref.shape
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(k), fin)         # exp overflow of K_eq in cold layers -> k_rev = 0 on both sides
+    rel = np.abs(k - ref)[fin] / np.maximum(np.abs(ref[fin]), 1e-300)
+    print("%s: device k vs oracle max rel %.2e over %d entries" % (tag, rel.max(), fin.sum()))
+    assert rel.max() < 1e-12
+    assert np.array_equal(k == 0, ref == 0)
+    # per-column T-P: two columns, the second 5 % hotter
+    col2 = _abi.Columns(dn, nz, 2)
+    T2 = np.stack([st["Tco"], np.minimum(st["Tco"] * 1.05, 6000.)])
+    col2.compute_k(T2, np.stack([st["M"], st["M"]]))
+    k2 = col2.get_k()
+    assert np.array_equal(k2[0].T, k)
+    with np.errstate(over="ignore"):
+        ref2 = rates_oracle.compute_k(net, T2[1], st["M"], nasa9, use_lowT_limit_rates=LOW_T.get(tag, False))
+    fin = np.isfinite(ref2)
+    assert np.max(np.abs(k2[1].T - ref2)[fin] / np.maximum(np.abs(ref2[fin]), 1e-300)) < 1e-12

@@ -24,7 +24,7 @@ SYMBOLS = [
     "vk_column_create", "vk_column_destroy", "vk_set_atm", "vk_set_k", "vk_set_k_rows", "vk_set_step_opts",
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
-    "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream",
+    "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
 ]
 
 
@@ -32,6 +32,13 @@ class VulcanB200Error(RuntimeError):
     def __init__(self, code, msg):
         RuntimeError.__init__(self, "vulcan_b200 error %d: %s" % (code, msg))
         self.code = code
+
+
+class RateDesc(C.Structure):
+    _fields_ = [("npair", C.c_int), ("kind", C.POINTER(C.c_int)), ("arrhenius", C.POINTER(C.c_double)), ("cap_kind", C.POINTER(C.c_int)),
+                ("cap", C.POINTER(C.c_double)), ("reverse", C.POINTER(C.c_ubyte)), ("removed", C.POINTER(C.c_ubyte)),
+                ("gibbs_ptr", C.POINTER(C.c_int)), ("gibbs_sp", C.POINTER(C.c_int)), ("gibbs_nu", C.POINTER(C.c_int)),
+                ("dnu", C.POINTER(C.c_int)), ("nasa9", C.POINTER(C.c_double))]
 
 
 class NetworkDesc(C.Structure):
@@ -104,6 +111,9 @@ def load():
     lib.vk_photo_update.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
     lib.vk_photo_read.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
     lib.vk_photo_reset.argtypes = [_vp]
+    lib.vk_rates_set.argtypes = [_vp, C.POINTER(RateDesc)]
+    lib.vk_compute_k.argtypes = [_vp, _dp, _dp, C.c_int]
+    lib.vk_get_k.argtypes = [_vp, _dp]
     lib.vk_ens_setup.argtypes = [_vp, C.POINTER(EnsOpts)]
     lib.vk_ens_set_state.argtypes = [_vp, _dp, _dp]
     lib.vk_ens_run.argtypes = [_vp, C.c_int]
@@ -164,6 +174,17 @@ class DeviceNetwork(object):
         check(self.lib.vk_network_create(C.byref(d), int(device), C.byref(h)))
         self.handle = h
         self.ni, self.nr, self.device = t["ni"], t["nr"], device
+
+    def set_rates(self, rate_table):
+        """upload a vulcan_b200.rates.RateTable (vk_rates_set): enables Columns.compute_k."""
+        r = rate_table
+        bp = lambda a: a.ctypes.data_as(C.POINTER(C.c_ubyte))
+        self._rates_keep = r
+        arr, cap = f64(r.arrhenius), f64(r.cap)
+        self._rates_arrays = (arr, cap)
+        d = RateDesc(int(r.npair), iptr(r.kind), dptr(arr), iptr(r.cap_kind), dptr(cap), bp(r.reverse), bp(r.removed),
+                     iptr(r.gibbs_ptr), iptr(r.gibbs_sp), iptr(r.gibbs_nu), iptr(r.dnu), dptr(r.nasa9))
+        check(self.lib.vk_rates_set(self.handle, C.byref(d)))
 
     def close(self):
         if getattr(self, "handle", None):
@@ -245,6 +266,21 @@ class Columns(object):
             raise ValueError("k: expected %s, got %s" % (want, k.shape))
         check(self.lib.vk_set_k(self.handle, dptr(k), int(shared)))
         self._k_shared = bool(shared)
+
+    def compute_k(self, Tco, M):
+        """rate coefficients on the device (needs DeviceNetwork.set_rates): Tco, M [nz] (shared) or [ncol, nz]."""
+        Tco, M = f64(Tco), f64(M)
+        shared = Tco.ndim == 1
+        want = (self.nz,) if shared else (self.ncol, self.nz)
+        if Tco.shape != want or M.shape != want:
+            raise ValueError("Tco / M: expected %s" % (want,))
+        check(self.lib.vk_compute_k(self.handle, dptr(Tco), dptr(M), int(shared)))
+        self._k_shared = bool(shared)
+
+    def get_k(self):
+        k = np.empty((self.nz, self.nr + 1) if getattr(self, "_k_shared", True) else (self.ncol, self.nz, self.nr + 1))
+        check(self.lib.vk_get_k(self.handle, dptr(k)))
+        return k
 
     def set_k_rows(self, rows, vals):
         rows, vals = i32(rows), f64(vals)

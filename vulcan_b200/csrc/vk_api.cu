@@ -19,6 +19,7 @@ int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *
                 double *nega_dev, int *anyneg_dev);
 void photo_destroy(vk_column *c);
 void ens_destroy(vk_column *c);
+void rates_destroy(vk_network *n);
 
 template <typename T>
 static int dev_copy(std::vector<void *> &allocs, const T *host, size_t n, const T **out)
@@ -93,6 +94,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
     VK_CUDA(cudaSetDevice(device));
     vk_network *n = new vk_network();
     n->device = device;
+    n->rates = nullptr;
     const int ni = d->ni, nr = d->nr;
     std::vector<uchar4> rf(nr + 1), rp(nr + 1);
     int has_pow = 0;
@@ -250,6 +252,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
 void vk_network_destroy(vk_network *n)
 {
     if (!n) return;
+    rates_destroy(n);
     for (void *p : n->allocs) cudaFree(p);
     delete n;
 }

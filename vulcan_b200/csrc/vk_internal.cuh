@@ -88,10 +88,12 @@ struct StepOptsDev {
 
 }  // namespace vk
 
+struct RateTables;
 struct vk_network {
     int device;
     vk::NetDev d;
     std::vector<void *> allocs;
+    RateTables *rates;          // on-device rate-coefficient tables (vk_rates_set), optional
 };
 
 struct PhotoState;
