@@ -51,28 +51,33 @@ def synthetic_columns(y_base, n_0, compo, atom_names, kzz_scale, met_scale, c_to
     return y, atom_ini
 
 
+def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine):
+    """a vk_column handle for `ncol` columns of a sweep: per-column Kzz, everything else of the atmosphere replicated."""
+    col = _abi.Columns(devnet, nz, ncol)
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (ncol,) + np.shape(a)))
+    a = atm_common
+    col.set_atm(Kzz=np.ascontiguousarray(kzz), vz=rep(a["vz"]), dzi=rep(a["dzi"]), Dzz=rep(a["Dzz"]), vs=rep(a["vs"]),
+                Tco=rep(a["Tco"]), g=rep(a["g"]), M=rep(a["M"]), Ti=rep(a["Ti"]), Hpi=rep(a["Hpi"]), ms=rep(a["ms"]),
+                alpha=rep(a["alpha"]), top_flux=rep(a["top_flux"]), bot_flux=rep(a["bot_flux"]),
+                bot_vdep=rep(a["bot_vdep"]), use_moldiff=a["use_moldiff"], use_settling=a["use_settling"],
+                use_topflux=a["use_topflux"], use_botflux=a["use_botflux"], gas_indx=a.get("gas_indx"),
+                gas_indx_lhs=a.get("gas_indx_lhs"), shared=False)
+    col.set_k(k)                                        # thermal + photolysis rates shared by the sweep (same T-P, same star)
+    col.set_step_opts(cfg["mtol"], cfg["atol"], refine=refine)
+    return col
+
+
 class EnsembleRunner(object):
     """The columns [lo, hi) of an ensemble resident on one GPU, advanced by the device-resident controller."""
 
     def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=0):
         self.ncol = y.shape[0]
         self.devnet = _abi.DeviceNetwork(network, device)
-        self.col = _abi.Columns(self.devnet, nz, self.ncol)
-        ni = network.ni
-        rep = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (self.ncol,) + np.shape(a)))
-        a = atm_common
-        self.col.set_atm(Kzz=np.ascontiguousarray(kzz), vz=rep(a["vz"]), dzi=rep(a["dzi"]), Dzz=rep(a["Dzz"]), vs=rep(a["vs"]),
-                         Tco=rep(a["Tco"]), g=rep(a["g"]), M=rep(a["M"]), Ti=rep(a["Ti"]), Hpi=rep(a["Hpi"]), ms=rep(a["ms"]),
-                         alpha=rep(a["alpha"]), top_flux=rep(a["top_flux"]), bot_flux=rep(a["bot_flux"]),
-                         bot_vdep=rep(a["bot_vdep"]), use_moldiff=a["use_moldiff"], use_settling=a["use_settling"],
-                         use_topflux=a["use_topflux"], use_botflux=a["use_botflux"], gas_indx=a.get("gas_indx"),
-                         gas_indx_lhs=a.get("gas_indx_lhs"), shared=False)
-        self.col.set_k(k)                                   # thermal + photolysis rates shared by the sweep (same T-P, same star)
-        self.col.set_step_opts(cfg["mtol"], cfg["atol"], refine=refine)
+        self.col = _make_columns(self.devnet, nz, self.ncol, atm_common, kzz, k, cfg, refine)
         self.col.ens_setup(cfg["rtol"], cfg["loss_eps"], cfg["dt_min"], cfg["dt_max"], cfg["dt_var_min"], cfg["dt_var_max"],
                            cfg["pos_cut"], cfg["nega_cut"], compo, atom_ini, np.broadcast_to(n_0, (self.ncol, nz)))
         self.col.ens_set_state(y, dt)
-        self.ni = ni
+        self.ni = network.ni
 
     def run(self, n_steps):
         self.col.ens_run(n_steps)
@@ -80,6 +85,40 @@ class EnsembleRunner(object):
 
     def state(self, want_y=True):
         return self.col.ens_get_state(want_y)
+
+
+class PipelinedHostSolver(object):
+    """`vk_ros2_solve` on HOST buffers for a large batch of columns (the reference-facing call: y, ymix, dt in; sol, ymix, delta
+    out).  The batch is split into `n_groups` vk_column handles, each with its own CUDA stream, driven from a thread pool (the
+    ctypes calls release the GIL): the H2D copy of one group, the kernels of another and the D2H copy of a third overlap, so the
+    host round trip costs max(transfer, compute) instead of their sum.  Pass page-locked arrays (e.g. numpy views of pinned torch
+    tensors) to have them DMA'd directly."""
+
+    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=4, device=0, refine=0):
+        from concurrent.futures import ThreadPoolExecutor
+        self.ncol = kzz.shape[0]
+        self.nz, self.ni = nz, network.ni
+        self.devnet = _abi.DeviceNetwork(network, device)
+        n_groups = max(1, min(n_groups, self.ncol))
+        self.bounds = [partition(self.ncol, n_groups, g) for g in range(n_groups)]
+        self.cols = [_make_columns(self.devnet, nz, hi - lo, atm_common, kzz[lo:hi], k, cfg, refine) for lo, hi in self.bounds]
+        self.pool = ThreadPoolExecutor(max_workers=n_groups)
+
+    def solve_into(self, y, ymix, dt, sol, ymix_out, delta, status):
+        """all arrays C-contiguous float64 ([ncol, nz, ni] / [ncol]); status int32 [ncol]"""
+        per = self.nz * self.ni
+        y, ymix, sol, ymix_out = (a.reshape(self.ncol * per) for a in (y, ymix, sol, ymix_out))
+
+        def one(g):
+            lo, hi = self.bounds[g]
+            self.cols[g].ros2_solve_into(y[lo * per:hi * per], ymix[lo * per:hi * per], dt[lo:hi], sol[lo * per:hi * per],
+                                         ymix_out[lo * per:hi * per], delta[lo:hi], status[lo:hi])
+        list(self.pool.map(one, range(len(self.cols))))
+
+    def close(self):
+        self.pool.shutdown()
+        for c in self.cols:
+            c.close()
 
 
 def gather_final(local_ymix, world_size, rank, device):
