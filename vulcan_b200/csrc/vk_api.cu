@@ -1,5 +1,6 @@
 // C ABI glue (include/vulcan_b200.h): handles, host<->device staging, kernel sequencing for one attempted Ros2 step.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "vk_internal.cuh"
@@ -601,6 +602,10 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
     if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
     if (!D || !up || !dn || !rhs || !x) { set_error("null buffer"); return VK_ERR_INVALID; }
     VK_CUDA(cudaSetDevice(c->net->device));
+    {   // a non-sticky error left behind by an unrelated earlier runtime call must not be blamed on this one
+        cudaError_t stale = cudaGetLastError();
+        if (stale != cudaSuccess && getenv("VK_DEBUG")) fprintf(stderr, "vulcan_b200: stale CUDA error at vk_blocktri_solve entry: %s\n", cudaGetErrorString(stale));
+    }
     const size_t nblk = (size_t)c->ncol * c->nz, nv = nblk * c->ni;
     double *Dd = nullptr, *upd = nullptr, *dnd = nullptr;
     VK_CUDA(cudaMalloc((void **)&Dd, sizeof(double) * nv * c->ni));
