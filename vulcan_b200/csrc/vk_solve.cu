@@ -163,7 +163,7 @@ __device__ long long g_trace[128 * 8];
 #define TRACE(kk, ev, dep) do { } while (0)
 #endif
 
-enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3, VK_BAR_RAW = 5 };   // + panel parity
+enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3, VK_BAR_RAW = 5, VK_BAR_COLS = 7 };   // + panel parity (not COLS)
 
 template <int NIP, int MINB>
 __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(FactorArgs a)
@@ -209,7 +209,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         // idle warps of the spread layout: only the two block-wide barriers of every layer
         for (int j = 0; j < nz; j++) {
             if (__syncthreads_or(0)) return;
-            __syncthreads();
         }
         return;
     }
@@ -251,8 +250,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 step(std::integral_constant<int, 0>{}, m);
                 if (m + 1 < NR) step(std::integral_constant<int, 1>{}, m + 1);
             }
-            if (__syncthreads_or(bad)) return;
-            __syncthreads();
+            if (__syncthreads_or(bad)) return;     // the one block-wide barrier of a layer (the second one is among the column warps)
         }
         return;
     }
@@ -260,49 +258,43 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     // ================= column warps =================
     const int c0 = 8 * w + 2 * t;        // my columns c0, c0+1 ; my rows 8*i + g
     double A[NR][2];
-    double zreg = 0.0;                   // z_{j-1}[tid] for tid < NIP
     auto publish_raw = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < NR; i++)
             *reinterpret_cast<double2 *>(mraw + ((size_t)buf * NIP + 8 * i + g) * 8 + 2 * t) = make_double2(A[i][0], A[i][1]);
     };
 
-    for (int j = 0; j < nz; j++) {
-        if (w == 0) TRACE(100, 0, zreg);
-        // ---- S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}); W_{j-1} is still in A; D_j, up, dn arrive by TMA
-        double rj = 0.0;
-        if (fuse && tid < ni) rj = a.rhs[(cbase + j) * ni + tid];
-        mbar_wait(mbar, j & 1);
-        {
-            double u0 = 0.0, u1 = 0.0;
-            if (j > 0) { u0 = updn[c0]; u1 = updn[c0 + 1]; }
-#pragma unroll
-            for (int i = 0; i < NR; i++) {
-                const int r = 8 * i + g;
-                const double2 d = *reinterpret_cast<const double2 *>(dbuf + r * NIP + c0);
-                if (j > 0) {
-                    const double l = updn[NIP + r];
-                    A[i][0] = d.x - (l * A[i][0]) * u0;
-                    A[i][1] = d.y - (l * A[i][1]) * u1;
-                } else {
-                    A[i][0] = d.x;
-                    A[i][1] = d.y;
-                }
-            }
-        }
-        if (fuse && tid < NIP) tvec[tid] = (j == 0) ? rj : rj - updn[NIP + tid] * zreg;
+    // tiles the inverse warp needs for P_0 and P_1 of a layer (from warps 0 and 1), raw columns of panel 0
+    auto publish_first = [&]() {
         if (w == 0) {
-            TRACE(100, 1, A[0][0]);
             *reinterpret_cast<double2 *>(hbuf + 64 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
             bar_arrive<VK_BAR_TILE, 64>();
             *reinterpret_cast<double2 *>(hraw + 64 + g * 8 + 2 * t) = make_double2(A[1][0], A[1][1]);
             bar_arrive<VK_BAR_RAW + 1, 64>();
-            publish_raw(0);
         } else if (w == 1) {
             *reinterpret_cast<double2 *>(hbuf + 128 + g * 8 + 2 * t) = make_double2(A[0][0], A[0][1]);
             *reinterpret_cast<double2 *>(hbuf + 128 + 64 + g * 8 + 2 * t) = make_double2(A[1][0], A[1][1]);
             bar_arrive<VK_BAR_TILE + 1, 64>();
         }
+    };
+    // ---- layer 0: S_0 = D_0
+    {
+        double r0 = 0.0;
+        if (fuse && tid < ni) r0 = a.rhs[cbase * ni + tid];
+        mbar_wait(mbar, 0);
+#pragma unroll
+        for (int i = 0; i < NR; i++) {
+            const double2 d = *reinterpret_cast<const double2 *>(dbuf + (8 * i + g) * NIP + c0);
+            A[i][0] = d.x;
+            A[i][1] = d.y;
+        }
+        if (fuse && tid < NIP) tvec[tid] = r0;
+        publish_first();
+        if (w == 0) publish_raw(0);
+    }
+
+    for (int j = 0; j < nz; j++) {
+        if (w == 0) TRACE(100, 0, A[0][0]);
         double u0 = 0.0, u1 = 0.0;       // B fragments of my pivot-row tile of the coming panel
         if (w != 0) to_bfrag(A[0][0], A[0][1], g, t, u0, u1);
         auto panel = [&](auto ktc) {
@@ -396,10 +388,21 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
             return;
         }
-        // ---- W_j = A : stays in registers for the next layer; written out; fused forward elimination
+        // ---- W_j = A: written out, forward elimination of stage 1 fused (z_j = W_j (r_j - dn_j z_{j-1})), and - tile by tile, behind
+        // the store - the Schur update of the NEXT layer, S_{j+1} = D_{j+1} - diag(dn_{j+1}) W_j diag(up_j) (D, up, dn already in shared
+        // memory by TMA).  Warps 0 and 1 hand their first two new tiles to the inverse warp as soon as they exist, so the P_0 chain of
+        // layer j+1 runs behind the rest of this write-out instead of in front of idle column warps.
+        const bool more = j + 1 < nz;
+        double rnext = 0.0;
+        if (fuse && more && tid < ni) rnext = a.rhs[(cbase + j + 1) * ni + tid];
         double *Wj = a.W + (cbase + j) * NIP * NIP;
         double tv0 = 0.0, tv1 = 0.0;
         if (fuse) { tv0 = tvec[c0]; tv1 = tvec[c0 + 1]; }
+        double su0 = 0.0, su1 = 0.0;
+        if (more) {
+            mbar_wait(mbar, (j + 1) & 1);
+            su0 = updn[c0]; su1 = updn[c0 + 1];
+        }
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int r = 8 * i + g;
@@ -410,16 +413,24 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 part += __shfl_xor_sync(0xffffffffu, part, 2);
                 if (t == 0) zpart[w * NIP + r] = part;
             }
+            if (more) {
+                const double2 d = *reinterpret_cast<const double2 *>(dbuf + r * NIP + c0);
+                const double l = updn[NIP + r];
+                A[i][0] = d.x - (l * A[i][0]) * su0;
+                A[i][1] = d.y - (l * A[i][1]) * su1;
+                if (i == 1) publish_first();
+            }
         }
-        __syncthreads();
-        if (fuse && tid < NIP) {   // z_j = W_j (r_j - dn_j * z_{j-1})
+        if (more && w == 0) publish_raw(0);
+        bar_sync<VK_BAR_COLS, NW * 32>();
+        if (fuse && tid < NIP) {   // z_j = W_j (r_j - dn_j * z_{j-1}); right-hand side of the next layer's elimination
             double acc = 0.0;
 #pragma unroll
             for (int q = 0; q < NW; q++) acc += zpart[q * NIP + tid];
-            zreg = acc;
             a.z[(cbase + j) * NIP + tid] = acc;
+            if (more) tvec[tid] = rnext - updn[NIP + tid] * acc;
         }
-        if (w == 0) TRACE(100, 4, zreg);
+        if (w == 0) TRACE(100, 4, A[0][0]);
         // (the panel barriers of the next layer order the zpart / tvec reuse)
     }
 }
