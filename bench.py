@@ -53,17 +53,20 @@ def build_columns(case, lo, hi):
 
 
 class ClockSampler(object):
-    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line).  The sampler is started ahead of the region
+    (nvidia-smi needs ~0.1 s to emit its first line) at a 20 ms period; every line is stamped when it is read and only the lines
+    that fall inside [mark_begin, mark_end] are used - a region shorter than one period falls back to the nearest lines."""
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -71,16 +74,29 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        t0, t1 = self.t0 or 0.0, self.t1 or time.time()
+        inside = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.03]
+        note = None
+        if not inside and self.rows:       # region shorter than a sampling period: the lines closest to it
+            mid = 0.5 * (t0 + t1)
+            inside = [r for ts, r in sorted(self.rows, key=lambda x: abs(x[0] - mid))[:3]]
+            note = "timed region shorter than the sampling period: nearest samples"
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -89,8 +105,11 @@ class ClockSampler(object):
                         reasons.add(n)
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "period_ms": 20}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_fp64_peak(device):
@@ -224,12 +243,15 @@ def main():
     runner.col.ens_set_state(y, np.full(ncol, dt0))         # every timed run starts from the same state
     runner.run(1)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    time.sleep(0.25)                                         # let nvidia-smi reach its sampling loop before the timed region
+    barrier()
+    sampler.mark_begin()
     t_wall0 = time.time()
     ms = runner.run(args.steps)                              # CUDA events on the handle's stream bracket exactly K steps
     barrier()
     wall = time.time() - t_wall0
+    sampler.mark_end()
     clocks = sampler.stop()
     tms = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
