@@ -10,6 +10,8 @@ Fixture levels:
   L2  clip / loss / step_ok (op.py:2447-2493)
   L4  compute_tau / compute_flux / compute_J (op.py:2580-2786)
   L5  full run trajectory (written by --full): per-step (t, dt, delta), final y
+  L6  condensation operators of the caller (written by --conden): inputs / outputs of Integration.conden and
+      *_conden_evap_relax (op.py:1109-1421) at selected counts + the fix_species switch (op.py:862-893)
 
 usage (from the repo root):
   python oracle/stage_reference.py --config HD189
@@ -125,6 +127,11 @@ def capture_step(s, tag, count):
                atom_loss_in=np.array([var.atom_loss.get(a, 0.0) for a in cfg.atom_list]),
                fix_species_start=para.fix_species_start)
     out.update(dyn_atm(atm))
+    if cfg.use_condense and para.fix_species_start:       # the state Ros2.solver's fixed-species rows read (op.py:2896-2906, 2960-2970)
+        out["fix_species"] = np.array(list(cfg.fix_species))
+        out["fix_y"] = np.array([var.fix_y[sp] for sp in cfg.fix_species])
+        out["conden_min_lev"] = np.array([int(atm.conden_min_lev[sp]) for sp in cfg.fix_species])
+        out["fix_from_coldtrap"] = bool(cfg.fix_species_from_coldtrap_lev)
     # ---- L0: components, evaluated by the reference functions on a copy of the state
     y = var.y.copy()
     if not cfg.use_vm_mol and cfg.use_moldiff and not cfg.use_settling:
@@ -232,7 +239,74 @@ def capture_photo(s, tag, count, nsub=16):
     print("wrote", path, "aflux_change=%.3e,%.3e" % (out["aflux_change1"], out["aflux_change2"]), flush=True)
 
 
-def run(config, refdir, steps, full, max_steps=None):
+def hook_conden(s, tag, counts, store):
+    """L6: wrap the reference's own condensation operators (bound methods of op.Integration) and record what they read and
+    write at the counts in `counts`, plus every call's (count, name) in order.  Nothing numerical is altered."""
+    var0, atm, cfg, integ = s.var, s.atm, s.cfg, s.integ
+    sp_idx = s.species.index
+    st = store
+    st["calls"] = []
+    st["static"] = dict(
+        condense_sp=np.array(list(cfg.condense_sp)), non_gas_sp=np.array(list(cfg.non_gas_sp)),
+        use_relax=np.array(list(cfg.use_relax) if cfg.use_relax else [], dtype="U8"), humidity=float(getattr(cfg, "humidity", 1.0)),
+        conden_re_list=np.array(list(var0.conden_re_list), dtype=int),
+        conden_Rf=np.array([var0.Rf[re] for re in var0.conden_re_list]),
+        sat_p=np.array([atm.sat_p[sp] for sp in cfg.condense_sp]), sat_mix=np.array([atm.sat_mix[sp] for sp in cfg.condense_sp]),
+        r_p_keys=np.array(list(atm.r_p.keys())), r_p=np.array([atm.r_p[k] for k in atm.r_p.keys()]),
+        rho_p_keys=np.array(list(atm.rho_p.keys())), rho_p=np.array([atm.rho_p[k] for k in atm.rho_p.keys()]),
+        fix_species=np.array(list(cfg.fix_species)), pco=atm.pco.copy(),
+        fix_species_from_coldtrap_lev=bool(getattr(cfg, "fix_species_from_coldtrap_lev", False)),
+    )
+
+    def wrap(name):
+        orig = getattr(integ, name)
+
+        def f(var, atm_):
+            c = s.para.count
+            nprev = sum(1 for _, n in st["calls"] if n == name)
+            st["calls"].append((c, name))
+            cap = c in counts or nprev < 2 or (c % 400 == 0 and nprev < 4000) or st.get("switch_count") == c
+            # the first two calls, every 400th count, and the iteration of the fix_species switch
+            if cap:
+                pre = "c%05d_%s_" % (c, name)
+                st[pre + "y_in"], st[pre + "ymix_in"], st[pre + "dt"], st[pre + "t"] = var.y.copy(), var.ymix.copy(), var.dt, var.t
+                st[pre + "Dzz"] = atm_.Dzz.copy()
+            v = orig(var, atm_)
+            if name == "conden" and cfg.fix_species and v.t > cfg.stop_conden_time and not s.para.fix_species_start:
+                # Integration.__call__ performs the fix_species switch right after this call (op.py:862-893): keep its input
+                st["switch_count"], st["switch_t"], st["switch_y"], st["switch_ymix"] = c, v.t, v.y.copy(), v.ymix.copy()
+                st["switch_vs_before"], st["switch_rtol_before"] = atm_.vs.copy(), float(cfg.rtol)
+            if cap:
+                st[pre + "y_out"], st[pre + "ymix_out"] = v.y.copy(), v.ymix.copy()
+                if name == "conden":
+                    st[pre + "k_rows"] = np.array([[np.broadcast_to(np.asarray(v.k[re + d], dtype=float), (s.nz,)) for d in (0, 1)]
+                                                    for re in v.conden_re_list])
+            return v
+        setattr(integ, name, f)
+
+    for n in ("conden", "h2o_conden_evap_relax", "nh3_conden_evap_relax"):
+        wrap(n)
+
+
+def finish_conden(s, tag, store, traj):
+    """after the run: the fix_species switch as the reference left it (op.py:862-893)."""
+    var, atm, para, cfg = s.var, s.atm, s.para, s.cfg
+    out = {k: v for k, v in store.items() if k not in ("calls", "static")}
+    out.update({"static_" + k: v for k, v in store["static"].items()})
+    out["calls_count"] = np.array([c for c, n in store["calls"]], dtype=int)
+    out["calls_name"] = np.array([n for c, n in store["calls"]])
+    out["fix_species_start"] = bool(para.fix_species_start)
+    if para.fix_species_start:
+        out["fix_y"] = np.array([var.fix_y[sp] for sp in cfg.fix_species])
+        out["conden_min_lev"] = np.array([int(atm.conden_min_lev[sp]) for sp in cfg.fix_species])
+        out["vs_after"] = atm.vs.copy()
+        out["rtol_after"] = float(cfg.rtol)
+    path = os.path.join(GOLD, "%s_conden.npz" % tag)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "calls=%d fix_species_start=%s" % (len(store["calls"]), para.fix_species_start), flush=True)
+
+
+def run(config, refdir, steps, full, max_steps=None, conden=None, after_switch=None):
     sys.path.insert(0, HERE)
     import ref_session
     assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0 (SURVEY.md §8c)"
@@ -251,6 +325,13 @@ def run(config, refdir, steps, full, max_steps=None):
 
     def hooked(var_, atm_, para_):
         c = para_.count
+        if after_switch is not None and para_.fix_species_start:
+            state.setdefault("switch", c)                  # first one_step with the fixed-species rows active
+            if c == state["switch"] + after_switch:
+                s.var, s.atm, s.para = var_, atm_, para_
+                capture_step(s, tag, c)
+                var_, para_ = s.var, s.para
+                print("captured step %d (fix_species switch seen at %d)" % (c, state["switch"]), flush=True)
         if c in steps:
             s.var, s.atm, s.para = var_, atm_, para_
             capture_step(s, tag, c)
@@ -264,6 +345,9 @@ def run(config, refdir, steps, full, max_steps=None):
         return v, p
 
     solver.one_step = hooked
+    cstore = {}
+    if conden is not None:
+        hook_conden(s, tag, set(conden), cstore)
     last = max(steps) if steps else 0
     if not full:
         cfg.count_max = last          # Integration.stop: count > count_max (op.py:1080)
@@ -271,6 +355,8 @@ def run(config, refdir, steps, full, max_steps=None):
         cfg.count_max = max_steps
     integ(var, atm, para, s.make_atm)
     wall = time.time() - state["t0"]
+    if conden is not None:
+        finish_conden(s, tag, cstore, traj)
     if full:
         tr = np.array(traj)
         np.savez_compressed(os.path.join(GOLD, "%s_full.npz" % tag), traj=tr, y=var.y, ymix=var.ymix, t=var.t,
@@ -289,6 +375,9 @@ if __name__ == "__main__":
     ap.add_argument("--steps", default="0,10,100,300")
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--conden", default=None, help="comma list of counts at which the condensation operators are captured (L6)")
+    ap.add_argument("--after-switch", type=int, default=None, help="capture an L0-L2 step fixture this many steps after fix_species starts")
     a = ap.parse_args()
     steps = [int(x) for x in a.steps.split(",") if x != ""]
-    run(a.config, a.refdir or "/tmp/vulcan_ref_%s" % a.config, steps, a.full, a.max_steps)
+    conden = None if a.conden is None else [int(x) for x in a.conden.split(",") if x != ""]
+    run(a.config, a.refdir or "/tmp/vulcan_ref_%s" % a.config, steps, a.full, a.max_steps, conden, a.after_switch)

@@ -50,6 +50,10 @@ def use(*a, **k):
 CONFIGS = {
     "HD189": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={}, extra=""),
     "Jupiter": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={}, extra=""),
+    # fixture-only variant: the shipped Jupiter cfg with the fix_species switch (op.py:862-893) brought forward from 1e8 s to
+    # 2e6 s of model time, so that a few hundred reference steps reach the switch and the fixed-species rows of Ros2.solver
+    # (op.py:2896-2906, 2921-2924, 2960-2970)
+    "JupiterFix": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"stop_conden_time": "2e6"}, extra=""),
     "HD209S": dict(
         src="cfg_examples/vulcan_cfg_HD189.py",
         edits={

@@ -185,6 +185,28 @@ def mock_objects(case, with_photo=True):
     return cfg, var, atm, para
 
 
+def attach_conden(case, cfg, var, atm):
+    """add what the condensation operators of the caller read (op.py:1109-1421, 862-893) from <cfg>_conden.npz (recorded from
+    the reference's live objects by oracle/dump_fixtures.py --conden): saturation pressures, particle sizes / densities, the
+    condensation reaction list.  Returns the fixture dict (None when the config does not condense)."""
+    path = os.path.join(GOLD, "%s_conden.npz" % case.tag)
+    if not os.path.exists(path):
+        return None
+    cf = dict(np.load(path, allow_pickle=False))
+    csp = [str(x) for x in cf["static_condense_sp"]]
+    atm.sat_p = {s: cf["static_sat_p"][q] for q, s in enumerate(csp)}
+    atm.sat_mix = {s: cf["static_sat_mix"][q] for q, s in enumerate(csp)}
+    atm.r_p = {str(k): float(v) for k, v in zip(cf["static_r_p_keys"], cf["static_r_p"])}
+    atm.rho_p = {str(k): float(v) for k, v in zip(cf["static_rho_p_keys"], cf["static_rho_p"])}
+    atm.conden_min_lev = {}
+    cfg.humidity = float(cf["static_humidity"])
+    cfg.fix_species_from_coldtrap_lev = bool(cf["static_fix_species_from_coldtrap_lev"]) if "static_fix_species_from_coldtrap_lev" in cf \
+        else True          # both shipped condensing cfgs set it (vulcan_cfg_Jupiter.py:121, vulcan_cfg_Earth.py:120)
+    var.conden_re_list = [int(x) for x in cf["static_conden_re_list"]]
+    var.Rf = {re: str(n) for re, n in zip(var.conden_re_list, cf["static_conden_Rf"])}
+    return cf
+
+
 def ulp_diff(a, b):
     """max distance in units in the last place between two float64 arrays (same sign assumed where it matters)."""
     a = np.ascontiguousarray(a, dtype=np.float64)

@@ -6,8 +6,13 @@ Mirrored (same order of operations, same criteria):  __call__ (photo cadence swi
 update_phi_esc every update_frq steps op.py:904-906, hydrostatic rescale op.py:909-914, f_dy, save_step, step_size), backup
 (op.py:937-941), update_mu_dz (op.py:944-984), update_phi_esc (op.py:986-999), f_dy (op.py:1003-1015), conv (op.py:1018-1065),
 stop (op.py:1067-1087), save_step (op.py:1089-1105).
-Not built yet ("next"): the condensation operators `conden` / `*_conden_evap_relax` (op.py:1109-1421) and
-`use_adapt_rtol`; configurations that enable them raise NotImplementedError instead of silently skipping physics.
+Condensation: `conden` (op.py:1109-1300, growth rates of the `X -> X_l_s` reactions written into var.k),
+`h2o_conden_evap_relax` / `nh3_conden_evap_relax` (op.py:1340-1421, implicit-Euler relaxation to saturation) and the
+fix_species switch with its cold-trap levels (op.py:859-893) are mirrored expression by expression (same evaluation order, so
+they are bit-identical to the reference on the same inputs: tests/test_integration_host.py against fixtures recorded from the
+reference's own operators).  They act once per ACCEPTED step on nz-vectors of one or two species - bookkeeping of the caller,
+not part of the Ros2 stage arithmetic - and stay on the host next to conv()/save_step, which need var.y on the host anyway.
+Not built: `use_adapt_rtol` (no shipped cfg defines it) raises NotImplementedError instead of silently skipping.
 
 All arithmetic of the step itself runs on the GPU behind the C ABI; what is left here is the reference's own per-step host
 bookkeeping (numpy), kept on the host because `conv()` compares against the stored history `y_time`.
@@ -50,8 +55,15 @@ class Integration(object):
                 self.n_photo_updates += 1
                 self.t_photo += time.time() - tp
             var, para = self.odesolver.one_step(var, atm, para)                                      # op.py:832
-            if getattr(cfg, "use_condense", False) and var.t >= cfg.start_conden_time and not para.fix_species_start:
-                raise NotImplementedError("condensation operators conden / relax (op.py:859-902, 1109-1421)")
+            if getattr(cfg, "use_condense", False) and var.t >= cfg.start_conden_time and not para.fix_species_start:   # op.py:859-902
+                var = self.conden(var, atm)
+                if cfg.fix_species and var.t > cfg.stop_conden_time:
+                    self.start_fix_species(var, atm, para)
+                if cfg.use_relax:
+                    if 'H2O' in cfg.use_relax:
+                        var = self.h2o_conden_evap_relax(var, atm)
+                    if 'NH3' in cfg.use_relax:
+                        var = self.nh3_conden_evap_relax(var, atm)
             if para.count % cfg.update_frq == 0:                                                     # op.py:904-906
                 atm = self.update_mu_dz(var, atm)
                 atm = self.update_phi_esc(var, atm)
@@ -66,6 +78,110 @@ class Integration(object):
                 para.end_case = 4
                 break
         return var, atm, para
+
+    # ------------------------------------------------------------------------------------------------ op.py:862-893
+    def start_fix_species(self, var, atm, para):
+        """first step after stop_conden_time: freeze the condensable species, record their cold-trap levels, switch rtol,
+        turn the settling velocity off (op.py:862-893)."""
+        cfg, sp_index = self.cfg, self.species.index
+        nz = var.y.shape[0]
+        para.fix_species_start = True
+        cfg.rtol = cfg.post_conden_rtol
+        atm.vs *= 0
+        var.fix_y = {}
+        if not hasattr(atm, "conden_min_lev"):
+            atm.conden_min_lev = {}
+        for sp in cfg.fix_species:
+            var.fix_y[sp] = np.copy(var.y[:, sp_index(sp)])
+            if cfg.fix_species_from_coldtrap_lev:
+                if sp in ('H2O_l_s', 'H2SO4_l', 'NH3_l_s', 'S8_l_s'):
+                    atm.conden_min_lev[sp] = nz - 1
+                else:
+                    sat_rho = atm.n_0 * atm.sat_mix[sp]
+                    conden_status = var.y[:, sp_index(sp)] >= sat_rho
+                    atm.conden_status = conden_status
+                    if list(var.y[conden_status, sp_index(sp)]):
+                        min_sat = np.amin(atm.sat_mix[sp][conden_status])
+                        atm.min_sat = min_sat
+                        atm.conden_min_lev[sp] = np.where(atm.sat_mix[sp] == min_sat)[0].item()
+                    else:
+                        atm.conden_min_lev[sp] = 0
+
+    # growth-rate reactions handled by conden: Rf string -> (gas species, particle key of r_p / rho_p, molecular mass in amu as the
+    # reference writes it, op.py:1122-1296), humidity factor applies to water only
+    CONDEN = {'H2O -> H2O_l_s': ('H2O', 'H2O_l_s', 18.), 'NH3 -> NH3_l': ('NH3', 'NH3_l_s', 17.),
+              'H2SO4 -> H2SO4_l': ('H2SO4', 'H2SO4_l', 98.022), 'S2 -> S2_l_s': ('S2', 'S2_l_s', 45.019),
+              'S4 -> S4_l_s': ('S4', 'S4_l_s', 32.06 * 4), 'S8 -> S8_l_s': ('S8', 'S8_l_s', 360.152), 'C -> C_s': ('C', 'C_s', 12.011)}
+
+    def conden(self, var, atm):                                                                      # op.py:1109-1300
+        cfg, sp_index = self.cfg, self.species.index
+        nz = var.y.shape[0]
+        for re in var.conden_re_list:
+            ent = self.CONDEN.get(var.Rf[re])
+            if ent is None or ent[0] not in cfg.condense_sp:
+                continue
+            gas, part, amu = ent
+            if gas in ('H2O', 'NH3') and cfg.use_relax:                        # relaxation replaces the growth reaction (op.py:1124-1126)
+                var.k[re] = np.repeat(0., nz)
+                var.k[re + 1] = np.repeat(0., nz)
+                continue
+            m = amu / NAVO
+            rho_p, r_p = atm.rho_p[part], atm.r_p[part]
+            sat = atm.sat_p[gas] / KB / atm.Tco
+            if gas == 'H2O':
+                sat = sat * cfg.humidity
+            Dg = np.insert(atm.Dzz[:, sp_index(gas)], 0, atm.Dzz[0, sp_index(gas)])
+            rate = Dg * m / rho_p / r_p ** 2 * (var.y[:, sp_index(gas)] - sat)
+            var.k[re] = np.maximum(rate, 0)                                    # positive: condensation
+            var.k[re + 1] = np.abs(np.minimum(rate, 0))                        # negative: evaporation
+        return var
+
+    def h2o_conden_evap_relax(self, var, atm):                                                       # op.py:1340-1376
+        cfg, sp_index = self.cfg, self.species.index
+        iw, il = sp_index('H2O'), sp_index('H2O_l_s')
+        m = 18. / NAVO
+        rho_p, r_p = atm.rho_p['H2O_l_s'], atm.r_p['H2O_l_s']
+        sat_humidity = atm.sat_p['H2O'] / KB / atm.Tco * cfg.humidity
+        Dg = np.insert(atm.Dzz[:, iw], 0, atm.Dzz[0, iw])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            tau = 1. / (Dg * m / rho_p / r_p ** 2 * (var.y[:, iw] - sat_humidity))
+            conden_indx = np.where(tau > 0)
+            evap_indx = np.where(tau < 0)
+            sat_mix = sat_humidity / atm.n_0
+            y_conden = (var.ymix[:, iw] + var.dt / tau * sat_mix) / (1. + var.dt / tau)
+            ice_loss = (var.y[:, iw] - sat_humidity) * var.dt / tau
+        ice_loss = np.minimum(var.y[:, il], ice_loss)
+        var.ymix[conden_indx, il] += (var.ymix[conden_indx, iw] - y_conden[conden_indx])
+        var.ymix[conden_indx, iw] = y_conden[conden_indx]
+        var.ymix[evap_indx, iw] += ice_loss[evap_indx] / atm.n_0[evap_indx]
+        var.ymix[evap_indx, il] -= ice_loss[evap_indx] / atm.n_0[evap_indx]
+        var.y = var.ymix * np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))
+        return var
+
+    def nh3_conden_evap_relax(self, var, atm):                                                       # op.py:1378-1421
+        sp_index = self.species.index
+        ig, il = sp_index('NH3'), sp_index('NH3_l_s')
+        m = 17. / NAVO
+        rho_p, r_p = atm.rho_p['NH3_l_s'], atm.r_p['NH3_l_s']
+        sat_p = atm.sat_p['NH3'] / KB / atm.Tco
+        sat_mix = sat_p / atm.n_0
+        conden_top = np.argmin(sat_mix)
+        Dg = np.insert(atm.Dzz[:, ig], 0, atm.Dzz[0, ig])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            tau = 1. / (Dg * m / rho_p / r_p ** 2 * (var.y[:, ig] - sat_p))
+            conden_indx = np.where(tau > 0)[0]
+            evap_indx = np.where(tau < 0)[0]
+            conden_indx = [i for i in conden_indx if i <= conden_top]         # no condensation above the top of the condensation zone
+            y_conden = (var.ymix[:, ig] + var.dt / tau * sat_mix) / (1. + var.dt / tau)
+            ice_loss = (var.y[:, ig] - sat_p) * var.dt / tau
+        ice_loss = np.minimum(var.y[:, il], ice_loss)
+        var.ymix[conden_indx, il] += (var.ymix[conden_indx, ig] - y_conden[conden_indx])
+        var.ymix[conden_indx, ig] = y_conden[conden_indx]
+        var.ymix[evap_indx, ig] += ice_loss[evap_indx] / atm.n_0[evap_indx]
+        var.ymix[evap_indx, il] -= ice_loss[evap_indx] / atm.n_0[evap_indx]
+        var.ymix[:, il] = np.maximum(var.ymix[:, il], 0)
+        var.y = var.ymix * np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))
+        return var
 
     def backup(self, var):                                                                           # op.py:937-941
         var.y_prev = np.copy(var.y)
