@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define VK_ABI_VERSION 1
+#define VK_ABI_VERSION 2
 
 typedef enum {
     VK_OK = 0,
@@ -96,6 +96,12 @@ typedef struct {
     const double *Tco, *g, *M;     /* [nz] */
     const double *Ti, *Hpi;        /* [nz-1] */
     const double *ms, *alpha, *top_flux, *bot_flux, *bot_vdep; /* [ni] */
+    /* ABI 2: vulcan_cfg.use_vm_mol selects diffdf_vm / lhs_jac_tot_vm or, with use_settling, diffdf_settling_vm /
+     * lhs_jac_settling_vm (op.py:2879-2888; 1599-1694, 1794-1898, 2044-2119, 2366-2444) */
+    int use_vm_mol;
+    const double *vm;        /* [nz][ni] atm.vm, the advective velocity of molecular diffusion (build_atm.py:735-739); NULL unless use_vm_mol */
+    int n_diff_esc;          /* vulcan_cfg.diff_esc: species with diffusion-limited escape; only the *_vm lhs variants read it (op.py:2101-2107) */
+    const int *diff_esc_idx; /* [n_diff_esc] */
 } vk_atm_view;
 int vk_set_atm(vk_column *col, const vk_atm_view *atm);
 

@@ -332,6 +332,7 @@ def run(config, refdir, steps, full, max_steps=None, conden=None, after_switch=N
                 capture_step(s, tag, c)
                 var_, para_ = s.var, s.para
                 print("captured step %d (fix_species switch seen at %d)" % (c, state["switch"]), flush=True)
+                cfg.count_max = c + 1          # nothing more to record: let Integration.stop end the run (op.py:1080)
         if c in steps:
             s.var, s.atm, s.para = var_, atm_, para_
             capture_step(s, tag, c)

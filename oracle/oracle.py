@@ -38,7 +38,8 @@ class _Atm(C.Structure):
                 ("use_topflux", C.c_int), ("use_botflux", C.c_int), ("n_gas", C.c_int), ("gas_indx", _ip),
                 ("n_gas_lhs", C.c_int), ("gas_indx_lhs", _ip), ("Kzz", _dp), ("vz", _dp), ("dzi", _dp), ("Dzz", _dp),
                 ("vs", _dp), ("Tco", _dp), ("g", _dp), ("Ti", _dp), ("Hpi", _dp), ("ms", _dp), ("alpha", _dp),
-                ("top_flux", _dp), ("bot_flux", _dp), ("bot_vdep", _dp), ("M", _dp)]
+                ("top_flux", _dp), ("bot_flux", _dp), ("bot_vdep", _dp), ("M", _dp), ("use_vm_mol", C.c_int), ("vm", _dp),
+                ("n_diff_esc", C.c_int), ("diff_esc_idx", _ip)]
 
 
 class _Opts(C.Structure):
@@ -87,7 +88,7 @@ class Oracle(object):
     # -------------------------------------------------------------- helpers
     def make_atm(self, nz, Kzz, vz, dzi, Dzz, vs, Tco, g, Ti, Hpi, ms, alpha, top_flux, bot_flux, bot_vdep, M,
                  use_moldiff=True, use_settling=False, use_topflux=False, use_botflux=False, gas_indx=None,
-                 gas_indx_lhs=None):
+                 gas_indx_lhs=None, use_vm_mol=False, vm=None, diff_esc_idx=None):
         ni = self.ni
         arrs = dict(Kzz=_f64(Kzz), vz=_f64(vz), dzi=_f64(dzi), Dzz=_f64(Dzz), vs=_f64(vs), Tco=_f64(Tco), g=_f64(g),
                     Ti=_f64(Ti), Hpi=_f64(Hpi), ms=_f64(ms), alpha=_f64(alpha), top_flux=_f64(top_flux),
@@ -95,12 +96,17 @@ class Oracle(object):
         gi = _i32(gas_indx) if gas_indx is not None and len(gas_indx) != ni else None
         gl = _i32(gas_indx_lhs) if gas_indx_lhs is not None and len(gas_indx_lhs) != ni else None
         arrs["gi"], arrs["gl"] = gi, gl
+        arrs["vm"] = _f64(vm) if use_vm_mol else None
+        de = _i32(diff_esc_idx) if (use_vm_mol and diff_esc_idx is not None and len(diff_esc_idx)) else None
+        arrs["de"] = de
         a = _Atm(nz, ni, int(use_moldiff), int(use_settling), int(use_topflux), int(use_botflux),
                  0 if gi is None else len(gi), None if gi is None else _i(gi),
                  0 if gl is None else len(gl), None if gl is None else _i(gl),
                  _d(arrs["Kzz"]), _d(arrs["vz"]), _d(arrs["dzi"]), _d(arrs["Dzz"]), _d(arrs["vs"]), _d(arrs["Tco"]),
                  _d(arrs["g"]), _d(arrs["Ti"]), _d(arrs["Hpi"]), _d(arrs["ms"]), _d(arrs["alpha"]),
-                 _d(arrs["top_flux"]), _d(arrs["bot_flux"]), _d(arrs["bot_vdep"]), _d(arrs["M"]))
+                 _d(arrs["top_flux"]), _d(arrs["bot_flux"]), _d(arrs["bot_vdep"]), _d(arrs["M"]),
+                 int(bool(use_vm_mol)), None if arrs["vm"] is None else _d(arrs["vm"]),
+                 0 if de is None else len(de), None if de is None else _i(de))
         a._keep = arrs
         return a
 

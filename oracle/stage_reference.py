@@ -54,6 +54,11 @@ CONFIGS = {
     # 2e6 s of model time, so that a few hundred reference steps reach the switch and the fixed-species rows of Ros2.solver
     # (op.py:2896-2906, 2921-2924, 2960-2970)
     "JupiterFix": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"stop_conden_time": "2e6"}, extra=""),
+    # use_vm_mol variants ("under testing" in the reference, vulcan_cfg.py:77): upwind advective form of molecular diffusion,
+    # diffdf_vm + lhs_jac_tot_vm (op.py:1599-1694, 2044-2119) and, with settling, diffdf_settling_vm + lhs_jac_settling_vm
+    # (op.py:1794-1898, 2366-2444)
+    "HD189vm": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_vm_mol": "True"}, extra=""),
+    "JupiterVm": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"use_vm_mol": "True"}, extra=""),
     "HD209S": dict(
         src="cfg_examples/vulcan_cfg_HD189.py",
         edits={
@@ -73,6 +78,12 @@ CONFIGS = {
         src="cfg_examples/vulcan_cfg_Earth.py",
         edits={"network": "'thermo/NCHO_earth_photo_network.txt'"},
         extra="",  # filled in by stage() (species filtering needs the network parsed)
+    ),
+    # Earth + use_vm_mol: lhs_jac_settling_vm with the diffusion-limited escape term (diff_esc = ['H2','H'], op.py:2425-2431)
+    "EarthVm": dict(
+        src="cfg_examples/vulcan_cfg_Earth.py",
+        edits={"network": "'thermo/NCHO_earth_photo_network.txt'", "use_vm_mol": "True"},
+        extra="",
     ),
 }
 
@@ -163,7 +174,7 @@ def stage(config, dest, run_codegen=True, quiet=True):
     edits = dict(COMMON_OFF)
     edits.update(cfg["edits"])
     extra = cfg["extra"]
-    if config == "Earth":
+    if config in ("Earth", "EarthVm"):
         # BASELINE names NCHO_earth_photo_network.txt, which lacks the sulphur
         # species the shipped Earth cfg / BC file mention -> restrict to species in the network.
         sp = set(_network_species(os.path.join(dest, "thermo/NCHO_earth_photo_network.txt")))

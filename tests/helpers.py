@@ -19,7 +19,12 @@ def have(tag, name):
     return os.path.exists(os.path.join(GOLD, "%s_%s" % (tag, name)))
 
 
+# fixture variants that run a base config's network with different cfg switches (oracle/stage_reference.py::CONFIGS)
+NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}
+
+
 def load_network(tag):
+    tag = NETWORK_OF.get(tag, tag)
     with open(os.path.join(GOLD, tag + "_network.json")) as f:
         return Network.from_json(f.read())
 
@@ -54,12 +59,20 @@ class Case(object):
             gas_indx=self.gas_indx if non_gas else None,
             # lhs_jac_tot keys the gas mask on use_condense (op.py:1981), the other variants on non_gas_sp
             gas_indx_lhs=self.gas_indx if (bool(cfg["use_condense"]) if (cfg["use_moldiff"] and not cfg["use_settling"]) else non_gas) else None,
+            # use_vm_mol: the *_vm stencils (op.py:1599-1694, 1794-1898, 2044-2119, 2366-2444); diff_esc only enters their lhs
+            use_vm_mol=bool(cfg.get("use_vm_mol", False)), vm=st["vm"],
+            diff_esc_idx=[list(self.net.species).index(s) for s in cfg.get("diff_esc", [])],
         )
 
 
 # every (config, step) fixture pair generated from the unmodified reference (oracle/dump_fixtures.py); BASELINE.json configs
 CASES = [("HD189", 0), ("HD189", 10), ("HD189", 100), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30),
          ("HD209S", 0), ("HD209S", 30)]
+# use_vm_mol variants: diffdf_vm / lhs_jac_tot_vm (HD189vm), diffdf_settling_vm / lhs_jac_settling_vm (JupiterVm),
+# the latter with the diffusion-limited escape term (EarthVm)
+VM_CASES = [p for p in [("HD189vm", 0), ("HD189vm", 30), ("JupiterVm", 0), ("JupiterVm", 30), ("EarthVm", 0), ("EarthVm", 30)]
+            if have(p[0], "step%04d.npz" % p[1])]
+CASES = CASES + VM_CASES
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
 
 
@@ -100,7 +113,8 @@ def gpu_columns(case, ncol=1, refine=0):
                 Ti=kw["Ti"], Hpi=kw["Hpi"], ms=kw["ms"], alpha=kw["alpha"], top_flux=kw["top_flux"], bot_flux=kw["bot_flux"],
                 bot_vdep=kw["bot_vdep"], use_moldiff=kw["use_moldiff"], use_settling=kw["use_settling"],
                 use_topflux=kw["use_topflux"], use_botflux=kw["use_botflux"], gas_indx=kw["gas_indx"],
-                gas_indx_lhs=kw["gas_indx_lhs"], shared=True)
+                gas_indx_lhs=kw["gas_indx_lhs"], use_vm_mol=kw["use_vm_mol"], vm=kw["vm"], diff_esc_idx=kw["diff_esc_idx"],
+                shared=True)
     col.set_k(case.k)
     o = step_opts(case)
     fbv = None
@@ -158,7 +172,7 @@ def mock_objects(case, with_photo=True):
                           ms=st["ms"].copy(), alpha=st["alpha"].copy(), top_flux=fx["top_flux_dyn"].copy(), bot_flux=st["bot_flux"].copy(),
                           bot_vdep=st["bot_vdep"].copy(), gas_indx=list(st["gas_indx"]), n_0=st["n_0"].copy(), dz=fx["dz"].copy(),
                           pico=st["pico"].copy(), pco=st["pco"].copy(), pref_indx=int(st["pref_indx"]), gs=float(cfgd["gs"]),
-                          Hp=fx["Hp"].copy(), zco=fx["zco"].copy(), mu=fx["mu"].copy())
+                          Hp=fx["Hp"].copy(), zco=fx["zco"].copy(), mu=fx["mu"].copy(), vm=st["vm"].copy())
     para = SimpleNamespace(delta=0.0, small_y=0.0, nega_y=0.0, delta_count=0, nega_count=0, loss_count=0, count=int(fx["count"]),
                            fix_species_start=False, solver_str="", end_case=0, switch_final_photo_frq=False)
     if with_photo and cfgd.get("use_photo") and "photo_sp" in st:

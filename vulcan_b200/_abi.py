@@ -53,7 +53,8 @@ class AtmView(C.Structure):
                 ("use_botflux", C.c_int), ("n_gas", C.c_int), ("gas_indx", _ip), ("n_gas_lhs", C.c_int),
                 ("gas_indx_lhs", _ip), ("Kzz", _dp), ("vz", _dp), ("dzi", _dp), ("Dzz", _dp), ("vs", _dp),
                 ("Tco", _dp), ("g", _dp), ("M", _dp), ("Ti", _dp), ("Hpi", _dp), ("ms", _dp), ("alpha", _dp),
-                ("top_flux", _dp), ("bot_flux", _dp), ("bot_vdep", _dp)]
+                ("top_flux", _dp), ("bot_flux", _dp), ("bot_vdep", _dp),
+                ("use_vm_mol", C.c_int), ("vm", _dp), ("n_diff_esc", C.c_int), ("diff_esc_idx", _ip)]
 
 
 class StepOpts(C.Structure):
@@ -233,7 +234,8 @@ class Columns(object):
     # ---------------------------------------------------------------- inputs
     def set_atm(self, Kzz, vz, dzi, Dzz, vs, Tco, g, M, Ti, Hpi, ms, alpha, top_flux, bot_flux, bot_vdep,
                 use_moldiff=True, use_settling=False, use_topflux=False, use_botflux=False, gas_indx=None,
-                gas_indx_lhs=None, shared=True):
+                gas_indx_lhs=None, use_vm_mol=False, vm=None, diff_esc_idx=None, shared=True):
+        """use_vm_mol / vm / diff_esc_idx: the reference's *_vm stencil variants (op.py:2879-2888); vm is atm.vm [nz, ni]."""
         nz, ni = self.nz, self.ni
         rep = () if shared else (self.ncol,)
 
@@ -248,12 +250,19 @@ class Columns(object):
                     bot_flux=arr(bot_flux, (ni,)), bot_vdep=arr(bot_vdep, (ni,)))
         gi = None if gas_indx is None or len(gas_indx) == ni else i32(gas_indx)
         gl = None if gas_indx_lhs is None or len(gas_indx_lhs) == ni else i32(gas_indx_lhs)
+        use_vm_mol = bool(use_vm_mol) and bool(use_moldiff)
+        if use_vm_mol:
+            if vm is None:
+                raise ValueError("use_vm_mol needs atm.vm")
+            keep["vm"] = arr(vm, (nz, ni))
+        de = i32(diff_esc_idx) if (use_vm_mol and diff_esc_idx is not None and len(diff_esc_idx)) else None
         v = AtmView(int(shared), int(use_moldiff), int(use_settling), int(use_topflux), int(use_botflux),
                     0 if gi is None else len(gi), iptr(gi), 0 if gl is None else len(gl), iptr(gl),
                     dptr(keep["Kzz"]), dptr(keep["vz"]), dptr(keep["dzi"]), dptr(keep["Dzz"]), dptr(keep["vs"]),
                     dptr(keep["Tco"]), dptr(keep["g"]), dptr(keep["M"]), dptr(keep["Ti"]), dptr(keep["Hpi"]),
                     dptr(keep["ms"]), dptr(keep["alpha"]), dptr(keep["top_flux"]), dptr(keep["bot_flux"]),
-                    dptr(keep["bot_vdep"]))
+                    dptr(keep["bot_vdep"]), int(use_vm_mol), dptr(keep["vm"]) if use_vm_mol else None,
+                    0 if de is None else len(de), iptr(de))
         check(self.lib.vk_set_atm(self.handle, C.byref(v)))
 
     def set_k(self, k, shared=None):

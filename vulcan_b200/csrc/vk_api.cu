@@ -350,6 +350,19 @@ int vk_set_atm(vk_column *c, const vk_atm_view *v)
     CPA(Dzz, (size_t)(nz - 1) * ni); CPA(vs, (size_t)(nz - 1) * ni);
     CPA(Tco, nz); CPA(g, nz); CPA(M, nz);
     CPA(ms, ni); CPA(alpha, ni); CPA(top_flux, ni); CPA(bot_flux, ni); CPA(bot_vdep, ni);
+    a.use_vm_mol = (v->use_vm_mol && v->use_moldiff) ? 1 : 0;      // Ros2.solver's dispatch (op.py:2879-2888)
+    a.vm = nullptr; a.csv = 0; a.n_diff_esc = 0; a.diff_esc_idx = nullptr;
+    if (a.use_vm_mol) {
+        if (!v->vm && rc == VK_OK) { set_error("use_vm_mol needs atm.vm"); rc = VK_ERR_INVALID; }
+        CPA(vm, (size_t)nz * ni);
+        a.csv = v->shared ? 0 : (size_t)nz * ni;
+        if (rc == VK_OK && v->n_diff_esc > 0) {
+            for (int q = 0; q < v->n_diff_esc; q++)
+                if (v->diff_esc_idx[q] < 0 || v->diff_esc_idx[q] >= ni) { set_error("diff_esc species out of range"); rc = VK_ERR_INVALID; }
+            a.n_diff_esc = v->n_diff_esc;
+            if (rc == VK_OK) rc = dev_copy(c->atm_allocs, v->diff_esc_idx, (size_t)a.n_diff_esc, &a.diff_esc_idx);
+        }
+    }
 #undef CPA
     if (rc != VK_OK) return rc;
     // atmosphere-only stencil pieces (evaluated once per vk_set_atm)

@@ -52,10 +52,47 @@ __global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p)
     const AtmLayer L = atm_at(a, col);
     const double *dzi = L.dzi, *Dzz = L.Dzz, *vs = L.vs, *g = L.g;
     const size_t base = ((size_t)col * nz + j) * ni;
+    const double *vmv = a.use_vm_mol ? a.vm + col * a.csv : nullptr;
+    const int stl = a.use_settling && a.use_moldiff;
     for (int i = threadIdx.x; i < ni; i += blockDim.x) {
         double Q = 0, QB = 0, QC = 0, TA = 0, TB = 0, TC = 0, SA = 0, SB = 0, SC = 0;
         if (j < nz - 1) Q = Dzz[(size_t)j * ni + i] / dzi[j];
-        if (j == 0) {
+        if (a.use_vm_mol) {
+            // use_vm_mol (diffdf_vm op.py:1644-1673, diffdf_settling_vm op.py:1845-1879 and their lhs twins): no thermal/gravity
+            // brackets; S* hold the upwind terms of vm, T* those of vs.  vm has nz rows (`vm[-1]` = row nz-1, `vs[-1]` = row nz-2);
+            // the settling variant has NO vm term in the bottom row, so S* carry the vs term there.
+            if (j == 0) {
+                double D0 = Dzz[i];
+                QB = 1. / (dzi[0]) * (D0 / dzi[0]);
+                QC = -1. / (dzi[0]) * (D0 / dzi[0]);
+                const double w = stl ? vs[i] : vmv[i];
+                SA = (posv(w)) / dzi[0];
+                SB = (negv(w)) / dzi[0];
+            } else if (j == nz - 1) {
+                const int m = nz - 2;
+                double Dm = Dzz[(size_t)m * ni + i];
+                QB = -1. / (dzi[m]) * (Dm / dzi[m]);
+                QC = 1. / (dzi[m]) * (Dm / dzi[m]);
+                const double wt = vmv[(size_t)(nz - 1) * ni + i];
+                SA = (negv(wt)) / dzi[m];
+                SC = (posv(wt)) / dzi[m];
+                TA = (negv(vs[(size_t)m * ni + i])) / dzi[m];
+                TC = (posv(vs[(size_t)m * ni + i])) / dzi[m];
+            } else {
+                double dz_ave = 0.5 * (dzi[j - 1] + dzi[j]);
+                double Dj = Dzz[(size_t)j * ni + i], Dm = Dzz[(size_t)(j - 1) * ni + i];
+                QB = 1. / dz_ave * Dj / dzi[j];
+                QC = 1. / dz_ave * Dm / dzi[j - 1];
+                const double wj = vmv[(size_t)j * ni + i], wm = vmv[(size_t)(j - 1) * ni + i];
+                SA = (posv(wj) - negv(wm)) / dz_ave;
+                SB = (negv(wj)) / dz_ave;
+                SC = (posv(wm)) / dz_ave;
+                const double vj = vs[(size_t)j * ni + i], vmn = vs[(size_t)(j - 1) * ni + i];
+                TA = (posv(vj) - negv(vmn)) / dz_ave;
+                TB = (negv(vj)) / dz_ave;
+                TC = (posv(vmn)) / dz_ave;
+            }
+        } else if (j == 0) {
             double D0 = Dzz[i];
             QB = 1. / (dzi[0]) * (D0 / dzi[0]);
             QC = -1. / (dzi[0]) * (D0 / dzi[0]);
@@ -135,6 +172,65 @@ int launch_atm_pre(vk_column *c, int ncol_atm)
     atm_pre_kernel<<<ncol_atm * c->nz, 96, 0, c->stream>>>(c->atm, ncol_atm, c->atm.pre);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
+}
+
+// ---- use_vm_mol: how the consumers combine the upwind terms (pos: 0 bottom row, 1 interior, 2 top row).  Ai/Bi/Ci enter
+// holding the diffusive part only.  The reference adds the terms in a different order on the two sides:
+//   diffdf_vm / diffdf_settling_vm (op.py:1644-1650, 1670-1673 / 1845-1855, 1876-1879): interior  Ai += -(vm..)/dz -(vs..)/dz  is ONE
+//   right-hand expression; top row vm[-1] first, then vs[-1]
+//   lhs_jac_tot_vm / lhs_jac_settling_vm (op.py:2090-2118 / 2412-2442): vs terms first, then vm terms, each its own subtraction
+__device__ __forceinline__ void vm_rhs_adv(const AtmPre &P, size_t pb, int pos, int st, double &Ai, double &Bi, double &Ci)
+{
+    if (pos == 0) {
+        Ai = Ai - P.SA[pb];
+        Bi = Bi - P.SB[pb];
+    } else if (pos == 2) {
+        Ai = Ai + P.SA[pb];
+        Ci = Ci + P.SC[pb];
+        if (st) {
+            Ai = Ai + P.TA[pb];
+            Ci = Ci + P.TC[pb];
+        }
+    } else if (st) {
+        Ai += -P.SA[pb] - P.TA[pb];
+        Bi += -P.SB[pb] - P.TB[pb];
+        Ci += +P.SC[pb] + P.TC[pb];
+    } else {
+        Ai += -P.SA[pb];
+        Bi += -P.SB[pb];
+        Ci += +P.SC[pb];
+    }
+}
+__device__ __forceinline__ void vm_lhs_adv(const AtmPre &P, size_t pb, int pos, int st, double &ta, double &tb, double &tc)
+{
+    if (pos == 0) {
+        ta = ta - P.SA[pb];
+        tb = tb - P.SB[pb];
+    } else if (pos == 2) {
+        if (st) {
+            ta = ta + P.TA[pb];
+            tc = tc + P.TC[pb];
+        }
+        ta = ta + P.SA[pb];
+        tc = tc + P.SC[pb];
+    } else {
+        if (st) {
+            ta = ta - P.TA[pb];
+            tb = tb - P.TB[pb];
+            tc = tc + P.TC[pb];
+        }
+        ta = ta - P.SA[pb];
+        tb = tb - P.SB[pb];
+        tc = tc + P.SC[pb];
+    }
+}
+// diffusion-limited escape on the top diagonal, only in the *_vm lhs variants (op.py:2101-2107, 2425-2431)
+__device__ __forceinline__ double vm_diff_lim(const AtmDev &a, const AtmLayer &L, int i, double ytop)
+{
+    double diff_lim = 0.0;
+    for (int q = 0; q < a.n_diff_esc; q++)
+        if (a.diff_esc_idx[q] == i && ytop > 0) diff_lim += L.top_flux[i] / ytop;
+    return diff_lim;
 }
 
 // per-layer scalars that depend on the layer sums (one thread per block computes them)
@@ -234,6 +330,7 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
     for (int p = tid; 2 * p + 1 <= nr; p += nt) rate[2 * p + 1] = rate[2 * p + 1] - rate[2 * p + 2];
     const AtmLayer L = atm_at(A.atm, col);
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
     if (tid >= RHS_NT - 3) {       // three threads: A, B, C of the eddy + advection stencil from the precomputed prefactors
         const int q = tid - (RHS_NT - 3);
         const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
@@ -291,11 +388,18 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
         double diff;
         if (j == 0) {
             if (md) {
-                double Ai = P.QC[pb] * s.sp / 2. / s.ys0 + P.TA[pb];
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp + P.TB[pb];
-                if (st) {
-                    Ai = Ai - P.SA[pb];
-                    Bi = Bi - P.SB[pb];
+                double Ai = P.QC[pb] * s.sp / 2. / s.ys0;
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+                if (vmm) {
+                    double Cx = 0.0;
+                    vm_rhs_adv(P, pb, 0, st, Ai, Bi, Cx);
+                } else {
+                    Ai = Ai + P.TA[pb];
+                    Bi = Bi + P.TB[pb];
+                    if (st) {
+                        Ai = Ai - P.SA[pb];
+                        Bi = Bi - P.SB[pb];
+                    }
                 }
                 diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
             } else {
@@ -304,11 +408,18 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
             if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
         } else if (j == nz - 1) {
             if (md) {
-                double Ai = P.QB[pb] * s.sm / 2. / s.ys0 - P.TA[pb];
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm - P.TC[pb];
-                if (st) {
-                    Ai = Ai + P.SA[pb];
-                    Ci = Ci + P.SC[pb];
+                double Ai = P.QB[pb] * s.sm / 2. / s.ys0;
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
+                if (vmm) {
+                    double Bx = 0.0;
+                    vm_rhs_adv(P, pb, 2, st, Ai, Bx, Ci);
+                } else {
+                    Ai = Ai - P.TA[pb];
+                    Ci = Ci - P.TC[pb];
+                    if (st) {
+                        Ai = Ai + P.SA[pb];
+                        Ci = Ci + P.SC[pb];
+                    }
                 }
                 diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
             } else {
@@ -321,14 +432,18 @@ __global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
                 double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
                 double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
                 double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (st) {
-                    Ai = Ai - P.SA[pb];
-                    Bi = Bi - P.SB[pb];
-                    Ci = Ci + P.SC[pb];
+                if (vmm) {
+                    vm_rhs_adv(P, pb, 1, st, Ai, Bi, Ci);
+                } else {
+                    if (st) {
+                        Ai = Ai - P.SA[pb];
+                        Bi = Bi - P.SB[pb];
+                        Ci = Ci + P.SC[pb];
+                    }
+                    Ai += P.TA[pb];
+                    Bi += P.TB[pb];
+                    Ci += -P.TC[pb];
                 }
-                Ai += P.TA[pb];
-                Bi += P.TB[pb];
-                Ci += -P.TC[pb];
                 double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
                 diff = t1 + t2;
             } else {
@@ -459,6 +574,7 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
     __syncwarp();
     const AtmLayer L = atm_at(A.atm, col);
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
     if (lane < 3) {
         const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
         const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
@@ -523,11 +639,18 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
         double diff;
         if (j == 0) {
             if (md) {
-                double Ai = P.QC[pb] * s.sp / 2. / s.ys0 + P.TA[pb];
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp + P.TB[pb];
-                if (st) {
-                    Ai = Ai - P.SA[pb];
-                    Bi = Bi - P.SB[pb];
+                double Ai = P.QC[pb] * s.sp / 2. / s.ys0;
+                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+                if (vmm) {
+                    double Cx = 0.0;
+                    vm_rhs_adv(P, pb, 0, st, Ai, Bi, Cx);
+                } else {
+                    Ai = Ai + P.TA[pb];
+                    Bi = Bi + P.TB[pb];
+                    if (st) {
+                        Ai = Ai - P.SA[pb];
+                        Bi = Bi - P.SB[pb];
+                    }
                 }
                 diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
             } else {
@@ -536,11 +659,18 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
             if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
         } else if (j == nz - 1) {
             if (md) {
-                double Ai = P.QB[pb] * s.sm / 2. / s.ys0 - P.TA[pb];
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm - P.TC[pb];
-                if (st) {
-                    Ai = Ai + P.SA[pb];
-                    Ci = Ci + P.SC[pb];
+                double Ai = P.QB[pb] * s.sm / 2. / s.ys0;
+                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
+                if (vmm) {
+                    double Bx = 0.0;
+                    vm_rhs_adv(P, pb, 2, st, Ai, Bx, Ci);
+                } else {
+                    Ai = Ai - P.TA[pb];
+                    Ci = Ci - P.TC[pb];
+                    if (st) {
+                        Ai = Ai + P.SA[pb];
+                        Ci = Ci + P.SC[pb];
+                    }
                 }
                 diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
             } else {
@@ -553,14 +683,18 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
                 double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
                 double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
                 double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (st) {
-                    Ai = Ai - P.SA[pb];
-                    Bi = Bi - P.SB[pb];
-                    Ci = Ci + P.SC[pb];
+                if (vmm) {
+                    vm_rhs_adv(P, pb, 1, st, Ai, Bi, Ci);
+                } else {
+                    if (st) {
+                        Ai = Ai - P.SA[pb];
+                        Bi = Bi - P.SB[pb];
+                        Ci = Ci + P.SC[pb];
+                    }
+                    Ai += P.TA[pb];
+                    Bi += P.TB[pb];
+                    Ci += -P.TC[pb];
                 }
-                Ai += P.TA[pb];
-                Bi += P.TB[pb];
-                Ci += -P.TC[pb];
                 double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
                 diff = t1 + t2;
             } else {
@@ -668,6 +802,7 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
     const AtmLayer L = atm_at(A.atm, col);
     const double *dzi = L.dzi;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
     const double rr = 1. + 1. / sqrt(2.);
     const double c0 = 1. / (rr * A.dt[col]);
     const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
@@ -706,11 +841,18 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
             d -= eA;
             u -= eB;
             if (md) {
-                double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
-                double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
-                if (st) {
-                    ta = ta - P.SA[pb];
-                    tb = tb - P.SB[pb];
+                double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0);
+                double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp);
+                if (vmm) {
+                    double tx = 0.0;
+                    vm_lhs_adv(P, pb, 0, st, ta, tb, tx);
+                } else {
+                    ta = ta + P.TA[pb];
+                    tb = tb + P.TB[pb];
+                    if (st) {
+                        ta = ta - P.SA[pb];
+                        tb = tb - P.SB[pb];
+                    }
                 }
                 d -= ta;
                 if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
@@ -719,14 +861,22 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
                 if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
             }
         } else if (j == nz - 1) {
+            if (vmm && A.atm.n_diff_esc > 0) d -= vm_diff_lim(A.atm, L, i, y0[i]);   // before the stencil terms (op.py:2107)
             d -= eA;
             l -= eC;
             if (md) {
-                double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
-                double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
-                if (st) {
-                    ta = ta + P.SA[pb];
-                    tc = tc + P.SC[pb];
+                double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0);
+                double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm);
+                if (vmm) {
+                    double tx = 0.0;
+                    vm_lhs_adv(P, pb, 2, st, ta, tx, tc);
+                } else {
+                    ta = ta - P.TA[pb];
+                    tc = tc - P.TC[pb];
+                    if (st) {
+                        ta = ta + P.SA[pb];
+                        tc = tc + P.SC[pb];
+                    }
                 }
                 d -= ta;
                 l -= tc;
@@ -736,13 +886,20 @@ __global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
             u -= eB;
             l -= eC;
             if (md) {
-                double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
-                double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
-                double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
-                if (st) {
-                    ta = ta - P.SA[pb];
-                    tb = tb - P.SB[pb];
-                    tc = tc + P.SC[pb];
+                double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
+                double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
+                double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
+                if (vmm) {
+                    vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
+                } else {
+                    ta = ta + P.TA[pb];
+                    tb = tb + P.TB[pb];
+                    tc = tc - P.TC[pb];
+                    if (st) {
+                        ta = ta - P.SA[pb];
+                        tb = tb - P.SB[pb];
+                        tc = tc + P.SC[pb];
+                    }
                 }
                 d -= ta;
                 u -= tb;
@@ -848,6 +1005,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
     const AtmLayer L = atm_at(A.atm, col);
     const double *dzi = L.dzi;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
     const double rr = 1. + 1. / sqrt(2.);
     const double c0 = 1. / (rr * A.dt[col]);
     const AtmPre &P = A.atm.pre;
@@ -887,6 +1045,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         const size_t base = ((size_t)col * nz + j) * ni;
         const size_t vbase = ((size_t)col * nz + j) * ld;
         double eA = 0.0, tA = 0.0, tV = 0.0;       // subtracted from the diagonal in this order after the gather
+        double tE = 0.0;                           // diffusion-limited escape (top row of the *_vm variants), subtracted first
         if (tid < ld && !(dbg & 8)) {
             const int i = tid;
             if (i >= ni) {
@@ -902,26 +1061,41 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
                     eB = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
                     u -= eB;
                     if (md) {
-                        double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0) + P.TA[pb];
-                        double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp) + P.TB[pb];
-                        if (st) {
-                            ta = ta - P.SA[pb];
-                            tb = tb - P.SB[pb];
+                        double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0);
+                        double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp);
+                        if (vmm) {
+                            double tx = 0.0;
+                            vm_lhs_adv(P, pb, 0, st, ta, tb, tx);
+                        } else {
+                            ta = ta + P.TA[pb];
+                            tb = tb + P.TB[pb];
+                            if (st) {
+                                ta = ta - P.SA[pb];
+                                tb = tb - P.SB[pb];
+                            }
                         }
                         tA = ta;
                         u -= tb;
                     }
                     if (A.atm.use_botflux) tV = -1. * L.bot_vdep[i] / dzi[0];
                 } else if (j == nz - 1) {
+                    if (vmm && A.atm.n_diff_esc > 0) tE = vm_diff_lim(A.atm, L, i, y0[i]);   // top layer: nothing is prefetched over y0
                     eA = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
                     eC = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
                     l -= eC;
                     if (md) {
-                        double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0) - P.TA[pb];
-                        double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm) - P.TC[pb];
-                        if (st) {
-                            ta = ta + P.SA[pb];
-                            tc = tc + P.SC[pb];
+                        double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0);
+                        double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm);
+                        if (vmm) {
+                            double tx = 0.0;
+                            vm_lhs_adv(P, pb, 2, st, ta, tx, tc);
+                        } else {
+                            ta = ta - P.TA[pb];
+                            tc = tc - P.TC[pb];
+                            if (st) {
+                                ta = ta + P.SA[pb];
+                                tc = tc + P.SC[pb];
+                            }
                         }
                         tA = ta;
                         l -= tc;
@@ -933,13 +1107,20 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
                     u -= eB;
                     l -= eC;
                     if (md) {
-                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0 + P.TA[pb];
-                        double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp)) + P.TB[pb];
-                        double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm)) - P.TC[pb];
-                        if (st) {
-                            ta = ta - P.SA[pb];
-                            tb = tb - P.SB[pb];
-                            tc = tc + P.SC[pb];
+                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
+                        double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
+                        double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
+                        if (vmm) {
+                            vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
+                        } else {
+                            ta = ta + P.TA[pb];
+                            tb = tb + P.TB[pb];
+                            tc = tc - P.TC[pb];
+                            if (st) {
+                                ta = ta - P.SA[pb];
+                                tb = tb - P.SB[pb];
+                                tc = tc + P.SC[pb];
+                            }
                         }
                         tA = ta;
                         u -= tb;
@@ -1015,6 +1196,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
                 blk[i * ld + i] = 1.0;
             } else {
                 double d = c0 + blk[i * ld + i];
+                d -= tE;
                 d -= eA;
                 if (md) d -= tA;
                 if (A.atm.use_botflux && j == 0) d -= tV;

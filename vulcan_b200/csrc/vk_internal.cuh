@@ -74,6 +74,11 @@ struct AtmDev {
     const double *Kzz, *vz, *dzi, *Dzz, *vs, *Tco, *g, *M, *Ti, *Hpi, *ms, *alpha, *top_flux, *bot_flux, *bot_vdep;
     AtmPre pre;
     size_t pre_cs;              // column stride of the AtmPre arrays (0 when shared)
+    // use_vm_mol (op.py:2879-2888): vm [nz][ni] with column stride csv; in this mode the AtmPre T*/S* arrays hold upwind terms
+    int use_vm_mol, n_diff_esc;
+    const double *vm;
+    size_t csv;
+    const int *diff_esc_idx;
 };
 
 struct StepOptsDev {

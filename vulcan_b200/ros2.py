@@ -79,10 +79,11 @@ class Ros2(object):
         cfg = self.cfg
         vals = {n: np.asarray(getattr(atm, n), dtype=np.float64) for n in _DYN_ATM}
         flags = (bool(cfg.use_moldiff), bool(cfg.use_settling), bool(cfg.use_topflux), bool(cfg.use_botflux), bool(cfg.use_vm_mol))
-        if cfg.use_vm_mol:
-            raise NotImplementedError("use_vm_mol upwind variants (op.py:1599-1694) are not built yet")
+        use_vm = bool(cfg.use_vm_mol) and bool(cfg.use_moldiff)      # Ros2.solver's dispatch (op.py:2869-2888)
+        if use_vm:
+            vals["vm"] = np.asarray(atm.vm, dtype=np.float64)        # build_atm.py:735-739
         c = self._atm_cache
-        if c is not None and c[0] == flags and all(np.array_equal(c[1][n], vals[n]) for n in _DYN_ATM):
+        if c is not None and c[0] == flags and all(np.array_equal(c[1][n], vals[n]) for n in vals):
             return
         gas = self._gas(atm)
         if cfg.use_moldiff and not cfg.use_settling:
@@ -90,7 +91,9 @@ class Ros2(object):
         else:
             gas_lhs = gas
         self._columns(nz).set_atm(use_moldiff=flags[0], use_settling=flags[1], use_topflux=flags[2], use_botflux=flags[3],
-                                  gas_indx=gas, gas_indx_lhs=gas_lhs, shared=True, **vals)
+                                  gas_indx=gas, gas_indx_lhs=gas_lhs, use_vm_mol=use_vm,
+                                  diff_esc_idx=[self.species.index(sp) for sp in getattr(cfg, "diff_esc", [])] if use_vm else None,
+                                  shared=True, **vals)
         self._atm_cache = (flags, {n: v.copy() for n, v in vals.items()})
 
     def _sync_k(self, var, nz):
