@@ -204,6 +204,8 @@ def attach_conden(case, cfg, var, atm):
     the reference's live objects by oracle/dump_fixtures.py --conden): saturation pressures, particle sizes / densities, the
     condensation reaction list.  Returns the fixture dict (None when the config does not condense)."""
     path = os.path.join(GOLD, "%s_conden.npz" % case.tag)
+    if not os.path.exists(path):       # cfg-switch variants share the base config's saturation curves / particle tables
+        path = os.path.join(GOLD, "%s_conden.npz" % NETWORK_OF.get(case.tag, case.tag))
     if not os.path.exists(path):
         return None
     cf = dict(np.load(path, allow_pickle=False))
@@ -231,3 +233,39 @@ def ulp_diff(a, b):
     d = np.where(same, np.abs(ia - ib), np.inf)
     d = np.where((a == 0) & (b == 0), 0, d)
     return float(d.max())
+
+
+def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
+    """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
+    object and the Integration mirror until Integration.stop() says so (op.py:1067-1087).  `abi`: replaces the ctypes binding
+    the solver object talks to (only the CPU host-logic tests pass the oracle-backed stand-in of tests/oracle_columns.py)."""
+    import time
+    from vulcan_b200 import ros2 as ros2_mod
+    from vulcan_b200.integration import Integration
+    from vulcan_b200.ros2 import Ros2
+    real_abi = ros2_mod._abi
+    if abi is not None:
+        ros2_mod._abi = abi
+    try:
+        case = Case(tag, 0)
+        cfg, var, atm, para = mock_objects(case)
+        attach_conden(case, cfg, var, atm)
+        if count_max is not None:
+            cfg.count_max = count_max
+        var.y = case.st["y_ini"].copy()
+        if cfg.non_gas_sp:
+            var.ymix = var.y / np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))
+        else:
+            var.ymix = var.y / np.vstack(np.sum(var.y, axis=1))
+        solver = Ros2(cfg=cfg, species=list(case.st["species"]), compo=case.st["compo"], network=case.net, refine=refine)
+        solver.naming_solver(para)
+        # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
+        solver.compute_tau(var, atm)
+        solver.compute_flux(var, atm)
+        solver.compute_J(var, atm)
+        integ = Integration(solver, cfg, case.net.species)
+        t0 = time.time()
+        var, atm, para = integ(var, atm, para, max_wall_s=max_wall_s)
+        return case, var, atm, para, integ, time.time() - t0
+    finally:
+        ros2_mod._abi = real_abi           # never leak the stand-in into other tests of the same process

@@ -1,0 +1,30 @@
+"""Shared body of the lock-step tests: run the first N accepted steps of a config from the reference's initial state through the
+reference-facing host code (drop-in Ros2 object + Integration mirror) and compare the state reached with the state the
+UNMODIFIED reference had at the same step count (tests/golden/<cfg>_step00NN.npz: y, ymix, t, next dt, recorded at the top of
+its loop iteration NN).  Between step 0 and step NN the reference ran: the photolysis update at count 0, update_mu_dz /
+update_phi_esc at count 0, NN x (one_step incl. rejected attempts, condensation operators where enabled, hydrostatic rescale,
+step_size) - so agreement checks the whole per-step protocol, not one solver call."""
+import numpy as np
+
+from helpers import Case, have, run_config
+
+# (config, step count of the second fixture).  BASELINE.json configs 1-4 + the use_vm_mol variants.
+LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD189vm", 30), ("JupiterVm", 30), ("EarthVm", 30)]
+LOCKSTEP = [p for p in LOCKSTEP if have(p[0], "step%04d.npz" % p[1]) and have(p[0], "step0000.npz")]
+
+
+def lockstep(tag, nstep, abi=None, refine=1):
+    ref = Case(tag, nstep)
+    case, var, atm, para, integ, wall = run_config(tag, refine=refine, count_max=nstep - 1, abi=abi)   # Integration.stop: count > count_max
+    assert para.count == nstep
+    fx, cfg = ref.fx, ref.cfg
+    out = dict(t=abs(var.t - float(fx["t"])) / float(fx["t"]), dt=abs(var.dt - float(fx["dt"])) / float(fx["dt"]))
+    yr, mr = fx["y"], fx["ymix"]
+    m = (yr > cfg["atol"]) & (mr > cfg["mtol"])                      # the reference's own significance mask (op.py:2949-2950)
+    out["y"] = float(np.max(np.abs(var.y - yr)[m] / yr[m]))
+    m30 = yr > 1e-30
+    out["y_all"] = float(np.max(np.abs(var.y - yr)[m30] / yr[m30]))
+    out["ymix"] = float(np.max(np.abs(var.ymix - mr)[m] / mr[m]))
+    out["rejected"] = para.delta_count + para.nega_count + para.loss_count
+    out["wall"] = wall
+    return out

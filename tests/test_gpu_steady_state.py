@@ -13,36 +13,9 @@ import time
 import numpy as np
 import pytest
 
-from helpers import Case, GOLD, attach_conden, have, mock_objects
+from helpers import Case, GOLD, have, run_config
 
 pytestmark = pytest.mark.gpu
-
-
-def run_config(tag, refine=0, max_wall_s=600, count_max=None):
-    """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
-    object and the Integration mirror until Integration.stop() says so (op.py:1067-1087)."""
-    from vulcan_b200.integration import Integration
-    from vulcan_b200.ros2 import Ros2
-    case = Case(tag, 0)
-    cfg, var, atm, para = mock_objects(case)
-    attach_conden(case, cfg, var, atm)
-    if count_max is not None:
-        cfg.count_max = count_max
-    var.y = case.st["y_ini"].copy()
-    if cfg.non_gas_sp:
-        var.ymix = var.y / np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))
-    else:
-        var.ymix = var.y / np.vstack(np.sum(var.y, axis=1))
-    solver = Ros2(cfg=cfg, species=list(case.st["species"]), compo=case.st["compo"], network=case.net, refine=refine)
-    solver.naming_solver(para)
-    # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
-    solver.compute_tau(var, atm)
-    solver.compute_flux(var, atm)
-    solver.compute_J(var, atm)
-    integ = Integration(solver, cfg, case.net.species)
-    t0 = time.time()
-    var, atm, para = integ(var, atm, para, max_wall_s=max_wall_s)
-    return case, var, atm, para, integ, time.time() - t0
 
 
 def run_hd189(refine=0, max_wall_s=600):
