@@ -358,7 +358,9 @@ def main():
         try:
             from test_gpu_steady_state import run_hd189
             from helpers import GOLD
-            c0, var, atm, para, integ, wall_ss = run_hd189(refine=refine)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):      # the solver object prints like the reference does; stdout carries ONE JSON line
+                c0, var, atm, para, integ, wall_ss = run_hd189(refine=refine)
             ref = np.load(os.path.join(GOLD, "HD189_full.npz"))
             n_rej = para.delta_count + para.nega_count + para.loss_count
             line["single_column"]["time_to_steady_state"] = {

@@ -59,6 +59,12 @@ CONFIGS = {
     # (op.py:1794-1898, 2366-2444)
     "HD189vm": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_vm_mol": "True"}, extra=""),
     "JupiterVm": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"use_vm_mol": "True"}, extra=""),
+    # use_ion (op.py:2789-2820 compute_Jion, 2908-2911 / 2926 electron rows, 2998-3004 charge balance).  No shipped network has an
+    # `# ionisation` section, so this fixture-only variant appends one to NCHO_photo_network.txt in the scratch copy (ION_TEST_*
+    # below: H and H2 photo-ionisation with the shipped H / H2 ion cross sections and NASA-9 data of e, H_p, H2_p, H3_p plus four
+    # ion-neutral / recombination reactions).  The network is a test input; the code that runs it is the unmodified reference.
+    "HD189ion": dict(src="cfg_examples/vulcan_cfg_HD189.py",
+                     edits={"use_ion": "True", "network": "'thermo/NCHO_photo_ion_test_network.txt'"}, extra=""),
     "HD209S": dict(
         src="cfg_examples/vulcan_cfg_HD189.py",
         edits={
@@ -86,6 +92,37 @@ CONFIGS = {
         extra="",
     ),
 }
+
+ION_TEST_TWO_BODY = """\
+9001 [ H_p + e -> H                       ]  4.00E-12    -0.640       0.0      ion test (radiative recombination)
+9003 [ H2_p + e -> H + H                  ]  1.60E-08    -0.430       0.0      ion test
+9005 [ H2_p + H2 -> H3_p + H              ]  2.00E-09     0.000       0.0      ion test
+9007 [ H3_p + e -> H2 + H                 ]  4.00E-08    -0.500       0.0      ion test
+"""
+ION_TEST_IONISATION = """\
+# ionisation
+# id	# Reactions                                     sp		br_index #(starting from 1)
+9101 [ H -> H_p + e                       ]             H       1
+9103 [ H2 -> H2_p + e                     ]             H2      1
+"""
+
+
+def write_ion_test_network(dest):
+    """NCHO_photo_network.txt + four ion reactions at the end of the two-body block + an `# ionisation` section (ids are
+    renumbered by the reference's own make_chem_funs.py:35-110 when it rewrites the network file)."""
+    src = os.path.join(dest, "thermo", "NCHO_photo_network.txt")
+    out = os.path.join(dest, "thermo", "NCHO_photo_ion_test_network.txt")
+    with open(src) as f:
+        lines = f.readlines()
+    k = [i for i, l in enumerate(lines) if l.startswith("# 3-body and Diss")][0]
+    lines[k:k] = [ION_TEST_TWO_BODY, "\n"]
+    if not lines[-1].endswith("\n"):
+        lines[-1] += "\n"
+    lines.append(ION_TEST_IONISATION)
+    with open(out, "w") as f:
+        f.writelines(lines)
+    return out
+
 
 COMMON_OFF = {
     "use_live_plot": "False",
@@ -198,6 +235,8 @@ def stage(config, dest, run_codegen=True, quiet=True):
             "rho_p": "{'H2O_l_s': 0.9}",
             "remove_list": "[]",
         })
+    if config == "HD189ion":
+        write_ion_test_network(dest)
     text = _edit_cfg(text, edits)
     text += "\n# --- shims added by oracle/stage_reference.py (non-numerical) ---\nuse_adapt_rtol = False\n" + extra
     with open(os.path.join(dest, "vulcan_cfg.py"), "w") as f:
