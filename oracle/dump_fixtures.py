@@ -97,6 +97,19 @@ def static_dict(s):
             branch_sp=np.array([psp.index(sp) for sp, b in br]), branch_no=np.array([b for sp, b in br]),
             branch_rate_index=np.array([var.pho_rate_index[b] for b in br]),
         )
+        if cfg.use_ion:                     # photo-ionisation tables (op.py:253-269, 617-618, 751-768) and the charge bookkeeping
+            isp = sorted(var.ion_sp)
+            ibr = [(sp, b) for sp in isp for b in range(1, var.ion_branch[sp] + 1)]
+            import build_atm
+            d.update(
+                ion_sp=np.array(isp), ion_sp_idx=np.array([s.species.index(x) for x in isp]),
+                ion_cross=np.array([var.cross[sp] for sp in isp]),          # total absorption of the ionising species (compute_tau)
+                cross_Jion=np.array([var.cross_Jion[b] for b in ibr]),
+                ion_branch_sp=np.array([isp.index(sp) for sp, b in ibr]), ion_branch_no=np.array([b for sp, b in ibr]),
+                ion_branch_rate_index=np.array([var.ion_rate_index[b] for b in ibr]),
+                charge_list=np.array(list(var.charge_list)),
+                charge=np.array([float(build_atm.compo[build_atm.compo_row.index(sp)]["e"]) for sp in s.species]),
+            )
         if cfg.T_cross_sp:
             tsp = [sp for sp in psp if sp in cfg.T_cross_sp]
             d.update(T_cross_sp=np.array(tsp),
@@ -230,6 +243,11 @@ def capture_photo(s, tag, count, nsub=16):
         out["aflux_change%d" % it] = float(var.aflux_change)
         out["J%d" % it] = np.array([var.J_sp[b] for b in br])
         out["kphoto%d" % it] = np.array([np.asarray(var.k[var.pho_rate_index[b]]) for b in br])
+        if cfg.use_ion:                      # compute_Jion (op.py:2789-2820)
+            solver.compute_Jion(var, atm)
+            ibr = [(sp, b) for sp in sorted(var.ion_sp) for b in range(1, var.ion_branch[sp] + 1)]
+            out["Jion%d" % it] = np.array([var.Jion_sp[b] for b in ibr])
+            out["kion%d" % it] = np.array([np.asarray(var.k[var.ion_rate_index[b]]) for b in ibr])
     for n, v in keep.items():
         setattr(var, n, v)
     var.k.update(keep_k)

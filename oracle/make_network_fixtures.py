@@ -11,8 +11,12 @@ from vulcan_b200.network import Network
 REF = os.environ.get("VULCAN_REFERENCE", "/root/reference")
 NETS = {"HD189": "NCHO_photo_network.txt", "Jupiter": "NCHO_photo_network_lowT_Jupiter.txt",
         "Earth": "NCHO_earth_photo_network.txt", "HD209S": "SNCHO_photo_network_2025.txt"}
+# fixture-only ion test network: written into the scratch copy by oracle/stage_reference.py::write_ion_test_network
+ION = "/tmp/vulcan_ref_HD189ion/thermo/NCHO_photo_ion_test_network.txt"
+if os.path.exists(ION):
+    NETS["HD189ion"] = ION
 for tag, fn in NETS.items():
-    net = Network.from_file(os.path.join(REF, "thermo", fn))
+    net = Network.from_file(fn if os.path.isabs(fn) else os.path.join(REF, "thermo", fn))
     out = os.path.join(os.path.dirname(HERE), "tests", "golden", tag + "_network.json")
     with open(out, "w") as f:
         f.write(net.to_json())

@@ -50,10 +50,11 @@ def use(*a, **k):
 CONFIGS = {
     "HD189": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={}, extra=""),
     "Jupiter": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={}, extra=""),
-    # fixture-only variant: the shipped Jupiter cfg with the fix_species switch (op.py:862-893) brought forward from 1e8 s to
-    # 2e6 s of model time, so that a few hundred reference steps reach the switch and the fixed-species rows of Ros2.solver
-    # (op.py:2896-2906, 2921-2924, 2960-2970)
-    "JupiterFix": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"stop_conden_time": "2e6"}, extra=""),
+    # fixture-only variant: the shipped Jupiter cfg with condensation brought forward from 1e6 s to 10 s of model time and the
+    # fix_species switch (op.py:862-893) from 1e8 s to 500 s, so that ~200 reference steps exercise conden / the relaxation operators,
+    # reach the switch and the fixed-species rows of Ros2.solver (op.py:2896-2906, 2921-2924, 2960-2970).  (The shipped times are
+    # out of reach of a fixture run: 3000 reference steps = 27 min of CPU only get to t = 6.6e5 s.)
+    "JupiterFix": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"start_conden_time": "10.", "stop_conden_time": "500."}, extra=""),
     # use_vm_mol variants ("under testing" in the reference, vulcan_cfg.py:77): upwind advective form of molecular diffusion,
     # diffdf_vm + lhs_jac_tot_vm (op.py:1599-1694, 2044-2119) and, with settling, diffdf_settling_vm + lhs_jac_settling_vm
     # (op.py:1794-1898, 2366-2444)

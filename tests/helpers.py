@@ -20,7 +20,7 @@ def have(tag, name):
 
 
 # fixture variants that run a base config's network with different cfg switches (oracle/stage_reference.py::CONFIGS)
-NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}
+NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
 
 
 def load_network(tag):
@@ -72,7 +72,9 @@ CASES = [("HD189", 0), ("HD189", 10), ("HD189", 100), ("HD189", 300), ("Jupiter"
 # the latter with the diffusion-limited escape term (EarthVm)
 VM_CASES = [p for p in [("HD189vm", 0), ("HD189vm", 30), ("JupiterVm", 0), ("JupiterVm", 30), ("EarthVm", 0), ("EarthVm", 30)]
             if have(p[0], "step%04d.npz" % p[1])]
-CASES = CASES + VM_CASES
+# use_ion on the ion test network (oracle/stage_reference.py::write_ion_test_network): electron rows, charge balance, compute_Jion
+ION_CASES = [p for p in [("HD189ion", 0), ("HD189ion", 30)] if have(p[0], "step%04d.npz" % p[1])]
+CASES = CASES + VM_CASES + ION_CASES
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
 
 
@@ -93,14 +95,39 @@ def step_opts(case):
         for s in list(cfg.get("non_gas_sp", [])) + list(cfg.get("condense_sp", [])):
             dz[sp.index(s)] = 1
     assert not bool(case.fx["fix_species_start"]), "fixtures are taken before fix_species starts"
+    fix_mask = fix_y = None
+    if cfg.get("use_ion"):       # atm.fix_e_indx rows (store.py:157, op.py:2908-2911, 2926): the solve leaves the electrons untouched
+        ie = sp.index("e")
+        fix_mask = np.zeros((case.nz, ni), dtype=np.uint8)
+        fix_y = np.zeros((case.nz, ni))
+        fix_mask[:, ie] = 1
+        fix_y[:, ie] = case.y[:, ie]
+        dz = np.zeros(ni, dtype=np.uint8) if dz is None else dz
+        dz[ie] = 1
     return dict(fix_bot_idx=fbi, fix_bot_mix=fbm, n0_bot=float(case.st["n_0"][0]),
                 zero_delta_row0=bool(cfg.get("use_botflux") or fix_bot), delta_zero_sp=dz,
-                gas_indx_mix=case.gas_indx if cfg.get("non_gas_sp") else None)
+                gas_indx_mix=case.gas_indx if cfg.get("non_gas_sp") else None, fix_mask=fix_mask, fix_y=fix_y)
+
+
+def charge_balance(case, sol):
+    """op.py:2998-3004: [e] from charge neutrality after the step (host bookkeeping on one nz-vector)"""
+    if not case.cfg.get("use_ion"):
+        return sol
+    sp = list(case.net.species)
+    sol = sol.copy()
+    ie = sp.index("e")
+    sol[..., ie] = 0
+    for s in case.st["charge_list"]:
+        i = sp.index(str(s))
+        sol[..., ie] -= case.st["charge"][i] * sol[..., i]
+    return sol
 
 
 def oracle_step(case, oracle, atm, refine=0):
     o = step_opts(case)
-    return oracle.ros2_solver(atm, case.y, case.ymix, case.k, case.dt, case.cfg["mtol"], case.cfg["atol"], refine=refine, **o)
+    res = oracle.ros2_solver(atm, case.y, case.ymix, case.k, case.dt, case.cfg["mtol"], case.cfg["atol"], refine=refine, **o)
+    res["sol"] = charge_balance(case, res["sol"])
+    return res
 
 
 def gpu_columns(case, ncol=1, refine=0):
@@ -120,8 +147,10 @@ def gpu_columns(case, ncol=1, refine=0):
     fbv = None
     if len(o["fix_bot_idx"]):
         fbv = np.repeat((o["fix_bot_mix"] * o["n0_bot"])[None], ncol, axis=0)
+    rep = lambda a: None if a is None else np.repeat(a[None], ncol, axis=0)
     col.set_step_opts(case.cfg["mtol"], case.cfg["atol"], refine=refine, zero_delta_row0=o["zero_delta_row0"],
-                      fix_bot_idx=o["fix_bot_idx"], fix_bot_val=fbv, delta_zero_sp=o["delta_zero_sp"])
+                      fix_bot_idx=o["fix_bot_idx"], fix_bot_val=fbv, delta_zero_sp=o["delta_zero_sp"],
+                      fix_mask=rep(o["fix_mask"]), fix_y=rep(o["fix_y"]))
     return col
 
 
@@ -189,6 +218,16 @@ def mock_objects(case, with_photo=True):
             var.n_branch[s] = max(var.n_branch.get(s, 0), b)
             var.cross_J[(s, b)] = st["cross_J"][q]
             var.pho_rate_index[(s, b)] = int(st["branch_rate_index"][q])
+        if "ion_sp" in st:                      # use_ion: op.py:253-269, 617-618; build_atm.py:148-161, 271-277
+            isp = [str(s) for s in st["ion_sp"]]
+            var.ion_sp = set(isp)
+            var.cross.update({s: st["ion_cross"][i] for i, s in enumerate(isp)})
+            var.ion_branch, var.cross_Jion, var.ion_rate_index = {}, {}, {}
+            for q in range(len(st["ion_branch_sp"])):
+                s, b = isp[int(st["ion_branch_sp"][q])], int(st["ion_branch_no"][q])
+                var.ion_branch[s] = max(var.ion_branch.get(s, 0), b)
+                var.cross_Jion[(s, b)] = st["cross_Jion"][q]
+                var.ion_rate_index[(s, b)] = int(st["ion_branch_rate_index"][q])
         if "T_cross_sp" in st:
             tsp = [str(x) for x in st["T_cross_sp"]]
             var.cross_T = {s: st["cross_T"][q] for q, s in enumerate(tsp)}
@@ -196,6 +235,8 @@ def mock_objects(case, with_photo=True):
             for q, b in enumerate(st["cross_J_T_branch"]):
                 b = int(b)
                 var.cross_J_T[(psp[int(st["branch_sp"][b])], int(st["branch_no"][b]))] = st["cross_J_T"][q]
+    if "charge_list" in st:
+        var.charge_list = [str(s) for s in st["charge_list"]]
     return cfg, var, atm, para
 
 
@@ -235,6 +276,35 @@ def ulp_diff(a, b):
     return float(d.max())
 
 
+def photolysis_via_dropin(tag, step, abi=None):
+    """two consecutive photolysis updates (compute_tau / flux / J and, with use_ion, compute_Jion) through the drop-in solver object
+    from a zeroed diffuse-flux state, as recorded in <cfg>_photo<step>.npz; returns (fixture, [var after update 1, 2] summaries)"""
+    from vulcan_b200 import ros2 as ros2_mod
+    from vulcan_b200.ros2 import Ros2
+    real_abi = ros2_mod._abi
+    if abi is not None:
+        ros2_mod._abi = abi
+    try:
+        case = Case(tag, step)
+        cfg, var, atm, para = mock_objects(case)
+        px = dict(np.load(os.path.join(GOLD, "%s_photo%04d.npz" % (tag, step))))
+        var.y, var.ymix = px["y"], px["ymix"]
+        atm.dz = px["dz"]
+        solver = Ros2(cfg=cfg, compo=case.st["compo"], network=case.net, charge=case.st["charge"] if "charge" in case.st else None)
+        out = []
+        for it in (1, 2):
+            solver.compute_tau(var, atm)
+            solver.compute_flux(var, atm)
+            solver.compute_J(var, atm)
+            if cfg.use_ion:
+                solver.compute_Jion(var, atm)
+            out.append(dict(aflux=var.aflux.copy(), aflux_change=var.aflux_change, k={i: np.array(v, dtype=float, copy=True) for i, v in var.k.items()},
+                            Jion={b: v.copy() for b, v in getattr(var, "Jion_sp", {}).items()}))
+        return case, px, out
+    finally:
+        ros2_mod._abi = real_abi
+
+
 def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
     """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
     object and the Integration mirror until Integration.stop() says so (op.py:1067-1087).  `abi`: replaces the ctypes binding
@@ -257,7 +327,8 @@ def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
             var.ymix = var.y / np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))
         else:
             var.ymix = var.y / np.vstack(np.sum(var.y, axis=1))
-        solver = Ros2(cfg=cfg, species=list(case.st["species"]), compo=case.st["compo"], network=case.net, refine=refine)
+        solver = Ros2(cfg=cfg, species=list(case.st["species"]), compo=case.st["compo"], network=case.net, refine=refine,
+                      charge=case.st["charge"] if "charge" in case.st else None)
         solver.naming_solver(para)
         # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
         solver.compute_tau(var, atm)

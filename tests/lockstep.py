@@ -8,8 +8,9 @@ import numpy as np
 
 from helpers import Case, have, run_config
 
-# (config, step count of the second fixture).  BASELINE.json configs 1-4 + the use_vm_mol variants.
-LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD189vm", 30), ("JupiterVm", 30), ("EarthVm", 30)]
+# (config, step count of the second fixture).  BASELINE.json configs 1-4 + the use_vm_mol variants + use_ion on the ion test network.
+LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD189vm", 30), ("JupiterVm", 30), ("EarthVm", 30),
+            ("HD189ion", 30)]
 LOCKSTEP = [p for p in LOCKSTEP if have(p[0], "step%04d.npz" % p[1]) and have(p[0], "step0000.npz")]
 
 
@@ -28,3 +29,25 @@ def lockstep(tag, nstep, abi=None, refine=1):
     out["rejected"] = para.delta_count + para.nega_count + para.loss_count
     out["wall"] = wall
     return out
+
+
+def check_ion_photolysis(abi=None):
+    """compute_Jion (op.py:2789-2820) through the drop-in object against the reference's own output on the ion test network"""
+    from helpers import photolysis_via_dropin
+    case, px, out = photolysis_via_dropin("HD189ion", 0, abi=abi)
+    st = case.st
+    isp = [str(s) for s in st["ion_sp"]]
+    for it in (1, 2):
+        o = out[it - 1]
+        sel = px["bin_sel"]
+        ref = px["aflux%d" % it]
+        assert np.max(np.abs(o["aflux"][:, sel] - ref) / np.maximum(np.abs(ref), 1e-30 * np.abs(ref).max())) < 1e-9
+        for q in range(len(st["ion_branch_sp"])):
+            s, b = isp[int(st["ion_branch_sp"][q])], int(st["ion_branch_no"][q])
+            jref, kref = px["Jion%d" % it][q], px["kion%d" % it][q]
+            assert np.abs(jref).max() > 0
+            assert np.allclose(o["Jion"][(s, b)], jref, rtol=1e-9, atol=1e-12 * np.abs(jref).max() + 1e-300), (s, b)
+            assert np.allclose(o["k"][int(st["ion_branch_rate_index"][q])], kref, rtol=1e-9, atol=1e-12 * np.abs(kref).max() + 1e-300)
+        for q in range(len(st["branch_sp"])):       # the photodissociation rows next to them are unaffected
+            kref = px["kphoto%d" % it][q]
+            assert np.allclose(o["k"][int(st["branch_rate_index"][q])], kref, rtol=1e-9, atol=1e-12 * np.abs(kref).max() + 1e-300)

@@ -4,7 +4,8 @@ reference's initial state, must arrive at the state the UNMODIFIED reference had
 (tests/lockstep.py).  The CPU twin (tests/test_lockstep_host.py) runs the same host code on the oracle-backed stand-in."""
 import pytest
 
-from lockstep import LOCKSTEP, lockstep
+from helpers import have
+from lockstep import LOCKSTEP, check_ion_photolysis, lockstep
 
 pytestmark = pytest.mark.gpu
 
@@ -16,3 +17,9 @@ def test_first_steps_reproduce_the_reference(tag, nstep):
           (tag, nstep, r["t"], r["dt"], r["y"], r["y_all"], r["ymix"], r["rejected"], r["wall"]))
     assert r["t"] < 1e-9 and r["dt"] < 1e-6       # same accept / reject sequence and step sizes as the reference
     assert r["y"] < 1e-8 and r["ymix"] < 1e-8     # CPU twin measures 2e-15 ... 2e-9 (two different backward-stable solvers)
+
+
+@pytest.mark.skipif(not have("HD189ion", "photo0000.npz"), reason="fixture missing")
+def test_compute_Jion_on_the_gpu():
+    """photo-ionisation rates (op.py:2789-2820): the ion branches ride in the device branch table of jrate_kernel"""
+    check_ion_photolysis()

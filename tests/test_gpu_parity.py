@@ -54,6 +54,8 @@ def test_lhs_blocks(case):
 
 def test_blocktri_solve_vs_truth(case):
     """the GPU block-tridiagonal solve is at least as close to the extended-precision solution as LAPACK's (reference)."""
+    if "k1" not in case.fx:
+        pytest.skip("no LAPACK stage vectors in this fixture (rows replaced inside Ros2.solver: electrons / fixed species)")
     o = case.oracle
     D, up, dn = o.lhs(case.atm, case.y, case.k, case.dt)
     rhs = case.fx["chemdf"] + case.fx["diffdf"]

@@ -3,7 +3,8 @@ wired to the oracle-backed stand-in of the C ABI (tests/oracle_columns.py) and m
 first N steps of every BASELINE single-column config.  The GPU twin of this test is tests/test_gpu_lockstep.py."""
 import pytest
 
-from lockstep import LOCKSTEP, lockstep
+from helpers import have
+from lockstep import LOCKSTEP, check_ion_photolysis, lockstep
 from oracle_columns import oracle_backed_abi
 
 
@@ -14,6 +15,11 @@ def test_first_steps_reproduce_the_reference(tag, nstep):
           (tag, nstep, r["t"], r["dt"], r["y"], r["y_all"], r["ymix"], r["rejected"], r["wall"]))
     assert r["t"] < 1e-9 and r["dt"] < 1e-6
     assert r["y"] < 1e-8 and r["ymix"] < 1e-8
+
+
+@pytest.mark.skipif(not have("HD189ion", "photo0000.npz"), reason="fixture missing")
+def test_compute_Jion_host_protocol():
+    check_ion_photolysis(abi=oracle_backed_abi())
 
 
 def test_stand_in_is_not_left_installed():

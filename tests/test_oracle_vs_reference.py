@@ -83,6 +83,8 @@ def test_solver_vs_truth(case):
     """Production dt: the oracle's block solve must be at least as close to an extended-precision solution of the
     SAME system as the reference's LAPACK result is (both measured on y + k1/r under the reference's own
     significance mask, op.py:2948-2950), and delta must agree to the accuracy delta is used at (rtol test)."""
+    if "k1" not in case.fx:
+        pytest.skip("no LAPACK stage vectors in this fixture (rows replaced inside Ros2.solver: electrons / fixed species)")
     o = case.oracle
     D, up, dn = o.lhs(case.atm, case.y, case.k, case.dt)
     rhs = case.fx["chemdf"] + case.fx["diffdf"]

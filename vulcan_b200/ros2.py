@@ -17,7 +17,7 @@ _DYN_ATM = ("Kzz", "vz", "dzi", "Dzz", "vs", "Tco", "g", "M", "Ti", "Hpi", "ms",
 
 
 class Ros2(object):
-    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=0, network=None):
+    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=0, network=None, charge=None):
         """cfg: the vulcan_cfg module (imported like the reference does when omitted); species: chem_funs.spec_list
         (only used to cross-check the network compiler's species order); compo: {species: {atom: n}} or an
         [ni][na] array for `loss` (read from cfg.com_file when omitted)."""
@@ -43,6 +43,8 @@ class Ros2(object):
         self._loss_eps, self._rtol0 = cfg.loss_eps, cfg.rtol
         self._dt_var_min, self._dt_var_max, self._dt_min, self._dt_max = cfg.dt_var_min, cfg.dt_var_max, cfg.dt_min, cfg.dt_max
         self._compo = self._load_compo(compo)
+        # use_ion: the 'e' column of all_compose.txt (build_atm.py:161), read by the charge balance (op.py:2998-3004)
+        self._charge = self._load_charge(charge) if getattr(cfg, "use_ion", False) else None
         self._devnet = _abi.DeviceNetwork(self.network, device)
         self._col = None
         self._k_cache = None
@@ -64,6 +66,17 @@ class Ros2(object):
         if isinstance(compo, dict):
             return np.array([[compo[s][a] for a in atoms] for s in self.species], dtype=float)
         return np.asarray(compo, dtype=float)
+
+    def _load_charge(self, charge):
+        if charge is None:
+            with open(self.cfg.com_file) as f:
+                cols = f.readline().split()
+            tab = np.genfromtxt(self.cfg.com_file, names=True, dtype=["U20"] + ["int"] * (len(cols) - 2) + ["float"])
+            rows = list(tab["species"])
+            return np.array([float(tab[rows.index(s)]["e"]) for s in self.species])
+        if isinstance(charge, dict):
+            return np.array([float(charge[s]) for s in self.species])
+        return np.asarray(charge, dtype=float)
 
     def _columns(self, nz):
         if self._col is None or self._col.nz != nz:
@@ -129,7 +142,17 @@ class Ros2(object):
                     fix_y[:top, i] = np.asarray(var.fix_y[s])[:top]
                     dz_sp[i] = 1
         if cfg.use_ion:
-            raise NotImplementedError("use_ion (electron row / charge balance, op.py:2908-2911, 2998-3004) is not built yet")
+            # atm.fix_e_indx (store.py:157): the electron row of every layer is  1/(r h) e_i  with a zero right-hand side in both
+            # stages (op.py:2908-2911, 2926), i.e. the solve leaves e untouched: sol[:, e] = y[:, e] and its delta is exactly 0
+            ie = self.species.index("e")
+            if fix_mask is None:
+                fix_mask = np.zeros((nz, ni), dtype=np.uint8)
+                fix_y = np.zeros((nz, ni))
+            if dz_sp is None:
+                dz_sp = np.zeros(ni, dtype=np.uint8)
+            fix_mask[:, ie] = 1
+            fix_y[:, ie] = np.asarray(var.y)[:, ie]
+            dz_sp[ie] = 1
         fbi = list(self.fix_sp_bot_index)
         fbv = self.fix_sp_bot_mix * atm.n_0[0] if fbi else None               # op.py:2946
         zero0 = bool(cfg.use_botflux or cfg.use_fix_sp_bot)                   # op.py:2953
@@ -162,6 +185,12 @@ class Ros2(object):
         var.y = sol[0]
         var.ymix = ymix[0]
         para.delta = float(delta[0]) if status[0] == 0 else float("nan")     # a singular block fails step_ok like a NaN would
+        if cfg.use_ion:                                                      # op.py:2998-3004: [e] from charge neutrality (ymix is not redone)
+            ie = self.species.index("e")
+            var.y[:, ie] = 0
+            for sp in var.charge_list:
+                i = self.species.index(sp)
+                var.y[:, ie] -= self._charge[i] * var.y[:, i]
         return var, para
 
     def one_step(self, var, atm, para):                                      # op.py:3091-3103
@@ -249,8 +278,6 @@ class Ros2(object):
     # ------------------------------------------------------------------ photolysis (op.py:2580-2786)
     def _photo_setup(self, var, atm, nz):
         cfg, sp = self.cfg, self.species
-        if cfg.use_ion:
-            raise NotImplementedError("photo-ionisation (compute_Jion, op.py:2789-2820) is not built yet")
         absp = sorted(set(var.photo_sp) | set(getattr(var, "ion_sp", set())))
         psp = sorted(var.photo_sp)
         tsp = list(getattr(cfg, "T_cross_sp", []))
@@ -268,6 +295,18 @@ class Ros2(object):
             cross_J_T = np.array([var.cross_J_T[(s, b)] if s in tsp else np.zeros((nz, nbin)) for s, b in br])
         rid = np.array([0 if var.pho_rate_index[b] in cfg.remove_list else var.pho_rate_index[b] for b in br], dtype=np.int32)
         self._branches = br
+        self._ion_branches = []
+        if cfg.use_ion:
+            # compute_Jion (op.py:2789-2820) is the same trapezoid contraction as compute_J over the ion cross sections (no
+            # temperature dependence): its branches ride in the same device table behind the photodissociation branches
+            ibr = [(s, b) for s in sorted(var.ion_sp) for b in range(1, var.ion_branch[s] + 1)]
+            self._ion_branches = ibr
+            cross_J = np.concatenate([cross_J, np.array([var.cross_Jion[b] for b in ibr])])
+            rid = np.concatenate([rid, np.array([0 if var.ion_rate_index[b] in cfg.remove_list else var.ion_rate_index[b]
+                                                  for b in ibr], dtype=np.int32)])
+            if br_is_T.any():
+                br_is_T = np.concatenate([br_is_T, np.zeros(len(ibr), dtype=np.uint8)])
+                cross_J_T = np.concatenate([cross_J_T, np.zeros((len(ibr), nz, nbin))])
         self._columns(nz).photo_setup(var.bins, var.sflux_top, var.sflux_din12_indx, var.dbin1, var.dbin2, cfg.sl_angle, cfg.edd,
                                       cfg.flux_atol, cfg.f_diurnal, [sp.index(s) for s in absp], cross_abs,
                                       [sp.index(s) for s in psp], np.array([var.cross[s] for s in psp]),
@@ -310,7 +349,22 @@ class Ros2(object):
                 var.k[var.pho_rate_index[(s, b)]] = var.J_sp[(s, b)] * self.cfg.f_diurnal
         self._k_cache = None          # the device copy of k already holds the new J rows; re-verified on the next solver call
         self._k_ids = None
+        self._jion_cache = c if self.cfg.use_ion else None     # Integration calls compute_Jion right after (op.py:828-829)
         self._photo_cache = None
 
-    def compute_Jion(self, var, atm):
-        raise NotImplementedError("photo-ionisation (op.py:2789-2820) is listed as 'next' in SURVEY.md §8f")
+    def compute_Jion(self, var, atm):                                        # op.py:2789-2820
+        c = getattr(self, "_jion_cache", None)
+        if c is None:
+            c = self._photo_run(var, atm)
+            self._photo_cache = None
+        nz = var.y.shape[0]
+        var.Jion_sp = dict([((s, b), np.zeros(nz)) for s in var.ion_sp for b in range(var.ion_branch[s] + 1)])
+        n0 = len(self._branches)
+        for q, (s, b) in enumerate(self._ion_branches):
+            var.Jion_sp[(s, b)] = c["J"][n0 + q].copy()
+            var.Jion_sp[(s, 0)] += var.Jion_sp[(s, b)]
+            if var.ion_rate_index[(s, b)] not in self.cfg.remove_list:
+                var.k[var.ion_rate_index[(s, b)]] = var.Jion_sp[(s, b)] * self.cfg.f_diurnal
+        self._k_cache = None
+        self._k_ids = None
+        self._jion_cache = None
