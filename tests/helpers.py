@@ -74,7 +74,10 @@ VM_CASES = [p for p in [("HD189vm", 0), ("HD189vm", 30), ("JupiterVm", 0), ("Jup
             if have(p[0], "step%04d.npz" % p[1])]
 # use_ion on the ion test network (oracle/stage_reference.py::write_ion_test_network): electron rows, charge balance, compute_Jion
 ION_CASES = [p for p in [("HD189ion", 0), ("HD189ion", 30)] if have(p[0], "step%04d.npz" % p[1])]
-CASES = CASES + VM_CASES + ION_CASES
+# Jupiter after the fix_species switch (fixture-only cfg variant JupiterFix): fixed-species rows inside Ros2.solver
+import glob as _glob
+FIX_CASES = [("JupiterFix", int(os.path.basename(f)[len("JupiterFix_step"):-4])) for f in sorted(_glob.glob(os.path.join(GOLD, "JupiterFix_step*.npz")))]
+CASES = CASES + VM_CASES + ION_CASES + FIX_CASES
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
 
 
@@ -94,8 +97,16 @@ def step_opts(case):
         dz = np.zeros(ni, dtype=np.uint8)
         for s in list(cfg.get("non_gas_sp", [])) + list(cfg.get("condense_sp", [])):
             dz[sp.index(s)] = 1
-    assert not bool(case.fx["fix_species_start"]), "fixtures are taken before fix_species starts"
     fix_mask = fix_y = None
+    if bool(case.fx["fix_species_start"]):       # op.py:2896-2906, 2921-2924, 2960-2970: rows of the fixed species below their cold trap
+        fix_mask = np.zeros((case.nz, ni), dtype=np.uint8)
+        fix_y = np.zeros((case.nz, ni))
+        for q, s in enumerate(case.fx["fix_species"]):
+            i = sp.index(str(s))
+            top = case.nz if not bool(case.fx["fix_from_coldtrap"]) else int(case.fx["conden_min_lev"][q])
+            fix_mask[:top, i] = 1
+            fix_y[:top, i] = case.fx["fix_y"][q][:top]
+            dz[i] = 1
     if cfg.get("use_ion"):       # atm.fix_e_indx rows (store.py:157, op.py:2908-2911, 2926): the solve leaves the electrons untouched
         ie = sp.index("e")
         fix_mask = np.zeros((case.nz, ni), dtype=np.uint8)

@@ -3,7 +3,7 @@ inputs and against the golden fixtures produced by the unmodified reference.  Ru
 import numpy as np
 import pytest
 
-from helpers import CASES, PHOTO_CASES, Case, GOLD, case_id, gpu_columns, have, oracle_step, photo_tables, step_opts, ulp_diff
+from helpers import CASES, PHOTO_CASES, Case, GOLD, case_id, charge_balance, gpu_columns, have, oracle_step, photo_tables, step_opts, ulp_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -41,14 +41,29 @@ def test_lhs_blocks(case):
     (same term order) and within Jacobian rounding of the reference's sympy ordering."""
     D, up, dn = case.col.eval_lhs(case.y, case.dt)
     Do, upo, dno = case.oracle.lhs(case.atm, case.y, case.k, case.dt)
-    assert np.array_equal(up[0], case.fx["lhs_up"]) and np.array_equal(dn[0], case.fx["lhs_dn"])
+    fup, fdn, fblocks = case.fx["lhs_up"].copy(), case.fx["lhs_dn"].copy(), case.fx["lhs_blocks"].copy()
+    fm = step_opts(case)["fix_mask"]
+    if fm is not None:
+        # rows Ros2.solver replaces AFTER jac_tot (electrons, op.py:2908-2911): the device lhs has them already, so apply the same
+        # surgery to the oracle's and the reference's raw lhs_jac_tot output before comparing
+        c0 = 1. / (R * case.dt)
+        jj, ii = np.nonzero(fm)
+        Do[jj, ii, :] = 0.0
+        Do[jj, ii, ii] = c0
+        for a in (upo, dno, fup, fdn):
+            a[jj, ii] = 0.0
+        for q, j in enumerate(case.fx["layers"]):
+            rows = np.nonzero(fm[j])[0]
+            fblocks[q][rows, :] = 0.0
+            fblocks[q][rows, rows] = c0
+    assert np.array_equal(up[0], fup) and np.array_equal(dn[0], fdn)
     assert np.array_equal(up[0], upo) and np.array_equal(dn[0], dno)
     # entries longer than 16 terms are summed in 16-term segments on the GPU (balanced warps): rounding-level vs the oracle
     scale = np.abs(Do).max(axis=2, keepdims=True)
     assert np.max(np.abs(D[0] - Do) / np.maximum(scale, 1e-300)) < 4e-15
     assert np.array_equal(D[0] != 0, Do != 0)
     for i, j in enumerate(case.fx["layers"]):
-        ref = case.fx["lhs_blocks"][i]
+        ref = fblocks[i]
         assert np.max(np.abs(D[0, j] - ref) / np.maximum(np.abs(ref).max(axis=1, keepdims=True), 1e-300)) < 4e-15
 
 
@@ -86,6 +101,11 @@ def test_ros2_step(case):
     col = _columns(case, refine=1)
     sol, ymix, delta, status = col.ros2_solve(case.y, case.ymix, case.dt)
     assert status[0] == 0
+    so = step_opts(case)
+    if so["fix_mask"] is not None and not cfg.get("use_ion"):     # fixed species below their cold trap: re-imposed exactly (op.py:2960-2968)
+        fm = so["fix_mask"].astype(bool)
+        assert np.array_equal(sol[0][fm], so["fix_y"][fm])
+    sol = charge_balance(case, sol)          # use_ion only: [e] from charge neutrality is the caller's bookkeeping (op.py:2998-3004)
     ref = case.fx["sol"]
     if case.dt <= 1e-6:
         m = ref > 1e-30

@@ -4,7 +4,7 @@ REFERENCE (oracle/dump_fixtures.py, PYTHONHASHSEED=0).  The reference ships no t
 import numpy as np
 import pytest
 
-from helpers import CASES, PHOTO_CASES, Case, case_id, have, oracle_step, photo_tables, ulp_diff
+from helpers import CASES, PHOTO_CASES, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
 from oracle import Oracle
 
 R = 1. + 1. / 2. ** 0.5
@@ -77,6 +77,27 @@ def test_solver_one_step_small_dt(case):
     assert abs(res["delta"] - float(case.fx["delta"])) <= 1e-10 * float(case.fx["delta"])
     m = case.fx["sol_ymix"] > 1e-30
     assert np.max(np.abs(res["ymix"] - case.fx["sol_ymix"])[m] / case.fx["sol_ymix"][m]) < 1e-10
+
+
+def test_solver_with_replaced_rows(case):
+    """rows Ros2.solver replaces by  1/(r h) e_i  with a zero right-hand side: the fixed species below their cold trap after the
+    fix_species switch (op.py:2896-2906, 2921-2924, 2960-2970) and the electrons with use_ion (op.py:2908-2911, 2926, 2998-3004).
+    Production dt, so the comparison with the reference's LAPACK result is made under the reference's own significance mask."""
+    o = step_opts(case)
+    if o["fix_mask"] is None:
+        pytest.skip("no replaced rows in this fixture")
+    res = oracle_step(case, case.oracle, case.atm, refine=1)
+    ref, cfg = case.fx["sol"], case.cfg
+    fm = o["fix_mask"].astype(bool)
+    if not cfg.get("use_ion"):
+        assert np.array_equal(res["sol"][fm], o["fix_y"][fm])          # re-imposed exactly (op.py:2960-2968)
+        assert np.array_equal(ref[fm], o["fix_y"][fm])
+    m = (ref > cfg["atol"]) & (case.fx["sol_ymix"] > cfg["mtol"])
+    err = np.max(np.abs(res["sol"] - ref)[m] / ref[m])
+    print("%s-%d dt %.2e: replaced rows %d, max rel diff vs reference under its mask %.2e, delta %.6e vs %.6e" %
+          (case.tag, case.step, case.dt, int(fm.sum()), err, res["delta"], float(case.fx["delta"])))
+    assert err < (1e-10 if case.dt <= 1e-6 else 1e-5)
+    assert abs(res["delta"] - float(case.fx["delta"])) <= 1e-6 * float(case.fx["delta"])
 
 
 def test_solver_vs_truth(case):
