@@ -945,7 +945,7 @@ static inline LhsMlSmem lhs_ml_layout(const NetDev &n, int ld)
     L.ym = o; o += n.ni + 2; L.y0 = o; o += n.ni + 2; L.yp = o; o += n.ni + 2;
     L.dprod = o; o += n.n_uniq + 2;
     L.part = o; o += n.n_part + 2;
-    L.misc = o; o += 16;
+    L.misc = o; o += 16 + 16;       // [0..3] layer sums, [4] spare, [8..15] coefficient table, [16..31] 128 diagonal-in-pattern flags
     o += o & 1;
     L.blk = o; o += ld * ld + (ld & 1);
     L.tab = o;
@@ -969,7 +969,6 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
     const int tid = threadIdx.x, nt = blockDim.x;
     double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
     double *ysum = sm + SL.misc, *ctab = sm + SL.misc + 8, *blk = sm + SL.blk;
-    int *gctr = reinterpret_cast<int *>(sm + SL.misc + 4);   // group counter of the gather
     uint2 *grp = reinterpret_cast<uint2 *>(sm + SL.tab);
     uint2 *multi = grp + (A.net.n_grp + 1);
     unsigned *uq = reinterpret_cast<unsigned *>(multi + (A.net.n_multi + 1));
@@ -998,10 +997,31 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         for (int i = tid; i < (A.net.n_tt + 1) / 2; i += nt) dst[i] = src[i];
     }
     if (tid == 0) dprod[A.net.n_uniq] = 0.0;      // the padding product
+    // The block buffer is zeroed ONCE: every layer has the same sparsity pattern, the gather assigns (never accumulates into) each
+    // pattern entry, so entries outside the pattern stay zero from layer to layer.  Only the diagonal needs care: a diagonal entry that
+    // is not in the chemical pattern would otherwise carry the previous layer's value into  d = c0 + blk[i][i]  -> per-species flags.
     for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
+    unsigned char *dflag = reinterpret_cast<unsigned char *>(sm + SL.misc + 16);
+    if (tid < 128) dflag[tid] = 0;
     if (tid == 0) { y0[ni + 1] = 1.0; }
     if (tid < 8) ctab[tid] = c_jac_coef[tid];     // per-lane lookups: shared memory (a constant bank would serialise)
-    if (tid == 0) *gctr = 0;
+    __syncthreads();
+    for (int i = tid; i < A.net.n_grp * 32; i += nt) {
+        const unsigned sg = seg[i];
+        const unsigned row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+        if (row != 0xffu && row == colx) dflag[row] = 1;       // whole entry or a partial of a split one: both end up in blk[row][row]
+    }
+    for (int i = tid; i < A.net.n_multi; i += nt) {
+        const uint2 me = multi[i];
+        if ((me.x & 0xffff) == (me.x >> 16)) dflag[me.x & 0xffff] = 1;
+    }
+    const unsigned blk_s = (unsigned)__cvta_generic_to_shared(blk);
+    const unsigned blk_bytes = (unsigned)(ld * ld * sizeof(double));
+    const bool bulk = (blk_bytes % 16u) == 0 && !(dbg & 16);
+    const int warp = tid >> 5;
+    // gather hand-out: pairs of groups dealt round-robin, the warps that own no species (no transport work) first
+    const int nwarp = nt >> 5, nw_tr = (ld + 31) >> 5;
+    const int gslot = (warp >= nw_tr) ? warp - nw_tr : warp + (nwarp - nw_tr);
     const AtmLayer L = atm_at(A.atm, col);
     const double *dzi = L.dzi;
     const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
@@ -1012,7 +1032,12 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
 
     for (int j = j0; j < j1; j++) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (tid == 0) y0[ni] = A.atm.M[col * A.atm.csz + j];
+        if (tid == 0) {
+            y0[ni] = A.atm.M[col * A.atm.csz + j];
+            // the previous layer's block is still being read out of shared memory by the bulk store: the first writers (gather /
+            // diagonal) run behind the barrier below
+            if (bulk) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         __syncthreads();
         // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums
         if (!(dbg & 4)) for (int u = tid; u < A.net.n_uniq; u += nt) {
@@ -1137,11 +1162,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         // counts, no divergence
         {
             const int lane = tid & 31;
-            while (!(dbg & 2)) {
-                int gI = 0;
-                if (lane == 0) gI = atomicAdd(gctr, 2);
-                gI = __shfl_sync(0xffffffffu, gI, 0);
-                if (gI >= A.net.n_grp) break;
+            for (int gI = 2 * gslot; gI < A.net.n_grp && !(dbg & 2); gI += 2 * nwarp) {
                 const int gJ = gI + 1;
                 const bool two = gJ < A.net.n_grp;
                 const uint2 ga = grp[gI], gb = grp[two ? gJ : gI];
@@ -1187,7 +1208,6 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
             for (int q = 0; q < n; q++) acc += part[s0 + q];
             blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
         }
-        if (tid == 0) *gctr = 0;
         __syncthreads();
         // ---- diagonal: c0 + negJ_ss - transport
         if (tid < ld && !(dbg & 8)) {
@@ -1195,7 +1215,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
             if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
                 blk[i * ld + i] = 1.0;
             } else {
-                double d = c0 + blk[i * ld + i];
+                double d = c0 + (dflag[i] ? blk[i * ld + i] : 0.0);
                 d -= tE;
                 d -= eA;
                 if (md) d -= tA;
@@ -1207,20 +1227,26 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
                 blk[i * ld + i] = d;
             }
         }
+        // every thread's generic-proxy writes of the block (gather, split entries, diagonal) -> visible to the async proxy, then the barrier
+        if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        // ---- phase D: stream the block out and zero it behind the copy
+        // ---- phase D: the finished block leaves as ONE asynchronous TMA bulk store (shared -> global); nothing is re-zeroed (see the
+        // set-up).  The copy is drained at the top of the next layer, behind that layer's wait for its prefetched rows.
         double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
         if (dbg & 1) {
-        } else if ((ld & 1) == 0) {
-            for (int q = tid; q < ld * ld / 2; q += nt) {
-                reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
-                reinterpret_cast<double2 *>(blk)[q] = make_double2(0.0, 0.0);
+        } else if (bulk) {
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Dg), "r"(blk_s), "r"(blk_bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+        } else if ((ld & 1) == 0) {
+            for (int q = tid; q < ld * ld / 2; q += nt) reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
         } else {
-            for (int q = tid; q < ld * ld; q += nt) { Dg[q] = blk[q]; blk[q] = 0.0; }
+            for (int q = tid; q < ld * ld; q += nt) Dg[q] = blk[q];
         }
-        // (the barrier at the top of the next iteration orders the zeroed block and the prefetched rows)
+        // (the barrier at the top of the next iteration orders the stored block and the prefetched rows)
     }
+    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store
 }
 
 // ------------------------------------------------------------------------------------------------------------------
