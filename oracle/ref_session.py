@@ -17,7 +17,9 @@ class Session(object):
     pass
 
 
-def setup(refdir=None):
+def setup(refdir=None, solver_factory=None):
+    """solver_factory(op, vulcan_cfg, chem_funs) -> solver object: replaces `getattr(op, vulcan_cfg.ode_solver)()` (vulcan.py:162-163),
+    i.e. the ONE line INTEGRATION.md changes; everything else below is the reference's own call sequence."""
     if refdir is not None:
         os.chdir(refdir)
         sys.path.insert(0, refdir)
@@ -50,7 +52,7 @@ def setup(refdir=None):
     atm = make_atm.f_mu_dz(var, atm, output)
     make_atm.mol_diff(atm)
     make_atm.BC_flux(atm)
-    solver = getattr(op, vulcan_cfg.ode_solver)()
+    solver = getattr(op, vulcan_cfg.ode_solver)() if solver_factory is None else solver_factory(op, vulcan_cfg, chem_funs)
     if vulcan_cfg.use_photo:
         rate.make_bins_read_cross(var, atm)
         make_atm.read_sflux(var, atm)
