@@ -13,7 +13,7 @@ y = np.repeat(c.y[None], ncol, 0); ym = np.repeat(c.ymix[None], ncol, 0); dt = n
 for _ in range(2): col.ros2_solve(y, ym, dt)
 lib = _abi.load()
 lib.vk_debug_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
-names = ["lhs", "rhs", "factor", "solve(bwd)", "solve(fwd+bwd)"]
+names = ["lhs", "rhs", "factor", "solve(fwd+bwd)"]
 out = []
 for w, n in enumerate(names):
     ms = ctypes.c_float(0)

@@ -68,6 +68,7 @@ class Case(object):
 # every (config, step) fixture pair generated from the unmodified reference (oracle/dump_fixtures.py); BASELINE.json configs
 CASES = [("HD189", 0), ("HD189", 10), ("HD189", 100), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30),
          ("HD209S", 0), ("HD209S", 30)]
+CASES += [p for p in [("HD209S", 150), ("HD209S", 400)] if have(p[0], "step%04d.npz" % p[1])]     # production dt (1.8e4 s, 2.4e5 s)
 # use_vm_mol variants: diffdf_vm / lhs_jac_tot_vm (HD189vm), diffdf_settling_vm / lhs_jac_settling_vm (JupiterVm),
 # the latter with the diffusion-limited escape term (EarthVm)
 VM_CASES = [p for p in [("HD189vm", 0), ("HD189vm", 30), ("JupiterVm", 0), ("JupiterVm", 30), ("EarthVm", 0), ("EarthVm", 30)]

@@ -14,7 +14,7 @@ LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD1
 LOCKSTEP = [p for p in LOCKSTEP if have(p[0], "step%04d.npz" % p[1]) and have(p[0], "step0000.npz")]
 
 
-def lockstep(tag, nstep, abi=None, refine=1):
+def lockstep(tag, nstep, abi=None, refine=0):
     ref = Case(tag, nstep)
     case, var, atm, para, integ, wall = run_config(tag, refine=refine, count_max=nstep - 1, abi=abi)   # Integration.stop: count > count_max
     assert para.count == nstep

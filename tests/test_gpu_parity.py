@@ -93,6 +93,30 @@ def test_blocktri_solve_vs_truth(case):
     assert np.abs(res).max() <= 1e-9 * np.abs(rhs).max()
 
 
+def test_blocktri_solve_conserves_elements(case):
+    """backward stability of the device solve (see tests/test_oracle_vs_reference.py::test_solve_conserves_elements): residual and the
+    element budget of k1 at LAPACK's level on the reference's own systems, production dt included (HD209S steps 150 / 400)."""
+    if "k1" not in case.fx:
+        pytest.skip("no LAPACK stage vectors in this fixture")
+    o = case.oracle
+    D, up, dn = o.lhs(case.atm, case.y, case.k, case.dt)
+    rhs = case.fx["chemdf"] + case.fx["diffdf"]
+    x, st = case.col.blocktri_solve(D, up, dn, rhs, refine=0)
+    assert st[0] == 0
+    xt = o.blocktri_truth(D, up, dn, rhs, 3)
+    compo = case.st["compo"]
+    tot = (case.y[:, :, None] * compo[None]).sum(axis=(0, 1))
+    bud = lambda v: (v[:, :, None] * compo[None]).sum(axis=(0, 1)) / tot
+    res = lambda v: np.abs(rhs - o.blocktri_matvec(D, up, dn, v)).max() / np.abs(rhs).max()
+    e_x, e_ref = np.abs(bud(x[0]) - bud(xt)).max(), np.abs(bud(case.fx["k1"]) - bud(xt)).max()
+    print("%s-%d dt %.2e: residual gpu %.1e LAPACK %.1e | element budget error of k1  gpu %.1e LAPACK %.1e" %
+          (case.tag, case.step, case.dt, res(x[0]), res(case.fx["k1"]), e_x, e_ref))
+    assert res(x[0]) <= max(50 * res(case.fx["k1"]), 1e-12)      # max-norm residual relative to max |rhs|: same scale for both solvers
+    # measured: equal to LAPACK's everywhere except HD209S-400 (dt = 2.4e5 s: 1.2e-4 vs 7.6e-6, the deepest layer's CH4); the
+    # explicit-inverse solve this replaced was at 7.5e-5 ... 0.35 over the same run
+    assert e_x <= max(50 * e_ref, 1e-9)
+
+
 def test_ros2_step(case):
     """one attempted step through vk_ros2_solve vs the reference's Ros2.solver output.
     Small dt: BASELINE's 1e-10 on every n > 1e-30.  Production dt: conditioning-limited, so the comparison is made under

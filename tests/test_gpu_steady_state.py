@@ -49,3 +49,48 @@ def test_hd189_to_steady_state():
     assert rel[m].max() < 5e-3          # measured 4.5e-4; reference self-spread at this level: 7e-3 ... 9e-3
     assert rel[yr > 1e-12].max() < 2e-2  # measured 1.3e-3; reference self-spread: 2e-2
     assert np.median(rel[yr > 1e-20]) < 1e-3   # measured 1.7e-5; reference self-spread: 5e-6 ... 1e-5
+
+
+def test_hd209s_to_steady_state():
+    """BASELINE config 4 (HD 209458b, SNCHO_photo_network_2025: ni = 93, nr = 1192, the largest block size) from the reference's initial
+    state to the reference's own convergence criterion.  Reference (tests/golden/HD209S_full.npz): 1143 steps, 73 rejected,
+    t = 1.08e8 s, 1160 s wall on one core of the build container."""
+    if not have("HD209S", "full.npz"):
+        pytest.skip("fixture missing")
+    case, var, atm, para, integ, wall = run_config("HD209S")
+    ref = np.load("%s/HD209S_full.npz" % GOLD)
+    n_rej = para.delta_count + para.nega_count + para.loss_count
+    ym, yr = var.ymix, ref["ymix"]
+    rel = np.abs(ym - yr) / np.maximum(yr, 1e-300)
+    msg = ["HD209S steady state on the GPU: %d accepted steps (+%d rejected), t = %.4e s, wall %.2f s (%d photolysis updates, %.2f s)" %
+           (para.count, n_rej, var.t, wall, integ.n_photo_updates, integ.t_photo),
+           "reference: %d steps (+%d rejected), t = %.4e s, wall %.0f s  ->  %.0fx faster to steady state" %
+           (int(ref["count"]), int(ref["delta_count"]) + int(ref["nega_count"]) + int(ref["loss_count"]), float(ref["t"]), float(ref["wall_s"]),
+            float(ref["wall_s"]) / wall)]
+    for thr in (1e-20, 1e-12, 1e-8, 1e-4):
+        m = yr > thr
+        msg.append("  ymix > %.0e: max rel diff %.2e, median %.2e" % (thr, rel[m].max(), np.median(rel[m])))
+    # the two runs stop at different model times (each at the first step that meets the criterion while slow species still drift):
+    # compare also at the SAME model time, the reference's final t, by interpolating the stored history (save_step keeps every step)
+    tt = np.array(var.t_time)
+    if tt[0] < float(ref["t"]) < tt[-1]:
+        q = int(np.searchsorted(tt, float(ref["t"])))
+        n0 = case.st["n_0"]
+        gi = list(atm.gas_indx)
+        def mix(y):
+            return y / np.vstack(np.sum(y[:, gi], axis=1)) if cfg_non_gas else y / np.vstack(np.sum(y, axis=1))
+        cfg_non_gas = bool(case.cfg.get("non_gas_sp"))
+        w = (float(ref["t"]) - tt[q - 1]) / (tt[q] - tt[q - 1])
+        ym_t = (1 - w) * mix(var.y_time[q - 1]) + w * mix(var.y_time[q])
+        rel_t = np.abs(ym_t - yr) / np.maximum(yr, 1e-300)
+        msg.append("at the reference's final model time (t = %.4e s, GPU step %d):" % (float(ref["t"]), q))
+        for thr in (1e-20, 1e-12, 1e-8, 1e-4):
+            m = yr > thr
+            msg.append("  ymix > %.0e: max rel diff %.2e, median %.2e" % (thr, rel_t[m].max(), np.median(rel_t[m])))
+    loss = max(abs(v) for v in var.atom_loss.values())
+    msg.append("element conservation: max |atom loss| %.2e (reference's own final state: 5.8e-4)" % loss)
+    print("\n".join(msg))
+    assert para.end_case == 1, "did not converge by the reference's criterion (end_case %d)" % para.end_case
+    assert 0.8 * int(ref["count"]) <= para.count <= 1.2 * int(ref["count"])      # measured 1101 vs 1143
+    assert loss < 5e-3                                                            # measured 1.8e-3
+    assert rel[yr > 1e-4].max() < 0.3 and np.median(rel[yr > 1e-20]) < 2e-2       # measured 0.125 / 3.4e-3 (stop times differ 2x)

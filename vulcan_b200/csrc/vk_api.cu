@@ -48,9 +48,9 @@ int vk_step_device_impl(vk_column *c)
     if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
     if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
-    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f, c->z))) return rc;      // W_j and z = forward-eliminated f
+    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr))) return rc; // block LU factors F_j of the Schur blocks (c->W)
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 1))) return rc;                // k1 (backward sweep)  op.py:2914
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
     for (int it = 0; it < c->opts.refine; it++) {
         if ((rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res))) return rc;
         if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
@@ -287,7 +287,8 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->up, sizeof(double) * np);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dn, sizeof(double) * np);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->D, sizeof(double) * nb);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->W, sizeof(double) * nb);
+    // block LU factors of the Schur blocks, row stride nip + 2 (vk_solve.cu)
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->W, sizeof(double) * (size_t)ncol * nz * c->nip * (c->nip + 2));
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dt, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->delta, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->status, sizeof(int) * ncol);
@@ -694,8 +695,7 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
     for (int r = 0; r < reps && rc == VK_OK; r++) {
         if (which == 0) rc = vk::launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
         else if (which == 1) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);
-        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f, c->z);
-        else if (which == 3) rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 1);
+        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr);
         else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 0);
     }
     VK_CUDA(cudaEventRecord(b, c->stream));

@@ -5,8 +5,13 @@
 //     S_0 = D_0,   S_j = D_j - diag(dn_j) W_{j-1} diag(up_{j-1}),   W_j = S_j^{-1}
 //     z_j = W_j (r_j - dn_j * z_{j-1}),   x_{nz-1} = z_{nz-1},   x_j = z_j - W_j (up_j * x_{j+1})
 // One thread block per column marches over the layers.  W_j is formed by blocked in-register Gauss-Jordan inversion on the
-// FP64 tensor pipe (see factor_kernel).  The factor is stored once (W_j) and reused for the second Ros2 stage and for
-// iterative refinement - the reference factorises twice.
+// FP64 tensor pipe (see factor_kernel) and is used ONLY for the Schur update of the next layer (it never leaves the registers).
+// What is stored for the solves is the block LU factorisation F_j of S_j that the same sweep produces as a by-product (8 x 8
+// diagonal blocks: P_K = A_KK^{-1} on, Lt_iK = A_iK P_K below, V_Kw = P_K A_Kw above the block diagonal): x = fl(S^{-1}) t is not
+// backward stable - on the reference's own HD209S systems at production dt it leaves a residual of 1e-6 |r|, which the factor
+// r*dt turns into a carbon budget error of 1e-2 ... 0.35 PER STEP - whereas the block-LU solve leaves 2e-14 like LAPACK's banded
+// LU (tests/test_oracle_vs_reference.py::test_solve_conserves_elements, tests/test_gpu_parity.py).  The factor is stored once and
+// reused for the second Ros2 stage and for iterative refinement - the reference factorises twice.
 #include <type_traits>
 
 #include "vk_internal.cuh"
@@ -74,7 +79,8 @@ struct FactorArgs {
     const double *D;     // [ncol][nz][NIP][NIP]
     const double *up;    // [ncol][nz][NIP]
     const double *dn;
-    double *W;           // [ncol][nz][NIP][NIP]
+    double *W;           // [ncol][nz][NIP][NIP] explicit inverses (optional: only the fused stage-1 elimination of older callers needs them)
+    double *F;           // [ncol][nz][NIP][NIP+2] block LU factors of S_j for the solve sweeps (row stride NIP+2: conflict-free LDS.128)
     int *status;         // [ncol]
     const double *rhs;   // optional [ncol][nz][ni]: forward elimination fused into the factorisation
     double *z;           // [ncol][nz][NIP]
@@ -316,6 +322,13 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 }
                 const double2 pc = *reinterpret_cast<const double2 *>(pb + g * 8 + 2 * t);
                 A[kt][0] = pc.x; A[kt][1] = pc.y;
+                if (a.F) {      // block LU by-product: P_K on the diagonal tile, Lt_iK = A_iK P_K (= minus the new panel column) below it
+                    double *Ft = a.F + (cbase + j) * (size_t)(NIP * (NIP + 2)) + (size_t)g * (NIP + 2) + c0;
+                    *reinterpret_cast<double2 *>(Ft + (size_t)(8 * kt) * (NIP + 2)) = make_double2(pc.x, pc.y);
+#pragma unroll
+                    for (int i = kt + 1; i < NR; i++)
+                        *reinterpret_cast<double2 *>(Ft + (size_t)(8 * i) * (NIP + 2)) = make_double2(-A[i][0], -A[i][1]);
+                }
                 if constexpr (kt + 1 < NR) to_bfrag(A[kt + 1][0], A[kt + 1][1], g, t, u0, u1);
                 TRACE(kt, 6, A[0][0]);
             } else {
@@ -327,6 +340,9 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 dmma(v0, v1, pa.x, u0, 0.0, 0.0);
                 dmma(v0, v1, pa.y, u1, v0, v1);
                 A[kt][0] = v0; A[kt][1] = v1;
+                if (a.F && w > kt)   // block LU by-product: V_Kw = P_K A_Kw right of the diagonal tile
+                    *reinterpret_cast<double2 *>(a.F + (cbase + j) * (size_t)(NIP * (NIP + 2)) + (size_t)(8 * kt + g) * (NIP + 2) + c0) =
+                        make_double2(v0, v1);
                 if (kt == 3 && w == 4) TRACE(64, 2, v0);
                 double nv0, nv1;
                 to_bfrag(v0, v1, g, t, nv0, nv1);
@@ -406,7 +422,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int r = 8 * i + g;
-            *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c0) = make_double2(A[i][0], A[i][1]);
+            if (a.W) *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c0) = make_double2(A[i][0], A[i][1]);
             if (fuse) {
                 double part = fma(A[i][0], tv0, A[i][1] * tv1);
                 part += __shfl_xor_sync(0xffffffffu, part, 1);
@@ -436,79 +452,150 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward + backward sweeps with the stored W_j: 4 threads per block row, 16-byte loads, shuffle reduction.
-struct SolveArgs {
-    int nz, ni, nip;
-    const double *W, *up, *dn;   // padded layouts
+// lu_solve_kernel: forward + backward sweeps over the layers with the block LU factors F_j (see the header of this file).
+//   forward :  z_j = S_j^{-1} (r_j - dn_j * z_{j-1})        backward :  x_j = z_j - S_j^{-1} (up_j * x_{j+1})
+// One block per column, ONE THREAD PER BLOCK ROW.  F_j (NIP x (NIP+2) doubles) arrives by a 1-D TMA bulk copy into a double-buffered
+// shared-memory slot one layer ahead; the application of S_j^{-1} is a block forward / backward substitution over the NIP/8 panels:
+//   forward   K = 0 ..:   publish y_K ; barrier ; rows below:  y_i -= Lt_iK y_K                       (8 FMAs per row)
+//   backward  K = .. 0:   rows of K:  z_K = P_K y_K - s_K  (y_K exchanged by shuffles) ; publish ; barrier ; rows above:  s_i += V_iK z_K
+// i.e. 2 NIP/8 block barriers per layer and sweep, every row reading 64 contiguous bytes of its own F row per step.
+struct LuSolveArgs {
+    int nz, ni;
+    const double *F, *up, *dn;   // padded layouts
     const double *rhs;           // [ncol][nz][ni]
     double *x;                   // [ncol][nz][ni]
-    double *z;                   // [ncol][nz][nip] scratch
-    int skip_fwd;                // z already holds the forward-eliminated vector (fused into the factorisation)
+    double *z;                   // [ncol][nz][NIP] scratch
 };
 
-template <int NIP>
-__global__ void __launch_bounds__(NIP * 4, (NIP <= 72) ? 2 : 1) solve_kernel(SolveArgs a)
+template <int NIP, int NBUF>
+struct LuCfg {
+    static constexpr int LDF = NIP + 2;
+    static constexpr int NR = NIP / 8;
+    static constexpr int NT = ((NIP + 31) / 32) * 32;
+    static constexpr unsigned FBYTES = (unsigned)(sizeof(double) * NIP * LDF);
+    static constexpr size_t SMEM = (size_t)NBUF * FBYTES + sizeof(double) * 2 * NIP + 32;
+};
+
+template <int NIP, int NBUF>
+__global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveArgs a)
 {
-    constexpr int NCH = NIP / 8;
-    __shared__ __align__(16) double tvec[NIP];
-    __shared__ __align__(16) double zprev[NIP];
-    const int col = blockIdx.x, tid = threadIdx.x;
-    const int row = tid >> 2, part = tid & 3;
+    using C = LuCfg<NIP, NBUF>;
+    constexpr int LDF = C::LDF, NR = C::NR;
+    extern __shared__ __align__(128) double smem[];
+    double *fbuf = smem;                            // NBUF x NIP x LDF
+    double *yv = fbuf + (size_t)NBUF * NIP * LDF;   // NIP  published y_K
+    double *zv = yv + NIP;                          // NIP  published z_K
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(zv + NIP);   // NBUF mbarriers
+    const int col = blockIdx.x, i = threadIdx.x, lane = i & 31, pan = i >> 3;
+    const bool live = i < NIP;
     const int nz = a.nz, ni = a.ni;
-    const double *Wc = a.W + (size_t)col * nz * NIP * NIP;
+    const double *Fc = a.F + (size_t)col * nz * NIP * LDF;
     const double *upc = a.up + (size_t)col * nz * NIP;
     const double *dnc = a.dn + (size_t)col * nz * NIP;
     const double *rc = a.rhs + (size_t)col * nz * ni;
     double *xc = a.x + (size_t)col * nz * ni;
     double *zc = a.z + (size_t)col * nz * NIP;
 
-    double2 w[NCH];
-    auto load_w = [&](int j) {
-        const double *Wr = Wc + (size_t)j * NIP * NIP + (size_t)row * NIP + part * 2;
-#pragma unroll
-        for (int i = 0; i < NCH; i++) w[i] = *reinterpret_cast<const double2 *>(Wr + i * 8);
+    auto fetch = [&](int j, int v) {     // one thread: F_j -> slot v % NBUF
+        void *mb = mbar + (v % NBUF);
+        mbar_expect_tx(mb, C::FBYTES);
+        tma_load_1d(fbuf + (size_t)(v % NBUF) * NIP * LDF, Fc + (size_t)j * NIP * LDF, C::FBYTES, mb);
     };
-    auto matvec = [&]() -> double {
-        double acc0 = 0.0, acc1 = 0.0;
+    // S^{-1} t for my row (t enters as my component of the right-hand side)
+    auto apply = [&](const double *Fb, double t) -> double {
+        const double *Fr = Fb + (size_t)(live ? i : 0) * LDF;
 #pragma unroll
-        for (int i = 0; i < NCH; i++) {
-            double2 tv = *reinterpret_cast<const double2 *>(tvec + i * 8 + part * 2);
-            acc0 = fma(w[i].x, tv.x, acc0);
-            acc1 = fma(w[i].y, tv.y, acc1);
+        for (int K = 0; K < NR; K++) {
+            if (pan == K) yv[i] = t;
+            __syncthreads();
+            if (live && pan > K) {
+                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
+                const double2 *y = reinterpret_cast<const double2 *>(yv + 8 * K);
+                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+                double s0 = f0.x * y0.x, s1 = f0.y * y0.y;
+                s0 = fma(f1.x, y1.x, s0); s1 = fma(f1.y, y1.y, s1);
+                s0 = fma(f2.x, y2.x, s0); s1 = fma(f2.y, y2.y, s1);
+                s0 = fma(f3.x, y3.x, s0); s1 = fma(f3.y, y3.y, s1);
+                t -= s0 + s1;
+            }
         }
-        double acc = acc0 + acc1;
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        return acc;
+        double s = 0.0, z = 0.0;
+#pragma unroll
+        for (int K = NR - 1; K >= 0; K--) {
+            if (live && pan == K) {
+                const unsigned mask = 0xffu << (lane & 24);
+                const int base = lane & 24;
+                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
+                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3];
+                double p0 = f0.x * __shfl_sync(mask, t, base + 0), p1 = f0.y * __shfl_sync(mask, t, base + 1);
+                p0 = fma(f1.x, __shfl_sync(mask, t, base + 2), p0); p1 = fma(f1.y, __shfl_sync(mask, t, base + 3), p1);
+                p0 = fma(f2.x, __shfl_sync(mask, t, base + 4), p0); p1 = fma(f2.y, __shfl_sync(mask, t, base + 5), p1);
+                p0 = fma(f3.x, __shfl_sync(mask, t, base + 6), p0); p1 = fma(f3.y, __shfl_sync(mask, t, base + 7), p1);
+                z = (p0 + p1) - s;
+                zv[i] = z;
+            }
+            __syncthreads();
+            if (live && pan < K) {
+                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
+                const double2 *y = reinterpret_cast<const double2 *>(zv + 8 * K);
+                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+                double s0 = f0.x * y0.x, s1 = f0.y * y0.y;
+                s0 = fma(f1.x, y1.x, s0); s1 = fma(f1.y, y1.y, s1);
+                s0 = fma(f2.x, y2.x, s0); s1 = fma(f2.y, y2.y, s1);
+                s0 = fma(f3.x, y3.x, s0); s1 = fma(f3.y, y3.y, s1);
+                s += s0 + s1;
+            }
+        }
+        return z;
     };
-    // ---- forward: z_j = W_j (r_j - dn_j * z_{j-1})
-    if (tid < NIP) zprev[tid] = a.skip_fwd ? zc[(size_t)(nz - 1) * NIP + tid] : 0.0;
-    if (!a.skip_fwd) load_w(0);
-    for (int j = 0; j < nz && !a.skip_fwd; j++) {
-        __syncthreads();
-        if (tid < NIP) {
-            double r = (tid < ni) ? rc[(size_t)j * ni + tid] : 0.0;
-            tvec[tid] = (j == 0) ? r : r - dnc[(size_t)j * NIP + tid] * zprev[tid];
-        }
-        __syncthreads();
-        double acc = matvec();
-        if (j + 1 < nz) load_w(j + 1);
-        if (part == 0) { zprev[row] = acc; zc[(size_t)j * NIP + row] = acc; }
+
+    if (i == 0) {
+        for (int b = 0; b < NBUF; b++) mbar_init(mbar + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---- backward: x_j = z_j - W_j (up_j * x_{j+1});  zprev now holds x_{j+1}
     __syncthreads();
-    if (tid < ni) xc[(size_t)(nz - 1) * ni + tid] = zprev[tid];
-    if (nz > 1) load_w(nz - 2);
-    for (int j = nz - 2; j >= 0; j--) {
+    if (i == 0) fetch(0, 0);
+    const int nvisit = 2 * nz - 1;
+    auto layer_of = [&](int v) { return v < nz ? v : 2 * nz - 2 - v; };
+    int v = 0;
+    // ---- forward
+    double zprev = 0.0;
+    double rn = (i < ni) ? rc[i] : 0.0, dnn = 0.0;
+    for (int j = 0; j < nz; j++, v++) {
+        double t = rn - dnn * zprev;
+        if (j + 1 < nz) {
+            rn = (i < ni) ? rc[(size_t)(j + 1) * ni + i] : 0.0;
+            dnn = live ? dnc[(size_t)(j + 1) * NIP + i] : 0.0;
+        }
+        __syncthreads();                                    // every row is done with the slot the next fetch overwrites
+        if (NBUF == 2 && i == 0 && v + 1 < nvisit) fetch(layer_of(v + 1), v + 1);
+        mbar_wait(mbar + (v % NBUF), (v / NBUF) & 1);
+        const double z = apply(fbuf + (size_t)(v % NBUF) * NIP * LDF, t);
+        if (live) zc[(size_t)j * NIP + i] = z;
+        zprev = z;
+        if (NBUF == 1) {
+            __syncthreads();
+            if (i == 0 && v + 1 < nvisit) fetch(layer_of(v + 1), v + 1);
+        }
+    }
+    // ---- backward (zprev = z_{nz-1} = x_{nz-1})
+    double xnext = zprev;
+    if (i < ni) xc[(size_t)(nz - 1) * ni + i] = xnext;
+    double upn = 0.0, zj = 0.0;
+    if (nz > 1 && live) { upn = upc[(size_t)(nz - 2) * NIP + i]; zj = zc[(size_t)(nz - 2) * NIP + i]; }
+    for (int j = nz - 2; j >= 0; j--, v++) {
+        const double t = upn * xnext, zcur = zj;
+        if (j > 0 && live) { upn = upc[(size_t)(j - 1) * NIP + i]; zj = zc[(size_t)(j - 1) * NIP + i]; }
         __syncthreads();
-        if (tid < NIP) tvec[tid] = upc[(size_t)j * NIP + tid] * zprev[tid];
-        __syncthreads();
-        double acc = matvec();
-        if (j > 0) load_w(j - 1);
-        if (part == 0) {
-            double xv = zc[(size_t)j * NIP + row] - acc;
-            zprev[row] = xv;
-            if (row < ni) xc[(size_t)j * ni + row] = xv;
+        if (NBUF == 2 && i == 0 && v + 1 < nvisit) fetch(layer_of(v + 1), v + 1);
+        mbar_wait(mbar + (v % NBUF), (v / NBUF) & 1);
+        const double sv = apply(fbuf + (size_t)(v % NBUF) * NIP * LDF, t);
+        const double xv = zcur - sv;
+        if (i < ni) xc[(size_t)j * ni + i] = xv;
+        xnext = xv;
+        if (NBUF == 1) {
+            __syncthreads();
+            if (i == 0 && v + 1 < nvisit) fetch(layer_of(v + 1), v + 1);
         }
     }
 }
@@ -554,7 +641,7 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
                            const double *rhs, double *z)
 {
     using C = FactorCfg<NIP>;
-    FactorArgs a{c->nz, c->ni, D, up, dn, W, status, rhs, z};
+    FactorArgs a{c->nz, c->ni, D, up, dn, nullptr, W, status, rhs, z};     // `W` of the callers = the block LU factors F
     static bool attr_set = false;
     if (!attr_set) {
         VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -577,18 +664,35 @@ int launch_factor(vk_column *c, const double *D, const double *up, const double 
     }
 }
 
-int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z, int skip_fwd)
+template <int NIP, int NBUF>
+static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 {
-    SolveArgs a{c->nz, c->ni, c->nip, W, up, dn, rhs, x, z, skip_fwd};
-    switch (c->nip) {
-        case 48: solve_kernel<48><<<c->ncol, 48 * 4, 0, c->stream>>>(a); break;
-        case 72: solve_kernel<72><<<c->ncol, 72 * 4, 0, c->stream>>>(a); break;
-        case 96: solve_kernel<96><<<c->ncol, 96 * 4, 0, c->stream>>>(a); break;
-        case 120: solve_kernel<120><<<c->ncol, 120 * 4, 0, c->stream>>>(a); break;
-        default: set_error("no solve kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
+    using C = LuCfg<NIP, NBUF>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VK_CUDA(cudaFuncSetAttribute(lu_solve_kernel<NIP, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        attr_set = true;
     }
+    lu_solve_kernel<NIP, NBUF><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
+}
+
+// x = A^{-1} rhs with the stored block LU factors (`W` = F, [ncol][nz][nip][nip+2]); z is scratch
+int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z, int skip_fwd)
+{
+    if (skip_fwd) { set_error("fused forward elimination is not available with the block-LU solve"); return VK_ERR_INVALID; }
+    LuSolveArgs a{c->nz, c->ni, W, up, dn, rhs, x, z};
+    static int nbuf = -1;     // slots of the F prefetch per block: 2 = prefetch inside the block, 1 = more blocks per SM instead
+    // measured (592 HD189 columns): 1 slot (5 blocks per SM, the other blocks hide the copy) 1.28 ms = 90 % of the HBM floor, 2 slots 1.87 ms
+    if (nbuf < 0) { const char *e = getenv("VK_LU_NBUF"); nbuf = e ? atoi(e) : 1; }
+    switch (c->nip) {
+        case 48: return nbuf == 1 ? launch_lu_solve_t<48, 1>(c, a) : launch_lu_solve_t<48, 2>(c, a);
+        case 72: return nbuf == 1 ? launch_lu_solve_t<72, 1>(c, a) : launch_lu_solve_t<72, 2>(c, a);
+        case 96: return nbuf == 1 ? launch_lu_solve_t<96, 1>(c, a) : launch_lu_solve_t<96, 2>(c, a);
+        case 120: return launch_lu_solve_t<120, 1>(c, a);      // two slots of 117 KB do not fit
+        default: set_error("no solve kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
+    }
 }
 
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x, double *res)
