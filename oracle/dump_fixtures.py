@@ -324,13 +324,14 @@ def finish_conden(s, tag, store, traj):
     print("wrote", path, "calls=%d fix_species_start=%s" % (len(store["calls"]), para.fix_species_start), flush=True)
 
 
-def run(config, refdir, steps, full, max_steps=None, conden=None, after_switch=None):
+def run(config, refdir, steps, full, max_steps=None, conden=None, after_switch=None, tag=None):
     sys.path.insert(0, HERE)
     import ref_session
-    assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0 (SURVEY.md §8c)"
+    # fixtures are pinned to hash seed 0; `--tag` runs measure the reference's own seed-to-seed spread under another name
+    assert os.environ.get("PYTHONHASHSEED") == "0" or tag is not None, "run with PYTHONHASHSEED=0 (SURVEY.md §8c)"
     s = ref_session.setup(refdir)
     os.makedirs(GOLD, exist_ok=True)
-    tag = config
+    tag = tag or config
     var, atm, para, integ, solver, cfg = s.var, s.atm, s.para, s.integ, s.solver, s.cfg
     sd = static_dict(s)
     s.k_static = sd["k"]
@@ -396,7 +397,8 @@ if __name__ == "__main__":
     ap.add_argument("--max-steps", type=int, default=None)
     ap.add_argument("--conden", default=None, help="comma list of counts at which the condensation operators are captured (L6)")
     ap.add_argument("--after-switch", type=int, default=None, help="capture an L0-L2 step fixture this many steps after fix_species starts")
+    ap.add_argument("--tag", default=None, help="output name instead of the config name (self-spread runs with another PYTHONHASHSEED)")
     a = ap.parse_args()
     steps = [int(x) for x in a.steps.split(",") if x != ""]
     conden = None if a.conden is None else [int(x) for x in a.conden.split(",") if x != ""]
-    run(a.config, a.refdir or "/tmp/vulcan_ref_%s" % a.config, steps, a.full, a.max_steps, conden, a.after_switch)
+    run(a.config, a.refdir or "/tmp/vulcan_ref_%s" % a.config, steps, a.full, a.max_steps, conden, a.after_switch, a.tag)

@@ -683,9 +683,12 @@ int launch_solve(vk_column *c, const double *W, const double *up, const double *
 {
     if (skip_fwd) { set_error("fused forward elimination is not available with the block-LU solve"); return VK_ERR_INVALID; }
     LuSolveArgs a{c->nz, c->ni, W, up, dn, rhs, x, z};
-    static int nbuf = -1;     // slots of the F prefetch per block: 2 = prefetch inside the block, 1 = more blocks per SM instead
-    // measured (592 HD189 columns): 1 slot (5 blocks per SM, the other blocks hide the copy) 1.28 ms = 90 % of the HBM floor, 2 slots 1.87 ms
-    if (nbuf < 0) { const char *e = getenv("VK_LU_NBUF"); nbuf = e ? atoi(e) : 1; }
+    // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
+    // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per
+    // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
+    static int env_nbuf = -1;
+    if (env_nbuf < 0) { const char *e = getenv("VK_LU_NBUF"); env_nbuf = e ? atoi(e) : 0; }
+    const int nbuf = env_nbuf ? env_nbuf : (c->ncol >= 2 * 148 ? 1 : 2);
     switch (c->nip) {
         case 48: return nbuf == 1 ? launch_lu_solve_t<48, 1>(c, a) : launch_lu_solve_t<48, 2>(c, a);
         case 72: return nbuf == 1 ? launch_lu_solve_t<72, 1>(c, a) : launch_lu_solve_t<72, 2>(c, a);
