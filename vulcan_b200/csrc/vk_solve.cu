@@ -501,23 +501,29 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
         mbar_expect_tx(mb, C::FBYTES);
         tma_load_1d(fbuf + (size_t)(v % NBUF) * NIP * LDF, Fc + (size_t)j * NIP * LDF, C::FBYTES, mb);
     };
-    // S^{-1} t for my row (t enters as my component of the right-hand side)
+    // S^{-1} t for my row (t enters as my component of the right-hand side).  The 64 bytes of my F row that the NEXT step reads are
+    // loaded before that step's barrier (the factors are read-only here), products in four short chains: the in-layer chain of
+    // 2 NIP/8 dependent steps is what bounds a single column.
     auto apply = [&](const double *Fb, double t) -> double {
         const double *Fr = Fb + (size_t)(live ? i : 0) * LDF;
+        auto loadf = [&](int K, double2 (&f)[4]) {
+            const double2 *p = reinterpret_cast<const double2 *>(Fr + 8 * K);
+            f[0] = p[0]; f[1] = p[1]; f[2] = p[2]; f[3] = p[3];
+        };
+        auto dot8 = [](const double2 (&f)[4], const double2 *y) -> double {
+            const double2 y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
+            const double a0 = fma(f[0].y, y0.y, f[0].x * y0.x), a1 = fma(f[1].y, y1.y, f[1].x * y1.x);
+            const double a2 = fma(f[2].y, y2.y, f[2].x * y2.x), a3 = fma(f[3].y, y3.y, f[3].x * y3.x);
+            return (a0 + a1) + (a2 + a3);
+        };
+        double2 f[4];
+        loadf(0, f);
 #pragma unroll
         for (int K = 0; K < NR; K++) {
             if (pan == K) yv[i] = t;
             __syncthreads();
-            if (live && pan > K) {
-                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
-                const double2 *y = reinterpret_cast<const double2 *>(yv + 8 * K);
-                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
-                double s0 = f0.x * y0.x, s1 = f0.y * y0.y;
-                s0 = fma(f1.x, y1.x, s0); s1 = fma(f1.y, y1.y, s1);
-                s0 = fma(f2.x, y2.x, s0); s1 = fma(f2.y, y2.y, s1);
-                s0 = fma(f3.x, y3.x, s0); s1 = fma(f3.y, y3.y, s1);
-                t -= s0 + s1;
-            }
+            if (live && pan > K) t -= dot8(f, reinterpret_cast<const double2 *>(yv + 8 * K));
+            loadf(K + 1 < NR ? K + 1 : NR - 1, f);          // next forward step, or the first backward step (panel NR-1)
         }
         double s = 0.0, z = 0.0;
 #pragma unroll
@@ -525,26 +531,15 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
             if (live && pan == K) {
                 const unsigned mask = 0xffu << (lane & 24);
                 const int base = lane & 24;
-                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
-                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3];
-                double p0 = f0.x * __shfl_sync(mask, t, base + 0), p1 = f0.y * __shfl_sync(mask, t, base + 1);
-                p0 = fma(f1.x, __shfl_sync(mask, t, base + 2), p0); p1 = fma(f1.y, __shfl_sync(mask, t, base + 3), p1);
-                p0 = fma(f2.x, __shfl_sync(mask, t, base + 4), p0); p1 = fma(f2.y, __shfl_sync(mask, t, base + 5), p1);
-                p0 = fma(f3.x, __shfl_sync(mask, t, base + 6), p0); p1 = fma(f3.y, __shfl_sync(mask, t, base + 7), p1);
-                z = (p0 + p1) - s;
+                double2 y[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) y[c] = make_double2(__shfl_sync(mask, t, base + 2 * c), __shfl_sync(mask, t, base + 2 * c + 1));
+                z = dot8(f, y) - s;
                 zv[i] = z;
             }
             __syncthreads();
-            if (live && pan < K) {
-                const double2 *f = reinterpret_cast<const double2 *>(Fr + 8 * K);
-                const double2 *y = reinterpret_cast<const double2 *>(zv + 8 * K);
-                const double2 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3], y0 = y[0], y1 = y[1], y2 = y[2], y3 = y[3];
-                double s0 = f0.x * y0.x, s1 = f0.y * y0.y;
-                s0 = fma(f1.x, y1.x, s0); s1 = fma(f1.y, y1.y, s1);
-                s0 = fma(f2.x, y2.x, s0); s1 = fma(f2.y, y2.y, s1);
-                s0 = fma(f3.x, y3.x, s0); s1 = fma(f3.y, y3.y, s1);
-                s += s0 + s1;
-            }
+            if (live && pan < K) s += dot8(f, reinterpret_cast<const double2 *>(zv + 8 * K));
+            if (K > 0) loadf(K - 1, f);
         }
         return z;
     };
@@ -688,7 +683,7 @@ int launch_solve(vk_column *c, const double *W, const double *up, const double *
     // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
     static int env_nbuf = -1;
     if (env_nbuf < 0) { const char *e = getenv("VK_LU_NBUF"); env_nbuf = e ? atoi(e) : 0; }
-    const int nbuf = env_nbuf ? env_nbuf : (c->ncol >= 2 * 148 ? 1 : 2);
+    const int nbuf = env_nbuf ? env_nbuf : (c->ncol > 148 ? 1 : 2);       // (column groups of the pipelined host path share the SMs: 1 slot there too)
     switch (c->nip) {
         case 48: return nbuf == 1 ? launch_lu_solve_t<48, 1>(c, a) : launch_lu_solve_t<48, 2>(c, a);
         case 72: return nbuf == 1 ? launch_lu_solve_t<72, 1>(c, a) : launch_lu_solve_t<72, 2>(c, a);
