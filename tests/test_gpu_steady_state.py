@@ -87,10 +87,28 @@ def test_hd209s_to_steady_state():
         for thr in (1e-20, 1e-12, 1e-8, 1e-4):
             m = yr > thr
             msg.append("  ymix > %.0e: max rel diff %.2e, median %.2e" % (thr, rel_t[m].max(), np.median(rel_t[m])))
+    sp = list(case.net.species)
+    big = np.argwhere((yr > 1e-4) & (rel > 0.02))
+    if len(big):
+        worst = {}
+        for jj, ii in big:
+            worst[sp[ii]] = max(worst.get(sp[ii], (0, 0)), (float(rel[jj, ii]), int(jj)))
+        msg.append("species above 1e-4 that differ by more than 2 %% (max rel diff, layer): %s" %
+                   ", ".join("%s %.2g @%d" % (k, v[0], v[1]) for k, v in sorted(worst.items(), key=lambda kv: -kv[1][0])[:8]))
     loss = max(abs(v) for v in var.atom_loss.values())
     msg.append("element conservation: max |atom loss| %.2e (reference's own final state: 5.8e-4)" % loss)
     print("\n".join(msg))
     assert para.end_case == 1, "did not converge by the reference's criterion (end_case %d)" % para.end_case
     assert 0.8 * int(ref["count"]) <= para.count <= 1.2 * int(ref["count"])      # measured 1101 vs 1143
     assert loss < 5e-3                                                            # measured 1.8e-3
-    assert rel[yr > 1e-4].max() < 0.3 and np.median(rel[yr > 1e-20]) < 2e-2       # measured 0.125 / 3.4e-3 (stop times differ 2x)
+    # The state the reference's own algorithm settles on depends on which of two step-size plateaus the controller ends on (delta
+    # = 0.162 at dt = 2.43e5 s AND at dt = 5.2e4 s; both reference seeds hop from the first to the second after a rejection burst):
+    # the remaining tendency |f|/y of the upper layers scales with dt (scripts/steady_residual.py).  On the reference's plateau the GPU
+    # run agrees to 5e-3 (measured with refine=1: 1141 steps, last dt 5.212e4 vs 5.211e4); this run (refine=0) stays on the first one.
+    same_plateau = abs(var.dt / float(ref["traj"][-1, 3]) - 1.0) < 0.2
+    msg2 = "last dt %.3e (reference %.3e): %s plateau" % (var.dt, float(ref["traj"][-1, 3]), "same" if same_plateau else "other")
+    print(msg2)
+    if same_plateau:
+        assert rel[yr > 1e-4].max() < 2e-2
+    else:
+        assert rel[yr > 1e-4].max() < 0.3 and np.median(rel[yr > 1e-20]) < 2e-2   # measured 0.125 / 3.4e-3
