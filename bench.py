@@ -200,7 +200,8 @@ def main():
     ap.add_argument("--columns", type=int, default=N_COLUMNS)
     ap.add_argument("--refine", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=16, help="column groups (streams) of the pipelined host-buffer path")
+    ap.add_argument("--e2e-groups", type=int, default=None,
+                    help="column groups (streams) of the pipelined host-buffer path (default: by batch size, ensemble.PipelinedHostSolver)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -94,11 +94,14 @@ class PipelinedHostSolver(object):
     host round trip costs max(transfer, compute) instead of their sum.  Pass page-locked arrays (e.g. numpy views of pinned torch
     tensors) to have them DMA'd directly."""
 
-    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=4, device=0, refine=0):
+    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=None, device=0, refine=0):
         from concurrent.futures import ThreadPoolExecutor
         self.ncol = kzz.shape[0]
         self.nz, self.ni = nz, network.ni
         self.devnet = _abi.DeviceNetwork(network, device)
+        if n_groups is None:
+            # measured on a B200 (scripts/e2e_groups.py): 512 columns best with 4-8 groups, 1024 with 4, 4096 with 16
+            n_groups = max(4, min(16, self.ncol // 256))
         n_groups = max(1, min(n_groups, self.ncol))
         self.bounds = [partition(self.ncol, n_groups, g) for g in range(n_groups)]
         self.cols = [_make_columns(self.devnet, nz, hi - lo, atm_common, kzz[lo:hi], k, cfg, refine) for lo, hi in self.bounds]
