@@ -48,7 +48,7 @@ int vk_step_device_impl(vk_column *c)
     if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
     if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
-    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr))) return rc; // block LU factors F_j of the Schur blocks (c->W)
+    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc; // block LU factors F_j of the Schur blocks (c->W)
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
     if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
     for (int it = 0; it < c->opts.refine; it++) {
@@ -636,7 +636,7 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) rc = cuda_fail(e, "vk_blocktri_solve staging");
-    if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr);
+    if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
     if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
     for (int it = 0; rc == VK_OK && it < refine; it++) {
         rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res);
@@ -695,8 +695,8 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
     for (int r = 0; r < reps && rc == VK_OK; r++) {
         if (which == 0) rc = vk::launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
         else if (which == 1) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);
-        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status, nullptr, nullptr);
-        else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, 0);
+        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+        else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
     }
     VK_CUDA(cudaEventRecord(b, c->stream));
     VK_CUDA(cudaStreamSynchronize(c->stream));

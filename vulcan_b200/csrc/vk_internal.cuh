@@ -114,7 +114,7 @@ struct vk_column {
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
     double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx;  // work vectors [ncol][nz][ni]
-    double *D, *W;                            // [ncol][nz][nip][nip]  lhs diagonal blocks / inverse Schur blocks
+    double *D, *W;                            // D [ncol][nz][nip][nip] lhs diagonal blocks; W [ncol][nz][nip][nip+2] block LU factors of the Schur blocks
     double *up, *dn;                          // [ncol][nz][nip]
     double *dt, *delta;                       // [ncol]
     int *status;                              // [ncol]
@@ -137,10 +137,8 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dens
                double *dn_out);
 int launch_atm_pre(vk_column *c, int ncol_atm);
 // kernels (vk_solve.cu)
-int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status, const double *rhs,
-                  double *z);
-int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z,
-                 int skip_fwd = 0);
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status);
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z);
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
                     double *res);
 // kernels (vk_step.cu)

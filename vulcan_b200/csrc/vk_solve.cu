@@ -69,8 +69,8 @@ struct FactorCfg {
     static constexpr int HELPER = SPREAD ? 3 : NW;
     static constexpr int NT = NWARPS * 32;
     static constexpr int NSYNC = (NW + 1) * 32;  // threads on the panel barrier: column warps + the inverse warp
-    // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[3][64] + hbuf[2][2][64] + tvec[NIP] + zpart[NW][NIP] + mbarrier
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 192 + 256 + 128 + NIP + (size_t)NW * NIP + 2);
+    // doubles: dbuf[NIP*NIP] + updn[2*NIP] + mraw[2][NIP][8] + pbuf[3][64] + hbuf[2][2][64] + hraw[2][64] + mbarrier
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)NIP * NIP + 2 * NIP + 16 * NIP + 192 + 256 + 128 + 2);
     static constexpr unsigned TX_BYTES = (unsigned)(sizeof(double) * ((size_t)NIP * NIP + 2 * NIP));
 };
 
@@ -79,11 +79,8 @@ struct FactorArgs {
     const double *D;     // [ncol][nz][NIP][NIP]
     const double *up;    // [ncol][nz][NIP]
     const double *dn;
-    double *W;           // [ncol][nz][NIP][NIP] explicit inverses (optional: only the fused stage-1 elimination of older callers needs them)
     double *F;           // [ncol][nz][NIP][NIP+2] block LU factors of S_j for the solve sweeps (row stride NIP+2: conflict-free LDS.128)
     int *status;         // [ncol]
-    const double *rhs;   // optional [ncol][nz][ni]: forward elimination fused into the factorisation
-    double *z;           // [ncol][nz][NIP]
 };
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor pipe: lane 4g+t supplies A[g][t], B[t][g], C[g][2t..2t+1]
@@ -183,9 +180,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     double *pbuf = mraw + 16 * NIP;      // 3 x 64        P = A_KK^{-1} (the inverse warp runs up to two panels ahead)
     double *hbuf = pbuf + 192;           // 2 x 2 x 64    tiles handed to the inverse warp: [parity][0] = A_{K-1,K}, [parity][1] = A_KK
     double *hraw = hbuf + 256;           // 2 x 64        [parity of m] = A_mK, K = panel m-1 (from warp m-1)
-    double *tvec = hraw + 128;           // NIP           r_j - dn_j * z_{j-1}
-    double *zpart = tvec + NIP;          // NW x NIP      per-warp partial sums of W_j tvec
-    void *mbar = zpart + NW * NIP;       // mbarrier of the TMA prefetch
+    void *mbar = hraw + 128;             // mbarrier of the TMA prefetch
 
     const int col = blockIdx.x;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -193,7 +188,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     const int tid = w * 32 + lane;                         // thread index among the column warps
     const int ni = a.ni, nz = a.nz;
     const size_t cbase = (size_t)col * nz;
-    const bool fuse = a.rhs != nullptr;
     int bad = 0;
 
     auto prefetch = [&](int j) {         // one thread: D_j, up_{j-1}, dn_j -> shared memory
@@ -285,8 +279,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     };
     // ---- layer 0: S_0 = D_0
     {
-        double r0 = 0.0;
-        if (fuse && tid < ni) r0 = a.rhs[cbase * ni + tid];
         mbar_wait(mbar, 0);
 #pragma unroll
         for (int i = 0; i < NR; i++) {
@@ -294,7 +286,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             A[i][0] = d.x;
             A[i][1] = d.y;
         }
-        if (fuse && tid < NIP) tvec[tid] = r0;
         publish_first();
         if (w == 0) publish_raw(0);
     }
@@ -404,16 +395,10 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
             return;
         }
-        // ---- W_j = A: written out, forward elimination of stage 1 fused (z_j = W_j (r_j - dn_j z_{j-1})), and - tile by tile, behind
-        // the store - the Schur update of the NEXT layer, S_{j+1} = D_{j+1} - diag(dn_{j+1}) W_j diag(up_j) (D, up, dn already in shared
-        // memory by TMA).  Warps 0 and 1 hand their first two new tiles to the inverse warp as soon as they exist, so the P_0 chain of
-        // layer j+1 runs behind the rest of this write-out instead of in front of idle column warps.
+        // ---- A now holds W_j = S_j^{-1} (it stays in the registers; the block LU factors of S_j went out tile by tile above): Schur
+        // update of the NEXT layer, S_{j+1} = D_{j+1} - diag(dn_{j+1}) W_j diag(up_j) (D, up, dn already in shared memory by TMA).  Warps 0
+        // and 1 hand their first two new tiles to the inverse warp as soon as they exist, so the P_0 chain of layer j+1 starts at once.
         const bool more = j + 1 < nz;
-        double rnext = 0.0;
-        if (fuse && more && tid < ni) rnext = a.rhs[(cbase + j + 1) * ni + tid];
-        double *Wj = a.W + (cbase + j) * NIP * NIP;
-        double tv0 = 0.0, tv1 = 0.0;
-        if (fuse) { tv0 = tvec[c0]; tv1 = tvec[c0 + 1]; }
         double su0 = 0.0, su1 = 0.0;
         if (more) {
             mbar_wait(mbar, (j + 1) & 1);
@@ -422,13 +407,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int r = 8 * i + g;
-            if (a.W) *reinterpret_cast<double2 *>(Wj + (size_t)r * NIP + c0) = make_double2(A[i][0], A[i][1]);
-            if (fuse) {
-                double part = fma(A[i][0], tv0, A[i][1] * tv1);
-                part += __shfl_xor_sync(0xffffffffu, part, 1);
-                part += __shfl_xor_sync(0xffffffffu, part, 2);
-                if (t == 0) zpart[w * NIP + r] = part;
-            }
             if (more) {
                 const double2 d = *reinterpret_cast<const double2 *>(dbuf + r * NIP + c0);
                 const double l = updn[NIP + r];
@@ -439,15 +417,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         }
         if (more && w == 0) publish_raw(0);
         bar_sync<VK_BAR_COLS, NW * 32>();
-        if (fuse && tid < NIP) {   // z_j = W_j (r_j - dn_j * z_{j-1}); right-hand side of the next layer's elimination
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NW; q++) acc += zpart[q * NIP + tid];
-            a.z[(cbase + j) * NIP + tid] = acc;
-            if (more) tvec[tid] = rnext - updn[NIP + tid] * acc;
-        }
         if (w == 0) TRACE(100, 4, A[0][0]);
-        // (the panel barriers of the next layer order the zpart / tvec reuse)
     }
 }
 
@@ -632,11 +602,10 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int NIP, int MINB>
-static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status,
-                           const double *rhs, double *z)
+static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
 {
     using C = FactorCfg<NIP>;
-    FactorArgs a{c->nz, c->ni, D, up, dn, nullptr, W, status, rhs, z};     // `W` of the callers = the block LU factors F
+    FactorArgs a{c->nz, c->ni, D, up, dn, F, status};
     static bool attr_set = false;
     if (!attr_set) {
         VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
@@ -647,14 +616,14 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
     return VK_OK;
 }
 
-int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *W, int *status, const double *rhs,
-                  double *z)
+// F out: block LU factors of the Schur blocks, [ncol][nz][nip][nip+2]
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
 {
     switch (c->nip) {
-        case 48: return launch_factor_t<48, 2>(c, D, up, dn, W, status, rhs, z);
-        case 72: return launch_factor_t<72, 2>(c, D, up, dn, W, status, rhs, z);
-        case 96: return launch_factor_t<96, 1>(c, D, up, dn, W, status, rhs, z);
-        case 120: return launch_factor_t<120, 1>(c, D, up, dn, W, status, rhs, z);
+        case 48: return launch_factor_t<48, 2>(c, D, up, dn, F, status);
+        case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status);
+        case 96: return launch_factor_t<96, 1>(c, D, up, dn, F, status);
+        case 120: return launch_factor_t<120, 1>(c, D, up, dn, F, status);
         default: set_error("no factor kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
     }
 }
@@ -673,11 +642,10 @@ static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
     return VK_OK;
 }
 
-// x = A^{-1} rhs with the stored block LU factors (`W` = F, [ncol][nz][nip][nip+2]); z is scratch
-int launch_solve(vk_column *c, const double *W, const double *up, const double *dn, const double *rhs, double *x, double *z, int skip_fwd)
+// x = A^{-1} rhs with the stored block LU factors F ([ncol][nz][nip][nip+2]); z is scratch
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z)
 {
-    if (skip_fwd) { set_error("fused forward elimination is not available with the block-LU solve"); return VK_ERR_INVALID; }
-    LuSolveArgs a{c->nz, c->ni, W, up, dn, rhs, x, z};
+    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z};
     // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
     // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per
     // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
