@@ -10,7 +10,7 @@ import pytest
 
 from helpers import GOLD, load_network
 
-TAGS = ["HD189", "Jupiter", "Earth", "HD209S"]
+TAGS = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion"]      # the last one: ion test network (ionisation rows are zero at set-up like photolysis rows)
 LOW_T = {"Jupiter": True}            # cfg_examples/vulcan_cfg_Jupiter.py:7
 
 
