@@ -51,3 +51,29 @@ def check_ion_photolysis(abi=None):
         for q in range(len(st["branch_sp"])):       # the photodissociation rows next to them are unaffected
             kref = px["kphoto%d" % it][q]
             assert np.allclose(o["k"][int(st["branch_rate_index"][q])], kref, rtol=1e-9, atol=1e-12 * np.abs(kref).max() + 1e-300)
+
+
+def long_trajectory(tag, nstep, abi=None):
+    """the host protocol over `nstep` steps next to the reference's recorded trajectory (tests/golden/<cfg>_full.npz, column 1 = model
+    time before each step): returns the largest relative deviation of the model time and the two rejection counts."""
+    import os
+    from helpers import GOLD
+    from vulcan_b200 import ros2 as ros2_mod
+    ref = np.load(os.path.join(GOLD, tag + "_full.npz"))["traj"]
+    orig = ros2_mod.Ros2.one_step
+    worst = dict(t=0.0, where=0)
+
+    def traced(self, var, atm, para):
+        c = para.count
+        if c < len(ref) and ref[c, 1] > 0:
+            d = abs(var.t - ref[c, 1]) / ref[c, 1]
+            if d > worst["t"]:
+                worst["t"], worst["where"] = d, c
+        return orig(self, var, atm, para)
+    ros2_mod.Ros2.one_step = traced
+    try:
+        case, var, atm, para, integ, wall = run_config(tag, refine=0, count_max=nstep - 1, abi=abi, max_wall_s=3000)
+    finally:
+        ros2_mod.Ros2.one_step = orig
+    return dict(dev=worst["t"], where=worst["where"], count=para.count, rejected=para.delta_count + para.nega_count + para.loss_count,
+                ref_rejected=int(ref[:nstep, 5].sum()), wall=wall)

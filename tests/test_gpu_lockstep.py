@@ -5,7 +5,7 @@ reference's initial state, must arrive at the state the UNMODIFIED reference had
 import pytest
 
 from helpers import have
-from lockstep import LOCKSTEP, check_ion_photolysis, lockstep
+from lockstep import LOCKSTEP, check_ion_photolysis, lockstep, long_trajectory
 
 pytestmark = pytest.mark.gpu
 
@@ -23,3 +23,18 @@ def test_first_steps_reproduce_the_reference(tag, nstep):
 def test_compute_Jion_on_the_gpu():
     """photo-ionisation rates (op.py:2789-2820): the ion branches ride in the device branch table of jrate_kernel"""
     check_ion_photolysis()
+
+
+@pytest.mark.parametrize("tag,nstep,tol", [("Jupiter", 1200, 1e-5), ("Earth", 1200, 1e-2)])
+def test_long_trajectory_follows_the_reference(tag, nstep, tol):
+    """BASELINE configs 2 and 3 at production dt: 1200 steps of the whole protocol (rejections, condensation / relaxation operators,
+    photolysis cadence, update_mu_dz) next to the reference's recorded trajectory.  CPU twin with the oracle-backed ABI
+    (tests/trace_host.py): Jupiter 4.3e-7 with the same 105 rejections, Earth 1.3e-3 with the same 161 rejections."""
+    if not have(tag, "full.npz"):
+        pytest.skip("fixture missing")
+    r = long_trajectory(tag, nstep)
+    print("%s: %d steps on the GPU in %.1f s: largest relative deviation of the model time from the reference's trajectory %.2e (step %d); "
+          "rejected attempts %d (reference %d)" % (tag, r["count"], r["wall"], r["dev"], r["where"], r["rejected"], r["ref_rejected"]))
+    assert r["count"] == nstep
+    assert r["dev"] < tol
+    assert abs(r["rejected"] - r["ref_rejected"]) <= max(3, r["ref_rejected"] // 20)

@@ -4,7 +4,7 @@ first N steps of every BASELINE single-column config.  The GPU twin of this test
 import pytest
 
 from helpers import have
-from lockstep import LOCKSTEP, check_ion_photolysis, lockstep
+from lockstep import LOCKSTEP, check_ion_photolysis, lockstep, long_trajectory
 from oracle_columns import oracle_backed_abi
 
 
@@ -57,3 +57,11 @@ def test_production_dt_steps_conserve_elements():
     # measured 1.2e-4 (dt grows 1.8e4 -> 1.8e5 s; one LAPACK solve at these dt is itself only good to 6e-7 ... 8e-6 of the column total,
     # test_solve_conserves_elements); the explicit-inverse solve lost >= 1e-3 per step here
     assert drift < 5e-4
+
+
+@pytest.mark.skipif(not have("Jupiter", "full.npz"), reason="fixture missing")
+def test_jupiter_first_250_steps_follow_the_reference():
+    """CPU twin (shortened) of tests/test_gpu_lockstep.py::test_long_trajectory_follows_the_reference"""
+    r = long_trajectory("Jupiter", 250, abi=oracle_backed_abi())
+    print("Jupiter: %d steps, largest relative deviation of the model time %.2e, rejected %d (reference %d)" % (r["count"], r["dev"], r["rejected"], r["ref_rejected"]))
+    assert r["count"] == 250 and r["dev"] < 1e-6 and r["rejected"] == r["ref_rejected"]
