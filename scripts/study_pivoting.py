@@ -43,6 +43,25 @@ def inv_diag_pivots(A, ppiv):
     return out
 
 
+def gj_blocked_inverse(S, NB, ppiv):
+    """in-place blocked Gauss-Jordan inversion as factor_kernel runs it: panel K, P = A_KK^-1 (diagonal pivots),
+    V = P A_Kw, A_iw -= A_iK V (all rows i != K), A_iK <- -A_iK P, A_KK <- P."""
+    A = S.copy()
+    n = A.shape[0]
+    for a0 in range(0, n, NB):
+        b0 = min(a0 + NB, n)
+        K = slice(a0, b0)
+        rest = np.r_[0:a0, b0:n]
+        P = inv_diag_pivots(A[K, K], ppiv)
+        V = P @ A[K][:, rest]
+        AiK = A[rest][:, K].copy()
+        A[np.ix_(rest, rest)] -= AiK @ V
+        A[np.ix_(rest, np.arange(a0, b0))] = -AiK @ P
+        A[np.ix_(np.arange(a0, b0), rest)] = V
+        A[K, K] = P
+    return A
+
+
 def block_lu(S, NB, ppiv):
     A = S.copy()
     n = A.shape[0]
@@ -70,7 +89,7 @@ def block_lu_apply(F, NB, t):
 
 
 class Solver(object):
-    def __init__(self, D, up, dn, NB=8, ppiv=False, perm=None, lapack_blocks=False):
+    def __init__(self, D, up, dn, NB=8, ppiv=False, perm=None, lapack_blocks=False, winv="lapack"):
         nz, n, _ = D.shape
         self.nz, self.n, self.NB = nz, n, NB
         self.perm = np.arange(n) if perm is None else np.asarray(perm)
@@ -82,7 +101,9 @@ class Solver(object):
         for j in range(nz):
             S = self.D[j].copy() if j == 0 else self.D[j] - (self.dn[j][:, None] * Sinv) * self.up[j - 1][None, :]
             if j + 1 < nz:
-                Sinv = np.linalg.inv(S)
+                # the explicit inverse that only the Schur update reads: LAPACK (what the oracle's pivoted Gauss-Jordan amounts to),
+                # or the device's blocked Gauss-Jordan with diagonal pivots and NO exchange across panels ("gj-diag")
+                Sinv = np.linalg.inv(S) if winv == "lapack" else gj_blocked_inverse(S, NB, ppiv)
             if lapack_blocks:
                 import scipy.linalg as sl
                 self.F.append(sl.lu_factor(S))
@@ -142,11 +163,11 @@ def study(tag, step):
     loss = np.median(np.abs(np.einsum("jss->js", D)) - 1.0 / ((1 + 1 / 2 ** 0.5) * c.dt), axis=0)
     orders = {"ref": None, "diag-desc": np.argsort(-dmed, kind="stable"), "diag-asc": np.argsort(dmed, kind="stable"),
               "loss-desc": np.argsort(-loss, kind="stable")}
-    variants = [("base NB=8", dict()), ("NB=8 ppiv in panel", dict(ppiv=True)), ("NB=16", dict(NB=16)), ("NB=16 ppiv", dict(NB=16, ppiv=True)),
+    variants = [("base NB=8", dict()), ("NB=8, W by device GJ", dict(winv="gj")), ("NB=8 ppiv, W by device GJ+ppiv", dict(winv="gj", ppiv=True)), ("NB=8 ppiv in panel", dict(ppiv=True)), ("NB=16", dict(NB=16)), ("NB=16 ppiv", dict(NB=16, ppiv=True)),
                 ("LAPACK LU per block (full ppiv)", dict(lapack_blocks=True))]
     for oname, perm in orders.items():
         for vname, kw in variants:
-            if oname != "ref" and vname not in ("base NB=8", "NB=8 ppiv in panel"):
+            if oname != "ref" and vname not in ("base NB=8", "NB=8 ppiv in panel", "NB=8, W by device GJ"):
                 continue
             s = Solver(D, up, dn, perm=perm, **kw)
             x0 = s.solve(rhs)
