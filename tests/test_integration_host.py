@@ -97,3 +97,32 @@ def test_fix_species_switch_vs_reference():
     for q, s in enumerate(fs):
         assert np.array_equal(var.fix_y[s], cf["fix_y"][q]), s
         assert int(atm.conden_min_lev[s]) == int(cf["conden_min_lev"][q]), s
+
+
+def test_adapt_rtol_follows_the_reference_policy():
+    """`use_adapt_rtol` (op.py:835-853): every 10th step an element loss above `loss_criteria` doubles the criterion and cuts rtol by 25 %
+    (floor rtol_min); every 1000th step a loss below 2e-4 raises it by 25 % (ceiling rtol_max).  The expected sequence below is the
+    reference's block transcribed statement by statement; step_ok keeps the frozen rtol (default argument bound at import, op.py:2489)."""
+    from types import SimpleNamespace
+    from vulcan_b200.integration import Integration
+    cfg = SimpleNamespace(ini_update_photo_frq=100, use_condense=False, rtol=0.25, rtol_min=0.02, rtol_max=2.5)
+    integ = Integration(odesolver=None, cfg=cfg, species=["H"])
+    integ.loss_criteria = 0.0005
+    rng = np.random.default_rng(3)
+    ref_rtol, ref_crit = 0.25, 0.0005
+    for count in range(0, 4001):
+        loss = {"H": float(10.0 ** rng.uniform(-5, -2.5)) * (-1) ** count, "O": 1e-5}
+        var, para = SimpleNamespace(atom_loss=loss), SimpleNamespace(count=count)
+        integ.adapt_rtol(var, para)
+        # op.py:836-850
+        if count % 10 == 0:
+            if max([np.abs(v) for v in loss.values()]) >= ref_crit:
+                ref_crit *= 2.
+                ref_rtol *= 0.75
+                ref_rtol = max(ref_rtol, cfg.rtol_min)
+        if count % 1000 == 0 and count > 0:
+            if max([np.abs(v) for v in loss.values()]) < 2e-4:
+                ref_rtol *= 1.25
+                ref_rtol = min(ref_rtol, cfg.rtol_max)
+        assert cfg.rtol == ref_rtol and integ.loss_criteria == ref_crit
+    assert cfg.rtol < 0.25                     # the policy did act on this sequence

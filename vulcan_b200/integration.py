@@ -12,7 +12,7 @@ fix_species switch with its cold-trap levels (op.py:859-893) are mirrored expres
 they are bit-identical to the reference on the same inputs: tests/test_integration_host.py against fixtures recorded from the
 reference's own operators).  They act once per ACCEPTED step on nz-vectors of one or two species - bookkeeping of the caller,
 not part of the Ros2 stage arithmetic - and stay on the host next to conv()/save_step, which need var.y on the host anyway.
-Not built: `use_adapt_rtol` (no shipped cfg defines it) raises NotImplementedError instead of silently skipping.
+`use_adapt_rtol` (op.py:835-853; no shipped cfg defines the switch, SURVEY 8c shim 2) is mirrored in `adapt_rtol`.
 
 All arithmetic of the step itself runs on the GPU behind the C ABI; what is left here is the reference's own per-step host
 bookkeeping (numpy), kept on the host because `conv()` compares against the stored history `y_time`.
@@ -37,8 +37,7 @@ class Integration(object):
     # ------------------------------------------------------------------------------------------------ op.py:808-935
     def __call__(self, var, atm, para, max_wall_s=None):
         cfg = self.cfg
-        if getattr(cfg, "use_adapt_rtol", False):
-            raise NotImplementedError("use_adapt_rtol (op.py:836-856)")
+        self.loss_criteria = 0.0005                                                                  # op.py:811
         t0 = time.time()
         while not self.stop(var, para, atm):
             var = self.backup(var)
@@ -55,6 +54,8 @@ class Integration(object):
                 self.n_photo_updates += 1
                 self.t_photo += time.time() - tp
             var, para = self.odesolver.one_step(var, atm, para)                                      # op.py:832
+            if getattr(cfg, "use_adapt_rtol", False):                                                # op.py:835-853 ("TEST 2025")
+                self.adapt_rtol(var, para)
             if getattr(cfg, "use_condense", False) and var.t >= cfg.start_conden_time and not para.fix_species_start:   # op.py:859-902
                 var = self.conden(var, atm)
                 if cfg.fix_species and var.t > cfg.stop_conden_time:
@@ -78,6 +79,19 @@ class Integration(object):
                 para.end_case = 4
                 break
         return var, atm, para
+
+    # ------------------------------------------------------------------------------------------------ op.py:835-853
+    def adapt_rtol(self, var, para):
+        """`use_adapt_rtol`: element loss steers cfg.rtol.  Only step_size sees the new value (it reads vulcan_cfg.rtol live,
+        op.py:3111); step_ok / step_reject keep the rtol their default arguments froze at import (op.py:2489, 2495) - the mirror's
+        `_rtol0` - exactly as in the reference."""
+        cfg = self.cfg
+        worst = max(abs(v) for v in var.atom_loss.values())
+        if para.count % 10 == 0 and worst >= self.loss_criteria:
+            self.loss_criteria *= 2.
+            cfg.rtol = max(cfg.rtol * 0.75, cfg.rtol_min)
+        if para.count % 1000 == 0 and para.count > 0 and worst < 2e-4:
+            cfg.rtol = min(cfg.rtol * 1.25, cfg.rtol_max)
 
     # ------------------------------------------------------------------------------------------------ op.py:862-893
     def start_fix_species(self, var, atm, para):
