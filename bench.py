@@ -277,6 +277,20 @@ def main():
     fa, fb = ctypes.c_float(0), ctypes.c_float(0)
     runner.col.lib.vk_last_kernel_ms(runner.col.handle, ctypes.byref(fa), ctypes.byref(fb))
 
+    # ---- the HBM-side kernels of the step, each timed alone on the resident state (library profiling aid vk_debug_time_kernel,
+    # CUDA events on the column stream; scripts/kernel_times.py).  Supplementary: never allowed to break the bench line.
+    kernel_ms = {}
+    try:
+        lib = runner.col.lib
+        lib.vk_debug_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+        lib.vk_debug_time_kernel.restype = ctypes.c_int
+        for which, name in ((0, "lhs_ml_kernel"), (1, "rhs_warp_kernel"), (4, "lu_solve_kernel (forward + backward)")):
+            msk = ctypes.c_float(0)
+            if lib.vk_debug_time_kernel(runner.col.handle, which, 3, ctypes.byref(msk)) == 0 and msk.value > 0:
+                kernel_ms[name] = float(msk.value)
+    except Exception:
+        kernel_ms = {}
+
     # ---- the one collective: final gather of the mixing ratios ----------------------------------------------------------
     fin = runner.state(want_y=True)
     ymix_local = fin["y"] / fin["y"].sum(axis=2, keepdims=True)
@@ -344,6 +358,22 @@ def main():
                             "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                             "flops_per_column_step": FLOP_FACTOR(nz, ni), "kernel_ms": fms,
                             "share_of_step": fms / float(np.mean(tot_ms))}
+        # HBM roofline of the streaming kernels (north_star: "achieved HBM GB/s for the rate/RHS/diffusion kernels"), algorithmic bytes
+        # per column as DESIGN.md section 4 states them; peak = MEASURED_PEAKS.json (driver-written copy bandwidth) or the recipe's fallback
+        try:
+            hbm_peak, hbm_src = 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+            pk = os.path.join(REPO, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                hbm_peak, hbm_src = float(json.load(open(pk))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+            nip = ((ni + 23) // 24) * 24 if ni > 48 else 48          # padded block size the kernels are instantiated for (48 / 72 / 96 / 120)
+            alg = {"lhs_ml_kernel": nz * nip * nip * 8.0 + nz * ni * 8.0,                        # writes D (+ up, dn), reads y; k is shared (L2)
+                   "rhs_warp_kernel": 2.0 * nz * ni * 8.0,                                       # reads y, writes f; k is shared (L2)
+                   "lu_solve_kernel (forward + backward)": 2.0 * nz * nip * (nip + 2) * 8.0}     # reads the factors F_j once per sweep
+            line["hbm_kernels"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src, "kernels": [
+                {"kernel": name, "ms": msv, "algorithmic_bytes_per_column": alg[name], "achieved_gbs": alg[name] * ncol / (msv * 1e-3) / 1e9,
+                 "frac": alg[name] * ncol / (msv * 1e-3) / 1e9 / hbm_peak} for name, msv in kernel_ms.items()]}
+        except Exception:
+            pass
         # single-column numbers (BASELINE metric part 1)
         one = ensemble.EnsembleRunner(case.net, case.nz, case.y[None], np.array([case.dt]), atm_common, np.asarray(kw["Kzz"])[None],
                                       case.k, cfg, st["compo"], st["atom_ini"][None], st["n_0"], device=local_rank, refine=refine)
