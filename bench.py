@@ -31,7 +31,7 @@ sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
 
 N_COLUMNS = 4096
-CPU_STEPS_PER_THREAD = 48   # CPU legs: column-steps timed per host thread (~2-3 s wall, ~40 CPU-seconds on 16 threads)
+CPU_STEPS_PER_THREAD = int(os.environ.get("VK_BENCH_CPU_STEPS_PER_THREAD", "48"))   # CPU legs: column-steps timed per host thread (~2-3 s wall, ~40 CPU-seconds on 16 threads)
 BASE_STEP = 100          # fixture state the synthetic columns are derived from (dt = 4.84 s)
 FLOP_FACTOR = lambda nz, ni: nz * (2.0 * ni ** 3 + ni ** 2)                 # getrf+getri count + scaled Schur update
 FLOP_SOLVES = lambda nz, ni, nrhs: nrhs * nz * (2.0 * ni ** 2 + 2.0 * ni)   # forward/backward sweeps
