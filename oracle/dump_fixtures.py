@@ -120,8 +120,11 @@ def static_dict(s):
 
 
 def dyn_atm(atm):
-    return dict(dz=atm.dz.copy(), dzi=atm.dzi.copy(), mu=atm.mu.copy(), Hp=atm.Hp.copy(), Hpi=atm.Hpi.copy(),
-                Ti=atm.Ti.copy(), g=atm.g.copy(), top_flux_dyn=atm.top_flux.copy(), vs_dyn=atm.vs.copy(),
+    # use_moldiff = False: build_atm never calls mol_diff, so the interface arrays Hpi / Ti do not exist (and the _no_mol stencils
+    # never read them): stored as zeros of the interface shape
+    zi = np.zeros(len(atm.dzi))
+    return dict(dz=atm.dz.copy(), dzi=atm.dzi.copy(), mu=atm.mu.copy(), Hp=atm.Hp.copy(), Hpi=np.array(getattr(atm, "Hpi", zi), copy=True),
+                Ti=np.array(getattr(atm, "Ti", zi), copy=True), g=atm.g.copy(), top_flux_dyn=atm.top_flux.copy(), vs_dyn=atm.vs.copy(),
                 zco=atm.zco.copy())
 
 

@@ -59,6 +59,8 @@ CONFIGS = {
     # diffdf_vm + lhs_jac_tot_vm (op.py:1599-1694, 2044-2119) and, with settling, diffdf_settling_vm + lhs_jac_settling_vm
     # (op.py:1794-1898, 2366-2444)
     "HD189vm": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_vm_mol": "True"}, extra=""),
+    # use_moldiff = False: eddy diffusion only, diffdf_no_mol + lhs_jac_no_mol (op.py:1438-1494, 2122-2166)
+    "HD189nomol": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_moldiff": "False"}, extra=""),
     "JupiterVm": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"use_vm_mol": "True"}, extra=""),
     # use_ion (op.py:2789-2820 compute_Jion, 2908-2911 / 2926 electron rows, 2998-3004 charge balance).  No shipped network has an
     # `# ionisation` section, so this fixture-only variant appends one to NCHO_photo_network.txt in the scratch copy (ION_TEST_*

@@ -20,7 +20,7 @@ def have(tag, name):
 
 
 # fixture variants that run a base config's network with different cfg switches (oracle/stage_reference.py::CONFIGS)
-NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
+NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "HD189nomol": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
 
 
 def load_network(tag):
@@ -79,6 +79,10 @@ ION_CASES = [p for p in [("HD189ion", 0), ("HD189ion", 30)] if have(p[0], "step%
 import glob as _glob
 FIX_CASES = [("JupiterFix", int(os.path.basename(f)[len("JupiterFix_step"):-4])) for f in sorted(_glob.glob(os.path.join(GOLD, "JupiterFix_step*.npz")))]
 CASES = CASES + VM_CASES + ION_CASES + FIX_CASES
+# use_moldiff = False (diffdf_no_mol / lhs_jac_no_mol, op.py:1438-1494, 2122-2166): recorded at the end of round 1 in a GPU-less session.
+# Pins the ORACLE on the CPU (tests/test_oracle_vs_reference.py, tests/test_lockstep_host.py); deliberately NOT part of CASES / LOCKSTEP
+# yet, which also parametrise the -m gpu tests: the device's _no_mol branch has not run on a GPU.
+NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], "step%04d.npz" % p[1])]
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
 
 

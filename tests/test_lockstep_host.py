@@ -8,7 +8,11 @@ from lockstep import LOCKSTEP, check_ion_photolysis, lockstep, long_trajectory
 from oracle_columns import oracle_backed_abi
 
 
-@pytest.mark.parametrize("tag,nstep", LOCKSTEP, ids=["%s-%d" % p for p in LOCKSTEP])
+# HD189nomol (use_moldiff = False): CPU only for now, see helpers.NOMOL_CASES
+HOST_LOCKSTEP = LOCKSTEP + ([("HD189nomol", 30)] if have("HD189nomol", "step0030.npz") and have("HD189nomol", "step0000.npz") else [])
+
+
+@pytest.mark.parametrize("tag,nstep", HOST_LOCKSTEP, ids=["%s-%d" % p for p in HOST_LOCKSTEP])
 def test_first_steps_reproduce_the_reference(tag, nstep):
     r = lockstep(tag, nstep, abi=oracle_backed_abi())
     print("%s: after %d steps  t %.1e  dt %.1e  y (masked) %.1e  y (>1e-30) %.1e  ymix %.1e  rejected %d  wall %.1f s" %

@@ -4,13 +4,13 @@ REFERENCE (oracle/dump_fixtures.py, PYTHONHASHSEED=0).  The reference ships no t
 import numpy as np
 import pytest
 
-from helpers import CASES, PHOTO_CASES, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
+from helpers import CASES, NOMOL_CASES, PHOTO_CASES, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
 from oracle import Oracle
 
 R = 1. + 1. / 2. ** 0.5
 
 
-@pytest.fixture(scope="module", params=CASES, ids=case_id)
+@pytest.fixture(scope="module", params=CASES + NOMOL_CASES, ids=case_id)
 def case(request):
     tag, step = request.param
     if not have(tag, "step%04d.npz" % step):
