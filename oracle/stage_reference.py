@@ -88,6 +88,12 @@ CONFIGS = {
         edits={"network": "'thermo/NCHO_earth_photo_network.txt'"},
         extra="",  # filled in by stage() (species filtering needs the network parsed)
     ),
+    # the Earth cfg AS SHIPPED: cfg_examples/vulcan_cfg_Earth.py:11 names SNCHO_full_photo_network.txt (ni = 99, nr = 1284 - the largest
+    # network the reference ships a cfg for), sulphur boundary fluxes and const_mix included.  The cfg does not run as shipped: its
+    # const_mix / atom_list name Ar, which SNCHO_full_photo_network.txt does not contain (build_atm.py:195 ValueError) -> Ar dropped
+    "EarthS": dict(src="cfg_examples/vulcan_cfg_Earth.py",
+                   edits={"atom_list": "['H', 'O', 'C', 'N', 'S']",
+                          "const_mix": "{'N2':0.78, 'O2':0.20, 'H2O':1e-6, 'CO2':4E-4, 'SO2': 2e-10}"}, extra=""),
     # Earth + use_vm_mol: lhs_jac_settling_vm with the diffusion-limited escape term (diff_esc = ['H2','H'], op.py:2425-2431)
     "EarthVm": dict(
         src="cfg_examples/vulcan_cfg_Earth.py",

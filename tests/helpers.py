@@ -83,6 +83,11 @@ CASES = CASES + VM_CASES + ION_CASES + FIX_CASES
 # Pins the ORACLE on the CPU (tests/test_oracle_vs_reference.py, tests/test_lockstep_host.py); deliberately NOT part of CASES / LOCKSTEP
 # yet, which also parametrise the -m gpu tests: the device's _no_mol branch has not run on a GPU.
 NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], "step%04d.npz" % p[1])]
+# the Earth cfg with the network it actually names (cfg_examples/vulcan_cfg_Earth.py:11: SNCHO_full_photo_network.txt, ni = 99, nr = 1284;
+# H2SO4 condensation, sulphur boundary fluxes): the largest shipped cfg, padded block size 120.  Same status as NOMOL_CASES: pins the
+# oracle and the host protocol on the CPU; the chemistry kernels have not run this size class on a GPU.
+NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s
+PHOTO_CASES_CPU_ONLY = [p for p in [("EarthS", 0), ("EarthS", 30)] if have(p[0], "photo%04d.npz" % p[1])]
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
 
 

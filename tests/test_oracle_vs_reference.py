@@ -4,7 +4,7 @@ REFERENCE (oracle/dump_fixtures.py, PYTHONHASHSEED=0).  The reference ships no t
 import numpy as np
 import pytest
 
-from helpers import CASES, NOMOL_CASES, PHOTO_CASES, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
+from helpers import CASES, NOMOL_CASES, PHOTO_CASES, PHOTO_CASES_CPU_ONLY, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
 from oracle import Oracle
 
 R = 1. + 1. / 2. ** 0.5
@@ -46,7 +46,10 @@ def test_chemjac_blocks(case):
     J = case.oracle.chemjac(case.y, case.st["M"], case.k)
     for i, j in enumerate(case.fx["layers"]):
         ref = case.fx["negjac_blocks"][i]
-        assert np.array_equal(ref != 0, J[j] != 0)
+        # same sparsity, except where a product of three tiny factors lands in the denormal range in one multiplication order and
+        # underflows to 0 in the other (EarthS-30: 3.7e-320 vs 0)
+        differ = (ref != 0) != (J[j] != 0)
+        assert not differ.any() or max(np.abs(ref[differ]).max(), np.abs(J[j][differ]).max()) < 2.3e-308
         scale = np.abs(ref).max(axis=1, keepdims=True)
         assert np.max(np.abs(-J[j] - ref) / np.maximum(scale, 1e-300)) < 4e-15
 
@@ -163,7 +166,7 @@ def test_clip_loss(case):
     assert np.allclose(loss, case.fx["atom_loss"], rtol=1e-12, atol=1e-300)
 
 
-@pytest.mark.parametrize("tag,step", PHOTO_CASES, ids=[case_id(p) for p in PHOTO_CASES])
+@pytest.mark.parametrize("tag,step", PHOTO_CASES + PHOTO_CASES_CPU_ONLY, ids=[case_id(p) for p in PHOTO_CASES + PHOTO_CASES_CPU_ONLY])
 def test_photolysis(tag, step):
     """compute_tau / compute_flux / compute_J (op.py:2580-2786): two consecutive updates from a zeroed diffuse field.
     The reference sums species in Python-set order (hash dependent), the oracle in sorted order -> rounding level."""
