@@ -59,6 +59,11 @@ CONFIGS = {
     # diffdf_vm + lhs_jac_tot_vm (op.py:1599-1694, 2044-2119) and, with settling, diffdf_settling_vm + lhs_jac_settling_vm
     # (op.py:1794-1898, 2366-2444)
     "HD189vm": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_vm_mol": "True"}, extra=""),
+    # use_vz = True with a sign-changing vertical wind (the upwind advection terms of diffdf / lhs_jac_tot, op.py:1531-1595, 1996-2034: every
+    # shipped cfg has use_vz = False, i.e. vz = 0).  vz_prof = 'file' reads a `vz` column from the atm file (build_atm.py:420-422): the
+    # scratch copy gets atm_HD189_Kzz.txt + a vz column of +-150 cm/s (comparable to Kzz / H) - a test INPUT; the code is the unmodified reference
+    "HD189vz": dict(src="cfg_examples/vulcan_cfg_HD189.py",
+                    edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/atm_HD189_Kzz_vz_test.txt'"}, extra=""),
     # use_moldiff = False: eddy diffusion only, diffdf_no_mol + lhs_jac_no_mol (op.py:1438-1494, 2122-2166)
     "HD189nomol": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_moldiff": "False"}, extra=""),
     "JupiterVm": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"use_vm_mol": "True"}, extra=""),
@@ -101,6 +106,21 @@ CONFIGS = {
         extra="",
     ),
 }
+
+def write_vz_test_atm(dest):
+    """atm/atm_HD189_Kzz.txt + a fourth column vz (cm/s): one and a half sine periods over the table, amplitude 150 cm/s, so that both
+    signs and both sign changes of the upwind switch occur in the column."""
+    import math
+    src, dst = os.path.join(dest, "atm/atm_HD189_Kzz.txt"), os.path.join(dest, "atm/atm_HD189_Kzz_vz_test.txt")
+    with open(src) as f:
+        lines = f.read().splitlines()
+    rows = [ln for ln in lines[2:] if ln.strip()]
+    out = [lines[0] + "\t (cm/s)", lines[1] + "\t vz"]
+    for q, ln in enumerate(rows):
+        out.append("%s\t %.3E" % (ln, 150.0 * math.sin(3.0 * math.pi * q / (len(rows) - 1))))
+    with open(dst, "w") as f:
+        f.write("\n".join(out) + "\n")
+
 
 ION_TEST_TWO_BODY = """\
 9001 [ H_p + e -> H                       ]  4.00E-12    -0.640       0.0      ion test (radiative recombination)
@@ -246,6 +266,8 @@ def stage(config, dest, run_codegen=True, quiet=True):
         })
     if config == "HD189ion":
         write_ion_test_network(dest)
+    if config == "HD189vz":
+        write_vz_test_atm(dest)
     text = _edit_cfg(text, edits)
     text += "\n# --- shims added by oracle/stage_reference.py (non-numerical) ---\nuse_adapt_rtol = False\n" + extra
     with open(os.path.join(dest, "vulcan_cfg.py"), "w") as f:
