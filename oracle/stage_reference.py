@@ -64,6 +64,12 @@ CONFIGS = {
     # scratch copy gets atm_HD189_Kzz.txt + a vz column of +-150 cm/s (comparable to Kzz / H) - a test INPUT; the code is the unmodified reference
     "HD189vz": dict(src="cfg_examples/vulcan_cfg_HD189.py",
                     edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/atm_HD189_Kzz_vz_test.txt'"}, extra=""),
+    # the same for the settling stencils: diffdf_settling / lhs_jac_settling (op.py:1696-1791, 2295-2364) and their use_vm_mol twins
+    # (op.py:1794-1898, 2366-2444); amplitude 5 cm/s (Jupiter's Kzz / H is of that order)
+    "JupiterVz": dict(src="cfg_examples/vulcan_cfg_Jupiter.py",
+                      edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/Jupiter_deep_top_vz_test.txt'"}, extra=""),
+    "JupiterVmVz": dict(src="cfg_examples/vulcan_cfg_Jupiter.py",
+                        edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/Jupiter_deep_top_vz_test.txt'", "use_vm_mol": "True"}, extra=""),
     # use_moldiff = False: eddy diffusion only, diffdf_no_mol + lhs_jac_no_mol (op.py:1438-1494, 2122-2166)
     "HD189nomol": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"use_moldiff": "False"}, extra=""),
     "JupiterVm": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"use_vm_mol": "True"}, extra=""),
@@ -107,17 +113,17 @@ CONFIGS = {
     ),
 }
 
-def write_vz_test_atm(dest):
+def write_vz_test_atm(dest, name="atm/atm_HD189_Kzz.txt", out_name="atm/atm_HD189_Kzz_vz_test.txt", amp=150.0):
     """atm/atm_HD189_Kzz.txt + a fourth column vz (cm/s): one and a half sine periods over the table, amplitude 150 cm/s, so that both
     signs and both sign changes of the upwind switch occur in the column."""
     import math
-    src, dst = os.path.join(dest, "atm/atm_HD189_Kzz.txt"), os.path.join(dest, "atm/atm_HD189_Kzz_vz_test.txt")
+    src, dst = os.path.join(dest, name), os.path.join(dest, out_name)
     with open(src) as f:
         lines = f.read().splitlines()
     rows = [ln for ln in lines[2:] if ln.strip()]
     out = [lines[0] + "\t (cm/s)", lines[1] + "\t vz"]
     for q, ln in enumerate(rows):
-        out.append("%s\t %.3E" % (ln, 150.0 * math.sin(3.0 * math.pi * q / (len(rows) - 1))))
+        out.append("%s\t %.3E" % (ln, amp * math.sin(3.0 * math.pi * q / (len(rows) - 1))))
     with open(dst, "w") as f:
         f.write("\n".join(out) + "\n")
 
@@ -268,6 +274,8 @@ def stage(config, dest, run_codegen=True, quiet=True):
         write_ion_test_network(dest)
     if config == "HD189vz":
         write_vz_test_atm(dest)
+    if config in ("JupiterVz", "JupiterVmVz"):
+        write_vz_test_atm(dest, "atm/Jupiter_deep_top.txt", "atm/Jupiter_deep_top_vz_test.txt", amp=5.0)
     text = _edit_cfg(text, edits)
     text += "\n# --- shims added by oracle/stage_reference.py (non-numerical) ---\nuse_adapt_rtol = False\n" + extra
     with open(os.path.join(dest, "vulcan_cfg.py"), "w") as f:

@@ -20,7 +20,7 @@ def have(tag, name):
 
 
 # fixture variants that run a base config's network with different cfg switches (oracle/stage_reference.py::CONFIGS)
-NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "HD189nomol": "HD189", "HD189vz": "HD189", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
+NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "HD189nomol": "HD189", "HD189vz": "HD189", "JupiterVz": "Jupiter", "JupiterVmVz": "Jupiter", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
 
 
 def load_network(tag):
@@ -88,7 +88,8 @@ NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], 
 # oracle and the host protocol on the CPU; the chemistry kernels have not run this size class on a GPU.
 # use_vz = True with a sign-changing vertical wind (fixture-only atm file, oracle/stage_reference.py::write_vz_test_atm): the upwind advection
 # terms of every stencil variant, which no shipped cfg switches on.  The device kernels carry vz too but every GPU fixture so far has vz = 0.
-NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30)] if have(p[0], "step%04d.npz" % p[1])]
+NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30), ("JupiterVz", 0), ("JupiterVz", 30), ("JupiterVmVz", 0), ("JupiterVmVz", 30)]
+                if have(p[0], "step%04d.npz" % p[1])]         # diffdf / _settling / _settling_vm with vz != 0
 NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s
 PHOTO_CASES_CPU_ONLY = [p for p in [("EarthS", 0), ("EarthS", 30)] if have(p[0], "photo%04d.npz" % p[1])]
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
