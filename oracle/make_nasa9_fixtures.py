@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 REF = os.environ.get("VULCAN_REFERENCE", "/root/reference")
 ALIAS = {"CH3CCH": "CH3C2H"}
-for tag in ("HD189", "Jupiter", "Earth", "HD209S", "HD189ion"):
+for tag in ("HD189", "Jupiter", "Earth", "HD209S", "HD189ion", "EarthS"):
     with open(os.path.join(REPO, "tests", "golden", tag + "_network.json")) as f:
         species = json.load(f)["species"]
     coef = np.zeros((len(species), 20))

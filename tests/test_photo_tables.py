@@ -12,7 +12,7 @@ from helpers import GOLD, REPO, have
 REF = os.environ.get("VULCAN_REFERENCE", "/root/reference")
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "thermo", "photo_cross")), reason="reference data tree not present")
 
-TAGS = [t for t in ("HD189", "Jupiter", "Earth", "HD209S", "HD189ion") if have(t, "static.npz")]
+TAGS = [t for t in ("HD189", "Jupiter", "Earth", "HD209S", "HD189ion", "EarthS") if have(t, "static.npz")]
 
 
 def _cfg(tag):

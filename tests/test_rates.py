@@ -3,6 +3,7 @@ var.k (<cfg>_static.npz, written by the unmodified reference: read_rate + lim_lo
 chem_funs.Gibbs); the device kernel (vk_compute_k) is then checked against the oracle to 1e-12 relative: libm vs CUDA pow / exp / log
 differ by an ulp, and K_eq = exp(-sum nu g/RT) amplifies one ulp of the sum by |sum| (up to ~700 in the cold layers of Jupiter / Earth:
 measured 1.1e-13 there, 2e-14 for the hot Jupiters)."""
+import json
 import os
 
 import numpy as np
@@ -10,6 +11,7 @@ import pytest
 
 from helpers import GOLD, load_network
 
+TAGS_CPU = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion", "EarthS"]    # EarthS (SNCHO_full, ni = 99): oracle only for now
 TAGS = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion"]      # the last one: ion test network (ionisation rows are zero at set-up like photolysis rows)
 LOW_T = {"Jupiter": True}            # cfg_examples/vulcan_cfg_Jupiter.py:7
 
@@ -23,17 +25,21 @@ def _load(tag):
     return net, st, nasa9, hi
 
 
-@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("tag", TAGS_CPU)
 def test_oracle_matches_reference_k_bit_for_bit(tag):
     import rates_oracle
     net, st, nasa9, hi = _load(tag)
     with np.errstate(over="ignore"):
-        k = rates_oracle.compute_k(net, st["Tco"], st["M"], nasa9, use_lowT_limit_rates=LOW_T.get(tag, False))
+        # remove_list (remove_rate, op.py:311-317): only the shipped Earth cfg uses it ([315, 316]) - fixture EarthS
+        remove = json.loads(str(st["cfg_json"])).get("remove_list", [])
+        k = rates_oracle.compute_k(net, st["Tco"], st["M"], nasa9, remove_list=remove, use_lowT_limit_rates=LOW_T.get(tag, False))
+    if tag == "EarthS":
+        assert list(remove) == [315, 316] and not k[315].any() and not k[316].any()
     assert np.array_equal(k[1:hi], st["k"][1:hi])
     assert not k[hi:].any()
 
 
-@pytest.mark.parametrize("tag", TAGS)
+@pytest.mark.parametrize("tag", TAGS_CPU)
 def test_rate_table_structure(tag):
     from vulcan_b200.rates import RateTable
     net, st, nasa9, hi = _load(tag)
