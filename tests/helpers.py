@@ -227,6 +227,11 @@ def mock_objects(case, with_photo=True):
                           bot_vdep=st["bot_vdep"].copy(), gas_indx=list(st["gas_indx"]), n_0=st["n_0"].copy(), dz=fx["dz"].copy(),
                           pico=st["pico"].copy(), pco=st["pco"].copy(), pref_indx=int(st["pref_indx"]), gs=float(cfgd["gs"]),
                           Hp=fx["Hp"].copy(), zco=fx["zco"].copy(), mu=fx["mu"].copy(), vm=st["vm"].copy())
+    if not cfgd["use_moldiff"]:
+        # what the reference's atm object looks like then (found by running the drop-in class inside the unmodified reference): vulcan.py
+        # never calls mol_diff, so Ti / Hpi do not exist (build_atm.py:569-571) and ms is np.empty garbage (store.py:129)
+        del atm.Ti, atm.Hpi
+        atm.ms = np.full(case.ni, np.nan)
     para = SimpleNamespace(delta=0.0, small_y=0.0, nega_y=0.0, delta_count=0, nega_count=0, loss_count=0, count=int(fx["count"]),
                            fix_species_start=False, solver_str="", end_case=0, switch_final_photo_frq=False)
     if with_photo and cfgd.get("use_photo") and "photo_sp" in st:
@@ -359,7 +364,7 @@ def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
         solver.compute_tau(var, atm)
         solver.compute_flux(var, atm)
         solver.compute_J(var, atm)
-        integ = Integration(solver, cfg, case.net.species)
+        integ = Integration(solver, cfg, case.net.species, mass=None if cfg.use_moldiff else case.st["ms"])
         t0 = time.time()
         var, atm, para = integ(var, atm, para, max_wall_s=max_wall_s)
         return case, var, atm, para, integ, time.time() - t0

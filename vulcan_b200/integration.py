@@ -26,8 +26,9 @@ NAVO = 6.02214086e23     # phy_const.py:4
 
 
 class Integration(object):
-    def __init__(self, odesolver, cfg, species, verbose=False):
+    def __init__(self, odesolver, cfg, species, verbose=False, mass=None):
         self.odesolver, self.cfg, self.species, self.verbose = odesolver, cfg, list(species), verbose
+        self._mass = None if mass is None else np.asarray(mass, dtype=np.float64)     # molar masses, see _mol_mass
         self.update_photo_frq = cfg.ini_update_photo_frq                      # op.py:800
         if getattr(cfg, "use_condense", False):
             self.non_gas_sp_index = [self.species.index(sp) for sp in cfg.non_gas_sp]
@@ -203,14 +204,29 @@ class Integration(object):
         var.atom_loss_prev = var.atom_loss.copy()
         return var
 
+    def _mol_mass(self, atm):
+        """molar mass per species as mean_mass reads it (build_atm.py:511-520: the `mass` column of vulcan_cfg.com_file).  atm.ms holds the
+        same numbers once mol_diff has run (build_atm.py:675) - but with use_moldiff = False it is np.empty garbage (store.py:129), so
+        then the masses come from the `mass=` argument or the compose file."""
+        if self._mass is None:
+            if self.cfg.use_moldiff:
+                return atm.ms
+            with open(self.cfg.com_file) as f:
+                cols = f.readline().split()
+            tab = np.genfromtxt(self.cfg.com_file, names=True, dtype=["U20"] + ["int"] * (len(cols) - 2) + ["float"])
+            rows = list(tab["species"])
+            self._mass = np.array([tab[rows.index(sp)][cols[-1]] for sp in self.species], dtype=np.float64)
+        return self._mass
+
     def update_mu_dz(self, var, atm):                                                                # op.py:944-984
         cfg = self.cfg
         nz = var.y.shape[0]
         pref_indx = int(atm.pref_indx)
         Tco, pico = atm.Tco.copy(), atm.pico.copy()
         mu = np.zeros(nz)
+        ms = self._mol_mass(atm)
         for i in range(len(self.species)):                                                           # build_atm.py:515-520
-            mu += atm.ms[i] * var.ymix[:, i]
+            mu += ms[i] * var.ymix[:, i]
         atm.mu = mu
         Hp = atm.Hp
         for i in range(pref_indx, nz):

@@ -90,7 +90,15 @@ class Ros2(object):
 
     def _sync_atm(self, atm, nz):
         cfg = self.cfg
-        vals = {n: np.asarray(getattr(atm, n), dtype=np.float64) for n in _DYN_ATM}
+        if cfg.use_moldiff:
+            vals = {n: np.asarray(getattr(atm, n), dtype=np.float64) for n in _DYN_ATM}
+        else:
+            # use_moldiff = False: vulcan.py never calls mol_diff, so atm.Ti / atm.Hpi do not exist (build_atm.py:569-571) and atm.ms is
+            # np.empty garbage (store.py:129); diffdf_no_mol / lhs_jac_no_mol (op.py:1438-1494, 2122-2166) read none of the molecular-
+            # diffusion arrays -> zeros of the right shape go to the device (found by running the class inside the unmodified reference)
+            ni = len(self.species)
+            zeros = {"Ti": (nz - 1,), "Hpi": (nz - 1,), "ms": (ni,), "alpha": (ni,), "Dzz": (nz - 1, ni)}
+            vals = {n: (np.zeros(zeros[n]) if n in zeros else np.asarray(getattr(atm, n), dtype=np.float64)) for n in _DYN_ATM}
         flags = (bool(cfg.use_moldiff), bool(cfg.use_settling), bool(cfg.use_topflux), bool(cfg.use_botflux), bool(cfg.use_vm_mol))
         use_vm = bool(cfg.use_vm_mol) and bool(cfg.use_moldiff)      # Ros2.solver's dispatch (op.py:2869-2888)
         if use_vm:
