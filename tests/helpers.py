@@ -90,6 +90,8 @@ NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], 
 # terms of every stencil variant, which no shipped cfg switches on.  The device kernels carry vz too but every GPU fixture so far has vz = 0.
 NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30), ("JupiterVz", 0), ("JupiterVz", 30), ("JupiterVmVz", 0), ("JupiterVmVz", 30)]
                 if have(p[0], "step%04d.npz" % p[1])]         # diffdf / _settling / _settling_vm with vz != 0
+# thermochemistry only (NCHO_thermo_network.txt: no photo section, use_photo = False)
+NOMOL_CASES += [p for p in [("HD189thermo", 0), ("HD189thermo", 30)] if have(p[0], "step%04d.npz" % p[1])]
 NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s
 PHOTO_CASES_CPU_ONLY = [p for p in [("EarthS", 0), ("EarthS", 30)] if have(p[0], "photo%04d.npz" % p[1])]
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
@@ -361,9 +363,10 @@ def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
                       charge=case.st["charge"] if "charge" in case.st else None)
         solver.naming_solver(para)
         # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
-        solver.compute_tau(var, atm)
-        solver.compute_flux(var, atm)
-        solver.compute_J(var, atm)
+        if cfg.use_photo:
+            solver.compute_tau(var, atm)
+            solver.compute_flux(var, atm)
+            solver.compute_J(var, atm)
         integ = Integration(solver, cfg, case.net.species, mass=None if cfg.use_moldiff else case.st["ms"])
         t0 = time.time()
         var, atm, para = integ(var, atm, para, max_wall_s=max_wall_s)
