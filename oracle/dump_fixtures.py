@@ -146,7 +146,8 @@ def capture_step(s, tag, count):
     if cfg.use_condense and para.fix_species_start:       # the state Ros2.solver's fixed-species rows read (op.py:2896-2906, 2960-2970)
         out["fix_species"] = np.array(list(cfg.fix_species))
         out["fix_y"] = np.array([var.fix_y[sp] for sp in cfg.fix_species])
-        out["conden_min_lev"] = np.array([int(atm.conden_min_lev[sp]) for sp in cfg.fix_species])
+        # fix_species_from_coldtrap_lev = False: the whole column is fixed and conden_min_lev is only filled for the condensing gases
+        out["conden_min_lev"] = np.array([int(atm.conden_min_lev.get(sp, s.nz)) for sp in cfg.fix_species])
         out["fix_from_coldtrap"] = bool(cfg.fix_species_from_coldtrap_lev)
     # ---- L0: components, evaluated by the reference functions on a copy of the state
     y = var.y.copy()
@@ -319,7 +320,8 @@ def finish_conden(s, tag, store, traj):
     out["fix_species_start"] = bool(para.fix_species_start)
     if para.fix_species_start:
         out["fix_y"] = np.array([var.fix_y[sp] for sp in cfg.fix_species])
-        out["conden_min_lev"] = np.array([int(atm.conden_min_lev[sp]) for sp in cfg.fix_species])
+        # fix_species_from_coldtrap_lev = False: the whole column is fixed and conden_min_lev is only filled for the condensing gases
+        out["conden_min_lev"] = np.array([int(atm.conden_min_lev.get(sp, s.nz)) for sp in cfg.fix_species])
         out["vs_after"] = atm.vs.copy()
         out["rtol_after"] = float(cfg.rtol)
     path = os.path.join(GOLD, "%s_conden.npz" % tag)

@@ -55,6 +55,9 @@ CONFIGS = {
     # reach the switch and the fixed-species rows of Ros2.solver (op.py:2896-2906, 2921-2924, 2960-2970).  (The shipped times are
     # out of reach of a fixture run: 3000 reference steps = 27 min of CPU only get to t = 6.6e5 s.)
     "JupiterFix": dict(src="cfg_examples/vulcan_cfg_Jupiter.py", edits={"start_conden_time": "10.", "stop_conden_time": "500."}, extra=""),
+    # the same with fix_species_from_coldtrap_lev = False: the WHOLE column of every fixed species is frozen (op.py:2898-2899, 2962-2963)
+    "JupiterFixAll": dict(src="cfg_examples/vulcan_cfg_Jupiter.py",
+                          edits={"start_conden_time": "10.", "stop_conden_time": "500.", "fix_species_from_coldtrap_lev": "False"}, extra=""),
     # use_vm_mol variants ("under testing" in the reference, vulcan_cfg.py:77): upwind advective form of molecular diffusion,
     # diffdf_vm + lhs_jac_tot_vm (op.py:1599-1694, 2044-2119) and, with settling, diffdf_settling_vm + lhs_jac_settling_vm
     # (op.py:1794-1898, 2366-2444)

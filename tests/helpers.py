@@ -20,7 +20,7 @@ def have(tag, name):
 
 
 # fixture variants that run a base config's network with different cfg switches (oracle/stage_reference.py::CONFIGS)
-NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "HD189nomol": "HD189", "HD189vz": "HD189", "JupiterVz": "Jupiter", "JupiterVmVz": "Jupiter", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
+NETWORK_OF = {"JupiterFix": "Jupiter", "HD189vm": "HD189", "HD189nomol": "HD189", "HD189vz": "HD189", "JupiterVz": "Jupiter", "JupiterVmVz": "Jupiter", "JupiterFixAll": "Jupiter", "JupiterVm": "Jupiter", "EarthVm": "Earth"}   # HD189ion has its own
 
 
 def load_network(tag):
@@ -90,6 +90,8 @@ NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], 
 # terms of every stencil variant, which no shipped cfg switches on.  The device kernels carry vz too but every GPU fixture so far has vz = 0.
 NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30), ("JupiterVz", 0), ("JupiterVz", 30), ("JupiterVmVz", 0), ("JupiterVmVz", 30)]
                 if have(p[0], "step%04d.npz" % p[1])]         # diffdf / _settling / _settling_vm with vz != 0
+# fix_species with fix_species_from_coldtrap_lev = False: whole columns of the fixed species are replaced rows (op.py:2898-2899, 2962-2963)
+NOMOL_CASES += [p for p in [("JupiterFixAll", 153)] if have(p[0], "step%04d.npz" % p[1])]
 # thermochemistry only (NCHO_thermo_network.txt: no photo section, use_photo = False)
 NOMOL_CASES += [p for p in [("HD189thermo", 0), ("HD189thermo", 30)] if have(p[0], "step%04d.npz" % p[1])]
 NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s
