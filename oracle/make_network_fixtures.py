@@ -12,7 +12,8 @@ REF = os.environ.get("VULCAN_REFERENCE", "/root/reference")
 NETS = {"HD189": "NCHO_photo_network.txt", "Jupiter": "NCHO_photo_network_lowT_Jupiter.txt",
         "Earth": "NCHO_earth_photo_network.txt", "HD209S": "SNCHO_photo_network_2025.txt",
         "EarthS": "SNCHO_full_photo_network.txt",
-        "HD189thermo": "NCHO_thermo_network.txt"}        # no photo section (use_photo = False)        # the network cfg_examples/vulcan_cfg_Earth.py names (ni = 99: padded block size 120)
+        "HD189thermo": "NCHO_thermo_network.txt",
+        "HD189cho": "CHO_photo_network.txt"}             # ni = 41: padded block size 48        # no photo section (use_photo = False)        # the network cfg_examples/vulcan_cfg_Earth.py names (ni = 99: padded block size 120)
 # fixture-only ion test network: written into the scratch copy by oracle/stage_reference.py::write_ion_test_network
 ION = "/tmp/vulcan_ref_HD189ion/thermo/NCHO_photo_ion_test_network.txt"
 if os.path.exists(ION):

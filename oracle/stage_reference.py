@@ -73,6 +73,8 @@ CONFIGS = {
                       edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/Jupiter_deep_top_vz_test.txt'"}, extra=""),
     "JupiterVmVz": dict(src="cfg_examples/vulcan_cfg_Jupiter.py",
                         edits={"use_vz": "True", "vz_prof": "'file'", "atm_file": "'atm/Jupiter_deep_top_vz_test.txt'", "use_vm_mol": "True"}, extra=""),
+    # the smallest shipped photochemical network (CHO_photo_network.txt, ni = 41: padded block size 48)
+    "HD189cho": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"network": "'thermo/CHO_photo_network.txt'", "atom_list": "['H', 'O', 'C']"}, extra=""),
     # thermochemistry only: a network without a photo section and use_photo = False (no compute_tau / flux / J calls at all)
     "HD189thermo": dict(src="cfg_examples/vulcan_cfg_HD189.py", edits={"network": "'thermo/NCHO_thermo_network.txt'", "use_photo": "False"}, extra=""),
     # use_moldiff = False: eddy diffusion only, diffdf_no_mol + lhs_jac_no_mol (op.py:1438-1494, 2122-2166)

@@ -92,6 +92,8 @@ NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30), ("JupiterVz", 0), (
                 if have(p[0], "step%04d.npz" % p[1])]         # diffdf / _settling / _settling_vm with vz != 0
 # fix_species with fix_species_from_coldtrap_lev = False: whole columns of the fixed species are replaced rows (op.py:2898-2899, 2962-2963)
 NOMOL_CASES += [p for p in [("JupiterFixAll", 153)] if have(p[0], "step%04d.npz" % p[1])]
+# the smallest shipped photochemical network (CHO_photo_network.txt, ni = 41: padded block size 48)
+NOMOL_CASES += [p for p in [("HD189cho", 0), ("HD189cho", 30)] if have(p[0], "step%04d.npz" % p[1])]
 # thermochemistry only (NCHO_thermo_network.txt: no photo section, use_photo = False)
 NOMOL_CASES += [p for p in [("HD189thermo", 0), ("HD189thermo", 30)] if have(p[0], "step%04d.npz" % p[1])]
 NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s

@@ -9,7 +9,7 @@ from oracle_columns import oracle_backed_abi
 
 
 # HD189nomol (use_moldiff = False), EarthS (the shipped Earth cfg's own network, ni = 99): CPU only for now, see helpers.NOMOL_CASES
-HOST_LOCKSTEP = LOCKSTEP + [p for p in [("HD189nomol", 30), ("HD189vz", 30), ("JupiterVz", 30), ("JupiterVmVz", 30), ("HD189thermo", 30), ("EarthS", 30)] if have(p[0], "step0030.npz") and have(p[0], "step0000.npz")]
+HOST_LOCKSTEP = LOCKSTEP + [p for p in [("HD189nomol", 30), ("HD189vz", 30), ("JupiterVz", 30), ("JupiterVmVz", 30), ("HD189thermo", 30), ("HD189cho", 30), ("EarthS", 30)] if have(p[0], "step0030.npz") and have(p[0], "step0000.npz")]
 
 
 @pytest.mark.parametrize("tag,nstep", HOST_LOCKSTEP, ids=["%s-%d" % p for p in HOST_LOCKSTEP])
@@ -18,7 +18,10 @@ def test_first_steps_reproduce_the_reference(tag, nstep):
     print("%s: after %d steps  t %.1e  dt %.1e  y (masked) %.1e  y (>1e-30) %.1e  ymix %.1e  rejected %d  wall %.1f s" %
           (tag, nstep, r["t"], r["dt"], r["y"], r["y_all"], r["ymix"], r["rejected"], r["wall"]))
     assert r["t"] < 1e-9 and r["dt"] < 1e-6
-    assert r["y"] < 1e-8 and r["ymix"] < 1e-8
+    # y under the reference's mask.  HD189cho: the REFERENCE's own LAPACK solve is 2.8e-7 away from the 80-bit solution of its system at
+    # step 30 (block LU: 6e-16; tests/test_oracle_vs_reference.py::test_solver_vs_truth measures both), so that is what the states differ by
+    ytol = {"HD189cho": 5e-6}.get(tag, 1e-8)
+    assert r["y"] < ytol and r["ymix"] < ytol
 
 
 @pytest.mark.skipif(not have("HD189ion", "photo0000.npz"), reason="fixture missing")
