@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define VK_ABI_VERSION 2
+#define VK_ABI_VERSION 3
 
 typedef enum {
     VK_OK = 0,
@@ -138,11 +138,12 @@ int vk_set_step_opts(vk_column *col, const vk_step_opts *opts);
 int vk_ros2_solve(vk_column *col, const double *y, const double *ymix, const double *dt, double *sol,
                   double *ymix_out, double *delta, int *status);
 
-/* ODESolver.clip + loss (op.py:2447-2487) on host arrays.  compo [ni][na]; atom_sum out [ncol][na];
- * small_y / nega_y [ncol] are ACCUMULATED like para.small_y / para.nega_y. */
+/* ODESolver.clip + loss (op.py:2447-2487) on host arrays.  compo [ni][na] (na <= 8); atom_sum out [ncol][na];
+ * small_y / nega_y [ncol] are ACCUMULATED like para.small_y / para.nega_y.  mtol = vulcan_cfg.mtol of the mask
+ * y[(ymix < mtol) & (y < 0)] = 0 (op.py:2459); a negative value means "the mtol of vk_set_step_opts". */
 int vk_clip_loss(vk_column *col, double *y, const double *ymix_in, double *ymix_out, int na, const double *compo,
-                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double *atom_sum, double *small_y,
-                 double *nega_y, int *any_negative);
+                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double mtol, double *atom_sum,
+                 double *small_y, double *nega_y, int *any_negative);
 
 /* ---- component entry points (parity tests, diagnostics) ---------------------------------------------------- */
 /* chem_funs.chemdf (chem_funs.py:931) + ODESolver.diffdf* (op.py:1438-1898): out_chem/out_diff [ncol][nz][ni],
@@ -197,6 +198,10 @@ int vk_ens_get_state(vk_column *col, double *y, double *t, double *dt, int *n_ac
 
 /* timing of the last vk_ros2_solve / vk_ens_run on the handle's stream, measured with CUDA events (ms) */
 int vk_last_kernel_ms(vk_column *col, float *ms_total, float *ms_factor);
+/* profiling aid (bench.py, scripts/kernel_times.py): `reps` back-to-back launches of ONE kernel of the step on the resident state with
+ * the step's own launch arguments, timed with CUDA events on the handle's stream; *ms = average per launch.
+ * which: 0 Jacobian + lhs assembly, 1 right-hand side (stage 1), 2 block-tridiagonal factorisation, 3 / 4 solve sweeps (forward + backward) */
+int vk_debug_time_kernel(vk_column *col, int which, int reps, float *ms);
 /* raw device pointers for callers that keep state resident (torch tensors): y/ymix/sol [ncol][nz][ni] */
 int vk_device_buffers(vk_column *col, void **y_dev, void **ymix_dev, void **sol_dev, void **k_dev);
 int vk_stream(vk_column *col, void **cuda_stream);

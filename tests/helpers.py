@@ -79,15 +79,14 @@ ION_CASES = [p for p in [("HD189ion", 0), ("HD189ion", 30)] if have(p[0], "step%
 import glob as _glob
 FIX_CASES = [("JupiterFix", int(os.path.basename(f)[len("JupiterFix_step"):-4])) for f in sorted(_glob.glob(os.path.join(GOLD, "JupiterFix_step*.npz")))]
 CASES = CASES + VM_CASES + ION_CASES + FIX_CASES
-# use_moldiff = False (diffdf_no_mol / lhs_jac_no_mol, op.py:1438-1494, 2122-2166): recorded at the end of round 1 in a GPU-less session.
-# Pins the ORACLE on the CPU (tests/test_oracle_vs_reference.py, tests/test_lockstep_host.py); deliberately NOT part of CASES / LOCKSTEP
-# yet, which also parametrise the -m gpu tests: the device's _no_mol branch has not run on a GPU.
+# use_moldiff = False (diffdf_no_mol / lhs_jac_no_mol, op.py:1438-1494, 2122-2166).  The fixture sets below were recorded at the end of
+# round 1 in a GPU-less session and pinned the oracle only; since round 2 they are part of CASES / LOCKSTEP, i.e. they run on the device
+# in the -m gpu tests as well (cfg-switch branches _no_mol / vz != 0, padded block sizes 48 and 120, fix_species over whole columns).
 NOMOL_CASES = [p for p in [("HD189nomol", 0), ("HD189nomol", 30)] if have(p[0], "step%04d.npz" % p[1])]
 # the Earth cfg with the network it actually names (cfg_examples/vulcan_cfg_Earth.py:11: SNCHO_full_photo_network.txt, ni = 99, nr = 1284;
-# H2SO4 condensation, sulphur boundary fluxes): the largest shipped cfg, padded block size 120.  Same status as NOMOL_CASES: pins the
-# oracle and the host protocol on the CPU; the chemistry kernels have not run this size class on a GPU.
+# H2SO4 condensation, sulphur boundary fluxes): the largest shipped cfg, padded block size 120.
 # use_vz = True with a sign-changing vertical wind (fixture-only atm file, oracle/stage_reference.py::write_vz_test_atm): the upwind advection
-# terms of every stencil variant, which no shipped cfg switches on.  The device kernels carry vz too but every GPU fixture so far has vz = 0.
+# terms of every stencil variant, which no shipped cfg switches on.
 NOMOL_CASES += [p for p in [("HD189vz", 0), ("HD189vz", 30), ("JupiterVz", 0), ("JupiterVz", 30), ("JupiterVmVz", 0), ("JupiterVmVz", 30)]
                 if have(p[0], "step%04d.npz" % p[1])]         # diffdf / _settling / _settling_vm with vz != 0
 # fix_species with fix_species_from_coldtrap_lev = False: whole columns of the fixed species are replaced rows (op.py:2898-2899, 2962-2963)
@@ -97,8 +96,9 @@ NOMOL_CASES += [p for p in [("HD189cho", 0), ("HD189cho", 30)] if have(p[0], "st
 # thermochemistry only (NCHO_thermo_network.txt: no photo section, use_photo = False)
 NOMOL_CASES += [p for p in [("HD189thermo", 0), ("HD189thermo", 30)] if have(p[0], "step%04d.npz" % p[1])]
 NOMOL_CASES += [p for p in [("EarthS", 0), ("EarthS", 30), ("EarthS", 100), ("EarthS", 300)] if have(p[0], "step%04d.npz" % p[1])]   # dt 1e-10 ... 1e4 s
-PHOTO_CASES_CPU_ONLY = [p for p in [("EarthS", 0), ("EarthS", 30)] if have(p[0], "photo%04d.npz" % p[1])]
+CASES = CASES + NOMOL_CASES
 PHOTO_CASES = [("HD189", 0), ("HD189", 300), ("Jupiter", 0), ("Jupiter", 30), ("Earth", 0), ("Earth", 30), ("HD209S", 0), ("HD209S", 30)]
+PHOTO_CASES += [p for p in [("EarthS", 0), ("EarthS", 30)] if have(p[0], "photo%04d.npz" % p[1])]
 
 
 def case_id(p):

@@ -10,7 +10,10 @@ from helpers import Case, have, run_config
 
 # (config, step count of the second fixture).  BASELINE.json configs 1-4 + the use_vm_mol variants + use_ion on the ion test network.
 LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD189vm", 30), ("JupiterVm", 30), ("EarthVm", 30),
-            ("HD189ion", 30)]
+            ("HD189ion", 30),
+            # cfg-switch variants first run on the device in round 2: use_moldiff = False, vz != 0 in three stencil variants, thermochemistry
+            # only, the smallest (ni = 41, block 48) and the largest (ni = 99, block 120) shipped networks
+            ("HD189nomol", 30), ("HD189vz", 30), ("JupiterVz", 30), ("JupiterVmVz", 30), ("HD189thermo", 30), ("HD189cho", 30), ("EarthS", 30)]
 LOCKSTEP = [p for p in LOCKSTEP if have(p[0], "step%04d.npz" % p[1]) and have(p[0], "step0000.npz")]
 
 

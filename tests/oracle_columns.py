@@ -54,9 +54,9 @@ class OracleColumns(object):
                                  zero_delta_row0=o["zero_delta_row0"], delta_zero_sp=o["delta_zero_sp"], gas_indx_mix=self.gas_indx)
         return res["sol"][None], res["ymix"][None], np.array([res["delta"]]), np.zeros(1, dtype=np.int32)
 
-    def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None):
+    def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None, mtol=None):
         res = self.o.clip_loss(np.asarray(y).reshape(self.nz, self.ni), np.asarray(ymix_in).reshape(self.nz, self.ni), compo, pos_cut,
-                               nega_cut, self.opts["mtol"] if self.opts else 0.0, gas_indx=self.gas_indx, atom_skip=atom_skip)
+                               nega_cut, mtol if mtol is not None else (self.opts["mtol"] if self.opts else 0.0), gas_indx=self.gas_indx, atom_skip=atom_skip)
         asum = res["atom_sum"]
         if atom_skip is not None and atom_sum is not None:
             asum = np.where(np.asarray(atom_skip, dtype=bool), np.ravel(atom_sum), asum)

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _abi.load()
     for name in _header_symbols():
         assert hasattr(lib, name), name
-    assert lib.vk_abi_version() == 2
+    assert lib.vk_abi_version() == 3
 
 
 def test_no_cpu_fallback():

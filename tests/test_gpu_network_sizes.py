@@ -1,20 +1,16 @@
-"""GPU check staged for the first gpurun of the next round (NOT collected by pytest yet: it has never run on a GPU, and a faulting
-kernel would poison the CUDA context of the whole `-m gpu` session).  The chemistry kernels (rhs_warp_kernel, lhs_ml_kernel / lhs_kernel)
-have only ever executed the four BASELINE networks + the ion test network (ni <= 93, padded block 72 / 96); the reference ships networks
-up to ni = 99 (SNCHO_full_photo_network.txt - the one cfg_examples/vulcan_cfg_Earth.py names - and the DMS network, ni = 97), which
-take the padded block size 120 and may take the single-layer lhs fallback (shared-memory budget).  This script runs seeded random
-networks of every size class through eval_rhs / eval_lhs / ros2_solve on cuda:0 and compares with the oracle (oracle/ is the checker,
-as in tests/).     gpurun -- 'timeout 300 python scripts/gpu_network_sizes.py'
-Once green: move the body into tests/test_gpu_properties.py as a parametrised test."""
-import os
-import sys
+"""Random networks of every size class through the chemistry kernels + one Ros2 step on the device (round-1 staging script
+scripts/gpu_network_sizes.py, now a parametrised -m gpu test).  The fixtures cover ni = 41, 65, 69, 71, 93, 99; the reference ships
+networks up to ni = 99 and the kernels are instantiated up to the padded block size 120, so seeded random networks fill the gaps:
+chemdf / diffdf / couplings bit-identical to the oracle, blocks to rounding, one small step to 1e-10."""
 import numpy as np
-REPO = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "tests")); sys.path.insert(0, os.path.join(REPO, "oracle"))
-from helpers import Case                      # noqa: E402
-from oracle import Oracle                     # noqa: E402
-from vulcan_b200 import _abi                  # noqa: E402
-from vulcan_b200.network import Network       # noqa: E402
+import pytest
+
+from helpers import Case
+from oracle import Oracle
+from vulcan_b200 import _abi
+from vulcan_b200.network import Network
+
+pytestmark = pytest.mark.gpu
 
 R = 1.0 + 1.0 / 2 ** 0.5
 
@@ -92,8 +88,6 @@ def check(ni, seed=0, ncol=3):
     return ok_chem and ok_diff and ok_cpl and e_lhs < 1e-13 and e_sol < 1e-10 and not status.any()
 
 
-if __name__ == "__main__":
-    sizes = [int(a) for a in sys.argv[1:]] or [20, 41, 56, 74, 93, 97, 99, 110, 120]
-    res = [check(ni) for ni in sizes]
-    print("ALL OK" if all(res) else "FAILURES: %s" % [s for s, r in zip(sizes, res) if not r])
-    sys.exit(0 if all(res) else 1)
+@pytest.mark.parametrize("ni", [20, 41, 56, 74, 93, 97, 99, 110, 120])
+def test_random_network_of_size(ni):
+    assert check(ni)

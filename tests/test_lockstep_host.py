@@ -8,8 +8,7 @@ from lockstep import LOCKSTEP, check_ion_photolysis, lockstep, long_trajectory
 from oracle_columns import oracle_backed_abi
 
 
-# HD189nomol (use_moldiff = False), EarthS (the shipped Earth cfg's own network, ni = 99): CPU only for now, see helpers.NOMOL_CASES
-HOST_LOCKSTEP = LOCKSTEP + [p for p in [("HD189nomol", 30), ("HD189vz", 30), ("JupiterVz", 30), ("JupiterVmVz", 30), ("HD189thermo", 30), ("HD189cho", 30), ("EarthS", 30)] if have(p[0], "step0030.npz") and have(p[0], "step0000.npz")]
+HOST_LOCKSTEP = LOCKSTEP
 
 
 @pytest.mark.parametrize("tag,nstep", HOST_LOCKSTEP, ids=["%s-%d" % p for p in HOST_LOCKSTEP])

@@ -4,13 +4,13 @@ REFERENCE (oracle/dump_fixtures.py, PYTHONHASHSEED=0).  The reference ships no t
 import numpy as np
 import pytest
 
-from helpers import CASES, NOMOL_CASES, PHOTO_CASES, PHOTO_CASES_CPU_ONLY, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
+from helpers import CASES, PHOTO_CASES, Case, case_id, have, oracle_step, step_opts, photo_tables, ulp_diff
 from oracle import Oracle
 
 R = 1. + 1. / 2. ** 0.5
 
 
-@pytest.fixture(scope="module", params=CASES + NOMOL_CASES, ids=case_id)
+@pytest.fixture(scope="module", params=CASES, ids=case_id)
 def case(request):
     tag, step = request.param
     if not have(tag, "step%04d.npz" % step):
@@ -170,7 +170,7 @@ def test_clip_loss(case):
     assert np.allclose(loss, case.fx["atom_loss"], rtol=1e-12, atol=1e-300)
 
 
-@pytest.mark.parametrize("tag,step", PHOTO_CASES + PHOTO_CASES_CPU_ONLY, ids=[case_id(p) for p in PHOTO_CASES + PHOTO_CASES_CPU_ONLY])
+@pytest.mark.parametrize("tag,step", PHOTO_CASES, ids=[case_id(p) for p in PHOTO_CASES])
 def test_photolysis(tag, step):
     """compute_tau / compute_flux / compute_J (op.py:2580-2786): two consecutive updates from a zeroed diffuse field.
     The reference sums species in Python-set order (hash dependent), the oracle in sorted order -> rounding level."""

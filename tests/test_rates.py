@@ -11,8 +11,8 @@ import pytest
 
 from helpers import GOLD, load_network
 
-TAGS_CPU = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion", "EarthS"]    # EarthS (SNCHO_full, ni = 99): oracle only for now
-TAGS = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion"]      # the last one: ion test network (ionisation rows are zero at set-up like photolysis rows)
+TAGS = ["HD189", "Jupiter", "Earth", "HD209S", "HD189ion", "EarthS"]      # HD189ion: ion test network (ionisation rows are zero at set-up like photolysis rows); EarthS: SNCHO_full, ni = 99
+TAGS_CPU = TAGS
 LOW_T = {"Jupiter": True}            # cfg_examples/vulcan_cfg_Jupiter.py:7
 
 

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libvulcan_b200_trace.so" if os.environ.get("VK_TRACE") else "libvulcan_b200.so")
+LIB_PATH = os.path.join(HERE, "_lib", "libvulcan_b200.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -25,6 +25,7 @@ SYMBOLS = [
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
     "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
+    "vk_debug_time_kernel",
 ]
 
 
@@ -104,7 +105,7 @@ def load():
     lib.vk_set_k_rows.argtypes = [_vp, C.c_int, _ip, _dp]
     lib.vk_set_step_opts.argtypes = [_vp, C.POINTER(StepOpts)]
     lib.vk_ros2_solve.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]
-    lib.vk_clip_loss.argtypes = [_vp, _dp, _dp, _dp, C.c_int, _dp, _bp, C.c_double, C.c_double, _dp, _dp, _dp, _ip]
+    lib.vk_clip_loss.argtypes = [_vp, _dp, _dp, _dp, C.c_int, _dp, _bp, C.c_double, C.c_double, C.c_double, _dp, _dp, _dp, _ip]
     lib.vk_eval_rhs.argtypes = [_vp, _dp, _dp, _dp]
     lib.vk_eval_lhs.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
     lib.vk_blocktri_solve.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp, C.c_int, _ip]
@@ -122,6 +123,7 @@ def load():
     lib.vk_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.vk_device_buffers.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
     lib.vk_stream.argtypes = [_vp, C.POINTER(_vp)]
+    lib.vk_debug_time_kernel.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -325,7 +327,8 @@ class Columns(object):
             assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.size == self.ncol * self.nz * self.ni
         check(self.lib.vk_ros2_solve(self.handle, dptr(y), dptr(ymix), dptr(dt), dptr(sol), dptr(ymix_out), dptr(delta), iptr(status)))
 
-    def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None):
+    def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None, mtol=None):
+        """mtol: vulcan_cfg.mtol of the clip mask (op.py:2459); None = the value last given to set_step_opts"""
         y = self._shape(y, (self.nz, self.ni)).copy()
         ymix_in = self._shape(ymix_in, (self.nz, self.ni))
         compo = f64(compo)
@@ -337,7 +340,8 @@ class Columns(object):
         anyneg = np.zeros(self.ncol, dtype=np.int32)
         sk = None if atom_skip is None else u8(atom_skip)
         check(self.lib.vk_clip_loss(self.handle, dptr(y), dptr(ymix_in), dptr(ymo), na, dptr(compo), bptr(sk),
-                                    float(pos_cut), float(nega_cut), dptr(asum), dptr(sm), dptr(ng), iptr(anyneg)))
+                                    float(pos_cut), float(nega_cut), -1.0 if mtol is None else float(mtol), dptr(asum), dptr(sm),
+                                    dptr(ng), iptr(anyneg)))
         return dict(y=y, ymix=ymo, atom_sum=asum, small_y=sm, nega_y=ng, any_negative=anyneg)
 
     # ---------------------------------------------------------------- components
@@ -410,6 +414,12 @@ class Columns(object):
         a, b = C.c_float(0), C.c_float(0)
         check(self.lib.vk_last_kernel_ms(self.handle, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def time_kernel(self, which, reps=3):
+        """vk_debug_time_kernel: average ms of one kernel of the step on the resident state (0 lhs, 1 rhs, 2 factor, 4 solve)"""
+        ms = C.c_float(0)
+        check(self.lib.vk_debug_time_kernel(self.handle, int(which), int(reps), C.byref(ms)))
+        return ms.value
 
     # ---------------------------------------------------------------- device-resident ensemble driver
     def ens_setup(self, rtol, loss_eps, dt_min, dt_max, dt_var_min, dt_var_max, pos_cut, nega_cut, compo, atom_ini, n_0):

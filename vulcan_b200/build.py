@@ -10,8 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
-TRACE = bool(os.environ.get("VK_TRACE"))
-LIB = os.path.join(LIBDIR, "libvulcan_b200_trace.so" if TRACE else "libvulcan_b200.so")
+LIB = os.path.join(LIBDIR, "libvulcan_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = {"vk_api.cu": [], "vk_chem.cu": ["-fmad=false"], "vk_step.cu": ["-fmad=false"], "vk_photo.cu": ["-fmad=false"],
@@ -33,10 +32,10 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, src.replace(".cu", "_trace.o" if TRACE else ".o"))
+        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-DVK_TRACE"] if TRACE else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -2,6 +2,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 
 #include "vk_internal.cuh"
 
@@ -13,6 +15,20 @@ int cuda_fail(cudaError_t e, const char *what)
 {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
     return VK_ERR_CUDA;
+}
+
+int ensure_smem(const void *func, int device, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    if (bytes <= 48 * 1024) return VK_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = done[std::make_pair(func, device)];
+    if (bytes > have) {
+        VK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    return VK_OK;
 }
 
 int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *ymix_out_dev, int na, const double *compo_dev,
@@ -312,6 +328,9 @@ void vk_column_destroy(vk_column *c)
     for (double *v : vecs) if (v) cudaFree(v);
     if (c->status) cudaFree(c->status);
     if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->clip_d) cudaFree(c->clip_d);
+    if (c->clip_i) cudaFree(c->clip_i);
+    if (c->clip_h) cudaFreeHost(c->clip_h);
     free_list(c->atm_allocs);
     free_list(c->opt_allocs);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -518,47 +537,52 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
 }
 
 int vk_clip_loss(vk_column *c, double *y, const double *ymix_in, double *ymix_out, int na, const double *compo,
-                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double *atom_sum, double *small_y,
+                 const unsigned char *atom_skip, double pos_cut, double nega_cut, double mtol, double *atom_sum, double *small_y,
                  double *nega_y, int *any_negative)
 {
     int rc = ready(c);
     if (rc) return rc;
-    if (!y || !ymix_in || !ymix_out || !compo || !atom_sum || !small_y || !nega_y || !any_negative || na < 1) { set_error("null buffer"); return VK_ERR_INVALID; }
+    if (!y || !ymix_in || !ymix_out || !compo || !atom_sum || !small_y || !nega_y || !any_negative || na < 1 || na > 8) { set_error("null buffer / na out of range"); return VK_ERR_INVALID; }
     const size_t nv = (size_t)c->ncol * c->nz * c->ni;
-    std::vector<void *> tmp;
-    const double *dcompo = nullptr, *dsmall = nullptr, *dnega = nullptr;
-    const unsigned char *dskip = nullptr;
-    double *dasum = nullptr; int *dneg = nullptr;
-    rc = dev_copy(tmp, compo, (size_t)c->ni * na, &dcompo);
-    if (rc == VK_OK && atom_skip) rc = dev_copy(tmp, atom_skip, (size_t)na, &dskip);
-    if (rc == VK_OK) rc = dev_copy(tmp, small_y, (size_t)c->ncol, &dsmall);
-    if (rc == VK_OK) rc = dev_copy(tmp, nega_y, (size_t)c->ncol, &dnega);
-    cudaError_t e = cudaSuccess;
-    if (rc == VK_OK) {
-        e = cudaMalloc((void **)&dasum, sizeof(double) * c->ncol * na);
-        if (e == cudaSuccess) { tmp.push_back(dasum); e = cudaMemcpy(dasum, atom_sum, sizeof(double) * c->ncol * na, cudaMemcpyHostToDevice); }
-        if (e == cudaSuccess) e = cudaMalloc((void **)&dneg, sizeof(int) * c->ncol);
-        if (e == cudaSuccess) tmp.push_back(dneg);
-        // sol / ymix buffers double as staging for the clip
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->sol, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(c->ymix, ymix_in, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "vk_clip_loss staging");
+    // persistent scratch (one allocation per handle, not per call): compo [ni][8] | atom_sum [ncol][8] | small, nega [ncol] | skip [8] | anyneg [ncol]
+    const size_t n_d = (size_t)c->ni * 8 + (size_t)c->ncol * 8 + 2 * (size_t)c->ncol;
+    if (!c->clip_d) {
+        VK_CUDA(cudaMalloc((void **)&c->clip_d, sizeof(double) * n_d));
+        cudaError_t e = cudaMalloc((void **)&c->clip_i, sizeof(int) * ((size_t)c->ncol + 2));
+        if (e == cudaSuccess) e = cudaMallocHost((void **)&c->clip_h, sizeof(double) * n_d + sizeof(int) * ((size_t)c->ncol + 2));
+        if (e != cudaSuccess) { cudaFree(c->clip_d); c->clip_d = nullptr; if (c->clip_i) cudaFree(c->clip_i); c->clip_i = nullptr; return cuda_fail(e, "vk_clip_loss scratch"); }
     }
-    if (rc == VK_OK)
-        rc = launch_clip(c, c->sol, c->ymix, c->ymix_out, na, dcompo, dskip, pos_cut, nega_cut, dasum, const_cast<double *>(dsmall),
-                         const_cast<double *>(dnega), dneg);
-    if (rc == VK_OK) {
-        e = cudaMemcpyAsync(y, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ymix_out, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(atom_sum, dasum, sizeof(double) * c->ncol * na, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(small_y, dsmall, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(nega_y, dnega, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(any_negative, dneg, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "vk_clip_loss readback");
-    }
-    for (void *p : tmp) cudaFree(p);
-    return rc;
+    double *d_compo = c->clip_d, *d_asum = d_compo + (size_t)c->ni * 8, *d_small = d_asum + (size_t)c->ncol * 8, *d_nega = d_small + c->ncol;
+    int *d_neg = c->clip_i + 2;
+    unsigned char *d_skip = reinterpret_cast<unsigned char *>(c->clip_i);
+    double *h = c->clip_h, *h_compo = h, *h_asum = h_compo + (size_t)c->ni * 8, *h_small = h_asum + (size_t)c->ncol * 8, *h_nega = h_small + c->ncol;
+    int *h_i = reinterpret_cast<int *>(h + n_d);
+    memcpy(h_compo, compo, sizeof(double) * c->ni * na);
+    memcpy(h_asum, atom_sum, sizeof(double) * c->ncol * na);
+    memcpy(h_small, small_y, sizeof(double) * c->ncol);
+    memcpy(h_nega, nega_y, sizeof(double) * c->ncol);
+    memset(h_i, 0, 8);
+    if (atom_skip) memcpy(h_i, atom_skip, (size_t)na);
+    VK_CUDA(cudaMemcpyAsync(c->clip_d, h, sizeof(double) * n_d, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->clip_i, h_i, 8, cudaMemcpyHostToDevice, c->stream));
+    // sol / ymix buffers double as staging for the clip
+    VK_CUDA(cudaMemcpyAsync(c->sol, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->ymix, ymix_in, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
+    const double keep_mtol = c->opts.mtol;
+    if (mtol >= 0) c->opts.mtol = mtol;              // op.py:2459 reads vulcan_cfg.mtol; negative: the value of vk_set_step_opts
+    rc = launch_clip(c, c->sol, c->ymix, c->ymix_out, na, d_compo, atom_skip ? d_skip : nullptr, pos_cut, nega_cut, d_asum, d_small, d_nega, d_neg);
+    c->opts.mtol = keep_mtol;
+    if (rc) return rc;
+    VK_CUDA(cudaMemcpyAsync(y, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(ymix_out, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(h_asum, d_asum, sizeof(double) * ((size_t)c->ncol * 8 + 2 * (size_t)c->ncol), cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaMemcpyAsync(h_i + 2, d_neg, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(atom_sum, h_asum, sizeof(double) * c->ncol * na);
+    memcpy(small_y, h_small, sizeof(double) * c->ncol);
+    memcpy(nega_y, h_nega, sizeof(double) * c->ncol);
+    memcpy(any_negative, h_i + 2, sizeof(int) * c->ncol);
+    return VK_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -681,7 +705,7 @@ int vk_stream(vk_column *c, void **cuda_stream)
 
 }  // extern "C"
 
-// debug / profiling aid (not part of the public header): time `reps` launches of one kernel of the step on the resident state.
+// profiling aid (declared in the public header): time `reps` launches of one kernel of the step on the resident state.
 // which: 0 = lhs, 1 = rhs (stage 1), 2 = factor, 3 = solve (backward only), 4 = solve (forward + backward)
 extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms)
 {

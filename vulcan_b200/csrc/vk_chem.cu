@@ -1,8 +1,8 @@
 // Chemistry + transport kernels: one thread block per (column, layer).
 //
-//   rhs_kernel : chem_funs.chemdf (make_chem_funs.py:113-430) + ODESolver.diffdf / diffdf_settling / diffdf_no_mol
+//   rhs_warp_kernel : chem_funs.chemdf (make_chem_funs.py:113-430) + ODESolver.diffdf / diffdf_settling / diffdf_no_mol
 //                (op.py:1438-1791), optionally the Ros2 stage-2 right-hand side  f(y+k1/r) - 2/(r h) k1 (op.py:2917-2928)
-//   lhs_kernel : chem_funs.neg_symjac block (make_chem_funs.py:653-717) + lhs_jac_tot / _settling / _no_mol
+//   lhs_ml_kernel : chem_funs.neg_symjac block (make_chem_funs.py:653-717) + lhs_jac_tot / _settling / _no_mol
 //                (op.py:1973-2364):  D = 1/(r h) I - J_chem - J_transport, up/dn = the diagonal couplings
 //   atm_pre_kernel : the parts of the transport stencil that depend on the atmosphere only (molecular-diffusion quotients,
 //                thermal/gravity brackets, settling terms) evaluated ONCE per vk_set_atm with the reference's operation
@@ -254,221 +254,6 @@ struct RhsArgs {
     double *out_sum, *out_chem, *out_diff;  // any may be NULL; out_sum = chem + diff (stage 2: - 2/(r h) k1)
     const unsigned char *fix_mask;          // rows forced to zero (op.py:2896-2925)
 };
-
-#define RHS_NT 256
-#define RHS_TR0 128      // first thread of the transport group
-
-__global__ void __launch_bounds__(RHS_NT) rhs_kernel(RhsArgs A)
-{
-    extern __shared__ double sm[];
-    const int ni = A.net.ni, nr = A.net.nr, nz = A.nz;
-    const int col = blockIdx.x / nz, j = blockIdx.x % nz;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double *ym = sm;                    // y[j-1]  (ni+2)
-    double *y0 = ym + (ni + 2);         // y[j]    yx: [ni] = M, [ni+1] = 1.0
-    double *yp = y0 + (ni + 2);         // y[j+1]
-    double *kz = yp + (ni + 2);         // k[j][0..nr]
-    double *rate = kz + (nr + 2);       // rate[0..nr]  (phase 2: rate[odd j] <- rate[j] - rate[j+1])
-    double *tmp = rate + (nr + 2);      // 3*ni scratch for gas-compacted sums
-    double *ysum = tmp + 3 * ni;        // [4]
-    double *dsp = ysum + 4;             // [ni] transport tendency per species
-    LayerScal *S = reinterpret_cast<LayerScal *>(dsp + ni + (ni & 1));
-
-    const size_t base = ((size_t)col * nz + j) * ni;
-    const double rr = 1. + 1. / sqrt(2.);
-    for (int i = tid; i < ni; i += nt) {
-        double v0 = A.y[base + i];
-        double vm = (j > 0) ? A.y[base - ni + i] : 0.0;
-        double vp = (j < nz - 1) ? A.y[base + ni + i] : 0.0;
-        if (A.k1) {   // yk2 = y + k1/r   (op.py:2917)
-            v0 = v0 + A.k1[base + i] / rr;
-            if (j > 0) vm = vm + A.k1[base - ni + i] / rr;
-            if (j < nz - 1) vp = vp + A.k1[base + ni + i] / rr;
-            if (A.yk2_out) A.yk2_out[base + i] = v0;
-        }
-        y0[i] = v0; ym[i] = vm; yp[i] = vp;
-    }
-    if (tid == 0) { y0[ni] = A.atm.M[col * A.atm.csz + j]; y0[ni + 1] = 1.0; }
-    const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
-    for (int i = tid; i <= nr; i += nt) kz[i] = kg[i];
-    __syncthreads();
-
-    // ---- phase 1: rates of progress rate[i] = k[i]*f0*f1*f2*f3 (written order); layer sums (numpy pairwise order)
-    for (int i = tid + 1; i <= nr; i += nt) {
-        uchar4 f = A.net.rate_fac[i];
-        double v = kz[i];
-        if (!A.net.has_pow) {
-            v = v * y0[f.x]; v = v * y0[f.y]; v = v * y0[f.z]; v = v * y0[f.w];   // padding slots multiply by exactly 1.0
-        } else {
-            uchar4 p = A.net.rate_pow[i];
-            unsigned char ff[4] = {f.x, f.y, f.z, f.w}, pp[4] = {p.x, p.y, p.z, p.w};
-            for (int q = 0; q < 4; q++) {
-                double b = y0[ff[q]];
-                double t = (pp[q] == 1) ? b : ((pp[q] == 2) ? b * b : pow(b, (double)pp[q]));
-                v = v * t;
-            }
-        }
-        rate[i] = v;
-    }
-    if (tid >= RHS_NT - 32) {      // last warp: the three layer sums, 8 lanes each, numpy association (vk_device_math.cuh)
-        const int lane_ = tid - (RHS_NT - 32), q = lane_ >> 3;
-        const int jj = j - 1 + q;
-        const bool act = (q < 3) && jj >= 0 && jj < nz;
-        const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-        double sres;
-        if (A.atm.n_gas > 0) {     // np.sum(y[:,gas_indx], axis=1) is a plain left-to-right sum (see row_sum)
-            sres = 0.0;
-            if (act && (lane_ & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas, A.atm.gas_indx, tmp);
-        } else {
-            sres = np_pairwise_group8(row, ni, act);
-        }
-        if (act && (lane_ & 7) == 0) ysum[q] = sres;
-    }
-    __syncthreads();
-
-    // ---- phase 2: v_j = rate[j] - rate[j+1] for every pair; one thread: the layer scalars of the stencil
-    for (int p = tid; 2 * p + 1 <= nr; p += nt) rate[2 * p + 1] = rate[2 * p + 1] - rate[2 * p + 2];
-    const AtmLayer L = atm_at(A.atm, col);
-    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
-    const int vmm = A.atm.use_vm_mol;
-    if (tid >= RHS_NT - 3) {       // three threads: A, B, C of the eddy + advection stencil from the precomputed prefactors
-        const int q = tid - (RHS_NT - 3);
-        const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
-        const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-        const double sp = ysp + ys0, smm = ys0 + ysm;
-        if (q == 0) {
-            double v;
-            if (j == 0) v = ls[0] * sp / 2. / ys0;
-            else if (j == nz - 1) v = ls[0] * smm / 2. / ys0;
-            else v = ls[0] * (ls[1] * sp / 2. + ls[2] * smm / 2.) / ys0;
-            v += ls[5];
-            S->Aa = v; S->m1 = ls[8]; S->sp = sp; S->sm = smm; S->ys0 = ys0; S->ysp = ysp; S->ysm = ysm;
-        } else if (q == 1) {
-            double v = 0.0;
-            if (j < nz - 1) { v = ls[3] * sp / 2. / ysp; v += ls[6]; }
-            S->Bb = v;
-        } else {
-            double v = 0.0;
-            if (j > 0) { v = ls[4] * smm / 2. / ysm; v += ls[7]; }
-            S->Cc = v;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 3: chemistry sums (threads 0..ni-1) run beside the transport stencil (threads RHS_TR0..RHS_TR0+ni-1)
-    double chem = 0.0;
-    if (tid < ni) {
-        // left-to-right sum of coef * v_j in network order (make_chem_funs.py:258-285).  The additions form one dependent
-        // chain (order = parity); descriptors and rates are fetched four terms ahead so that only the DADD latency remains.
-        const int q0 = A.net.rhs_ptr[tid], q1 = A.net.rhs_ptr[tid + 1];
-        int q = q0;
-        if (q < q1) {
-            const int t = A.net.rhs_term[q];
-            chem = (double)((signed char)(t & 0xff)) * rate[t >> 8];
-            q++;
-        }
-        for (; q + 4 <= q1; q += 4) {
-            const int t0 = A.net.rhs_term[q], t1 = A.net.rhs_term[q + 1], t2 = A.net.rhs_term[q + 2], t3 = A.net.rhs_term[q + 3];
-            const double a0 = (double)((signed char)(t0 & 0xff)) * rate[t0 >> 8];
-            const double a1 = (double)((signed char)(t1 & 0xff)) * rate[t1 >> 8];
-            const double a2 = (double)((signed char)(t2 & 0xff)) * rate[t2 >> 8];
-            const double a3 = (double)((signed char)(t3 & 0xff)) * rate[t3 >> 8];
-            chem = chem + a0; chem = chem + a1; chem = chem + a2; chem = chem + a3;
-        }
-        for (; q < q1; q++) {
-            const int t = A.net.rhs_term[q];
-            chem = chem + (double)((signed char)(t & 0xff)) * rate[t >> 8];
-        }
-    } else if (tid >= RHS_TR0 && tid < RHS_TR0 + ni) {
-        const int i = tid - RHS_TR0;
-        const LayerScal s = *S;
-        const double *dzi = L.dzi;
-        const AtmPre &P = A.atm.pre;
-        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
-        double diff;
-        if (j == 0) {
-            if (md) {
-                double Ai = P.QC[pb] * s.sp / 2. / s.ys0;
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
-                if (vmm) {
-                    double Cx = 0.0;
-                    vm_rhs_adv(P, pb, 0, st, Ai, Bi, Cx);
-                } else {
-                    Ai = Ai + P.TA[pb];
-                    Bi = Bi + P.TB[pb];
-                    if (st) {
-                        Ai = Ai - P.SA[pb];
-                        Bi = Bi - P.SB[pb];
-                    }
-                }
-                diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
-            } else {
-                diff = s.Aa * y0[i] + s.Bb * yp[i];
-            }
-            if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
-        } else if (j == nz - 1) {
-            if (md) {
-                double Ai = P.QB[pb] * s.sm / 2. / s.ys0;
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (vmm) {
-                    double Bx = 0.0;
-                    vm_rhs_adv(P, pb, 2, st, Ai, Bx, Ci);
-                } else {
-                    Ai = Ai - P.TA[pb];
-                    Ci = Ci - P.TC[pb];
-                    if (st) {
-                        Ai = Ai + P.SA[pb];
-                        Ci = Ci + P.SC[pb];
-                    }
-                }
-                diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
-            } else {
-                diff = s.Aa * y0[i] + s.Cc * ym[i];
-            }
-            if (A.atm.use_topflux) diff += L.top_flux[i] / dzi[nz - 2];
-        } else {
-            double t1 = s.Aa * y0[i] + s.Bb * yp[i] + s.Cc * ym[i];
-            if (md) {
-                double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (vmm) {
-                    vm_rhs_adv(P, pb, 1, st, Ai, Bi, Ci);
-                } else {
-                    if (st) {
-                        Ai = Ai - P.SA[pb];
-                        Bi = Bi - P.SB[pb];
-                        Ci = Ci + P.SC[pb];
-                    }
-                    Ai += P.TA[pb];
-                    Bi += P.TB[pb];
-                    Ci += -P.TC[pb];
-                }
-                double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
-                diff = t1 + t2;
-            } else {
-                diff = t1;
-            }
-        }
-        dsp[i] = diff;
-    }
-    __syncthreads();
-    if (tid < ni) {
-        const int i = tid;
-        const double diff = dsp[i];
-        if (A.out_chem) A.out_chem[base + i] = chem;
-        if (A.out_diff) A.out_diff[base + i] = diff;
-        if (A.out_sum) {
-            double f = chem + diff;                                   // op.py:2892 / 2918
-            if (A.fix_mask && A.fix_mask[base + i]) f = 0.0;          // op.py:2904, 2924
-            if (A.k1) {
-                double c = 2. / (rr * A.dt[col]);
-                f = f - c * A.k1[base + i];                           // op.py:2928
-            }
-            A.out_sum[base + i] = f;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------------
 // rhs_warp_kernel: ONE WARP per (column, layer), RHS_WPB layers per block, no block-wide barrier after the tables are staged.
@@ -731,201 +516,8 @@ struct LhsArgs {
     const unsigned char *fix_mask;
 };
 
-__global__ void __launch_bounds__(256, 3) lhs_kernel(LhsArgs A)
-{
-    extern __shared__ double sm[];
-    const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
-    const int col = blockIdx.x / nz, j = blockIdx.x % nz;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double *ym = sm;
-    double *y0 = ym + (ni + 2);
-    double *yp = y0 + (ni + 2);
-    double *kz = yp + (ni + 2);
-    double *tmp = kz + (nr + 2);
-    double *ysum = tmp + 3 * ni;
-    double *part = ysum + 4;                                   // partial sums of split Jacobian entries
-    double *blk = part + A.net.n_part + (A.net.n_part & 1);    // ld*ld block
-
-    const size_t base = ((size_t)col * nz + j) * ni;
-    for (int i = tid; i < ni; i += nt) {
-        y0[i] = A.y[base + i];
-        ym[i] = (j > 0) ? A.y[base - ni + i] : 0.0;
-        yp[i] = (j < nz - 1) ? A.y[base + ni + i] : 0.0;
-    }
-    if (tid == 0) { y0[ni] = A.atm.M[col * A.atm.csz + j]; y0[ni + 1] = 1.0; }
-    const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
-    for (int i = tid; i <= nr; i += nt) kz[i] = kg[i];
-    for (int q = tid; q < ld * ld; q += nt) blk[q] = 0.0;
-    __syncthreads();
-    if (tid >= 224) {              // last warp: the three layer sums, 8 lanes each, numpy association
-        const int lane_ = tid - 224, q = lane_ >> 3;
-        const int jj = j - 1 + q;
-        const bool act = (q < 3) && jj >= 0 && jj < nz;
-        const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
-        double sres;
-        if (A.atm.n_gas_lhs > 0) {
-            sres = 0.0;
-            if (act && (lane_ & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, tmp);
-        } else {
-            sres = np_pairwise_group8(row, ni, act);
-        }
-        if (act && (lane_ & 7) == 0) ysum[q] = sres;
-    }
-    // ---- chemical Jacobian: segments of <= 16 terms, sorted by length so that the 32 lanes of a warp carry equal work
-    for (int s = tid; s < A.net.n_seg; s += nt) {
-        const uint4 sg = A.net.jac_seg[s];     // x = row | col << 16, y = first term, z = n terms | slot << 16
-        const int q0 = (int)sg.y, q1 = q0 + (int)(sg.z & 0xffff);
-        double acc = 0.0;
-        for (int q = q0; q < q1; q++) {
-            const uint2 t = A.net.jac_term[q];
-            const double coef = (double)((signed char)((t.x >> 16) & 0xff));
-            double term = coef * kz[t.x & 0xffff];
-            term = term * y0[t.y & 0xff];
-            term = term * y0[(t.y >> 8) & 0xff];
-            term = term * y0[(t.y >> 16) & 0xff];
-            acc += term;
-        }
-        const unsigned slot = sg.z >> 16;
-        if (slot == 0xffffu) blk[(sg.x & 0xffff) * ld + (sg.x >> 16)] = -acc;
-        else part[slot] = acc;
-    }
-    __syncthreads();
-    for (int m = tid; m < A.net.n_multi; m += nt) {          // entries that were split: fixed-order sum of their partials
-        const uint2 me = A.net.jac_multi[m];                 // x = row | col << 16, y = first slot | n << 16
-        const int s0 = (int)(me.y & 0xffff), n = (int)(me.y >> 16);
-        double acc = 0.0;
-        for (int q = 0; q < n; q++) acc += part[s0 + q];
-        blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
-    }
-    __syncthreads();
-    // ---- diagonal: c0 + negJ_ss - transport;  couplings up/dn   (op.py:1998-2040)
-    const AtmLayer L = atm_at(A.atm, col);
-    const double *dzi = L.dzi;
-    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
-    const int vmm = A.atm.use_vm_mol;
-    const double rr = 1. + 1. / sqrt(2.);
-    const double c0 = 1. / (rr * A.dt[col]);
-    const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-    const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
-    // species-independent eddy + advection parts (three threads, one division each)
-    if (tid < 3) {
-        double v = 0.0;
-        if (j == 0) {
-            if (tid == 0) v = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
-            if (tid == 1) v = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
-        } else if (j == nz - 1) {
-            if (tid == 0) v = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
-            if (tid == 2) v = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
-        } else {
-            if (tid == 0) v = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
-            if (tid == 1) v = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
-            if (tid == 2) v = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
-        }
-        tmp[tid] = v;
-    }
-    __syncthreads();
-    const double eA = tmp[0], eB = tmp[1], eC = tmp[2];
-    const size_t vbase = ((size_t)col * nz + j) * ld;
-    const AtmPre &P = A.atm.pre;
-    for (int i = tid; i < ld; i += nt) {
-        if (i >= ni) {   // padding: decoupled identity rows keep the padded block invertible
-            blk[i * ld + i] = 1.0;
-            A.up[vbase + i] = 0.0;
-            A.dn[vbase + i] = 0.0;
-            continue;
-        }
-        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
-        double d = c0 + blk[i * ld + i];
-        double u = 0.0, l = 0.0;
-        if (j == 0) {
-            d -= eA;
-            u -= eB;
-            if (md) {
-                double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0);
-                double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp);
-                if (vmm) {
-                    double tx = 0.0;
-                    vm_lhs_adv(P, pb, 0, st, ta, tb, tx);
-                } else {
-                    ta = ta + P.TA[pb];
-                    tb = tb + P.TB[pb];
-                    if (st) {
-                        ta = ta - P.SA[pb];
-                        tb = tb - P.SB[pb];
-                    }
-                }
-                d -= ta;
-                if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
-                u -= tb;
-            } else {
-                if (A.atm.use_botflux) d -= -1. * L.bot_vdep[i] / dzi[0];
-            }
-        } else if (j == nz - 1) {
-            if (vmm && A.atm.n_diff_esc > 0) d -= vm_diff_lim(A.atm, L, i, y0[i]);   // before the stencil terms (op.py:2107)
-            d -= eA;
-            l -= eC;
-            if (md) {
-                double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0);
-                double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm);
-                if (vmm) {
-                    double tx = 0.0;
-                    vm_lhs_adv(P, pb, 2, st, ta, tx, tc);
-                } else {
-                    ta = ta - P.TA[pb];
-                    tc = tc - P.TC[pb];
-                    if (st) {
-                        ta = ta + P.SA[pb];
-                        tc = tc + P.SC[pb];
-                    }
-                }
-                d -= ta;
-                l -= tc;
-            }
-        } else {
-            d -= eA;
-            u -= eB;
-            l -= eC;
-            if (md) {
-                double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
-                double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
-                double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
-                if (vmm) {
-                    vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
-                } else {
-                    ta = ta + P.TA[pb];
-                    tb = tb + P.TB[pb];
-                    tc = tc - P.TC[pb];
-                    if (st) {
-                        ta = ta - P.SA[pb];
-                        tb = tb - P.SB[pb];
-                        tc = tc + P.SC[pb];
-                    }
-                }
-                d -= ta;
-                u -= tb;
-                l -= tc;
-            }
-        }
-        if (A.fix_mask && A.fix_mask[base + i]) {   // op.py:2903-2906: row -> 1/(r h) e_i
-            for (int t = 0; t < ni; t++) blk[i * ld + t] = 0.0;
-            d = c0; u = 0.0; l = 0.0;
-        }
-        blk[i * ld + i] = d;
-        A.up[vbase + i] = u;
-        A.dn[vbase + i] = l;
-    }
-    __syncthreads();
-    double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
-    if ((ld & 1) == 0) {
-        for (int q = tid; q < ld * ld / 2; q += nt)
-            reinterpret_cast<double2 *>(Dg)[q] = reinterpret_cast<const double2 *>(blk)[q];
-    } else {
-        for (int q = tid; q < ld * ld; q += nt) Dg[q] = blk[q];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
-// lhs_ml_kernel: the same block as lhs_kernel, restructured for throughput.
+// lhs_ml_kernel: chem_funs.neg_symjac block + lhs_jac_* diagonal and couplings.
 //  * One thread block walks `lpb` (1..30, chosen by the launcher) consecutive layers of a column; the network tables (distinct products, 16-bit term descriptors,
 //    segment schedule - 40 KB for NCHO) are staged in shared memory ONCE per block, so the per-term work never waits on L2.
 //  * The 5953 Jacobian terms of NCHO are coefficient x one of only 1603 distinct products k_r y_a y_b y_c: the products are formed
@@ -1261,11 +853,7 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     const RhsWarpSmem SL = rhs_warp_layout(c->ni, c->nr);
     const size_t smem = sizeof(double) * (size_t)RHS_WPB * SL.total + sizeof(uchar4) * (c->nr + 2) +
                         sizeof(unsigned short) * (a.net.n_rhs + 8) + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
-        VK_CUDA(cudaFuncSetAttribute(rhs_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    { int rc = ensure_smem((const void *)rhs_warp_kernel, c->net->device, smem); if (rc) return rc; }
     const int n_layers = c->ncol * c->nz;
     rhs_warp_kernel<<<(n_layers + RHS_WPB - 1) / RHS_WPB, RHS_WPB * 32, smem, c->stream>>>(a, n_layers);
     VK_CUDA(cudaGetLastError());
@@ -1277,34 +865,21 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     LhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
     a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask;
-    if (a.net.lhs_ml_ok) {
-        const LhsMlSmem SL = lhs_ml_layout(a.net, ld);
-        if (SL.total_bytes <= 227 * 1024) {
-            static int configured = 0;
-            if (SL.total_bytes > configured) {
-                VK_CUDA(cudaFuncSetAttribute(lhs_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SL.total_bytes));
-                configured = SL.total_bytes;
-            }
-            // layers per block: amortise the table staging (40 KB per block) but keep >= ~8 blocks per SM in the grid
-            int lpb = (int)(((long long)c->ncol * c->nz) / (8 * 148));
-            lpb = std::max(1, std::min(lpb, 30));
-            { const char *e = getenv("VK_LHS_LPB"); if (e) lpb = atoi(e); }
-            const int bpc = (c->nz + lpb - 1) / lpb;
-            static int dbg = -1;
-            if (dbg < 0) { const char *e = getenv("VK_LHS_DBG"); dbg = e ? atoi(e) : 0; }
-            lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
-            VK_CUDA(cudaGetLastError());
-            return VK_OK;
-        }
+    if (!a.net.lhs_ml_ok) {
+        set_error("network exceeds the packing limits of the Jacobian kernel (nr < 2048, ni < 127, < 8191 distinct products, coefficients in +-{1,2,3,4})");
+        return VK_ERR_UNSUPPORTED;
     }
-    const int np = c->net->d.n_part + (c->net->d.n_part & 1);
-    size_t smem = sizeof(double) * (3 * (c->ni + 2) + (c->nr + 2) + 3 * c->ni + 4 + np + (size_t)ld * ld) + 16;
-    static size_t configured = 0;
-    if (smem > configured) {
-        VK_CUDA(cudaFuncSetAttribute(lhs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    lhs_kernel<<<c->ncol * c->nz, 256, smem, c->stream>>>(a);
+    const LhsMlSmem SL = lhs_ml_layout(a.net, ld);
+    if (SL.total_bytes > 227 * 1024) { set_error("Jacobian kernel tables do not fit the shared memory of one SM"); return VK_ERR_UNSUPPORTED; }
+    { int rc = ensure_smem((const void *)lhs_ml_kernel, c->net->device, (size_t)SL.total_bytes); if (rc) return rc; }
+    // layers per block: amortise the table staging (40 KB per block) but keep >= ~8 blocks per SM in the grid
+    int lpb = (int)(((long long)c->ncol * c->nz) / (8 * 148));
+    lpb = std::max(1, std::min(lpb, 30));
+    { const char *e = getenv("VK_LHS_LPB"); if (e) lpb = atoi(e); }
+    const int bpc = (c->nz + lpb - 1) / lpb;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("VK_LHS_DBG"); dbg = e ? atoi(e) : 0; }
+    lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }

@@ -23,6 +23,11 @@ int cuda_fail(cudaError_t e, const char *what);
         if (_e != cudaSuccess) return vk::cuda_fail(_e, #call);    \
     } while (0)
 
+// opt-in to more than 48 KB of dynamic shared memory for `func`: the attribute belongs to the device's primary context, so it is
+// tracked per (function, device) - a process may drive several devices (Ros2 / DeviceNetwork / EnsembleRunner take `device`) and
+// PipelinedHostSolver launches from a thread pool (mutex inside)
+int ensure_smem(const void *func, int device, size_t bytes);
+
 // ---- compiled network on the device ---------------------------------------------------------------------------
 // factor slots are bytes: species index (< 254), ni = third body M, ni+1 = constant 1.0
 struct NetDev {
@@ -127,6 +132,9 @@ struct vk_column {
     size_t h_pin_bytes;
     PhotoState *photo;
     EnsState *ens;
+    // persistent scratch of vk_clip_loss (device doubles / ints + one pinned host mirror)
+    double *clip_d, *clip_h;
+    int *clip_i;
 };
 
 namespace vk {

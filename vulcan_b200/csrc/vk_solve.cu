@@ -159,13 +159,6 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-#ifdef VK_TRACE
-__device__ long long g_trace[128 * 8];
-#define TRACE(kk, ev, dep) do { if (j == 5 && lane == 0) { long long c_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c_) : "d"(dep)); g_trace[(kk) * 8 + (ev)] = c_; } } while (0)
-#else
-#define TRACE(kk, ev, dep) do { } while (0)
-#endif
-
 enum { VK_BAR_PANEL = 1, VK_BAR_TILE = 3, VK_BAR_RAW = 5, VK_BAR_COLS = 7 };   // + panel parity (not COLS)
 
 template <int NIP, int MINB>
@@ -291,7 +284,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     }
 
     for (int j = 0; j < nz; j++) {
-        if (w == 0) TRACE(100, 0, A[0][0]);
         double u0 = 0.0, u1 = 0.0;       // B fragments of my pivot-row tile of the coming panel
         if (w != 0) to_bfrag(A[0][0], A[0][1], g, t, u0, u1);
         auto panel = [&](auto ktc) {
@@ -300,7 +292,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
             const double *pb = pbuf + (kt % 3) * 64;
             bar_sync<VK_BAR_PANEL + par, NT>();           // raw panel columns + P of panel kt visible
             if (kt == 1 && tid == 0 && j + 1 < nz) prefetch(j + 1);   // every column warp has consumed dbuf / updn by now
-            if (w == (kt + 1) % NW) TRACE(kt, 0, u0);
             if (w == kt) {
                 // ---- panel columns: A_iK <- -A_iK P, A_KK <- P.  A operand = my own (x, y) pair, B operand = -P
                 const double b0 = -pb[(2 * t) * 8 + g], b1 = -pb[(2 * t + 1) * 8 + g];
@@ -321,12 +312,9 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                         *reinterpret_cast<double2 *>(Ft + (size_t)(8 * i) * (NIP + 2)) = make_double2(-A[i][0], -A[i][1]);
                 }
                 if constexpr (kt + 1 < NR) to_bfrag(A[kt + 1][0], A[kt + 1][1], g, t, u0, u1);
-                TRACE(kt, 6, A[0][0]);
             } else {
                 // ---- V = P A_Kw (new pivot rows of my columns)
-                if (kt == 3 && w == 4) TRACE(64, 0, u0);
                 const double2 pa = *reinterpret_cast<const double2 *>(pb + g * 8 + 2 * t);
-                if (kt == 3 && w == 4) TRACE(64, 1, pa.x);
                 double v0, v1;
                 dmma(v0, v1, pa.x, u0, 0.0, 0.0);
                 dmma(v0, v1, pa.y, u1, v0, v1);
@@ -334,11 +322,9 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                 if (a.F && w > kt)   // block LU by-product: V_Kw = P_K A_Kw right of the diagonal tile
                     *reinterpret_cast<double2 *>(a.F + (cbase + j) * (size_t)(NIP * (NIP + 2)) + (size_t)(8 * kt + g) * (NIP + 2) + c0) =
                         make_double2(v0, v1);
-                if (kt == 3 && w == 4) TRACE(64, 2, v0);
                 double nv0, nv1;
                 to_bfrag(v0, v1, g, t, nv0, nv1);
                 nv0 = -nv0; nv1 = -nv1;
-                if (kt == 3 && w == 4) TRACE(64, 3, nv1);
                 const double *mr = mraw + ((size_t)par * NIP + g) * 8 + 2 * t;
                 auto upd = [&](auto ic) {
                     constexpr int i = decltype(ic)::value;
@@ -363,7 +349,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                         *reinterpret_cast<double2 *>(hbuf + hp * 128 + g * 8 + 2 * t) = make_double2(A[kt + 1][0], A[kt + 1][1]);
                         *reinterpret_cast<double2 *>(hbuf + hp * 128 + 64 + g * 8 + 2 * t) = make_double2(A[kt + 2][0], A[kt + 2][1]);
                         bar_arrive<VK_BAR_TILE + hp, 64>();
-                        TRACE(kt, 1, A[kt + 2][0]);
                     }
                 }
 #pragma unroll
@@ -372,25 +357,18 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
                     const double2 m = *reinterpret_cast<const double2 *>(mr + i * 64);
                     dmma(A[i][0], A[i][1], m.x, nv0, A[i][0], A[i][1]);
                     dmma(A[i][0], A[i][1], m.y, nv1, A[i][0], A[i][1]);
-                    if (kt == 3 && w == 4 && i == 0) TRACE(64, 4, A[i][0]);
-                    if (kt == 3 && w == 4 && i == 1) TRACE(64, 5, A[i][0]);
-                    if (kt == 3 && w == 4 && i == 2) TRACE(64, 6, A[i][0]);
-                    if (kt == 3 && w == 4 && i == 8) TRACE(64, 7, A[i][0]);
                 }
                 if constexpr (kt + 1 < NR) {
                     if (w == kt + 1) {
                         publish_raw((kt + 1) & 1);
-                        TRACE(kt, 4, A[0][0]);
                     }
                 }
-                if (w == (kt + 3) % NW) TRACE(kt, 5, A[0][0]);
             }
         };
 #define VK_PANEL(N) if constexpr ((N) < NR) panel(std::integral_constant<int, (N)>{});
         VK_PANEL(0) VK_PANEL(1) VK_PANEL(2) VK_PANEL(3) VK_PANEL(4) VK_PANEL(5) VK_PANEL(6) VK_PANEL(7)
         VK_PANEL(8) VK_PANEL(9) VK_PANEL(10) VK_PANEL(11) VK_PANEL(12) VK_PANEL(13) VK_PANEL(14)
 #undef VK_PANEL
-        if (w == 0) TRACE(100, 3, A[0][0]);
         if (__syncthreads_or(bad)) {
             if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
             return;
@@ -417,7 +395,6 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         }
         if (more && w == 0) publish_raw(0);
         bar_sync<VK_BAR_COLS, NW * 32>();
-        if (w == 0) TRACE(100, 4, A[0][0]);
     }
 }
 
@@ -606,11 +583,7 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
 {
     using C = FactorCfg<NIP>;
     FactorArgs a{c->nz, c->ni, D, up, dn, F, status};
-    static bool attr_set = false;
-    if (!attr_set) {
-        VK_CUDA(cudaFuncSetAttribute(factor_kernel<NIP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_set = true;
-    }
+    { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB>, c->net->device, C::SMEM); if (rc) return rc; }
     factor_kernel<NIP, MINB><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
@@ -632,11 +605,7 @@ template <int NIP, int NBUF>
 static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 {
     using C = LuCfg<NIP, NBUF>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        VK_CUDA(cudaFuncSetAttribute(lu_solve_kernel<NIP, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        attr_set = true;
-    }
+    { int rc = ensure_smem((const void *)lu_solve_kernel<NIP, NBUF>, c->net->device, C::SMEM); if (rc) return rc; }
     lu_solve_kernel<NIP, NBUF><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
@@ -670,11 +639,3 @@ int launch_residual(vk_column *c, const double *D, const double *up, const doubl
 }
 
 }  // namespace vk
-
-
-#ifdef VK_TRACE
-extern "C" int vk_debug_trace(long long *out)
-{
-    return (int)cudaMemcpyFromSymbol(out, vk::g_trace, sizeof(long long) * 128 * 8);
-}
-#endif

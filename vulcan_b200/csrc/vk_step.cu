@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(256) clip_kernel(ClipArgs a)
     const int nz = a.nz, ni = a.ni, na = a.na;
     const int col = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     double *red = sm;                 // nt * (na + 2)
-    double *tmp = red + nt * (na + 2);// nt * ni?  (row sums use a per-thread scratch only when a gas mask is present)
     double *yc = a.y + (size_t)col * nz * ni;
     const double *ymc = a.ymix_in + (size_t)col * nz * ni;
     double small = 0.0, nega = 0.0;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(256) clip_kernel(ClipArgs a)
     }
     // ymix = y / sum_gas(y) per layer, numpy pairwise order
     for (int j = tid; j < nz; j += nt) {
-        double s = row_sum(yc + (size_t)j * ni, ni, a.n_gas, a.gas_indx, tmp + (size_t)tid * ni);
+        double s = row_sum(yc + (size_t)j * ni, ni, a.n_gas, a.gas_indx, nullptr);
         for (int i = 0; i < ni; i++) a.ymix_out[((size_t)col * nz + j) * ni + i] = yc[(size_t)j * ni + i] / s;
     }
 }
@@ -162,12 +161,7 @@ int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *
     ClipArgs a{c->nz, c->ni, na, y_dev, ymix_in_dev, ymix_out_dev, compo_dev, skip_dev, pos_cut, nega_cut, c->opts.mtol,
                c->atm.n_gas, c->atm.gas_indx, atom_sum_dev, small_dev, nega_dev, anyneg_dev};
     const int nt = 256;
-    size_t smem = sizeof(double) * ((size_t)nt * (na + 2) + (c->atm.n_gas > 0 ? (size_t)nt * c->ni : 0));
-    static size_t configured = 48 * 1024;
-    if (smem > configured) {
-        VK_CUDA(cudaFuncSetAttribute(clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    const size_t smem = sizeof(double) * (size_t)nt * (na + 2);      // <= 20 KB
     clip_kernel<<<c->ncol, nt, smem, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;

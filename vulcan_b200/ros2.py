@@ -85,12 +85,16 @@ class Ros2(object):
             self._photo_ready = False
         return self._col
 
+    def _flag(self, name):
+        """optional vulcan_cfg switches are read the same way everywhere (older cfg files lack some of them)"""
+        return bool(getattr(self.cfg, name, False))
+
     def _gas(self, atm):
         return np.asarray(atm.gas_indx, dtype=np.int32) if self.non_gas_sp else None
 
     def _sync_atm(self, atm, nz):
         cfg = self.cfg
-        if cfg.use_moldiff:
+        if self._flag("use_moldiff"):
             vals = {n: np.asarray(getattr(atm, n), dtype=np.float64) for n in _DYN_ATM}
         else:
             # use_moldiff = False: vulcan.py never calls mol_diff, so atm.Ti / atm.Hpi do not exist (build_atm.py:569-571) and atm.ms is
@@ -99,16 +103,16 @@ class Ros2(object):
             ni = len(self.species)
             zeros = {"Ti": (nz - 1,), "Hpi": (nz - 1,), "ms": (ni,), "alpha": (ni,), "Dzz": (nz - 1, ni)}
             vals = {n: (np.zeros(zeros[n]) if n in zeros else np.asarray(getattr(atm, n), dtype=np.float64)) for n in _DYN_ATM}
-        flags = (bool(cfg.use_moldiff), bool(cfg.use_settling), bool(cfg.use_topflux), bool(cfg.use_botflux), bool(cfg.use_vm_mol))
-        use_vm = bool(cfg.use_vm_mol) and bool(cfg.use_moldiff)      # Ros2.solver's dispatch (op.py:2869-2888)
+        flags = tuple(self._flag(n) for n in ("use_moldiff", "use_settling", "use_topflux", "use_botflux", "use_vm_mol"))
+        use_vm = flags[4] and flags[0]                               # Ros2.solver's dispatch (op.py:2869-2888)
         if use_vm:
             vals["vm"] = np.asarray(atm.vm, dtype=np.float64)        # build_atm.py:735-739
         c = self._atm_cache
         if c is not None and c[0] == flags and all(np.array_equal(c[1][n], vals[n]) for n in vals):
             return
         gas = self._gas(atm)
-        if cfg.use_moldiff and not cfg.use_settling:
-            gas_lhs = np.asarray(atm.gas_indx, dtype=np.int32) if cfg.use_condense else None     # op.py:1981-1984
+        if flags[0] and not flags[1]:
+            gas_lhs = np.asarray(atm.gas_indx, dtype=np.int32) if self._flag("use_condense") else None     # op.py:1981-1984
         else:
             gas_lhs = gas
         self._columns(nz).set_atm(use_moldiff=flags[0], use_settling=flags[1], use_topflux=flags[2], use_botflux=flags[3],
@@ -119,11 +123,14 @@ class Ros2(object):
 
     def _sync_k(self, var, nz):
         """var.k is a dict {1..nr -> (nz,) array} (store.py:25).  During integration the reference only REBINDS entries
-        (compute_J op.py:2785, conden op.py:1122-1176), so the identity of the value objects is a sufficient change detector;
-        a full comparison is still made every 64 calls."""
-        ids = tuple(map(id, var.k.values()))
+        (compute_J op.py:2785, conden op.py:1122-1176), so the identity of the value objects is a sufficient change detector - the
+        previous objects are kept ALIVE here and compared with `is` (an id() alone could be reused by a new array once the old one
+        is freed); a full comparison by value is still made every 64 calls (in-place writes)."""
+        refs = list(var.k.values())
         self._k_calls = getattr(self, "_k_calls", 0) + 1
-        if self._k_cache is not None and ids == self._k_ids and self._k_calls % 64:
+        old = self._k_ids
+        if self._k_cache is not None and old is not None and len(old) == len(refs) and all(a is b for a, b in zip(old, refs)) \
+                and self._k_calls % 64:
             return
         k = np.zeros((nz, self.nr + 1))
         for i in range(1, self.nr + 1):
@@ -131,12 +138,12 @@ class Ros2(object):
         if self._k_cache is None or not np.array_equal(self._k_cache, k):
             self._columns(nz).set_k(k)
             self._k_cache = k
-        self._k_ids = ids
+        self._k_ids = refs
 
     def _sync_opts(self, var, atm, para, nz):
         cfg, ni = self.cfg, self.ni
         fix_mask = fix_y = dz_sp = None
-        if cfg.use_condense:
+        if self._flag("use_condense"):
             dz_sp = np.zeros(ni, dtype=np.uint8)
             dz_sp[self.non_gas_sp_index] = 1
             dz_sp[self.condense_sp_index] = 1
@@ -149,7 +156,7 @@ class Ros2(object):
                     fix_mask[:top, i] = 1
                     fix_y[:top, i] = np.asarray(var.fix_y[s])[:top]
                     dz_sp[i] = 1
-        if cfg.use_ion:
+        if self._flag("use_ion"):
             # atm.fix_e_indx (store.py:157): the electron row of every layer is  1/(r h) e_i  with a zero right-hand side in both
             # stages (op.py:2908-2911, 2926), i.e. the solve leaves e untouched: sol[:, e] = y[:, e] and its delta is exactly 0
             ie = self.species.index("e")
@@ -163,7 +170,7 @@ class Ros2(object):
             dz_sp[ie] = 1
         fbi = list(self.fix_sp_bot_index)
         fbv = self.fix_sp_bot_mix * atm.n_0[0] if fbi else None               # op.py:2946
-        zero0 = bool(cfg.use_botflux or cfg.use_fix_sp_bot)                   # op.py:2953
+        zero0 = bool(self._flag("use_botflux") or cfg.use_fix_sp_bot)         # op.py:2953
         key = (zero0, tuple(fbi), None if fbv is None else fbv.tobytes(), None if dz_sp is None else dz_sp.tobytes(),
                None if fix_mask is None else fix_mask.tobytes(), None if fix_y is None else fix_y.tobytes(), self.mtol, self.atol)
         if key != self._opts_key:
@@ -173,7 +180,7 @@ class Ros2(object):
 
     # ------------------------------------------------------------------ the Ros2 protocol
     def naming_solver(self, para):                                           # op.py:3078-3088
-        print("Include molecular diffusion." if self.cfg.use_moldiff else "No molecular diffusion.")
+        print("Include molecular diffusion." if self._flag("use_moldiff") else "No molecular diffusion.")
         para.solver_str = "solver"
 
     def solver(self, var, atm, para):
@@ -193,7 +200,7 @@ class Ros2(object):
         var.y = sol[0]
         var.ymix = ymix[0]
         para.delta = float(delta[0]) if status[0] == 0 else float("nan")     # a singular block fails step_ok like a NaN would
-        if cfg.use_ion:                                                      # op.py:2998-3004: [e] from charge neutrality (ymix is not redone)
+        if self._flag("use_ion"):                                            # op.py:2998-3004: [e] from charge neutrality (ymix is not redone)
             ie = self.species.index("e")
             var.y[:, ie] = 0
             for sp in var.charge_list:
@@ -222,7 +229,7 @@ class Ros2(object):
             skip = np.array([a in loss_ex for a in self.cfg.atom_list], dtype=np.uint8)
         prev = np.array([var.atom_sum.get(a, 0.0) for a in self.cfg.atom_list], dtype=float)
         res = self._columns(nz).clip_loss(var.y, var.ymix, self._compo, pos_cut, nega_cut, atom_sum=prev, atom_skip=skip,
-                                          small_y=[para.small_y], nega_y=[para.nega_y])
+                                          small_y=[para.small_y], nega_y=[para.nega_y], mtol=self.mtol)
         para.small_y, para.nega_y = float(res["small_y"][0]), float(res["nega_y"][0])
         for q, a in enumerate(self.cfg.atom_list):
             if a not in loss_ex:                                             # op.py:2482-2485
@@ -304,7 +311,7 @@ class Ros2(object):
         rid = np.array([0 if var.pho_rate_index[b] in cfg.remove_list else var.pho_rate_index[b] for b in br], dtype=np.int32)
         self._branches = br
         self._ion_branches = []
-        if cfg.use_ion:
+        if self._flag("use_ion"):
             # compute_Jion (op.py:2789-2820) is the same trapezoid contraction as compute_J over the ion cross sections (no
             # temperature dependence): its branches ride in the same device table behind the photodissociation branches
             ibr = [(s, b) for s in sorted(var.ion_sp) for b in range(1, var.ion_branch[s] + 1)]
@@ -357,7 +364,7 @@ class Ros2(object):
                 var.k[var.pho_rate_index[(s, b)]] = var.J_sp[(s, b)] * self.cfg.f_diurnal
         self._k_cache = None          # the device copy of k already holds the new J rows; re-verified on the next solver call
         self._k_ids = None
-        self._jion_cache = c if self.cfg.use_ion else None     # Integration calls compute_Jion right after (op.py:828-829)
+        self._jion_cache = c if self._flag("use_ion") else None     # Integration calls compute_Jion right after (op.py:828-829)
         self._photo_cache = None
 
     def compute_Jion(self, var, atm):                                        # op.py:2789-2820
