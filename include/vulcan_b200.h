@@ -119,7 +119,9 @@ int vk_set_k_rows(vk_column *col, int n_rows, const int *rows, const double *val
 /* step options: the vulcan_cfg / para state consulted inside Ros2.solver (op.py:2896-2970) */
 typedef struct {
     double mtol, atol;               /* vulcan_cfg.mtol / atol (op.py:2949-2950) */
-    int refine;                      /* fp64 iterative-refinement passes per linear solve (0 = none) */
+    int refine;                      /* iterative refinement of each linear solve with a double-double residual: 0 none, n > 0 that many
+                                      * passes, -1 AUTO: one pass on the columns with dt >= refine_dt_min, kept only if it lowers the
+                                      * element-weighted residual compo^T (rhs - A x) (needs compo) */
     int zero_delta_row0;             /* use_botflux or use_fix_sp_bot: delta[0] = 0 (op.py:2953) */
     int n_fix_bot;                   /* use_fix_sp_bot (op.py:2945-2946) */
     const int *fix_bot_idx;          /* [n_fix_bot] species */
@@ -127,6 +129,9 @@ typedef struct {
     const unsigned char *delta_zero_sp; /* [ni] species whose delta is ignored (op.py:2956-2970) or NULL */
     const unsigned char *fix_mask;   /* [ncol][nz][ni] rows pinned to identity (fix_species / electrons) or NULL */
     const double *fix_y;             /* [ncol][nz][ni] values re-imposed where fix_mask (op.py:2960-2968) or NULL */
+    /* ABI 3 */
+    int na; const double *compo;     /* [ni][na] atoms per species (build_atm.py:18-25, thermo/all_compose.txt) or NULL */
+    double refine_dt_min;            /* refine = -1: step size (s) from which a column is refined */
 } vk_step_opts;
 int vk_set_step_opts(vk_column *col, const vk_step_opts *opts);
 
@@ -196,6 +201,8 @@ int vk_ens_run(vk_column *col, int n_steps);
 /* accepted / rejected counters [ncol], model time t [ncol], dt [ncol], y [ncol][nz][ni]; any may be NULL */
 int vk_ens_get_state(vk_column *col, double *y, double *t, double *dt, int *n_accept, int *n_reject);
 
+/* refine = -1 bookkeeping: refinement passes kept / tried by the safeguard since the handle was created, [ncol] each, may be NULL */
+int vk_refine_stats(vk_column *col, int *kept, int *tried);
 /* timing of the last vk_ros2_solve / vk_ens_run on the handle's stream, measured with CUDA events (ms) */
 int vk_last_kernel_ms(vk_column *col, float *ms_total, float *ms_factor);
 /* profiling aid (bench.py, scripts/kernel_times.py): `reps` back-to-back launches of ONE kernel of the step on the resident state with

@@ -45,7 +45,8 @@ class _Atm(C.Structure):
 class _Opts(C.Structure):
     _fields_ = [("fix_mask", _bp), ("fix_y", _dp), ("n_fix_bot", C.c_int), ("fix_bot_idx", _ip), ("fix_bot_mix", _dp),
                 ("n0_bot", C.c_double), ("zero_delta_row0", C.c_int), ("delta_zero_sp", _bp), ("n_gas_mix", C.c_int),
-                ("gas_indx_mix", _ip), ("mtol", C.c_double), ("atol", C.c_double), ("refine", C.c_int)]
+                ("gas_indx_mix", _ip), ("mtol", C.c_double), ("atol", C.c_double), ("refine", C.c_int),
+                ("na", C.c_int), ("compo", _dp), ("refine_dt_min", C.c_double)]
 
 
 def _d(a):
@@ -179,7 +180,8 @@ class Oracle(object):
 
     # -------------------------------------------------------------- the step
     def ros2_solver(self, atm, y, ymix, k, dt, mtol, atol, refine=0, fix_mask=None, fix_y=None, fix_bot_idx=(),
-                    fix_bot_mix=(), n0_bot=0.0, zero_delta_row0=False, delta_zero_sp=None, gas_indx_mix=None):
+                    fix_bot_mix=(), n0_bot=0.0, zero_delta_row0=False, delta_zero_sp=None, gas_indx_mix=None, compo=None,
+                    refine_dt_min=1.0e3):
         y, ymix, k = _f64(y), _f64(ymix), _f64(k)
         nz, ni = y.shape
         fm = None if fix_mask is None else np.ascontiguousarray(fix_mask, dtype=np.uint8)
@@ -187,9 +189,11 @@ class Oracle(object):
         fbi, fbm = _i32(fix_bot_idx), _f64(fix_bot_mix)
         dz = None if delta_zero_sp is None else np.ascontiguousarray(delta_zero_sp, dtype=np.uint8)
         gm = _i32(gas_indx_mix) if gas_indx_mix is not None and len(gas_indx_mix) != ni else None
+        cp = None if compo is None else _f64(compo)
         o = _Opts(None if fm is None else _b(fm), None if fy is None else _d(fy), len(fbi), _i(fbi), _d(fbm),
                   float(n0_bot), int(zero_delta_row0), None if dz is None else _b(dz),
-                  0 if gm is None else len(gm), None if gm is None else _i(gm), float(mtol), float(atol), int(refine))
+                  0 if gm is None else len(gm), None if gm is None else _i(gm), float(mtol), float(atol), int(refine),
+                  0 if cp is None else cp.shape[1], None if cp is None else _d(cp), float(refine_dt_min))
         sol, ymo, k1, k2 = np.empty_like(y), np.empty_like(y), np.empty_like(y), np.empty_like(y)
         delta = C.c_double(0)
         rc = self.lib.vko_ros2_solver(C.byref(self.cnet), C.byref(atm), C.byref(o), _d(y), _d(ymix), _d(k),

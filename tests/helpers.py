@@ -156,7 +156,7 @@ def charge_balance(case, sol):
 
 def oracle_step(case, oracle, atm, refine=0):
     o = step_opts(case)
-    res = oracle.ros2_solver(atm, case.y, case.ymix, case.k, case.dt, case.cfg["mtol"], case.cfg["atol"], refine=refine, **o)
+    res = oracle.ros2_solver(atm, case.y, case.ymix, case.k, case.dt, case.cfg["mtol"], case.cfg["atol"], refine=refine, compo=case.st["compo"], **o)
     res["sol"] = charge_balance(case, res["sol"])
     return res
 
@@ -181,7 +181,7 @@ def gpu_columns(case, ncol=1, refine=0):
     rep = lambda a: None if a is None else np.repeat(a[None], ncol, axis=0)
     col.set_step_opts(case.cfg["mtol"], case.cfg["atol"], refine=refine, zero_delta_row0=o["zero_delta_row0"],
                       fix_bot_idx=o["fix_bot_idx"], fix_bot_val=fbv, delta_zero_sp=o["delta_zero_sp"],
-                      fix_mask=rep(o["fix_mask"]), fix_y=rep(o["fix_y"]))
+                      fix_mask=rep(o["fix_mask"]), fix_y=rep(o["fix_y"]), compo=case.st["compo"])
     return col
 
 
@@ -341,7 +341,7 @@ def photolysis_via_dropin(tag, step, abi=None):
         ros2_mod._abi = real_abi
 
 
-def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
+def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edit=None):
     """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
     object and the Integration mirror until Integration.stop() says so (op.py:1067-1087).  `abi`: replaces the ctypes binding
     the solver object talks to (only the CPU host-logic tests pass the oracle-backed stand-in of tests/oracle_columns.py)."""
@@ -358,6 +358,9 @@ def run_config(tag, refine=0, max_wall_s=600, count_max=None, abi=None):
         attach_conden(case, cfg, var, atm)
         if count_max is not None:
             cfg.count_max = count_max
+        if cfg_edit:
+            for name, val in cfg_edit.items():
+                setattr(cfg, name, val)
         var.y = case.st["y_ini"].copy()
         if cfg.non_gas_sp:
             var.ymix = var.y / np.vstack(np.sum(var.y[:, atm.gas_indx], axis=1))

@@ -17,7 +17,7 @@ LOCKSTEP = [("HD189", 10), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("HD1
 LOCKSTEP = [p for p in LOCKSTEP if have(p[0], "step%04d.npz" % p[1]) and have(p[0], "step0000.npz")]
 
 
-def lockstep(tag, nstep, abi=None, refine=0):
+def lockstep(tag, nstep, abi=None, refine=-1):
     ref = Case(tag, nstep)
     case, var, atm, para, integ, wall = run_config(tag, refine=refine, count_max=nstep - 1, abi=abi)   # Integration.stop: count > count_max
     assert para.count == nstep
@@ -75,7 +75,7 @@ def long_trajectory(tag, nstep, abi=None):
         return orig(self, var, atm, para)
     ros2_mod.Ros2.one_step = traced
     try:
-        case, var, atm, para, integ, wall = run_config(tag, refine=0, count_max=nstep - 1, abi=abi, max_wall_s=3000)
+        case, var, atm, para, integ, wall = run_config(tag, refine=-1, count_max=nstep - 1, abi=abi, max_wall_s=3000)
     finally:
         ros2_mod.Ros2.one_step = orig
     return dict(dev=worst["t"], where=worst["where"], count=para.count, rejected=para.delta_count + para.nega_count + para.loss_count,

@@ -40,10 +40,10 @@ class OracleColumns(object):
         self.k = np.array(k, dtype=np.float64).reshape(self.nz, self.nr + 1)
 
     def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None, delta_zero_sp=None,
-                      fix_mask=None, fix_y=None):
+                      fix_mask=None, fix_y=None, compo=None, refine_dt_min=1.0e3):
         self.opts = dict(mtol=mtol, atol=atol, refine=refine, zero_delta_row0=zero_delta_row0, fix_bot_idx=list(fix_bot_idx),
                          fix_bot_val=None if fix_bot_val is None else np.asarray(fix_bot_val, dtype=float).ravel(),
-                         delta_zero_sp=delta_zero_sp, fix_mask=fix_mask, fix_y=fix_y)
+                         delta_zero_sp=delta_zero_sp, fix_mask=fix_mask, fix_y=fix_y, compo=compo, refine_dt_min=refine_dt_min)
 
     def ros2_solve(self, y, ymix, dt):
         o = self.opts
@@ -51,7 +51,8 @@ class OracleColumns(object):
         res = self.o.ros2_solver(self.atm, np.asarray(y).reshape(self.nz, self.ni), np.asarray(ymix).reshape(self.nz, self.ni), self.k,
                                  float(np.ravel(dt)[0]), o["mtol"], o["atol"], refine=o["refine"], fix_mask=o["fix_mask"], fix_y=o["fix_y"],
                                  fix_bot_idx=o["fix_bot_idx"], fix_bot_mix=fbv if fbv is not None else (), n0_bot=1.0,
-                                 zero_delta_row0=o["zero_delta_row0"], delta_zero_sp=o["delta_zero_sp"], gas_indx_mix=self.gas_indx)
+                                 zero_delta_row0=o["zero_delta_row0"], delta_zero_sp=o["delta_zero_sp"], gas_indx_mix=self.gas_indx,
+                                 compo=o["compo"], refine_dt_min=o["refine_dt_min"])
         return res["sol"][None], res["ymix"][None], np.array([res["delta"]]), np.zeros(1, dtype=np.int32)
 
     def clip_loss(self, y, ymix_in, compo, pos_cut, nega_cut, atom_sum=None, small_y=None, nega_y=None, atom_skip=None, mtol=None):

@@ -16,7 +16,11 @@ def test_first_steps_reproduce_the_reference(tag, nstep):
     print("%s: after %d steps on the GPU  t %.1e  dt %.1e  y (masked) %.1e  y (>1e-30) %.1e  ymix %.1e  rejected %d  wall %.2f s" %
           (tag, nstep, r["t"], r["dt"], r["y"], r["y_all"], r["ymix"], r["rejected"], r["wall"]))
     assert r["t"] < 1e-9 and r["dt"] < 1e-6       # same accept / reject sequence and step sizes as the reference
-    assert r["y"] < 1e-8 and r["ymix"] < 1e-8     # CPU twin measures 2e-15 ... 2e-9 (two different backward-stable solvers)
+    # CPU twin measures 2e-15 ... 2e-9 (two different backward-stable solvers).  HD189cho: the REFERENCE's own LAPACK solve is 2.8e-7 away
+    # from the 80-bit solution of its system at step 30 (block LU: 6e-16; tests/test_oracle_vs_reference.py::test_solver_vs_truth measures
+    # both), so that is what the two states differ by
+    ytol = {"HD189cho": 5e-6}.get(tag, 1e-8)
+    assert r["y"] < ytol and r["ymix"] < ytol
 
 
 @pytest.mark.skipif(not have("HD189ion", "photo0000.npz"), reason="fixture missing")

@@ -57,9 +57,9 @@ def check(ni, seed=0, ncol=3):
     y = n0[:, None] * mix / mix.sum(axis=1, keepdims=True)
     ymix = y / y.sum(axis=1, keepdims=True)
     k = np.zeros((nz, net.nr + 1))
-    k[:, 1:] = 10.0 ** rng.uniform(-24, -17, (nz, net.nr))        # k n <= ~1e4 /s: dt = 1e-6 s is a small step
+    k[:, 1:] = 10.0 ** rng.uniform(-24, -17, (nz, net.nr))
     k[:, 2::2] *= 10.0 ** rng.uniform(-6, 0, (nz, net.nr // 2))
-    dt = 1e-6
+    dt = 1e-12                                                    # a genuinely small step for these random rates (1e-6 s gives delta ~ 1e5)
     o = Oracle(net)
     atm = o.make_atm(**kw)
     dev = _abi.DeviceNetwork(net, 0)

@@ -111,10 +111,21 @@ def test_blocktri_solve_conserves_elements(case):
     e_x, e_ref = np.abs(bud(x[0]) - bud(xt)).max(), np.abs(bud(case.fx["k1"]) - bud(xt)).max()
     print("%s-%d dt %.2e: residual gpu %.1e LAPACK %.1e | element budget error of k1  gpu %.1e LAPACK %.1e" %
           (case.tag, case.step, case.dt, res(x[0]), res(case.fx["k1"]), e_x, e_ref))
-    assert res(x[0]) <= max(50 * res(case.fx["k1"]), 1e-12)      # max-norm residual relative to max |rhs|: same scale for both solvers
+    # max-norm residual relative to max |rhs|: same scale for both solvers.  The block-LU residual scatters with the summation order of the
+    # same algorithm: JupiterVmVz-30 LAPACK 5e-14, C oracle 4e-13, numpy/BLAS order 3e-12, device 4e-12
+    assert res(x[0]) <= max(100 * res(case.fx["k1"]), 1e-11)
     # measured: equal to LAPACK's everywhere except HD209S-400 (dt = 2.4e5 s: 1.2e-4 vs 7.6e-6, the deepest layer's CH4); the
     # explicit-inverse solve this replaced was at 7.5e-5 ... 0.35 over the same run
     assert e_x <= max(50 * e_ref, 1e-9)
+    # the default of the product (refine = -1): one pass with the double-double residual, kept only if it lowers the element-weighted
+    # residual.  CPU study on the same systems (80-bit residual): 20 - 50 x per pass, e.g. HD209S-400 7e-6 -> 4e-7, where fp64-residual
+    # refinement gains nothing (6e-6) - so the budget must end up BELOW LAPACK's
+    xa, sta = case.col.blocktri_solve(D, up, dn, rhs, refine=-1)
+    e_a = np.abs(bud(xa[0]) - bud(xt)).max()
+    kept, tried = case.col.refine_stats()
+    print("   refine=auto: element budget error %.1e (kept %d of %d passes so far on this handle), residual %.1e" % (e_a, kept[0], tried[0], res(xa[0])))
+    assert sta[0] == 0 and e_a <= max(0.5 * e_ref, 1e-15 * np.abs(bud(xt)).max(), 1e-30)
+    assert e_a <= e_x * 1.0000001
 
 
 def test_ros2_step(case):

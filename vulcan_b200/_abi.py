@@ -25,7 +25,7 @@ SYMBOLS = [
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
     "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
-    "vk_debug_time_kernel",
+    "vk_debug_time_kernel", "vk_refine_stats",
 ]
 
 
@@ -61,7 +61,7 @@ class AtmView(C.Structure):
 class StepOpts(C.Structure):
     _fields_ = [("mtol", C.c_double), ("atol", C.c_double), ("refine", C.c_int), ("zero_delta_row0", C.c_int),
                 ("n_fix_bot", C.c_int), ("fix_bot_idx", _ip), ("fix_bot_val", _dp), ("delta_zero_sp", _bp),
-                ("fix_mask", _bp), ("fix_y", _dp)]
+                ("fix_mask", _bp), ("fix_y", _dp), ("na", C.c_int), ("compo", _dp), ("refine_dt_min", C.c_double)]
 
 
 class PhotoView(C.Structure):
@@ -79,6 +79,10 @@ class EnsOpts(C.Structure):
                 ("dt_var_min", C.c_double), ("dt_var_max", C.c_double), ("pos_cut", C.c_double), ("nega_cut", C.c_double),
                 ("na", C.c_int), ("compo", _dp), ("atom_ini", _dp), ("n_0", _dp)]
 
+
+# refine = -1 (auto): columns are refined from this step size on.  Below it the element-budget error of one backward-stable solve,
+# eps |A||x| r dt, is < 1e-9 per step on every fixture
+REFINE_DT_MIN = 1.0e3
 
 _lib = None
 
@@ -123,6 +127,7 @@ def load():
     lib.vk_last_kernel_ms.argtypes = [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.vk_device_buffers.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
     lib.vk_stream.argtypes = [_vp, C.POINTER(_vp)]
+    lib.vk_refine_stats.argtypes = [_vp, _ip, _ip]
     lib.vk_debug_time_kernel.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = lib
     return lib
@@ -298,14 +303,17 @@ class Columns(object):
         check(self.lib.vk_set_k_rows(self.handle, len(rows), iptr(rows), dptr(vals)))
 
     def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None,
-                      delta_zero_sp=None, fix_mask=None, fix_y=None):
+                      delta_zero_sp=None, fix_mask=None, fix_y=None, compo=None, refine_dt_min=REFINE_DT_MIN):
+        """refine: passes of iterative refinement per solve (double-double residual); -1 = auto: one safeguarded pass on the columns
+        whose dt >= refine_dt_min (needs compo [ni, na])."""
         fbi = i32(fix_bot_idx)
         fbv = None if len(fbi) == 0 else f64(fix_bot_val).reshape(self.ncol, len(fbi))
         dz = None if delta_zero_sp is None else u8(delta_zero_sp)
         fm = None if fix_mask is None else u8(fix_mask).reshape(self.ncol, self.nz, self.ni)
         fy = None if fix_y is None else f64(fix_y).reshape(self.ncol, self.nz, self.ni)
+        cp = None if compo is None else f64(compo).reshape(self.ni, -1)
         o = StepOpts(float(mtol), float(atol), int(refine), int(zero_delta_row0), len(fbi), iptr(fbi) if len(fbi) else None,
-                     dptr(fbv), bptr(dz), bptr(fm), dptr(fy))
+                     dptr(fbv), bptr(dz), bptr(fm), dptr(fy), 0 if cp is None else cp.shape[1], dptr(cp), float(refine_dt_min))
         check(self.lib.vk_set_step_opts(self.handle, C.byref(o)))
 
     # ---------------------------------------------------------------- hot path
@@ -409,6 +417,11 @@ class Columns(object):
 
     def photo_reset(self):
         check(self.lib.vk_photo_reset(self.handle))
+
+    def refine_stats(self):
+        kept, tried = np.zeros(self.ncol, dtype=np.int32), np.zeros(self.ncol, dtype=np.int32)
+        check(self.lib.vk_refine_stats(self.handle, iptr(kept), iptr(tried)))
+        return kept, tried
 
     def last_kernel_ms(self):
         a, b = C.c_float(0), C.c_float(0)

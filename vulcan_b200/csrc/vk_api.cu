@@ -67,18 +67,10 @@ int vk_step_device_impl(vk_column *c)
     if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc; // block LU factors F_j of the Schur blocks (c->W)
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
     if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
-    for (int it = 0; it < c->opts.refine; it++) {
-        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res))) return rc;
-        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
-        if ((rc = launch_axpy(c, c->k1, c->dx))) return rc;
-    }
+    if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->f, c->k1, c->opts.refine, c->dt))) return rc;
     if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
     if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z))) return rc;                 // k2                op.py:2929
-    for (int it = 0; it < c->opts.refine; it++) {
-        if ((rc = launch_residual(c, c->D, c->up, c->dn, c->rhs, c->k2, c->res))) return rc;
-        if ((rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z))) return rc;
-        if ((rc = launch_axpy(c, c->k2, c->dx))) return rc;
-    }
+    if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->rhs, c->k2, c->opts.refine, c->dt))) return rc;
     if ((rc = launch_epilogue(c))) return rc;                                                       // sol, delta, ymix  op.py:2932-2993
     VK_CUDA(cudaEventRecord(c->ev3, c->stream));
     return VK_OK;
@@ -296,7 +288,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev3);
-    double **vecs[] = {&c->y, &c->ymix, &c->sol, &c->ymix_out, &c->f, &c->k1, &c->k2, &c->yk2, &c->rhs, &c->res, &c->dx};
+    double **vecs[] = {&c->y, &c->ymix, &c->sol, &c->ymix_out, &c->f, &c->k1, &c->k2, &c->yk2, &c->rhs, &c->res, &c->dx, &c->xn};
     for (double **v : vecs)
         if (e == cudaSuccess) e = cudaMalloc((void **)v, sizeof(double) * nv);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->z, sizeof(double) * np);
@@ -308,6 +300,9 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dt, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->delta, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->status, sizeof(int) * ncol);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->refine_kept, sizeof(int) * 2 * ncol);
+    if (e == cudaSuccess) e = cudaMemset(c->refine_kept, 0, sizeof(int) * 2 * ncol);
+    if (e == cudaSuccess) c->refine_tried = c->refine_kept + ncol;
     c->h_pin_bytes = sizeof(double) * (4 * nv + 4 * (size_t)ncol) + 64;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
     if (e != cudaSuccess) { cuda_fail(e, "vk_column_create allocation"); vk_column_destroy(c); return VK_ERR_CUDA; }
@@ -323,7 +318,8 @@ void vk_column_destroy(vk_column *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     photo_destroy(c);
     ens_destroy(c);
-    double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->z, c->up, c->dn,
+    if (c->refine_kept) cudaFree(c->refine_kept);
+    double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->xn, c->z, c->up, c->dn,
                       c->D, c->W, c->dt, c->delta, c->k};
     for (double *v : vecs) if (v) cudaFree(v);
     if (c->status) cudaFree(c->status);
@@ -482,6 +478,13 @@ int vk_set_step_opts(vk_column *c, const vk_step_opts *o)
     if (rc == VK_OK && o->delta_zero_sp) rc = dev_copy(c->opt_allocs, o->delta_zero_sp, (size_t)c->ni, &d.delta_zero_sp);
     if (rc == VK_OK && o->fix_mask) rc = dev_copy(c->opt_allocs, o->fix_mask, nv, &d.fix_mask);
     if (rc == VK_OK && o->fix_y) rc = dev_copy(c->opt_allocs, o->fix_y, nv, &d.fix_y);
+    d.refine_dt_min = o->refine_dt_min;
+    if (rc == VK_OK && o->compo && o->na > 0) {
+        if (o->na > 8) { set_error("at most 8 elements in atom_list are supported"); return VK_ERR_UNSUPPORTED; }
+        d.na = o->na;
+        rc = dev_copy(c->opt_allocs, o->compo, (size_t)c->ni * o->na, &d.compo);
+    }
+    if (rc == VK_OK && o->refine < 0 && !d.compo) { set_error("refine = auto (-1) needs compo / na"); return VK_ERR_INVALID; }
     return rc;
 }
 
@@ -662,11 +665,7 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
     if (e != cudaSuccess) rc = cuda_fail(e, "vk_blocktri_solve staging");
     if (rc == VK_OK) rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
     if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
-    for (int it = 0; rc == VK_OK && it < refine; it++) {
-        rc = launch_residual(c, c->D, c->up, c->dn, c->f, c->k1, c->res);
-        if (rc == VK_OK) rc = launch_solve(c, c->W, c->up, c->dn, c->res, c->dx, c->z);
-        if (rc == VK_OK) rc = launch_axpy(c, c->k1, c->dx);
-    }
+    if (rc == VK_OK) rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->f, c->k1, refine, nullptr);   // refine < 0: safeguarded pass on every column
     if (rc == VK_OK) {
         e = cudaMemcpyAsync(x, c->k1, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess && status) e = cudaMemcpyAsync(status, c->status, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream);
@@ -676,6 +675,16 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
     cudaStreamSynchronize(c->stream);
     cudaFree(Dd); if (upd) cudaFree(upd); if (dnd) cudaFree(dnd);
     return rc;
+}
+
+int vk_refine_stats(vk_column *c, int *kept, int *tried)
+{
+    if (!c) { set_error("null handle"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    if (kept) VK_CUDA(cudaMemcpy(kept, c->refine_kept, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost));
+    if (tried) VK_CUDA(cudaMemcpy(tried, c->refine_tried, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost));
+    return VK_OK;
 }
 
 int vk_last_kernel_ms(vk_column *c, float *ms_total, float *ms_factor)

@@ -94,6 +94,9 @@ struct StepOptsDev {
     const unsigned char *delta_zero_sp;
     const unsigned char *fix_mask;    // [ncol][nz][ni]
     const double *fix_y;
+    int na;                           // refine = auto: element composition for the safeguard
+    const double *compo;              // [ni][na]
+    double refine_dt_min;
 };
 
 }  // namespace vk
@@ -118,7 +121,8 @@ struct vk_column {
     // state
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
-    double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx;  // work vectors [ncol][nz][ni]
+    double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx, *xn;  // work vectors [ncol][nz][ni]
+    int *refine_kept, *refine_tried;          // [ncol] refinement passes kept / tried by the safeguard (refine = auto)
     double *D, *W;                            // D [ncol][nz][nip][nip] lhs diagonal blocks; W [ncol][nz][nip][nip+2] block LU factors of the Schur blocks
     double *up, *dn;                          // [ncol][nz][nip]
     double *dt, *delta;                       // [ncol]
@@ -146,10 +150,12 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dens
 int launch_atm_pre(vk_column *c, int ncol_atm);
 // kernels (vk_solve.cu)
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status);
-int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z);
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,
+                 const double *dt_pred = nullptr, double dt_min = 0.0);
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
-                    double *res);
+                    double *res, const double *dt_pred = nullptr, double dt_min = 0.0);
+int launch_refine(vk_column *c, const double *D, const double *up, const double *dn, const double *F, const double *rhs, double *x,
+                  int refine, const double *dt_pred);
 // kernels (vk_step.cu)
 int launch_epilogue(vk_column *c);
-int launch_axpy(vk_column *c, double *x, const double *dx);
 }  // namespace vk

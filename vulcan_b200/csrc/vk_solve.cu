@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int w = C::SPREAD ? wid - (wid >> 2) : wid;     // column-warp index (meaningless for the other warps)
     const int tid = w * 32 + lane;                         // thread index among the column warps
-    const int ni = a.ni, nz = a.nz;
+    const int nz = a.nz;
     const size_t cbase = (size_t)col * nz;
     int bad = 0;
 
@@ -412,6 +412,8 @@ struct LuSolveArgs {
     const double *rhs;           // [ncol][nz][ni]
     double *x;                   // [ncol][nz][ni]
     double *z;                   // [ncol][nz][NIP] scratch
+    const double *dt;            // optional per-column predicate (refine = auto): columns with dt < dt_min are skipped
+    double dt_min;
 };
 
 template <int NIP, int NBUF>
@@ -434,6 +436,7 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
     double *zv = yv + NIP;                          // NIP  published z_K
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(zv + NIP);   // NBUF mbarriers
     const int col = blockIdx.x, i = threadIdx.x, lane = i & 31, pan = i >> 3;
+    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
     const bool live = i < NIP;
     const int nz = a.nz, ni = a.ni;
     const double *Fc = a.F + (size_t)col * nz * NIP * LDF;
@@ -543,17 +546,45 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// residual  res = rhs - A x  (iterative refinement): one block per (column, layer), 4 threads per row
+// residual  res = rhs - A x  for iterative refinement, accumulated in DOUBLE-DOUBLE (error-free products by FMA, error-free sums;
+// Ogita / Rump / Oishi "Dot2"): one block per (column, layer), 4 threads per row.
+// Why extended precision: the element budget of a solve is  compo^T (rhs - A x) * r * dt  (chemistry conserves elements, compo^T J = 0).
+// A residual evaluated in plain fp64 carries a rounding error eps |A| |x| of its own - as large as the residual a backward-stable
+// solve leaves - so fp64 refinement cannot lower the budget error (measured on the reference's HD209S system at dt = 2.4e5 s:
+// 7e-6 -> 6e-6 -> 1e-5), whereas the same pass with an exact residual gains 20 - 50 x (7e-6 -> 4e-7 -> 2e-8); DESIGN.md section 4.2.
+// `dt` / `dt_min` (optional): columns whose step size is below the threshold are skipped (refine = auto).
 struct ResidArgs {
     int nz, ni, nip;
     const double *D, *up, *dn, *rhs, *x;
     double *res;
+    const double *dt;       // [ncol] or NULL
+    double dt_min;
 };
+struct dd_t { double hi, lo; };
+__device__ __forceinline__ void dd_fma_acc(dd_t &s, double a, double b)
+{
+    const double p = __dmul_rn(a, b);
+    const double pe = __fma_rn(a, b, -p);                 // a b = p + pe exactly
+    const double t = __dadd_rn(s.hi, p);
+    const double bb = __dsub_rn(t, s.hi);
+    const double e = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, bb)), __dsub_rn(p, bb));     // s.hi + p = t + e exactly
+    s.hi = t;
+    s.lo = __dadd_rn(s.lo, __dadd_rn(e, pe));
+}
+__device__ __forceinline__ void dd_add(dd_t &s, double ohi, double olo)
+{
+    const double t = __dadd_rn(s.hi, ohi);
+    const double bb = __dsub_rn(t, s.hi);
+    const double e = __dadd_rn(__dsub_rn(s.hi, __dsub_rn(t, bb)), __dsub_rn(ohi, bb));
+    s.hi = t;
+    s.lo = __dadd_rn(__dadd_rn(s.lo, olo), e);
+}
 __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
 {
     extern __shared__ double xs[];   // x_j padded
     const int nz = a.nz, ni = a.ni, nip = a.nip;
     const int col = blockIdx.x / nz, j = blockIdx.x % nz;
+    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
     const int tid = threadIdx.x;
     const size_t vb = ((size_t)col * nz + j) * ni;
     for (int i = tid; i < nip; i += blockDim.x) xs[i] = (i < ni) ? a.x[vb + i] : 0.0;
@@ -561,20 +592,95 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
     const int row = tid >> 2, part = tid & 3;
     const bool live = row < nip;
     const double *Dr = a.D + (((size_t)col * nz + j) * nip + (live ? row : 0)) * nip;
-    double acc = 0.0;
+    dd_t acc{0.0, 0.0};
     for (int c = part * 2; live && c < nip; c += 8) {
         double2 d = *reinterpret_cast<const double2 *>(Dr + c);
-        acc = fma(d.x, xs[c], acc);
-        acc = fma(d.y, xs[c + 1], acc);
+        dd_fma_acc(acc, d.x, xs[c]);
+        dd_fma_acc(acc, d.y, xs[c + 1]);
     }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    {
+        double oh = __shfl_xor_sync(0xffffffffu, acc.hi, 1), ol = __shfl_xor_sync(0xffffffffu, acc.lo, 1);
+        dd_add(acc, oh, ol);
+        oh = __shfl_xor_sync(0xffffffffu, acc.hi, 2); ol = __shfl_xor_sync(0xffffffffu, acc.lo, 2);
+        dd_add(acc, oh, ol);
+    }
     if (part == 0 && row < ni) {
         const size_t pb = ((size_t)col * nz + j) * nip;
-        if (j + 1 < nz) acc = fma(a.up[pb + row], a.x[vb + ni + row], acc);
-        if (j > 0) acc = fma(a.dn[pb + row], a.x[vb - ni + row], acc);
-        a.res[vb + row] = a.rhs[vb + row] - acc;
+        if (j + 1 < nz) dd_fma_acc(acc, a.up[pb + row], a.x[vb + ni + row]);
+        if (j > 0) dd_fma_acc(acc, a.dn[pb + row], a.x[vb - ni + row]);
+        dd_t r{a.rhs[vb + row], 0.0};
+        dd_add(r, -acc.hi, -acc.lo);
+        a.res[vb + row] = __dadd_rn(r.hi, r.lo);
     }
+}
+
+// xn = x + dx (per column predicate like resid_kernel)
+__global__ void refine_axpy_kernel(size_t per, const double *x, const double *dx, double *xn, const double *dt, double dt_min)
+{
+    const int col = blockIdx.y;
+    if (dt && !(dt[col] >= dt_min)) return;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < per; q += (size_t)gridDim.x * blockDim.x)
+        xn[col * per + q] = x[col * per + q] + dx[col * per + q];
+}
+
+// Safeguard of one refinement pass (refine = auto): the pass is kept only if it lowers the ELEMENT-WEIGHTED residual - the quantity it is
+// there to protect:  E_a = sum_{j,i} compo[i][a] res[j][i],  measured against  N_a = sum compo[i][a] |x[j][i]|  (scale of element a in x).
+// One block per column; every sum is formed in a fixed order (thread q owns the entries q, q + 256, ...; fixed shared-memory tree), so the
+// decision - and with it the result - is reproducible and independent of the batch a column sits in.
+struct SelectArgs {
+    int nz, ni, na;
+    const double *compo;       // [ni][na]
+    const double *res0, *res1; // residual before / after the pass
+    const double *xn;
+    double *x;
+    const double *dt;
+    double dt_min;
+    int *kept, *tried;         // [ncol] counters
+};
+__global__ void __launch_bounds__(256) refine_select_kernel(SelectArgs a)
+{
+    __shared__ double red[3][8][8];      // [quantity][element][warp]
+    __shared__ int take;
+    const int col = blockIdx.x, tid = threadIdx.x, na = a.na;
+    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
+    const size_t per = (size_t)a.nz * a.ni, base = col * per;
+    double e0[8], e1[8], nn[8];
+    for (int q = 0; q < 8; q++) e0[q] = e1[q] = nn[q] = 0.0;
+    for (size_t q = tid; q < per; q += 256) {
+        const int i = (int)(q % a.ni);
+        const double r0 = a.res0[base + q], r1 = a.res1[base + q], ax = fabs(a.x[base + q]);
+        for (int at = 0; at < na; at++) {
+            const double w = a.compo[i * na + at];
+            e0[at] = fma(w, r0, e0[at]); e1[at] = fma(w, r1, e1[at]); nn[at] = fma(w, ax, nn[at]);
+        }
+    }
+    for (int at = 0; at < na; at++) {
+        for (int off = 16; off > 0; off >>= 1) {
+            e0[at] += __shfl_xor_sync(0xffffffffu, e0[at], off);
+            e1[at] += __shfl_xor_sync(0xffffffffu, e1[at], off);
+            nn[at] += __shfl_xor_sync(0xffffffffu, nn[at], off);
+        }
+        if ((tid & 31) == 0) { red[0][at][tid >> 5] = e0[at]; red[1][at][tid >> 5] = e1[at]; red[2][at][tid >> 5] = nn[at]; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double w0 = 0.0, w1 = 0.0;
+        bool finite = true;
+        for (int at = 0; at < na; at++) {
+            double s0 = 0.0, s1 = 0.0, n = 0.0;
+            for (int w = 0; w < 8; w++) { s0 += red[0][at][w]; s1 += red[1][at][w]; n += red[2][at][w]; }
+            if (!(n > 0.0)) continue;
+            w0 = fmax(w0, fabs(s0) / n);
+            w1 = fmax(w1, fabs(s1) / n);
+            finite = finite && (s1 == s1);
+        }
+        take = (finite && w1 < w0) ? 1 : 0;
+        if (a.tried) a.tried[col] += 1;
+        if (a.kept && take) a.kept[col] += 1;
+    }
+    __syncthreads();
+    if (take)
+        for (size_t q = tid; q < per; q += 256) a.x[base + q] = a.xn[base + q];
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -612,9 +718,10 @@ static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 }
 
 // x = A^{-1} rhs with the stored block LU factors F ([ncol][nz][nip][nip+2]); z is scratch
-int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z)
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,
+                 const double *dt_pred, double dt_min)
 {
-    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z};
+    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, dt_pred, dt_min};
     // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
     // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per
     // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
@@ -630,10 +737,45 @@ int launch_solve(vk_column *c, const double *F, const double *up, const double *
     }
 }
 
-int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x, double *res)
+int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x, double *res,
+                    const double *dt_pred, double dt_min)
 {
-    ResidArgs a{c->nz, c->ni, c->nip, D, up, dn, rhs, x, res};
+    ResidArgs a{c->nz, c->ni, c->nip, D, up, dn, rhs, x, res, dt_pred, dt_min};
     resid_kernel<<<c->ncol * c->nz, 512, sizeof(double) * c->nip, c->stream>>>(a);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+
+// x <- A^{-1} rhs refined.  refine > 0: that many passes x += A^{-1}(rhs - A x) with the double-double residual.  refine < 0 (auto): ONE
+// pass on the columns whose step size is >= opts.refine_dt_min (dt_pred = their dt; NULL: every column), kept only if it lowers the
+// element-weighted residual (refine_select_kernel).  Work vectors: c->res, c->dx, c->xn.
+int launch_refine(vk_column *c, const double *D, const double *up, const double *dn, const double *F, const double *rhs, double *x,
+                  int refine, const double *dt_pred)
+{
+    int rc = VK_OK;
+    const size_t per = (size_t)c->nz * c->ni;
+    dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, 32), (unsigned)c->ncol);
+    if (refine > 0) {
+        for (int it = 0; it < refine && rc == VK_OK; it++) {
+            rc = launch_residual(c, D, up, dn, rhs, x, c->res, nullptr, 0.0);
+            if (rc == VK_OK) rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, nullptr, 0.0);
+            if (rc == VK_OK) {
+                refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, x, nullptr, 0.0);
+                VK_CUDA(cudaGetLastError());
+            }
+        }
+        return rc;
+    }
+    if (refine == 0) return VK_OK;
+    if (!c->opts.compo || c->opts.na < 1) { set_error("refine = auto needs the element composition (vk_step_opts.compo)"); return VK_ERR_INVALID; }
+    const double dmin = c->opts.refine_dt_min;
+    if ((rc = launch_residual(c, D, up, dn, rhs, x, c->res, dt_pred, dmin))) return rc;
+    if ((rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, dt_pred, dmin))) return rc;
+    refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, c->xn, dt_pred, dmin);
+    VK_CUDA(cudaGetLastError());
+    if ((rc = launch_residual(c, D, up, dn, rhs, c->xn, c->dx, dt_pred, dmin))) return rc;
+    SelectArgs sa{c->nz, c->ni, c->opts.na, c->opts.compo, c->res, c->dx, c->xn, x, dt_pred, dmin, c->refine_kept, c->refine_tried};
+    refine_select_kernel<<<c->ncol, 256, 0, c->stream>>>(sa);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }

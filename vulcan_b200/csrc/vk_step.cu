@@ -78,18 +78,6 @@ int launch_epilogue(vk_column *c)
     return VK_OK;
 }
 
-__global__ void axpy_kernel(size_t n, double *x, const double *dx)
-{
-    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) x[q] = x[q] + dx[q];
-}
-int launch_axpy(vk_column *c, double *x, const double *dx)
-{
-    const size_t n = (size_t)c->ncol * c->nz * c->ni;
-    axpy_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, c->stream>>>(n, x, dx);
-    VK_CUDA(cudaGetLastError());
-    return VK_OK;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // ODESolver.clip + loss (op.py:2447-2487), one block per column.
 struct ClipArgs {

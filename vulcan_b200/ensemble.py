@@ -51,7 +51,7 @@ def synthetic_columns(y_base, n_0, compo, atom_names, kzz_scale, met_scale, c_to
     return y, atom_ini
 
 
-def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine):
+def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine, compo=None):
     """a vk_column handle for `ncol` columns of a sweep: per-column Kzz, everything else of the atmosphere replicated."""
     col = _abi.Columns(devnet, nz, ncol)
     rep = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (ncol,) + np.shape(a)))
@@ -63,17 +63,19 @@ def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine):
                 use_topflux=a["use_topflux"], use_botflux=a["use_botflux"], gas_indx=a.get("gas_indx"),
                 gas_indx_lhs=a.get("gas_indx_lhs"), shared=False)
     col.set_k(k)                                        # thermal + photolysis rates shared by the sweep (same T-P, same star)
-    col.set_step_opts(cfg["mtol"], cfg["atol"], refine=refine)
+    if refine < 0 and compo is None:
+        raise ValueError("refine = -1 (auto) needs the element composition `compo` [ni, na]")
+    col.set_step_opts(cfg["mtol"], cfg["atol"], refine=refine, compo=compo)
     return col
 
 
 class EnsembleRunner(object):
     """The columns [lo, hi) of an ensemble resident on one GPU, advanced by the device-resident controller."""
 
-    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=0):
+    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=-1):
         self.ncol = y.shape[0]
         self.devnet = _abi.DeviceNetwork(network, device)
-        self.col = _make_columns(self.devnet, nz, self.ncol, atm_common, kzz, k, cfg, refine)
+        self.col = _make_columns(self.devnet, nz, self.ncol, atm_common, kzz, k, cfg, refine, compo)
         self.col.ens_setup(cfg["rtol"], cfg["loss_eps"], cfg["dt_min"], cfg["dt_max"], cfg["dt_var_min"], cfg["dt_var_max"],
                            cfg["pos_cut"], cfg["nega_cut"], compo, atom_ini, np.broadcast_to(n_0, (self.ncol, nz)))
         self.col.ens_set_state(y, dt)
@@ -94,7 +96,7 @@ class PipelinedHostSolver(object):
     host round trip costs max(transfer, compute) instead of their sum.  Pass page-locked arrays (e.g. numpy views of pinned torch
     tensors) to have them DMA'd directly."""
 
-    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=None, device=0, refine=0):
+    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=None, device=0, refine=0, compo=None):
         from concurrent.futures import ThreadPoolExecutor
         self.ncol = kzz.shape[0]
         self.nz, self.ni = nz, network.ni
@@ -104,7 +106,7 @@ class PipelinedHostSolver(object):
             n_groups = max(4, min(16, self.ncol // 256))
         n_groups = max(1, min(n_groups, self.ncol))
         self.bounds = [partition(self.ncol, n_groups, g) for g in range(n_groups)]
-        self.cols = [_make_columns(self.devnet, nz, hi - lo, atm_common, kzz[lo:hi], k, cfg, refine) for lo, hi in self.bounds]
+        self.cols = [_make_columns(self.devnet, nz, hi - lo, atm_common, kzz[lo:hi], k, cfg, refine, compo) for lo, hi in self.bounds]
         self.pool = ThreadPoolExecutor(max_workers=n_groups)
 
     def solve_into(self, y, ymix, dt, sol, ymix_out, delta, status):

@@ -17,10 +17,12 @@ _DYN_ATM = ("Kzz", "vz", "dzi", "Dzz", "vs", "Tco", "g", "M", "Ti", "Hpi", "ms",
 
 
 class Ros2(object):
-    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=0, network=None, charge=None):
+    def __init__(self, cfg=None, species=None, compo=None, device=0, refine=-1, network=None, charge=None, refine_dt_min=None):
         """cfg: the vulcan_cfg module (imported like the reference does when omitted); species: chem_funs.spec_list
         (only used to cross-check the network compiler's species order); compo: {species: {atom: n}} or an
-        [ni][na] array for `loss` (read from cfg.com_file when omitted)."""
+        [ni][na] array for `loss` (read from cfg.com_file when omitted).
+        refine: iterative refinement of the two linear solves of a step (double-double residual): 0 none, n > 0 passes, -1 (default)
+        one pass per solve once dt >= refine_dt_min (default _abi.REFINE_DT_MIN), kept only if it lowers the element-weighted residual."""
         if cfg is None:
             import vulcan_cfg as cfg          # reference module (op.py:30)
         self.cfg = cfg
@@ -30,6 +32,7 @@ class Ros2(object):
         self.species = self.network.species
         self.ni, self.nr = self.network.ni, self.network.nr
         self.device, self.refine = device, refine
+        self.refine_dt_min = getattr(_abi, "REFINE_DT_MIN", 1.0e3) if refine_dt_min is None else refine_dt_min
         self.mtol, self.atol = cfg.mtol, cfg.atol                           # op.py:1427-1428
         self.non_gas_sp = list(getattr(cfg, "non_gas_sp", []))
         sp = self.species
@@ -172,10 +175,12 @@ class Ros2(object):
         fbv = self.fix_sp_bot_mix * atm.n_0[0] if fbi else None               # op.py:2946
         zero0 = bool(self._flag("use_botflux") or cfg.use_fix_sp_bot)         # op.py:2953
         key = (zero0, tuple(fbi), None if fbv is None else fbv.tobytes(), None if dz_sp is None else dz_sp.tobytes(),
-               None if fix_mask is None else fix_mask.tobytes(), None if fix_y is None else fix_y.tobytes(), self.mtol, self.atol)
+               None if fix_mask is None else fix_mask.tobytes(), None if fix_y is None else fix_y.tobytes(), self.mtol, self.atol,
+               self.refine, self.refine_dt_min)
         if key != self._opts_key:
             self._columns(nz).set_step_opts(self.mtol, self.atol, refine=self.refine, zero_delta_row0=zero0, fix_bot_idx=fbi,
-                                            fix_bot_val=fbv, delta_zero_sp=dz_sp, fix_mask=fix_mask, fix_y=fix_y)
+                                            fix_bot_val=fbv, delta_zero_sp=dz_sp, fix_mask=fix_mask, fix_y=fix_y, compo=self._compo,
+                                            refine_dt_min=self.refine_dt_min)
             self._opts_key = key
 
     # ------------------------------------------------------------------ the Ros2 protocol
