@@ -57,7 +57,7 @@ def check(ni, seed=0, ncol=3):
     y = n0[:, None] * mix / mix.sum(axis=1, keepdims=True)
     ymix = y / y.sum(axis=1, keepdims=True)
     k = np.zeros((nz, net.nr + 1))
-    k[:, 1:] = 10.0 ** rng.uniform(-24, -17, (nz, net.nr))
+    k[:, 1:] = 10.0 ** rng.uniform(-40, -32, (nz, net.nr))        # three-body terms k n M dt <= 1e-2 at n = M = 1e21, dt = 1e-12 s: a small step
     k[:, 2::2] *= 10.0 ** rng.uniform(-6, 0, (nz, net.nr // 2))
     dt = 1e-12                                                    # a genuinely small step for these random rates (1e-6 s gives delta ~ 1e5)
     o = Oracle(net)

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libvulcan_b200.so")
+LIB_PATH = os.environ.get("VK_LIB_PATH") or os.path.join(HERE, "_lib", "libvulcan_b200.so")     # VK_LIB_PATH: diagnostic build variants
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

@@ -24,15 +24,21 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, solve_flags=()):
+    """variant / solve_flags: diagnostic builds (scripts/bisect_solve_budget.py): extra nvcc flags for vk_solve.cu only, objects and
+    library under a suffixed name (libvulcan_b200_<variant>.so); the product build takes neither."""
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIBDIR, exist_ok=True)
+    lib = LIB if not variant else os.path.join(LIBDIR, "libvulcan_b200_%s.so" % variant)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vulcan_b200.h"))
     objs, procs = [], []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        if variant and src == "vk_solve.cu":
+            o = os.path.join(LIBDIR, "vk_solve_%s.o" % variant)
+            extra = list(extra) + list(solve_flags)
         objs.append(o)
         if force or _newer(o, [s] + headers):
             cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
@@ -45,9 +51,9 @@ def build(force=False, verbose=False):
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    if force or procs or _newer(LIB, objs):
-        subprocess.run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"], check=True)
-    return LIB
+    if force or procs or _newer(lib, objs):
+        subprocess.run([nvcc] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"], check=True)
+    return lib
 
 
 if __name__ == "__main__":

@@ -22,6 +22,9 @@ namespace vk {
 // inf / 0 / nan, caught by the singular-pivot flag
 __device__ __forceinline__ double fast_rcp(double x)
 {
+#ifdef VK_EXACT_RCP
+    return 1.0 / x;
+#endif
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     double e = fma(-x, r, 1.0);
