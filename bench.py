@@ -2,7 +2,8 @@
 """bench.py — throughput of the B200-native Ros2 hot path (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (N>1: launched by torch.distributed.run)
-  python bench.py --impl reference [--gpus N] ...                CPU arm: the oracle port of the reference path on host cores
+  python bench.py --impl reference [--gpus N] ...                CPU arm: the UNMODIFIED reference (oracle/_ref, numpy/scipy) on the host cores,
+                                                                  one process per core; the C oracle port beside it / when oracle/_ref is absent
 
 Workload (config.workload): BASELINE config "ensemble sweep: 4096 HD189-like columns over a Kzz x metallicity x C/O grid"
 (NCHO_photo_network: ni=69, nr=878, nz=150), STRONG scaling: the 4096 columns are partitioned across the N ranks, no
@@ -164,32 +165,124 @@ def host_threads():
     return max(1, min(n, 64))
 
 
+WORKLOAD = "ensemble sweep: 4096 HD189-like columns (NCHO_photo_network ni=69 nr=878 nz=150), Kzz x metallicity x C/O; one step = one " \
+           "attempted Ros2 step (Ros2.solver, op.py:2860-3007) of every column"
+REF_CALLS_PER_STEP = int(os.environ.get("VK_BENCH_REF_CALLS", "3"))    # reference arm: op.Ros2.solver calls per worker process and bench step
+
+
+def reference_workers(n_proc, refdir):
+    """n_proc host processes of the UNMODIFIED reference (oracle/ref_worker.py on oracle/_ref/HD189), each set up like vulcan.py does"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", PYTHONHASHSEED="0")
+    procs = [subprocess.Popen([sys.executable, os.path.join(REPO, "oracle", "ref_worker.py"), refdir, "2"], stdin=subprocess.PIPE,
+                              stdout=subprocess.PIPE, stderr=(None if os.environ.get("VK_BENCH_DEBUG") else subprocess.DEVNULL), text=True, bufsize=1, env=env) for _ in range(n_proc)]
+    for p in procs:
+        line = p.stdout.readline()
+        if not line.startswith("READY"):
+            for q in procs:
+                q.kill()
+            raise RuntimeError("reference worker failed to start: %r" % line)
+    return procs
+
+
+def reference_step(procs, n_calls):
+    """every worker runs n_calls solver calls concurrently; returns the wall time of the slowest and the summed per-process time"""
+    t0 = time.time()
+    for p in procs:
+        p.stdin.write("GO %d\n" % n_calls)
+        p.stdin.flush()
+    inner = [float(p.stdout.readline().split()[1]) for p in procs]
+    return time.time() - t0, inner
+
+
+def measure_cpu_arm(case, n_steps, n_warm, budget_s=150.0):
+    """The reference's own CPU implementation of the path on the box's host cores (BASELINE north_star: "timed on the GPU box's own host
+    cores in the same run, with the core count stated").  When oracle/_ref/HD189 is present (staged by oracle/build_ref.py in the build
+    container; it travels with the snapshot) this times REAL op.Ros2.solver calls of the unmodified numpy/scipy reference: one process per
+    host core (independent columns = independent processes, OMP_NUM_THREADS = 1 as vulcan.py:52 forces), `kind` "reference".  The C port of
+    the GPU algorithm (oracle/vk_oracle.c) on the same cores is reported beside it (`cpu_port`), and alone when oracle/_ref is absent.
+    Returns (value, ms_per_bench_step, bench steps done, column-steps per bench step, cpu_baseline dict, cpu_port dict or None)."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import build_ref
+    threads = host_threads()
+    refdir = build_ref.staged("HD189")
+    port = None
+    try:
+        cpu_port_rate(case, max(2 * threads, 16), threads, 2 * threads)
+        port = cpu_port_rate(case, max(2 * threads, 16), threads, max(CPU_STEPS_PER_THREAD // 4, 2) * threads)
+    except Exception:
+        port = None
+    if refdir is None:
+        n_sample = max(2 * threads, 16)
+        n_total = CPU_STEPS_PER_THREAD * threads
+        rates, walls = [], []
+        for _ in range(max(1, n_warm > 0)):
+            cpu_port_rate(case, n_sample, threads, 4 * threads)
+        t_all = time.time()
+        for _ in range(n_steps):
+            t0 = time.time()
+            rates.append(cpu_port_rate(case, n_sample, threads, n_total))
+            walls.append(time.time() - t0)
+            if time.time() - t_all > budget_s:
+                break
+        v, kind, cores = float(np.mean(rates)), "port", threads
+        sample = "%d column-steps per bench step on %d host threads with the C oracle port (oracle/vk_oracle.c: same algorithm as the GPU " \
+                 "path, refine=0); oracle/_ref absent, so the unmodified reference could not be timed here" % (n_total, threads)
+        per_step = n_total
+    else:
+        try:
+            avail = int([ln for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0].split()[1]) // (1 << 20)     # GiB
+        except Exception:
+            avail = 64
+        n_proc = max(1, min(threads, 32, avail // 3))          # ~2.5 GB per process (dense 857 MB Jacobian + band copy + LAPACK workspace)
+        procs = reference_workers(n_proc, refdir)
+        try:
+            for _ in range(max(1, min(n_warm, 2))):
+                reference_step(procs, 1)
+            walls, inner = [], []
+            t_all = time.time()
+            for _ in range(n_steps):
+                w, inn = reference_step(procs, REF_CALLS_PER_STEP)
+                walls.append(w)
+                inner += inn
+                if time.time() - t_all > budget_s:
+                    break
+            one = reference_step(procs[:1], REF_CALLS_PER_STEP)[0] / REF_CALLS_PER_STEP if n_proc > 1 else None     # a single process alone
+        finally:
+            for p in procs:
+                try:
+                    p.stdin.write("QUIT\n"); p.stdin.flush()
+                except Exception:
+                    pass
+            for p in procs:
+                try:
+                    p.wait(timeout=10)
+                except Exception:
+                    p.kill()
+        per_step = n_proc * REF_CALLS_PER_STEP
+        v, kind, cores = per_step / float(np.mean(walls)), "reference", n_proc
+        sample = "%d op.Ros2.solver calls of the UNMODIFIED reference per bench step: %d host processes x %d calls (oracle/_ref/HD189, " \
+                 "numpy/scipy, OMP_NUM_THREADS=1 each; %.2f s per call with all processes running%s; host has %d usable threads)" % (
+                     per_step, n_proc, REF_CALLS_PER_STEP, float(np.mean(inner)) / REF_CALLS_PER_STEP,
+                     "" if one is None else ", %.2f s per call for one process alone" % one, threads)
+    cb = {"value": v, "unit": "column-steps/s", "cores": cores, "kind": kind, "sample": sample}
+    cp = None if port is None else {"value": port, "unit": "column-steps/s", "cores": threads, "kind": "port",
+                                    "sample": "C port of the GPU algorithm (oracle/vk_oracle.c) on %d host threads" % threads}
+    return v, 1e3 * float(np.mean(walls)), len(walls), per_step, cb, cp
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     case = load_case()
-    threads = host_threads()
-    n_sample = max(2 * threads, 16)
-    n_total = CPU_STEPS_PER_THREAD * threads
-    rates = []
-    for _ in range(max(1, args.warmup > 0)):
-        cpu_port_rate(case, n_sample, threads, 4 * threads)
-    t0 = time.time()
-    for _ in range(args.steps):
-        rates.append(cpu_port_rate(case, n_sample, threads, n_total))
-        if time.time() - t0 > 150:
-            break
-    v = float(np.mean(rates))
+    v, ms, n_done, per_step, cb, cp = measure_cpu_arm(case, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "ensemble column-steps/s", "value": v, "unit": "column-steps/s", "n_gpus": args.gpus,
-        "steps": len(rates), "warmup": args.warmup, "ms_per_step": 1e3 * N_COLUMNS / v, "higher_is_better": True,
+        "steps": n_done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ensemble sweep: 4096 HD189-like columns (NCHO_photo_network ni=69 nr=878 nz=150), Kzz x metallicity x C/O",
-                   "sample_columns_per_step": n_total},
-        "cpu_baseline": {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port",
-                         "sample": "%d column-steps per bench step on %d host threads with the C oracle port (oracle/vk_oracle.c: same "
-                                   "algorithm as the GPU path, refine=0); the UNMODIFIED numpy/scipy reference measured in the "
-                                   "build container is 0.42-0.50 s per solver call on 1 core (BASELINE.md), i.e. ~4x slower than this port" % (n_total, threads)},
+        "config": {"workload": WORKLOAD, "column_steps_per_bench_step": per_step,
+                   "note": "ms_per_step is the MEASURED wall time of one bench step of this arm (a bounded sample of the workload: "
+                           "%d column-steps), value = column-steps / s of that sample" % per_step},
+        "cpu_baseline": cb, "cpu_port": cp,
         "e2e": {"value": v, "unit": "column-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -203,7 +296,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--columns", type=int, default=N_COLUMNS)
-    ap.add_argument("--refine", type=int, default=0)
+    ap.add_argument("--refine", type=int, default=-1, help="iterative refinement of the linear solves: -1 = the product default (auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=None,
                     help="column groups (streams) of the pipelined host-buffer path (default: by batch size, ensemble.PipelinedHostSolver)")
@@ -307,7 +400,7 @@ def main():
     hm[:] = (y / y.sum(axis=2, keepdims=True)).ravel()
     hdt = np.full(ncol, dt0); hdelta = np.empty(ncol); hstat = np.zeros(ncol, dtype=np.int32)
     host = ensemble.PipelinedHostSolver(case.net, case.nz, atm_common, kzz, case.k, cfg, n_groups=args.e2e_groups,
-                                        device=local_rank, refine=args.refine)
+                                        device=local_rank, refine=args.refine, compo=st["compo"])
     e2e_steps = max(2, min(args.steps, 5))
     for _ in range(2):
         host.solve_into(hy, hm, hdt, hs, ho, hdelta, hstat)
@@ -325,13 +418,16 @@ def main():
     if rank == 0:
         ni, nz = case.net.ni, case.nz
         refine = args.refine
-        launches_per_step = 2 + 1 + 1 + (2 + 2 * refine) + 2 * refine + 2 * refine + 1 + 1 + 1 + 1
+        # kernels of one step: rhs x2, lhs, factor, solve x2, refinement (forced: resid + solve + axpy per pass and stage; auto: init + resid +
+        # 4 x (solve, axpy, resid, select) per stage - blocks of columns below refine_dt_min exit at once), epilogue, clip, control, apply
+        n_ref = 2 * 3 * refine if refine > 0 else (2 * (2 + 4 * 4) if refine == -1 else (2 * (2 + 4 * -refine) if refine < 0 else 0))
+        launches_per_step = 2 + 1 + 1 + 2 + n_ref + 1 + 1 + 1 + 1
         line = {
             "metric": "ensemble column-steps/s", "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ensemble sweep: %d HD189-like columns (NCHO_photo_network ni=69 nr=878 nz=150), Kzz x metallicity x C/O, "
-                                   "partitioned across %d GPU(s); attempted steps, refine=%d" % (ncols_total, world, refine),
+            "config": {"workload": WORKLOAD if ncols_total == N_COLUMNS else WORKLOAD.replace("4096", str(ncols_total)),
+                       "partition": "columns partitioned across %d GPU(s), no collective in the step" % world, "refine": refine,
                        "columns_per_gpu": ncol, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
                        "accepted_fraction": float(np.sum(s["n_accept"])) / float(np.sum(s["n_accept"]) + np.sum(s["n_reject"]))},
             "e2e": {"value": e2e_value, "unit": "column-steps/s", "h2d_bytes_per_step": int(2 * nv * 8 * world + 8 * ncols_total),
@@ -410,14 +506,10 @@ def main():
         except Exception as e:      # never lose the bench line over the auxiliary number
             line["single_column"]["time_to_steady_state"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
-            threads = host_threads()
-            n_sample = max(2 * threads, 16)
-            n_total = CPU_STEPS_PER_THREAD * threads
-            cpu_port_rate(case, n_sample, threads, 2 * threads)         # untimed: thread pool / page-in
-            v = cpu_port_rate(case, n_sample, threads, n_total)
-            line["cpu_baseline"] = {"value": v, "unit": "column-steps/s", "cores": threads, "kind": "port",
-                                    "sample": "%d column-steps of the same workload on %d host threads, C oracle port (oracle/vk_oracle.c); the "
-                                              "unmodified numpy/scipy reference is ~4x slower per step (0.42-0.50 s, BASELINE.md)" % (n_total, threads)}
+            v, ms_cpu, n_done, per_step, cb, cp = measure_cpu_arm(case, 2, 1, budget_s=40.0)
+            line["cpu_baseline"] = cb
+            if cp is not None:
+                line["cpu_port"] = cp
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -120,8 +120,9 @@ int vk_set_k_rows(vk_column *col, int n_rows, const int *rows, const double *val
 typedef struct {
     double mtol, atol;               /* vulcan_cfg.mtol / atol (op.py:2949-2950) */
     int refine;                      /* iterative refinement of each linear solve with a double-double residual: 0 none, n > 0 that many
-                                      * passes, -1 AUTO: one pass on the columns with dt >= refine_dt_min, kept only if it lowers the
-                                      * element-weighted residual compo^T (rhs - A x) (needs compo) */
+                                      * passes, -1 AUTO: on the columns with dt >= refine_dt_min up to 4 passes, each kept only if it lowers
+                                      * the element-weighted residual compo^T (rhs - A x), until the element-budget error of the solve
+                                      * is below 1e-11 (needs compo); -n: the same with at most n passes */
     int zero_delta_row0;             /* use_botflux or use_fix_sp_bot: delta[0] = 0 (op.py:2953) */
     int n_fix_bot;                   /* use_fix_sp_bot (op.py:2945-2946) */
     const int *fix_bot_idx;          /* [n_fix_bot] species */

@@ -15,20 +15,43 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 
+def private_view(refdir):
+    """a per-process view of the staged reference: symlinks to everything except fastchem_vulcan/ (copied: FastChem reads its input
+    from and writes its output into that directory, build_atm.py:84-131, so concurrent workers must not share it) and output/"""
+    import atexit
+    import shutil
+    import tempfile
+    view = tempfile.mkdtemp(prefix="vk_ref_worker_")
+    atexit.register(shutil.rmtree, view, True)
+    for name in os.listdir(refdir):
+        src = os.path.join(refdir, name)
+        if name == "fastchem_vulcan":
+            shutil.copytree(src, os.path.join(view, name), symlinks=True)
+        elif name in ("output", "plot", "__pycache__"):
+            os.makedirs(os.path.join(view, name), exist_ok=True)
+        else:
+            os.symlink(src, os.path.join(view, name))
+    return view
+
+
 def main():
-    refdir = sys.argv[1]
+    refdir = private_view(os.path.abspath(sys.argv[1]))
     warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     import contextlib
     import io
     import ref_session
-    real_stdout = sys.stdout
+    # the protocol goes over a private copy of stdout; fd 1 itself is pointed at /dev/null (the reference's FastChem subprocess and its
+    # own prints write there)
+    real_stdout = os.fdopen(os.dup(1), "w")
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 1)
     with contextlib.redirect_stdout(io.StringIO()):
         s = ref_session.setup(refdir)
         var, atm, para, solver = s.var, s.atm, s.para, s.solver
         for _ in range(warm):                                   # a few accepted steps: leaves the dt = 1e-10 start, pages everything in
+            var = s.integ.backup(var)                           # op.py:937-941 (y_prev, atom_loss_prev) as Integration.__call__ does
             var, para = solver.one_step(var, atm, para)
             var = solver.step_size(var, para)
-            var.y_prev, var.ymix_prev = var.y.copy(), var.ymix.copy()
     y0, ymix0, dt0 = var.y.copy(), var.ymix.copy(), var.dt
     print("READY", flush=True, file=real_stdout)
     for line in sys.stdin:

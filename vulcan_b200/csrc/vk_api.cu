@@ -300,9 +300,9 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dt, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->delta, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->status, sizeof(int) * ncol);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->refine_kept, sizeof(int) * 2 * ncol);
-    if (e == cudaSuccess) e = cudaMemset(c->refine_kept, 0, sizeof(int) * 2 * ncol);
-    if (e == cudaSuccess) c->refine_tried = c->refine_kept + ncol;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->refine_kept, sizeof(int) * 3 * ncol);
+    if (e == cudaSuccess) e = cudaMemset(c->refine_kept, 0, sizeof(int) * 3 * ncol);
+    if (e == cudaSuccess) { c->refine_tried = c->refine_kept + ncol; c->refine_act = c->refine_kept + 2 * ncol; }
     c->h_pin_bytes = sizeof(double) * (4 * nv + 4 * (size_t)ncol) + 64;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
     if (e != cudaSuccess) { cuda_fail(e, "vk_column_create allocation"); vk_column_destroy(c); return VK_ERR_CUDA; }

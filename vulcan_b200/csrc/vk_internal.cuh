@@ -122,7 +122,7 @@ struct vk_column {
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
     double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx, *xn;  // work vectors [ncol][nz][ni]
-    int *refine_kept, *refine_tried;          // [ncol] refinement passes kept / tried by the safeguard (refine = auto)
+    int *refine_kept, *refine_tried, *refine_act;   // [ncol] refinement passes kept / tried by the safeguard, active flags (refine = auto)
     double *D, *W;                            // D [ncol][nz][nip][nip] lhs diagonal blocks; W [ncol][nz][nip][nip+2] block LU factors of the Schur blocks
     double *up, *dn;                          // [ncol][nz][nip]
     double *dt, *delta;                       // [ncol]
@@ -151,9 +151,9 @@ int launch_atm_pre(vk_column *c, int ncol_atm);
 // kernels (vk_solve.cu)
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status);
 int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,
-                 const double *dt_pred = nullptr, double dt_min = 0.0);
+                 const int *act = nullptr);
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
-                    double *res, const double *dt_pred = nullptr, double dt_min = 0.0);
+                    double *res, const int *act = nullptr);
 int launch_refine(vk_column *c, const double *D, const double *up, const double *dn, const double *F, const double *rhs, double *x,
                   int refine, const double *dt_pred);
 // kernels (vk_step.cu)

@@ -415,8 +415,7 @@ struct LuSolveArgs {
     const double *rhs;           // [ncol][nz][ni]
     double *x;                   // [ncol][nz][ni]
     double *z;                   // [ncol][nz][NIP] scratch
-    const double *dt;            // optional per-column predicate (refine = auto): columns with dt < dt_min are skipped
-    double dt_min;
+    const int *act;              // optional per-column flags (refine = auto): columns with act == 0 are skipped
 };
 
 template <int NIP, int NBUF>
@@ -439,7 +438,7 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
     double *zv = yv + NIP;                          // NIP  published z_K
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(zv + NIP);   // NBUF mbarriers
     const int col = blockIdx.x, i = threadIdx.x, lane = i & 31, pan = i >> 3;
-    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
+    if (a.act && !a.act[col]) return;
     const bool live = i < NIP;
     const int nz = a.nz, ni = a.ni;
     const double *Fc = a.F + (size_t)col * nz * NIP * LDF;
@@ -555,13 +554,12 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
 // A residual evaluated in plain fp64 carries a rounding error eps |A| |x| of its own - as large as the residual a backward-stable
 // solve leaves - so fp64 refinement cannot lower the budget error (measured on the reference's HD209S system at dt = 2.4e5 s:
 // 7e-6 -> 6e-6 -> 1e-5), whereas the same pass with an exact residual gains 20 - 50 x (7e-6 -> 4e-7 -> 2e-8); DESIGN.md section 4.2.
-// `dt` / `dt_min` (optional): columns whose step size is below the threshold are skipped (refine = auto).
+// `act` (optional): per-column flags, columns with act == 0 are skipped (refine = auto).
 struct ResidArgs {
     int nz, ni, nip;
     const double *D, *up, *dn, *rhs, *x;
     double *res;
-    const double *dt;       // [ncol] or NULL
-    double dt_min;
+    const int *act;         // [ncol] or NULL: columns with act == 0 are skipped (refine = auto)
 };
 struct dd_t { double hi, lo; };
 __device__ __forceinline__ void dd_fma_acc(dd_t &s, double a, double b)
@@ -587,7 +585,7 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
     extern __shared__ double xs[];   // x_j padded
     const int nz = a.nz, ni = a.ni, nip = a.nip;
     const int col = blockIdx.x / nz, j = blockIdx.x % nz;
-    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
+    if (a.act && !a.act[col]) return;
     const int tid = threadIdx.x;
     const size_t vb = ((size_t)col * nz + j) * ni;
     for (int i = tid; i < nip; i += blockDim.x) xs[i] = (i < ni) ? a.x[vb + i] : 0.0;
@@ -617,44 +615,55 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
     }
 }
 
-// xn = x + dx (per column predicate like resid_kernel)
-__global__ void refine_axpy_kernel(size_t per, const double *x, const double *dx, double *xn, const double *dt, double dt_min)
+// refine = auto: which columns are refined at all (step size >= dt_min; every column when dt is NULL)
+__global__ void refine_init_kernel(int ncol, const double *dt, double dt_min, int *act)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < ncol) act[col] = (!dt || dt[col] >= dt_min) ? 1 : 0;
+}
+// xn = x + dx
+__global__ void refine_axpy_kernel(size_t per, const double *x, const double *dx, double *xn, const int *act)
 {
     const int col = blockIdx.y;
-    if (dt && !(dt[col] >= dt_min)) return;
+    if (act && !act[col]) return;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < per; q += (size_t)gridDim.x * blockDim.x)
         xn[col * per + q] = x[col * per + q] + dx[col * per + q];
 }
 
-// Safeguard of one refinement pass (refine = auto): the pass is kept only if it lowers the ELEMENT-WEIGHTED residual - the quantity it is
-// there to protect:  E_a = sum_{j,i} compo[i][a] res[j][i],  measured against  N_a = sum compo[i][a] |x[j][i]|  (scale of element a in x).
-// One block per column; every sum is formed in a fixed order (thread q owns the entries q, q + 256, ...; fixed shared-memory tree), so the
-// decision - and with it the result - is reproducible and independent of the batch a column sits in.
+// Safeguard of a refinement pass (refine = auto): the pass is kept only if it lowers the ELEMENT-WEIGHTED residual - the quantity it is
+// there to protect:  E_a = sum_{j,i} compo[i][a] res[j][i],  weighed per element a against  N_a = sum compo[i][a] |x[j][i]|.
+// A kept pass whose remaining element-budget error  |E_a| r dt / T_a  (T_a = atoms of element a in the column) is still above `tol`
+// leaves the column active for another pass; a rejected pass (the 1-ulp sensitivity of these systems makes ~1 pass in 10 diverge at
+// dt > 1e5 s) ends the refinement of that column.  One block per column; every sum is formed in a fixed order
+// (thread q owns the entries q, q + 256, ...; fixed shuffle tree; warps added 0..7), so the decision - and with it the result - is
+// reproducible and independent of the batch a column sits in.
 struct SelectArgs {
     int nz, ni, na;
     const double *compo;       // [ni][na]
-    const double *res0, *res1; // residual before / after the pass
-    const double *xn;
+    double *res0;              // residual before the pass; receives the residual after it when the pass is kept
+    const double *res1;
+    const double *xn, *y;
     double *x;
-    const double *dt;
-    double dt_min;
+    const double *dt;          // [ncol] or NULL
+    double tol;
+    int *act;
     int *kept, *tried;         // [ncol] counters
 };
 __global__ void __launch_bounds__(256) refine_select_kernel(SelectArgs a)
 {
-    __shared__ double red[3][8][8];      // [quantity][element][warp]
+    __shared__ double red[4][8][8];      // [quantity][element][warp]
     __shared__ int take;
     const int col = blockIdx.x, tid = threadIdx.x, na = a.na;
-    if (a.dt && !(a.dt[col] >= a.dt_min)) return;
+    if (!a.act[col]) return;
     const size_t per = (size_t)a.nz * a.ni, base = col * per;
-    double e0[8], e1[8], nn[8];
-    for (int q = 0; q < 8; q++) e0[q] = e1[q] = nn[q] = 0.0;
+    double e0[8], e1[8], nn[8], tt[8];
+    for (int q = 0; q < 8; q++) e0[q] = e1[q] = nn[q] = tt[q] = 0.0;
     for (size_t q = tid; q < per; q += 256) {
         const int i = (int)(q % a.ni);
-        const double r0 = a.res0[base + q], r1 = a.res1[base + q], ax = fabs(a.x[base + q]);
+        const double r0 = a.res0[base + q], r1 = a.res1[base + q], ax = fabs(a.x[base + q]), ay = a.y ? fabs(a.y[base + q]) : 0.0;
         for (int at = 0; at < na; at++) {
             const double w = a.compo[i * na + at];
-            e0[at] = fma(w, r0, e0[at]); e1[at] = fma(w, r1, e1[at]); nn[at] = fma(w, ax, nn[at]);
+            e0[at] = fma(w, r0, e0[at]); e1[at] = fma(w, r1, e1[at]); nn[at] = fma(w, ax, nn[at]); tt[at] = fma(w, ay, tt[at]);
         }
     }
     for (int at = 0; at < na; at++) {
@@ -662,28 +671,32 @@ __global__ void __launch_bounds__(256) refine_select_kernel(SelectArgs a)
             e0[at] += __shfl_xor_sync(0xffffffffu, e0[at], off);
             e1[at] += __shfl_xor_sync(0xffffffffu, e1[at], off);
             nn[at] += __shfl_xor_sync(0xffffffffu, nn[at], off);
+            tt[at] += __shfl_xor_sync(0xffffffffu, tt[at], off);
         }
-        if ((tid & 31) == 0) { red[0][at][tid >> 5] = e0[at]; red[1][at][tid >> 5] = e1[at]; red[2][at][tid >> 5] = nn[at]; }
+        if ((tid & 31) == 0) { red[0][at][tid >> 5] = e0[at]; red[1][at][tid >> 5] = e1[at]; red[2][at][tid >> 5] = nn[at]; red[3][at][tid >> 5] = tt[at]; }
     }
     __syncthreads();
     if (tid == 0) {
-        double w0 = 0.0, w1 = 0.0;
+        double w0 = 0.0, w1 = 0.0, bud1 = 0.0;
         bool finite = true;
+        const double rdt = a.dt ? (1. + 1. / sqrt(2.)) * a.dt[col] : 0.0;
         for (int at = 0; at < na; at++) {
-            double s0 = 0.0, s1 = 0.0, n = 0.0;
-            for (int w = 0; w < 8; w++) { s0 += red[0][at][w]; s1 += red[1][at][w]; n += red[2][at][w]; }
+            double s0 = 0.0, s1 = 0.0, n = 0.0, t = 0.0;
+            for (int w = 0; w < 8; w++) { s0 += red[0][at][w]; s1 += red[1][at][w]; n += red[2][at][w]; t += red[3][at][w]; }
             if (!(n > 0.0)) continue;
             w0 = fmax(w0, fabs(s0) / n);
             w1 = fmax(w1, fabs(s1) / n);
+            if (t > 0.0) bud1 = fmax(bud1, fabs(s1) * rdt / t);
             finite = finite && (s1 == s1);
         }
         take = (finite && w1 < w0) ? 1 : 0;
-        if (a.tried) a.tried[col] += 1;
-        if (a.kept && take) a.kept[col] += 1;
+        a.tried[col] += 1;
+        if (take) a.kept[col] += 1;
+        a.act[col] = (take && a.dt && a.y && bud1 > a.tol) ? 1 : 0;
     }
     __syncthreads();
     if (take)
-        for (size_t q = tid; q < per; q += 256) a.x[base + q] = a.xn[base + q];
+        for (size_t q = tid; q < per; q += 256) { a.x[base + q] = a.xn[base + q]; a.res0[base + q] = a.res1[base + q]; }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -721,10 +734,9 @@ static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 }
 
 // x = A^{-1} rhs with the stored block LU factors F ([ncol][nz][nip][nip+2]); z is scratch
-int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,
-                 const double *dt_pred, double dt_min)
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z, const int *act)
 {
-    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, dt_pred, dt_min};
+    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, act};
     // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
     // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per
     // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
@@ -741,17 +753,20 @@ int launch_solve(vk_column *c, const double *F, const double *up, const double *
 }
 
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x, double *res,
-                    const double *dt_pred, double dt_min)
+                    const int *act)
 {
-    ResidArgs a{c->nz, c->ni, c->nip, D, up, dn, rhs, x, res, dt_pred, dt_min};
+    ResidArgs a{c->nz, c->ni, c->nip, D, up, dn, rhs, x, res, act};
     resid_kernel<<<c->ncol * c->nz, 512, sizeof(double) * c->nip, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
 
-// x <- A^{-1} rhs refined.  refine > 0: that many passes x += A^{-1}(rhs - A x) with the double-double residual.  refine < 0 (auto): ONE
-// pass on the columns whose step size is >= opts.refine_dt_min (dt_pred = their dt; NULL: every column), kept only if it lowers the
-// element-weighted residual (refine_select_kernel).  Work vectors: c->res, c->dx, c->xn.
+// x <- A^{-1} rhs refined.  refine > 0: that many passes x += A^{-1}(rhs - A x) with the double-double residual.  refine < 0 (AUTO): up
+// to -refine... VK_REFINE_AUTO_PASSES passes on the columns whose step size is >= opts.refine_dt_min (dt_pred = their dt; NULL: every
+// column), each kept only if it lowers the element-weighted residual, until the element-budget error of the solve is below
+// VK_REFINE_BUDGET_TOL (refine_select_kernel).  Work vectors: c->res, c->dx, c->xn; flags c->refine_act.
+#define VK_REFINE_AUTO_PASSES 4
+#define VK_REFINE_BUDGET_TOL 1.0e-11
 int launch_refine(vk_column *c, const double *D, const double *up, const double *dn, const double *F, const double *rhs, double *x,
                   int refine, const double *dt_pred)
 {
@@ -760,10 +775,10 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
     dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, 32), (unsigned)c->ncol);
     if (refine > 0) {
         for (int it = 0; it < refine && rc == VK_OK; it++) {
-            rc = launch_residual(c, D, up, dn, rhs, x, c->res, nullptr, 0.0);
-            if (rc == VK_OK) rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, nullptr, 0.0);
+            rc = launch_residual(c, D, up, dn, rhs, x, c->res, nullptr);
+            if (rc == VK_OK) rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, nullptr);
             if (rc == VK_OK) {
-                refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, x, nullptr, 0.0);
+                refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, x, nullptr);
                 VK_CUDA(cudaGetLastError());
             }
         }
@@ -771,15 +786,21 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
     }
     if (refine == 0) return VK_OK;
     if (!c->opts.compo || c->opts.na < 1) { set_error("refine = auto needs the element composition (vk_step_opts.compo)"); return VK_ERR_INVALID; }
-    const double dmin = c->opts.refine_dt_min;
-    if ((rc = launch_residual(c, D, up, dn, rhs, x, c->res, dt_pred, dmin))) return rc;
-    if ((rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, dt_pred, dmin))) return rc;
-    refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, c->xn, dt_pred, dmin);
+    int *act = c->refine_act;
+    refine_init_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(c->ncol, dt_pred, c->opts.refine_dt_min, act);
     VK_CUDA(cudaGetLastError());
-    if ((rc = launch_residual(c, D, up, dn, rhs, c->xn, c->dx, dt_pred, dmin))) return rc;
-    SelectArgs sa{c->nz, c->ni, c->opts.na, c->opts.compo, c->res, c->dx, c->xn, x, dt_pred, dmin, c->refine_kept, c->refine_tried};
-    refine_select_kernel<<<c->ncol, 256, 0, c->stream>>>(sa);
-    VK_CUDA(cudaGetLastError());
+    if ((rc = launch_residual(c, D, up, dn, rhs, x, c->res, act))) return rc;
+    const int passes = (refine == -1) ? VK_REFINE_AUTO_PASSES : -refine;
+    for (int it = 0; it < passes; it++) {
+        if ((rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, act))) return rc;
+        refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, c->xn, act);
+        VK_CUDA(cudaGetLastError());
+        if ((rc = launch_residual(c, D, up, dn, rhs, c->xn, c->dx, act))) return rc;
+        SelectArgs sa{c->nz, c->ni, c->opts.na, c->opts.compo, c->res, c->dx, c->xn, dt_pred ? c->y : nullptr, x, dt_pred,
+                      VK_REFINE_BUDGET_TOL, act, c->refine_kept, c->refine_tried};
+        refine_select_kernel<<<c->ncol, 256, 0, c->stream>>>(sa);
+        VK_CUDA(cudaGetLastError());
+    }
     return VK_OK;
 }
 

@@ -96,8 +96,10 @@ class PipelinedHostSolver(object):
     host round trip costs max(transfer, compute) instead of their sum.  Pass page-locked arrays (e.g. numpy views of pinned torch
     tensors) to have them DMA'd directly."""
 
-    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=None, device=0, refine=0, compo=None):
+    def __init__(self, network, nz, atm_common, kzz, k, cfg, n_groups=None, device=0, refine=None, compo=None):
         from concurrent.futures import ThreadPoolExecutor
+        if refine is None:
+            refine = -1 if compo is not None else 0        # the product default (auto) needs the element composition
         self.ncol = kzz.shape[0]
         self.nz, self.ni = nz, network.ni
         self.devnet = _abi.DeviceNetwork(network, device)
