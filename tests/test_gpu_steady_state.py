@@ -18,7 +18,7 @@ from helpers import Case, GOLD, have, run_config
 pytestmark = pytest.mark.gpu
 
 
-def run_hd189(refine=0, max_wall_s=600):
+def run_hd189(refine=-1, max_wall_s=600):
     return run_config("HD189", refine, max_wall_s)
 
 
@@ -100,7 +100,9 @@ def test_hd209s_to_steady_state():
     print("\n".join(msg))
     assert para.end_case == 1, "did not converge by the reference's criterion (end_case %d)" % para.end_case
     assert 0.8 * int(ref["count"]) <= para.count <= 1.2 * int(ref["count"])      # measured 1101 vs 1143
-    assert loss < 5e-3                                                            # measured 1.8e-3
+    # measured 9.9e-4 (S; O 6.1e-4, C 2.8e-4) with the default refine = -1; 1.8e-3 ... 5e-3 without refinement or with a single pass: at the
+    # dt = 2.43e5 s plateau the same ill-conditioned system is solved hundreds of times, so a systematic budget error adds up linearly
+    assert loss < 1.5e-3
     # The state the reference's own algorithm settles on depends on which of two step-size plateaus the controller ends on (delta
     # = 0.162 at dt = 2.43e5 s AND at dt = 5.2e4 s; both reference seeds hop from the first to the second after a rejection burst):
     # the remaining tendency |f|/y of the upper layers scales with dt (scripts/steady_residual.py).  On the reference's plateau the GPU
@@ -109,6 +111,62 @@ def test_hd209s_to_steady_state():
     msg2 = "last dt %.3e (reference %.3e): %s plateau" % (var.dt, float(ref["traj"][-1, 3]), "same" if same_plateau else "other")
     print(msg2)
     if same_plateau:
-        assert rel[yr > 1e-4].max() < 2e-2
+        assert rel[yr > 1e-4].max() < 5e-3 and rel[yr > 1e-12].max() < 2e-2
     else:
-        assert rel[yr > 1e-4].max() < 0.3 and np.median(rel[yr > 1e-20]) < 2e-2   # measured 0.125 / 3.4e-3
+        # measured 0.123 / 3.9e-4: H2O / H2 / O above layer 115, where the local truncation error of Ros2 at delta = 0.162 scales with dt
+        assert rel[yr > 1e-4].max() < 0.15 and np.median(rel[yr > 1e-20]) < 2e-3
+        # ON the reference's plateau the agreement is at the reference's own seed-to-seed spread (5e-4 above 1e-4): a second run with two
+        # forced refinement passes at every dt sees 67 instead of 60 rejections, hops to dt = 5.2e4 s like both reference seeds and ends
+        # within 9.3e-4 (> 1e-4) / 2.1e-3 (> 1e-8) / 3.1e-3 (> 1e-12) of the reference's final state, element loss 5.6e-4 (reference 5.8e-4)
+        case2, var2, atm2, para2, integ2, wall2 = run_config("HD209S", refine=2)
+        rel2 = np.abs(var2.ymix - yr) / np.maximum(yr, 1e-300)
+        loss2 = max(abs(v) for v in var2.atom_loss.values())
+        on2 = abs(var2.dt / float(ref["traj"][-1, 3]) - 1.0) < 0.2
+        print("refine=2: %d steps (+%d rejected), last dt %.3e (%s plateau), vs reference: > 1e-4 %.2e, > 1e-8 %.2e, > 1e-12 %.2e, loss %.2e" % (
+            para2.count, para2.delta_count + para2.nega_count + para2.loss_count, var2.dt, "reference's" if on2 else "other",
+            rel2[yr > 1e-4].max(), rel2[yr > 1e-8].max(), rel2[yr > 1e-12].max(), loss2))
+        assert loss2 < 8e-4
+        if on2:
+            assert rel2[yr > 1e-4].max() < 5e-3 and rel2[yr > 1e-12].max() < 2e-2
+
+
+@pytest.mark.parametrize("tag", ["HD189", "HD209S"])
+def test_tightened_stopping_rule_against_the_reference_self_spread(tag):
+    """VERDICT r01 item 1c.  The steady state f(y) = 0 does not depend on the path, so the unmodified reference was run (two hash seeds,
+    oracle/fixed_point_reference.py -> tests/golden/<cfg>_fixedpoint.npz) with its stopping rule tightened from yconv_cri = 0.01 to 1e-8
+    (slope_cri and the yconv_min clause switched off): it NEVER meets it - after 3001 steps HD189 still moves by longdy = 0.02 ... 0.24 per
+    look-back window at dt ~ 6e4 s (the local error delta = 0.162 keeps the controller there), the two seeds differ by 8.4e-3 above 1e-4
+    and one seed drifts by 2.9e-2 within its last 500 steps.  BASELINE's 1e-6 is therefore not a property the reference has against
+    itself; what is required here is that the GPU run, same cfg numbers, ends no farther from either reference seed than the reference's
+    own seed-to-seed + in-run spread."""
+    if not have(tag, "fixedpoint.npz"):
+        pytest.skip("fixture missing")
+    import json
+    fp = np.load("%s/%s_fixedpoint.npz" % (GOLD, tag))
+    info = json.loads(str(fp["info_json"]))
+    tight = json.loads(str(fp["tightened"]))
+    case, var, atm, para, integ, wall = run_config(tag, cfg_edit=dict(yconv_cri=tight["yconv_cri"], slope_cri=tight["slope_cri"],
+                                                                      yconv_min=tight["yconv_min"], count_max=tight["count_max"]), max_wall_s=900)
+    n_rej = para.delta_count + para.nega_count + para.loss_count
+    print("%s tightened on the GPU: %d steps (+%d rejected), t = %.4e s, last dt %.3e, longdy %.3e, end_case %d, wall %.1f s; reference seeds: "
+          "%d / %d steps, t = %.3e / %.3e, longdy %.2e / %.2e, end_case %d / %d, wall %.0f / %.0f s" % (
+              tag, para.count, n_rej, var.t, var.dt, var.longdy, para.end_case, wall, info["seed0"]["count"], info["seed1"]["count"],
+              info["seed0"]["t"], info["seed1"]["t"], info["seed0"]["longdy"], info["seed1"]["longdy"], info["seed0"]["end_case"],
+              info["seed1"]["end_case"], info["seed0"]["wall_s"], info["seed1"]["wall_s"]))
+    worst = {}
+    for thr in ("1e-20", "1e-12", "1e-08", "0.0001"):
+        self_spread = max(info["seed0_vs_seed1_final"][thr][0], info["seed0"]["drift_last_500_steps"][thr][0], info["seed1"]["drift_last_500_steps"][thr][0])
+        self_med = max(info["seed0_vs_seed1_final"][thr][1], info["seed0"]["drift_last_500_steps"][thr][1], info["seed1"]["drift_last_500_steps"][thr][1])
+        for seed in ("seed0", "seed1"):
+            yr = fp["ymix_" + seed]
+            rel = np.abs(var.ymix - yr) / np.maximum(yr, 1e-300)
+            m = yr > float(thr)
+            worst[thr] = max(worst.get(thr, 0.0), float(rel[m].max()))
+            print("  ymix > %s vs %s: max %.2e median %.2e   (reference against itself: max %.2e median %.2e)" % (
+                thr, seed, rel[m].max(), np.median(rel[m]), self_spread, self_med))
+            if thr != "1e-20":       # above 1e-20 the reference differs from itself by factors (3.9: trace species in the upper layers)
+                assert rel[m].max() <= 1.5 * self_spread
+            assert np.median(rel[m]) <= max(3 * self_med, 1e-6)
+    loss = max(abs(v) for v in var.atom_loss.values())
+    print("  element loss %.2e (reference seeds: %.2e / %.2e)" % (loss, max(abs(v) for v in info["seed0"]["atom_loss"]), max(abs(v) for v in info["seed1"]["atom_loss"])))
+    assert loss <= 2.0 * max(max(abs(v) for v in info["seed0"]["atom_loss"]), 3e-4)

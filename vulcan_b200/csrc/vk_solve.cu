@@ -692,7 +692,9 @@ __global__ void __launch_bounds__(256) refine_select_kernel(SelectArgs a)
         take = (finite && w1 < w0) ? 1 : 0;
         a.tried[col] += 1;
         if (take) a.kept[col] += 1;
-        a.act[col] = (take && a.dt && a.y && bud1 > a.tol) ? 1 : 0;
+        // another pass?  with dt and y known: while the remaining element-budget error is above the tolerance; without (component entry
+        // point vk_blocktri_solve): while passes keep being accepted
+        a.act[col] = (take && (!(a.dt && a.y) || bud1 > a.tol)) ? 1 : 0;
     }
     __syncthreads();
     if (take)
