@@ -202,6 +202,31 @@ int vk_ens_run(vk_column *col, int n_steps);
 /* accepted / rejected counters [ncol], model time t [ncol], dt [ncol], y [ncol][nz][ni]; any may be NULL */
 int vk_ens_get_state(vk_column *col, double *y, double *t, double *dt, int *n_accept, int *n_reject);
 
+/* ---- device-resident run to steady state (Integration.__call__ / stop / conv / save_step / update_mu_dz /
+ * update_phi_esc, op.py:808-1105, per column and without a host round trip).  Call after vk_ens_setup + vk_ens_set_state. */
+typedef struct {
+    double st_factor, mtol_conv, atol, yconv_cri, slope_cri, yconv_min, flux_cri, trun_min, runtime;   /* vulcan_cfg (op.py:1018-1087) */
+    int conv_step, count_min, count_max;
+    const unsigned char *conv_ignore_sp;     /* [ni] species left out of conv: conver_ignore + non_gas_sp (op.py:1045-1049) or NULL */
+    int use_photo, ini_update_photo_frq, final_update_photo_frq;   /* photolysis cadence (op.py:800, 818-829); needs vk_photo_setup */
+    int update_frq;                          /* update_mu_dz / update_phi_esc every update_frq accepted steps (op.py:904-906); 0 = never */
+    int pref_indx; double gs, Rp, max_flux;  /* atm.pref_indx, atm.gs, vulcan_cfg.Rp, vulcan_cfg.max_flux (op.py:944-999) */
+    const double *pico;                      /* [nz+1] atm.pico, shared by the batch */
+    const double *ms;                        /* [ni] molar masses as mean_mass reads them (build_atm.py:511-520) */
+    const double *zco, *Hp, *dz;             /* [ncol][nz+1], [ncol][nz], [ncol][nz] initial atm.zco / Hp / dz */
+    int n_diff_esc; const int *diff_esc_idx; /* vulcan_cfg.diff_esc */
+    int hist_cap, hist_stride;               /* ring of accepted states for conv: hist_cap states, every hist_stride-th accepted step
+                                              * (hist_cap = conv_step, hist_stride = 1: the reference's look-back exactly) */
+} vk_steady_opts;
+int vk_ens_setup_steady(vk_column *col, const vk_steady_opts *o);
+/* one photolysis update of every active column from the resident state (vulcan.py:170-176 does one at set-up, before the loop) */
+int vk_ens_photo_update(vk_column *col);
+/* up to max_iterations attempted steps of every column that has not stopped; *n_active_left = columns still running afterwards */
+int vk_ens_run_steady(vk_column *col, int max_iterations, int *n_active_left);
+/* per column: para.end_case (0 = still running, 1 converged, 2 runtime, 3 count_max), var.longdy, var.longdydt, var.aflux_change,
+ * atm.dz [ncol][nz], atm.zco [ncol][nz+1]; any pointer may be NULL */
+int vk_ens_get_steady(vk_column *col, int *end_case, double *longdy, double *longdydt, double *aflux_change, double *dz, double *zco);
+
 /* refine = -1 bookkeeping: refinement passes kept / tried by the safeguard since the handle was created, [ncol] each, may be NULL */
 int vk_refine_stats(vk_column *col, int *kept, int *tried);
 /* timing of the last vk_ros2_solve / vk_ens_run on the handle's stream, measured with CUDA events (ms) */

@@ -341,7 +341,7 @@ def photolysis_via_dropin(tag, step, abi=None):
         ros2_mod._abi = real_abi
 
 
-def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edit=None):
+def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edit=None, device_loop=False):
     """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
     object and the Integration mirror until Integration.stop() says so (op.py:1067-1087).  `abi`: replaces the ctypes binding
     the solver object talks to (only the CPU host-logic tests pass the oracle-backed stand-in of tests/oracle_columns.py)."""
@@ -374,9 +374,36 @@ def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edi
             solver.compute_tau(var, atm)
             solver.compute_flux(var, atm)
             solver.compute_J(var, atm)
-        integ = Integration(solver, cfg, case.net.species, mass=None if cfg.use_moldiff else case.st["ms"])
+        if device_loop:      # the device-resident loop (vulcan_b200/steady.py) instead of the host mirror of op.Integration
+            from vulcan_b200.steady import DeviceIntegration
+            integ = DeviceIntegration(solver)
+            if not cfg.use_moldiff:
+                solver._masses = lambda: case.st["ms"]
+        else:
+            integ = Integration(solver, cfg, case.net.species, mass=None if cfg.use_moldiff else case.st["ms"])
         t0 = time.time()
         var, atm, para = integ(var, atm, para, max_wall_s=max_wall_s)
         return case, var, atm, para, integ, time.time() - t0
     finally:
         ros2_mod._abi = real_abi           # never leak the stand-in into other tests of the same process
+
+
+def steady_ensemble_from_fixture(case, y, atom_ini, kzz_scale, photo=True, **kw):
+    """vulcan_b200.ensemble.SteadyEnsemble for columns derived from one fixture config (its atmosphere, rates, star): the inputs the
+    reference would build per column, assembled from <cfg>_static.npz / <cfg>_step0000.npz"""
+    from vulcan_b200 import ensemble
+    st, fx, cfg = case.st, case.fx, case.cfg
+    akw = case.atm_kwargs()
+    kzz = np.asarray(kzz_scale)[:, None] * np.asarray(akw["Kzz"])[None, :]
+    grid = dict(pico=st["pico"], ms=st["ms"], zco=fx["zco"], Hp=fx["Hp"], dz=fx["dz"], pref_indx=int(st["pref_indx"]), gs=float(cfg["gs"]))
+    ph = None
+    if photo and cfg.get("use_photo"):
+        pt = photo_tables(st)
+        ph = dict(bins=st["bins"], sflux_top=st["sflux_top"], i12=int(st["sflux_din12_indx"]), dbin1=float(st["dbin1"]), dbin2=float(st["dbin2"]),
+                  sl_angle=cfg["sl_angle"], edd=cfg["edd"], flux_atol=cfg["flux_atol"], f_diurnal=cfg["f_diurnal"], abs_idx=st["photo_sp_idx"],
+                  cross_abs=pt["cross"], photo_idx=st["photo_sp_idx"], cross_photo=pt["cross"], scat_idx=st["scat_sp_idx"],
+                  cross_scat=st["cross_scat"], cross_J=st["cross_J"], br_rate_index=st["branch_rate_index"], abs_is_T=pt["abs_is_T"],
+                  cross_abs_T=pt["cross_T"], br_is_T=pt["br_is_T"], cross_J_T=pt["cross_J_T"])
+    sp = list(case.net.species)
+    return ensemble.SteadyEnsemble(case.net, case.nz, y, np.full(y.shape[0], float(cfg["dttry"])), akw, kzz, case.k, cfg, st["compo"], atom_ini,
+                                   st["n_0"], grid, photo=ph, diff_esc_idx=[sp.index(s) for s in cfg.get("diff_esc", []) or []], **kw)

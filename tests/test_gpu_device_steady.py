@@ -1,0 +1,54 @@
+"""Device-resident run to steady state (vulcan_b200/csrc/vk_steady.cu): stop / conv against the on-device history ring, the
+photolysis cadence, update_mu_dz / update_phi_esc and save_step per column with no host round trip inside the loop.
+ 1. one HD189 column: the device loop against the host mirror of the reference's op.Integration driving the SAME kernels through the
+    drop-in class (which the lock-step tests pin to the reference's own trajectory) - same stopping step, same state;
+ 2. a small ensemble of distinct columns: every column converges on its own (different step counts), finished columns are frozen, and a
+    column of the batch ends exactly where the same column ends when it is run alone."""
+import numpy as np
+import pytest
+
+from helpers import Case, GOLD, have, run_config, steady_ensemble_from_fixture
+
+pytestmark = pytest.mark.gpu
+
+
+def test_hd189_device_loop_matches_host_loop():
+    c1, v1, a1, p1, i1, w1 = run_config("HD189")
+    c2, v2, a2, p2, i2, w2 = run_config("HD189", device_loop=True)
+    rel = np.abs(v2.ymix - v1.ymix) / np.maximum(v1.ymix, 1e-300)
+    print("HD189 to steady state: host loop %d steps (+%d rejected) t %.4e in %.2f s | device loop %d steps (+%d rejected) t %.4e in %.2f s "
+          "(end_case %d, longdy %.3e / %.3e) | ymix > 1e-20 max rel diff %.2e, > 1e-8 %.2e" % (
+              p1.count, p1.delta_count + p1.nega_count + p1.loss_count, v1.t, w1, p2.count, i2.n_rejected, v2.t, w2, p2.end_case,
+              v1.longdy, v2.longdy, rel[v1.ymix > 1e-20].max(), rel[v1.ymix > 1e-8].max()))
+    assert p2.end_case == 1
+    # same arithmetic per step (the mean-molecular-weight update differs by the last bits of log()), so the two loops follow each other
+    # until rounding separates the accept / reject decisions: step counts within 2 %, states within the reference's own seed-to-seed spread
+    assert abs(p2.count - p1.count) <= 0.02 * p1.count
+    assert abs(v2.t - v1.t) <= 0.05 * v1.t
+    assert rel[v1.ymix > 1e-8].max() < 5e-3
+    if have("HD189", "full.npz"):
+        yr = np.load("%s/HD189_full.npz" % GOLD)["ymix"]
+        relr = np.abs(v2.ymix - yr) / np.maximum(yr, 1e-300)
+        print("device loop vs the reference's own final state: > 1e-4 %.2e, > 1e-12 %.2e, median(> 1e-20) %.2e" % (
+            relr[yr > 1e-4].max(), relr[yr > 1e-12].max(), np.median(relr[yr > 1e-20])))
+        assert relr[yr > 1e-4].max() < 5e-3 and relr[yr > 1e-12].max() < 2e-2
+
+
+def test_ensemble_runs_every_column_to_its_own_convergence():
+    from vulcan_b200 import ensemble
+    c = Case("HD189", 0)
+    ncol = 6
+    kz = np.array([0.1, 0.3, 1.0, 1.0, 3.0, 10.0])
+    met = np.array([1.0, 1.0, 1.0, 2.0, 1.0, 0.5])
+    co = np.array([0.55, 0.55, 0.55, 0.8, 0.3, 0.55])
+    y, atom_ini = ensemble.synthetic_columns(c.st["y_ini"], c.st["n_0"], c.st["compo"], c.cfg["atom_list"], kz, met, co)
+    runner = steady_ensemble_from_fixture(c, y, atom_ini, kz)
+    out = runner.run_to_steady_state(max_iterations=4000)
+    print("ensemble of %d columns: steps %s rejected %s end_case %s t %s wall %.1f s" % (
+        ncol, out["n_accept"].tolist(), out["n_reject"].tolist(), out["end_case"].tolist(), ["%.2e" % t for t in out["t"]], out["wall_s"]))
+    assert (out["end_case"] == 1).all()
+    assert len(set(out["n_accept"].tolist())) > 1                    # columns stop after different numbers of steps
+    # column 2 (Kzz x 1, solar composition) alone
+    alone = steady_ensemble_from_fixture(c, y[2:3], atom_ini[2:3], kz[2:3]).run_to_steady_state(max_iterations=4000)
+    assert alone["n_accept"][0] == out["n_accept"][2] and alone["t"][0] == out["t"][2]
+    assert np.array_equal(alone["y"][0], out["y"][2])

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
     "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
-    "vk_debug_time_kernel", "vk_refine_stats",
+    "vk_debug_time_kernel", "vk_refine_stats", "vk_ens_setup_steady", "vk_ens_photo_update", "vk_ens_run_steady", "vk_ens_get_steady",
 ]
 
 
@@ -84,6 +84,16 @@ class EnsOpts(C.Structure):
 # eps |A||x| r dt, is < 1e-9 per step on every fixture
 REFINE_DT_MIN = 1.0e3
 
+class SteadyOpts(C.Structure):
+    _fields_ = [("st_factor", C.c_double), ("mtol_conv", C.c_double), ("atol", C.c_double), ("yconv_cri", C.c_double),
+                ("slope_cri", C.c_double), ("yconv_min", C.c_double), ("flux_cri", C.c_double), ("trun_min", C.c_double),
+                ("runtime", C.c_double), ("conv_step", C.c_int), ("count_min", C.c_int), ("count_max", C.c_int),
+                ("conv_ignore_sp", _bp), ("use_photo", C.c_int), ("ini_update_photo_frq", C.c_int), ("final_update_photo_frq", C.c_int),
+                ("update_frq", C.c_int), ("pref_indx", C.c_int), ("gs", C.c_double), ("Rp", C.c_double), ("max_flux", C.c_double),
+                ("pico", _dp), ("ms", _dp), ("zco", _dp), ("Hp", _dp), ("dz", _dp), ("n_diff_esc", C.c_int), ("diff_esc_idx", _ip),
+                ("hist_cap", C.c_int), ("hist_stride", C.c_int)]
+
+
 _lib = None
 
 
@@ -128,6 +138,10 @@ def load():
     lib.vk_device_buffers.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
     lib.vk_stream.argtypes = [_vp, C.POINTER(_vp)]
     lib.vk_refine_stats.argtypes = [_vp, _ip, _ip]
+    lib.vk_ens_setup_steady.argtypes = [_vp, C.POINTER(SteadyOpts)]
+    lib.vk_ens_photo_update.argtypes = [_vp]
+    lib.vk_ens_run_steady.argtypes = [_vp, C.c_int, _ip]
+    lib.vk_ens_get_steady.argtypes = [_vp, _ip, _dp, _dp, _dp, _dp, _dp]
     lib.vk_debug_time_kernel.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = lib
     return lib
@@ -451,6 +465,43 @@ class Columns(object):
 
     def ens_run(self, n_steps):
         check(self.lib.vk_ens_run(self.handle, int(n_steps)))
+
+    def ens_setup_steady(self, cfg, pico, ms, zco, Hp, dz, pref_indx, gs, conv_ignore_sp=None, diff_esc_idx=(), hist_cap=None,
+                         hist_stride=1, use_photo=None):
+        """device-resident run to steady state (vk_ens_setup_steady): cfg = mapping or object with the vulcan_cfg names read by
+        Integration.stop / conv / __call__ (op.py:808-1087); zco / Hp / dz [ncol, nz(+1)] or one column's arrays (broadcast)."""
+        g = (lambda n, d=None: cfg.get(n, d)) if isinstance(cfg, dict) else (lambda n, d=None: getattr(cfg, n, d))
+        nz, ncol = self.nz, self.ncol
+        rep = lambda a, tail: f64(np.broadcast_to(f64(a), (ncol,) + tail))
+        keep = dict(pico=f64(pico), ms=f64(ms), zco=rep(zco, (nz + 1,)), Hp=rep(Hp, (nz,)), dz=rep(dz, (nz,)))
+        ig = None if conv_ignore_sp is None else u8(conv_ignore_sp)
+        de = i32(diff_esc_idx) if len(diff_esc_idx) else None
+        conv_step = int(g("conv_step"))
+        cap = conv_step if hist_cap is None else int(hist_cap)
+        up = bool(g("use_photo")) if use_photo is None else bool(use_photo)
+        o = SteadyOpts(float(g("st_factor")), float(g("mtol_conv")), float(g("atol")), float(g("yconv_cri")), float(g("slope_cri")),
+                       float(g("yconv_min")), float(g("flux_cri")), float(g("trun_min")), float(g("runtime")), conv_step,
+                       int(g("count_min")), int(g("count_max")), bptr(ig), int(up), int(g("ini_update_photo_frq", 100) or 100),
+                       int(g("final_update_photo_frq", 5) or 5), int(g("update_frq", 0) or 0), int(pref_indx), float(gs), float(g("Rp")),
+                       float(g("max_flux", 1e13) or 1e13), dptr(keep["pico"]), dptr(keep["ms"]), dptr(keep["zco"]), dptr(keep["Hp"]),
+                       dptr(keep["dz"]), 0 if de is None else len(de), iptr(de), cap, int(hist_stride))
+        check(self.lib.vk_ens_setup_steady(self.handle, C.byref(o)))
+
+    def ens_photo_update(self):
+        check(self.lib.vk_ens_photo_update(self.handle))
+
+    def ens_run_steady(self, max_iterations):
+        left = C.c_int(0)
+        check(self.lib.vk_ens_run_steady(self.handle, int(max_iterations), C.byref(left)))
+        return left.value
+
+    def ens_get_steady(self, want_grid=False):
+        ec = np.zeros(self.ncol, dtype=np.int32)
+        ld, ldt, ch = np.empty(self.ncol), np.empty(self.ncol), np.empty(self.ncol)
+        dz = np.empty((self.ncol, self.nz)) if want_grid else None
+        zco = np.empty((self.ncol, self.nz + 1)) if want_grid else None
+        check(self.lib.vk_ens_get_steady(self.handle, iptr(ec), dptr(ld), dptr(ldt), dptr(ch), dptr(dz), dptr(zco)))
+        return dict(end_case=ec, longdy=ld, longdydt=ldt, aflux_change=ch, dz=dz, zco=zco)
 
     def ens_get_state(self, want_y=True):
         y = np.empty((self.ncol, self.nz, self.ni)) if want_y else None

@@ -66,10 +66,10 @@ int vk_step_device_impl(vk_column *c)
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
     if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc; // block LU factors F_j of the Schur blocks (c->W)
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z))) return rc;                   // k1                op.py:2914
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act))) return rc;           // k1                op.py:2914
     if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->f, c->k1, c->opts.refine, c->dt))) return rc;
     if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z))) return rc;                 // k2                op.py:2929
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z, c->act))) return rc;         // k2                op.py:2929
     if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->rhs, c->k2, c->opts.refine, c->dt))) return rc;
     if ((rc = launch_epilogue(c))) return rc;                                                       // sol, delta, ymix  op.py:2932-2993
     VK_CUDA(cudaEventRecord(c->ev3, c->stream));

@@ -44,11 +44,12 @@ __device__ __forceinline__ double phi_br(const AtmLayer &L, int m, int i, double
 //   QB : interior 1./dz_ave*Dzz[j]/dzi[j]      ; j=0: 1./dzi0*(D0/dzi0)            ; top: -1./dzi_m*(Dm/dzi_m)   (the A quotient)
 //   QC : interior 1./dz_ave*Dzz[j-1]/dzi[j-1]  ; j=0: -1./dzi0*(D0/dzi0) (A quot.) ; top:  1./dzi_m*(Dm/dzi_m)
 //   TA/TB/TC : thermal-gravity terms; SA/SB/SC : settling terms (signs applied by the consumer exactly as op.py does)
-__global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p)
+__global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p, const int *pred)
 {
     const int nz = a.nz, ni = a.ni;
     const int col = blockIdx.x / nz, j = blockIdx.x % nz;
     if (col >= ncol_atm) return;
+    if (pred && !pred[col]) return;
     const AtmLayer L = atm_at(a, col);
     const double *dzi = L.dzi, *Dzz = L.Dzz, *vs = L.vs, *g = L.g;
     const size_t base = ((size_t)col * nz + j) * ni;
@@ -169,7 +170,15 @@ __global__ void atm_pre_kernel(AtmDev a, int ncol_atm, AtmPre p)
 
 int launch_atm_pre(vk_column *c, int ncol_atm)
 {
-    atm_pre_kernel<<<ncol_atm * c->nz, 96, 0, c->stream>>>(c->atm, ncol_atm, c->atm.pre);
+    atm_pre_kernel<<<ncol_atm * c->nz, 96, 0, c->stream>>>(c->atm, ncol_atm, c->atm.pre, nullptr);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+// re-evaluation for the columns whose grid update_mu_dz has just changed (vk_steady.cu); per-column atmosphere only
+int launch_atm_pre_pred(vk_column *c, const int *pred)
+{
+    if (c->atm.pre_cs == 0 && c->ncol > 1) { set_error("per-column atmosphere needed"); return VK_ERR_INVALID; }
+    atm_pre_kernel<<<c->ncol * c->nz, 96, 0, c->stream>>>(c->atm, c->ncol, c->atm.pre, pred);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
@@ -253,6 +262,7 @@ struct RhsArgs {
     double *yk2_out;        // stage 2: store y + k1/r
     double *out_sum, *out_chem, *out_diff;  // any may be NULL; out_sum = chem + diff (stage 2: - 2/(r h) k1)
     const unsigned char *fix_mask;          // rows forced to zero (op.py:2896-2925)
+    const int *act;                         // [ncol] or NULL: stopped columns are skipped
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
     const int lay = blockIdx.x * RHS_WPB + w;
     if (lay >= n_layers_total) return;
     const int col = lay / nz, j = lay % nz;
+    if (A.act && !A.act[col]) return;
     double *ws = sm + (size_t)w * SL.total;
     double *ym = ws + SL.ym, *y0 = ws + SL.y0, *yp = ws + SL.yp, *v = ws + SL.v, *chem_s = ws + SL.chem;
     LayerScal *S = reinterpret_cast<LayerScal *>(ws + SL.scal);
@@ -514,6 +525,7 @@ struct LhsArgs {
     double *up, *dn;     // [ncol][nz][ld]
     int ld;              // nip for the solver layout, ni for the dense diagnostic output
     const unsigned char *fix_mask;
+    const int *act;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -557,6 +569,7 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
     extern __shared__ __align__(16) double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
     const int col = blockIdx.x / blocks_per_col, j0 = (blockIdx.x % blocks_per_col) * lpb;
+    if (A.act && !A.act[col]) return;
     const int j1 = min(j0 + lpb, nz);
     const int tid = threadIdx.x, nt = blockDim.x;
     double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
@@ -849,7 +862,7 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs;
     a.k1 = k1_for_rhs2; a.dt = dt_dev; a.yk2_out = k1_for_rhs2 ? c->yk2 : nullptr;
     a.out_sum = out_sum; a.out_chem = out_chem; a.out_diff = out_diff;
-    a.fix_mask = c->opts.fix_mask;
+    a.fix_mask = c->opts.fix_mask; a.act = c->act;
     const RhsWarpSmem SL = rhs_warp_layout(c->ni, c->nr);
     const size_t smem = sizeof(double) * (size_t)RHS_WPB * SL.total + sizeof(uchar4) * (c->nr + 2) +
                         sizeof(unsigned short) * (a.net.n_rhs + 8) + 16;
@@ -864,7 +877,7 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
 {
     LhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
-    a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask;
+    a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask; a.act = c->act;
     if (!a.net.lhs_ml_ok) {
         set_error("network exceeds the packing limits of the Jacobian kernel (nr < 2048, ni < 127, < 8191 distinct products, coefficients in +-{1,2,3,4})");
         return VK_ERR_UNSUPPORTED;

@@ -7,17 +7,7 @@
 //     rejected: y restored, dt *= dt_var_min, counters (op.py:2495-2534); retried by the next iteration.  As in the reference
 //               (reset_y restores y but not ymix, op.py:2530) the mixing ratios of the rejected solution are kept for the
 //               significance mask of the retry.
-#include "vk_internal.cuh"
-
-struct EnsState {
-    double rtol, loss_eps, dt_min, dt_max, dt_var_min, dt_var_max, pos_cut, nega_cut;
-    int na;
-    double *compo, *atom_ini, *n_0;       // [ni][na], [ncol][na], [ncol][nz]
-    double *atom_sum, *atom_loss_prev;    // [ncol][na]
-    double *small_y, *nega_y, *t;         // [ncol]
-    int *anyneg, *accept, *n_accept, *n_reject, *n_delta, *n_nega, *n_loss;   // [ncol]
-    std::vector<void *> allocs;
-};
+#include "vk_ens_state.cuh"
 
 namespace vk {
 
@@ -41,12 +31,18 @@ struct CtlArgs {
     const int *anyneg, *status;
     double *atom_loss_prev, *dt, *t;
     int *accept, *n_accept, *n_reject, *n_delta, *n_nega, *n_loss;
+    // steady-state driver (vk_steady.cu) or NULL / 0: columns that stopped are skipped; an accepted step records its time, flags the
+    // update_mu_dz cadence (op.py:904: count % update_frq == 0 with the count BEFORE save_step) and marks the column fresh
+    const int *act;
+    int *fresh, *do_mu;
+    double *t_time; int cap_t, update_frq;
 };
 
 __global__ void control_kernel(CtlArgs a)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= a.ncol) return;
+    if (a.act && !a.act[col]) { a.accept[col] = 0; if (a.do_mu) a.do_mu[col] = 0; return; }
     const double delta = a.delta[col];
     double dloss = 0.0;
     double loss[8];
@@ -70,8 +66,11 @@ __global__ void control_kernel(CtlArgs a)
         // mixing ratios of the failed attempt (ymix is not restored by reset_y), i.e. the attempt is effectively accepted
         if (dt < a.dt_min) { dt = a.dt_min; acc = 2; }
     }
+    if (a.fresh) a.fresh[col] = acc ? 1 : 0;
+    if (a.do_mu) a.do_mu[col] = (acc && a.update_frq > 0 && (a.n_accept[col] % a.update_frq) == 0) ? 1 : 0;
     if (acc) {
         a.t[col] += dt;                                                                                        // save_step op.py:1091
+        if (a.t_time && a.n_accept[col] < a.cap_t) a.t_time[(size_t)col * a.cap_t + a.n_accept[col]] = a.t[col];
         a.n_accept[col] += 1;
         {
             for (int q = 0; q < a.na; q++) a.atom_loss_prev[col * a.na + q] = loss[q];                        // backup op.py:941
@@ -94,12 +93,23 @@ struct ApplyArgs {
     const int *accept;
     const double *sol, *ymix_new, *n_0;
     double *y, *ymix;
+    const int *act;
+    // history ring of the steady-state driver: the state after accepted step number c = n_accept - 1 goes to slot (c / stride) % cap
+    // when c is a multiple of stride
+    double *hist; int hist_cap, hist_stride;
+    const int *n_accept;
 };
 __global__ void apply_kernel(ApplyArgs a)
 {
     const int col = blockIdx.y;
+    if (a.act && !a.act[col]) return;
     const int acc = a.accept[col];
     const size_t per = (size_t)a.nz * a.ni;
+    double *hslot = nullptr;
+    if (acc && a.hist) {
+        const int cidx = a.n_accept[col] - 1;              // control_kernel has already counted this step
+        if (cidx % a.hist_stride == 0) hslot = a.hist + ((size_t)col * a.hist_cap + (cidx / a.hist_stride) % a.hist_cap) * per;
+    }
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < per; q += (size_t)gridDim.x * blockDim.x) {
         const size_t g = col * per + q;
         const double ym = a.ymix_new[g];
@@ -111,9 +121,36 @@ __global__ void apply_kernel(ApplyArgs a)
                 gas = false;
                 for (int s = 0; s < a.n_gas; s++) gas = gas || (a.gas_indx[s] == i);
             }
-            a.y[g] = gas ? a.n_0[(size_t)col * a.nz + j] * ym : a.sol[g];   // hydrostatic rescale op.py:909-914
+            const double v = gas ? a.n_0[(size_t)col * a.nz + j] * ym : a.sol[g];   // hydrostatic rescale op.py:909-914
+            a.y[g] = v;
+            if (hslot) hslot[q] = v;                       // save_step: y_time.append(var.y) (op.py:1093)
         }
     }
+}
+
+int launch_ens_control(vk_column *c)
+{
+    EnsState *e = c->ens;
+    const bool st = e->steady_set && c->act;
+    CtlArgs a{c->ncol, e->na, e->rtol, e->loss_eps, e->dt_min, e->dt_max, e->dt_var_min, e->dt_var_max, e->atom_sum, e->atom_ini,
+              c->delta, e->anyneg, c->status, e->atom_loss_prev, c->dt, e->t, e->accept, e->n_accept, e->n_reject, e->n_delta,
+              e->n_nega, e->n_loss, c->act, st ? e->steady.fresh : nullptr, st ? e->steady.do_mu : nullptr,
+              st ? e->steady.t_time : nullptr, st ? e->steady.cap_t : 0, st ? e->steady.update_frq : 0};
+    control_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(a);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+
+int launch_ens_apply(vk_column *c)
+{
+    EnsState *e = c->ens;
+    const bool st = e->steady_set && c->act;
+    ApplyArgs b{c->nz, c->ni, c->atm.n_gas, c->atm.gas_indx, e->accept, c->sol, c->ymix_out, e->n_0, c->y, c->ymix, c->act,
+                st ? e->steady.hist : nullptr, st ? e->steady.hist_cap : 1, st ? e->steady.hist_stride : 1, e->n_accept};
+    dim3 grid((unsigned)std::min<size_t>(((size_t)c->nz * c->ni + 255) / 256, 64), (unsigned)c->ncol);
+    apply_kernel<<<grid, 256, 0, c->stream>>>(b);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
 }
 
 template <typename T>
@@ -141,6 +178,7 @@ int vk_ens_setup(vk_column *c, const vk_ens_opts *o)
     VK_CUDA(cudaStreamSynchronize(c->stream));
     ens_destroy(c);
     EnsState *e = new EnsState();
+    e->steady_set = false;
     c->ens = e;
     e->rtol = o->rtol; e->loss_eps = o->loss_eps; e->dt_min = o->dt_min; e->dt_max = o->dt_max; e->dt_var_min = o->dt_var_min;
     e->dt_var_max = o->dt_var_max; e->pos_cut = o->pos_cut; e->nega_cut = o->nega_cut; e->na = o->na;
@@ -213,15 +251,8 @@ int vk_ens_run(vk_column *c, int n_steps)
         rc = launch_clip(c, c->sol, c->ymix_out, c->ymix_out, e->na, e->compo, nullptr, e->pos_cut, e->nega_cut, e->atom_sum,
                          e->small_y, e->nega_y, e->anyneg);
         if (rc) break;
-        CtlArgs a{c->ncol, e->na, e->rtol, e->loss_eps, e->dt_min, e->dt_max, e->dt_var_min, e->dt_var_max, e->atom_sum, e->atom_ini,
-                  c->delta, e->anyneg, c->status, e->atom_loss_prev, c->dt, e->t, e->accept, e->n_accept, e->n_reject, e->n_delta,
-                  e->n_nega, e->n_loss};
-        control_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(a);
-        ApplyArgs b{c->nz, c->ni, c->atm.n_gas, c->atm.gas_indx, e->accept, c->sol, c->ymix_out, e->n_0, c->y, c->ymix};
-        dim3 grid((unsigned)std::min<size_t>(((size_t)c->nz * c->ni + 255) / 256, 64), (unsigned)c->ncol);
-        apply_kernel<<<grid, 256, 0, c->stream>>>(b);
-        cudaError_t ce = cudaGetLastError();
-        if (ce != cudaSuccess) rc = cuda_fail(ce, "ensemble control kernels");
+        rc = launch_ens_control(c);
+        if (rc == VK_OK) rc = launch_ens_apply(c);
     }
     (void)e0; (void)e3;
     cudaEventRecord(run1, c->stream);

@@ -136,6 +136,7 @@ struct vk_column {
     size_t h_pin_bytes;
     PhotoState *photo;
     EnsState *ens;
+    const int *act;             // steady-state driver: columns with act == 0 have stopped and are skipped by every kernel of the step (else NULL)
     // persistent scratch of vk_clip_loss (device doubles / ints + one pinned host mirror)
     double *clip_d, *clip_h;
     int *clip_i;
@@ -148,6 +149,7 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
 int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dense_out_ni, double *D_out, double *up_out,
                double *dn_out);
 int launch_atm_pre(vk_column *c, int ncol_atm);
+int launch_atm_pre_pred(vk_column *c, const int *pred);
 // kernels (vk_solve.cu)
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status);
 int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,

@@ -37,6 +37,7 @@ struct FluxArgs {
     double sl_angle, edd, flux_atol;
     double *tau, *sflux, *dflux_u, *dflux_d, *aflux;
     unsigned long long *change_bits;
+    const int *pred;           // [ncol] or NULL: only the flagged columns are updated (device-resident cadence, vk_steady.cu)
 };
 
 struct Coef { double chi, xi, phi, i_u, i_d; };
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
 {
     const int nz = a.nz, ni = a.ni, nbin = a.nbin;
     const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const bool live = gid < (size_t)a.ncol * nbin;
+    const bool live = gid < (size_t)a.ncol * nbin && (!a.pred || a.pred[gid / nbin]);
     double change = 0.0;
     bool has = false;
     if (live) {
@@ -150,6 +151,7 @@ struct JArgs {
     double *J;       // [ncol][n_br][nz]
     double *k;       // device k
     size_t k_cs;
+    const int *pred;
 };
 
 __global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
     const size_t nw = (size_t)a.ncol * a.n_br * a.nz;
     if (w >= nw) return;
     const int j = (int)(w % a.nz), br = (int)((w / a.nz) % a.n_br), col = (int)(w / ((size_t)a.nz * a.n_br));
+    if (a.pred && !a.pred[col]) return;
     const double *f = a.aflux + ((size_t)col * a.nz + j) * a.nbin;
     const double *c = (a.br_is_T && a.br_is_T[br]) ? a.cross_J_T + ((size_t)br * a.nz + j) * a.nbin : a.cross_J + (size_t)br * a.nbin;
     double s1 = 0.0, s2 = 0.0;
@@ -261,8 +264,24 @@ int vk_photo_reset(vk_column *c)
     return VK_OK;
 }
 
-// device-resident update (y, ymix already in c->y / c->ymix, dz in photo->dz)
-int vk_photo_update_device(vk_column *c, const double *y_dev, const double *ymix_dev)
+}  // extern "C"
+
+namespace vk {
+__global__ void photo_begin_kernel(int ncol, const int *pred, unsigned long long *bits)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < ncol && (!pred || pred[col])) bits[col] = 0ull;
+}
+__global__ void photo_end_kernel(int ncol, const int *pred, const unsigned long long *bits, double *change)
+{
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col < ncol && (!pred || pred[col])) change[col] = __longlong_as_double((long long)bits[col]);
+}
+
+// device-resident update: y, ymix, dz on the device; pred (optional) selects the columns; aflux_change_out (optional, device) receives
+// var.aflux_change of the updated columns
+int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_dev, const double *dz_dev, const int *pred,
+                        double *aflux_change_out)
 {
     PhotoState *p = c->photo;
     FluxArgs a;
@@ -271,11 +290,12 @@ int vk_photo_update_device(vk_column *c, const double *y_dev, const double *ymix
     a.abs_idx = p->abs_idx; a.photo_idx = p->photo_idx; a.scat_idx = p->scat_idx;
     a.cross_abs = p->cross_abs; a.cross_abs_T = p->cross_abs_T; a.cross_photo = p->cross_photo; a.cross_scat = p->cross_scat;
     a.abs_is_T = p->abs_is_T;
-    a.y = y_dev; a.ymix = ymix_dev; a.dz = p->dz; a.sflux_top = p->sflux_top; a.bins = p->bins;
+    a.y = y_dev; a.ymix = ymix_dev; a.dz = dz_dev; a.sflux_top = p->sflux_top; a.bins = p->bins;
     a.sl_angle = p->sl_angle; a.edd = p->edd; a.flux_atol = p->flux_atol;
     a.tau = p->tau; a.sflux = p->sflux; a.dflux_u = p->dflux_u; a.dflux_d = p->dflux_d; a.aflux = p->aflux;
-    a.change_bits = p->change_bits;
-    VK_CUDA(cudaMemsetAsync(p->change_bits, 0, sizeof(unsigned long long) * c->ncol, c->stream));
+    a.change_bits = p->change_bits; a.pred = pred;
+    const int nb = (c->ncol + 127) / 128;
+    photo_begin_kernel<<<nb, 128, 0, c->stream>>>(c->ncol, pred, p->change_bits);
     const size_t nthr = (size_t)c->ncol * p->nbin;
     flux_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
@@ -283,12 +303,16 @@ int vk_photo_update_device(vk_column *c, const double *y_dev, const double *ymix
     ja.nz = c->nz; ja.nbin = p->nbin; ja.i12 = p->i12; ja.n_br = p->n_br; ja.ncol = c->ncol; ja.nr = c->nr;
     ja.dbin1 = p->dbin1; ja.dbin2 = p->dbin2; ja.f_diurnal = p->f_diurnal;
     ja.aflux = p->aflux; ja.cross_J = p->cross_J; ja.cross_J_T = p->cross_J_T; ja.br_is_T = p->br_is_T;
-    ja.br_rate_index = p->br_rate_index; ja.J = p->J; ja.k = c->k; ja.k_cs = c->k_cs;
+    ja.br_rate_index = p->br_rate_index; ja.J = p->J; ja.k = c->k; ja.k_cs = c->k_cs; ja.pred = pred;
     const size_t nwarp = (size_t)c->ncol * p->n_br * c->nz;
     jrate_kernel<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, c->stream>>>(ja);
+    if (aflux_change_out) photo_end_kernel<<<nb, 128, 0, c->stream>>>(c->ncol, pred, p->change_bits, aflux_change_out);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
+}  // namespace vk
+
+extern "C" {
 
 int vk_photo_update(vk_column *c, const double *y, const double *ymix, const double *dz, double *J, double *aflux_change)
 {
@@ -301,7 +325,7 @@ int vk_photo_update(vk_column *c, const double *y, const double *ymix, const dou
     VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->ymix, ymix, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(p->dz, dz, sizeof(double) * c->ncol * c->nz, cudaMemcpyHostToDevice, c->stream));
-    int rc = vk_photo_update_device(c, c->y, c->ymix);
+    int rc = photo_update_device(c, c->y, c->ymix, p->dz, nullptr, nullptr);
     if (rc) return rc;
     if (J) VK_CUDA(cudaMemcpyAsync(J, p->J, sizeof(double) * (size_t)c->ncol * p->n_br * c->nz, cudaMemcpyDeviceToHost, c->stream));
     std::vector<unsigned long long> bits(c->ncol);

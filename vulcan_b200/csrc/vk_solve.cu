@@ -84,6 +84,7 @@ struct FactorArgs {
     const double *dn;
     double *F;           // [ncol][nz][NIP][NIP+2] block LU factors of S_j for the solve sweeps (row stride NIP+2: conflict-free LDS.128)
     int *status;         // [ncol]
+    const int *act;      // [ncol] or NULL: stopped columns are skipped
 };
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor pipe: lane 4g+t supplies A[g][t], B[t][g], C[g][2t..2t+1]
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     void *mbar = hraw + 128;             // mbarrier of the TMA prefetch
 
     const int col = blockIdx.x;
+    if (a.act && !a.act[col]) return;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int w = C::SPREAD ? wid - (wid >> 2) : wid;     // column-warp index (meaningless for the other warps)
     const int tid = w * 32 + lane;                         // thread index among the column warps
@@ -616,10 +618,10 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
 }
 
 // refine = auto: which columns are refined at all (step size >= dt_min; every column when dt is NULL)
-__global__ void refine_init_kernel(int ncol, const double *dt, double dt_min, int *act)
+__global__ void refine_init_kernel(int ncol, const double *dt, double dt_min, const int *col_act, int *act)
 {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col < ncol) act[col] = (!dt || dt[col] >= dt_min) ? 1 : 0;
+    if (col < ncol) act[col] = ((!dt || dt[col] >= dt_min) && (!col_act || col_act[col])) ? 1 : 0;
 }
 // xn = x + dx
 __global__ void refine_axpy_kernel(size_t per, const double *x, const double *dx, double *xn, const int *act)
@@ -706,7 +708,7 @@ template <int NIP, int MINB>
 static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
 {
     using C = FactorCfg<NIP>;
-    FactorArgs a{c->nz, c->ni, D, up, dn, F, status};
+    FactorArgs a{c->nz, c->ni, D, up, dn, F, status, c->act};
     { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB>, c->net->device, C::SMEM); if (rc) return rc; }
     factor_kernel<NIP, MINB><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
@@ -777,10 +779,10 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
     dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, 32), (unsigned)c->ncol);
     if (refine > 0) {
         for (int it = 0; it < refine && rc == VK_OK; it++) {
-            rc = launch_residual(c, D, up, dn, rhs, x, c->res, nullptr);
-            if (rc == VK_OK) rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, nullptr);
+            rc = launch_residual(c, D, up, dn, rhs, x, c->res, c->act);
+            if (rc == VK_OK) rc = launch_solve(c, F, up, dn, c->res, c->dx, c->z, c->act);
             if (rc == VK_OK) {
-                refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, x, nullptr);
+                refine_axpy_kernel<<<grid, 256, 0, c->stream>>>(per, x, c->dx, x, c->act);
                 VK_CUDA(cudaGetLastError());
             }
         }
@@ -789,7 +791,7 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
     if (refine == 0) return VK_OK;
     if (!c->opts.compo || c->opts.na < 1) { set_error("refine = auto needs the element composition (vk_step_opts.compo)"); return VK_ERR_INVALID; }
     int *act = c->refine_act;
-    refine_init_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(c->ncol, dt_pred, c->opts.refine_dt_min, act);
+    refine_init_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(c->ncol, dt_pred, c->opts.refine_dt_min, c->act, act);
     VK_CUDA(cudaGetLastError());
     if ((rc = launch_residual(c, D, up, dn, rhs, x, c->res, act))) return rc;
     const int passes = (refine == -1) ? VK_REFINE_AUTO_PASSES : -refine;

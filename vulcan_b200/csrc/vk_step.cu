@@ -14,6 +14,7 @@ struct EpiArgs {
     StepOptsDev o;
     int n_gas;
     const int *gas_indx;
+    const int *act;
 };
 
 __global__ void __launch_bounds__(128) epilogue_kernel(EpiArgs a)
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(128) epilogue_kernel(EpiArgs a)
     extern __shared__ double sm[];
     const int nz = a.nz, ni = a.ni;
     const int col = blockIdx.x / nz, j = blockIdx.x % nz;
+    if (a.act && !a.act[col]) return;
     const int tid = threadIdx.x;
     double *srow = sm;          // ni
     double *tmp = sm + ni;      // ni
@@ -71,7 +73,7 @@ int launch_epilogue(vk_column *c)
     a.sol = c->sol; a.ymix_out = c->ymix_out;
     a.delta_bits = reinterpret_cast<unsigned long long *>(c->delta);
     a.o = c->opts;
-    a.n_gas = c->atm.n_gas; a.gas_indx = c->atm.gas_indx;
+    a.n_gas = c->atm.n_gas; a.gas_indx = c->atm.gas_indx; a.act = c->act;
     VK_CUDA(cudaMemsetAsync(c->delta, 0, sizeof(double) * c->ncol, c->stream));
     epilogue_kernel<<<c->ncol * c->nz, 128, sizeof(double) * 2 * c->ni, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
@@ -93,6 +95,7 @@ struct ClipArgs {
     double *atom_sum;                 // [ncol][na]
     double *small_y, *nega_y;         // [ncol] accumulated
     int *any_negative;                // [ncol]
+    const int *act;
 };
 
 __global__ void __launch_bounds__(256) clip_kernel(ClipArgs a)
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) clip_kernel(ClipArgs a)
     extern __shared__ double sm[];
     const int nz = a.nz, ni = a.ni, na = a.na;
     const int col = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (a.act && !a.act[col]) return;
     double *red = sm;                 // nt * (na + 2)
     double *yc = a.y + (size_t)col * nz * ni;
     const double *ymc = a.ymix_in + (size_t)col * nz * ni;
@@ -147,7 +151,7 @@ int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *
 {
     if (na > 8) { set_error("at most 8 elements in atom_list are supported"); return VK_ERR_UNSUPPORTED; }
     ClipArgs a{c->nz, c->ni, na, y_dev, ymix_in_dev, ymix_out_dev, compo_dev, skip_dev, pos_cut, nega_cut, c->opts.mtol,
-               c->atm.n_gas, c->atm.gas_indx, atom_sum_dev, small_dev, nega_dev, anyneg_dev};
+               c->atm.n_gas, c->atm.gas_indx, atom_sum_dev, small_dev, nega_dev, anyneg_dev, c->act};
     const int nt = 256;
     const size_t smem = sizeof(double) * (size_t)nt * (na + 2);      // <= 20 KB
     clip_kernel<<<c->ncol, nt, smem, c->stream>>>(a);

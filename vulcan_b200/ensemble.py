@@ -89,6 +89,52 @@ class EnsembleRunner(object):
         return self.col.ens_get_state(want_y)
 
 
+class SteadyEnsemble(EnsembleRunner):
+    """An ensemble advanced to per-column steady state entirely on the device (vk_ens_setup_steady / vk_ens_run_steady): every column
+    stops on its own convergence test (Integration.stop / conv, op.py:1018-1087) and is frozen from then on; per column (steps, t, status)
+    are gathered at the end.
+
+    grid: dict(pico [nz+1], ms [ni], zco [nz+1], Hp [nz], dz [nz], pref_indx, gs) - what update_mu_dz reads (op.py:944-984);
+    photo: None or the keyword arguments of _abi.Columns.photo_setup (the sweep shares the star and the cross sections; J rates are per
+    column, so k is replicated per column)."""
+
+    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, grid, photo=None, device=0, refine=-1,
+                 hist_cap=None, hist_stride=None, diff_esc_idx=(), conv_ignore_sp=None):
+        ncol = y.shape[0]
+        if photo is not None and ncol > 1 and np.ndim(k) == 2:
+            k = np.ascontiguousarray(np.broadcast_to(np.asarray(k, dtype=np.float64), (ncol,) + np.shape(k)))
+        EnsembleRunner.__init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=device, refine=refine)
+        if photo is not None:
+            self.col.photo_setup(**photo)
+        conv_step = int(cfg["conv_step"])
+        if hist_cap is None:
+            # the exact look-back (every accepted state of the last conv_step steps) while it fits ~8 GB, else a thinned ring
+            per_state = nz * network.ni * 8
+            hist_cap = max(8, min(conv_step, int(8e9 // (per_state * ncol))))
+        if hist_stride is None:
+            hist_stride = max(1, -(-conv_step // hist_cap))
+        self.hist_cap, self.hist_stride = int(hist_cap), int(hist_stride)
+        self.col.ens_setup_steady(cfg, grid["pico"], grid["ms"], grid["zco"], grid["Hp"], grid["dz"], grid["pref_indx"], grid["gs"],
+                                  conv_ignore_sp=conv_ignore_sp, diff_esc_idx=diff_esc_idx, hist_cap=self.hist_cap,
+                                  hist_stride=self.hist_stride, use_photo=photo is not None)
+        if photo is not None:
+            self.col.ens_photo_update()                 # vulcan.py:170-176: one update at set-up, the loop updates again at count 0
+
+    def run_to_steady_state(self, max_iterations=20000, chunk=64):
+        import time
+        t0 = time.time()
+        left, it, dev_ms = self.ncol, 0, 0.0
+        while left and it < max_iterations:
+            left = self.col.ens_run_steady(chunk)
+            dev_ms += self.col.last_kernel_ms()[0]
+            it += chunk
+        st = self.col.ens_get_state(want_y=True)
+        sd = self.col.ens_get_steady()
+        st.update(end_case=sd["end_case"], longdy=sd["longdy"], longdydt=sd["longdydt"], aflux_change=sd["aflux_change"], iterations=it,
+                  wall_s=time.time() - t0, device_ms=dev_ms, columns_left=left)
+        return st
+
+
 class PipelinedHostSolver(object):
     """`vk_ros2_solve` on HOST buffers for a large batch of columns (the reference-facing call: y, ymix, dt in; sol, ymix, delta
     out).  The batch is split into `n_groups` vk_column handles, each with its own CUDA stream, driven from a thread pool (the

@@ -70,6 +70,14 @@ class Ros2(object):
             return np.array([[compo[s][a] for a in atoms] for s in self.species], dtype=float)
         return np.asarray(compo, dtype=float)
 
+    def _masses(self):
+        """molar mass per species as mean_mass reads it (build_atm.py:511-520: the `mass` column of vulcan_cfg.com_file)"""
+        with open(self.cfg.com_file) as f:
+            cols = f.readline().split()
+        tab = np.genfromtxt(self.cfg.com_file, names=True, dtype=["U20"] + ["int"] * (len(cols) - 2) + ["float"])
+        rows = list(tab["species"])
+        return np.array([tab[rows.index(sp)][cols[-1]] for sp in self.species], dtype=np.float64)
+
     def _load_charge(self, charge):
         if charge is None:
             with open(self.cfg.com_file) as f:
