@@ -1,4 +1,5 @@
-"""Host mirror of the reference's `op.Integration` loop (op.py:808-1105) for ONE column, driving the GPU solver object
+"""TEST INFRASTRUCTURE (moved out of the product package in round 2: it restates host code of the reference that is outside the hot path,
+SURVEY.md section 2 row 10; the product's own loop is the device-resident vulcan_b200/steady.py).  Host mirror of the reference's `op.Integration` loop (op.py:808-1105) for ONE column, driving the GPU solver object
 (`vulcan_b200.ros2.Ros2`) through the same protocol the reference's `vulcan.py:172-182` uses: this is what "run to steady
 state" means for the single-column metrics (steps/s, time-to-steady-state) on a box that has no reference checkout.
 

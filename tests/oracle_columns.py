@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE - a CPU stand-in for `vulcan_b200._abi.Columns` backed by the oracle (oracle/vk_oracle.c), used ONLY by
-the `-m "not gpu"` host-logic tests: it lets the reference-facing host code (vulcan_b200/ros2.py, vulcan_b200/integration.py)
+the `-m "not gpu"` host-logic tests: it lets the reference-facing host code (vulcan_b200/ros2.py, tests/integration_mirror.py)
 run its whole per-step protocol on a box without a GPU, so that the control flow the GPU lock-step tests exercise
 (tests/test_gpu_lockstep.py) is already checked against the reference's trajectory here.  The product never imports this
 module and has no CPU path (tests/test_abi.py)."""

@@ -1,5 +1,5 @@
 """HD 189733b from the reference's initial state to steady state on the GPU through the drop-in solver object and the
-Integration mirror (vulcan_b200/integration.py), compared with the reference's own full run (tests/golden/HD189_full.npz:
+Integration mirror (tests/integration_mirror.py), compared with the reference's own full run (tests/golden/HD189_full.npz:
 1312 steps, 211 rejected, t = 4.13e7 s, 907 s wall on the CPU).
 
 What can be asserted: BASELINE's "1e-6 relative above 1e-20 at the same step count within 1 %" is tighter than the reference's

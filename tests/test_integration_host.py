@@ -1,4 +1,4 @@
-"""Host mirror of the caller (vulcan_b200/integration.py) against the reference's own operators: the condensation growth
+"""Host mirror of the caller (tests/integration_mirror.py) against the reference's own operators: the condensation growth
 rates `conden`, the relaxation operators `h2o_conden_evap_relax` / `nh3_conden_evap_relax` (op.py:1109-1421) and the
 fix_species switch (op.py:862-893).  Inputs and outputs were recorded from the UNMODIFIED reference while it ran
 (oracle/dump_fixtures.py --conden -> tests/golden/<cfg>_conden.npz); the mirror keeps the reference's evaluation order, so
@@ -14,7 +14,7 @@ TAGS = [t for t in ("Jupiter", "JupiterFix", "Earth", "EarthS") if have(t, "cond
 
 
 def _objects(tag):
-    from vulcan_b200.integration import Integration
+    from integration_mirror import Integration
     step = 0
     if not have(tag, "step%04d.npz" % step):       # JupiterFix only has the post-switch step fixture
         import glob, os
@@ -105,7 +105,7 @@ def test_adapt_rtol_follows_the_reference_policy():
     (floor rtol_min); every 1000th step a loss below 2e-4 raises it by 25 % (ceiling rtol_max).  The expected sequence below is the
     reference's block transcribed statement by statement; step_ok keeps the frozen rtol (default argument bound at import, op.py:2489)."""
     from types import SimpleNamespace
-    from vulcan_b200.integration import Integration
+    from integration_mirror import Integration
     cfg = SimpleNamespace(ini_update_photo_frq=100, use_condense=False, rtol=0.25, rtol_min=0.02, rtol_max=2.5)
     integ = Integration(odesolver=None, cfg=cfg, species=["H"])
     integ.loss_criteria = 0.0005

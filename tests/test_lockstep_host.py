@@ -1,4 +1,4 @@
-"""Host logic of the reference-facing layer (vulcan_b200/ros2.py + vulcan_b200/integration.py) on the CPU: the solver object is
+"""Host logic of the reference-facing layer (vulcan_b200/ros2.py + tests/integration_mirror.py) on the CPU: the solver object is
 wired to the oracle-backed stand-in of the C ABI (tests/oracle_columns.py) and must reproduce the reference's state after the
 first N steps of every BASELINE single-column config.  The GPU twin of this test is tests/test_gpu_lockstep.py."""
 import pytest
@@ -39,7 +39,7 @@ def test_production_dt_steps_conserve_elements():
     reference's HD209S state at step 150 (dt = 1.8e4 s).  The explicit-inverse solve lost 1e-3 ... 0.35 of the carbon per step here."""
     from helpers import Case, mock_objects
     from vulcan_b200 import ros2 as ros2_mod
-    from vulcan_b200.integration import Integration
+    from integration_mirror import Integration
     from vulcan_b200.ros2 import Ros2
     case = Case("HD209S", 150)
     cfg, var, atm, para = mock_objects(case, with_photo=False)

@@ -264,9 +264,12 @@ int vk_ens_photo_update(vk_column *c)
     if (!c || !c->ens || !c->ens->steady_set || !c->photo) { set_error("steady state driver / photolysis not set up"); return VK_ERR_INVALID; }
     VK_CUDA(cudaSetDevice(c->net->device));
     SteadyDev &s = c->ens->steady;
+    VK_CUDA(cudaEventRecord(c->ev0, c->stream));
     int rc = photo_update_device(c, c->y, c->ymix, s.dz, s.act, s.aflux_change);
     if (rc) return rc;
+    VK_CUDA(cudaEventRecord(c->ev3, c->stream));
     VK_CUDA(cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->last_ms_total, c->ev0, c->ev3);       // vk_last_kernel_ms: the update (flux_kernel + jrate_kernel) on the device
     return VK_OK;
 }
 
