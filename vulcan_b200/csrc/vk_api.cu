@@ -62,9 +62,21 @@ int vk_step_device_impl(vk_column *c)
     VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
     VK_CUDA(cudaEventRecord(c->ev0, c->stream));
     if ((rc = launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr))) return rc;          // f(y_n)            op.py:2892
-    if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;                   // I/(r h) - J       op.py:2893
+    // I/(r h) - J (op.py:2893) and the block LU factors F_j of the Schur blocks (c->W): ONE kernel - the block's otherwise idle warps
+    // assemble D_{j+1} in shared memory while the column warps factor layer j; D reaches HBM only for the columns the refinement will
+    // read it for.  Fallback (tables do not fit next to the factor buffers, VK_FUSED=0): lhs_ml_kernel -> HBM -> factor_kernel
+    static int fused_env = -1;
+    if (fused_env < 0) { const char *e = getenv("VK_FUSED"); fused_env = e ? atoi(e) : 1; }
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
-    if ((rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status))) return rc; // block LU factors F_j of the Schur blocks (c->W)
+    rc = VK_ERR_UNSUPPORTED;
+    if (fused_env) rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, c->opts.refine > 0 ? 1 : (c->opts.refine < 0 ? 2 : 0));
+    c->last_fused = (rc == VK_OK);
+    if (rc == VK_ERR_UNSUPPORTED) {
+        if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;
+        VK_CUDA(cudaEventRecord(c->ev1, c->stream));
+        rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+    }
+    if (rc) return rc;
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
     if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act))) return rc;           // k1                op.py:2914
     if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->f, c->k1, c->opts.refine, c->dt))) return rc;
@@ -603,6 +615,13 @@ int vk_eval_rhs(vk_column *c, const double *y, double *out_chem, double *out_dif
     return VK_OK;
 }
 
+__global__ void unpad_system(int ni, int nip, const double *D, const double *up, const double *dn, double *Dd, double *upd, double *dnd)
+{
+    const size_t blk = blockIdx.x;
+    for (int q = threadIdx.x; q < ni * ni; q += blockDim.x) Dd[blk * ni * ni + q] = D[blk * nip * nip + (size_t)(q / ni) * nip + q % ni];
+    for (int i = threadIdx.x; i < ni; i += blockDim.x) { upd[blk * ni + i] = up[blk * nip + i]; dnd[blk * ni + i] = dn[blk * nip + i]; }
+}
+
 int vk_eval_lhs(vk_column *c, const double *y, const double *dt, double *D, double *up, double *dn)
 {
     int rc = ready(c);
@@ -611,6 +630,26 @@ int vk_eval_lhs(vk_column *c, const double *y, const double *dt, double *D, doub
     const size_t nv = (size_t)c->ncol * c->nz * c->ni;
     VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, dt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
+    const char *via = getenv("VK_LHS_VIA_FUSED");
+    if (via && atoi(via)) {
+        // parity aid: the blocks as the FUSED assembly + factorisation kernel forms them (producer warps, store_D = always), un-padded
+        // on the way out - must be bit-identical to lhs_ml_kernel's (tests/test_gpu_fused.py)
+        VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
+        rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, 1);
+        if (rc == VK_ERR_UNSUPPORTED) set_error("the fused kernel does not support this network / block size");
+        if (rc) return rc;
+        double *dD = nullptr, *dU = nullptr, *dL = nullptr;
+        VK_CUDA(cudaMalloc((void **)&dD, sizeof(double) * nv * c->ni));
+        VK_CUDA(cudaMalloc((void **)&dU, sizeof(double) * nv));
+        VK_CUDA(cudaMalloc((void **)&dL, sizeof(double) * nv));
+        unpad_system<<<(unsigned)((size_t)c->ncol * c->nz), 256, 0, c->stream>>>(c->ni, c->nip, c->D, c->up, c->dn, dD, dU, dL);
+        VK_CUDA(cudaMemcpyAsync(D, dD, sizeof(double) * nv * c->ni, cudaMemcpyDeviceToHost, c->stream));
+        VK_CUDA(cudaMemcpyAsync(up, dU, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+        VK_CUDA(cudaMemcpyAsync(dn, dL, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
+        VK_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(dD); cudaFree(dU); cudaFree(dL);
+        return VK_OK;
+    }
     // dense (unpadded) output layout: ld = ni; D / up / dn buffers are large enough (nip >= ni)
     if ((rc = launch_lhs(c, c->y, c->dt, c->ni, c->D, c->up, c->dn))) return rc;
     VK_CUDA(cudaMemcpyAsync(D, c->D, sizeof(double) * nv * c->ni, cudaMemcpyDeviceToHost, c->stream));
@@ -729,6 +768,7 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
         if (which == 0) rc = vk::launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
         else if (which == 1) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);
         else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+        else if (which == 5) rc = vk::launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, 0);
         else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
     }
     VK_CUDA(cudaEventRecord(b, c->stream));

@@ -15,6 +15,7 @@
 
 #include "vk_internal.cuh"
 #include "vk_device_math.cuh"
+#include "vk_factor_dev.cuh"
 
 namespace vk {
 
@@ -852,6 +853,348 @@ __global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL,
         // (the barrier at the top of the next iteration orders the stored block and the prefetched rows)
     }
     if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory must outlive the last store
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused assembly: the producer side of factor_kernel<NIP, MINB, true> (vk_factor_dev.cuh).  The NPROD otherwise idle warps of the block
+// run the layer loop of lhs_ml_kernel - same tables, same phases, same expression order, hence the same D bit for bit - but write the
+// finished block into the factor kernel's own D buffer in shared memory, one layer ahead of the column warps:
+//     FREE  (column warps arrive at panel 1 of layer j : D_j, up_{j-1}, dn_j consumed)  ->  producers assemble D_{j+1}, up_j, dn_{j+1}
+//     FULL  (producers arrive)  ->  the Schur update of layer j+1 may read them.
+// up / dn still go to HBM (the solve sweeps read them: 2 x NIP doubles per layer); D goes to HBM only for the columns that are going
+// to be refined (resid_kernel reads it) - store_D: 0 never, 1 always, 2 columns with dt >= dt_min.
+struct LhsProdSmem {    // offsets in doubles behind the factor kernel's own shared memory
+    int kz, ym, y0, yp, dprod, part, misc, trs, upprev, tab, total_bytes;
+};
+static inline LhsProdSmem lhs_prod_layout(const NetDev &n, int ld)
+{
+    LhsProdSmem L;
+    int o = 0;
+    L.kz = o; o += n.nr + 2;
+    L.ym = o; o += n.ni + 2; L.y0 = o; o += n.ni + 2; L.yp = o; o += n.ni + 2;
+    L.dprod = o; o += n.n_uniq + 2;
+    L.part = o; o += n.n_part + 2;
+    L.misc = o; o += 16 + 16;       // [0..3] layer sums, [8..15] coefficient table, [16..31] 128 diagonal-in-pattern flags
+    L.trs = o; o += 6 * ld;         // per species: eA, tA, tV, tE, u, l of the layer being assembled
+    L.upprev = o; o += ld;          // up_{j-1}
+    o += o & 1;
+    L.tab = o;
+    size_t bytes = sizeof(double) * (size_t)o + sizeof(uint2) * (n.n_grp + 1) + sizeof(uint2) * (n.n_multi + 1) +
+                   sizeof(unsigned) * (n.n_uniq + 2) + sizeof(unsigned) * ((size_t)n.n_grp * 32) + sizeof(unsigned short) * (n.n_tt + 8);
+    L.total_bytes = (int)((bytes + 15) & ~(size_t)15);
+    return L;
+}
+struct LhsProdArgs {
+    LhsArgs L;
+    LhsProdSmem SL;
+    int store_D;
+    double dt_min;
+};
+
+template <int NIP, class PA>
+__device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *updn, double *sm, int pw, int lane)
+{
+    using C = FactorCfg<NIP>;
+    constexpr int PNT = C::NPROD * 32, ld = NIP;
+    const LhsArgs &A = PR.L;
+    const LhsProdSmem &SL = PR.SL;
+    const int ni = A.net.ni, nr = A.net.nr;
+    const int tid = pw * 32 + lane;
+    double *kz = sm + SL.kz, *ym = sm + SL.ym, *y0 = sm + SL.y0, *yp = sm + SL.yp, *dprod = sm + SL.dprod, *part = sm + SL.part;
+    double *ysum = sm + SL.misc, *ctab = sm + SL.misc + 8, *trs = sm + SL.trs, *upprev = sm + SL.upprev;
+    uint2 *grp = reinterpret_cast<uint2 *>(sm + SL.tab);
+    uint2 *multi = grp + (A.net.n_grp + 1);
+    unsigned *uq = reinterpret_cast<unsigned *>(multi + (A.net.n_multi + 1));
+    unsigned *seg = uq + (A.net.n_uniq + 2);
+    unsigned short *tt = reinterpret_cast<unsigned short *>(seg + (size_t)A.net.n_grp * 32);
+    unsigned char *dflag = reinterpret_cast<unsigned char *>(sm + SL.misc + 16);
+    auto psync = [&]() { if (C::NPROD == 1) __syncwarp(); else bar_sync<VK_BAR_PROD, (PNT > 0 ? PNT : 32)>(); };
+
+    auto prefetch = [&](int j) {      // k row and the three y rows of layer j -> shared memory (cp.async, 8 bytes each)
+        const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
+        for (int i = tid; i <= nr; i += PNT) cp_async8(kz + i, kg + i);
+        const size_t base = ((size_t)col * nz + j) * ni;
+        for (int i = tid; i < ni; i += PNT) {
+            cp_async8(y0 + i, A.y + base + i);
+            if (j > 0) cp_async8(ym + i, A.y + base - ni + i);
+            if (j < nz - 1) cp_async8(yp + i, A.y + base + ni + i);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    prefetch(0);
+    for (int i = tid; i < A.net.n_grp; i += PNT) grp[i] = A.net.jac_grp[i];
+    for (int i = tid; i < A.net.n_grp * 32; i += PNT) seg[i] = A.net.jac_seg4[i];
+    for (int i = tid; i < A.net.n_multi; i += PNT) multi[i] = A.net.jac_multi[i];
+    for (int i = tid; i < A.net.n_uniq; i += PNT) uq[i] = A.net.jac_uniq[i];
+    {
+        const unsigned *src = reinterpret_cast<const unsigned *>(A.net.jac_tt);
+        unsigned *dst = reinterpret_cast<unsigned *>(tt);
+        for (int i = tid; i < (A.net.n_tt + 1) / 2; i += PNT) dst[i] = src[i];
+    }
+    if (tid == 0) { dprod[A.net.n_uniq] = 0.0; y0[ni + 1] = 1.0; }
+    for (int q = tid; q < ld * ld; q += PNT) blk[q] = 0.0;         // zeroed ONCE: every layer assigns the same pattern entries (see lhs_ml_kernel)
+    for (int i = tid; i < 128; i += PNT) dflag[i] = 0;
+    for (int i = tid; i < ld; i += PNT) upprev[i] = 0.0;
+    if (tid < 8) ctab[tid] = c_jac_coef[tid];
+    psync();
+    for (int i = tid; i < A.net.n_grp * 32; i += PNT) {
+        const unsigned sg = seg[i];
+        const unsigned row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+        if (row != 0xffu && row == colx) dflag[row] = 1;
+    }
+    for (int i = tid; i < A.net.n_multi; i += PNT) {
+        const uint2 me = multi[i];
+        if ((me.x & 0xffff) == (me.x >> 16)) dflag[me.x & 0xffff] = 1;
+    }
+    const unsigned blk_s = (unsigned)__cvta_generic_to_shared(blk);
+    const unsigned blk_bytes = (unsigned)(ld * ld * sizeof(double));
+    const AtmLayer L = atm_at(A.atm, col);
+    const double *dzi = L.dzi;
+    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
+    const double rr = 1. + 1. / sqrt(2.);
+    const double dtc = A.dt[col];
+    const double c0 = 1. / (rr * dtc);
+    const AtmPre &P = A.atm.pre;
+    const bool storeD = A.D && (PR.store_D == 1 || (PR.store_D == 2 && dtc >= PR.dt_min));
+    double *eAs = trs, *tAs = trs + ld, *tVs = trs + 2 * ld, *tEs = trs + 3 * ld, *us = trs + 4 * ld, *ls_ = trs + 5 * ld;
+
+    for (int j = 0; j < nz; j++) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (tid == 0) {
+            y0[ni] = A.atm.M[col * A.atm.csz + j];
+            if (storeD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous block has left shared memory
+        }
+        if (j > 0) bar_sync<VK_BAR_FREE, C::NFEED>();     // the column warps have consumed D_{j-1}, up_{j-2}, dn_{j-1}
+        psync();
+        // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums (last producer warp, numpy association)
+        for (int u = tid; u < A.net.n_uniq; u += PNT) {
+            const unsigned d = uq[u];
+            double x = kz[d & 0x7ffu];
+            x = x * y0[(d >> 11) & 0x7fu];
+            x = x * y0[(d >> 18) & 0x7fu];
+            x = x * y0[(d >> 25) & 0x7fu];
+            dprod[u] = x;
+        }
+        if (pw == C::NPROD - 1) {
+            const int q = lane >> 3;
+            const int jj = j - 1 + q;
+            const bool act = (q < 3) && jj >= 0 && jj < nz;
+            const double *row = (q == 0) ? ym : ((q == 1) ? y0 : yp);
+            double sres;
+            if (A.atm.n_gas_lhs > 0) {
+                sres = 0.0;
+                if (act && (lane & 7) == 0) sres = row_sum(row, ni, A.atm.n_gas_lhs, A.atm.gas_indx_lhs, nullptr);
+            } else {
+                sres = np_pairwise_group8(row, ni, act);
+            }
+            if (act && (lane & 7) == 0) ysum[q] = sres;
+        }
+        psync();
+        const size_t base = ((size_t)col * nz + j) * ni;
+        const size_t vbase = ((size_t)col * nz + j) * ld;
+        // ---- transport part of the diagonal and the couplings (op.py:1998-2040), expression by expression as in lhs_ml_kernel
+        for (int i = tid; i < ld; i += PNT) {
+            double eA = 0.0, tA = 0.0, tV = 0.0, tE = 0.0, u = 0.0, l = 0.0;
+            if (i < ni) {
+                const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
+                const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+                const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+                double eB = 0.0, eC = 0.0;
+                if (j == 0) {
+                    eA = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
+                    eB = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+                    u -= eB;
+                    if (md) {
+                        double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0);
+                        double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp);
+                        if (vmm) {
+                            double tx = 0.0;
+                            vm_lhs_adv(P, pb, 0, st, ta, tb, tx);
+                        } else {
+                            ta = ta + P.TA[pb];
+                            tb = tb + P.TB[pb];
+                            if (st) {
+                                ta = ta - P.SA[pb];
+                                tb = tb - P.SB[pb];
+                            }
+                        }
+                        tA = ta;
+                        u -= tb;
+                    }
+                    if (A.atm.use_botflux) tV = -1. * L.bot_vdep[i] / dzi[0];
+                } else if (j == nz - 1) {
+                    if (vmm && A.atm.n_diff_esc > 0) tE = vm_diff_lim(A.atm, L, i, y0[i]);
+                    eA = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
+                    eC = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+                    l -= eC;
+                    if (md) {
+                        double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0);
+                        double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm);
+                        if (vmm) {
+                            double tx = 0.0;
+                            vm_lhs_adv(P, pb, 2, st, ta, tx, tc);
+                        } else {
+                            ta = ta - P.TA[pb];
+                            tc = tc - P.TC[pb];
+                            if (st) {
+                                ta = ta + P.SA[pb];
+                                tc = tc + P.SC[pb];
+                            }
+                        }
+                        tA = ta;
+                        l -= tc;
+                    }
+                } else {
+                    eA = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
+                    eB = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
+                    eC = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+                    u -= eB;
+                    l -= eC;
+                    if (md) {
+                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
+                        double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
+                        double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
+                        if (vmm) {
+                            vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
+                        } else {
+                            ta = ta + P.TA[pb];
+                            tb = tb + P.TB[pb];
+                            tc = tc - P.TC[pb];
+                            if (st) {
+                                ta = ta - P.SA[pb];
+                                tb = tb - P.SB[pb];
+                                tc = tc + P.SC[pb];
+                            }
+                        }
+                        tA = ta;
+                        u -= tb;
+                        l -= tc;
+                    }
+                }
+                if (A.fix_mask && A.fix_mask[base + i]) { u = 0.0; l = 0.0; }
+            }
+            eAs[i] = eA; tAs[i] = tA; tVs[i] = tV; tEs[i] = tE; us[i] = u; ls_[i] = l;
+            A.up[vbase + i] = u;
+            A.dn[vbase + i] = l;
+        }
+        // ---- phase B: groups of 32 segments, two adjacent groups per warp and turn (see lhs_ml_kernel)
+        for (int gI = 2 * pw; gI < A.net.n_grp; gI += 2 * C::NPROD) {
+            const int gJ = gI + 1;
+            const bool two = gJ < A.net.n_grp;
+            const uint2 ga = grp[gI], gb = grp[two ? gJ : gI];
+            const unsigned short *ta = tt + ga.x + lane, *tb = tt + gb.x + lane;
+            const int na = (int)ga.y, nb = two ? (int)gb.y : 0;
+            double acc_a = 0.0, acc_b = 0.0;
+            int q = 0;
+#pragma unroll 2
+            for (; q < nb; q++) {
+                const unsigned da = ta[32 * q], db = tb[32 * q];
+                acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
+                acc_b += ctab[db >> 13] * dprod[db & 0x1fffu];
+            }
+#pragma unroll 2
+            for (; q < na; q++) {
+                const unsigned da = ta[32 * q];
+                acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
+            }
+            {
+                const unsigned sg = seg[gI * 32 + lane];
+                const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+                if (row != 0xffu) {
+                    if (slot == 0xffffu) blk[row * ld + colx] = -acc_a;
+                    else part[slot] = acc_a;
+                }
+            }
+            if (two) {
+                const unsigned sg = seg[gJ * 32 + lane];
+                const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+                if (row != 0xffu) {
+                    if (slot == 0xffffu) blk[row * ld + colx] = -acc_b;
+                    else part[slot] = acc_b;
+                }
+            }
+        }
+        psync();
+        if (j + 1 < nz) prefetch(j + 1);           // k / y rows of this layer are consumed (products formed, layer sums taken, y0 read by tE)
+        // ---- phase C: split entries (fixed-order sum of their partials)
+        for (int m = tid; m < A.net.n_multi; m += PNT) {
+            const uint2 me = multi[m];
+            const int s0 = (int)(me.y & 0xffff), n = (int)(me.y >> 16);
+            double acc = 0.0;
+            for (int q = 0; q < n; q++) acc += part[s0 + q];
+            blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
+        }
+        psync();
+        // ---- diagonal: c0 + negJ_ss - transport; the couplings the Schur update of this layer reads: up_{j-1}, dn_j
+        for (int i = tid; i < ld; i += PNT) {
+            if (i >= ni) {
+                blk[i * ld + i] = 1.0;
+            } else {
+                double d = c0 + (dflag[i] ? blk[i * ld + i] : 0.0);
+                d -= tEs[i];
+                d -= eAs[i];
+                if (md) d -= tAs[i];
+                if (A.atm.use_botflux && j == 0) d -= tVs[i];
+                if (A.fix_mask && A.fix_mask[base + i]) {
+                    for (int t = 0; t < ni; t++) blk[i * ld + t] = 0.0;
+                    d = c0;
+                }
+                blk[i * ld + i] = d;
+            }
+            updn[i] = upprev[i];
+            updn[ld + i] = ls_[i];
+            upprev[i] = us[i];
+        }
+        if (storeD) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __threadfence_block();
+        psync();
+        if (storeD && tid == 0) {
+            double *Dg = A.D + ((size_t)col * nz + j) * ld * ld;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Dg), "r"(blk_s), "r"(blk_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        bar_arrive<VK_BAR_FULL, C::NFEED>();
+        if (j > 0) {       // the block-wide barrier that ends factor layer j-1 (D_j is complete by then)
+            if (__syncthreads_or(0)) { if (storeD && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); return; }
+        }
+    }
+    __syncthreads_or(0);   // ... and the one of the last layer
+    if (storeD && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int NIP, int MINB>
+static int launch_factor_fused_t(vk_column *c, const LhsProdArgs &pa, double *F, int *status)
+{
+    using C = FactorCfg<NIP>;
+    FactorArgs a{c->nz, c->ni, nullptr, nullptr, nullptr, F, status, c->act};
+    const size_t smem = C::SMEM + 16 + (size_t)pa.SL.total_bytes;
+    if (smem > 227 * 1024) return VK_ERR_UNSUPPORTED;
+    { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, true, LhsProdArgs>, c->net->device, smem); if (rc) return rc; }
+    factor_kernel<NIP, MINB, true, LhsProdArgs><<<c->ncol, C::NT, smem, c->stream>>>(a, pa);
+    VK_CUDA(cudaGetLastError());
+    return VK_OK;
+}
+
+// lhs assembly + block-tridiagonal factorisation in ONE kernel.  Returns VK_ERR_UNSUPPORTED (no error message set) when the tables of
+// this network do not fit next to the factor kernel's buffers: the caller then takes the two-kernel path.
+int launch_factor_fused(vk_column *c, const double *y_dev, const double *dt_dev, double *D_out, double *up_out, double *dn_out, double *F,
+                        int *status, int store_D)
+{
+    LhsProdArgs pa;
+    LhsArgs &a = pa.L;
+    a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
+    a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = c->nip; a.fix_mask = c->opts.fix_mask; a.act = c->act;
+    if (!a.net.lhs_ml_ok) return VK_ERR_UNSUPPORTED;
+    pa.SL = lhs_prod_layout(a.net, c->nip);
+    pa.store_D = store_D; pa.dt_min = c->opts.refine_dt_min;
+    switch (c->nip) {
+        case 48: return launch_factor_fused_t<48, 2>(c, pa, F, status);
+        case 72: return launch_factor_fused_t<72, 2>(c, pa, F, status);
+        case 96: return launch_factor_fused_t<96, 1>(c, pa, F, status);
+        case 120: return launch_factor_fused_t<120, 1>(c, pa, F, status);
+        default: return VK_ERR_UNSUPPORTED;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------

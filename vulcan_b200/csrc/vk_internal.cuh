@@ -118,6 +118,7 @@ struct vk_column {
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev2, ev3;
     float last_ms_total, last_ms_factor;
+    bool last_fused;            // the last step took the fused assembly + factorisation kernel
     // state
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
@@ -148,6 +149,8 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
                const double *k1_for_rhs2, const double *dt_dev);
 int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int dense_out_ni, double *D_out, double *up_out,
                double *dn_out);
+int launch_factor_fused(vk_column *c, const double *y_dev, const double *dt_dev, double *D_out, double *up_out, double *dn_out, double *F,
+                        int *status, int store_D);
 int launch_atm_pre(vk_column *c, int ncol_atm);
 int launch_atm_pre_pred(vk_column *c, const int *pred);
 // kernels (vk_solve.cu)
