@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--reference", action="store_true", help="run the UNMODIFIED reference (op.Ros2) instead of the drop-in: the timing baseline")
     ap.add_argument("--device-loop", action="store_true", help="vulcan_b200.steady.DeviceIntegration instead of op.Integration")
     a = ap.parse_args()
+    if a.out:
+        a.out = os.path.abspath(a.out)           # ref_session.setup changes into the staged copy
     refdir = os.path.abspath(a.refdir or "/tmp/vulcan_ref_%s" % a.config)
     import ref_session
     from vulcan_b200 import ros2 as ros2_mod

@@ -195,38 +195,43 @@ __device__ __forceinline__ void dd_add(dd_t &s, double ohi, double olo)
     s.hi = t;
     s.lo = __dadd_rn(__dadd_rn(s.lo, olo), e);
 }
-__global__ void __launch_bounds__(512) resid_kernel(ResidArgs a)
+__global__ void __launch_bounds__(512) resid_kernel(ResidArgs a, int n_blocks)
 {
     extern __shared__ double xs[];   // x_j padded
     const int nz = a.nz, ni = a.ni, nip = a.nip;
-    const int col = blockIdx.x / nz, j = blockIdx.x % nz;
-    if (a.act && !a.act[col]) return;
     const int tid = threadIdx.x;
-    const size_t vb = ((size_t)col * nz + j) * ni;
-    for (int i = tid; i < nip; i += blockDim.x) xs[i] = (i < ni) ? a.x[vb + i] : 0.0;
-    __syncthreads();
-    const int row = tid >> 2, part = tid & 3;
-    const bool live = row < nip;
-    const double *Dr = a.D + (((size_t)col * nz + j) * nip + (live ? row : 0)) * nip;
-    dd_t acc{0.0, 0.0};
-    for (int c = part * 2; live && c < nip; c += 8) {
-        double2 d = *reinterpret_cast<const double2 *>(Dr + c);
-        dd_fma_acc(acc, d.x, xs[c]);
-        dd_fma_acc(acc, d.y, xs[c + 1]);
-    }
-    {
-        double oh = __shfl_xor_sync(0xffffffffu, acc.hi, 1), ol = __shfl_xor_sync(0xffffffffu, acc.lo, 1);
-        dd_add(acc, oh, ol);
-        oh = __shfl_xor_sync(0xffffffffu, acc.hi, 2); ol = __shfl_xor_sync(0xffffffffu, acc.lo, 2);
-        dd_add(acc, oh, ol);
-    }
-    if (part == 0 && row < ni) {
-        const size_t pb = ((size_t)col * nz + j) * nip;
-        if (j + 1 < nz) dd_fma_acc(acc, a.up[pb + row], a.x[vb + ni + row]);
-        if (j > 0) dd_fma_acc(acc, a.dn[pb + row], a.x[vb - ni + row]);
-        dd_t r{a.rhs[vb + row], 0.0};
-        dd_add(r, -acc.hi, -acc.lo);
-        a.res[vb + row] = __dadd_rn(r.hi, r.lo);
+    // a bounded grid walks the (column, layer) pairs: with refine = auto most launches find every column inactive, and a grid of
+    // ncol * nz empty blocks costs milliseconds of block scheduling (4096 columns: 614 400 blocks)
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int col = blk / nz, j = blk % nz;
+        if (a.act && !a.act[col]) { blk += (nz - 1 - j) / gridDim.x * gridDim.x; continue; }     // skip the rest of this column's layers
+        const size_t vb = ((size_t)col * nz + j) * ni;
+        __syncthreads();
+        for (int i = tid; i < nip; i += blockDim.x) xs[i] = (i < ni) ? a.x[vb + i] : 0.0;
+        __syncthreads();
+        const int row = tid >> 2, part = tid & 3;
+        const bool live = row < nip;
+        const double *Dr = a.D + (((size_t)col * nz + j) * nip + (live ? row : 0)) * nip;
+        dd_t acc{0.0, 0.0};
+        for (int c = part * 2; live && c < nip; c += 8) {
+            double2 d = *reinterpret_cast<const double2 *>(Dr + c);
+            dd_fma_acc(acc, d.x, xs[c]);
+            dd_fma_acc(acc, d.y, xs[c + 1]);
+        }
+        {
+            double oh = __shfl_xor_sync(0xffffffffu, acc.hi, 1), ol = __shfl_xor_sync(0xffffffffu, acc.lo, 1);
+            dd_add(acc, oh, ol);
+            oh = __shfl_xor_sync(0xffffffffu, acc.hi, 2); ol = __shfl_xor_sync(0xffffffffu, acc.lo, 2);
+            dd_add(acc, oh, ol);
+        }
+        if (part == 0 && row < ni) {
+            const size_t pb = ((size_t)col * nz + j) * nip;
+            if (j + 1 < nz) dd_fma_acc(acc, a.up[pb + row], a.x[vb + ni + row]);
+            if (j > 0) dd_fma_acc(acc, a.dn[pb + row], a.x[vb - ni + row]);
+            dd_t r{a.rhs[vb + row], 0.0};
+            dd_add(r, -acc.hi, -acc.lo);
+            a.res[vb + row] = __dadd_rn(r.hi, r.lo);
+        }
     }
 }
 
@@ -373,7 +378,8 @@ int launch_residual(vk_column *c, const double *D, const double *up, const doubl
                     const int *act)
 {
     ResidArgs a{c->nz, c->ni, c->nip, D, up, dn, rhs, x, res, act};
-    resid_kernel<<<c->ncol * c->nz, 512, sizeof(double) * c->nip, c->stream>>>(a);
+    const int n_blocks = c->ncol * c->nz;
+    resid_kernel<<<std::min(n_blocks, 148 * 16), 512, sizeof(double) * c->nip, c->stream>>>(a, n_blocks);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
@@ -389,7 +395,7 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
 {
     int rc = VK_OK;
     const size_t per = (size_t)c->nz * c->ni;
-    dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, 32), (unsigned)c->ncol);
+    dim3 grid((unsigned)std::min<size_t>((per + 255) / 256, c->ncol > 256 ? 4 : 32), (unsigned)c->ncol);
     if (refine > 0) {
         for (int it = 0; it < refine && rc == VK_OK; it++) {
             rc = launch_residual(c, D, up, dn, rhs, x, c->res, c->act);
