@@ -22,9 +22,14 @@ def test_fused_blocks_bit_identical(tag, step):
     y = np.repeat(c.y[None], 2, 0) * np.array([1.0, 1.0 + 1e-3])[:, None, None]
     dt = np.array([c.dt, 2 * c.dt])
     D0, u0, l0 = col.eval_lhs(y, dt)
+    from vulcan_b200 import _abi
     os.environ["VK_LHS_VIA_FUSED"] = "1"
     try:
         D1, u1, l1 = col.eval_lhs(y, dt)
+    except _abi.VulcanB200Error as e:
+        if e.code == _abi.VK_ERR_UNSUPPORTED:
+            pytest.skip("block size %d has no idle warps for the producers: this config takes the two-kernel path" % (24 * ((c.ni + 23) // 24)))
+        raise
     finally:
         del os.environ["VK_LHS_VIA_FUSED"]
     assert np.array_equal(u0, u1) and np.array_equal(l0, l1)

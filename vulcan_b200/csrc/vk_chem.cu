@@ -968,6 +968,7 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
         if (j > 0) bar_sync<VK_BAR_FREE, C::NFEED>();     // the column warps have consumed D_{j-1}, up_{j-2}, dn_{j-1}
         psync();
         // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums (last producer warp, numpy association)
+#pragma unroll 4
         for (int u = tid; u < A.net.n_uniq; u += PNT) {
             const unsigned d = uq[u];
             double x = kz[d & 0x7ffu];
@@ -1078,40 +1079,55 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             A.up[vbase + i] = u;
             A.dn[vbase + i] = l;
         }
-        // ---- phase B: groups of 32 segments, two adjacent groups per warp and turn (see lhs_ml_kernel)
-        for (int gI = 2 * pw; gI < A.net.n_grp; gI += 2 * C::NPROD) {
-            const int gJ = gI + 1;
-            const bool two = gJ < A.net.n_grp;
-            const uint2 ga = grp[gI], gb = grp[two ? gJ : gI];
-            const unsigned short *ta = tt + ga.x + lane, *tb = tt + gb.x + lane;
-            const int na = (int)ga.y, nb = two ? (int)gb.y : 0;
-            double acc_a = 0.0, acc_b = 0.0;
+        // ---- phase B: groups of 32 segments (see lhs_ml_kernel), FOUR adjacent groups per warp and turn: the producers are few warps, so
+        // the per-term chain (descriptor -> coefficient, product -> multiply -> add) is hidden by independent chains, not by other warps
+        for (int gI = 4 * pw; gI < A.net.n_grp; gI += 4 * C::NPROD) {
+            const int ng = min(4, A.net.n_grp - gI);
+            const unsigned short *tp[4];
+            int nn[4];
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint2 gg = grp[gI + (u < ng ? u : 0)];
+                tp[u] = tt + gg.x + lane;
+                nn[u] = (u < ng) ? (int)gg.y : 0;          // nn[0] >= nn[1] >= nn[2] >= nn[3] (groups sorted by decreasing length)
+            }
             int q = 0;
 #pragma unroll 2
-            for (; q < nb; q++) {
-                const unsigned da = ta[32 * q], db = tb[32 * q];
-                acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
-                acc_b += ctab[db >> 13] * dprod[db & 0x1fffu];
+            for (; q < nn[3]; q++) {
+                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q], d2 = tp[2][32 * q], d3 = tp[3][32 * q];
+                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
+                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
+                acc[2] += ctab[d2 >> 13] * dprod[d2 & 0x1fffu];
+                acc[3] += ctab[d3 >> 13] * dprod[d3 & 0x1fffu];
             }
 #pragma unroll 2
-            for (; q < na; q++) {
-                const unsigned da = ta[32 * q];
-                acc_a += ctab[da >> 13] * dprod[da & 0x1fffu];
+            for (; q < nn[2]; q++) {
+                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q], d2 = tp[2][32 * q];
+                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
+                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
+                acc[2] += ctab[d2 >> 13] * dprod[d2 & 0x1fffu];
             }
-            {
-                const unsigned sg = seg[gI * 32 + lane];
-                const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
-                if (row != 0xffu) {
-                    if (slot == 0xffffu) blk[row * ld + colx] = -acc_a;
-                    else part[slot] = acc_a;
-                }
+#pragma unroll 2
+            for (; q < nn[1]; q++) {
+                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q];
+                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
+                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
             }
-            if (two) {
-                const unsigned sg = seg[gJ * 32 + lane];
-                const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
-                if (row != 0xffu) {
-                    if (slot == 0xffffu) blk[row * ld + colx] = -acc_b;
-                    else part[slot] = acc_b;
+#pragma unroll 2
+            for (; q < nn[0]; q++) {
+                const unsigned d0 = tp[0][32 * q];
+                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (u < ng) {
+                    const unsigned sg = seg[(gI + u) * 32 + lane];
+                    const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
+                    if (row != 0xffu) {
+                        if (slot == 0xffffu) blk[row * ld + colx] = -acc[u];
+                        else part[slot] = acc[u];
+                    }
                 }
             }
         }
@@ -1167,6 +1183,7 @@ template <int NIP, int MINB>
 static int launch_factor_fused_t(vk_column *c, const LhsProdArgs &pa, double *F, int *status)
 {
     using C = FactorCfg<NIP>;
+    if (C::NPROD == 0) return VK_ERR_UNSUPPORTED;          // no idle warps in this block layout (NIP = 120): two-kernel path
     FactorArgs a{c->nz, c->ni, nullptr, nullptr, nullptr, F, status, c->act};
     const size_t smem = C::SMEM + 16 + (size_t)pa.SL.total_bytes;
     if (smem > 227 * 1024) return VK_ERR_UNSUPPORTED;
