@@ -26,6 +26,8 @@ int ensure_smem(const void *func, int device, size_t bytes)
     size_t &have = done[std::make_pair(func, device)];
     if (bytes > have) {
         VK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        // co-residency of two blocks needs the full shared-memory carve-out of the SM (the default heuristic sizes it for ONE block)
+        VK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         have = bytes;
     }
     return VK_OK;

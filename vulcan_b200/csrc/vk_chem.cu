@@ -11,6 +11,7 @@
 //
 // This translation unit is compiled with -fmad=false: every expression is evaluated with one IEEE rounding per operation in
 // the reference's order, so chemdf and diffdf are bit-identical to the numpy reference (tests/test_gpu_parity.py).
+#include <cstdio>
 #include <cstdlib>
 
 #include "vk_internal.cuh"
@@ -910,15 +911,34 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
     unsigned char *dflag = reinterpret_cast<unsigned char *>(sm + SL.misc + 16);
     auto psync = [&]() { if (C::NPROD == 1) __syncwarp(); else bar_sync<VK_BAR_PROD, (PNT > 0 ? PNT : 32)>(); };
 
-    auto prefetch = [&](int j) {      // k row and the three y rows of layer j -> shared memory (cp.async, 8 bytes each)
+    // The atmosphere-only stencil pieces of the layer (AtmPre: 9 arrays + Q of the layer below + 10 layer scalars) are prefetched too:
+    // read from global memory at the point of use they are a dozen SERIALISED DRAM round trips per layer (the loads sit behind the
+    // boundary / moldiff / settling branches), which 16 co-resident warps hide in lhs_ml_kernel and two producer warps cannot.  They
+    // land in the dprod region - dead between phase B of one layer and phase A of the next - and are consumed (transport part) BEFORE
+    // phase A overwrites it.
+    double *pre = dprod;                                   // [10][ni] Qm Q QB QC TA TB TC SA SB SC, then LS[10]
+    const AtmPre &PG = A.atm.pre;
+    auto prefetch = [&](int j) {      // k row, the three y rows and the stencil pieces of layer j -> shared memory (cp.async, 8 bytes each)
         const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
         for (int i = tid; i <= nr; i += PNT) cp_async8(kz + i, kg + i);
         const size_t base = ((size_t)col * nz + j) * ni;
+        const size_t pb0 = (size_t)col * A.atm.pre_cs + (size_t)j * ni;
         for (int i = tid; i < ni; i += PNT) {
             cp_async8(y0 + i, A.y + base + i);
             if (j > 0) cp_async8(ym + i, A.y + base - ni + i);
             if (j < nz - 1) cp_async8(yp + i, A.y + base + ni + i);
+            if (j > 0) cp_async8(pre + i, PG.Q + pb0 - ni + i);
+            cp_async8(pre + ni + i, PG.Q + pb0 + i);
+            cp_async8(pre + 2 * ni + i, PG.QB + pb0 + i);
+            cp_async8(pre + 3 * ni + i, PG.QC + pb0 + i);
+            cp_async8(pre + 4 * ni + i, PG.TA + pb0 + i);
+            cp_async8(pre + 5 * ni + i, PG.TB + pb0 + i);
+            cp_async8(pre + 6 * ni + i, PG.TC + pb0 + i);
+            cp_async8(pre + 7 * ni + i, PG.SA + pb0 + i);
+            cp_async8(pre + 8 * ni + i, PG.SB + pb0 + i);
+            cp_async8(pre + 9 * ni + i, PG.SC + pb0 + i);
         }
+        if (tid < 10) cp_async8(pre + 10 * ni + tid, PG.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10 + tid);
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch(0);
@@ -931,7 +951,7 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
         unsigned *dst = reinterpret_cast<unsigned *>(tt);
         for (int i = tid; i < (A.net.n_tt + 1) / 2; i += PNT) dst[i] = src[i];
     }
-    if (tid == 0) { dprod[A.net.n_uniq] = 0.0; y0[ni + 1] = 1.0; }
+    if (tid == 0) y0[ni + 1] = 1.0;
     for (int q = tid; q < ld * ld; q += PNT) blk[q] = 0.0;         // zeroed ONCE: every layer assigns the same pattern entries (see lhs_ml_kernel)
     for (int i = tid; i < 128; i += PNT) dflag[i] = 0;
     for (int i = tid; i < ld; i += PNT) upprev[i] = 0.0;
@@ -955,28 +975,18 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
     const double rr = 1. + 1. / sqrt(2.);
     const double dtc = A.dt[col];
     const double c0 = 1. / (rr * dtc);
-    const AtmPre &P = A.atm.pre;
+    AtmPre P;                                              // the prefetched copies, indexed by species
+    P.Q = pre + ni; P.QB = pre + 2 * ni; P.QC = pre + 3 * ni; P.TA = pre + 4 * ni; P.TB = pre + 5 * ni; P.TC = pre + 6 * ni;
+    P.SA = pre + 7 * ni; P.SB = pre + 8 * ni; P.SC = pre + 9 * ni; P.LS = pre + 10 * ni;
+    const double *Qm = pre;
     const bool storeD = A.D && (PR.store_D == 1 || (PR.store_D == 2 && dtc >= PR.dt_min));
     double *eAs = trs, *tAs = trs + ld, *tVs = trs + 2 * ld, *tEs = trs + 3 * ld, *us = trs + 4 * ld, *ls_ = trs + 5 * ld;
 
     for (int j = 0; j < nz; j++) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (tid == 0) {
-            y0[ni] = A.atm.M[col * A.atm.csz + j];
-            if (storeD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous block has left shared memory
-        }
-        if (j > 0) bar_sync<VK_BAR_FREE, C::NFEED>();     // the column warps have consumed D_{j-1}, up_{j-2}, dn_{j-1}
+        if (tid == 0) y0[ni] = A.atm.M[col * A.atm.csz + j];
         psync();
-        // ---- phase A: distinct products k_r y_a y_b y_c; the three layer sums (last producer warp, numpy association)
-#pragma unroll 4
-        for (int u = tid; u < A.net.n_uniq; u += PNT) {
-            const unsigned d = uq[u];
-            double x = kz[d & 0x7ffu];
-            x = x * y0[(d >> 11) & 0x7fu];
-            x = x * y0[(d >> 18) & 0x7fu];
-            x = x * y0[(d >> 25) & 0x7fu];
-            dprod[u] = x;
-        }
+        // ---- the three layer sums (last producer warp, numpy association)
         if (pw == C::NPROD - 1) {
             const int q = lane >> 3;
             const int jj = j - 1 + q;
@@ -999,8 +1009,8 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             double eA = 0.0, tA = 0.0, tV = 0.0, tE = 0.0, u = 0.0, l = 0.0;
             if (i < ni) {
                 const double ys0 = ysum[1], ysm = ysum[0], ysp = ysum[2];
-                const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
-                const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+                const double *ls = P.LS;
+                const size_t pb = (size_t)i;
                 double eB = 0.0, eC = 0.0;
                 if (j == 0) {
                     eA = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
@@ -1053,9 +1063,9 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
                     u -= eB;
                     l -= eC;
                     if (md) {
-                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
+                        double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + Qm[i] * (ysm + ys0) / 2.) / ys0;
                         double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
-                        double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
+                        double tc = ls[9] * (Qm[i] * (ysm + ys0) / (2. * ysm));
                         if (vmm) {
                             vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
                         } else {
@@ -1079,6 +1089,25 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             A.up[vbase + i] = u;
             A.dn[vbase + i] = l;
         }
+        psync();                                   // the stencil pieces are consumed: the products may overwrite them
+        // ---- phase A: distinct products k_r y_a y_b y_c
+#pragma unroll 4
+        for (int u = tid; u < A.net.n_uniq; u += PNT) {
+            const unsigned d = uq[u];
+            double x = kz[d & 0x7ffu];
+            x = x * y0[(d >> 11) & 0x7fu];
+            x = x * y0[(d >> 18) & 0x7fu];
+            x = x * y0[(d >> 25) & 0x7fu];
+            dprod[u] = x;
+        }
+        if (tid == 0) {
+            dprod[A.net.n_uniq] = 0.0;      // the padding product
+            if (storeD) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous block has left shared memory
+        }
+        // everything above touched only the producers' own buffers; from here on the block buffer is written: wait until the column
+        // warps have consumed D_{j-1}, up_{j-2}, dn_{j-1} (they arrive one panel into layer j-1)
+        if (j > 0) bar_sync<VK_BAR_FREE, C::NFEED>();
+        psync();
         // ---- phase B: groups of 32 segments (see lhs_ml_kernel), FOUR adjacent groups per warp and turn: the producers are few warps, so
         // the per-term chain (descriptor -> coefficient, product -> multiply -> add) is hidden by independent chains, not by other warps
         for (int gI = 4 * pw; gI < A.net.n_grp; gI += 4 * C::NPROD) {
@@ -1188,6 +1217,11 @@ static int launch_factor_fused_t(vk_column *c, const LhsProdArgs &pa, double *F,
     const size_t smem = C::SMEM + 16 + (size_t)pa.SL.total_bytes;
     if (smem > 227 * 1024) return VK_ERR_UNSUPPORTED;
     { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, true, LhsProdArgs>, c->net->device, smem); if (rc) return rc; }
+    if (getenv("VK_DEBUG")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, factor_kernel<NIP, MINB, true, LhsProdArgs>, C::NT, smem);
+        fprintf(stderr, "vulcan_b200: fused factor kernel NIP %d: %zu bytes of shared memory per block, %d block(s) per SM\n", NIP, smem, nb);
+    }
     factor_kernel<NIP, MINB, true, LhsProdArgs><<<c->ncol, C::NT, smem, c->stream>>>(a, pa);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
