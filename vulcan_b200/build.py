@@ -39,6 +39,9 @@ def build(force=False, verbose=False, variant=None, solve_flags=()):
         if variant and src == "vk_solve.cu":
             o = os.path.join(LIBDIR, "vk_solve_%s.o" % variant)
             extra = list(extra) + list(solve_flags)
+        if variant == "prodtrace" and src == "vk_chem.cu":
+            o = os.path.join(LIBDIR, "vk_chem_prodtrace.o")
+            extra = list(extra) + ["-DVK_PROD_TRACE"]
         objs.append(o)
         if force or _newer(o, [s] + headers):
             cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]

@@ -892,6 +892,13 @@ struct LhsProdArgs {
     double dt_min;
 };
 
+#ifdef VK_PROD_TRACE
+__device__ long long g_prod_trace[16];
+#define PTRACE(ev) do { if (col == 0 && j == 7 && tid == 0) g_prod_trace[ev] = clock64(); } while (0)
+#else
+#define PTRACE(ev) do { } while (0)
+#endif
+
 template <int NIP, class PA>
 __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *updn, double *sm, int pw, int lane)
 {
@@ -983,9 +990,11 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
     double *eAs = trs, *tAs = trs + ld, *tVs = trs + 2 * ld, *tEs = trs + 3 * ld, *us = trs + 4 * ld, *ls_ = trs + 5 * ld;
 
     for (int j = 0; j < nz; j++) {
+        PTRACE(0);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (tid == 0) y0[ni] = A.atm.M[col * A.atm.csz + j];
         psync();
+        PTRACE(1);
         // ---- the three layer sums (last producer warp, numpy association)
         if (pw == C::NPROD - 1) {
             const int q = lane >> 3;
@@ -1002,6 +1011,7 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             if (act && (lane & 7) == 0) ysum[q] = sres;
         }
         psync();
+        PTRACE(2);
         const size_t base = ((size_t)col * nz + j) * ni;
         const size_t vbase = ((size_t)col * nz + j) * ld;
         // ---- transport part of the diagonal and the couplings (op.py:1998-2040), expression by expression as in lhs_ml_kernel
@@ -1090,8 +1100,9 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             A.dn[vbase + i] = l;
         }
         psync();                                   // the stencil pieces are consumed: the products may overwrite them
+        PTRACE(3);
         // ---- phase A: distinct products k_r y_a y_b y_c
-#pragma unroll 4
+#pragma unroll 8
         for (int u = tid; u < A.net.n_uniq; u += PNT) {
             const unsigned d = uq[u];
             double x = kz[d & 0x7ffu];
@@ -1106,50 +1117,45 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
         }
         // everything above touched only the producers' own buffers; from here on the block buffer is written: wait until the column
         // warps have consumed D_{j-1}, up_{j-2}, dn_{j-1} (they arrive one panel into layer j-1)
+        PTRACE(4);
         if (j > 0) bar_sync<VK_BAR_FREE, C::NFEED>();
         psync();
-        // ---- phase B: groups of 32 segments (see lhs_ml_kernel), FOUR adjacent groups per warp and turn: the producers are few warps, so
-        // the per-term chain (descriptor -> coefficient, product -> multiply -> add) is hidden by independent chains, not by other warps
-        for (int gI = 4 * pw; gI < A.net.n_grp; gI += 4 * C::NPROD) {
-            const int ng = min(4, A.net.n_grp - gI);
-            const unsigned short *tp[4];
-            int nn[4];
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        PTRACE(5);
+        // ---- phase B: groups of 32 segments (see lhs_ml_kernel), EIGHT adjacent groups per warp and turn: the producers are few warps and
+        // share the SM's load/store unit with the column warps (measured: 165 clk per term step with 4 chains), so the per-term chain
+        // (descriptor -> product -> multiply -> add) is hidden by independent chains of the same lane, not by other warps.  The +-1/2/4/3
+        // coefficient is decoded arithmetically (one shared-memory load less per term); products by +-1, 2, 4 are exact, and x * 3.0 is the
+        // same rounding as the table version
+        auto coef = [](unsigned d) -> double {
+            const unsigned c = d >> 13;                        // codes: 1, -1, 2, -2, 4, -4, 3, -3
+            const double m = (c >> 1) == 0 ? 1.0 : ((c >> 1) == 1 ? 2.0 : ((c >> 1) == 2 ? 4.0 : 3.0));
+            return (c & 1u) ? -m : m;
+        };
+        for (int gI = 8 * pw; gI < A.net.n_grp; gI += 8 * C::NPROD) {
+            const int ng = min(8, A.net.n_grp - gI);
+            const unsigned short *tp[8];
+            int nn[8];
+            double acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 const uint2 gg = grp[gI + (u < ng ? u : 0)];
                 tp[u] = tt + gg.x + lane;
-                nn[u] = (u < ng) ? (int)gg.y : 0;          // nn[0] >= nn[1] >= nn[2] >= nn[3] (groups sorted by decreasing length)
+                nn[u] = (u < ng) ? (int)gg.y : 0;          // nn[0] >= nn[1] >= ... (groups sorted by decreasing length)
+                acc[u] = 0.0;
             }
             int q = 0;
-#pragma unroll 2
-            for (; q < nn[3]; q++) {
-                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q], d2 = tp[2][32 * q], d3 = tp[3][32 * q];
-                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
-                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
-                acc[2] += ctab[d2 >> 13] * dprod[d2 & 0x1fffu];
-                acc[3] += ctab[d3 >> 13] * dprod[d3 & 0x1fffu];
+            // staged loops: all eight chains while the shortest group lasts, then seven, ... (warp-uniform trip counts)
+#define VK_GATHER_STAGE(NCH)                                                          \
+            for (; q < nn[NCH - 1]; q++) {                                            \
+                unsigned dd[NCH];                                                     \
+                _Pragma("unroll") for (int u = 0; u < NCH; u++) dd[u] = tp[u][32 * q]; \
+                _Pragma("unroll") for (int u = 0; u < NCH; u++) acc[u] += coef(dd[u]) * dprod[dd[u] & 0x1fffu]; \
             }
-#pragma unroll 2
-            for (; q < nn[2]; q++) {
-                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q], d2 = tp[2][32 * q];
-                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
-                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
-                acc[2] += ctab[d2 >> 13] * dprod[d2 & 0x1fffu];
-            }
-#pragma unroll 2
-            for (; q < nn[1]; q++) {
-                const unsigned d0 = tp[0][32 * q], d1 = tp[1][32 * q];
-                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
-                acc[1] += ctab[d1 >> 13] * dprod[d1 & 0x1fffu];
-            }
-#pragma unroll 2
-            for (; q < nn[0]; q++) {
-                const unsigned d0 = tp[0][32 * q];
-                acc[0] += ctab[d0 >> 13] * dprod[d0 & 0x1fffu];
-            }
+            VK_GATHER_STAGE(8) VK_GATHER_STAGE(7) VK_GATHER_STAGE(6) VK_GATHER_STAGE(5)
+            VK_GATHER_STAGE(4) VK_GATHER_STAGE(3) VK_GATHER_STAGE(2) VK_GATHER_STAGE(1)
+#undef VK_GATHER_STAGE
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
+            for (int u = 0; u < 8; u++) {
                 if (u < ng) {
                     const unsigned sg = seg[(gI + u) * 32 + lane];
                     const unsigned slot = sg >> 16, row = sg & 0xffu, colx = (sg >> 8) & 0xffu;
@@ -1161,6 +1167,7 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             }
         }
         psync();
+        PTRACE(6);
         if (j + 1 < nz) prefetch(j + 1);           // k / y rows of this layer are consumed (products formed, layer sums taken, y0 read by tE)
         // ---- phase C: split entries (fixed-order sum of their partials)
         for (int m = tid; m < A.net.n_multi; m += PNT) {
@@ -1171,6 +1178,7 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             blk[(me.x & 0xffff) * ld + (me.x >> 16)] = -acc;
         }
         psync();
+        PTRACE(7);
         // ---- diagonal: c0 + negJ_ss - transport; the couplings the Schur update of this layer reads: up_{j-1}, dn_j
         for (int i = tid; i < ld; i += PNT) {
             if (i >= ni) {
@@ -1199,10 +1207,12 @@ __device__ void lhs_produce(const PA &PR, int col, int nz, double *blk, double *
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Dg), "r"(blk_s), "r"(blk_bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        PTRACE(8);
         bar_arrive<VK_BAR_FULL, C::NFEED>();
         if (j > 0) {       // the block-wide barrier that ends factor layer j-1 (D_j is complete by then)
             if (__syncthreads_or(0)) { if (storeD && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); return; }
         }
+        PTRACE(9);
     }
     __syncthreads_or(0);   // ... and the one of the last layer
     if (storeD && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -1292,3 +1302,7 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
 }
 
 }  // namespace vk
+
+#ifdef VK_PROD_TRACE
+extern "C" int vk_debug_prod_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, vk::g_prod_trace, sizeof(long long) * 16); }
+#endif
