@@ -202,9 +202,15 @@ __global__ void __launch_bounds__(512) resid_kernel(ResidArgs a, int n_blocks)
     const int tid = threadIdx.x;
     // a bounded grid walks the (column, layer) pairs: with refine = auto most launches find every column inactive, and a grid of
     // ncol * nz empty blocks costs milliseconds of block scheduling (4096 columns: 614 400 blocks)
+    if (a.act) {           // nothing to do at all?  (one pass over the flags instead of one flag load per (column, layer) pair)
+        const int ncol = n_blocks / nz;
+        int any = 0;
+        for (int c0 = tid; c0 < ncol; c0 += blockDim.x) any |= a.act[c0];
+        if (!__syncthreads_or(any)) return;
+    }
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         const int col = blk / nz, j = blk % nz;
-        if (a.act && !a.act[col]) { blk += (nz - 1 - j) / gridDim.x * gridDim.x; continue; }     // skip the rest of this column's layers
+        if (a.act && !a.act[col]) continue;
         const size_t vb = ((size_t)col * nz + j) * ni;
         __syncthreads();
         for (int i = tid; i < nip; i += blockDim.x) xs[i] = (i < ni) ? a.x[vb + i] : 0.0;
