@@ -73,7 +73,7 @@ int vk_step_device_impl(vk_column *c)
     if (fused_env < 0) { const char *e = getenv("VK_FUSED"); fused_env = e ? atoi(e) : 0; }
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
     rc = VK_ERR_UNSUPPORTED;
-    if (fused_env) rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, c->opts.refine > 0 ? 1 : (c->opts.refine < 0 ? 2 : 0));
+    if (fused_env && !c->use_cr) rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, c->opts.refine > 0 ? 1 : (c->opts.refine < 0 ? 2 : 0));
     c->last_fused = (rc == VK_OK);
     if (rc == VK_ERR_UNSUPPORTED) {
         if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;
@@ -323,6 +323,10 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
     if (e != cudaSuccess) { cuda_fail(e, "vk_column_create allocation"); vk_column_destroy(c); return VK_ERR_CUDA; }
     c->opts.mtol = 0; c->opts.atol = 0;
+    {   // one column: the latency path (block cyclic reduction over the layers, vk_cr.inl) unless VK_CR=0
+        const char *e = getenv("VK_CR");
+        c->use_cr = (ncol == 1) && !(e && atoi(e) == 0);
+    }
     *out = c;
     return VK_OK;
 }
@@ -334,6 +338,7 @@ void vk_column_destroy(vk_column *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     photo_destroy(c);
     ens_destroy(c);
+    cr_plan_free(c->cr);
     if (c->refine_kept) cudaFree(c->refine_kept);
     double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->xn, c->z, c->up, c->dn,
                       c->D, c->W, c->dt, c->delta, c->k};

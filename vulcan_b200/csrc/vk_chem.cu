@@ -1223,7 +1223,7 @@ static int launch_factor_fused_t(vk_column *c, const LhsProdArgs &pa, double *F,
 {
     using C = FactorCfg<NIP>;
     if (C::NPROD == 0) return VK_ERR_UNSUPPORTED;          // no idle warps in this block layout (NIP = 120): two-kernel path
-    FactorArgs a{c->nz, c->ni, nullptr, nullptr, nullptr, F, status, c->act};
+    FactorArgs a{c->nz, c->ni, nullptr, nullptr, nullptr, F, status, c->act, nullptr, nullptr, 0};
     const size_t smem = C::SMEM + 16 + (size_t)pa.SL.total_bytes;
     if (smem > 227 * 1024) return VK_ERR_UNSUPPORTED;
     { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, true, LhsProdArgs>, c->net->device, smem); if (rc) return rc; }

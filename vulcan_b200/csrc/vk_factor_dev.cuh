@@ -86,6 +86,11 @@ struct FactorArgs {
     double *F;           // [ncol][nz][NIP][NIP+2] block LU factors of S_j for the solve sweeps (row stride NIP+2: conflict-free LDS.128)
     int *status;         // [ncol]
     const int *act;      // [ncol] or NULL: stopped columns are skipped
+    // block-list mode (cyclic reduction, vk_cr.inl): nz = 1 and block b of the grid inverts / factors the block number blk_idx[b] of the
+    // pool D; its explicit inverse goes to Wout (same indexing as D), a singular block is reported in status[status_idx]
+    const int *blk_idx;
+    double *Wout;
+    int status_idx;
 };
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor pipe: lane 4g+t supplies A[g][t], B[t][g], C[g][2t..2t+1]
@@ -181,8 +186,8 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     double *hraw = hbuf + 256;           // 2 x 64        [parity of m] = A_mK, K = panel m-1 (from warp m-1)
     void *mbar = hraw + 128;             // mbarrier of the TMA prefetch
 
-    const int col = blockIdx.x;
-    if (a.act && !a.act[col]) return;
+    const int col = a.blk_idx ? a.blk_idx[blockIdx.x] : blockIdx.x;
+    if (a.act && !a.blk_idx && !a.act[col]) return;
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int w = C::SPREAD ? wid - (wid >> 2) : wid;     // column-warp index (meaningless for the other warps)
     const int tid = w * 32 + lane;                         // thread index among the column warps
@@ -386,8 +391,13 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         VK_PANEL(8) VK_PANEL(9) VK_PANEL(10) VK_PANEL(11) VK_PANEL(12) VK_PANEL(13) VK_PANEL(14)
 #undef VK_PANEL
         if (__syncthreads_or(bad)) {
-            if (tid == 0) a.status[col] = VK_ERR_SINGULAR;
+            if (tid == 0) a.status[a.blk_idx ? a.status_idx : col] = VK_ERR_SINGULAR;
             return;
+        }
+        if (a.Wout) {        // the explicit inverse W_j (block-list mode)
+            double *Wg = a.Wout + (cbase + j) * (size_t)(NIP * NIP);
+#pragma unroll
+            for (int i = 0; i < NR; i++) *reinterpret_cast<double2 *>(Wg + (size_t)(8 * i + g) * NIP + c0) = make_double2(A[i][0], A[i][1]);
         }
         // ---- A now holds W_j = S_j^{-1} (it stays in the registers; the block LU factors of S_j went out tile by tile above): Schur
         // update of the NEXT layer, S_{j+1} = D_{j+1} - diag(dn_{j+1}) W_j diag(up_j) (D, up, dn already in shared memory by TMA).  Warps 0

@@ -111,6 +111,7 @@ struct vk_network {
 
 struct PhotoState;
 struct EnsState;
+struct CrPlan;
 
 struct vk_column {
     vk_network *net;
@@ -137,6 +138,8 @@ struct vk_column {
     size_t h_pin_bytes;
     PhotoState *photo;
     EnsState *ens;
+    CrPlan *cr;                 // single-column latency path: plan + buffers of the block cyclic reduction (vk_cr.inl), built on first use
+    bool use_cr;                // this handle solves by cyclic reduction (ncol == 1 unless VK_CR=0)
     const int *act;             // steady-state driver: columns with act == 0 have stopped and are skipped by every kernel of the step (else NULL)
     // persistent scratch of vk_clip_loss (device doubles / ints + one pinned host mirror)
     double *clip_d, *clip_h;
@@ -159,6 +162,9 @@ int launch_solve(vk_column *c, const double *F, const double *up, const double *
                  const int *act = nullptr);
 int launch_residual(vk_column *c, const double *D, const double *up, const double *dn, const double *rhs, const double *x,
                     double *res, const int *act = nullptr);
+int launch_cr_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status);
+int launch_cr_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, const int *act);
+void cr_plan_free(CrPlan *p);
 int launch_refine(vk_column *c, const double *D, const double *up, const double *dn, const double *F, const double *rhs, double *x,
                   int refine, const double *dt_pred);
 // kernels (vk_step.cu)
