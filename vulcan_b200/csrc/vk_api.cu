@@ -73,7 +73,7 @@ int vk_step_device_impl(vk_column *c)
     if (fused_env < 0) { const char *e = getenv("VK_FUSED"); fused_env = e ? atoi(e) : 0; }
     VK_CUDA(cudaEventRecord(c->ev1, c->stream));
     rc = VK_ERR_UNSUPPORTED;
-    if (fused_env && !c->use_cr) rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, c->opts.refine > 0 ? 1 : (c->opts.refine < 0 ? 2 : 0));
+    if (fused_env && !c->cr_now) rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, c->opts.refine > 0 ? 1 : (c->opts.refine < 0 ? 2 : 0));
     c->last_fused = (rc == VK_OK);
     if (rc == VK_ERR_UNSUPPORTED) {
         if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;
@@ -326,6 +326,9 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     {   // one column: the latency path (block cyclic reduction over the layers, vk_cr.inl) unless VK_CR=0
         const char *e = getenv("VK_CR");
         c->use_cr = (ncol == 1) && !(e && atoi(e) == 0);
+        const char *m = getenv("VK_CR_DT_MAX");
+        c->cr_dt_max = m ? atof(m) : 2.5e4;
+        c->cr_now = c->use_cr;
     }
     *out = c;
     return VK_OK;
@@ -540,6 +543,7 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
         memcpy(hm, ymix, sizeof(double) * nv);
     }
     memcpy(hdt, dt, sizeof(double) * c->ncol);
+    c->cr_now = c->use_cr && dt[0] <= c->cr_dt_max;
     VK_CUDA(cudaMemcpyAsync(c->y, direct ? y : hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->ymix, direct ? ymix : hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, hdt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
@@ -696,6 +700,7 @@ int vk_blocktri_solve(vk_column *c, const double *D, const double *up, const dou
         if (stale != cudaSuccess && getenv("VK_DEBUG")) fprintf(stderr, "vulcan_b200: stale CUDA error at vk_blocktri_solve entry: %s\n", cudaGetErrorString(stale));
     }
     const size_t nblk = (size_t)c->ncol * c->nz, nv = nblk * c->ni;
+    c->cr_now = c->use_cr;
     double *Dd = nullptr, *upd = nullptr, *dnd = nullptr;
     VK_CUDA(cudaMalloc((void **)&Dd, sizeof(double) * nv * c->ni));
     cudaError_t e = cudaMalloc((void **)&upd, sizeof(double) * nv);
@@ -768,6 +773,7 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
 {
     if (!c || !ms || reps < 1) return VK_ERR_INVALID;
     VK_CUDA(cudaSetDevice(c->net->device));
+    c->cr_now = c->use_cr;
     cudaEvent_t a, b;
     VK_CUDA(cudaEventCreate(&a));
     VK_CUDA(cudaEventCreate(&b));

@@ -246,6 +246,12 @@ int vk_ens_run(vk_column *c, int n_steps)
     VK_CUDA(cudaEventRecord(run0, c->stream));
     int rc = VK_OK;
     for (int it = 0; it < n_steps && rc == VK_OK; it++) {
+        if (c->use_cr) {      // latency path: cyclic reduction while dt is below cr_dt_max (one small read-back per step of ONE column)
+            double hdt = 0.0;
+            VK_CUDA(cudaMemcpyAsync(&hdt, c->dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VK_CUDA(cudaStreamSynchronize(c->stream));
+            c->cr_now = hdt <= c->cr_dt_max;
+        }
         rc = vk_step_device_impl(c);
         if (rc) break;
         rc = launch_clip(c, c->sol, c->ymix_out, c->ymix_out, e->na, e->compo, nullptr, e->pos_cut, e->nega_cut, e->atom_sum,

@@ -139,7 +139,10 @@ struct vk_column {
     PhotoState *photo;
     EnsState *ens;
     CrPlan *cr;                 // single-column latency path: plan + buffers of the block cyclic reduction (vk_cr.inl), built on first use
-    bool use_cr;                // this handle solves by cyclic reduction (ncol == 1 unless VK_CR=0)
+    bool use_cr;                // this handle may solve by cyclic reduction (ncol == 1 unless VK_CR=0) ...
+    bool cr_now;                // ... and does so for the current step: only while dt <= cr_dt_max.  Beyond it (cond(A) > 1e16) the extra
+    double cr_dt_max;           // dense products of the reduction cost accuracy (HD209S at dt = 2.4e5 s: element budget 3.0e-4 against 1.2e-4
+                                // for block Thomas, and the refinement pass no longer contracts), so those steps take block Thomas
     const int *act;             // steady-state driver: columns with act == 0 have stopped and are skipped by every kernel of the step (else NULL)
     // persistent scratch of vk_clip_loss (device doubles / ints + one pinned host mirror)
     double *clip_d, *clip_h;

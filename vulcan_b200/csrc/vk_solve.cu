@@ -342,7 +342,7 @@ static int launch_factor_t(vk_column *c, const double *D, const double *up, cons
 // F out: block LU factors of the Schur blocks, [ncol][nz][nip][nip+2]
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
 {
-    if (c->use_cr) return launch_cr_factor(c, D, up, dn, F, status);
+    if (c->cr_now) return launch_cr_factor(c, D, up, dn, F, status);
     switch (c->nip) {
         case 48: return launch_factor_t<48, 2>(c, D, up, dn, F, status);
         case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status);
@@ -365,7 +365,7 @@ static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 // x = A^{-1} rhs with the stored block LU factors F ([ncol][nz][nip][nip+2]); z is scratch
 int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z, const int *act)
 {
-    if (c->use_cr) return launch_cr_solve(c, F, up, dn, rhs, x, act);
+    if (c->cr_now) return launch_cr_solve(c, F, up, dn, rhs, x, act);
     LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, act};
     // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
     // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per

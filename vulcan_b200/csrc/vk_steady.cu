@@ -287,6 +287,12 @@ int vk_ens_run_steady(vk_column *c, int max_iterations, int *n_active_left)
     int rc = VK_OK;
     c->act = s.act;
     for (int it = 0; it < max_iterations && rc == VK_OK; it++) {
+        if (c->use_cr) {      // latency path: cyclic reduction while dt is below cr_dt_max (one small read-back per step of ONE column)
+            double hdt = 0.0;
+            VK_CUDA(cudaMemcpyAsync(&hdt, c->dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            VK_CUDA(cudaStreamSynchronize(c->stream));
+            c->cr_now = hdt <= c->cr_dt_max;
+        }
         PreArgs pa{c->nz, c->ni, s, c->y, c->ymix, e->n_0, e->t, e->n_accept, c->atm.Kzz, c->atm.cs1};
         steady_pre_kernel<<<c->ncol, 256, 0, c->stream>>>(pa);
         if (s.use_photo) rc = photo_update_device(c, c->y, c->ymix, s.dz, s.do_photo, s.aflux_change);
