@@ -327,7 +327,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
         const char *e = getenv("VK_CR");
         c->use_cr = (ncol == 1) && !(e && atoi(e) == 0);
         const char *m = getenv("VK_CR_DT_MAX");
-        c->cr_dt_max = m ? atof(m) : 2.5e4;
+        c->cr_dt_max = m ? atof(m) : 1.0e5;
         c->cr_now = c->use_cr;
     }
     *out = c;

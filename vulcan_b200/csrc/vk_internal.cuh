@@ -142,7 +142,8 @@ struct vk_column {
     bool use_cr;                // this handle may solve by cyclic reduction (ncol == 1 unless VK_CR=0) ...
     bool cr_now;                // ... and does so for the current step: only while dt <= cr_dt_max.  Beyond it (cond(A) > 1e16) the extra
     double cr_dt_max;           // dense products of the reduction cost accuracy (HD209S at dt = 2.4e5 s: element budget 3.0e-4 against 1.2e-4
-                                // for block Thomas, and the refinement pass no longer contracts), so those steps take block Thomas
+                                // for block Thomas, the refinement pass no longer contracts, a whole run loses 1.5e-2 of its carbon), so
+                                // those steps take block Thomas.  Default 1e5 s (VK_CR_DT_MAX): HD189 / HD209S runs identical to Thomas-only
     const int *act;             // steady-state driver: columns with act == 0 have stopped and are skipped by every kernel of the step (else NULL)
     // persistent scratch of vk_clip_loss (device doubles / ints + one pinned host mirror)
     double *clip_d, *clip_h;
