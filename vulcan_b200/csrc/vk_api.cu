@@ -329,6 +329,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
         const char *m = getenv("VK_CR_DT_MAX");
         c->cr_dt_max = m ? atof(m) : 1.0e5;
         c->cr_now = c->use_cr;
+        c->dt_host_max = -1.0;
     }
     *out = c;
     return VK_OK;
@@ -544,6 +545,8 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
     }
     memcpy(hdt, dt, sizeof(double) * c->ncol);
     c->cr_now = c->use_cr && dt[0] <= c->cr_dt_max;
+    c->dt_host_max = dt[0];
+    for (int q = 1; q < c->ncol; q++) c->dt_host_max = std::max(c->dt_host_max, dt[q]);
     VK_CUDA(cudaMemcpyAsync(c->y, direct ? y : hy, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->ymix, direct ? ymix : hm, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, hdt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));

@@ -209,10 +209,11 @@ __global__ void __launch_bounds__(256) cr_level0_kernel(int nip, const CrKept *k
 // ---- dense levels: one block per job,  C = beta C + sign (A1 B1 + A2 B2)  on the FP64 tensor pipe.  Warp w owns the 8 columns [8w, 8w+8) of
 // C in the DMMA accumulator layout (lane 4g+t: rows 8i+g, columns 8w+2t, 8w+2t+1); A and B are staged in shared memory with padded row
 // stride (conflict-free fragment loads): a_frag = A[8i+g][4s+t], b_frag = B[4s+t][8w+g] for the k4 step s.
+template <int NIP> struct CrGemmLd { static constexpr int LD = (NIP <= 96) ? NIP + 2 : NIP; };   // NIP = 120: two padded operands exceed 227 KB
 template <int NIP>
 __global__ void __launch_bounds__((NIP / 8) * 32) cr_gemm_kernel(const CrJob *jobs, double *pool)
 {
-    constexpr int NW = NIP / 8, NR = NIP / 8, LD = NIP + 2;
+    constexpr int NW = NIP / 8, NR = NIP / 8, LD = CrGemmLd<NIP>::LD;
     extern __shared__ __align__(16) double sm[];
     double *As = sm, *Bs = sm + (size_t)NIP * LD;
     const CrJob jb = jobs[blockIdx.x];
@@ -359,7 +360,7 @@ static int cr_factor_t(vk_column *c, CrPlan *P, const double *D, const double *u
     using C = FactorCfg<NIP>;
     const size_t bs = (size_t)NIP * NIP;
     { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, false, NoProducer>, c->net->device, C::SMEM); if (rc) return rc; }
-    const size_t gsm = sizeof(double) * 2 * (size_t)NIP * (NIP + 2);
+    const size_t gsm = sizeof(double) * 2 * (size_t)NIP * CrGemmLd<NIP>::LD;
     { int rc = ensure_smem((const void *)cr_gemm_kernel<NIP>, c->net->device, gsm); if (rc) return rc; }
     // current diagonal blocks <- D (the original blocks stay in c->D for the refinement residual)
     VK_CUDA(cudaMemcpyAsync(P->pool, D, sizeof(double) * bs * P->nz, cudaMemcpyDeviceToDevice, c->stream));

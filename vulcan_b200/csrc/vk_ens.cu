@@ -251,6 +251,9 @@ int vk_ens_run(vk_column *c, int n_steps)
             VK_CUDA(cudaMemcpyAsync(&hdt, c->dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             VK_CUDA(cudaStreamSynchronize(c->stream));
             c->cr_now = hdt <= c->cr_dt_max;
+            c->dt_host_max = hdt;
+        } else {
+            c->dt_host_max = -1.0;
         }
         rc = vk_step_device_impl(c);
         if (rc) break;

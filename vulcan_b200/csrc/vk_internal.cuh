@@ -139,6 +139,8 @@ struct vk_column {
     PhotoState *photo;
     EnsState *ens;
     CrPlan *cr;                 // single-column latency path: plan + buffers of the block cyclic reduction (vk_cr.inl), built on first use
+    double dt_host_max;         // largest step size of the batch when the host knows it for the current step (vk_ros2_solve, the one-column
+                                // device loops), else < 0: refine = auto then skips its launches outright below refine_dt_min
     bool use_cr;                // this handle may solve by cyclic reduction (ncol == 1 unless VK_CR=0) ...
     bool cr_now;                // ... and does so for the current step: only while dt <= cr_dt_max.  Beyond it (cond(A) > 1e16) the extra
     double cr_dt_max;           // dense products of the reduction cost accuracy (HD209S at dt = 2.4e5 s: element budget 3.0e-4 against 1.2e-4

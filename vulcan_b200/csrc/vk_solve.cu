@@ -416,6 +416,7 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
         return rc;
     }
     if (refine == 0) return VK_OK;
+    if (dt_pred && c->dt_host_max >= 0.0 && c->dt_host_max < c->opts.refine_dt_min) return VK_OK;    // no column is refined: launch nothing
     if (!c->opts.compo || c->opts.na < 1) { set_error("refine = auto needs the element composition (vk_step_opts.compo)"); return VK_ERR_INVALID; }
     int *act = c->refine_act;
     refine_init_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(c->ncol, dt_pred, c->opts.refine_dt_min, c->act, act);

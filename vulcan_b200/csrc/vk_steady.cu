@@ -292,6 +292,9 @@ int vk_ens_run_steady(vk_column *c, int max_iterations, int *n_active_left)
             VK_CUDA(cudaMemcpyAsync(&hdt, c->dt, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             VK_CUDA(cudaStreamSynchronize(c->stream));
             c->cr_now = hdt <= c->cr_dt_max;
+            c->dt_host_max = hdt;
+        } else {
+            c->dt_host_max = -1.0;
         }
         PreArgs pa{c->nz, c->ni, s, c->y, c->ymix, e->n_0, e->t, e->n_accept, c->atm.Kzz, c->atm.cs1};
         steady_pre_kernel<<<c->ncol, 256, 0, c->stream>>>(pa);
