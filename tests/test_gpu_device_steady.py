@@ -48,7 +48,15 @@ def test_ensemble_runs_every_column_to_its_own_convergence():
         ncol, out["n_accept"].tolist(), out["n_reject"].tolist(), out["end_case"].tolist(), ["%.2e" % t for t in out["t"]], out["wall_s"]))
     assert (out["end_case"] == 1).all()
     assert len(set(out["n_accept"].tolist())) > 1                    # columns stop after different numbers of steps
-    # column 2 (Kzz x 1, solar composition) alone
+    # columns 2 and 3 as a batch of their own: bit-identical to what they did inside the batch of six (a batch of ONE would take the
+    # cyclic-reduction latency path, a different rounding of the same solve: compared to tolerance below)
+    two = steady_ensemble_from_fixture(c, y[2:4], atom_ini[2:4], kz[2:4]).run_to_steady_state(max_iterations=4000)
+    assert np.array_equal(two["n_accept"], out["n_accept"][2:4]) and np.array_equal(two["t"], out["t"][2:4])
+    assert np.array_equal(two["y"], out["y"][2:4])
     alone = steady_ensemble_from_fixture(c, y[2:3], atom_ini[2:3], kz[2:3]).run_to_steady_state(max_iterations=4000)
-    assert alone["n_accept"][0] == out["n_accept"][2] and alone["t"][0] == out["t"][2]
-    assert np.array_equal(alone["y"][0], out["y"][2])
+    print("column 2 alone (cyclic reduction below dt = 1e5 s): %d steps t %.6e against %d steps t %.6e in the batch" % (
+        alone["n_accept"][0], alone["t"][0], out["n_accept"][2], out["t"][2]))
+    assert abs(int(alone["n_accept"][0]) - int(out["n_accept"][2])) <= 0.02 * out["n_accept"][2]
+    ya, yb = alone["y"][0], out["y"][2]
+    m = yb > 1e-8 * yb.sum(axis=1, keepdims=True)
+    assert np.max(np.abs(ya - yb)[m] / yb[m]) < 5e-3

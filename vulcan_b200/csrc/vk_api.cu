@@ -270,6 +270,7 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->rhs_ptr, (size_t)ni + 1, &nd.rhs_ptr);
     if (rcode == VK_OK) rcode = dev_copy(n->allocs, d->jac_ptr, (size_t)d->n_ent + 1, &nd.jac_ptr);
     if (rcode != VK_OK) { vk_network_destroy(n); return rcode; }
+    VK_CUDA(cudaDeviceSynchronize());      // pageable cudaMemcpy may return before its DMA has landed; the handles' streams are non-blocking
     *out = n;
     return VK_OK;
 }
@@ -321,6 +322,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) { c->refine_tried = c->refine_kept + ncol; c->refine_act = c->refine_kept + 2 * ncol; }
     c->h_pin_bytes = sizeof(double) * (4 * nv + 4 * (size_t)ncol) + 64;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();      // the memset above is on the legacy stream, the handle's stream is non-blocking
     if (e != cudaSuccess) { cuda_fail(e, "vk_column_create allocation"); vk_column_destroy(c); return VK_ERR_CUDA; }
     c->opts.mtol = 0; c->opts.atol = 0;
     {   // one column: the latency path (block cyclic reduction over the layers, vk_cr.inl) unless VK_CR=0
@@ -423,6 +425,7 @@ int vk_set_atm(vk_column *c, const vk_atm_view *v)
             a.pre.LS = reinterpret_cast<double *>(ptr);
         }
         a.pre_cs = v->shared ? 0 : (size_t)nz * ni;
+        VK_CUDA(cudaDeviceSynchronize());  // the copies above ran on the legacy stream (pageable sources): land them before the handle's stream reads
         if ((rc = launch_atm_pre(c, (int)rep))) return rc;
         VK_CUDA(cudaStreamSynchronize(c->stream));
     }
@@ -510,6 +513,7 @@ int vk_set_step_opts(vk_column *c, const vk_step_opts *o)
         rc = dev_copy(c->opt_allocs, o->compo, (size_t)c->ni * o->na, &d.compo);
     }
     if (rc == VK_OK && o->refine < 0 && !d.compo) { set_error("refine = auto (-1) needs compo / na"); return VK_ERR_INVALID; }
+    if (rc == VK_OK) VK_CUDA(cudaDeviceSynchronize());
     return rc;
 }
 

@@ -196,6 +196,7 @@ int vk_ens_setup(vk_column *c, const vk_ens_opts *o)
     for (int **p : ints)
         if (rc == VK_OK) rc = ecopy(e, ni_, ncol, p);
     if (rc != VK_OK) ens_destroy(c);
+    else VK_CUDA(cudaDeviceSynchronize());      // memsets of the legacy stream before anything runs on the handle's non-blocking stream
     return rc;
 }
 

@@ -248,6 +248,7 @@ int vk_photo_setup(vk_column *c, const vk_photo_view *v)
     const unsigned long long *nulu = nullptr;
     if (rc == VK_OK) rc = pcopy(p, nulu, ncol, &p->change_bits);
     if (rc != VK_OK) photo_destroy(c);
+    else VK_CUDA(cudaDeviceSynchronize());      // memsets of the legacy stream before anything runs on the handle's non-blocking stream
     return rc;
 }
 

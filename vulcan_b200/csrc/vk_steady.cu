@@ -248,6 +248,9 @@ int vk_ens_setup_steady(vk_column *c, const vk_steady_opts *o)
     for (int **p : ints)
         if (rc == VK_OK) rc = scopy(e, ni_, ncol, p);
     if (rc != VK_OK) return rc;
+    // the cudaMemset calls above run on the legacy default stream, the handle's stream is non-blocking: without this barrier a memset
+    // may land AFTER the fill kernels below (seen: act reset to 0 -> a batch that never starts)
+    VK_CUDA(cudaDeviceSynchronize());
     const int nb = (int)((ncol + 127) / 128);
     fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, s.longdy, 1.0, s.act, 1);             // store.py:36-38: longdy = longdydt = 1
     fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, s.longdydt, 1.0, s.fresh, 1);
