@@ -271,7 +271,7 @@ def photolysis_via_dropin(tag, step, abi=None):
         ros2_mod._abi = real_abi
 
 
-def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edit=None, device_loop=False):
+def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edit=None, device_loop=False, dt_schedule=None):
     """one BASELINE.json single-column config from the reference's initial state (fixture step 0) through the drop-in solver
     object and the Integration mirror until Integration.stop() says so (op.py:1067-1087).  `abi`: replaces the ctypes binding
     the solver object talks to (only the CPU host-logic tests pass the oracle-backed stand-in of tests/oracle_columns.py)."""
@@ -299,6 +299,20 @@ def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edi
         solver = Ros2(cfg=cfg, species=list(case.st["species"]), compo=case.st["compo"], network=case.net, refine=refine,
                       charge=case.st["charge"] if "charge" in case.st else None)
         solver.naming_solver(para)
+        if dt_schedule is not None:
+            # REPLAY of the reference's own time grid: accepted step number c is taken with the step size the reference used for it
+            # (traj column dt_used of <cfg>_full.npz), no accept / reject decision and no step-size control of our own - what remains
+            # between the two final states is the arithmetic of the step alone, not the chaos of the controller
+            sched = np.asarray(dt_schedule, dtype=float)
+
+            def replay_step(var_, atm_, para_):
+                var_.dt = float(sched[para_.count])
+                var_, para_ = solver.solver(var_, atm_, para_)
+                return solver.clip(var_, para_, atm_)
+            solver.one_step = replay_step
+            solver.step_size = lambda var_, para_: var_
+            cfg.count_max = len(sched) - 1
+            cfg.count_min = len(sched) + 10          # the run ends when the schedule does (Integration.stop: count > count_max)
         # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
         if cfg.use_photo:
             solver.compute_tau(var, atm)
