@@ -311,8 +311,9 @@ def run_config(tag, refine=-1, max_wall_s=600, count_max=None, abi=None, cfg_edi
                 return solver.clip(var_, para_, atm_)
             solver.one_step = replay_step
             solver.step_size = lambda var_, para_: var_
-            cfg.count_max = len(sched) - 1
-            cfg.count_min = len(sched) + 10          # the run ends when the schedule does (Integration.stop: count > count_max)
+            cfg.count_max = len(sched) - 1           # the run ends when the schedule does (Integration.stop: count > count_max) ...
+            cfg.flux_cri = -1.0                      # ... and not earlier: conv() still evaluates longdy (the photolysis cadence switch reads
+                                                     # it, op.py:818-822) but can never be satisfied (aflux_change < flux_cri, op.py:1058)
         # vulcan.py:170-176: one photolysis update at set-up, then the loop updates again at count 0
         if cfg.use_photo:
             solver.compute_tau(var, atm)

@@ -298,7 +298,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     memset(static_cast<void *>(c), 0, sizeof(vk_column));
     new (&c->atm_allocs) std::vector<void *>();
     new (&c->opt_allocs) std::vector<void *>();
-    c->net = net; c->nz = nz; c->ncol = ncol; c->ni = net->d.ni; c->nr = net->d.nr; c->nip = net->d.nip;
+    c->net = net; c->device = net->device; c->nz = nz; c->ncol = ncol; c->ni = net->d.ni; c->nr = net->d.nr; c->nip = net->d.nip;
     const size_t nv = (size_t)ncol * nz * c->ni, nb = (size_t)ncol * nz * c->nip * c->nip, np = (size_t)ncol * nz * c->nip;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
@@ -340,7 +340,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
 void vk_column_destroy(vk_column *c)
 {
     if (!c) return;
-    cudaSetDevice(c->net->device);
+    if (cudaSetDevice(c->device) != cudaSuccess) cudaGetLastError();
     if (c->stream) cudaStreamSynchronize(c->stream);
     photo_destroy(c);
     ens_destroy(c);

@@ -17,10 +17,12 @@ namespace vk {
 
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what);
+#define VK_STR2(x) #x
+#define VK_STR(x) VK_STR2(x)
 #define VK_CUDA(call)                                              \
     do {                                                           \
         cudaError_t _e = (call);                                   \
-        if (_e != cudaSuccess) return vk::cuda_fail(_e, #call);    \
+        if (_e != cudaSuccess) return vk::cuda_fail(_e, #call " at " __FILE__ ":" VK_STR(__LINE__));    \
     } while (0)
 
 // opt-in to more than 48 KB of dynamic shared memory for `func`: the attribute belongs to the device's primary context, so it is
@@ -115,6 +117,7 @@ struct CrPlan;
 
 struct vk_column {
     vk_network *net;
+    int device;                 // copy of net->device: the network handle may be destroyed first (garbage-collection order of the bindings)
     int nz, ncol, ni, nr, nip;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev2, ev3;
