@@ -133,6 +133,8 @@ typedef struct {
     /* ABI 3 */
     int na; const double *compo;     /* [ni][na] atoms per species (build_atm.py:18-25, thermo/all_compose.txt) or NULL */
     double refine_dt_min;            /* refine = -1: step size (s) from which a column is refined */
+    int rhs_order;                   /* summation of the production / loss terms of chemdf (chem_funs.py:931): 0 = segmented (32 partial chains
+                                      * per layer, default), 1 = the reference's left-to-right order, bit-identical to the generated chemdf */
 } vk_step_opts;
 int vk_set_step_opts(vk_column *col, const vk_step_opts *opts);
 

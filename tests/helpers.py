@@ -114,7 +114,7 @@ def oracle_step(case, oracle, atm, refine=0):
     return res
 
 
-def gpu_columns(case, ncol=1, refine=0):
+def gpu_columns(case, ncol=1, refine=0, rhs_order=0):
     """a vk_column handle configured like the reference's solver object for this fixture (through the C ABI)."""
     from vulcan_b200 import _abi
     kw = case.atm_kwargs()
@@ -134,7 +134,7 @@ def gpu_columns(case, ncol=1, refine=0):
     rep = lambda a: None if a is None else np.repeat(a[None], ncol, axis=0)
     col.set_step_opts(case.cfg["mtol"], case.cfg["atol"], refine=refine, zero_delta_row0=o["zero_delta_row0"],
                       fix_bot_idx=o["fix_bot_idx"], fix_bot_val=fbv, delta_zero_sp=o["delta_zero_sp"],
-                      fix_mask=rep(o["fix_mask"]), fix_y=rep(o["fix_y"]), compo=case.st["compo"])
+                      fix_mask=rep(o["fix_mask"]), fix_y=rep(o["fix_y"]), compo=case.st["compo"], rhs_order=rhs_order)
     return col
 
 

@@ -40,7 +40,7 @@ class OracleColumns(object):
         self.k = np.array(k, dtype=np.float64).reshape(self.nz, self.nr + 1)
 
     def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None, delta_zero_sp=None,
-                      fix_mask=None, fix_y=None, compo=None, refine_dt_min=1.0e3):
+                      fix_mask=None, fix_y=None, compo=None, refine_dt_min=1.0e3, rhs_order=0):
         self.opts = dict(mtol=mtol, atol=atol, refine=refine, zero_delta_row0=zero_delta_row0, fix_bot_idx=list(fix_bot_idx),
                          fix_bot_val=None if fix_bot_val is None else np.asarray(fix_bot_val, dtype=float).ravel(),
                          delta_zero_sp=delta_zero_sp, fix_mask=fix_mask, fix_y=fix_y, compo=compo, refine_dt_min=refine_dt_min)

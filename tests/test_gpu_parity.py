@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 R = 1. + 1. / 2. ** 0.5
 
 
-def _columns(case, ncol=1, refine=0):
-    return gpu_columns(case, ncol, refine)
+def _columns(case, ncol=1, refine=0, rhs_order=0):
+    return gpu_columns(case, ncol, refine, rhs_order)
 
 
 @pytest.fixture(scope="module", params=CASES, ids=case_id)
@@ -37,12 +37,46 @@ def case(request):
 
 
 def test_rhs_bit_exact(case):
-    """chemdf + diffdf: bit-identical to the oracle AND to the reference fixture (make_chem_funs.py:113-430, op.py:1496-1597)."""
-    chem, diff = case.col.eval_rhs(case.y)
+    """chemdf + diffdf: bit-identical to the oracle AND to the reference fixture (make_chem_funs.py:113-430, op.py:1496-1597) with
+    rhs_order = 1, the reference's left-to-right summation order (the default is the segmented order, next test)."""
+    chem, diff = _columns(case, rhs_order=1).eval_rhs(case.y)
     assert np.array_equal(chem[0], case.oracle.chemdf(case.y, case.st["M"], case.k))
     assert np.array_equal(chem[0], case.fx["chemdf"])
     assert np.array_equal(diff[0], case.oracle.diffdf(case.atm, case.y))
     assert np.array_equal(diff[0], case.fx["diffdf"])
+
+
+def test_rhs_segmented_order(case):
+    """The default summation order of chemdf on the device (32 partial chains per layer, vk_chem.cu) against the reference order and against
+    an extended-precision sum of the same terms: per species the difference to the 80-bit sum must be at rounding level of the LARGEST term
+    sum (sum |terms|) - for both orders - and diffdf is untouched (bit-identical)."""
+    chem_f, diff_f = case.col.eval_rhs(case.y)
+    chem_r = case.fx["chemdf"]
+    assert np.array_equal(diff_f[0], case.fx["diffdf"])
+    t = case.net.tables()
+    ni, nr = case.ni, case.nr
+    yx = np.concatenate([case.y, case.st["M"][:, None], np.ones((case.nz, 1))], axis=1)          # slots ni = M, ni + 1 = 1.0
+    rate = case.k.copy()                                                                           # [nz, nr+1]
+    fac, pw = np.asarray(t["rate_fac"]).reshape(nr + 1, -1), np.asarray(t["rate_pow"]).reshape(nr + 1, -1)
+    for q in range(fac.shape[1]):
+        rate = rate * yx[:, fac[:, q]] ** pw[:, q][None, :]
+    rate[:, 0] = 0.0
+    ptr, pair, coef = np.asarray(t["rhs_ptr"]), np.asarray(t["rhs_pair"]), np.asarray(t["rhs_coef"])
+    worst_f = worst_r = 0.0
+    for s in range(ni):
+        idx = pair[ptr[s]:ptr[s + 1]]
+        if len(idx) == 0:
+            assert not chem_f[0][:, s].any()
+            continue
+        terms = coef[ptr[s]:ptr[s + 1]][None, :] * (rate[:, idx] - rate[:, idx + 1])           # [nz, n_terms] in double, as both kernels form them
+        truth = terms.astype(np.longdouble).sum(axis=1)
+        scale = np.abs(terms).sum(axis=1)
+        ok = scale > 0
+        worst_f = max(worst_f, float(np.max(np.abs(chem_f[0][:, s] - truth)[ok] / scale[ok])) if ok.any() else 0.0)
+        worst_r = max(worst_r, float(np.max(np.abs(chem_r[:, s] - truth)[ok] / scale[ok])) if ok.any() else 0.0)
+    print("%s-%d: chemdf vs the 80-bit sum of the same terms, relative to sum |terms|: segmented order %.2e, reference order %.2e" % (
+        case.tag, case.step, worst_f, worst_r))
+    assert worst_f < 1e-14 and worst_f <= max(4 * worst_r, 2e-15)
 
 
 def test_lhs_blocks(case):

@@ -61,7 +61,8 @@ class AtmView(C.Structure):
 class StepOpts(C.Structure):
     _fields_ = [("mtol", C.c_double), ("atol", C.c_double), ("refine", C.c_int), ("zero_delta_row0", C.c_int),
                 ("n_fix_bot", C.c_int), ("fix_bot_idx", _ip), ("fix_bot_val", _dp), ("delta_zero_sp", _bp),
-                ("fix_mask", _bp), ("fix_y", _dp), ("na", C.c_int), ("compo", _dp), ("refine_dt_min", C.c_double)]
+                ("fix_mask", _bp), ("fix_y", _dp), ("na", C.c_int), ("compo", _dp), ("refine_dt_min", C.c_double),
+                ("rhs_order", C.c_int)]
 
 
 class PhotoView(C.Structure):
@@ -317,9 +318,10 @@ class Columns(object):
         check(self.lib.vk_set_k_rows(self.handle, len(rows), iptr(rows), dptr(vals)))
 
     def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None,
-                      delta_zero_sp=None, fix_mask=None, fix_y=None, compo=None, refine_dt_min=REFINE_DT_MIN):
+                      delta_zero_sp=None, fix_mask=None, fix_y=None, compo=None, refine_dt_min=REFINE_DT_MIN, rhs_order=0):
         """refine: passes of iterative refinement per solve (double-double residual); -1 = auto: one safeguarded pass on the columns
-        whose dt >= refine_dt_min (needs compo [ni, na])."""
+        whose dt >= refine_dt_min (needs compo [ni, na]).  rhs_order: 0 = segmented summation of the production / loss terms (default),
+        1 = the reference's left-to-right order (chemdf bit-identical to the generated chem_funs.py)."""
         fbi = i32(fix_bot_idx)
         fbv = None if len(fbi) == 0 else f64(fix_bot_val).reshape(self.ncol, len(fbi))
         dz = None if delta_zero_sp is None else u8(delta_zero_sp)
@@ -327,7 +329,7 @@ class Columns(object):
         fy = None if fix_y is None else f64(fix_y).reshape(self.ncol, self.nz, self.ni)
         cp = None if compo is None else f64(compo).reshape(self.ni, -1)
         o = StepOpts(float(mtol), float(atol), int(refine), int(zero_delta_row0), len(fbi), iptr(fbi) if len(fbi) else None,
-                     dptr(fbv), bptr(dz), bptr(fm), dptr(fy), 0 if cp is None else cp.shape[1], dptr(cp), float(refine_dt_min))
+                     dptr(fbv), bptr(dz), bptr(fm), dptr(fy), 0 if cp is None else cp.shape[1], dptr(cp), float(refine_dt_min), int(rhs_order))
         check(self.lib.vk_set_step_opts(self.handle, C.byref(o)))
 
     # ---------------------------------------------------------------- hot path

@@ -179,6 +179,41 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
             load[best] += d->rhs_ptr[s + 1] - d->rhs_ptr[s] + 4;     // + a little per-species overhead
         }
     }
+    // segmented rhs summation: flat term list in species order, 32 equal chunks
+    std::vector<unsigned short> flat16;
+    std::vector<int> seg_ptr(ni + 1, 0), lane_slot0(32, 0);
+    int flat_ok = (rhs_unit && nr / 2 < 16383) ? 1 : 0, flat_T = 0, n_segs = 0;
+    if (flat_ok) {
+        const int nterm = d->n_rhs;
+        flat_T = std::max(1, (nterm + 31) / 32);
+        flat16.assign((size_t)32 * flat_T, (unsigned short)(nr / 2));          // padding: the always-zero pair slot v[npair], no flush
+        std::vector<int> sp_of(nterm);
+        for (int s = 0; s < ni; s++) for (int q = d->rhs_ptr[s]; q < d->rhs_ptr[s + 1]; q++) sp_of[q] = s;
+        int seg = 0, cur_sp = -1;
+        std::vector<int> first_seg(ni, -1), last_seg(ni, -1);
+        for (int f = 0; f < nterm; f++) {
+            const int l = f / flat_T, q = f % flat_T;
+            if (q == 0) lane_slot0[l] = seg;
+            const int s = sp_of[f];
+            if (first_seg[s] < 0) first_seg[s] = seg;
+            last_seg[s] = seg;
+            const bool flush = (f + 1 == nterm) || (sp_of[f + 1] != s) || (q == flat_T - 1);
+            const int ci = (int)d->rhs_coef[f];
+            flat16[(size_t)32 * q + l] = (unsigned short)((((d->rhs_pair[f] - 1) / 2) & 0x3fff) | (flush ? 0x4000 : 0) | (ci < 0 ? 0x8000 : 0));
+            if (flush) seg++;
+            (void)cur_sp;
+        }
+        for (int l = (nterm + flat_T - 1) / flat_T; l < 32; l++) lane_slot0[l] = seg;
+        n_segs = seg;
+        int run = 0;
+        for (int s = 0; s < ni; s++) {           // species without terms own no partial
+            seg_ptr[s] = (first_seg[s] >= 0) ? first_seg[s] : run;
+            if (last_seg[s] >= 0) run = last_seg[s] + 1;
+        }
+        seg_ptr[ni] = n_segs;
+        for (int s = ni - 1; s >= 0; s--) if (first_seg[s] < 0) seg_ptr[s] = seg_ptr[s + 1];
+    }
+    if (flat16.empty()) flat16.push_back(0);
     // work schedule of the Jacobian kernel: segments of <= 16 terms sorted by decreasing length
     struct Seg { unsigned rc; int q0; int len; int ent; };
     std::vector<Seg> segs;
@@ -264,6 +299,8 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
 #define CP(vec, field) if (rcode == VK_OK) rcode = dev_copy(n->allocs, vec.data(), vec.size(), &nd.field)
     CP(rf, rate_fac); CP(rp, rate_pow); CP(rt, rhs_term); CP(rc, jac_rc); CP(jt, jac_term); CP(segw, jac_seg); CP(multi, jac_multi);
     CP(rd16, rhs_desc16); CP(lane_sp, rhs_lane_sp);
+    CP(flat16, rhs_flat16); CP(seg_ptr, rhs_seg_ptr); CP(lane_slot0, rhs_lane_slot0);
+    nd.rhs_flat_ok = flat_ok; nd.rhs_flat_T = flat_T; nd.rhs_n_seg = n_segs;
     CP(uq, jac_uniq); CP(ttT, jac_tt); CP(seg4, jac_seg4); CP(grp, jac_grp);
     nd.rhs_unit = rhs_unit;
 #undef CP
@@ -507,6 +544,7 @@ int vk_set_step_opts(vk_column *c, const vk_step_opts *o)
     if (rc == VK_OK && o->fix_mask) rc = dev_copy(c->opt_allocs, o->fix_mask, nv, &d.fix_mask);
     if (rc == VK_OK && o->fix_y) rc = dev_copy(c->opt_allocs, o->fix_y, nv, &d.fix_y);
     d.refine_dt_min = o->refine_dt_min;
+    d.rhs_order = o->rhs_order;
     if (rc == VK_OK && o->compo && o->na > 0) {
         if (o->na > 8) { set_error("at most 8 elements in atom_list are supported"); return VK_ERR_UNSUPPORTED; }
         d.na = o->na;

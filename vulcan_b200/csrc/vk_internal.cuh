@@ -49,6 +49,14 @@ struct NetDev {
     int rhs_unit;
     const unsigned short *rhs_desc16;   // [n_rhs]
     const int *rhs_lane_sp;             // [32][VK_RHS_SPL]
+    // segmented summation (rhs_order = 0, the default): the n_rhs terms in species order are cut into 32 equal chunks, one per lane
+    // (T = rhs_flat_T terms each, stored transposed: term q of lane l at rhs_flat16[32 q + l]); bit 15 = minus, bit 14 = "flush the partial
+    // sum after this term" (end of the species or of the chunk), bits 0..13 = reaction pair; partial sums are numbered in flat order, species
+    // s owns the partials [rhs_seg_ptr[s], rhs_seg_ptr[s+1]), lane l starts at partial rhs_lane_slot0[l]
+    int rhs_flat_ok, rhs_flat_T, rhs_n_seg;
+    const unsigned short *rhs_flat16;   // [32 * T]
+    const int *rhs_seg_ptr;             // [ni + 1]
+    const int *rhs_lane_slot0;          // [32]
     // Jacobian work schedule: entries cut into segments of <= 16 terms, sorted by length (warp lanes carry equal work)
     int n_seg, n_multi, n_part;
     const uint4 *jac_seg;       // [n_seg]   x = row | col << 16, y = first term, z = n terms | slot << 16 (slot 0xffff: whole entry)
@@ -96,6 +104,7 @@ struct StepOptsDev {
     const unsigned char *delta_zero_sp;
     const unsigned char *fix_mask;    // [ncol][nz][ni]
     const double *fix_y;
+    int rhs_order;                    // 0: segmented summation of the production / loss terms (default), 1: the reference's left-to-right order
     int na;                           // refine = auto: element composition for the safeguard
     const double *compo;              // [ni][na]
     double refine_dt_min;
