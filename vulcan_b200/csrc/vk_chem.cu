@@ -596,7 +596,8 @@ __device__ __forceinline__ void cp_async8(double *dst, const double *src)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col, int lpb, int dbg)
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR, 2) lhs_ml_kernel(LhsArgs A, LhsMlSmem SL, int blocks_per_col, int lpb, int dbg)
 {
     extern __shared__ __align__(16) double sm[];
     const int ni = A.net.ni, nr = A.net.nr, nz = A.nz, ld = A.ld;
@@ -1319,7 +1320,11 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     }
     const LhsMlSmem SL = lhs_ml_layout(a.net, ld);
     if (SL.total_bytes > 227 * 1024) { set_error("Jacobian kernel tables do not fit the shared memory of one SM"); return VK_ERR_UNSUPPORTED; }
-    { int rc = ensure_smem((const void *)lhs_ml_kernel, c->net->device, (size_t)SL.total_bytes); if (rc) return rc; }
+    // threads per block: 256 (8 warps, <= 128 registers) or 512 (16 warps at <= 64 registers: twice the warps per SM to hide the latency
+    // of the gather's dependent shared-memory loads); VK_LHS_NT overrides
+    static int nthr = -1;
+    if (nthr < 0) { const char *e = getenv("VK_LHS_NT"); nthr = e ? atoi(e) : 256; if (nthr != 512 && nthr != 384) nthr = 256; }
+    { int rc = ensure_smem(nthr == 512 ? (const void *)lhs_ml_kernel<512> : (nthr == 384 ? (const void *)lhs_ml_kernel<384> : (const void *)lhs_ml_kernel<256>), c->net->device, (size_t)SL.total_bytes); if (rc) return rc; }
     // layers per block: amortise the table staging (40 KB per block) but keep >= ~8 blocks per SM in the grid
     int lpb = (int)(((long long)c->ncol * c->nz) / (8 * 148));
     lpb = std::max(1, std::min(lpb, 30));
@@ -1327,7 +1332,9 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     const int bpc = (c->nz + lpb - 1) / lpb;
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("VK_LHS_DBG"); dbg = e ? atoi(e) : 0; }
-    lhs_ml_kernel<<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
+    if (nthr == 512) lhs_ml_kernel<512><<<c->ncol * bpc, 512, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
+    else if (nthr == 384) lhs_ml_kernel<384><<<c->ncol * bpc, 384, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
+    else lhs_ml_kernel<256><<<c->ncol * bpc, 256, SL.total_bytes, c->stream>>>(a, SL, bpc, lpb, dbg);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }

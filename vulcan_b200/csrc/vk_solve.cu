@@ -345,7 +345,7 @@ int launch_factor(vk_column *c, const double *D, const double *up, const double 
     if (c->cr_now) return launch_cr_factor(c, D, up, dn, F, status);
     switch (c->nip) {
         case 48: return launch_factor_t<48, 2>(c, D, up, dn, F, status);
-        case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status);
+        case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status);      // (3 blocks per SM at <= 56 registers measured SLOWER: 25.3 vs 23.6 ms, spills)
         case 96: return launch_factor_t<96, 1>(c, D, up, dn, F, status);
         case 120: return launch_factor_t<120, 1>(c, D, up, dn, F, status);
         default: set_error("no factor kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
