@@ -229,6 +229,27 @@ int vk_ens_run_steady(vk_column *col, int max_iterations, int *n_active_left);
  * atm.dz [ncol][nz], atm.zco [ncol][nz+1]; any pointer may be NULL */
 int vk_ens_get_steady(vk_column *col, int *end_case, double *longdy, double *longdydt, double *aflux_change, double *dz, double *zco);
 
+/* ---- condensation operators of the caller: Integration.conden (op.py:1109-1300) and h2o / nh3_conden_evap_relax
+ * (op.py:1340-1421) on the device.  Tables come from the reference's containers (atm.sat_p, atm.r_p, atm.rho_p, var.conden_re_list, var.Rf). */
+typedef struct {
+    int n_re;                          /* condensation growth reactions `X -> X_l_s` handled by conden */
+    const int *re_idx, *gas_idx;       /* [n_re] forward reaction id, gas species */
+    const double *m, *rho_p, *r_p;     /* [n_re] molecular mass in g (amu / Navo as the reference writes it), atm.rho_p, atm.r_p */
+    const double *sat;                 /* [n_re][nz] saturation number density sat_p / kb / Tco (x humidity for H2O) */
+    const unsigned char *zero_rate;    /* [n_re] 1: the relaxation operator replaces the reaction, k[re] = k[re+1] = 0 (op.py:1124-1126) */
+    int n_relax;                       /* relaxation operators in call order (op.py:896-901) */
+    const int *relax_kind;             /* [n_relax] 1 = h2o_conden_evap_relax, 2 = nh3_conden_evap_relax */
+    const int *relax_gas, *relax_ice;  /* [n_relax] vapour / condensate species */
+    const int *relax_top;              /* [n_relax] NH3: top layer of the condensation zone, argmin(sat_mix) (op.py:1390); else nz */
+    const double *relax_m, *relax_rho, *relax_r;   /* [n_relax] */
+    const double *relax_sat;           /* [n_relax][nz] saturation number density */
+    double start_conden_time, stop_conden_time, post_conden_rtol;   /* vulcan_cfg (device-resident loop only) */
+} vk_conden_desc;
+int vk_conden_setup(vk_column *col, const vk_conden_desc *d);
+/* conden + the relaxation operators on host state: y, ymix [ncol][nz][ni] in / out, dt [ncol] (the step just taken), n_0 [ncol][nz];
+ * k_rows out [ncol][n_re][2][nz] (also written into the device copy of k) or NULL */
+int vk_conden_apply(vk_column *col, double *y, double *ymix, const double *dt, const double *n_0, double *k_rows);
+
 /* refine = -1 bookkeeping: refinement passes kept / tried by the safeguard since the handle was created, [ncol] each, may be NULL */
 int vk_refine_stats(vk_column *col, int *kept, int *tried);
 /* timing of the last vk_ros2_solve / vk_ens_run on the handle's stream, measured with CUDA events (ms) */

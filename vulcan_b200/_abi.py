@@ -25,7 +25,7 @@ SYMBOLS = [
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
     "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
-    "vk_debug_time_kernel", "vk_refine_stats", "vk_ens_setup_steady", "vk_ens_photo_update", "vk_ens_run_steady", "vk_ens_get_steady",
+    "vk_debug_time_kernel", "vk_refine_stats", "vk_ens_setup_steady", "vk_ens_photo_update", "vk_ens_run_steady", "vk_ens_get_steady", "vk_conden_setup", "vk_conden_apply",
 ]
 
 
@@ -95,6 +95,13 @@ class SteadyOpts(C.Structure):
                 ("hist_cap", C.c_int), ("hist_stride", C.c_int)]
 
 
+class CondenDesc(C.Structure):
+    _fields_ = [("n_re", C.c_int), ("re_idx", _ip), ("gas_idx", _ip), ("m", _dp), ("rho_p", _dp), ("r_p", _dp), ("sat", _dp), ("zero_rate", _bp),
+                ("n_relax", C.c_int), ("relax_kind", _ip), ("relax_gas", _ip), ("relax_ice", _ip), ("relax_top", _ip), ("relax_m", _dp),
+                ("relax_rho", _dp), ("relax_r", _dp), ("relax_sat", _dp), ("start_conden_time", C.c_double), ("stop_conden_time", C.c_double),
+                ("post_conden_rtol", C.c_double)]
+
+
 _lib = None
 
 
@@ -139,6 +146,8 @@ def load():
     lib.vk_device_buffers.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]
     lib.vk_stream.argtypes = [_vp, C.POINTER(_vp)]
     lib.vk_refine_stats.argtypes = [_vp, _ip, _ip]
+    lib.vk_conden_setup.argtypes = [_vp, C.POINTER(CondenDesc)]
+    lib.vk_conden_apply.argtypes = [_vp, _dp, _dp, _dp, _dp, _dp]
     lib.vk_ens_setup_steady.argtypes = [_vp, C.POINTER(SteadyOpts)]
     lib.vk_ens_photo_update.argtypes = [_vp]
     lib.vk_ens_run_steady.argtypes = [_vp, C.c_int, _ip]
@@ -433,6 +442,31 @@ class Columns(object):
 
     def photo_reset(self):
         check(self.lib.vk_photo_reset(self.handle))
+
+    # ---------------------------------------------------------------- condensation operators (op.py:1109-1421)
+    def conden_setup(self, re_idx, gas_idx, m, rho_p, r_p, sat, zero_rate, relax_kind=(), relax_gas=(), relax_ice=(), relax_top=(), relax_m=(),
+                     relax_rho=(), relax_r=(), relax_sat=None, start_conden_time=0.0, stop_conden_time=1e300, post_conden_rtol=0.0):
+        nz = self.nz
+        re_idx, gas_idx = i32(re_idx), i32(gas_idx)
+        n_re, n_rx = len(re_idx), len(relax_kind)
+        keep = [re_idx, gas_idx, f64(m), f64(rho_p), f64(r_p), f64(sat).reshape(n_re, nz) if n_re else f64(np.zeros((0, nz))), u8(zero_rate),
+                i32(relax_kind), i32(relax_gas), i32(relax_ice), i32(relax_top), f64(relax_m), f64(relax_rho), f64(relax_r),
+                f64(relax_sat).reshape(n_rx, nz) if n_rx else f64(np.zeros((0, nz)))]
+        d = CondenDesc(n_re, iptr(keep[0]), iptr(keep[1]), dptr(keep[2]), dptr(keep[3]), dptr(keep[4]), dptr(keep[5]), bptr(keep[6]), n_rx,
+                       iptr(keep[7]), iptr(keep[8]), iptr(keep[9]), iptr(keep[10]), dptr(keep[11]), dptr(keep[12]), dptr(keep[13]), dptr(keep[14]),
+                       float(start_conden_time), float(stop_conden_time), float(post_conden_rtol))
+        check(self.lib.vk_conden_setup(self.handle, C.byref(d)))
+        self._conden_nre = n_re
+
+    def conden_apply(self, y, ymix, dt, n_0):
+        """conden + the relaxation operators on the device: returns y, ymix, k_rows [ncol, n_re, 2, nz]"""
+        y = self._shape(y, (self.nz, self.ni)).copy()
+        ymix = self._shape(ymix, (self.nz, self.ni)).copy()
+        dt = f64(np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,)))
+        n_0 = f64(np.broadcast_to(f64(n_0), (self.ncol, self.nz)))
+        kr = np.zeros((self.ncol, self._conden_nre, 2, self.nz)) if self._conden_nre else None
+        check(self.lib.vk_conden_apply(self.handle, dptr(y), dptr(ymix), dptr(dt), dptr(n_0), dptr(kr)))
+        return y, ymix, kr
 
     def refine_stats(self):
         kept, tried = np.zeros(self.ncol, dtype=np.int32), np.zeros(self.ncol, dtype=np.int32)

@@ -14,7 +14,7 @@ LIB = os.path.join(LIBDIR, "libvulcan_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = {"vk_api.cu": [], "vk_chem.cu": ["-fmad=false"], "vk_step.cu": ["-fmad=false"], "vk_photo.cu": ["-fmad=false"],
-         "vk_solve.cu": [], "vk_ens.cu": ["-fmad=false"], "vk_steady.cu": ["-fmad=false"], "vk_rates.cu": ["-fmad=false"]}
+         "vk_solve.cu": [], "vk_ens.cu": ["-fmad=false"], "vk_steady.cu": ["-fmad=false"], "vk_conden.cu": ["-fmad=false"], "vk_rates.cu": ["-fmad=false"]}
 
 
 def _newer(target, deps):

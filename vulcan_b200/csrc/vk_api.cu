@@ -38,6 +38,7 @@ int launch_clip(vk_column *c, double *y_dev, const double *ymix_in_dev, double *
                 double *nega_dev, int *anyneg_dev);
 void photo_destroy(vk_column *c);
 void ens_destroy(vk_column *c);
+void conden_destroy(vk_column *c);
 void rates_destroy(vk_network *n);
 
 template <typename T>
@@ -381,6 +382,7 @@ void vk_column_destroy(vk_column *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     photo_destroy(c);
     ens_destroy(c);
+    conden_destroy(c);
     cr_plan_free(c->cr);
     if (c->refine_kept) cudaFree(c->refine_kept);
     double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->xn, c->z, c->up, c->dn,

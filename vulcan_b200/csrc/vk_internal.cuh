@@ -123,6 +123,7 @@ struct vk_network {
 struct PhotoState;
 struct EnsState;
 struct CrPlan;
+struct CondenState;
 
 struct vk_column {
     vk_network *net;
@@ -150,6 +151,7 @@ struct vk_column {
     size_t h_pin_bytes;
     PhotoState *photo;
     EnsState *ens;
+    CondenState *conden;        // condensation operators on the device (vk_conden.cu), optional
     CrPlan *cr;                 // single-column latency path: plan + buffers of the block cyclic reduction (vk_cr.inl), built on first use
     double dt_host_max;         // largest step size of the batch when the host knows it for the current step (vk_ros2_solve, the one-column
                                 // device loops), else < 0: refine = auto then skips its launches outright below refine_dt_min

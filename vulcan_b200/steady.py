@@ -12,6 +12,55 @@ import time
 import numpy as np
 
 
+KB = 1.38064852e-16      # phy_const.py:3
+NAVO = 6.02214086e23     # phy_const.py:4
+# growth reactions handled by Integration.conden: reaction string -> (gas species, particle key of atm.r_p / atm.rho_p, molecular mass in
+# amu exactly as the reference writes it, op.py:1122-1296)
+CONDEN_REACTIONS = {'H2O -> H2O_l_s': ('H2O', 'H2O_l_s', 18.), 'NH3 -> NH3_l': ('NH3', 'NH3_l_s', 17.),
+                    'H2SO4 -> H2SO4_l': ('H2SO4', 'H2SO4_l', 98.022), 'S2 -> S2_l_s': ('S2', 'S2_l_s', 45.019),
+                    'S4 -> S4_l_s': ('S4', 'S4_l_s', 32.06 * 4), 'S8 -> S8_l_s': ('S8', 'S8_l_s', 360.152), 'C -> C_s': ('C', 'C_s', 12.011)}
+
+
+def conden_tables(cfg, var, atm, species):
+    """keyword arguments of _abi.Columns.conden_setup from the reference's containers: what Integration.conden and the two relaxation
+    operators read (op.py:1109-1421) - var.conden_re_list / var.Rf, atm.sat_p, atm.r_p, atm.rho_p, atm.Tco, atm.n_0, vulcan_cfg.humidity,
+    condense_sp, use_relax."""
+    sp = list(species)
+    nz = len(atm.Tco)
+    Tco = np.asarray(atm.Tco, dtype=float)
+    use_relax = list(getattr(cfg, "use_relax", []) or [])
+    re_idx, gas_idx, m, rho_p, r_p, sat, zero = [], [], [], [], [], [], []
+    for re in var.conden_re_list:
+        ent = CONDEN_REACTIONS.get(var.Rf[re])
+        if ent is None or ent[0] not in cfg.condense_sp:
+            continue
+        gas, part, amu = ent
+        re_idx.append(int(re)); gas_idx.append(sp.index(gas))
+        if gas in ('H2O', 'NH3') and use_relax:                 # relaxation replaces the growth reaction (op.py:1124-1126)
+            zero.append(1); m.append(0.0); rho_p.append(1.0); r_p.append(1.0); sat.append(np.zeros(nz))
+            continue
+        zero.append(0)
+        m.append(amu / NAVO); rho_p.append(float(atm.rho_p[part])); r_p.append(float(atm.r_p[part]))
+        s_ = np.asarray(atm.sat_p[gas], dtype=float) / KB / Tco
+        if gas == 'H2O':
+            s_ = s_ * cfg.humidity
+        sat.append(s_)
+    kind, rgas, rice, rtop, rm, rrho, rr, rsat = [], [], [], [], [], [], [], []
+    if 'H2O' in use_relax:                                      # op.py:1340-1376
+        kind.append(1); rgas.append(sp.index('H2O')); rice.append(sp.index('H2O_l_s')); rtop.append(nz)
+        rm.append(18. / NAVO); rrho.append(float(atm.rho_p['H2O_l_s'])); rr.append(float(atm.r_p['H2O_l_s']))
+        rsat.append(np.asarray(atm.sat_p['H2O'], dtype=float) / KB / Tco * cfg.humidity)
+    if 'NH3' in use_relax:                                      # op.py:1378-1421
+        satp = np.asarray(atm.sat_p['NH3'], dtype=float) / KB / Tco
+        kind.append(2); rgas.append(sp.index('NH3')); rice.append(sp.index('NH3_l_s')); rtop.append(int(np.argmin(satp / np.asarray(atm.n_0, dtype=float))))
+        rm.append(17. / NAVO); rrho.append(float(atm.rho_p['NH3_l_s'])); rr.append(float(atm.r_p['NH3_l_s']))
+        rsat.append(satp)
+    return dict(re_idx=re_idx, gas_idx=gas_idx, m=m, rho_p=rho_p, r_p=r_p, sat=np.array(sat).reshape(len(re_idx), nz), zero_rate=zero,
+                relax_kind=kind, relax_gas=rgas, relax_ice=rice, relax_top=rtop, relax_m=rm, relax_rho=rrho, relax_r=rr,
+                relax_sat=np.array(rsat).reshape(len(kind), nz), start_conden_time=float(getattr(cfg, "start_conden_time", 0.0)),
+                stop_conden_time=float(getattr(cfg, "stop_conden_time", 1e300)), post_conden_rtol=float(getattr(cfg, "post_conden_rtol", 0.0)))
+
+
 class DeviceIntegration(object):
     def __init__(self, odesolver, chunk=64, verbose=False):
         self.odesolver, self.chunk, self.verbose = odesolver, int(chunk), verbose
