@@ -219,6 +219,14 @@ typedef struct {
     int n_diff_esc; const int *diff_esc_idx; /* vulcan_cfg.diff_esc */
     int hist_cap, hist_stride;               /* ring of accepted states for conv: hist_cap states, every hist_stride-th accepted step
                                               * (hist_cap = conv_step, hist_stride = 1: the reference's look-back exactly) */
+    /* condensation in the loop (op.py:856-901; needs vk_conden_setup, and zeroed fix_mask / fix_y in vk_set_step_opts for the switch) */
+    int use_condense;                        /* conden + relaxation operators after every accepted step from start_conden_time on */
+    int fix_species_switch;                  /* vulcan_cfg.fix_species non-empty: freeze them once t > stop_conden_time (op.py:860-893) */
+    int fix_from_coldtrap;                   /* vulcan_cfg.fix_species_from_coldtrap_lev */
+    int n_fix; const int *fix_sp;            /* vulcan_cfg.fix_species */
+    const unsigned char *fix_whole_column;   /* [n_fix] condensates (H2O_l_s, H2SO4_l, NH3_l_s, S8_l_s): frozen up to layer nz-2 (op.py:878-879) */
+    const double *fix_sat_mix;               /* [n_fix][nz] atm.sat_mix of the gas species (cold-trap level, op.py:881-892); zeros for condensates */
+    double start_conden_time, stop_conden_time, post_conden_rtol;
 } vk_steady_opts;
 int vk_ens_setup_steady(vk_column *col, const vk_steady_opts *o);
 /* one photolysis update of every active column from the resident state (vulcan.py:170-176 does one at set-up, before the loop) */
@@ -228,6 +236,9 @@ int vk_ens_run_steady(vk_column *col, int max_iterations, int *n_active_left);
 /* per column: para.end_case (0 = still running, 1 converged, 2 runtime, 3 count_max), var.longdy, var.longdydt, var.aflux_change,
  * atm.dz [ncol][nz], atm.zco [ncol][nz+1]; any pointer may be NULL */
 int vk_ens_get_steady(vk_column *col, int *end_case, double *longdy, double *longdydt, double *aflux_change, double *dz, double *zco);
+/* result of the fix_species switch (op.py:860-893) per column: para.fix_species_start, the rows frozen (fix_mask [ncol][nz][ni]; per
+ * species the count of set rows is atm.conden_min_lev) and the values they are frozen at (var.fix_y); any pointer may be NULL */
+int vk_ens_get_fix(vk_column *col, int *fix_started, unsigned char *fix_mask, double *fix_y);
 
 /* ---- condensation operators of the caller: Integration.conden (op.py:1109-1300) and h2o / nh3_conden_evap_relax
  * (op.py:1340-1421) on the device.  Tables come from the reference's containers (atm.sat_p, atm.r_p, atm.rho_p, var.conden_re_list, var.Rf). */

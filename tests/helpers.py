@@ -213,6 +213,8 @@ def attach_conden(case, cfg, var, atm):
     path = os.path.join(GOLD, "%s_conden.npz" % case.tag)
     if not os.path.exists(path):       # cfg-switch variants share the base config's saturation curves / particle tables
         path = os.path.join(GOLD, "%s_conden.npz" % NETWORK_OF.get(case.tag, case.tag))
+    if not os.path.exists(path):       # Jupiter: the tables were recorded with the JupiterFix timing variant of the same cfg
+        path = os.path.join(GOLD, "%sFix_conden.npz" % case.tag)
     if not os.path.exists(path):
         return None
     cf = dict(np.load(path, allow_pickle=False))

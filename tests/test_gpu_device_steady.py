@@ -60,3 +60,63 @@ def test_ensemble_runs_every_column_to_its_own_convergence():
     ya, yb = alone["y"][0], out["y"][2]
     m = yb > 1e-8 * yb.sum(axis=1, keepdims=True)
     assert np.max(np.abs(ya - yb)[m] / yb[m]) < 5e-3
+
+
+@pytest.mark.parametrize("tag,edit,count_max", [
+    ("Jupiter", {"start_conden_time": 10., "stop_conden_time": 500.}, 200),     # the JupiterFix timing: conden from step ~95, the switch at step 154
+    ("Jupiter", {}, 60),                                                         # shipped timing: no condensation yet within 60 steps
+    ("Earth", {}, 80),                                                           # start_conden_time = 0: H2O relaxation + H2SO4 growth from step 0
+])
+def test_condensing_config_device_loop_matches_host_loop(tag, edit, count_max):
+    """conden / relaxation / the fix_species switch inside the device-resident loop (op.py:856-901) against the host mirror of
+    op.Integration calling the reference-order numpy operators (tests/integration_mirror.py, bit-exact to the reference's recorded calls in
+    test_integration_host.py) around the same step kernels."""
+    if not (have(tag, "step0000.npz") and (have(tag, "conden.npz") or have(tag + "Fix", "conden.npz"))):
+        pytest.skip("fixture missing")
+    c1, v1, a1, p1, i1, w1 = run_config(tag, count_max=count_max, cfg_edit=edit)
+    c2, v2, a2, p2, i2, w2 = run_config(tag, count_max=count_max, cfg_edit=edit, device_loop=True)
+    m = v1.ymix > 1e-25
+    rel = np.abs(v2.ymix - v1.ymix)[m] / v1.ymix[m]
+    print("%s %s: host loop %d steps t %.6e dt %.4e fix %s | device loop %d steps (+%d rejected) t %.6e dt %.4e fix %s | ymix > 1e-25 max rel %.2e "
+          "median %.2e | %.2f s vs %.2f s" % (tag, edit, p1.count, v1.t, v1.dt, p1.fix_species_start, p2.count, i2.n_rejected, v2.t, v2.dt,
+                                               p2.fix_species_start, rel.max(), np.median(rel), w1, w2))
+    assert p2.count == p1.count and p2.end_case == p1.end_case == 3
+    assert bool(p2.fix_species_start) == bool(p1.fix_species_start)
+    assert abs(v2.t - v1.t) <= 1e-6 * v1.t
+    assert rel.max() < 1e-5
+    if p1.fix_species_start:
+        sp = list(c1.net.species)
+        for s in ("H2O", "NH3", "H2O_l_s", "NH3_l_s"):
+            assert int(a2.conden_min_lev[s]) == int(a1.conden_min_lev[s]), s
+            top = int(a1.conden_min_lev[s])
+            f1, f2 = np.asarray(v1.fix_y[s])[:top], np.asarray(v2.fix_y[s])[:top]
+            assert np.allclose(f2, f1, rtol=1e-6, atol=1e-300), s
+            # frozen rows are held at the recorded value through the remaining steps (op.py:2960-2970)
+            assert np.array_equal(v2.y[:top, sp.index(s)], f2), s
+        assert not np.asarray(a2.vs).any()
+
+
+def test_jupiter_device_loop_through_the_switch_vs_the_reference():
+    """the reference's own run of the Jupiter cfg with start_conden_time = 10 s, stop_conden_time = 500 s (fixture set JupiterFix, recorded
+    from the unmodified reference): 154 accepted steps incl. ~60 with conden + both relaxation operators and the fix_species switch; the
+    device-resident loop is compared with the state, the frozen values and the cold-trap levels the reference had when it entered step 154."""
+    if not (have("JupiterFix", "step0154.npz") and have("Jupiter", "step0000.npz")):
+        pytest.skip("fixture missing")
+    fx = dict(np.load("%s/JupiterFix_step0154.npz" % GOLD, allow_pickle=False))
+    full = dict(np.load("%s/JupiterFix_full.npz" % GOLD, allow_pickle=False))
+    edit = {"start_conden_time": 10., "stop_conden_time": 500.}
+    c, v, a, p, integ, w = run_config("Jupiter", count_max=153, cfg_edit=edit, device_loop=True)
+    assert p.count == 154 == int(fx["count"])
+    m = fx["ymix"] > 1e-25
+    rel = np.abs(v.ymix - fx["ymix"])[m] / fx["ymix"][m]
+    print("Jupiter (JupiterFix timing), device loop: %d steps (+%d rejected) in %.2f s, t %.10e (reference %.10e), fix_species_start %s; "
+          "ymix > 1e-25 vs the reference: max rel %.2e median %.2e" % (p.count, integ.n_rejected, w, v.t, float(fx["t"]), p.fix_species_start,
+                                                                         rel.max(), np.median(rel)))
+    assert bool(p.fix_species_start) == bool(fx["fix_species_start"]) is True
+    assert abs(v.t - float(fx["t"])) <= 1e-9 * float(fx["t"])
+    assert rel.max() < 1e-6
+    for q, s in enumerate([str(x) for x in fx["fix_species"]]):
+        assert int(a.conden_min_lev[s]) == int(fx["conden_min_lev"][q]), s
+        top = int(fx["conden_min_lev"][q])
+        assert np.allclose(np.asarray(v.fix_y[s])[:top], fx["fix_y"][q][:top], rtol=1e-6, atol=1e-300), s
+    assert not np.asarray(a.vs).any()

@@ -25,7 +25,7 @@ SYMBOLS = [
     "vk_ros2_solve", "vk_clip_loss", "vk_eval_rhs", "vk_eval_lhs", "vk_blocktri_solve", "vk_photo_setup",
     "vk_photo_update", "vk_photo_read", "vk_photo_reset", "vk_ens_setup", "vk_ens_set_state", "vk_ens_run",
     "vk_ens_get_state", "vk_last_kernel_ms", "vk_device_buffers", "vk_stream", "vk_rates_set", "vk_compute_k", "vk_get_k",
-    "vk_debug_time_kernel", "vk_refine_stats", "vk_ens_setup_steady", "vk_ens_photo_update", "vk_ens_run_steady", "vk_ens_get_steady", "vk_conden_setup", "vk_conden_apply",
+    "vk_debug_time_kernel", "vk_refine_stats", "vk_ens_setup_steady", "vk_ens_photo_update", "vk_ens_run_steady", "vk_ens_get_steady", "vk_ens_get_fix", "vk_conden_setup", "vk_conden_apply",
 ]
 
 
@@ -92,7 +92,10 @@ class SteadyOpts(C.Structure):
                 ("conv_ignore_sp", _bp), ("use_photo", C.c_int), ("ini_update_photo_frq", C.c_int), ("final_update_photo_frq", C.c_int),
                 ("update_frq", C.c_int), ("pref_indx", C.c_int), ("gs", C.c_double), ("Rp", C.c_double), ("max_flux", C.c_double),
                 ("pico", _dp), ("ms", _dp), ("zco", _dp), ("Hp", _dp), ("dz", _dp), ("n_diff_esc", C.c_int), ("diff_esc_idx", _ip),
-                ("hist_cap", C.c_int), ("hist_stride", C.c_int)]
+                ("hist_cap", C.c_int), ("hist_stride", C.c_int),
+                ("use_condense", C.c_int), ("fix_species_switch", C.c_int), ("fix_from_coldtrap", C.c_int), ("n_fix", C.c_int),
+                ("fix_sp", _ip), ("fix_whole_column", _bp), ("fix_sat_mix", _dp),
+                ("start_conden_time", C.c_double), ("stop_conden_time", C.c_double), ("post_conden_rtol", C.c_double)]
 
 
 class CondenDesc(C.Structure):
@@ -152,6 +155,7 @@ def load():
     lib.vk_ens_photo_update.argtypes = [_vp]
     lib.vk_ens_run_steady.argtypes = [_vp, C.c_int, _ip]
     lib.vk_ens_get_steady.argtypes = [_vp, _ip, _dp, _dp, _dp, _dp, _dp]
+    lib.vk_ens_get_fix.argtypes = [_vp, _ip, _bp, _dp]
     lib.vk_debug_time_kernel.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
     _lib = lib
     return lib
@@ -503,9 +507,11 @@ class Columns(object):
         check(self.lib.vk_ens_run(self.handle, int(n_steps)))
 
     def ens_setup_steady(self, cfg, pico, ms, zco, Hp, dz, pref_indx, gs, conv_ignore_sp=None, diff_esc_idx=(), hist_cap=None,
-                         hist_stride=1, use_photo=None):
+                         hist_stride=1, use_photo=None, condense=None):
         """device-resident run to steady state (vk_ens_setup_steady): cfg = mapping or object with the vulcan_cfg names read by
-        Integration.stop / conv / __call__ (op.py:808-1087); zco / Hp / dz [ncol, nz(+1)] or one column's arrays (broadcast)."""
+        Integration.stop / conv / __call__ (op.py:808-1087); zco / Hp / dz [ncol, nz(+1)] or one column's arrays (broadcast).
+        condense (optional, after conden_setup): dict(fix_sp=[...], fix_whole=[...], fix_sat_mix=[n_fix, nz], from_coldtrap=bool,
+        start_conden_time, stop_conden_time, post_conden_rtol) - conden / relaxation / the fix_species switch run inside the loop."""
         g = (lambda n, d=None: cfg.get(n, d)) if isinstance(cfg, dict) else (lambda n, d=None: getattr(cfg, n, d))
         nz, ncol = self.nz, self.ncol
         rep = lambda a, tail: f64(np.broadcast_to(f64(a), (ncol,) + tail))
@@ -521,6 +527,17 @@ class Columns(object):
                        int(g("final_update_photo_frq", 5) or 5), int(g("update_frq", 0) or 0), int(pref_indx), float(gs), float(g("Rp")),
                        float(g("max_flux", 1e13) or 1e13), dptr(keep["pico"]), dptr(keep["ms"]), dptr(keep["zco"]), dptr(keep["Hp"]),
                        dptr(keep["dz"]), 0 if de is None else len(de), iptr(de), cap, int(hist_stride))
+        if condense is not None:
+            n_fix = len(condense.get("fix_sp", ()))
+            keep["fsp"] = i32(condense["fix_sp"]) if n_fix else None
+            keep["fwh"] = u8(condense["fix_whole"]) if n_fix else None
+            keep["fsm"] = f64(condense["fix_sat_mix"]).reshape(n_fix, nz) if n_fix else None
+            o.use_condense, o.fix_species_switch, o.n_fix = 1, int(n_fix > 0), n_fix
+            o.fix_from_coldtrap = int(bool(condense.get("from_coldtrap", False)))
+            o.fix_sp, o.fix_whole_column, o.fix_sat_mix = iptr(keep["fsp"]), bptr(keep["fwh"]), dptr(keep["fsm"])
+            o.start_conden_time = float(condense["start_conden_time"])
+            o.stop_conden_time = float(condense["stop_conden_time"])
+            o.post_conden_rtol = float(condense["post_conden_rtol"])
         check(self.lib.vk_ens_setup_steady(self.handle, C.byref(o)))
 
     def ens_photo_update(self):
@@ -538,6 +555,13 @@ class Columns(object):
         zco = np.empty((self.ncol, self.nz + 1)) if want_grid else None
         check(self.lib.vk_ens_get_steady(self.handle, iptr(ec), dptr(ld), dptr(ldt), dptr(ch), dptr(dz), dptr(zco)))
         return dict(end_case=ec, longdy=ld, longdydt=ldt, aflux_change=ch, dz=dz, zco=zco)
+
+    def ens_get_fix(self):
+        fs = np.zeros(self.ncol, dtype=np.int32)
+        fm = np.zeros((self.ncol, self.nz, self.ni), dtype=np.uint8)
+        fy = np.zeros((self.ncol, self.nz, self.ni))
+        check(self.lib.vk_ens_get_fix(self.handle, iptr(fs), bptr(fm), dptr(fy)))
+        return dict(fix_started=fs, fix_mask=fm, fix_y=fy)
 
     def ens_get_state(self, want_y=True):
         y = np.empty((self.ncol, self.nz, self.ni)) if want_y else None

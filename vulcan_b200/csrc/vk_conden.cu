@@ -134,16 +134,17 @@ static int ccopy(CondenState *s, const T *host, size_t n, T **out)
     return VK_OK;
 }
 
-// conden + the relaxation operators on device state; pred (optional): the columns they act on
-int conden_device(vk_column *c, double *y_dev, double *ymix_dev, const double *dt_dev, const double *n0_dev, const int *pred, double *k_rows_out)
+// conden (part & 1) and the relaxation operators (part & 2) on device state; pred (optional): the columns they act on
+int conden_device(vk_column *c, double *y_dev, double *ymix_dev, const double *dt_dev, const double *n0_dev, const int *pred, double *k_rows_out,
+                  int part)
 {
     CondenDev &s = c->conden->d;
-    if (s.n_re > 0) {
+    if ((part & 1) && s.n_re > 0) {
         CondenArgs a{c->nz, c->ni, c->nr, c->ncol, s, y_dev, c->atm.Dzz, c->atm.csn, c->k, c->k_cs, pred, k_rows_out};
         const int total = c->ncol * s.n_re * c->nz;
         conden_rate_kernel<<<(total + 127) / 128, 128, 0, c->stream>>>(a);
     }
-    for (int w = 0; w < s.n_relax; w++) {
+    for (int w = 0; (part & 2) && w < s.n_relax; w++) {
         RelaxArgs r{c->nz, c->ni, w, s, y_dev, ymix_dev, c->atm.Dzz, c->atm.csn, n0_dev, dt_dev, c->atm.n_gas, c->atm.gas_indx, pred};
         relax_kernel<<<c->ncol, 256, sizeof(double) * c->nz, c->stream>>>(r);
     }
@@ -208,7 +209,7 @@ int vk_conden_apply(vk_column *c, double *y, double *ymix, const double *dt, con
     VK_CUDA(cudaMemcpyAsync(c->ymix_out, ymix, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, dt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(dn0, n_0, sizeof(double) * c->ncol * c->nz, cudaMemcpyHostToDevice, c->stream));
-    int rc = conden_device(c, c->sol, c->ymix_out, c->dt, dn0, nullptr, dk);
+    int rc = conden_device(c, c->sol, c->ymix_out, c->dt, dn0, nullptr, dk, 3);
     if (rc == VK_OK) {
         VK_CUDA(cudaMemcpyAsync(y, c->sol, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
         VK_CUDA(cudaMemcpyAsync(ymix, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));

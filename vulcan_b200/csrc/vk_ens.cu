@@ -36,6 +36,15 @@ struct CtlArgs {
     const int *act;
     int *fresh, *do_mu;
     double *t_time; int cap_t, update_frq;
+    // condensation in the loop: flags for the operators that follow an accepted step, evaluated with the model time BEFORE save_step
+    // like the reference (op.py:856, 860); rtol_col: the rtol step_size reads (vulcan_cfg.rtol, changed by the switch; step_ok keeps the
+    // value frozen in its default argument, op.py:2489)
+    int use_condense, use_fix;
+    double start_conden_time, stop_conden_time, post_conden_rtol;
+    const int *fix_started;
+    int *do_conden, *do_switch;
+    double *dt_used;
+    const double *rtol_col;
 };
 
 __global__ void control_kernel(CtlArgs a)
@@ -66,6 +75,15 @@ __global__ void control_kernel(CtlArgs a)
         // mixing ratios of the failed attempt (ymix is not restored by reset_y), i.e. the attempt is effectively accepted
         if (dt < a.dt_min) { dt = a.dt_min; acc = 2; }
     }
+    bool sw = false;
+    if (a.do_conden) {
+        const double t_before = a.t[col];
+        const int dc = (acc && a.use_condense && t_before >= a.start_conden_time && !a.fix_started[col]) ? 1 : 0;
+        a.do_conden[col] = dc;
+        sw = dc && a.use_fix && t_before > a.stop_conden_time;
+        a.do_switch[col] = sw ? 1 : 0;
+        a.dt_used[col] = dt;
+    }
     if (a.fresh) a.fresh[col] = acc ? 1 : 0;
     if (a.do_mu) a.do_mu[col] = (acc && a.update_frq > 0 && (a.n_accept[col] % a.update_frq) == 0) ? 1 : 0;
     if (acc) {
@@ -74,8 +92,10 @@ __global__ void control_kernel(CtlArgs a)
         a.n_accept[col] += 1;
         {
             for (int q = 0; q < a.na; q++) a.atom_loss_prev[col * a.na + q] = loss[q];                        // backup op.py:941
-            double d = (delta == 0) ? 0.01 * a.rtol : delta;                                                  // step_size op.py:3113-3120
-            double hf = 0.9 * sqrt(a.rtol / d);
+            // step_size runs after the switch inside the same iteration (op.py:866, 925), so that iteration already sees post_conden_rtol
+            const double rt = sw ? a.post_conden_rtol : (a.rtol_col ? a.rtol_col[col] : a.rtol);
+            double d = (delta == 0) ? 0.01 * rt : delta;                                                      // step_size op.py:3113-3120
+            double hf = 0.9 * sqrt(rt / d);
             hf = fmax(hf, a.dt_var_min);
             hf = fmin(hf, a.dt_var_max);
             dt = dt * hf;
@@ -135,7 +155,10 @@ int launch_ens_control(vk_column *c)
     CtlArgs a{c->ncol, e->na, e->rtol, e->loss_eps, e->dt_min, e->dt_max, e->dt_var_min, e->dt_var_max, e->atom_sum, e->atom_ini,
               c->delta, e->anyneg, c->status, e->atom_loss_prev, c->dt, e->t, e->accept, e->n_accept, e->n_reject, e->n_delta,
               e->n_nega, e->n_loss, c->act, st ? e->steady.fresh : nullptr, st ? e->steady.do_mu : nullptr,
-              st ? e->steady.t_time : nullptr, st ? e->steady.cap_t : 0, st ? e->steady.update_frq : 0};
+              st ? e->steady.t_time : nullptr, st ? e->steady.cap_t : 0, st ? e->steady.update_frq : 0,
+              st ? e->steady.use_condense : 0, st ? e->steady.use_fix : 0, st ? e->steady.start_conden_time : 0.0,
+              st ? e->steady.stop_conden_time : 0.0, st ? e->steady.post_conden_rtol : 0.0, st ? e->steady.fix_started : nullptr, (st && e->steady.use_condense) ? e->steady.do_conden : nullptr,
+              st ? e->steady.do_switch : nullptr, st ? e->steady.dt_used : nullptr, (st && e->steady.use_condense) ? e->steady.rtol_col : nullptr};
     control_kernel<<<(c->ncol + 127) / 128, 128, 0, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     return VK_OK;

@@ -18,6 +18,15 @@ struct SteadyDev {
     double *longdy, *longdydt, *aflux_change;                               // [ncol]
     double *t_time; int cap_t;          // [ncol][cap_t] model time after every accepted step
     double *hist; int hist_cap, hist_stride;   // [ncol][hist_cap][nz*ni] ring of accepted states
+    // condensation in the loop (op.py:856-901; operators in vk_conden.cu): conden + relaxation after every accepted step from
+    // start_conden_time on, until the fix_species switch (t > stop_conden_time) freezes the condensable species of the column
+    int use_condense, use_fix, fix_from_coldtrap, n_fix;
+    double start_conden_time, stop_conden_time, post_conden_rtol;
+    int *fix_sp;                        // [n_fix] species of vulcan_cfg.fix_species
+    unsigned char *fix_whole;           // [n_fix] condensates: frozen up to layer nz-2 whatever the saturation profile (op.py:878-879)
+    double *fix_sat_mix;                // [n_fix][nz] atm.sat_mix (gas species)
+    int *fix_started, *do_conden, *do_switch;   // [ncol]
+    double *dt_used, *rtol_col;         // [ncol] step size of the accepted attempt; rtol read by step_size (post_conden_rtol after the switch)
 };
 }  // namespace vk
 

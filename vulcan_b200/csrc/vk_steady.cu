@@ -28,6 +28,55 @@ int launch_ens_apply(vk_column *c);
 int launch_atm_pre_pred(vk_column *c, const int *pred);
 int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_dev, const double *dz_dev, const int *pred,
                         double *aflux_change_out);
+int conden_device(vk_column *c, double *y_dev, double *ymix_dev, const double *dt_dev, const double *n0_dev, const int *pred, double *k_rows_out,
+                  int part);
+
+// the fix_species switch of the flagged columns (op.py:860-893): record the values the condensable species are frozen at, their cold-trap
+// levels, switch the rtol read by step_size, turn the settling velocity off.  One block per column.
+struct SwitchArgs {
+    int nz, ni;
+    SteadyDev s;
+    AtmDev atm;
+    const double *y, *n_0;             // state after the step (post-clip), [ncol][nz][ni]; n_0 [ncol][nz]
+    unsigned char *fix_mask; double *fix_y;   // step options of the handle, [ncol][nz][ni]
+};
+__global__ void __launch_bounds__(128) steady_switch_kernel(SwitchArgs a)
+{
+    __shared__ double s_min;
+    __shared__ int s_lev;
+    const int col = blockIdx.x, tid = threadIdx.x, nz = a.nz, ni = a.ni;
+    SteadyDev &s = a.s;
+    if (!s.do_switch[col]) return;
+    const double *yc = a.y + (size_t)col * nz * ni, *n0 = a.n_0 + (size_t)col * nz;
+    for (int f = 0; f < s.n_fix; f++) {
+        const int i = s.fix_sp[f];
+        int top = nz;                                                  // fix_species_from_coldtrap_lev = False: the whole column
+        if (s.fix_from_coldtrap) {
+            if (s.fix_whole[f]) {
+                top = nz - 1;                                          // condensates (op.py:878-879)
+            } else {
+                if (tid == 0) {                                        // gas species: the level of the minimum saturation mixing ratio inside the
+                    const double *sm = s.fix_sat_mix + (size_t)f * nz; // region where it condenses (op.py:881-892)
+                    double best = 0.0; int have = 0, lev = 0;
+                    for (int j = 0; j < nz; j++)
+                        if (yc[(size_t)j * ni + i] >= n0[j] * sm[j] && (!have || sm[j] < best)) { best = sm[j]; have = 1; lev = j; }
+                    s_min = best; s_lev = have ? lev : 0;
+                }
+                __syncthreads();
+                top = s_lev;
+                __syncthreads();
+            }
+        }
+        for (int j = tid; j < nz; j += blockDim.x) {
+            const size_t q = ((size_t)col * nz + j) * ni + i;
+            a.fix_mask[q] = (j < top) ? 1 : 0;
+            a.fix_y[q] = (j < top) ? yc[(size_t)j * ni + i] : 0.0;
+        }
+    }
+    double *vs = const_cast<double *>(a.atm.vs) + col * a.atm.csn;     // atm.vs *= 0
+    for (int q = tid; q < (nz - 1) * ni; q += blockDim.x) vs[q] = 0.0 * vs[q];
+    if (tid == 0) { s.fix_started[col] = 1; s.rtol_col[col] = s.post_conden_rtol; }
+}
 
 struct PreArgs {
     int nz, ni;
@@ -228,6 +277,11 @@ int vk_ens_setup_steady(vk_column *c, const vk_steady_opts *o)
     s.pref_indx = o->pref_indx; s.gs = o->gs; s.Rp = o->Rp; s.max_flux = o->max_flux;
     s.hist_cap = o->hist_cap; s.hist_stride = o->hist_stride; s.cap_t = o->count_max + 2;
     s.n_diff_esc = o->n_diff_esc;
+    s.use_condense = o->use_condense; s.use_fix = o->fix_species_switch; s.fix_from_coldtrap = o->fix_from_coldtrap; s.n_fix = o->n_fix;
+    s.start_conden_time = o->start_conden_time; s.stop_conden_time = o->stop_conden_time; s.post_conden_rtol = o->post_conden_rtol;
+    if (s.use_condense && !c->conden) { set_error("use_condense needs vk_conden_setup"); return VK_ERR_INVALID; }
+    if (s.use_condense && s.use_fix && (!c->opts.fix_mask || !c->opts.fix_y)) { set_error("the fix_species switch writes the handle's fix_mask / fix_y: pass (zeroed) arrays to vk_set_step_opts"); return VK_ERR_INVALID; }
+    if (s.use_condense && c->atm.csn == 0 && c->ncol > 1) { set_error("the switch zeroes atm.vs per column: vk_set_atm with shared = 0"); return VK_ERR_INVALID; }
     int rc = VK_OK;
     s.ignore_sp = nullptr; s.diff_esc_idx = nullptr;
     if (o->conv_ignore_sp) rc = scopy(e, o->conv_ignore_sp, ni, &s.ignore_sp);
@@ -238,13 +292,19 @@ int vk_ens_setup_steady(vk_column *c, const vk_steady_opts *o)
     if (rc == VK_OK) rc = scopy(e, o->Hp, ncol * nz, &s.Hp);
     if (rc == VK_OK) rc = scopy(e, o->dz, ncol * nz, &s.dz);
     const double *nd = nullptr; const int *ni_ = nullptr;
+    s.fix_sp = nullptr; s.fix_whole = nullptr; s.fix_sat_mix = nullptr;
+    if (rc == VK_OK && s.n_fix > 0) rc = scopy(e, o->fix_sp, (size_t)s.n_fix, &s.fix_sp);
+    if (rc == VK_OK && s.n_fix > 0) rc = scopy(e, o->fix_whole_column, (size_t)s.n_fix, &s.fix_whole);
+    if (rc == VK_OK && s.n_fix > 0) rc = scopy(e, o->fix_sat_mix, (size_t)s.n_fix * nz, &s.fix_sat_mix);
+    if (rc == VK_OK) rc = scopy(e, nd, ncol, &s.dt_used);
+    if (rc == VK_OK) rc = scopy(e, nd, ncol, &s.rtol_col);
     if (rc == VK_OK) rc = scopy(e, nd, ncol * nz, &s.mu);
     if (rc == VK_OK) rc = scopy(e, nd, ncol, &s.longdy);
     if (rc == VK_OK) rc = scopy(e, nd, ncol, &s.longdydt);
     if (rc == VK_OK) rc = scopy(e, nd, ncol, &s.aflux_change);
     if (rc == VK_OK) rc = scopy(e, nd, ncol * (size_t)s.cap_t, &s.t_time);
     if (rc == VK_OK) rc = scopy(e, nd, ncol * (size_t)s.hist_cap * nz * ni, &s.hist);
-    int **ints[] = {&s.end_case, &s.act, &s.fresh, &s.do_photo, &s.do_mu, &s.photo_frq, &s.n_left};
+    int **ints[] = {&s.end_case, &s.act, &s.fresh, &s.do_photo, &s.do_mu, &s.photo_frq, &s.n_left, &s.fix_started, &s.do_conden, &s.do_switch};
     for (int **p : ints)
         if (rc == VK_OK) rc = scopy(e, ni_, ncol, p);
     if (rc != VK_OK) return rc;
@@ -255,6 +315,7 @@ int vk_ens_setup_steady(vk_column *c, const vk_steady_opts *o)
     fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, s.longdy, 1.0, s.act, 1);             // store.py:36-38: longdy = longdydt = 1
     fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, s.longdydt, 1.0, s.fresh, 1);
     fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, nullptr, 0.0, s.photo_frq, s.ini_frq > 0 ? s.ini_frq : 1);
+    fill_kernel<<<nb, 128, 0, c->stream>>>((int)ncol, s.rtol_col, e->rtol, nullptr, 0);
     VK_CUDA(cudaGetLastError());
     VK_CUDA(cudaStreamSynchronize(c->stream));
     e->steady_set = true;
@@ -306,6 +367,16 @@ int vk_ens_run_steady(vk_column *c, int max_iterations, int *n_active_left)
         if (rc == VK_OK) rc = launch_clip(c, c->sol, c->ymix_out, c->ymix_out, e->na, e->compo, nullptr, e->pos_cut, e->nega_cut, e->atom_sum,
                                           e->small_y, e->nega_y, e->anyneg);
         if (rc == VK_OK) rc = launch_ens_control(c);
+        if (rc == VK_OK && s.use_condense) {
+            // op.py:856-901 on the flagged columns: growth rates, then the switch (records the state BEFORE the relaxation operators), then relaxation
+            rc = conden_device(c, c->sol, c->ymix_out, s.dt_used, e->n_0, s.do_conden, nullptr, 1);
+            if (rc == VK_OK && s.use_fix) {
+                SwitchArgs sa{c->nz, c->ni, s, c->atm, c->sol, e->n_0, const_cast<unsigned char *>(c->opts.fix_mask), const_cast<double *>(c->opts.fix_y)};
+                steady_switch_kernel<<<c->ncol, 128, 0, c->stream>>>(sa);
+                rc = launch_atm_pre_pred(c, s.do_switch);
+            }
+            if (rc == VK_OK) rc = conden_device(c, c->sol, c->ymix_out, s.dt_used, e->n_0, s.do_conden, nullptr, 2);
+        }
         if (rc == VK_OK && s.update_frq > 0) {
             MuArgs ma{c->nz, c->ni, s, c->atm, c->ymix_out, c->sol};
             steady_mu_dz_kernel<<<c->ncol, 128, 0, c->stream>>>(ma);
@@ -343,6 +414,20 @@ int vk_ens_get_steady(vk_column *c, int *end_case, double *longdy, double *longd
     if (aflux_change) VK_CUDA(cudaMemcpy(aflux_change, s.aflux_change, sizeof(double) * ncol, cudaMemcpyDeviceToHost));
     if (dz) VK_CUDA(cudaMemcpy(dz, s.dz, sizeof(double) * ncol * c->nz, cudaMemcpyDeviceToHost));
     if (zco) VK_CUDA(cudaMemcpy(zco, s.zco, sizeof(double) * ncol * (c->nz + 1), cudaMemcpyDeviceToHost));
+    return VK_OK;
+}
+
+int vk_ens_get_fix(vk_column *c, int *fix_started, unsigned char *fix_mask, double *fix_y)
+{
+    if (!c || !c->ens || !c->ens->steady_set) { set_error("steady state driver not set up"); return VK_ERR_INVALID; }
+    VK_CUDA(cudaSetDevice(c->net->device));
+    SteadyDev &s = c->ens->steady;
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t ncol = c->ncol, per = (size_t)c->nz * c->ni;
+    if (fix_started) VK_CUDA(cudaMemcpy(fix_started, s.fix_started, sizeof(int) * ncol, cudaMemcpyDeviceToHost));
+    if ((fix_mask || fix_y) && (!c->opts.fix_mask || !c->opts.fix_y)) { set_error("no fix_mask / fix_y on this handle"); return VK_ERR_INVALID; }
+    if (fix_mask) VK_CUDA(cudaMemcpy(fix_mask, c->opts.fix_mask, ncol * per, cudaMemcpyDeviceToHost));
+    if (fix_y) VK_CUDA(cudaMemcpy(fix_y, c->opts.fix_y, sizeof(double) * ncol * per, cudaMemcpyDeviceToHost));
     return VK_OK;
 }
 

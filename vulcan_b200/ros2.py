@@ -151,9 +151,14 @@ class Ros2(object):
             self._k_cache = k
         self._k_ids = refs
 
-    def _sync_opts(self, var, atm, para, nz):
+    def _sync_opts(self, var, atm, para, nz, alloc_fix=False):
+        """alloc_fix: pass zeroed fix_mask / fix_y even before the fix_species switch - the device-resident loop (steady.py) writes
+        them itself when the switch happens on the device"""
         cfg, ni = self.cfg, self.ni
         fix_mask = fix_y = dz_sp = None
+        if alloc_fix:
+            fix_mask = np.zeros((nz, ni), dtype=np.uint8)
+            fix_y = np.zeros((nz, ni))
         if self._flag("use_condense"):
             dz_sp = np.zeros(ni, dtype=np.uint8)
             dz_sp[self.non_gas_sp_index] = 1
@@ -161,6 +166,7 @@ class Ros2(object):
             if para.fix_species_start:                                        # op.py:2896-2906, 2960-2970
                 fix_mask = np.zeros((nz, ni), dtype=np.uint8)
                 fix_y = np.zeros((nz, ni))
+                alloc_fix = False
                 for s in cfg.fix_species:
                     i = self.species.index(s)
                     top = nz if not cfg.fix_species_from_coldtrap_lev else int(atm.conden_min_lev[s])
@@ -185,11 +191,11 @@ class Ros2(object):
         key = (zero0, tuple(fbi), None if fbv is None else fbv.tobytes(), None if dz_sp is None else dz_sp.tobytes(),
                None if fix_mask is None else fix_mask.tobytes(), None if fix_y is None else fix_y.tobytes(), self.mtol, self.atol,
                self.refine, self.refine_dt_min)
-        if key != self._opts_key:
+        if key != self._opts_key or alloc_fix:
             self._columns(nz).set_step_opts(self.mtol, self.atol, refine=self.refine, zero_delta_row0=zero0, fix_bot_idx=fbi,
                                             fix_bot_val=fbv, delta_zero_sp=dz_sp, fix_mask=fix_mask, fix_y=fix_y, compo=self._compo,
                                             refine_dt_min=self.refine_dt_min)
-            self._opts_key = key
+            self._opts_key = None if alloc_fix else key      # the device loop changes the arrays behind this cache
 
     # ------------------------------------------------------------------ the Ros2 protocol
     def naming_solver(self, para):                                           # op.py:3078-3088

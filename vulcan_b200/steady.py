@@ -1,4 +1,5 @@
-"""Device-resident replacement of the reference's `op.Integration` loop (op.py:783-1105) for the configurations without condensation:
+"""Device-resident replacement of the reference's `op.Integration` loop (op.py:783-1105), condensation included (conden, the H2O / NH3
+relaxation operators and the fix_species switch, op.py:856-901):
 `DeviceIntegration(solver)(var, atm, para)` runs the whole time integration of ONE column on the GPU - attempted steps, accept / reject,
 step size, hydrostatic rescale, stop / conv against the stored history, the photolysis cadence, update_mu_dz / update_phi_esc - with one
 host round trip per `chunk` iterations instead of several per step, and writes the reference's containers back at the end
@@ -69,16 +70,19 @@ class DeviceIntegration(object):
     def __call__(self, var, atm, para, make_atm=None, max_wall_s=None):
         s = self.odesolver
         cfg = s.cfg
-        if getattr(cfg, "use_condense", False):
-            raise NotImplementedError("condensation / relaxation operators (op.py:1109-1421) run per accepted step on the host: use the "
-                                      "reference's op.Integration with the drop-in solver object for this configuration")
         if getattr(cfg, "use_ion", False) or getattr(cfg, "use_adapt_rtol", False):
             raise NotImplementedError("use_ion / use_adapt_rtol are not part of the device-resident loop")
+        if getattr(cfg, "use_fix_H2He", False) and "H2" not in cfg.use_fix_sp_bot:
+            raise NotImplementedError("use_fix_H2He changes the bottom boundary at t > 1e6 s on the host (op.py:2935-2941)")
+        condensing = bool(getattr(cfg, "use_condense", False)) and not para.fix_species_start
+        fix_species = list(getattr(cfg, "fix_species", []) or []) if condensing else []
+        if condensing and not set(fix_species) <= set(cfg.condense_sp) | set(cfg.non_gas_sp):
+            raise NotImplementedError("fix_species outside condense_sp / non_gas_sp changes delta_zero_sp at the switch")
         y = np.ascontiguousarray(var.y, dtype=np.float64)
         nz = y.shape[0]
         s._sync_atm(atm, nz)
         s._sync_k(var, nz)
-        s._sync_opts(var, atm, para, nz)
+        s._sync_opts(var, atm, para, nz, alloc_fix=bool(fix_species))
         use_photo = bool(getattr(cfg, "use_photo", False))
         if use_photo and not s._photo_ready:
             s._photo_setup(var, atm, nz)
@@ -92,8 +96,19 @@ class DeviceIntegration(object):
         for sp in getattr(cfg, "conver_ignore", []) or []:
             ignore[s.species.index(sp)] = 1
         ms = np.asarray(atm.ms, dtype=float) if getattr(cfg, "use_moldiff", True) else np.asarray(s._masses(), dtype=float)
+        condense = None
+        if condensing:
+            tabs = conden_tables(cfg, var, atm, s.species)
+            col.conden_setup(**tabs)
+            whole = [sp in ('H2O_l_s', 'H2SO4_l', 'NH3_l_s', 'S8_l_s') for sp in fix_species]                  # op.py:878
+            sat_mix = [np.zeros(nz) if w else np.asarray(atm.sat_mix[sp], dtype=float) for sp, w in zip(fix_species, whole)]
+            condense = dict(fix_sp=[s.species.index(sp) for sp in fix_species], fix_whole=whole, fix_sat_mix=np.array(sat_mix).reshape(len(fix_species), nz),
+                            from_coldtrap=bool(getattr(cfg, "fix_species_from_coldtrap_lev", False)),
+                            start_conden_time=tabs["start_conden_time"], stop_conden_time=tabs["stop_conden_time"],
+                            post_conden_rtol=tabs["post_conden_rtol"])
         col.ens_setup_steady(cfg, atm.pico, ms, atm.zco, atm.Hp, atm.dz, int(atm.pref_indx), float(atm.gs), conv_ignore_sp=ignore,
-                             diff_esc_idx=[s.species.index(sp) for sp in getattr(cfg, "diff_esc", []) or []], use_photo=use_photo)
+                             diff_esc_idx=[s.species.index(sp) for sp in getattr(cfg, "diff_esc", []) or []], use_photo=use_photo,
+                             condense=condense)
         t0 = time.time()
         left, it = 1, 0
         while left:
@@ -118,6 +133,19 @@ class DeviceIntegration(object):
         if left == 0:
             para.end_case = int(sd["end_case"][0])
         atm.dz, atm.zco = sd["dz"][0], sd["zco"][0]
+        if fix_species:
+            fx = col.ens_get_fix()
+            if fx["fix_started"][0]:                                                                          # op.py:866-892
+                para.fix_species_start = True
+                cfg.rtol = cfg.post_conden_rtol
+                atm.vs = atm.vs * 0
+                var.fix_y = {}
+                for sp in fix_species:
+                    i = s.species.index(sp)
+                    var.fix_y[sp] = fx["fix_y"][0][:, i].copy()
+                    if getattr(cfg, "fix_species_from_coldtrap_lev", False):
+                        atm.conden_min_lev[sp] = int(fx["fix_mask"][0][:, i].sum())
+        s._opts_key = None
         for q, a in enumerate(atoms):
             var.atom_sum[a] = float(np.sum(s._compo[:, q][None, :] * var.y))
             var.atom_loss[a] = (var.atom_sum[a] - var.atom_ini[a]) / var.atom_ini[a]
