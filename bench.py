@@ -378,7 +378,9 @@ def main():
         lib = runner.col.lib
         lib.vk_debug_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         lib.vk_debug_time_kernel.restype = ctypes.c_int
-        for which, name in ((0, "lhs_ml_kernel"), (1, "rhs_warp_kernel"), (4, "lu_solve_kernel (forward + backward)")):
+        for which, name in ((0, "lhs_ml_kernel"), (1, "rhs_warp_kernel"), (6, "emitted chemdf kernel (part of the rhs line)"),
+                            (3, "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)"),
+                            (4, "lu_solve_kernel (forward + backward)")):
             msk = ctypes.c_float(0)
             if lib.vk_debug_time_kernel(runner.col.handle, which, 3, ctypes.byref(msk)) == 0 and msk.value > 0:
                 kernel_ms[name] = float(msk.value)
@@ -460,6 +462,8 @@ def main():
             nip = ((ni + 23) // 24) * 24 if ni > 48 else 48          # padded block size the kernels are instantiated for (48 / 72 / 96 / 120)
             alg = {"lhs_ml_kernel": nz * nip * nip * 8.0 + nz * ni * 8.0,                        # writes D (+ up, dn), reads y; k is shared (L2)
                    "rhs_warp_kernel": 2.0 * nz * ni * 8.0,                                       # reads y, writes f; k is shared (L2)
+                   "emitted chemdf kernel (part of the rhs line)": 2.0 * nz * ni * 8.0,          # reads y, writes chemdf; k is shared (L2)
+                   "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)": 1.0 * nz * nip * (nip + 2) * 8.0,
                    "lu_solve_kernel (forward + backward)": 2.0 * nz * nip * (nip + 2) * 8.0}     # reads the factors F_j once per sweep
             line["hbm_kernels"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src, "kernels": [
                 {"kernel": name, "ms": msv, "algorithmic_bytes_per_column": alg[name], "achieved_gbs": alg[name] * ncol / (msv * 1e-3) / 1e9,

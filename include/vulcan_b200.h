@@ -133,8 +133,11 @@ typedef struct {
     /* ABI 3 */
     int na; const double *compo;     /* [ni][na] atoms per species (build_atm.py:18-25, thermo/all_compose.txt) or NULL */
     double refine_dt_min;            /* refine = -1: step size (s) from which a column is refined */
-    int rhs_order;                   /* summation of the production / loss terms of chemdf (chem_funs.py:931): 0 = segmented (32 partial chains
-                                      * per layer, default), 1 = the reference's left-to-right order, bit-identical to the generated chemdf */
+    int rhs_order;                   /* chemdf (chem_funs.py:931): 0 (default) = the fastest kernel this library has for the network: the EMITTED
+                                      * straight-line kernel (vulcan_b200/emit.py; reference summation order, bit-identical to the generated
+                                      * chemdf) when one is compiled in, else the table-driven kernel with the segmented summation (32 partial
+                                      * chains per layer); 1 = reference order (emitted, else table-driven left-to-right); 2 = table-driven,
+                                      * reference order; 3 = table-driven, segmented */
 } vk_step_opts;
 int vk_set_step_opts(vk_column *col, const vk_step_opts *opts);
 

@@ -91,8 +91,12 @@ def test_condensing_config_device_loop_matches_host_loop(tag, edit, count_max):
             top = int(a1.conden_min_lev[s])
             f1, f2 = np.asarray(v1.fix_y[s])[:top], np.asarray(v2.fix_y[s])[:top]
             assert np.allclose(f2, f1, rtol=1e-6, atol=1e-300), s
-            # frozen rows are held at the recorded value through the remaining steps (op.py:2960-2970)
-            assert np.array_equal(v2.y[:top, sp.index(s)], f2), s
+            # frozen rows are held at the recorded value through the remaining steps (op.py:2960-2970); the gas species are then
+            # rescaled with the layer's hydrostatic density like every other gas (op.py:909-914), the condensates stay exact
+            if s.endswith("_l_s"):
+                assert np.array_equal(v2.y[:top, sp.index(s)], f2), s
+            else:
+                assert np.allclose(v2.y[:top, sp.index(s)], f2, rtol=1e-2), s
         assert not np.asarray(a2.vs).any()
 
 
@@ -120,3 +124,38 @@ def test_jupiter_device_loop_through_the_switch_vs_the_reference():
         top = int(fx["conden_min_lev"][q])
         assert np.allclose(np.asarray(v.fix_y[s])[:top], fx["fix_y"][q][:top], rtol=1e-6, atol=1e-300), s
     assert not np.asarray(a.vs).any()
+
+
+def test_ensemble_columns_against_reference_runs():
+    """eight sampled columns of the synthetic sweep (Kzz x 0.1 ... 10, metallicity x 0.3 ... 3, C/O 0.3 ... 1.0), each run
+    to ITS OWN steady state by the unmodified reference (oracle/ensemble_reference.py -> tests/golden/HD189_ens8_reference.npz: op.Integration
+    + op.Ros2 on the re-weighted state, 520 ... 850 s per column on one host core), against the same eight columns converged as ONE
+    device-resident batch.  Both sides stop at the reference's default rule (yconv_cri = 0.01: the state still moves by up to a percent per
+    look-back window when the run stops, and two hash seeds of the reference itself differ by that much), so the bound is the
+    percent level of that rule, not rounding."""
+    import os
+    path = os.path.join(GOLD, "HD189_ens8_reference.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture missing")
+    from vulcan_b200 import ensemble
+    ref = dict(np.load(path))
+    kz, met, co = ref["params"].T
+    c = Case("HD189", 0)
+    y, atom_ini = ensemble.synthetic_columns(c.st["y_ini"], c.st["n_0"], c.st["compo"], c.cfg["atom_list"], kz, met, co)
+    assert np.allclose(y, ref["y_ini"], rtol=1e-13, atol=0)              # the reference runs started from the same columns
+    runner = steady_ensemble_from_fixture(c, y, atom_ini, kz)
+    out = runner.run_to_steady_state(max_iterations=8000)
+    ymix = out["y"] / out["y"].sum(axis=2, keepdims=True)
+    worst4 = worst8 = 0.0
+    for q in range(len(kz)):
+        yr = ref["ymix"][q]
+        rel = np.abs(ymix[q] - yr) / np.maximum(yr, 1e-300)
+        r4, r8, med = rel[yr > 1e-4].max(), rel[yr > 1e-8].max(), np.median(rel[yr > 1e-20])
+        worst4, worst8 = max(worst4, r4), max(worst8, r8)
+        print("column %d (Kzz x %4.1f, metallicity x %3.1f, C/O %.2f): device %4d steps t %.3e end_case %d | reference %4d steps t %.3e | "
+              "ymix > 1e-4 %.2e, > 1e-8 %.2e, median(> 1e-20) %.2e" % (q, kz[q], met[q], co[q], out["n_accept"][q], out["t"][q], out["end_case"][q],
+                                                                      ref["count"][q], ref["t"][q], r4, r8, med))
+    print("eight columns as one batch: %.1f s on the device; the reference needed %.0f s of host time (sum over columns)" % (
+        out["wall_s"], float(ref["wall_s"].sum())))
+    assert (out["end_case"] == 1).all() and (ref["end_case"] == 1).all()
+    assert worst4 < 2e-2 and worst8 < 1e-1

@@ -36,21 +36,34 @@ def case(request):
     return c
 
 
-def test_rhs_bit_exact(case):
-    """chemdf + diffdf: bit-identical to the oracle AND to the reference fixture (make_chem_funs.py:113-430, op.py:1496-1597) with
-    rhs_order = 1, the reference's left-to-right summation order (the default is the segmented order, next test)."""
-    chem, diff = _columns(case, rhs_order=1).eval_rhs(case.y)
+@pytest.mark.parametrize("rhs_order", [1, 2])
+def test_rhs_bit_exact(case, rhs_order):
+    """chemdf + diffdf: bit-identical to the oracle AND to the reference fixture (make_chem_funs.py:113-430, op.py:1496-1597) in the
+    reference's left-to-right summation order: rhs_order = 1 -> the EMITTED straight-line kernel of the network where the library has one
+    (vulcan_b200/emit.py), 2 -> the table-driven kernel."""
+    chem, diff = _columns(case, rhs_order=rhs_order).eval_rhs(case.y)
     assert np.array_equal(chem[0], case.oracle.chemdf(case.y, case.st["M"], case.k))
     assert np.array_equal(chem[0], case.fx["chemdf"])
     assert np.array_equal(diff[0], case.oracle.diffdf(case.atm, case.y))
     assert np.array_equal(diff[0], case.fx["diffdf"])
 
 
+def test_rhs_default_kernel(case):
+    """rhs_order = 0 on ONE column (what the drop-in call runs): the table-driven kernel with the segmented summation - diffdf bit-identical,
+    chemdf within the rounding of a few partial sums of the reference (quantified against an 80-bit sum in the next test).  Batches that share
+    their rate coefficients take the EMITTED kernel instead, which is bit-identical: test_rhs_emitted_batch."""
+    chem, diff = case.col.eval_rhs(case.y)
+    assert np.array_equal(diff[0], case.fx["diffdf"])
+    scale = np.abs(case.fx["chemdf"]).max(axis=1, keepdims=True) + 1e-300
+    assert np.max(np.abs(chem[0] - case.fx["chemdf"]) / scale) < 1e-9
+
+
 def test_rhs_segmented_order(case):
-    """The default summation order of chemdf on the device (32 partial chains per layer, vk_chem.cu) against the reference order and against
+    """The segmented summation order of the table-driven chemdf kernel (32 partial chains per layer, vk_chem.cu; the default for networks
+    without an emitted kernel) against the reference order and against
     an extended-precision sum of the same terms: per species the difference to the 80-bit sum must be at rounding level of the LARGEST term
     sum (sum |terms|) - for both orders - and diffdf is untouched (bit-identical)."""
-    chem_f, diff_f = case.col.eval_rhs(case.y)
+    chem_f, diff_f = _columns(case, rhs_order=3).eval_rhs(case.y)
     chem_r = case.fx["chemdf"]
     assert np.array_equal(diff_f[0], case.fx["diffdf"])
     t = case.net.tables()
@@ -228,6 +241,39 @@ def test_batched_columns_identical():
     s4, mm4, d4, st4 = col4.ros2_solve(y4, m4, np.full(4, c.dt))
     for i in range(4):
         assert np.array_equal(s4[i], s1[0]) and np.array_equal(mm4[i], m1[0]) and d4[i] == d1[0] and st4[i] == 0
+
+
+EMIT_CASES = [p for p in [("HD189", 100), ("Jupiter", 30), ("Earth", 30), ("HD209S", 30), ("EarthS", 100), ("HD189vm", 30), ("JupiterVmVz", 30),
+                          ("HD189nomol", 30)] if have(p[0], "step%04d.npz" % p[1])]
+
+
+@pytest.mark.parametrize("tag,step", EMIT_CASES, ids=[case_id(p) for p in EMIT_CASES])
+def test_rhs_emitted_batch(tag, step):
+    """the emitted chemdf kernel + elementwise stencil kernels (vk_emit.cu, rhs_stencil_kernel: batches >= 32 columns that share their rate
+    coefficients - the BASELINE ensemble) on a batch of 40 DISTINCT columns (a partial block of 128): chemdf and diffdf of every sampled
+    column bit-identical to the oracle restatement of the reference, and a whole attempted step bit-identical to the table-driven path."""
+    from vulcan_b200 import emit
+    from oracle import Oracle
+    c = Case(tag, step)
+    c.oracle = Oracle(c.net)
+    c.atm = c.oracle.make_atm(**c.atm_kwargs())
+    assert emit.has_kernel(c.net)
+    ncol = 40
+    rng = np.random.default_rng(7)
+    y = c.y[None] * (1.0 + 0.3 * rng.uniform(-1.0, 1.0, size=(ncol,) + c.y.shape))
+    y[0] = c.y
+    col = _columns(c, ncol)
+    chem, diff = col.eval_rhs(y)
+    assert np.array_equal(chem[0], c.fx["chemdf"]) and np.array_equal(diff[0], c.fx["diffdf"])
+    for q in (1, 17, 39):
+        assert np.array_equal(chem[q], c.oracle.chemdf(y[q], c.st["M"], c.k)), q
+        assert np.array_equal(diff[q], c.oracle.diffdf(c.atm, y[q])), q
+    tab = _columns(c, ncol, rhs_order=2)                     # table-driven kernels, reference order
+    ymix = y / y.sum(axis=2, keepdims=True)
+    dt = np.full(ncol, min(c.dt, 1e2))
+    s1, m1, d1, st1 = col.ros2_solve(y, ymix, dt)
+    s2, m2, d2, st2 = tab.ros2_solve(y, ymix, dt)
+    assert np.array_equal(s1, s2) and np.array_equal(m1, m2) and np.array_equal(d1, d2) and np.array_equal(st1, st2)
 
 
 @pytest.mark.parametrize("tag,step", PHOTO_CASES, ids=[case_id(p) for p in PHOTO_CASES])

@@ -333,8 +333,10 @@ class Columns(object):
     def set_step_opts(self, mtol, atol, refine=0, zero_delta_row0=False, fix_bot_idx=(), fix_bot_val=None,
                       delta_zero_sp=None, fix_mask=None, fix_y=None, compo=None, refine_dt_min=REFINE_DT_MIN, rhs_order=0):
         """refine: passes of iterative refinement per solve (double-double residual); -1 = auto: one safeguarded pass on the columns
-        whose dt >= refine_dt_min (needs compo [ni, na]).  rhs_order: 0 = segmented summation of the production / loss terms (default),
-        1 = the reference's left-to-right order (chemdf bit-identical to the generated chem_funs.py)."""
+        whose dt >= refine_dt_min (needs compo [ni, na]).  rhs_order (chemdf): 0 (default) = the emitted straight-line kernel of the network
+        when the library has one (vulcan_b200/emit.py; reference order, bit-identical to the generated chem_funs.py), else the table-driven
+        kernel with the segmented summation; 1 = reference order (emitted, else table-driven); 2 = table-driven reference order; 3 =
+        table-driven segmented."""
         fbi = i32(fix_bot_idx)
         fbv = None if len(fbi) == 0 else f64(fix_bot_val).reshape(self.ncol, len(fbi))
         dz = None if delta_zero_sp is None else u8(delta_zero_sp)

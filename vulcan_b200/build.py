@@ -14,7 +14,8 @@ LIB = os.path.join(LIBDIR, "libvulcan_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = {"vk_api.cu": [], "vk_chem.cu": ["-fmad=false"], "vk_step.cu": ["-fmad=false"], "vk_photo.cu": ["-fmad=false"],
-         "vk_solve.cu": [], "vk_ens.cu": ["-fmad=false"], "vk_steady.cu": ["-fmad=false"], "vk_conden.cu": ["-fmad=false"], "vk_rates.cu": ["-fmad=false"]}
+         "vk_solve.cu": [], "vk_ens.cu": ["-fmad=false"], "vk_steady.cu": ["-fmad=false"], "vk_conden.cu": ["-fmad=false"], "vk_rates.cu": ["-fmad=false"],
+         "vk_emit.cu": []}
 
 
 def _newer(target, deps):
@@ -33,9 +34,14 @@ def build(force=False, verbose=False, variant=None, solve_flags=()):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "vulcan_b200.h"))
     objs, procs = [], []
-    for src, extra in UNITS.items():
+    units = dict(UNITS)
+    # emitted chemistry kernels: one generated unit per registered network (vulcan_b200/emit.py, networks/*.npz -> csrc/gen/*.cu)
+    from . import emit
+    for g in emit.generate_all(verbose=verbose):
+        units[os.path.join("gen", os.path.basename(g))] = ["-fmad=false"]
+    for src, extra in units.items():
         s = os.path.join(CSRC, src)
-        o = os.path.join(LIBDIR, src.replace(".cu", ".o"))
+        o = os.path.join(LIBDIR, os.path.basename(src).replace(".cu", ".o"))
         if variant and src == "vk_solve.cu":
             o = os.path.join(LIBDIR, "vk_solve_%s.o" % variant)
             extra = list(extra) + list(solve_flags)

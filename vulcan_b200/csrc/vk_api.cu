@@ -79,11 +79,11 @@ int vk_step_device_impl(vk_column *c)
     if (rc == VK_ERR_UNSUPPORTED) {
         if ((rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn))) return rc;
         VK_CUDA(cudaEventRecord(c->ev1, c->stream));
-        rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
-    }
+        rc = launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f);       // (+ forward elimination of the k1 solve at small dt)
+    } else c->fwd_valid = 0;
     if (rc) return rc;
     VK_CUDA(cudaEventRecord(c->ev2, c->stream));
-    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act))) return rc;           // k1                op.py:2914
+    if ((rc = launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act, c->fwd_valid ? c->fwd_done : nullptr))) return rc;           // k1                op.py:2914
     if ((rc = launch_refine(c, c->D, c->up, c->dn, c->W, c->f, c->k1, c->opts.refine, c->dt))) return rc;
     if ((rc = launch_rhs(c, c->y, c->rhs, nullptr, nullptr, c->k1, c->dt))) return rc;            // f(y+k1/r) - 2/(rh) k1   op.py:2917-2928
     if ((rc = launch_solve(c, c->W, c->up, c->dn, c->rhs, c->k2, c->z, c->act))) return rc;         // k2                op.py:2929
@@ -121,6 +121,10 @@ int vk_network_create(const vk_network_desc *d, int device, vk_network **out)
     vk_network *n = new vk_network();
     n->device = device;
     n->rates = nullptr;
+    n->table_hash = network_table_hash(d);
+    n->emit = emit_lookup(n->table_hash, d->ni, d->nr);
+    if (getenv("VK_DEBUG")) fprintf(stderr, "vulcan_b200: network ni %d nr %d table hash %016llx: %s\n", d->ni, d->nr, n->table_hash,
+                                    n->emit ? "emitted chemdf kernel" : "table-driven chemdf");
     const int ni = d->ni, nr = d->nr;
     std::vector<uchar4> rf(nr + 1), rp(nr + 1);
     int has_pow = 0;
@@ -355,9 +359,9 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dt, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->delta, sizeof(double) * ncol);
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->status, sizeof(int) * ncol);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->refine_kept, sizeof(int) * 3 * ncol);
-    if (e == cudaSuccess) e = cudaMemset(c->refine_kept, 0, sizeof(int) * 3 * ncol);
-    if (e == cudaSuccess) { c->refine_tried = c->refine_kept + ncol; c->refine_act = c->refine_kept + 2 * ncol; }
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->refine_kept, sizeof(int) * 4 * ncol);
+    if (e == cudaSuccess) e = cudaMemset(c->refine_kept, 0, sizeof(int) * 4 * ncol);
+    if (e == cudaSuccess) { c->refine_tried = c->refine_kept + ncol; c->refine_act = c->refine_kept + 2 * ncol; c->fwd_done = c->refine_kept + 3 * ncol; }
     c->h_pin_bytes = sizeof(double) * (4 * nv + 4 * (size_t)ncol) + 64;
     if (e == cudaSuccess) e = cudaMallocHost((void **)&c->h_pin, c->h_pin_bytes);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();      // the memset above is on the legacy stream, the handle's stream is non-blocking
@@ -386,7 +390,7 @@ void vk_column_destroy(vk_column *c)
     cr_plan_free(c->cr);
     if (c->refine_kept) cudaFree(c->refine_kept);
     double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->xn, c->z, c->up, c->dn,
-                      c->D, c->W, c->dt, c->delta, c->k};
+                      c->D, c->W, c->dt, c->delta, c->k, c->chem_tmp, c->ysum_tmp, static_cast<double *>(c->scal_tmp)};
     for (double *v : vecs) if (v) cudaFree(v);
     if (c->status) cudaFree(c->status);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -815,7 +819,9 @@ int vk_stream(vk_column *c, void **cuda_stream)
 }  // extern "C"
 
 // profiling aid (declared in the public header): time `reps` launches of one kernel of the step on the resident state.
-// which: 0 = lhs, 1 = rhs (stage 1), 2 = factor, 3 = solve (backward only), 4 = solve (forward + backward)
+// which: 0 = lhs, 1 = rhs (stage 1), 2 = factor (+ the fused forward elimination of the first solve where dt allows, as in the step),
+// 3 = first solve of the step (backward sweep only for the columns whose forward elimination the factorisation did), 4 = solve (forward +
+// backward), 5 = fused assembly + factorisation, 6 = the emitted chemdf kernel alone
 extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms)
 {
     if (!c || !ms || reps < 1) return VK_ERR_INVALID;
@@ -829,8 +835,14 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
     for (int r = 0; r < reps && rc == VK_OK; r++) {
         if (which == 0) rc = vk::launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
         else if (which == 1) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);
-        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status);
+        else if (which == 2) rc = vk::launch_factor(c, c->D, c->up, c->dn, c->W, c->status, c->f);
         else if (which == 5) rc = vk::launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, 0);
+        else if (which == 6) {
+            if (!c->chem_tmp) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);      // allocates the scratch of the emitted path
+            if (rc == VK_OK && !c->chem_tmp) { set_error("this handle does not take the emitted chemistry path"); rc = VK_ERR_UNSUPPORTED; }
+            if (rc == VK_OK) rc = vk::launch_chem_emitted(c, c->y, nullptr, c->chem_tmp, c->ysum_tmp, nullptr);
+        }
+        else if (which == 3) rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act, c->fwd_valid ? c->fwd_done : nullptr);
         else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);
     }
     VK_CUDA(cudaEventRecord(b, c->stream));

@@ -266,7 +266,87 @@ struct RhsArgs {
     const unsigned char *fix_mask;          // rows forced to zero (op.py:2896-2925)
     const int *act;                         // [ncol] or NULL: stopped columns are skipped
     int fast;                               // segmented summation of the production / loss terms instead of the reference's order
+    const double *chem_in;                  // chemdf already evaluated by the emitted kernel of this network (vk_emit.cu): only the transport
+                                            // stencil, the combine and the outputs are left to this kernel
 };
+
+// transport part of dy/dt of species i at layer j of column col (ODESolver.diffdf / diffdf_settling / diffdf_no_mol / *_vm, op.py:1438-1898),
+// expression by expression in the reference's order; s: the layer scalars, y0v / ymv / ypv: y_i at layers j, j-1, j+1
+__device__ __forceinline__ double stencil_diff(const AtmDev &atm, const AtmLayer &L, const LayerScal &s, int nz, int ni, int col, int j, int i,
+                                               double y0v, double ymv, double ypv)
+{
+    const int md = atm.use_moldiff, st = atm.use_settling && atm.use_moldiff;
+    const int vmm = atm.use_vm_mol;
+    const double *dzi = L.dzi;
+    const AtmPre &P = atm.pre;
+    const size_t pb = ((size_t)col * atm.pre_cs + (size_t)j * ni) + i;
+    double diff;
+    if (j == 0) {
+        if (md) {
+            double Ai = P.QC[pb] * s.sp / 2. / s.ys0;
+            double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+            if (vmm) {
+                double Cx = 0.0;
+                vm_rhs_adv(P, pb, 0, st, Ai, Bi, Cx);
+            } else {
+                Ai = Ai + P.TA[pb];
+                Bi = Bi + P.TB[pb];
+                if (st) {
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
+                }
+            }
+            diff = (s.Aa + Ai) * y0v + (s.Bb + Bi) * ypv;
+        } else {
+            diff = s.Aa * y0v + s.Bb * ypv;
+        }
+        if (atm.use_botflux) diff += (L.bot_flux[i] - y0v * L.bot_vdep[i]) / dzi[0];
+    } else if (j == nz - 1) {
+        if (md) {
+            double Ai = P.QB[pb] * s.sm / 2. / s.ys0;
+            double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
+            if (vmm) {
+                double Bx = 0.0;
+                vm_rhs_adv(P, pb, 2, st, Ai, Bx, Ci);
+            } else {
+                Ai = Ai - P.TA[pb];
+                Ci = Ci - P.TC[pb];
+                if (st) {
+                    Ai = Ai + P.SA[pb];
+                    Ci = Ci + P.SC[pb];
+                }
+            }
+            diff = (s.Aa + Ai) * y0v + (s.Cc + Ci) * ymv;
+        } else {
+            diff = s.Aa * y0v + s.Cc * ymv;
+        }
+        if (atm.use_topflux) diff += L.top_flux[i] / dzi[nz - 2];
+    } else {
+        double t1 = s.Aa * y0v + s.Bb * ypv + s.Cc * ymv;
+        if (md) {
+            double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
+            double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
+            double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
+            if (vmm) {
+                vm_rhs_adv(P, pb, 1, st, Ai, Bi, Ci);
+            } else {
+                if (st) {
+                    Ai = Ai - P.SA[pb];
+                    Bi = Bi - P.SB[pb];
+                    Ci = Ci + P.SC[pb];
+                }
+                Ai += P.TA[pb];
+                Bi += P.TB[pb];
+                Ci += -P.TC[pb];
+            }
+            double t2 = Ai * y0v + Bi * ypv + Ci * ymv;
+            diff = t1 + t2;
+        } else {
+            diff = t1;
+        }
+    }
+    return diff;
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // rhs_warp_kernel: ONE WARP per (column, layer), RHS_WPB layers per block, no block-wide barrier after the tables are staged.
@@ -303,10 +383,13 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
     // block-shared tables: rate factors [nr+1] (uchar4), 16-bit descriptors [n_rhs] (reference order) or [32 T] (segmented, transposed)
     uchar4 *rfac = reinterpret_cast<uchar4 *>(sm + (size_t)RHS_WPB * SL.total);
     unsigned short *td = reinterpret_cast<unsigned short *>(rfac + (nr + 2));
-    for (int i = tid; i <= nr; i += blockDim.x) rfac[i] = A.net.rate_fac[i];
-    if (fast) { for (int i = tid; i < 32 * A.net.rhs_flat_T; i += blockDim.x) td[i] = A.net.rhs_flat16[i]; }
-    else if (A.net.rhs_unit) for (int i = tid; i < A.net.n_rhs; i += blockDim.x) td[i] = A.net.rhs_desc16[i];
-    __syncthreads();
+    const bool have_chem = A.chem_in != nullptr;
+    if (!have_chem) {
+        for (int i = tid; i <= nr; i += blockDim.x) rfac[i] = A.net.rate_fac[i];
+        if (fast) { for (int i = tid; i < 32 * A.net.rhs_flat_T; i += blockDim.x) td[i] = A.net.rhs_flat16[i]; }
+        else if (A.net.rhs_unit) for (int i = tid; i < A.net.n_rhs; i += blockDim.x) td[i] = A.net.rhs_desc16[i];
+        __syncthreads();
+    }
 
     const int lay = blockIdx.x * RHS_WPB + w;
     if (lay >= n_layers_total) return;
@@ -336,7 +419,7 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
 
     // ---- pair rates v_p = rate[2p+1] - rate[2p+2], rate[i] = k[i]*f0*f1*f2*f3 in written order (padding slots multiply by 1.0)
     const double *kg = A.k + col * A.k_cs + (size_t)j * (nr + 1);
-    for (int p = lane; p < npair; p += 32) {
+    for (int p = lane; p < (have_chem ? 0 : npair); p += 32) {
         double r2[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -405,7 +488,7 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
     // are added in order.  Differs from the reference's left-to-right sum by the rounding of those few partial sums (checked against an
     // extended-precision sum, tests/test_gpu_parity.py::test_rhs_segmented_order); the warp no longer waits for its longest chain (H:
     // 170 dependent adds while 31 lanes idle) - 420 instead of 2450 issue slots per layer for NCHO.
-    if (fast) {
+    if (fast && !have_chem) {
         double *part = ws + SL.part;
         if (lane == 0) v[npair] = 0.0;
         __syncwarp();
@@ -428,7 +511,7 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
     }
     // ---- chemistry, reference order: left-to-right sum of coef * v_p per species in network order (make_chem_funs.py:258-285)
     const int *my_sp = A.net.rhs_lane_sp + lane * VK_RHS_SPL;
-    for (int slot = 0; slot < (fast ? 0 : VK_RHS_SPL); slot++) {
+    for (int slot = 0; slot < ((fast || have_chem) ? 0 : VK_RHS_SPL); slot++) {
         const int s = my_sp[slot];
         if (s < 0) break;
         const int q0 = A.net.rhs_ptr[s], q1 = A.net.rhs_ptr[s + 1];
@@ -460,76 +543,9 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
 
     // ---- transport stencil + output, species i = lane, lane + 32, ...
     const LayerScal s = *S;
-    const double *dzi = L.dzi;
-    const AtmPre &P = A.atm.pre;
     for (int i = lane; i < ni; i += 32) {
-        const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
-        double diff;
-        if (j == 0) {
-            if (md) {
-                double Ai = P.QC[pb] * s.sp / 2. / s.ys0;
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
-                if (vmm) {
-                    double Cx = 0.0;
-                    vm_rhs_adv(P, pb, 0, st, Ai, Bi, Cx);
-                } else {
-                    Ai = Ai + P.TA[pb];
-                    Bi = Bi + P.TB[pb];
-                    if (st) {
-                        Ai = Ai - P.SA[pb];
-                        Bi = Bi - P.SB[pb];
-                    }
-                }
-                diff = (s.Aa + Ai) * y0[i] + (s.Bb + Bi) * yp[i];
-            } else {
-                diff = s.Aa * y0[i] + s.Bb * yp[i];
-            }
-            if (A.atm.use_botflux) diff += (L.bot_flux[i] - y0[i] * L.bot_vdep[i]) / dzi[0];
-        } else if (j == nz - 1) {
-            if (md) {
-                double Ai = P.QB[pb] * s.sm / 2. / s.ys0;
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (vmm) {
-                    double Bx = 0.0;
-                    vm_rhs_adv(P, pb, 2, st, Ai, Bx, Ci);
-                } else {
-                    Ai = Ai - P.TA[pb];
-                    Ci = Ci - P.TC[pb];
-                    if (st) {
-                        Ai = Ai + P.SA[pb];
-                        Ci = Ci + P.SC[pb];
-                    }
-                }
-                diff = (s.Aa + Ai) * y0[i] + (s.Cc + Ci) * ym[i];
-            } else {
-                diff = s.Aa * y0[i] + s.Cc * ym[i];
-            }
-            if (A.atm.use_topflux) diff += L.top_flux[i] / dzi[nz - 2];
-        } else {
-            double t1 = s.Aa * y0[i] + s.Bb * yp[i] + s.Cc * ym[i];
-            if (md) {
-                double Ai = s.m1 * (P.Q[pb] * s.sp / 2. + P.Q[pb - ni] * s.sm / 2.) / s.ys0;
-                double Bi = P.QB[pb] * s.sp / 2. / s.ysp;
-                double Ci = P.QC[pb] * s.sm / 2. / s.ysm;
-                if (vmm) {
-                    vm_rhs_adv(P, pb, 1, st, Ai, Bi, Ci);
-                } else {
-                    if (st) {
-                        Ai = Ai - P.SA[pb];
-                        Bi = Bi - P.SB[pb];
-                        Ci = Ci + P.SC[pb];
-                    }
-                    Ai += P.TA[pb];
-                    Bi += P.TB[pb];
-                    Ci += -P.TC[pb];
-                }
-                double t2 = Ai * y0[i] + Bi * yp[i] + Ci * ym[i];
-                diff = t1 + t2;
-            } else {
-                diff = t1;
-            }
-        }
-        const double chem = chem_s[i];
+        const double diff = stencil_diff(A.atm, L, s, nz, ni, col, j, i, y0[i], ym[i], yp[i]);
+        const double chem = have_chem ? A.chem_in[base + i] : chem_s[i];
         if (A.out_chem) A.out_chem[base + i] = chem;
         if (A.out_diff) A.out_diff[base + i] = diff;
         if (A.out_sum) {
@@ -541,6 +557,76 @@ __global__ void __launch_bounds__(RHS_WPB * 32) rhs_warp_kernel(RhsArgs A, int n
             }
             A.out_sum[base + i] = f;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The right-hand side behind an EMITTED chemdf kernel (vk_emit.cu): chemdf and the layer sums of y are already in HBM, what is left is
+// elementwise.  layer_scal_kernel: one thread per (column, layer) forms the eddy / advection coefficients of the layer (the scalars lanes
+// 0-2 of rhs_warp_kernel form); rhs_stencil_kernel: one thread per (column, layer, species) adds the transport stencil, applies the stage-2
+// combine and the fixed-row mask - same expressions, same order, bit-identical to rhs_warp_kernel.
+struct StencilArgs {
+    AtmDev atm;
+    int nz, ni, ncol;
+    const double *y;        // y (stage 1) or y + k1/r (stage 2, written by the emitted kernel)
+    const double *k1, *dt;  // stage 2 combine
+    const double *chem, *ysum;
+    LayerScal *S;           // [ncol][nz]
+    double *out_sum, *out_chem, *out_diff;
+    const unsigned char *fix_mask;
+    const int *act;
+};
+__global__ void __launch_bounds__(128) layer_scal_kernel(StencilArgs A)
+{
+    const int lay = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nz = A.nz;
+    if (lay >= A.ncol * nz) return;
+    const int col = lay / nz, j = lay - col * nz;
+    if (A.act && !A.act[col]) return;
+    const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+    const double ys0 = A.ysum[lay], ysm = (j > 0) ? A.ysum[lay - 1] : 0.0, ysp = (j < nz - 1) ? A.ysum[lay + 1] : 0.0;
+    const double sp = ysp + ys0, smm = ys0 + ysm;
+    LayerScal S;
+    double x;
+    if (j == 0) x = ls[0] * sp / 2. / ys0;
+    else if (j == nz - 1) x = ls[0] * smm / 2. / ys0;
+    else x = ls[0] * (ls[1] * sp / 2. + ls[2] * smm / 2.) / ys0;
+    x += ls[5];
+    S.Aa = x; S.m1 = ls[8]; S.sp = sp; S.sm = smm; S.ys0 = ys0; S.ysp = ysp; S.ysm = ysm;
+    x = 0.0;
+    if (j < nz - 1) { x = ls[3] * sp / 2. / ysp; x += ls[6]; }
+    S.Bb = x;
+    x = 0.0;
+    if (j > 0) { x = ls[4] * smm / 2. / ysm; x += ls[7]; }
+    S.Cc = x;
+    A.S[lay] = S;
+}
+__global__ void __launch_bounds__(256) rhs_stencil_kernel(StencilArgs A)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ni = A.ni, nz = A.nz;
+    if (e >= (size_t)A.ncol * nz * ni) return;
+    const int lay = (int)(e / ni), i = (int)(e - (size_t)lay * ni);
+    const int col = lay / nz, j = lay - col * nz;
+    if (A.act && !A.act[col]) return;
+    const AtmLayer L = atm_at(A.atm, col);
+    const LayerScal s = A.S[lay];
+    const double y0v = A.y[e];
+    const double ymv = (j > 0) ? A.y[e - ni] : 0.0;
+    const double ypv = (j < nz - 1) ? A.y[e + ni] : 0.0;
+    const double diff = stencil_diff(A.atm, L, s, nz, ni, col, j, i, y0v, ymv, ypv);
+    const double chem = A.chem[e];
+    if (A.out_chem) A.out_chem[e] = chem;
+    if (A.out_diff) A.out_diff[e] = diff;
+    if (A.out_sum) {
+        double f = chem + diff;                                   // op.py:2892 / 2918
+        if (A.fix_mask && A.fix_mask[e]) f = 0.0;                 // op.py:2904, 2924
+        if (A.k1) {
+            const double rr = 1. + 1. / sqrt(2.);
+            double c = 2. / (rr * A.dt[col]);
+            f = f - c * A.k1[e];                                  // op.py:2928
+        }
+        A.out_sum[e] = f;
     }
 }
 
@@ -1298,7 +1384,32 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     a.k1 = k1_for_rhs2; a.dt = dt_dev; a.yk2_out = k1_for_rhs2 ? c->yk2 : nullptr;
     a.out_sum = out_sum; a.out_chem = out_chem; a.out_diff = out_diff;
     a.fix_mask = c->opts.fix_mask; a.act = c->act;
-    a.fast = (c->opts.rhs_order == 0 && a.net.rhs_flat_ok) ? 1 : 0;
+    a.fast = ((c->opts.rhs_order == 0 || c->opts.rhs_order == 3) && a.net.rhs_flat_ok) ? 1 : 0;
+    // chemistry through the emitted kernel of this network when the library has one (reference summation order, bit-identical to the
+    // table-driven reference-order path); VK_EMIT=0 or rhs_order = 2 / 3 keep the table-driven kernels
+    static int emit_env = -1;
+    if (emit_env < 0) { const char *e = getenv("VK_EMIT"); emit_env = e ? atoi(e) : 1; }
+    a.chem_in = nullptr;
+    // emitted path: batches that share their rate coefficients (block = one layer of 128 columns, vk_emit_rt.cuh)
+    if (c->net->emit && emit_env && c->opts.rhs_order < 2 && c->k_cs == 0 && c->ncol >= 32) {
+        const size_t nl = (size_t)c->ncol * c->nz;
+        if (!c->chem_tmp) {
+            VK_CUDA(cudaMalloc((void **)&c->chem_tmp, sizeof(double) * nl * c->ni));
+            VK_CUDA(cudaMalloc((void **)&c->ysum_tmp, sizeof(double) * nl));
+            VK_CUDA(cudaMalloc((void **)&c->scal_tmp, sizeof(LayerScal) * nl));
+        }
+        int rc = launch_chem_emitted(c, y_dev, k1_for_rhs2, c->chem_tmp, c->ysum_tmp, k1_for_rhs2 ? c->yk2 : nullptr);
+        if (rc) return rc;
+        StencilArgs sa;
+        sa.atm = c->atm; sa.nz = c->nz; sa.ni = c->ni; sa.ncol = c->ncol;
+        sa.y = k1_for_rhs2 ? c->yk2 : y_dev; sa.k1 = k1_for_rhs2; sa.dt = dt_dev;
+        sa.chem = c->chem_tmp; sa.ysum = c->ysum_tmp; sa.S = static_cast<LayerScal *>(c->scal_tmp);
+        sa.out_sum = out_sum; sa.out_chem = out_chem; sa.out_diff = out_diff; sa.fix_mask = c->opts.fix_mask; sa.act = c->act;
+        layer_scal_kernel<<<(unsigned)((nl + 127) / 128), 128, 0, c->stream>>>(sa);
+        rhs_stencil_kernel<<<(unsigned)((nl * c->ni + 255) / 256), 256, 0, c->stream>>>(sa);
+        VK_CUDA(cudaGetLastError());
+        return VK_OK;
+    }
     const RhsWarpSmem SL = rhs_warp_layout(c->ni, c->nr, a.fast ? a.net.rhs_n_seg : 0);
     const size_t smem = sizeof(double) * (size_t)RHS_WPB * SL.total + sizeof(uchar4) * (c->nr + 2) +
                         sizeof(unsigned short) * (std::max(a.net.n_rhs, 32 * a.net.rhs_flat_T) + 8) + 16;

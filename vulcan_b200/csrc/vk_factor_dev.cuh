@@ -72,6 +72,9 @@ struct FactorCfg {
     // fused assembly (FUSED = true): the idle warps of the spread layout are the producers of D_{j+1}
     static constexpr int NPROD = SPREAD ? NW / 3 - 1 : 0;            // producer warps: 1 / 2 / 3 / 4 for NIP = 48 / 72 / 96 / 120
     static constexpr int NFEED = (NW + NPROD) * 32;                  // threads on the dbuf hand-over barriers
+    // fused forward elimination: tvec[NIP] + zpart[NW][NIP] behind the buffers above
+    static constexpr size_t FWD_OFF = (SMEM_DOUBLES + 1) & ~(size_t)1;
+    static constexpr size_t SMEM_FWD = sizeof(double) * (FWD_OFF + (size_t)NIP + (size_t)NW * NIP);
 };
 struct NoProducer {};
 // producer side of the fused kernel (defined in vk_lhs_dev.cuh, instantiated only by vk_chem.cu)
@@ -91,6 +94,15 @@ struct FactorArgs {
     const int *blk_idx;
     double *Wout;
     int status_idx;
+    // forward elimination of stage 1 fused into the sweep (optional, rhs != NULL): for columns with dt < fwd_dt_max the kernel forms
+    // z_j = W_j (r_j - dn_j z_{j-1}) from the explicit inverse it holds in registers and sets fwd_done[col] = 1, so that the first
+    // solve only runs its backward sweep (one read of F less).  x = fl(S^-1) t is not backward stable: it is used only
+    // below the step size from which the element budget needs the block LU solve (and refinement), fwd_dt_max = refine_dt_min
+    const double *rhs;   // [ncol][nz][ni]
+    double *z;           // [ncol][nz][NIP]
+    const double *dt;    // [ncol]
+    double fwd_dt_max;
+    int *fwd_done;       // [ncol]
 };
 
 // D(8x8) = A(8x4) B(4x8) + C on the FP64 tensor pipe: lane 4g+t supplies A[g][t], B[t][g], C[g][2t..2t+1]
@@ -194,6 +206,10 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
     const int nz = a.nz;
     const size_t cbase = (size_t)col * nz;
     int bad = 0;
+    bool fuse = false;
+    if constexpr (!FUSED) fuse = a.rhs != nullptr && a.blk_idx == nullptr && a.dt[col] < a.fwd_dt_max;
+    double *tvec = smem + C::FWD_OFF;    // NIP        t_j = r_j - dn_j z_{j-1}
+    double *zpart = tvec + NIP;          // NW x NIP   per column warp: its columns' share of W_j t_j
 
     auto prefetch = [&](int j) {         // one thread: D_j, up_{j-1}, dn_j -> shared memory
         mbar_expect_tx(mbar, (j > 0) ? C::TX_BYTES : (unsigned)(sizeof(double) * NIP * NIP));
@@ -298,6 +314,8 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         }
         publish_first();
         if (w == 0) publish_raw(0);
+        if (a.fwd_done && tid == 0) a.fwd_done[col] = fuse ? 1 : 0;
+        if (fuse && tid < NIP) tvec[tid] = (tid < a.ni) ? a.rhs[cbase * a.ni + tid] : 0.0;      // (ordered by the panel barriers of layer 0)
     }
 
     for (int j = 0; j < nz; j++) {
@@ -403,6 +421,11 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         // update of the NEXT layer, S_{j+1} = D_{j+1} - diag(dn_{j+1}) W_j diag(up_j) (D, up, dn already in shared memory by TMA).  Warps 0
         // and 1 hand their first two new tiles to the inverse warp as soon as they exist, so the P_0 chain of layer j+1 starts at once.
         const bool more = j + 1 < nz;
+        double rnext = 0.0, tv0 = 0.0, tv1 = 0.0;
+        if (fuse) {
+            if (more && tid < a.ni) rnext = a.rhs[(cbase + j + 1) * a.ni + tid];
+            tv0 = tvec[c0]; tv1 = tvec[c0 + 1];
+        }
         double su0 = 0.0, su1 = 0.0;
         if (more) {
             if constexpr (FUSED) bar_sync<VK_BAR_FULL, C::NFEED>(); else mbar_wait(mbar, (j + 1) & 1);
@@ -411,6 +434,12 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
 #pragma unroll
         for (int i = 0; i < NR; i++) {
             const int r = 8 * i + g;
+            if (fuse) {
+                double part = fma(A[i][0], tv0, A[i][1] * tv1);
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                if (t == 0) zpart[w * NIP + r] = part;
+            }
             if (more) {
                 const double2 d = *reinterpret_cast<const double2 *>(dbuf + r * NIP + c0);
                 const double l = updn[NIP + r];
@@ -421,6 +450,14 @@ __global__ void __launch_bounds__(FactorCfg<NIP>::NT, MINB) factor_kernel(Factor
         }
         if (more && w == 0) publish_raw(0);
         bar_sync<VK_BAR_COLS, NW * 32>();
+        if (fuse && tid < NIP) {   // z_j = W_j (r_j - dn_j z_{j-1}); right-hand side of the next layer's elimination
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NW; q++) acc += zpart[q * NIP + tid];
+            a.z[(cbase + j) * NIP + tid] = acc;
+            if (more) tvec[tid] = rnext - updn[NIP + tid] * acc;
+        }
+        // (the panel barriers of the next layer order the reuse of zpart / tvec, and the prefetch of layer j+2 that overwrites updn)
     }
 }
 

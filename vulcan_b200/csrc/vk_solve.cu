@@ -31,6 +31,7 @@ struct LuSolveArgs {
     double *x;                   // [ncol][nz][ni]
     double *z;                   // [ncol][nz][NIP] scratch
     const int *act;              // optional per-column flags (refine = auto): columns with act == 0 are skipped
+    const int *fwd_done;         // optional per-column flags: z already holds the forward-eliminated vector (fused into factor_kernel)
 };
 
 template <int NIP, int NBUF>
@@ -116,14 +117,18 @@ __global__ void __launch_bounds__(LuCfg<NIP, NBUF>::NT) lu_solve_kernel(LuSolveA
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (i == 0) fetch(0, 0);
-    const int nvisit = 2 * nz - 1;
-    auto layer_of = [&](int v) { return v < nz ? v : 2 * nz - 2 - v; };
+    // visits: layers 0 .. nz-1 forward, nz-2 .. 0 backward; a column whose forward elimination was fused into the factorisation starts
+    // with the backward part (voff = nz)
+    const bool skip = a.fwd_done && a.fwd_done[col];
+    const int voff = skip ? nz : 0;
+    const int nvisit = 2 * nz - 1 - voff;
+    auto layer_of = [&](int v) { const int vv = v + voff; return vv < nz ? vv : 2 * nz - 2 - vv; };
+    if (i == 0 && nvisit > 0) fetch(layer_of(0), 0);
     int v = 0;
     // ---- forward
-    double zprev = 0.0;
+    double zprev = (skip && live) ? zc[(size_t)(nz - 1) * NIP + i] : 0.0;
     double rn = (i < ni) ? rc[i] : 0.0, dnn = 0.0;
-    for (int j = 0; j < nz; j++, v++) {
+    for (int j = 0; j < nz && !skip; j++, v++) {
         double t = rn - dnn * zprev;
         if (j + 1 < nz) {
             rn = (i < ni) ? rc[(size_t)(j + 1) * ni + i] : 0.0;
@@ -329,25 +334,34 @@ __global__ void __launch_bounds__(256) refine_select_kernel(SelectArgs a)
 
 // ------------------------------------------------------------------------------------------------------------------
 template <int NIP, int MINB>
-static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
+static int launch_factor_t(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status, const double *fwd_rhs)
 {
     using C = FactorCfg<NIP>;
-    FactorArgs a{c->nz, c->ni, D, up, dn, F, status, c->act, nullptr, nullptr, 0};
-    { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, false, NoProducer>, c->net->device, C::SMEM); if (rc) return rc; }
-    factor_kernel<NIP, MINB, false, NoProducer><<<c->ncol, C::NT, C::SMEM, c->stream>>>(a, NoProducer{});
+    FactorArgs a{c->nz, c->ni, D, up, dn, F, status, c->act, nullptr, nullptr, 0, fwd_rhs, c->z, c->dt, c->opts.refine_dt_min, c->fwd_done};
+    if (!fwd_rhs) a.fwd_done = nullptr;
+    const size_t smem = fwd_rhs ? C::SMEM_FWD : C::SMEM;
+    { int rc = ensure_smem((const void *)factor_kernel<NIP, MINB, false, NoProducer>, c->net->device, C::SMEM_FWD); if (rc) return rc; }
+    factor_kernel<NIP, MINB, false, NoProducer><<<c->ncol, C::NT, smem, c->stream>>>(a, NoProducer{});
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
 
 // F out: block LU factors of the Schur blocks, [ncol][nz][nip][nip+2]
-int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status)
+// fwd_rhs (optional): right-hand side of the first solve; its forward elimination is fused into the sweep for the columns with
+// dt < refine_dt_min (c->fwd_done[col] = 1, z in c->z; pass c->fwd_done to that solve)
+int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status, const double *fwd_rhs)
 {
+    static int env_fwd = -1;
+    if (env_fwd < 0) { const char *e = getenv("VK_FWD_FUSED"); env_fwd = e ? atoi(e) : 1; }
+    if (!env_fwd || !c->fwd_done) fwd_rhs = nullptr;
+    c->fwd_valid = 0;
     if (c->cr_now) return launch_cr_factor(c, D, up, dn, F, status);
+    c->fwd_valid = fwd_rhs != nullptr;
     switch (c->nip) {
-        case 48: return launch_factor_t<48, 2>(c, D, up, dn, F, status);
-        case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status);      // (3 blocks per SM at <= 56 registers measured SLOWER: 25.3 vs 23.6 ms, spills)
-        case 96: return launch_factor_t<96, 1>(c, D, up, dn, F, status);
-        case 120: return launch_factor_t<120, 1>(c, D, up, dn, F, status);
+        case 48: return launch_factor_t<48, 2>(c, D, up, dn, F, status, fwd_rhs);
+        case 72: return launch_factor_t<72, 2>(c, D, up, dn, F, status, fwd_rhs);      // (3 blocks per SM at <= 56 registers measured SLOWER: 25.3 vs 23.6 ms, spills)
+        case 96: return launch_factor_t<96, 1>(c, D, up, dn, F, status, fwd_rhs);
+        case 120: return launch_factor_t<120, 1>(c, D, up, dn, F, status, fwd_rhs);
         default: set_error("no factor kernel for this padded block size"); return VK_ERR_UNSUPPORTED;
     }
 }
@@ -363,10 +377,11 @@ static int launch_lu_solve_t(vk_column *c, const LuSolveArgs &a)
 }
 
 // x = A^{-1} rhs with the stored block LU factors F ([ncol][nz][nip][nip+2]); z is scratch
-int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z, const int *act)
+int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z, const int *act,
+                 const int *fwd_done)
 {
     if (c->cr_now) return launch_cr_solve(c, F, up, dn, rhs, x, act);
-    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, act};
+    LuSolveArgs a{c->nz, c->ni, F, up, dn, rhs, x, z, act, fwd_done};
     // slots of the F prefetch per block: 2 = the next layer's copy overlaps this layer's substitution inside the block (few columns:
     // nothing else hides the copy latency), 1 = more blocks per SM hide it instead.  Measured, 592 HD189 columns: 1 slot (5 blocks per
     // SM) 1.28 ms = 93 % of the measured HBM peak, 2 slots 1.87 ms; one column: 2 slots.
