@@ -379,6 +379,7 @@ def main():
         lib.vk_debug_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
         lib.vk_debug_time_kernel.restype = ctypes.c_int
         for which, name in ((0, "lhs_ml_kernel"), (1, "rhs_warp_kernel"), (6, "emitted chemdf kernel (part of the rhs line)"),
+                            (7, "emitted Jacobian kernel (part of the lhs line)"),
                             (3, "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)"),
                             (4, "lu_solve_kernel (forward + backward)")):
             msk = ctypes.c_float(0)
@@ -463,6 +464,7 @@ def main():
             alg = {"lhs_ml_kernel": nz * nip * nip * 8.0 + nz * ni * 8.0,                        # writes D (+ up, dn), reads y; k is shared (L2)
                    "rhs_warp_kernel": 2.0 * nz * ni * 8.0,                                       # reads y, writes f; k is shared (L2)
                    "emitted chemdf kernel (part of the rhs line)": 2.0 * nz * ni * 8.0,          # reads y, writes chemdf; k is shared (L2)
+                   "emitted Jacobian kernel (part of the lhs line)": nz * ni * nip * 8.0 + nz * ni * 8.0,   # writes the ni dense rows of D, reads y
                    "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)": 1.0 * nz * nip * (nip + 2) * 8.0,
                    "lu_solve_kernel (forward + backward)": 2.0 * nz * nip * (nip + 2) * 8.0}     # reads the factors F_j once per sweep
             line["hbm_kernels"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src, "kernels": [

@@ -14,35 +14,94 @@ CASES = [p for p in [("HD189", 0), ("HD189", 300), ("Jupiter", 30), ("Earth", 30
          if have(p[0], "step%04d.npz" % p[1])]
 
 
+def _statements(line):
+    s = line.strip().replace("const double ", "").replace("double ", "")
+    return [x.strip() for x in s.split(";") if x.strip()]
+
+
 def _evaluate(src, y, M, k):
-    """numpy interpretation of the emitted kernel(s): y [nz, ni], M [nz], k [nz, nr+1] -> chemdf [nz, ni]"""
+    """numpy interpretation of the emitted chemdf kernel(s): y [nz, ni], M [nz], k [nz, nr+1] -> chemdf [nz, ni]"""
     nz, ni = y.shape
     yx = np.concatenate([y, M[:, None]], axis=1)
     out = np.full((nz, ni), np.nan)
-    ns, lo = {}, 0
+    ns, active = {}, False
     for line in src.splitlines():
         s = line.strip()
         if s.startswith("__global__"):
-            ns = {}
+            ns, active = {}, "chemdf_" in s
             continue
-        if not s or s in ("{", "}") or s.startswith("}") or s.startswith(("//", "#", "namespace", "VK_EMIT_", "int launch", "const size_t", "return", "const EmitRegistrar", "}}")):
+        if not active or not s or s in ("{", "}") or s.startswith("}") or s.startswith(("//", "#", "VK_EMIT")):
             continue
-        s = s.replace("const double ", "").replace("double ", "")
-        if re.match(r"f\d+ = 0\.0, ", s):
-            for part in s.rstrip(";").split(", "):
-                name, val = part.split(" = ")
-                ns[name] = np.zeros(nz)
+        if s.startswith(("int launch", "const size_t", "return", "const EmitRegistrar")):
+            active = False
             continue
-        for stmt in [x for x in s.split(";") if x.strip()]:
-            stmt = stmt.strip()
+        for stmt in _statements(s):
+            if re.match(r"f\d+ = 0\.0(, f\d+ = 0\.0)*$", stmt):
+                for part in stmt.split(", "):
+                    ns[part.split(" = ")[0]] = np.zeros(nz)
+                continue
             m = re.match(r"F\((\d+)\) = f(\d+)$", stmt)
             if m:
                 out[:, int(m.group(1))] = ns["f" + m.group(2)]
                 continue
-            stmt = re.sub(r"K\((\d+)\)", lambda q: "k[:, %d]" % (lo + int(q.group(1))), stmt)
+            stmt = re.sub(r"K\((\d+)\)", r"k[:, \1]", stmt)
             stmt = re.sub(r"Y\((\d+)\)", r"yx[:, \1]", stmt)
             exec(stmt, {"k": k, "yx": yx, "pow": np.power}, ns)
     return out
+
+
+class _Rows(dict):
+    def __init__(self, nz):
+        dict.__init__(self)
+        self.nz = nz
+
+    def __missing__(self, key):
+        return np.zeros(self.nz)
+
+
+def _evaluate_jac(src, y, M, k, nip):
+    """numpy interpretation of the emitted Jacobian kernel: -> -J [nz, nip, nip] (rows >= ni stay zero: lhs_diag_kernel writes them)"""
+    nz, ni = y.shape
+    J = np.zeros((nz, nip, nip))
+    rT = _Rows(nz)
+    for s_ in range(ni):
+        rT[s_] = y[:, s_].copy()                       # the staged y row (S(s) = rT[s])
+    ns, active = {"yM": M}, False
+    for line in src.splitlines():
+        s = line.strip()
+        if s.startswith("__global__"):
+            active = "negjac_" in s
+            continue
+        if not active:
+            continue
+        if s.startswith("int launch"):
+            break
+        m = re.match(r"VK_EMITJ_BEGIN\((\d+), (\d+)\)", s)
+        if m:
+            for r in range(int(m.group(2))):
+                rT[r] = np.zeros(nz)
+            continue
+        m = re.match(r"VK_EMITJ_ROW\((\d+), (\d+), (\d+)\)", s)
+        if m:
+            for t in range(nip):
+                J[:, int(m.group(1)), t] = rT[t]
+            continue
+        s = s.split("//")[0].strip("{} ")
+        if not s or s.startswith(("#", "VK_EMIT")):
+            continue
+        for stmt in _statements(s):
+            if re.match(r"(t|a\d+_\d+(, a\d+_\d+)*)$", stmt):          # declarations without initialiser
+                continue
+            if re.match(r"[yc]\d+ = S\(\d+\)(, [yc]\d+ = S\(\d+\))*$", stmt):
+                for part in stmt.split(", "):
+                    name, src_ = part.split(" = ")
+                    ns[name] = rT[int(src_[2:-1])].copy()
+                continue
+            stmt = re.sub(r"K\((\d+)\)", r"k[:, \1]", stmt)
+            stmt = re.sub(r"R\((\d+)\)", r"rT[\1]", stmt)
+            stmt = re.sub(r"= 0\.0$", "= zeros()", stmt)
+            exec(stmt, {"k": k, "rT": rT, "zeros": lambda: np.zeros(nz)}, ns)
+    return J
 
 
 @pytest.mark.parametrize("tag,step", CASES)
@@ -53,6 +112,21 @@ def test_emitted_chemdf_is_bit_identical_to_the_reference(tag, step):
     assert not np.isnan(chem).any()                      # every species is stored by exactly one pass
     assert np.array_equal(chem, c.fx["chemdf"])
     assert ("launch_%016x" % h) in src and ("0x%016xull" % h) in src
+
+
+@pytest.mark.parametrize("tag,step", CASES)
+def test_emitted_jacobian_is_bit_identical_to_the_oracle(tag, step):
+    """the emitted Jacobian kernel sums the terms of every entry left to right in the order of the oracle's vko_chemjac (the analytic
+    restatement of chem_funs.symjac, pinned against the reference's sympy Jacobian in test_oracle_vs_reference.py): same bits"""
+    from oracle import Oracle
+    c = Case(tag, step)
+    src, h = emit.emit_chemdf(c.net.tables(), tag)
+    assert ("negjac_%016x" % h) in src
+    nip = emit.pad_block(c.ni)
+    negJ = _evaluate_jac(src, c.y, c.st["M"], c.k, nip)
+    Jo = Oracle(c.net).chemjac(c.y, c.st["M"], c.k)
+    assert np.array_equal(negJ[:, :c.ni, :c.ni], -Jo)
+    assert not negJ[:, c.ni:, :].any() and not negJ[:, :, c.ni:].any()
 
 
 def test_hash_and_registry_of_the_baseline_networks():

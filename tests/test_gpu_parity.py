@@ -268,12 +268,41 @@ def test_rhs_emitted_batch(tag, step):
     for q in (1, 17, 39):
         assert np.array_equal(chem[q], c.oracle.chemdf(y[q], c.st["M"], c.k)), q
         assert np.array_equal(diff[q], c.oracle.diffdf(c.atm, y[q])), q
-    tab = _columns(c, ncol, rhs_order=2)                     # table-driven kernels, reference order
-    ymix = y / y.sum(axis=2, keepdims=True)
+    # lhs through the emitted Jacobian kernel + lhs_diag_kernel: every entry the left-to-right sum of its terms in the oracle's order, so
+    # the blocks are bit-identical to the oracle's (the table-driven kernel sums long entries in 16-term segments: 4e-15)
     dt = np.full(ncol, min(c.dt, 1e2))
+    D, up, dn = col.eval_lhs(y, dt)
+    for q in (0, 17, 39):
+        Do, upo, dno = c.oracle.lhs(c.atm, y[q], c.k, float(dt[q]))
+        fm = step_opts(c)["fix_mask"]
+        if fm is not None:
+            jj, ii = np.nonzero(fm)
+            Do[jj, ii, :] = 0.0
+            Do[jj, ii, ii] = 1. / (R * dt[q])
+            upo[jj, ii] = 0.0
+            dno[jj, ii] = 0.0
+        assert np.array_equal(up[q], upo) and np.array_equal(dn[q], dno), q
+        scale = np.abs(Do).max(axis=2, keepdims=True)
+        err = np.max(np.abs(D[q] - Do) / np.maximum(scale, 1e-300))
+        assert err < 4e-15, (q, err)
+        assert np.array_equal(D[q] != 0, Do != 0)
+    # a whole attempted step against the table-driven kernels (rhs bit-identical, lhs at rounding level)
+    import os
+    tab = _columns(c, ncol, rhs_order=2)
+    ymix = y / y.sum(axis=2, keepdims=True)
     s1, m1, d1, st1 = col.ros2_solve(y, ymix, dt)
-    s2, m2, d2, st2 = tab.ros2_solve(y, ymix, dt)
-    assert np.array_equal(s1, s2) and np.array_equal(m1, m2) and np.array_equal(d1, d2) and np.array_equal(st1, st2)
+    os.environ["VK_EMIT_JAC"] = "0"
+    try:
+        jt = _columns(c, ncol)                               # emitted chemdf, table-driven Jacobian
+        s3, m3, d3, st3 = jt.ros2_solve(y, ymix, dt)
+        s2, m2, d2, st2 = tab.ros2_solve(y, ymix, dt)
+    finally:
+        os.environ.pop("VK_EMIT_JAC", None)
+    assert np.array_equal(s3, s2) and np.array_equal(m3, m2) and np.array_equal(d3, d2) and np.array_equal(st3, st2)
+    assert np.array_equal(st1, st2)
+    m = np.abs(s2) > 1e-8 * np.abs(s2).max(axis=2, keepdims=True)
+    assert np.max(np.abs(s1 - s2)[m] / np.abs(s2)[m]) < 1e-6
+    assert np.allclose(d1, d2, rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.parametrize("tag,step", PHOTO_CASES, ids=[case_id(p) for p in PHOTO_CASES])

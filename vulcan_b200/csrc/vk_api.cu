@@ -390,7 +390,7 @@ void vk_column_destroy(vk_column *c)
     cr_plan_free(c->cr);
     if (c->refine_kept) cudaFree(c->refine_kept);
     double *vecs[] = {c->y, c->ymix, c->sol, c->ymix_out, c->f, c->k1, c->k2, c->yk2, c->rhs, c->res, c->dx, c->xn, c->z, c->up, c->dn,
-                      c->D, c->W, c->dt, c->delta, c->k, c->chem_tmp, c->ysum_tmp, static_cast<double *>(c->scal_tmp)};
+                      c->D, c->W, c->dt, c->delta, c->k, c->chem_tmp, c->ysum_tmp, static_cast<double *>(c->scal_tmp), c->ysum_lhs_tmp};
     for (double *v : vecs) if (v) cudaFree(v);
     if (c->status) cudaFree(c->status);
     if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -695,12 +695,20 @@ int vk_eval_lhs(vk_column *c, const double *y, const double *dt, double *D, doub
     VK_CUDA(cudaMemcpyAsync(c->y, y, sizeof(double) * nv, cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaMemcpyAsync(c->dt, dt, sizeof(double) * c->ncol, cudaMemcpyHostToDevice, c->stream));
     const char *via = getenv("VK_LHS_VIA_FUSED");
-    if (via && atoi(via)) {
+    const char *ej = getenv("VK_EMIT_JAC");
+    // batches that the step assembles through the EMITTED Jacobian kernel (vk_chem.cu: launch_lhs) are evaluated the same way here: padded
+    // blocks, un-padded on the way out
+    const bool emitted = !(via && atoi(via)) && !(ej && !atoi(ej)) && emit_has_jac(c->net->emit) && c->k_cs == 0 && c->ncol >= 32;
+    if ((via && atoi(via)) || emitted) {
         // parity aid: the blocks as the FUSED assembly + factorisation kernel forms them (producer warps, store_D = always), un-padded
         // on the way out - must be bit-identical to lhs_ml_kernel's (tests/test_gpu_fused.py)
-        VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
-        rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, 1);
-        if (rc == VK_ERR_UNSUPPORTED) set_error("the fused kernel does not support this network / block size");
+        if (emitted) {
+            rc = launch_lhs(c, c->y, c->dt, c->nip, c->D, c->up, c->dn);
+        } else {
+            VK_CUDA(cudaMemsetAsync(c->status, 0, sizeof(int) * c->ncol, c->stream));
+            rc = launch_factor_fused(c, c->y, c->dt, c->D, c->up, c->dn, c->W, c->status, 1);
+            if (rc == VK_ERR_UNSUPPORTED) set_error("the fused kernel does not support this network / block size");
+        }
         if (rc) return rc;
         double *dD = nullptr, *dU = nullptr, *dL = nullptr;
         VK_CUDA(cudaMalloc((void **)&dD, sizeof(double) * nv * c->ni));
@@ -841,6 +849,10 @@ extern "C" int vk_debug_time_kernel(vk_column *c, int which, int reps, float *ms
             if (!c->chem_tmp) rc = vk::launch_rhs(c, c->y, c->f, nullptr, nullptr, nullptr, nullptr);      // allocates the scratch of the emitted path
             if (rc == VK_OK && !c->chem_tmp) { set_error("this handle does not take the emitted chemistry path"); rc = VK_ERR_UNSUPPORTED; }
             if (rc == VK_OK) rc = vk::launch_chem_emitted(c, c->y, nullptr, c->chem_tmp, c->ysum_tmp, nullptr);
+        }
+        else if (which == 7) {
+            if (!c->ysum_lhs_tmp) VK_CUDA(cudaMalloc((void **)&c->ysum_lhs_tmp, sizeof(double) * (size_t)c->ncol * c->nz));
+            rc = vk::launch_jac_emitted(c, c->y, c->D, c->ysum_lhs_tmp);
         }
         else if (which == 3) rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z, c->act, c->fwd_valid ? c->fwd_done : nullptr);
         else rc = vk::launch_solve(c, c->W, c->up, c->dn, c->f, c->k1, c->z);

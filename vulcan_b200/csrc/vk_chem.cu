@@ -1420,11 +1420,156 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     return VK_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// lhs behind an EMITTED Jacobian kernel (vk_emit.cu: -J as dense rows in D, layer sums in ysum): one thread per (column, layer, row of the
+// padded block) adds what lhs_jac_tot adds around the chemical Jacobian (op.py:1973-2444) - c0 = 1/(r dt) and the transport terms on the
+// diagonal, the couplings up / dn, identity rows for fixed species and for the padding - same expressions, same order as lhs_ml_kernel.
+struct LhsDiagArgs {
+    AtmDev atm;
+    int nz, ni, ncol, ld;
+    const double *y, *dt, *ysum;
+    double *D, *up, *dn;
+    const unsigned char *fix_mask;
+    const int *act;
+};
+__global__ void __launch_bounds__(256) lhs_diag_kernel(LhsDiagArgs A)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ni = A.ni, nz = A.nz, ld = A.ld;
+    if (e >= (size_t)A.ncol * nz * ld) return;
+    const int lay = (int)(e / ld), i = (int)(e - (size_t)lay * ld);
+    const int col = lay / nz, j = lay - col * nz;
+    if (A.act && !A.act[col]) return;
+    double *Drow = A.D + ((size_t)lay * ld + i) * ld;
+    const size_t vbase = (size_t)lay * ld;
+    // padding rows ni .. ld-1: decoupled identity rows keep the padded block invertible; thread i writes column i of each (coalesced)
+    for (int r = ni; r < ld; r++) A.D[((size_t)lay * ld + r) * ld + i] = (r == i) ? 1.0 : 0.0;
+    if (i >= ni) {
+        A.up[vbase + i] = 0.0;
+        A.dn[vbase + i] = 0.0;
+        return;
+    }
+    const double rr = 1. + 1. / sqrt(2.);
+    const double c0 = 1. / (rr * A.dt[col]);
+    const AtmLayer L = atm_at(A.atm, col);
+    const AtmPre &P = A.atm.pre;
+    const double *dzi = L.dzi;
+    const int md = A.atm.use_moldiff, st = A.atm.use_settling && A.atm.use_moldiff;
+    const int vmm = A.atm.use_vm_mol;
+    const size_t base = (size_t)lay * ni;
+    const double ys0 = A.ysum[lay], ysm = (j > 0) ? A.ysum[lay - 1] : 0.0, ysp = (j < nz - 1) ? A.ysum[lay + 1] : 0.0;
+    const double *ls = A.atm.pre.LS + ((size_t)col * (A.atm.pre_cs ? nz : 0) + j) * 10;
+    const size_t pb = ((size_t)col * A.atm.pre_cs + (size_t)j * ni) + i;
+    double eA = 0.0, tA = 0.0, tV = 0.0, tE = 0.0;
+    double eB = 0.0, eC = 0.0, u = 0.0, l = 0.0;
+    if (j == 0) {
+        eA = ls[0] * (ysp + ys0) / (2. * ys0) + ls[5];
+        eB = ls[3] * (ysp + ys0) / (2. * ysp) + ls[6];
+        u -= eB;
+        if (md) {
+            double ta = P.QC[pb] * (ysp + ys0) / (2. * ys0);
+            double tb = P.QB[pb] * (ysp + ys0) / (2. * ysp);
+            if (vmm) {
+                double tx = 0.0;
+                vm_lhs_adv(P, pb, 0, st, ta, tb, tx);
+            } else {
+                ta = ta + P.TA[pb];
+                tb = tb + P.TB[pb];
+                if (st) {
+                    ta = ta - P.SA[pb];
+                    tb = tb - P.SB[pb];
+                }
+            }
+            tA = ta;
+            u -= tb;
+        }
+        if (A.atm.use_botflux) tV = -1. * L.bot_vdep[i] / dzi[0];
+    } else if (j == nz - 1) {
+        if (vmm && A.atm.n_diff_esc > 0) tE = vm_diff_lim(A.atm, L, i, A.y[base + i]);
+        eA = ls[0] * (ysm + ys0) / (2. * ys0) + ls[5];
+        eC = ls[4] * (ysm + ys0) / (2. * ysm) + ls[7];
+        l -= eC;
+        if (md) {
+            double ta = P.QB[pb] * (ys0 + ysm) / (2. * ys0);
+            double tc = P.QC[pb] * (ys0 + ysm) / (2. * ysm);
+            if (vmm) {
+                double tx = 0.0;
+                vm_lhs_adv(P, pb, 2, st, ta, tx, tc);
+            } else {
+                ta = ta - P.TA[pb];
+                tc = tc - P.TC[pb];
+                if (st) {
+                    ta = ta + P.SA[pb];
+                    tc = tc + P.SC[pb];
+                }
+            }
+            tA = ta;
+            l -= tc;
+        }
+    } else {
+        eA = ls[8] * (ls[1] * (ysp + ys0) / 2. + ls[2] * (ysm + ys0) / 2.) / ys0 + ls[5];
+        eB = ls[9] * (ls[1] * (ysp + ys0) / (2. * ysp)) + ls[6];
+        eC = ls[9] * (ls[2] * (ysm + ys0) / (2. * ysm)) + ls[7];
+        u -= eB;
+        l -= eC;
+        if (md) {
+            double ta = ls[8] * (P.Q[pb] * (ysp + ys0) / 2. + P.Q[pb - ni] * (ysm + ys0) / 2.) / ys0;
+            double tb = ls[9] * (P.Q[pb] * (ysp + ys0) / (2. * ysp));
+            double tc = ls[9] * (P.Q[pb - ni] * (ysm + ys0) / (2. * ysm));
+            if (vmm) {
+                vm_lhs_adv(P, pb, 1, st, ta, tb, tc);
+            } else {
+                ta = ta + P.TA[pb];
+                tb = tb + P.TB[pb];
+                tc = tc - P.TC[pb];
+                if (st) {
+                    ta = ta - P.SA[pb];
+                    tb = tb - P.SB[pb];
+                    tc = tc + P.SC[pb];
+                }
+            }
+            tA = ta;
+            u -= tb;
+            l -= tc;
+        }
+    }
+    const bool fixed = A.fix_mask && A.fix_mask[base + i];
+    if (fixed) { u = 0.0; l = 0.0; }
+    A.up[vbase + i] = u;
+    A.dn[vbase + i] = l;
+    double d = c0 + Drow[i];
+    d -= tE;
+    d -= eA;
+    if (md) d -= tA;
+    if (A.atm.use_botflux && j == 0) d -= tV;
+    if (fixed) {                 // op.py:2903-2906: row -> 1/(r h) e_i
+        for (int t = 0; t < ni; t++) Drow[t] = 0.0;
+        d = c0;
+    }
+    Drow[i] = d;
+}
+
 int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, double *D_out, double *up_out, double *dn_out)
 {
     LhsArgs a;
     a.net = c->net->d; a.atm = c->atm; a.nz = c->nz; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs; a.dt = dt_dev;
     a.D = D_out; a.up = up_out; a.dn = dn_out; a.ld = ld; a.fix_mask = c->opts.fix_mask; a.act = c->act;
+    // emitted path (batches that share their rate coefficients): -J as straight-line code, then the elementwise diagonal / coupling kernel
+    const char *ej = getenv("VK_EMIT_JAC");      // (read per call: the parity tests switch it inside one process)
+    const int emit_env = ej ? atoi(ej) : 1;
+    if (emit_env && emit_has_jac(c->net->emit) && c->k_cs == 0 && c->ncol >= 32 && ld == c->nip && !getenv("VK_LHS_DEBUG")) {
+        const size_t nl = (size_t)c->ncol * c->nz;
+        if (!c->ysum_lhs_tmp) VK_CUDA(cudaMalloc((void **)&c->ysum_lhs_tmp, sizeof(double) * nl));
+        int rc = launch_jac_emitted(c, y_dev, D_out, c->ysum_lhs_tmp);
+        if (rc) return rc;
+        LhsDiagArgs da;
+        da.atm = c->atm; da.nz = c->nz; da.ni = c->ni; da.ncol = c->ncol; da.ld = ld;
+        da.y = y_dev; da.dt = dt_dev; da.ysum = c->ysum_lhs_tmp; da.D = D_out; da.up = up_out; da.dn = dn_out;
+        da.fix_mask = c->opts.fix_mask; da.act = c->act;
+        lhs_diag_kernel<<<(unsigned)((nl * ld + 255) / 256), 256, 0, c->stream>>>(da);
+        VK_CUDA(cudaGetLastError());
+        return VK_OK;
+    }
     if (!a.net.lhs_ml_ok) {
         set_error("network exceeds the packing limits of the Jacobian kernel (nr < 2048, ni < 127, < 8191 distinct products, coefficients in +-{1,2,3,4})");
         return VK_ERR_UNSUPPORTED;

@@ -78,4 +78,20 @@ int launch_chem_emitted(vk_column *c, const double *y_dev, const double *k1, dou
     return VK_OK;
 }
 
+// -J of every layer as dense rows into D_out ([ncol][nz][nip][nip]) and the layer sums lhs_jac_tot reads into ysum_out, through the emitted
+// Jacobian kernel of this network
+int launch_jac_emitted(vk_column *c, const double *y_dev, double *D_out, double *ysum_out)
+{
+    const emitted::EmitEntry *e = static_cast<const emitted::EmitEntry *>(c->net->emit);
+    if (!e || !e->jac) { set_error("no emitted Jacobian kernel for this network"); return VK_ERR_UNSUPPORTED; }
+    if (c->k_cs != 0) { set_error("the emitted Jacobian kernel needs rate coefficients shared by the batch"); return VK_ERR_UNSUPPORTED; }
+    emitted::EmitJacArgs a;
+    a.nz = c->nz; a.ncol = c->ncol; a.y = y_dev; a.k = c->k;
+    a.M = c->atm.M; a.M_cs = c->atm.csz; a.D = D_out; a.ysum = ysum_out;
+    a.n_gas = c->atm.n_gas_lhs; a.gas_indx = c->atm.gas_indx_lhs; a.act = c->act;
+    if (e->jac(a, c->stream)) return cuda_fail(cudaGetLastError(), "emitted Jacobian kernel");
+    return VK_OK;
+}
+bool emit_has_jac(const void *entry) { return entry && static_cast<const emitted::EmitEntry *>(entry)->jac != nullptr; }
+
 }  // namespace vk

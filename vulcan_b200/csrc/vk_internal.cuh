@@ -139,6 +139,7 @@ struct vk_column {
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
     double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx, *xn;  // work vectors [ncol][nz][ni]
+    double *ysum_lhs_tmp;       // layer sums written by the emitted Jacobian kernel
     double *chem_tmp, *ysum_tmp; void *scal_tmp;   // emitted chemdf path (allocated on first use): chemdf [ncol][nz][ni], layer sums and layer scalars [ncol][nz]
     int *fwd_done; int fwd_valid;   // [ncol] forward elimination of the first solve fused into the factorisation (launch_factor); valid for the last factorisation
     int *refine_kept, *refine_tried, *refine_act;   // [ncol] refinement passes kept / tried by the safeguard, active flags (refine = auto)
@@ -183,6 +184,8 @@ int launch_atm_pre_pred(vk_column *c, const int *pred);
 // kernels (vk_solve.cu)
 unsigned long long network_table_hash(const vk_network_desc *d);
 const void *emit_lookup(unsigned long long hash, int ni, int nr);
+int launch_jac_emitted(vk_column *c, const double *y_dev, double *D_out, double *ysum_out);
+bool emit_has_jac(const void *entry);
 int launch_chem_emitted(vk_column *c, const double *y_dev, const double *k1, double *chem_out, double *ysum_out, double *yk2_out);
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status, const double *fwd_rhs = nullptr);
 int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,

@@ -30,6 +30,10 @@ from .network import Network
 HERE = os.path.dirname(os.path.abspath(__file__))
 NET_DIR = os.path.join(HERE, "networks")
 GEN_DIR = os.path.join(HERE, "csrc", "gen")
+JAC_TB = int(os.environ.get('VK_EMIT_JAC_TB', 128))     # emit_negjac: threads (columns) per block
+JAC_BLOCKS = int(os.environ.get('VK_EMIT_JAC_BLOCKS', 2)) # emit_negjac: resident blocks per SM aimed at
+JAC_COLD_MAX = 32     # emit_negjac: at most this many species are read from shared memory instead of registers
+ROW_ACC = 24          # emit_negjac: entries of a row accumulated in registers before the row buffer is touched       # emit_negjac: forbid common sub-expressions across Jacobian rows (see there)
 MAX_ACC = 84          # dy/dt accumulators held in registers per pass (2 registers each); larger networks take several passes
 
 
@@ -59,6 +63,103 @@ def _fnv_fast(t):
 def _coef_lit(c):
     a = abs(c)
     return "%d.0" % int(a) if a == int(a) else repr(float(a))
+
+
+def pad_block(ni):
+    """padded block size the factor / solve kernels are instantiated for (vk_api.cu: pad_block)"""
+    for n in (48, 72, 96, 120):
+        if ni <= n:
+            return n
+    raise ValueError("ni > 120")
+
+
+def emit_negjac(t, h, w):
+    """the chemical Jacobian (chem_funs.neg_symjac, make_chem_funs.py:653-717; analytic terms of Network.tables()) as straight-line code:
+    one thread per (column, layer) forms the entries ROW BY ROW - every entry the left-to-right sum of its terms coef * k * prod(y), exactly
+    the order of the oracle's vko_chemjac - into its own row buffer in shared memory; the finished dense row (NIP doubles, zeros included)
+    leaves as one asynchronous bulk copy issued by the thread, and the next row is formed while it drains.  y of the species the terms read
+    most lives in registers, the rest behind the row buffer.  Returns False when the tables carry no Jacobian."""
+    if "jac_ptr" not in t or t.get("jac_ptr") is None:
+        return False
+    ni, nr, mjf = t["ni"], t["nr"], int(t["maxjf"])
+    nip = pad_block(ni)
+    jp, jr, jc = np.asarray(t["jac_ptr"]), np.asarray(t["jac_row"]), np.asarray(t["jac_col"])
+    jk, jcoef, jfac = np.asarray(t["jac_k"]), np.asarray(t["jac_coef"]), np.asarray(t["jac_fac"]).reshape(-1, mjf)
+    rows = [[] for _ in range(ni)]
+    for e in range(len(jr)):
+        rows[int(jr[e])].append(e)
+    # hot species live in registers, cold ones (least used by the Jacobian terms) behind the thread's row buffer in shared memory; the row
+    # stride is chosen so that JAC_TB threads x JAC_BLOCKS blocks fit the shared memory of an SM
+    use = np.bincount(jfac[jfac < ni].ravel(), minlength=ni)
+    ks_bytes = 8 * (nr + 2)
+    budget = (226 * 1024) // JAC_BLOCKS - ks_bytes
+    if JAC_TB * 8 * (nip + 2) > budget:
+        budget = 226 * 1024 - ks_bytes
+    rld = min((budget // (JAC_TB * 8)) & ~1, nip + 2 + ni)
+    n_cold = max(0, min(rld - (nip + 2), ni - 8, JAC_COLD_MAX))
+    rld = nip + 2 + n_cold + (n_cold & 1)
+    cold = {int(sp): q for q, sp in enumerate(np.argsort(use, kind="stable")[:n_cold])}
+    cb = nip + 2
+    yname = lambda sl: "yM" if sl == ni else ("rT[%d]" % (cb + cold[sl]) if sl in cold else "y%d" % sl)
+    blocks = max(1, min(JAC_BLOCKS, (226 * 1024) // (JAC_TB * 8 * rld + ks_bytes)))
+    w("// %d of %d species in registers, %d in shared memory (%.1f %% of the factor reads); row stride %d doubles, %d block(s) per SM" % (
+        ni - n_cold, ni, n_cold, 100.0 * sum(use[sp] for sp in cold) / max(1, use.sum()), rld, blocks))
+    w("__global__ void __launch_bounds__(%d, %d) negjac_%016x(EmitJacArgs a)" % (JAC_TB, blocks, h))
+    w("{")
+    w("    VK_EMITJ_PROLOGUE(%d, %d, %d, %d, %d)" % (ni, nr, nip, rld, JAC_TB))
+    w("    const double " + ", ".join("y%d = S(%d)" % (s, s) for s in range(ni) if s not in cold) + ";")
+    if cold:
+        w("    { const double " + ", ".join("c%d = S(%d)" % (q, sp) for sp, q in sorted(cold.items(), key=lambda x: x[1])) + ";")
+        w("      " + " ".join("rT[%d] = c%d;" % (cb + q, q) for q in range(n_cold)) + " }")
+    w("    VK_EMITJ_BEGIN(%d, %d)" % (ni, nip))
+    prev = set()
+    for s in range(ni):
+        cur = set()
+        w("    {   // row %d" % s)
+        w("        double t;")
+        ents = rows[s]
+        opened = False
+        for g0 in range(0, max(1, len(ents)), ROW_ACC):
+            grp = ents[g0:g0 + ROW_ACC]
+            if grp:
+                w("        double " + ", ".join("a%d_%d" % (g0, q) for q in range(len(grp))) + ";")
+            for q, e in enumerate(grp):
+                acc = "a%d_%d" % (g0, q)
+                cur.add(int(jc[e]))
+                first = True
+                for qq in range(int(jp[e]), int(jp[e + 1])):
+                    c = float(jcoef[qq])
+                    kx = "K(%d)" % int(jk[qq])
+                    head = kx if c == 1.0 else ("-" + kx if c == -1.0 else "%s%s * %s" % ("-" if c < 0 else "", _coef_lit(c), kx))
+                    stm = ["t = %s;" % head]
+                    for f in range(mjf):
+                        sl = int(jfac[qq, f])
+                        if sl == ni + 1:
+                            continue
+                        stm.append("t = t * %s;" % yname(sl))
+                    stm.append("%s = t;" % acc if first else "%s = %s + t;" % (acc, acc))
+                    first = False
+                    w("        " + " ".join(stm))
+            if not opened:
+                w("        VK_EMITJ_ROW_OPEN(%d)" % s)
+                opened = True
+            if grp:
+                w("        " + " ".join("R(%d) = -a%d_%d;" % (int(jc[e]), g0, q) for q, e in enumerate(grp)))
+        stale = sorted(prev - cur)
+        if stale:
+            w("        " + " ".join("R(%d) = 0.0;" % c for c in stale))
+        w("    }")
+        w("    VK_EMITJ_ROW(%d, %d, %d)" % (s, ni, nip))
+        prev = cur
+    w("    VK_EMITJ_END()")
+    w("}")
+    w("int launch_jac_%016x(const EmitJacArgs &a, cudaStream_t st)" % h)
+    w("{")
+    w("    const size_t smem = emitj_smem_bytes(%d, %d, %d);" % (rld, nr, JAC_TB))
+    w("    VK_EMITJ_LAUNCH(negjac_%016x, %d)" % (h, JAC_TB))
+    w("    return 0;")
+    w("}")
+    return True
 
 
 def emit_chemdf(t, name):
@@ -140,13 +241,17 @@ def emit_chemdf(t, name):
         w("    VK_EMIT_LAUNCH(chemdf_%016x_p%d)" % (h, g))
     w("    return 0;")
     w("}")
-    w("const EmitRegistrar reg_%016x(0x%016xull, %d, %d, \"%s\", launch_%016x);" % (h, h, ni, nr, name, h))
+    have_jac = emit_negjac(t, h, w)
+    w("const EmitRegistrar reg_%016x(0x%016xull, %d, %d, \"%s\", launch_%016x, %s);" % (
+        h, h, ni, nr, name, h, ("launch_jac_%016x" % h) if have_jac else "nullptr"))
     w("}  // namespace")
     w("}}  // namespace vk::emitted")
     return "\n".join(out) + "\n", h
 
 
-TABLE_KEYS = ("ni", "nr", "maxf", "rate_fac", "rate_pow", "rhs_ptr", "rhs_pair", "rhs_coef")
+TABLE_KEYS = ("ni", "nr", "maxf", "rate_fac", "rate_pow", "rhs_ptr", "rhs_pair", "rhs_coef",
+              "maxjf", "jac_ptr", "jac_row", "jac_col", "jac_k", "jac_coef", "jac_fac")
+HASH_KEYS = TABLE_KEYS[:8]
 
 
 def register_network(net, name=None):
@@ -173,7 +278,7 @@ def has_kernel(net):
     h = _fnv_fast(net.tables())
     for path in glob.glob(os.path.join(NET_DIR, "*.npz")):
         z = np.load(path)
-        if _fnv_fast({k: (int(z[k]) if z[k].ndim == 0 else z[k]) for k in TABLE_KEYS}) == h:
+        if _fnv_fast({k: (int(z[k]) if z[k].ndim == 0 else z[k]) for k in HASH_KEYS}) == h:
             return True
     return False
 
@@ -186,7 +291,7 @@ def generate_all(verbose=True):
     for path in sorted(glob.glob(os.path.join(NET_DIR, "*.npz"))):
         name = os.path.splitext(os.path.basename(path))[0]
         z = np.load(path)
-        t = {k: (int(z[k]) if z[k].ndim == 0 else z[k]) for k in TABLE_KEYS}
+        t = {k: (int(z[k]) if z[k].ndim == 0 else z[k]) for k in TABLE_KEYS if k in z.files}
         try:
             src, h = emit_chemdf(t, name)
         except ValueError as e:
