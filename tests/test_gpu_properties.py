@@ -90,11 +90,12 @@ def test_multi_wave_batch_and_column_order():
 
 
 def test_pipelined_host_solver_matches_single_handle(monkeypatch):
-    """ensemble.PipelinedHostSolver (column groups on separate streams) returns exactly what one handle returns.  (Jacobian through the
-    table-driven kernel on both sides: a handle of 37 columns would take the emitted Jacobian kernel, groups of 7 - 8 columns would not,
-    and the two sum long entries in different orders - compared to rounding level in test_rhs_emitted_batch.)"""
+    """ensemble.PipelinedHostSolver (column groups on separate streams) returns exactly what one handle returns.  (Table-driven chemistry
+    kernels on both sides: a handle of 37 columns would take the emitted kernels, groups of 7 - 8 columns would not, and the two sum in
+    different orders - compared to rounding level in test_rhs_emitted_batch.)"""
     from vulcan_b200 import ensemble
     monkeypatch.setenv("VK_EMIT_JAC", "0")
+    monkeypatch.setenv("VK_EMIT", "0")
     c = Case("HD189", 10)
     ncol = 37
     kw = c.atm_kwargs()

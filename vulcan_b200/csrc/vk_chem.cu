@@ -1387,8 +1387,8 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     a.fast = ((c->opts.rhs_order == 0 || c->opts.rhs_order == 3) && a.net.rhs_flat_ok) ? 1 : 0;
     // chemistry through the emitted kernel of this network when the library has one (reference summation order, bit-identical to the
     // table-driven reference-order path); VK_EMIT=0 or rhs_order = 2 / 3 keep the table-driven kernels
-    static int emit_env = -1;
-    if (emit_env < 0) { const char *e = getenv("VK_EMIT"); emit_env = e ? atoi(e) : 1; }
+    const char *ee = getenv("VK_EMIT");          // (read per call: the parity tests switch it inside one process)
+    const int emit_env = ee ? atoi(ee) : 1;
     a.chem_in = nullptr;
     // emitted path: batches that share their rate coefficients (block = one layer of 128 columns, vk_emit_rt.cuh)
     if (c->net->emit && emit_env && c->opts.rhs_order < 2 && c->k_cs == 0 && c->ncol >= 32) {
