@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--columns", type=int, default=N_COLUMNS)
+    ap.add_argument("--groups", type=int, default=None, help="column groups (streams) of the device-resident runner; default: ensemble.auto_groups")
     ap.add_argument("--refine", type=int, default=-1, help="iterative refinement of the linear solves: -1 = the product default (auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=None,
@@ -329,8 +330,9 @@ def main():
     atm_common = dict(kw)
     # every column starts like a fresh reference run: its own (re-weighted) state with dt = dttry (vulcan_cfg.dttry, store.py:32)
     dt0 = float(cfg["dttry"])
-    runner = ensemble.EnsembleRunner(case.net, case.nz, y, np.full(hi - lo, dt0), atm_common, kzz, case.k, cfg, st["compo"],
-                                     atom_ini, st["n_0"], device=local_rank, refine=args.refine)
+    # the public ensemble runner: column groups on separate streams (ensemble.auto_groups), advanced concurrently
+    runner = ensemble.GroupedEnsembleRunner(case.net, case.nz, y, np.full(hi - lo, dt0), atm_common, kzz, case.k, cfg, st["compo"],
+                                            atom_ini, st["n_0"], device=local_rank, refine=args.refine, n_groups=args.groups)
     ncol = hi - lo
 
     def barrier():
@@ -340,7 +342,7 @@ def main():
 
     # ---- device-resident loop ------------------------------------------------------------------------------------
     runner.run(args.warmup)
-    runner.col.ens_set_state(y, np.full(ncol, dt0))         # every timed run starts from the same state
+    runner.set_state(y, np.full(ncol, dt0))                 # every timed run starts from the same state
     runner.run(1)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -348,7 +350,7 @@ def main():
     barrier()
     sampler.mark_begin()
     t_wall0 = time.time()
-    ms = runner.run(args.steps)                              # CUDA events on the handle's stream bracket exactly K steps
+    ms = runner.run(args.steps)                              # CUDA events on every group's stream bracket exactly K steps: the slowest group
     barrier()
     wall = time.time() - t_wall0
     sampler.mark_end()
@@ -361,33 +363,39 @@ def main():
     s = runner.state(want_y=False)
 
     # ---- per-kernel time of the dominant kernel (factor) for the roofline: CUDA events inside the step ---------------
-    fac_ms, tot_ms = [], []
-    for _ in range(3):
-        runner.run(1)
-        a, b = runner.col.last_kernel_ms()
-        tot_ms.append(a)
-    # ev1..ev2 of the last step bracket the factor kernel
+    # one group (stream): ev1..ev2 of the last step bracket the factor kernel inside the step.  Several groups: their kernels overlap inside
+    # the step, so the kernel is timed on every group's resident state alone (vk_debug_time_kernel, CUDA events on the group's stream, the
+    # step's own launch arguments) and the launches are summed - the burst peak applies to that number
     import ctypes
     fa, fb = ctypes.c_float(0), ctypes.c_float(0)
-    runner.col.lib.vk_last_kernel_ms(runner.col.handle, ctypes.byref(fa), ctypes.byref(fb))
+    if runner.n_groups == 1:
+        for _ in range(3):
+            runner.run(1)
+        runner.col.lib.vk_last_kernel_ms(runner.col.handle, ctypes.byref(fa), ctypes.byref(fb))
+        factor_ms, factor_how = float(fb.value), "CUDA events around the kernel inside the step"
+    else:
+        runner.run(1)
+        factor_ms = float(sum(r.col.time_kernel(2, 3) for r in runner.runners))
+        factor_how = "sum over the %d column groups, each group's launch timed alone on its resident state (inside the step the groups overlap)" % runner.n_groups
 
     # ---- the HBM-side kernels of the step, each timed alone on the resident state (library profiling aid vk_debug_time_kernel,
     # CUDA events on the column stream; scripts/kernel_times.py).  Supplementary: never allowed to break the bench line.
     kernel_ms = {}
     try:
-        lib = runner.col.lib
-        lib.vk_debug_time_kernel.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
-        lib.vk_debug_time_kernel.restype = ctypes.c_int
-        for which, name in ((0, "lhs_ml_kernel"), (1, "rhs_warp_kernel"), (6, "emitted chemdf kernel (part of the rhs line)"),
+        for which, name in ((0, "lhs: Jacobian + diagonal / couplings (emitted negjac + lhs_diag_kernel, or lhs_ml_kernel)"), (1, "rhs: chemdf + transport stencil (emitted chemdf + rhs_stencil_kernel, or rhs_warp_kernel)"), (6, "emitted chemdf kernel (part of the rhs line)"),
                             (7, "emitted Jacobian kernel (part of the lhs line)"),
                             (3, "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)"),
                             (4, "lu_solve_kernel (forward + backward)")):
-            msk = ctypes.c_float(0)
-            if lib.vk_debug_time_kernel(runner.col.handle, which, 3, ctypes.byref(msk)) == 0 and msk.value > 0:
-                kernel_ms[name] = float(msk.value)
+            try:
+                msv = float(sum(r.col.time_kernel(which, 3) for r in runner.runners))      # every group's launch, timed alone
+            except Exception:
+                continue
+            if msv > 0:
+                kernel_ms[name] = msv
     except Exception:
         kernel_ms = {}
 
+    runner_groups = runner.n_groups
     # ---- the one collective: final gather of the mixing ratios ----------------------------------------------------------
     fin = runner.state(want_y=True)
     ymix_local = fin["y"] / fin["y"].sum(axis=2, keepdims=True)
@@ -396,7 +404,7 @@ def main():
     # ---- e2e through the reference-facing call (vk_ros2_solve on HOST buffers, pinned), H2D + D2H inside the timed region ------
     # the public API for large batches is ensemble.PipelinedHostSolver: column groups on separate streams so that copies overlap
     # the kernels of the other groups
-    runner.col.close()
+    runner.close()
     nv = ncol * case.nz * case.net.ni
     pin = [torch.empty(nv, dtype=torch.float64).pin_memory() for _ in range(4)]
     hy, hm, hs, ho = [p.numpy() for p in pin]
@@ -425,24 +433,26 @@ def main():
         # kernels of one step: rhs x2, lhs, factor, solve x2, refinement (forced: resid + solve + axpy per pass and stage; auto: init + resid +
         # 4 x (solve, axpy, resid, select) per stage - blocks of columns below refine_dt_min exit at once), epilogue, clip, control, apply
         n_ref = 2 * 3 * refine if refine > 0 else (2 * (2 + 4 * 4) if refine == -1 else (2 * (2 + 4 * -refine) if refine < 0 else 0))
-        launches_per_step = 2 + 1 + 1 + 2 + n_ref + 1 + 1 + 1 + 1
+        # (rhs = emitted chemdf + layer scalars + stencil, lhs = emitted Jacobian + diagonal kernel for groups >= 32 columns of a registered network)
+        emitted = (ncol // runner_groups) >= 32
+        launches_per_step = (2 * 3 + 2 if emitted else 2 + 1) + 1 + 2 + n_ref + 1 + 1 + 1 + 1
         line = {
             "metric": "ensemble column-steps/s", "value": value, "unit": "column-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if ncols_total == N_COLUMNS else WORKLOAD.replace("4096", str(ncols_total)),
                        "partition": "columns partitioned across %d GPU(s), no collective in the step" % world, "refine": refine,
-                       "columns_per_gpu": ncol, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
+                       "columns_per_gpu": ncol, "column_groups": runner_groups, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
                        "accepted_fraction": float(np.sum(s["n_accept"])) / float(np.sum(s["n_accept"]) + np.sum(s["n_reject"]))},
             "e2e": {"value": e2e_value, "unit": "column-steps/s", "h2d_bytes_per_step": int(2 * nv * 8 * world + 8 * ncols_total),
                     "d2h_bytes_per_step": int(2 * nv * 8 * world + 12 * ncols_total)},
-            "gpu_launches": launches_per_step * args.steps,
+            "gpu_launches": launches_per_step * args.steps * runner_groups,
             "clocks": clocks, "wall_s_timed_region": wall,
             "final_gather_rows": None if gathered is None else int(gathered.shape[0]),
         }
         # roofline of the dominant kernel (block-tridiagonal factorisation: FP64 pipe bound)
         peak = measured_fp64_peak(device)
-        fms = float(fb.value)
+        fms = factor_ms
         flops = ncol * FLOP_FACTOR(nz, ni)
         # DRAM traffic of the kernel is not measurable without a profiler (a run under ncu is never a bench value): null here; the ncu
         # capture of the same kernel is committed under profiles/ and quoted in DESIGN.md section 6
@@ -451,8 +461,8 @@ def main():
                             "achieved": flops / (fms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                             "frac": flops / (fms * 1e-3) / 1e12 / peak, "traffic": traffic,
                             "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                            "flops_per_column_step": FLOP_FACTOR(nz, ni), "kernel_ms": fms,
-                            "share_of_step": fms / float(np.mean(tot_ms))}
+                            "flops_per_column_step": FLOP_FACTOR(nz, ni), "kernel_ms": fms, "kernel_ms_how": factor_how,
+                            "share_of_step": fms / (ms_max / args.steps)}
         # HBM roofline of the streaming kernels (north_star: "achieved HBM GB/s for the rate/RHS/diffusion kernels"), algorithmic bytes
         # per column as DESIGN.md section 4 states them; peak = MEASURED_PEAKS.json (driver-written copy bandwidth) or the recipe's fallback
         try:
@@ -461,8 +471,8 @@ def main():
             if os.path.exists(pk):
                 hbm_peak, hbm_src = float(json.load(open(pk))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
             nip = ((ni + 23) // 24) * 24 if ni > 48 else 48          # padded block size the kernels are instantiated for (48 / 72 / 96 / 120)
-            alg = {"lhs_ml_kernel": nz * nip * nip * 8.0 + nz * ni * 8.0,                        # writes D (+ up, dn), reads y; k is shared (L2)
-                   "rhs_warp_kernel": 2.0 * nz * ni * 8.0,                                       # reads y, writes f; k is shared (L2)
+            alg = {"lhs: Jacobian + diagonal / couplings (emitted negjac + lhs_diag_kernel, or lhs_ml_kernel)": nz * nip * nip * 8.0 + nz * ni * 8.0,                        # writes D (+ up, dn), reads y; k is shared (L2)
+                   "rhs: chemdf + transport stencil (emitted chemdf + rhs_stencil_kernel, or rhs_warp_kernel)": 2.0 * nz * ni * 8.0,                                       # reads y, writes f; k is shared (L2)
                    "emitted chemdf kernel (part of the rhs line)": 2.0 * nz * ni * 8.0,          # reads y, writes chemdf; k is shared (L2)
                    "emitted Jacobian kernel (part of the lhs line)": nz * ni * nip * 8.0 + nz * ni * 8.0,   # writes the ni dense rows of D, reads y
                    "lu_solve_kernel (first solve: backward sweep, forward fused into the factorisation)": 1.0 * nz * nip * (nip + 2) * 8.0,

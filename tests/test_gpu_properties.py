@@ -115,3 +115,27 @@ def test_pipelined_host_solver_matches_single_handle(monkeypatch):
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
     assert not outs[0][3].any() and np.all(outs[0][2] > 0)
+
+
+def test_grouped_ensemble_runner_matches_one_handle():
+    """ensemble.GroupedEnsembleRunner (column groups on separate streams, advanced concurrently from host threads): every column ends exactly
+    where it ends in one handle - columns are independent and both group sizes take the same kernels"""
+    from vulcan_b200 import ensemble
+    c = Case("HD189", 0)
+    ncol = 80
+    kz, met, co = [a[:ncol] for a in ensemble.sweep_grid()]
+    y, atom_ini = ensemble.synthetic_columns(c.st["y_ini"], c.st["n_0"], c.st["compo"], c.cfg["atom_list"], kz, met, co)
+    kw = c.atm_kwargs()
+    kzz = kz[:, None] * np.asarray(kw["Kzz"])[None, :]
+    dt = np.full(ncol, float(c.cfg["dttry"]))
+    one = ensemble.EnsembleRunner(c.net, c.nz, y, dt, dict(kw), kzz, c.k, c.cfg, c.st["compo"], atom_ini, c.st["n_0"])
+    two = ensemble.GroupedEnsembleRunner(c.net, c.nz, y, dt, dict(kw), kzz, c.k, c.cfg, c.st["compo"], atom_ini, c.st["n_0"], n_groups=2)
+    assert two.n_groups == 2
+    one.run(25)
+    two.run(25)
+    a, b = one.state(), two.state()
+    for key in ("n_accept", "n_reject", "t", "dt", "y"):
+        assert np.array_equal(a[key], b[key]), key
+    assert a["n_accept"].min() > 10
+    two.close()
+    one.col.close()

@@ -89,6 +89,70 @@ class EnsembleRunner(object):
         return self.col.ens_get_state(want_y)
 
 
+def auto_groups(ncol):
+    """column groups for GroupedEnsembleRunner: two from 256 columns on.  Measured on a B200 (HD189 network, ms per step with 1 / 2 / 4 / 8
+    groups): 512 columns 8.09 / 7.25 / 7.28 / -, 1024: 15.1 / 13.5 / 13.3 / -, 2048: 27.5 / 26.7 / 26.3 / 26.7, 4096: 54.0 / 52.2 / 52.8 /
+    52.4 - two groups take most of the gain and keep every launch large (8 groups of 512 columns are 1.7 waves of the factor kernel each)"""
+    return 2 if ncol >= 256 else 1
+
+
+class GroupedEnsembleRunner(object):
+    """EnsembleRunner over G column groups - one vk_column handle and stream per group, advanced concurrently from G host threads.  The
+    kernels of a step are bound by different units (factorisation: FP64 pipe, solves: HBM, emitted chemistry: issue latency), and a batch
+    leaves tails (512 columns are 1.7 waves of the factor kernel's 296 resident blocks): with several groups in flight the tail of one
+    group's kernel runs next to another group's kernel of another kind.  Same arithmetic per column as one handle (columns are
+    independent; the kernels a group takes depend on its size only through the >= 32 column threshold of the emitted kernels)."""
+
+    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=-1, n_groups=None):
+        self.ncol = y.shape[0]
+        G = auto_groups(self.ncol) if n_groups is None else max(1, min(int(n_groups), self.ncol))
+        self.bounds = [partition(self.ncol, G, g) for g in range(G)]
+        dt = np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,))
+        self.runners = [EnsembleRunner(network, nz, y[lo:hi], np.ascontiguousarray(dt[lo:hi]), dict(atm_common), kzz[lo:hi], k, cfg, compo,
+                                       atom_ini[lo:hi], n_0, device=device, refine=refine) for lo, hi in self.bounds]
+        self.col = self.runners[0].col          # (profiling aids address one handle)
+        self.ni = network.ni
+
+    @property
+    def n_groups(self):
+        return len(self.runners)
+
+    def run(self, n_steps):
+        """n_steps attempted steps of every column; returns the device time (ms) of the slowest group's stream (the groups run concurrently)"""
+        if len(self.runners) == 1:
+            return self.runners[0].run(n_steps)
+        import threading
+        ms = [0.0] * len(self.runners)
+        err = []
+
+        def one(g):
+            try:
+                ms[g] = self.runners[g].run(n_steps)
+            except Exception as e:          # surfaced in the calling thread
+                err.append(e)
+        th = [threading.Thread(target=one, args=(g,)) for g in range(len(self.runners))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if err:
+            raise err[0]
+        return max(ms)
+
+    def set_state(self, y, dt):
+        dt = np.broadcast_to(np.asarray(dt, dtype=np.float64), (self.ncol,))
+        for r, (lo, hi) in zip(self.runners, self.bounds):
+            r.col.ens_set_state(y[lo:hi], np.ascontiguousarray(dt[lo:hi]))
+
+    def state(self, want_y=True):
+        parts = [r.state(want_y) for r in self.runners]
+        return {key: (None if parts[0][key] is None else np.concatenate([p[key] for p in parts], axis=0)) for key in parts[0]}
+
+    def close(self):
+        for r in self.runners:
+            r.col.close()
+
+
 class SteadyEnsemble(EnsembleRunner):
     """An ensemble advanced to per-column steady state entirely on the device (vk_ens_setup_steady / vk_ens_run_steady): every column
     stops on its own convergence test (Integration.stop / conv, op.py:1018-1087) and is frozen from then on; per column (steps, t, status)
