@@ -17,22 +17,26 @@ struct EpiArgs {
     const int *act;
 };
 
-__global__ void __launch_bounds__(128) epilogue_kernel(EpiArgs a)
+// one WARP per (column, layer), 4 layers per block: the layer sum (numpy's pairwise association, np_pairwise_group8) is formed by 8 lanes
+// instead of one thread walking the row while 127 wait
+#define EPI_WPB 4
+__global__ void __launch_bounds__(EPI_WPB * 32) epilogue_kernel(EpiArgs a, int n_layers_total)
 {
     extern __shared__ double sm[];
     const int nz = a.nz, ni = a.ni;
-    const int col = blockIdx.x / nz, j = blockIdx.x % nz;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lay = blockIdx.x * EPI_WPB + w;
+    if (lay >= n_layers_total) return;
+    const int col = lay / nz, j = lay - col * nz;
     if (a.act && !a.act[col]) return;
-    const int tid = threadIdx.x;
-    double *srow = sm;          // ni
-    double *tmp = sm + ni;      // ni
-    __shared__ double ssum;
-    const size_t base = ((size_t)col * nz + j) * ni;
+    double *srow = sm + (size_t)w * (2 * ni + 2);   // ni
+    double *tmp = srow + ni;                        // ni (scratch of the gas-only sum)
+    const size_t base = (size_t)lay * ni;
     const double r = 1. + 1. / sqrt(2.);
     const double c1 = 3. / (2. * r), c2 = 1 / (2. * r);
     double dmax = 0.0;
     bool has = false;
-    for (int i = tid; i < ni; i += blockDim.x) {
+    for (int i = lane; i < ni; i += 32) {
         const size_t q = base + i;
         double s = a.y[q] + c1 * a.k1[q] + c2 * a.k2[q];                   // op.py:2932
         if (j == 0)
@@ -52,17 +56,24 @@ __global__ void __launch_bounds__(128) epilogue_kernel(EpiArgs a)
         a.sol[q] = s;
         srow[i] = s;
     }
-    // block max of non-negative doubles (NaN has the largest bit pattern and therefore propagates like np.amax)
+    // warp max of non-negative doubles (NaN has the largest bit pattern and therefore propagates like np.amax)
     unsigned long long bits = has ? (unsigned long long)__double_as_longlong(dmax) : 0ull;
     for (int off = 16; off > 0; off >>= 1) {
         unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, off);
         bits = (o > bits) ? o : bits;
     }
-    if ((tid & 31) == 0 && bits) atomicMax(a.delta_bits + col, bits);
-    __syncthreads();
-    if (tid == 0) ssum = row_sum(srow, ni, a.n_gas, a.gas_indx, tmp);       // op.py:2990-2993
-    __syncthreads();
-    for (int i = tid; i < ni; i += blockDim.x) a.ymix_out[base + i] = srow[i] / ssum;
+    if (lane == 0 && bits) atomicMax(a.delta_bits + col, bits);
+    __syncwarp();
+    double ssum;                                                            // op.py:2990-2993
+    if (a.n_gas > 0) {
+        ssum = 0.0;
+        if (lane == 0) ssum = row_sum(srow, ni, a.n_gas, a.gas_indx, tmp);
+        ssum = __shfl_sync(0xffffffffu, ssum, 0);
+    } else {
+        ssum = np_pairwise_group8(srow, ni, lane < 8);
+        ssum = __shfl_sync(0xffffffffu, ssum, 0);
+    }
+    for (int i = lane; i < ni; i += 32) a.ymix_out[base + i] = srow[i] / ssum;
 }
 
 int launch_epilogue(vk_column *c)
@@ -75,7 +86,8 @@ int launch_epilogue(vk_column *c)
     a.o = c->opts;
     a.n_gas = c->atm.n_gas; a.gas_indx = c->atm.gas_indx; a.act = c->act;
     VK_CUDA(cudaMemsetAsync(c->delta, 0, sizeof(double) * c->ncol, c->stream));
-    epilogue_kernel<<<c->ncol * c->nz, 128, sizeof(double) * 2 * c->ni, c->stream>>>(a);
+    const int n_layers = c->ncol * c->nz;
+    epilogue_kernel<<<(n_layers + EPI_WPB - 1) / EPI_WPB, EPI_WPB * 32, sizeof(double) * EPI_WPB * (2 * c->ni + 2), c->stream>>>(a, n_layers);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
 }
@@ -138,10 +150,19 @@ __global__ void __launch_bounds__(256) clip_kernel(ClipArgs a)
             if (!(a.atom_skip && a.atom_skip[at])) a.atom_sum[(size_t)col * na + at] = red[(2 + at) * nt];
         a.any_negative[col] = anyb;
     }
-    // ymix = y / sum_gas(y) per layer, numpy pairwise order
-    for (int j = tid; j < nz; j += nt) {
-        double s = row_sum(yc + (size_t)j * ni, ni, a.n_gas, a.gas_indx, nullptr);
-        for (int i = 0; i < ni; i++) a.ymix_out[((size_t)col * nz + j) * ni + i] = yc[(size_t)j * ni + i] / s;
+    // ymix = y / sum_gas(y) per layer, numpy pairwise order: one warp per layer (8 lanes form the sum, the row is written coalesced)
+    const int w = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    for (int j = w; j < nz; j += nw) {
+        const double *row = yc + (size_t)j * ni;
+        double s;
+        if (a.n_gas > 0) {
+            s = 0.0;
+            if (lane == 0) s = row_sum(row, ni, a.n_gas, a.gas_indx, nullptr);
+        } else {
+            s = np_pairwise_group8(row, ni, lane < 8);
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        for (int i = lane; i < ni; i += 32) a.ymix_out[((size_t)col * nz + j) * ni + i] = row[i] / s;
     }
 }
 
