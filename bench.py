@@ -316,6 +316,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU path (use --impl reference for the CPU arm)")
     args.warmup = max(args.warmup, 3)
+    # one process per GPU: this rank's threads and page-locked buffers on the GPU's NUMA node (best effort, reported in config.numa)
+    numa = ensemble.bind_to_gpu_numa_node(local_rank) if world > 1 else {"node": None}
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -442,7 +444,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if ncols_total == N_COLUMNS else WORKLOAD.replace("4096", str(ncols_total)),
                        "partition": "columns partitioned across %d GPU(s), no collective in the step" % world, "refine": refine,
-                       "columns_per_gpu": ncol, "column_groups": runner_groups, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
+                       "columns_per_gpu": ncol, "column_groups": runner_groups, "numa_rank0": numa, "l2": "per-step working set (2 x %.1f MB per column) exceeds L2: no flush needed" % (nz * 72 * 72 * 8 / 1e6),
                        "accepted_fraction": float(np.sum(s["n_accept"])) / float(np.sum(s["n_accept"]) + np.sum(s["n_reject"]))},
             "e2e": {"value": e2e_value, "unit": "column-steps/s", "h2d_bytes_per_step": int(2 * nv * 8 * world + 8 * ncols_total),
                     "d2h_bytes_per_step": int(2 * nv * 8 * world + 12 * ncols_total)},

@@ -58,6 +58,17 @@ static int pad_block(int ni)
     return 24 * ((ni + 23) / 24);
 }
 
+// wait for the handle's stream.  Batches: through a blocking-sync event - the calling thread sleeps.  Several ranks x several column-group
+// threads per rank outnumber the host cores of a GPU box (8 ranks x 4 groups on 16 threads); spinning waiters then take the cores away from
+// the threads that still have launches to issue.  One column: a spinning wait (the wake-up latency of a blocking wait is of the order of a step)
+int stream_wait(vk_column *c)
+{
+    if (c->ncol < 32 || !c->ev_sync) { VK_CUDA(cudaStreamSynchronize(c->stream)); return VK_OK; }
+    VK_CUDA(cudaEventRecord(c->ev_sync, c->stream));
+    VK_CUDA(cudaEventSynchronize(c->ev_sync));
+    return VK_OK;
+}
+
 // device-side sequence of one attempted step; y, ymix, dt already resident
 int vk_step_device_impl(vk_column *c)
 {
@@ -347,6 +358,7 @@ int vk_column_create(vk_network *net, int nz, int ncol, vk_column **out)
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev2);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev3);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
     double **vecs[] = {&c->y, &c->ymix, &c->sol, &c->ymix_out, &c->f, &c->k1, &c->k2, &c->yk2, &c->rhs, &c->res, &c->dx, &c->xn};
     for (double **v : vecs)
         if (e == cudaSuccess) e = cudaMalloc((void **)v, sizeof(double) * nv);
@@ -403,6 +415,7 @@ void vk_column_destroy(vk_column *c)
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->ev2) cudaEventDestroy(c->ev2);
     if (c->ev3) cudaEventDestroy(c->ev3);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     if (c->stream) cudaStreamDestroy(c->stream);
     c->atm_allocs.~vector();
     c->opt_allocs.~vector();
@@ -603,7 +616,7 @@ int vk_ros2_solve(vk_column *c, const double *y, const double *ymix, const doubl
     VK_CUDA(cudaMemcpyAsync(direct ? ymix_out : ho, c->ymix_out, sizeof(double) * nv, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(hdl, c->delta, sizeof(double) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
     VK_CUDA(cudaMemcpyAsync(hst, c->status, sizeof(int) * c->ncol, cudaMemcpyDeviceToHost, c->stream));
-    VK_CUDA(cudaStreamSynchronize(c->stream));
+    { int rcw = stream_wait(c); if (rcw) return rcw; }
     if (!direct) {
         memcpy(sol, hs, sizeof(double) * nv);
         memcpy(ymix_out, ho, sizeof(double) * nv);

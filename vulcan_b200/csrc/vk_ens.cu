@@ -289,8 +289,7 @@ int vk_ens_run(vk_column *c, int n_steps)
     }
     (void)e0; (void)e3;
     cudaEventRecord(run1, c->stream);
-    cudaError_t ce = cudaStreamSynchronize(c->stream);
-    if (rc == VK_OK && ce != cudaSuccess) rc = cuda_fail(ce, "vk_ens_run");
+    { const int rcw = stream_wait(c); if (rc == VK_OK) rc = rcw; }        // (batches: blocking wait, the host thread sleeps)
     if (rc == VK_OK) cudaEventElapsedTime(&c->last_ms_total, run0, run1);
     if (rc == VK_OK && n_steps > 0) cudaEventElapsedTime(&c->last_ms_factor, c->ev1, c->ev2);   // factor kernel of the last step
     cudaEventDestroy(run0);

@@ -133,6 +133,7 @@ struct vk_column {
     int nz, ncol, ni, nr, nip;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1, ev2, ev3;
+    cudaEvent_t ev_sync;        // blocking-sync event: host threads of big batches sleep instead of spinning while the stream drains
     float last_ms_total, last_ms_factor;
     bool last_fused;            // the last step took the fused assembly + factorisation kernel
     // state
@@ -187,6 +188,7 @@ const void *emit_lookup(unsigned long long hash, int ni, int nr);
 int launch_jac_emitted(vk_column *c, const double *y_dev, double *D_out, double *ysum_out);
 bool emit_has_jac(const void *entry);
 int launch_chem_emitted(vk_column *c, const double *y_dev, const double *k1, double *chem_out, double *ysum_out, double *yk2_out);
+int stream_wait(vk_column *c);
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status, const double *fwd_rhs = nullptr);
 int launch_solve(vk_column *c, const double *F, const double *up, const double *dn, const double *rhs, double *x, double *z,
                  const int *act = nullptr, const int *fwd_done = nullptr);

@@ -392,8 +392,7 @@ int vk_ens_run_steady(vk_column *c, int max_iterations, int *n_active_left)
         count_active_kernel<<<1, 256, 0, c->stream>>>(c->ncol, s.act, s.n_left);
     }
     cudaEventRecord(run1, c->stream);
-    cudaError_t ce = cudaStreamSynchronize(c->stream);
-    if (rc == VK_OK && ce != cudaSuccess) rc = cuda_fail(ce, "vk_ens_run_steady");
+    { const int rcw = stream_wait(c); if (rc == VK_OK) rc = rcw; }        // (batches: blocking wait, the host thread sleeps)
     if (rc == VK_OK) cudaEventElapsedTime(&c->last_ms_total, run0, run1);
     if (rc == VK_OK && n_active_left) VK_CUDA(cudaMemcpy(n_active_left, s.n_left, sizeof(int), cudaMemcpyDeviceToHost));
     cudaEventDestroy(run0);

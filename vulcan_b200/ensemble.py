@@ -89,6 +89,56 @@ class EnsembleRunner(object):
         return self.col.ens_get_state(want_y)
 
 
+def bind_to_gpu_numa_node(device):
+    """One process per GPU on a multi-socket host: run this rank's host threads on the CPUs of the GPU's NUMA node and prefer that node for
+    its page-locked buffers (first touch), so that the H2D / D2H copies of the host-buffer path do not cross the socket interconnect.
+    Call before the pinned buffers and the worker threads exist.  Returns what was done (dict) - everything is best effort: a container
+    may hide the topology or confine the process to CPUs of another node."""
+    import ctypes
+    import os
+    info = {"device": int(device), "node": None, "cpus_bound": None, "mempolicy": None}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(int(device))).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                  # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+    except Exception as e:
+        info["error"] = "no NUMA node for the device: %s" % e
+        return info
+    info["node"] = node
+    if node < 0:
+        return info
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        both = cpus & allowed
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            info["cpus_bound"] = len(both)
+        else:
+            info["cpus_bound"] = 0 if not both else len(both)
+    except Exception as e:
+        info["error"] = "affinity: %s" % e
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238        # x86_64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+        info["mempolicy"] = "preferred node %d" % node if rc == 0 else "set_mempolicy failed (errno %d)" % ctypes.get_errno()
+    except Exception as e:
+        info["mempolicy"] = "unavailable: %s" % e
+    return info
+
+
 def auto_groups(ncol):
     """column groups for GroupedEnsembleRunner: two from 256 columns on.  Measured on a B200 (HD189 network, ms per step with 1 / 2 / 4 / 8
     groups): 512 columns 8.09 / 7.25 / 7.28 / -, 1024: 15.1 / 13.5 / 13.3 / -, 2048: 27.5 / 26.7 / 26.3 / 26.7, 4096: 54.0 / 52.2 / 52.8 /
