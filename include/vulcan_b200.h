@@ -105,7 +105,10 @@ typedef struct {
 } vk_atm_view;
 int vk_set_atm(vk_column *col, const vk_atm_view *atm);
 
-/* rate coefficients: var.k packed [ncol][nz][nr+1] (or one copy when shared != 0) */
+/* rate coefficients: var.k packed.  shared = 1: one copy [nz][nr+1] serves every column; 0: [ncol][nz][nr+1]; 2: [ncol][nz][nr+1] with the
+ * caller's promise that all rows outside the network's photolysis / ionisation / condensation sections are identical in every column (one
+ * T-P profile; only the rows the run itself rewrites - J rates, condensation growth rates - differ): the emitted chemistry kernels then
+ * apply to the batch.  vk_set_k_rows with per-column values for any other row withdraws the promise. */
 int vk_set_k(vk_column *col, const double *k, int shared);
 /* rate coefficients computed ON the device from temperature and total number density (needs vk_rates_set):
  * Tco, M [ncol][nz], or [nz] when shared != 0.  Photolysis rows are zero until vk_photo_update fills them. */

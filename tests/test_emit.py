@@ -44,7 +44,7 @@ def _evaluate(src, y, M, k):
             if m:
                 out[:, int(m.group(1))] = ns["f" + m.group(2)]
                 continue
-            stmt = re.sub(r"K\((\d+)\)", r"k[:, \1]", stmt)
+            stmt = re.sub(r"KG?\((\d+)\)", r"k[:, \1]", stmt)
             stmt = re.sub(r"Y\((\d+)\)", r"yx[:, \1]", stmt)
             exec(stmt, {"k": k, "yx": yx, "pow": np.power}, ns)
     return out
@@ -97,7 +97,7 @@ def _evaluate_jac(src, y, M, k, nip):
                     name, src_ = part.split(" = ")
                     ns[name] = rT[int(src_[2:-1])].copy()
                 continue
-            stmt = re.sub(r"K\((\d+)\)", r"k[:, \1]", stmt)
+            stmt = re.sub(r"KG?\((\d+)\)", r"k[:, \1]", stmt)
             stmt = re.sub(r"R\((\d+)\)", r"rT[\1]", stmt)
             stmt = re.sub(r"= 0\.0$", "= zeros()", stmt)
             exec(stmt, {"k": k, "rT": rT, "zeros": lambda: np.zeros(nz)}, ns)
@@ -137,6 +137,21 @@ def test_hash_and_registry_of_the_baseline_networks():
         t = net.tables()
         assert emit.table_hash(t) == emit._fnv_fast(t)
         assert emit.has_kernel(net), "%s: tables not registered under vulcan_b200/networks (python -m vulcan_b200.emit <network file>)" % tag
+
+
+def test_dynamic_rows_are_read_per_column():
+    """the k indices a run rewrites per column (photolysis / ionisation / condensation sections) are emitted as KG(i) - read from the
+    thread's own column - and every other index as K(i) - the block's shared copy of the row"""
+    c = Case("HD189", 0)
+    t = c.net.tables()
+    src, h = emit.emit_chemdf(t, "HD189")
+    dyn = set(int(x) for x in t["dyn_k"])
+    photo = {rid + d for _, _, rid in c.net.photo_table() for d in (0, 1)}
+    assert photo <= dyn and len(photo) > 0
+    kg = {int(x) for x in re.findall(r"KG\((\d+)\)", src)}
+    ks = {int(x) for x in re.findall(r"(?<!G)K\((\d+)\)", src.replace("KG(", "G("))}
+    assert kg and kg <= dyn and not (ks & dyn)
+    assert ("dyn_%016x[] = {" % h) in src
 
 
 def test_terms_out_of_reaction_order_are_refused():

@@ -313,6 +313,58 @@ def test_rhs_emitted_batch(tag, step):
     assert np.allclose(d1, d2, rtol=5e-2 if tag.startswith("JupiterFix") else 1e-3, atol=1e-12)
 
 
+@pytest.mark.parametrize("tag,step", [p for p in [("HD189", 100), ("Jupiter", 30), ("EarthS", 100)] if have(p[0], "step%04d.npz" % p[1])])
+def test_emitted_batch_with_per_column_photolysis_rows(tag, step):
+    """per-column k whose thermal rows are identical (one T-P profile) and whose photolysis / condensation rows differ per column - what a
+    steady-state ensemble with photolysis holds (vk_set_k shared = 2): the emitted kernels read the static rows from the block's shared copy
+    (K) and the dynamic rows from the thread's own column (KG).  chemdf bit-identical to the oracle with THAT column's k, Jacobian 4e-15;
+    per-column values for a thermal row (vk_set_k_rows) withdraw the promise and the batch falls back to the table-driven kernels."""
+    from oracle import Oracle
+    c = Case(tag, step)
+    o = Oracle(c.net)
+    atm = o.make_atm(**c.atm_kwargs())
+    ncol = 40
+    rng = np.random.default_rng(11)
+    y = c.y[None] * (1.0 + 0.05 * rng.uniform(-1.0, 1.0, size=(ncol, 1, c.y.shape[1])))
+    dyn = np.asarray(c.net.tables()["dyn_k"])
+    assert len(dyn) > 0
+    kk = np.repeat(c.k[None], ncol, axis=0)
+    kk[:, :, dyn] *= rng.uniform(0.8, 1.25, size=(ncol, 1, len(dyn)))                     # mild: every column stays a state a run could be in
+    kk[0] = c.k
+    y[0] = c.y
+    col = _columns(c, ncol)
+    col.set_k(kk, static_rows_shared=True)
+    chem, diff = col.eval_rhs(y)
+    dt = np.full(ncol, min(c.dt, 1e2))
+    D, up, dn = col.eval_lhs(y, dt)
+    for q in (0, 13, 39):
+        assert np.array_equal(chem[q], o.chemdf(y[q], c.st["M"], kk[q])), q
+        Do, upo, dno = o.lhs(atm, y[q], kk[q], float(dt[q]))
+        scale = np.abs(Do).max(axis=2, keepdims=True)
+        assert np.max(np.abs(D[q] - Do) / np.maximum(scale, 1e-300)) < 4e-15, q
+        assert np.array_equal(up[q], upo) and np.array_equal(dn[q], dno)
+    ymix = y / y.sum(axis=2, keepdims=True)
+    s1, m1, d1, st1 = col.ros2_solve(y, ymix, dt)
+    tab = _columns(c, ncol)
+    tab.set_k(kk)                                            # no promise: table-driven kernels
+    s2, m2, d2, st2 = tab.ros2_solve(y, ymix, dt)
+    m = np.abs(s2) > 1e-8 * np.abs(s2).max(axis=2, keepdims=True)
+    err = np.max(np.abs(s1 - s2)[m] / np.abs(s2)[m])
+    print("%s-%d: whole step with per-column photolysis rows, emitted vs table-driven kernels: %.2e" % (tag, step, err))
+    assert err < 1e-4 and np.array_equal(st1, st2)          # (the solve amplifies the 4e-15 of the Jacobian; the strict checks are above)
+    # a thermal row with per-column values: the emitted path must not be taken any more (it would read column 0's value for everybody)
+    therm = int([i for i in range(1, c.nr + 1) if i not in set(dyn.tolist()) and c.k[:, i].any()][0])
+    vals = np.repeat(c.k[:, therm][None, None, :], ncol, axis=0) * np.linspace(0.5, 2.0, ncol)[:, None, None]
+    col.set_k_rows([therm], vals)
+    kk2 = kk.copy()
+    kk2[:, :, therm] = vals[:, 0, :]
+    chem2, _ = col.eval_rhs(y)
+    for q in (0, 13, 39):
+        ref = o.chemdf(y[q], c.st["M"], kk2[q])
+        scale = np.abs(ref).max(axis=1, keepdims=True) + 1e-300
+        assert np.max(np.abs(chem2[q] - ref) / scale) < 1e-9, q                          # (table-driven default order: segmented)
+
+
 @pytest.mark.parametrize("tag,step", PHOTO_CASES, ids=[case_id(p) for p in PHOTO_CASES])
 def test_photolysis(tag, step):
     """compute_tau / compute_flux / compute_J on the GPU vs reference fixture (two consecutive updates)."""

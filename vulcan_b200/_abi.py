@@ -300,15 +300,17 @@ class Columns(object):
                     0 if de is None else len(de), iptr(de))
         check(self.lib.vk_set_atm(self.handle, C.byref(v)))
 
-    def set_k(self, k, shared=None):
-        """k: [nz, nr+1] (shared by all columns) or [ncol, nz, nr+1]."""
+    def set_k(self, k, shared=None, static_rows_shared=False):
+        """k: [nz, nr+1] (shared by all columns) or [ncol, nz, nr+1].  static_rows_shared (per-column k only): the rows outside the network's
+        photolysis / ionisation / condensation sections are identical in every column (one T-P profile) - vk_set_k(shared = 2), the emitted
+        chemistry kernels then apply to the batch."""
         k = f64(k)
         if shared is None:
             shared = (k.ndim == 2)
         want = (self.nz, self.nr + 1) if shared else (self.ncol, self.nz, self.nr + 1)
         if k.shape != want:
             raise ValueError("k: expected %s, got %s" % (want, k.shape))
-        check(self.lib.vk_set_k(self.handle, dptr(k), int(shared)))
+        check(self.lib.vk_set_k(self.handle, dptr(k), 1 if shared else (2 if static_rows_shared else 0)))
         self._k_shared = bool(shared)
 
     def compute_k(self, Tco, M):

@@ -494,17 +494,19 @@ int vk_set_k(vk_column *c, const double *k, int shared)
     if (!c || !k) { set_error("null argument"); return VK_ERR_INVALID; }
     VK_CUDA(cudaSetDevice(c->net->device));
     const size_t per = (size_t)c->nz * (c->nr + 1);
-    const size_t want_cs = shared ? 0 : per;
+    const bool one = (shared == 1);
+    const size_t want_cs = one ? 0 : per;
     if (!c->k || c->k_cs != want_cs || !c->k_set) {
         VK_CUDA(cudaStreamSynchronize(c->stream));
         if (c->k) cudaFree(c->k);
         c->k = nullptr;
-        VK_CUDA(cudaMalloc((void **)&c->k, sizeof(double) * per * (shared ? 1 : c->ncol)));
+        VK_CUDA(cudaMalloc((void **)&c->k, sizeof(double) * per * (one ? 1 : c->ncol)));
         c->k_cs = want_cs;
     }
-    VK_CUDA(cudaMemcpyAsync(c->k, k, sizeof(double) * per * (shared ? 1 : c->ncol), cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->k, k, sizeof(double) * per * (one ? 1 : c->ncol), cudaMemcpyHostToDevice, c->stream));
     VK_CUDA(cudaStreamSynchronize(c->stream));
     c->k_set = true;
+    c->k_static_shared = (shared == 2);
     return VK_OK;
 }
 
@@ -525,8 +527,11 @@ int vk_set_k_rows(vk_column *c, int n_rows, const int *rows, const double *vals)
     if (!c || !c->k_set || n_rows < 0 || (n_rows && (!rows || !vals))) { set_error("bad argument / k not set"); return VK_ERR_INVALID; }
     if (n_rows == 0) return VK_OK;
     VK_CUDA(cudaSetDevice(c->net->device));
-    for (int r = 0; r < n_rows; r++)
+    for (int r = 0; r < n_rows; r++) {
         if (rows[r] < 1 || rows[r] > c->nr) { set_error("reaction id out of range"); return VK_ERR_INVALID; }
+        // per-column values for a row the emitted kernels read from the block's shared copy: the promise of vk_set_k(shared = 2) is gone
+        if (c->k_cs && c->k_static_shared && !emit_row_is_dynamic(c->net->emit, rows[r])) c->k_static_shared = false;
+    }
     const int ncol_k = c->k_cs ? c->ncol : 1;
     const size_t n = (size_t)ncol_k * n_rows * c->nz;
     int *drows = nullptr; double *dvals = nullptr;
@@ -711,7 +716,7 @@ int vk_eval_lhs(vk_column *c, const double *y, const double *dt, double *D, doub
     const char *ej = getenv("VK_EMIT_JAC");
     // batches that the step assembles through the EMITTED Jacobian kernel (vk_chem.cu: launch_lhs) are evaluated the same way here: padded
     // blocks, un-padded on the way out
-    const bool emitted = !(via && atoi(via)) && !(ej && !atoi(ej)) && emit_has_jac(c->net->emit) && c->k_cs == 0 && c->ncol >= 32;
+    const bool emitted = !(via && atoi(via)) && !(ej && !atoi(ej)) && emit_has_jac(c->net->emit) && (c->k_cs == 0 || c->k_static_shared) && c->ncol >= 32;
     if ((via && atoi(via)) || emitted) {
         // parity aid: the blocks as the FUSED assembly + factorisation kernel forms them (producer warps, store_D = always), un-padded
         // on the way out - must be bit-identical to lhs_ml_kernel's (tests/test_gpu_fused.py)

@@ -1391,7 +1391,7 @@ int launch_rhs(vk_column *c, const double *y_dev, double *out_sum, double *out_c
     const int emit_env = ee ? atoi(ee) : 1;
     a.chem_in = nullptr;
     // emitted path: batches that share their rate coefficients (block = one layer of 128 columns, vk_emit_rt.cuh)
-    if (c->net->emit && emit_env && c->opts.rhs_order < 2 && c->k_cs == 0 && c->ncol >= 32) {
+    if (c->net->emit && emit_env && c->opts.rhs_order < 2 && (c->k_cs == 0 || c->k_static_shared) && c->ncol >= 32) {
         const size_t nl = (size_t)c->ncol * c->nz;
         if (!c->chem_tmp) {
             VK_CUDA(cudaMalloc((void **)&c->chem_tmp, sizeof(double) * nl * c->ni));
@@ -1557,7 +1557,7 @@ int launch_lhs(vk_column *c, const double *y_dev, const double *dt_dev, int ld, 
     // emitted path (batches that share their rate coefficients): -J as straight-line code, then the elementwise diagonal / coupling kernel
     const char *ej = getenv("VK_EMIT_JAC");      // (read per call: the parity tests switch it inside one process)
     const int emit_env = ej ? atoi(ej) : 1;
-    if (emit_env && emit_has_jac(c->net->emit) && c->k_cs == 0 && c->ncol >= 32 && ld == c->nip && !getenv("VK_LHS_DEBUG")) {
+    if (emit_env && emit_has_jac(c->net->emit) && (c->k_cs == 0 || c->k_static_shared) && c->ncol >= 32 && ld == c->nip && !getenv("VK_LHS_DEBUG")) {
         const size_t nl = (size_t)c->ncol * c->nz;
         if (!c->ysum_lhs_tmp) VK_CUDA(cudaMalloc((void **)&c->ysum_lhs_tmp, sizeof(double) * nl));
         int rc = launch_jac_emitted(c, y_dev, D_out, c->ysum_lhs_tmp);

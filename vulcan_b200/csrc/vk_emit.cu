@@ -68,10 +68,10 @@ int launch_chem_emitted(vk_column *c, const double *y_dev, const double *k1, dou
 {
     const emitted::EmitEntry *e = static_cast<const emitted::EmitEntry *>(c->net->emit);
     if (!e) { set_error("no emitted chemistry kernel for this network"); return VK_ERR_UNSUPPORTED; }
-    if (c->k_cs != 0) { set_error("the emitted chemistry kernel needs rate coefficients shared by the batch"); return VK_ERR_UNSUPPORTED; }
+    if (c->k_cs != 0 && !c->k_static_shared) { set_error("the emitted chemistry kernel needs rate coefficients shared by the batch"); return VK_ERR_UNSUPPORTED; }
     emitted::EmitArgs a;
     a.nz = c->nz; a.ncol = c->ncol;
-    a.y = y_dev; a.k1 = k1; a.yk2_out = yk2_out; a.k = c->k;
+    a.y = y_dev; a.k1 = k1; a.yk2_out = yk2_out; a.k = c->k; a.k_cs = c->k_cs;
     a.M = c->atm.M; a.M_cs = c->atm.csz;
     a.chem = chem_out; a.ysum = ysum_out; a.n_gas = c->atm.n_gas; a.gas_indx = c->atm.gas_indx; a.act = c->act;
     if (e->fn(a, c->stream)) return cuda_fail(cudaGetLastError(), "emitted chemdf kernel");
@@ -84,14 +84,23 @@ int launch_jac_emitted(vk_column *c, const double *y_dev, double *D_out, double 
 {
     const emitted::EmitEntry *e = static_cast<const emitted::EmitEntry *>(c->net->emit);
     if (!e || !e->jac) { set_error("no emitted Jacobian kernel for this network"); return VK_ERR_UNSUPPORTED; }
-    if (c->k_cs != 0) { set_error("the emitted Jacobian kernel needs rate coefficients shared by the batch"); return VK_ERR_UNSUPPORTED; }
+    if (c->k_cs != 0 && !c->k_static_shared) { set_error("the emitted Jacobian kernel needs rate coefficients shared by the batch"); return VK_ERR_UNSUPPORTED; }
     emitted::EmitJacArgs a;
-    a.nz = c->nz; a.ncol = c->ncol; a.y = y_dev; a.k = c->k;
+    a.nz = c->nz; a.ncol = c->ncol; a.y = y_dev; a.k = c->k; a.k_cs = c->k_cs;
     a.M = c->atm.M; a.M_cs = c->atm.csz; a.D = D_out; a.ysum = ysum_out;
     a.n_gas = c->atm.n_gas_lhs; a.gas_indx = c->atm.gas_indx_lhs; a.act = c->act;
     if (e->jac(a, c->stream)) return cuda_fail(cudaGetLastError(), "emitted Jacobian kernel");
     return VK_OK;
 }
 bool emit_has_jac(const void *entry) { return entry && static_cast<const emitted::EmitEntry *>(entry)->jac != nullptr; }
+// is k index i one of the rows the emitted kernels read per column (photolysis / ionisation / condensation)?
+bool emit_row_is_dynamic(const void *entry, int i)
+{
+    const emitted::EmitEntry *e = static_cast<const emitted::EmitEntry *>(entry);
+    if (!e) return false;
+    for (int q = 0; q < e->n_dyn; q++)
+        if (e->dyn[q] == i) return true;
+    return false;
+}
 
 }  // namespace vk

@@ -21,7 +21,8 @@ struct EmitArgs {
     const double *y;        // [ncol][nz][ni]
     const double *k1;       // stage 2: chemdf(y + k1/r) (op.py:2917); NULL for stage 1
     double *yk2_out;        // stage 2: y + k1/r
-    const double *k;        // [nz][nr+1], shared by the batch
+    const double *k;        // [ncol|1][nz][nr+1]: shared by the batch (k_cs = 0) or per column with identical "static" rows (see KG)
+    size_t k_cs;
     const double *M;        // atm.M [ncol|1][nz]
     size_t M_cs;
     double *chem;           // out [ncol][nz][ni]
@@ -34,7 +35,8 @@ struct EmitArgs {
 struct EmitJacArgs {
     int nz, ncol;
     const double *y;        // [ncol][nz][ni]
-    const double *k;        // [nz][nr+1], shared by the batch
+    const double *k;        // [ncol|1][nz][nr+1]
+    size_t k_cs;
     const double *M;        // atm.M [ncol|1][nz]
     size_t M_cs;
     double *D;              // [ncol][nz][NIP][NIP]
@@ -44,14 +46,16 @@ struct EmitJacArgs {
 };
 typedef int (*EmitLaunch)(const EmitArgs &, cudaStream_t);
 typedef int (*EmitJacLaunch)(const EmitJacArgs &, cudaStream_t);
-struct EmitEntry { unsigned long long hash; int ni, nr; const char *name; EmitLaunch fn; EmitJacLaunch jac; };
+// dyn / n_dyn: the k indices a run rewrites per column (photolysis, ionisation, condensation rows): the emitted code reads those through
+// KG(i) from the thread's own column, everything else through K(i) from the block's shared copy of the row
+struct EmitEntry { unsigned long long hash; int ni, nr; const char *name; EmitLaunch fn; EmitJacLaunch jac; const int *dyn; int n_dyn; };
 // registry of the kernels compiled into this library (vk_emit.cu); looked up by the hash of the uploaded tables in vk_network_create
 void emit_register(const EmitEntry &e);
 const EmitEntry *emit_find(unsigned long long hash, int ni, int nr);
 struct EmitRegistrar {
-    EmitRegistrar(unsigned long long hash, int ni, int nr, const char *name, EmitLaunch fn, EmitJacLaunch jac)
+    EmitRegistrar(unsigned long long hash, int ni, int nr, const char *name, EmitLaunch fn, EmitJacLaunch jac, const int *dyn, int n_dyn)
     {
-        emit_register(EmitEntry{hash, ni, nr, name, fn, jac});
+        emit_register(EmitEntry{hash, ni, nr, name, fn, jac, dyn, n_dyn});
     }
 };
 int emit_set_smem(const void *func, size_t bytes);      // per (function, device) opt-in above 48 KB
@@ -105,7 +109,8 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     double *ks = ys + ((NI) + 1) * VK_EMIT_LD;                                                                           \
     const int j = (int)(blockIdx.x % (unsigned)a.nz), col0 = (int)(blockIdx.x / (unsigned)a.nz) * VK_EMIT_TB;            \
     const int ncb = min(VK_EMIT_TB, a.ncol - col0);                                                                      \
-    for (int i = tid; i <= (NR); i += VK_EMIT_TB) ks[i] = a.k[(size_t)j * ((NR) + 1) + i];                               \
+    for (int i = tid; i <= (NR); i += VK_EMIT_TB) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];       \
+    const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
     {                                                                                                                    \
         const double rr = 1. + 1. / sqrt(2.);                                                                            \
         for (int cc = wrp; cc < VK_EMIT_TB; cc += VK_EMIT_TB / 32) {                                                     \
@@ -132,6 +137,7 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
 // volatile: every use re-reads the broadcast from shared memory.  Without it the compiler keeps k values it will need again in registers and,
 // out of registers, SPILLS them to local memory (2 KB per thread in the Jacobian kernel) - a shared-memory load is cheaper than either
 #define K(i) (*(const volatile double *)(ks + (i)))
+#define KG(i) kg[(i)]
 #define F(s) fT[(s) * VK_EMIT_LD]
 
 #define VK_EMIT_STORE_BEGIN(NI)                                                                                           \
@@ -160,7 +166,8 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     double *ks = rb + (TB) * (RLD);                                                                                      \
     const int j = (int)(blockIdx.x % (unsigned)a.nz), col0 = (int)(blockIdx.x / (unsigned)a.nz) * (TB);                  \
     const int ncb = min((TB), a.ncol - col0);                                                                            \
-    for (int i = tid; i <= (NR); i += (TB)) ks[i] = a.k[(size_t)j * ((NR) + 1) + i];                                     \
+    for (int i = tid; i <= (NR); i += (TB)) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];             \
+    const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
     for (int cc = wrp; cc < (TB); cc += (TB) / 32) {                                                                     \
         const size_t base = ((size_t)(col0 + cc) * a.nz + j) * (NI);                                                     \
         for (int s = lane; s < (NI); s += 32) rb[cc * (RLD) + s] = (cc < ncb) ? a.y[base + s] : 0.0;                     \

@@ -139,6 +139,8 @@ struct vk_column {
     // state
     double *y, *ymix, *sol, *ymix_out, *k;   // [ncol][nz][ni] x4, k [ncol or 1][nz][nr+1]
     size_t k_cs;                              // column stride of k (0 = shared)
+    bool k_static_shared;                     // per-column k whose rows outside the photolysis / ionisation / condensation sections are identical
+                                              // in every column (vk_set_k shared = 2): the emitted chemistry kernels apply
     double *f, *k1, *k2, *yk2, *rhs, *z, *res, *dx, *xn;  // work vectors [ncol][nz][ni]
     double *ysum_lhs_tmp;       // layer sums written by the emitted Jacobian kernel
     double *chem_tmp, *ysum_tmp; void *scal_tmp;   // emitted chemdf path (allocated on first use): chemdf [ncol][nz][ni], layer sums and layer scalars [ncol][nz]
@@ -187,6 +189,7 @@ unsigned long long network_table_hash(const vk_network_desc *d);
 const void *emit_lookup(unsigned long long hash, int ni, int nr);
 int launch_jac_emitted(vk_column *c, const double *y_dev, double *D_out, double *ysum_out);
 bool emit_has_jac(const void *entry);
+bool emit_row_is_dynamic(const void *entry, int i);
 int launch_chem_emitted(vk_column *c, const double *y_dev, const double *k1, double *chem_out, double *ysum_out, double *yk2_out);
 int stream_wait(vk_column *c);
 int launch_factor(vk_column *c, const double *D, const double *up, const double *dn, double *F, int *status, const double *fwd_rhs = nullptr);

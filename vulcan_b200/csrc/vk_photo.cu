@@ -22,6 +22,7 @@ struct PhotoState {
     double *aflux;                             // [ncol][nz][nbin]
     double *dz, *J;                            // [ncol][nz], [ncol][n_br][nz]
     unsigned long long *change_bits;           // [ncol]
+    double *pk;                                // [ncol][nz][n_abs + 2 n_scat + n_photo] packed y dz / ymix of the species the sweeps read
     std::vector<void *> allocs;
 };
 
@@ -38,17 +39,23 @@ struct FluxArgs {
     double *tau, *sflux, *dflux_u, *dflux_d, *aflux;
     unsigned long long *change_bits;
     const int *pred;           // [ncol] or NULL: only the flagged columns are updated (device-resident cadence, vk_steady.cu)
+    // what the sweeps read of y / ymix, packed per (column, layer) by photo_pack_kernel: [n_abs] y*dz of the absorbers, [n_scat] y*dz of the
+    // scatterers, [n_photo] ymix of the photo species, [n_scat] ymix of the scatterers - 464 contiguous bytes that every thread of a block
+    // reads at the same address (one cached broadcast) instead of three dependent loads (index, y, cross section) per species and layer
+    double *pk;
+    int pk_ld;
 };
 
+#define FLUX_TB 128
 struct Coef { double chi, xi, phi, i_u, i_d; };
 
-__device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double *ymj, int b, double tau_j, double tau_jp,
-                                                double dir_j, double dir_jp, double mu_ang)
+__device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double *ym_photo, const double *ym_scat, const double *xs_photo,
+                                                const double *xs_scat, double tau_j, double tau_jp, double dir_j, double dir_jp, double mu_ang)
 {
-    // single-scattering albedo (op.py:2621-2636)
+    // single-scattering albedo (op.py:2621-2636); xs_*: the thread's cross sections in shared memory (stride FLUX_TB)
     double tot_abs = 0.0, tot_scat = 0.0;
-    for (int s = 0; s < a.n_photo; s++) tot_abs += ymj[a.photo_idx[s]] * a.cross_photo[(size_t)s * a.nbin + b];
-    for (int s = 0; s < a.n_scat; s++) tot_scat += ymj[a.scat_idx[s]] * a.cross_scat[(size_t)s * a.nbin + b];
+    for (int s = 0; s < a.n_photo; s++) tot_abs += ym_photo[s] * xs_photo[s * FLUX_TB];
+    for (int s = 0; s < a.n_scat; s++) tot_scat += ym_scat[s] * xs_scat[s * FLUX_TB];
     double w0 = tot_scat / (tot_abs + tot_scat);
     if (w0 != w0) w0 = 0.0;                                   // np.nan_to_num
     else if (isinf(w0)) w0 = (w0 > 0) ? 1.7976931348623157e308 : -1.7976931348623157e308;
@@ -71,16 +78,45 @@ __device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double 
     return c;
 }
 
-__global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
+// y * dz and ymix of the species the sweeps read, one thread per (column, layer, slot)
+__global__ void __launch_bounds__(256) photo_pack_kernel(FluxArgs a)
 {
-    const int nz = a.nz, ni = a.ni, nbin = a.nbin;
-    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const bool live = gid < (size_t)a.ncol * nbin && (!a.pred || a.pred[gid / nbin]);
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int PL = a.pk_ld;
+    if (e >= (size_t)a.ncol * a.nz * PL) return;
+    const int q = (int)(e % PL);
+    const size_t lay = e / PL;
+    const int col = (int)(lay / a.nz);
+    if (a.pred && !a.pred[col]) return;
+    const double *yj = a.y + lay * a.ni, *ymj = a.ymix + lay * a.ni;
+    double v;
+    if (q < a.n_abs) v = yj[a.abs_idx[q]] * a.dz[lay];
+    else if (q < a.n_abs + a.n_scat) v = yj[a.scat_idx[q - a.n_abs]] * a.dz[lay];
+    else if (q < a.n_abs + a.n_scat + a.n_photo) v = ymj[a.photo_idx[q - a.n_abs - a.n_scat]];
+    else v = ymj[a.scat_idx[q - a.n_abs - a.n_scat - a.n_photo]];
+    a.pk[e] = v;
+}
+
+// one thread per (column, wavelength bin): blockIdx.y = column, the block's FLUX_TB bins keep their cross sections in shared memory
+// (xs[s][tid]: each thread only ever reads its own column of the tile)
+__global__ void __launch_bounds__(FLUX_TB) flux_kernel(FluxArgs a)
+{
+    extern __shared__ double xs[];
+    const int nz = a.nz, nbin = a.nbin;
+    const int col = blockIdx.y, tid = threadIdx.x;
+    if (a.pred && !a.pred[col]) return;
+    const int b = blockIdx.x * FLUX_TB + tid;
+    const bool live = b < nbin;
+    const int bb = live ? b : nbin - 1;
+    double *xs_abs = xs + tid, *xs_scat = xs_abs + (size_t)a.n_abs * FLUX_TB, *xs_photo = xs_scat + (size_t)a.n_scat * FLUX_TB;
+    for (int s = 0; s < a.n_abs; s++) xs_abs[s * FLUX_TB] = a.cross_abs[(size_t)s * nbin + bb];
+    for (int s = 0; s < a.n_scat; s++) xs_scat[s * FLUX_TB] = a.cross_scat[(size_t)s * nbin + bb];
+    for (int s = 0; s < a.n_photo; s++) xs_photo[s * FLUX_TB] = a.cross_photo[(size_t)s * nbin + bb];
     double change = 0.0;
     bool has = false;
     if (live) {
-        const int col = (int)(gid / nbin), b = (int)(gid % nbin);
-        const double *yc = a.y + (size_t)col * nz * ni, *ymc = a.ymix + (size_t)col * nz * ni, *dzc = a.dz + (size_t)col * nz;
+        const int PL = a.pk_ld;
+        const double *pkc = a.pk + (size_t)col * nz * PL;
         double *tau = a.tau + (size_t)col * (nz + 1) * nbin + b;
         double *sfl = a.sflux + (size_t)col * (nz + 1) * nbin + b;
         double *du = a.dflux_u + (size_t)col * (nz + 1) * nbin + b;
@@ -95,19 +131,20 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
         sfl[(size_t)nz * nbin] = s_above;
         double dd_above = dd[(size_t)nz * nbin];          // stays as left by the caller (zero): dflux_d[nz] is never written
         for (int j = nz - 1; j >= 0; j--) {
-            const double *yj = yc + (size_t)j * ni;
+            const double *pj = pkc + (size_t)j * PL;      // [n_abs] y dz | [n_scat] y dz | [n_photo] ymix | [n_scat] ymix
             double tj = 0.0;
             for (int s = 0; s < a.n_abs; s++) {
-                double f = yj[a.abs_idx[s]] * dzc[j];
-                double cs = (a.abs_is_T && a.abs_is_T[s]) ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : a.cross_abs[(size_t)s * nbin + b];
+                const double f = pj[s];
+                const double cs = (a.abs_is_T && a.abs_is_T[s]) ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : xs_abs[s * FLUX_TB];
                 tj += f * cs;
             }
-            for (int s = 0; s < a.n_scat; s++) tj += yj[a.scat_idx[s]] * dzc[j] * a.cross_scat[(size_t)s * nbin + b];
+            for (int s = 0; s < a.n_scat; s++) tj += pj[a.n_abs + s] * xs_scat[s * FLUX_TB];
             tj += tau_above;
             tau[(size_t)j * nbin] = tj;
             double sj = top * exp(-1. * tj / cosz);
             sfl[(size_t)j * nbin] = sj;
-            Coef c = two_stream_coef(a, ymc + (size_t)j * ni, b, tj, tau_above, sj * cosz, s_above * cosz, mu_ang);
+            Coef c = two_stream_coef(a, pj + a.n_abs + a.n_scat, pj + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, tj, tau_above,
+                                     sj * cosz, s_above * cosz, mu_ang);
             double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du[(size_t)j * nbin] + c.i_d / mu_ang);   // op.py:2692
             dd[(size_t)j * nbin] = ddj;
             dd_above = ddj; tau_above = tj; s_above = sj;
@@ -116,9 +153,11 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
         double du_below = du[0];
         for (int j = 1; j <= nz; j++) {
             const int m = j - 1;
+            const double *pm = pkc + (size_t)m * PL;
             double t_m = tau[(size_t)m * nbin], t_j = tau[(size_t)j * nbin];
             double s_m = sfl[(size_t)m * nbin], s_j = sfl[(size_t)j * nbin];
-            Coef c = two_stream_coef(a, ymc + (size_t)m * ni, b, t_m, t_j, s_m * cosz, s_j * cosz, mu_ang);
+            Coef c = two_stream_coef(a, pm + a.n_abs + a.n_scat, pm + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, t_m, t_j,
+                                     s_m * cosz, s_j * cosz, mu_ang);
             double duj = 1. / c.chi * (c.phi * du_below - c.xi * dd[(size_t)j * nbin] + c.i_u / mu_ang);   // op.py:2694
             du[(size_t)j * nbin] = duj;
             du_below = duj;
@@ -138,8 +177,11 @@ __global__ void __launch_bounds__(128) flux_kernel(FluxArgs a)
         }
     }
     unsigned long long bits = has ? (unsigned long long)__double_as_longlong(change) : 0ull;
-    // threads of one warp may straddle two columns only when nbin is not a multiple of 32: reduce per thread instead
-    if (live && bits) atomicMax(a.change_bits + (gid / nbin), bits);
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long o = __shfl_xor_sync(0xffffffffu, bits, off);
+        bits = (o > bits) ? o : bits;
+    }
+    if ((tid & 31) == 0 && bits) atomicMax(a.change_bits + col, bits);
 }
 
 struct JArgs {
@@ -297,8 +339,18 @@ int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_de
     a.change_bits = p->change_bits; a.pred = pred;
     const int nb = (c->ncol + 127) / 128;
     photo_begin_kernel<<<nb, 128, 0, c->stream>>>(c->ncol, pred, p->change_bits);
-    const size_t nthr = (size_t)c->ncol * p->nbin;
-    flux_kernel<<<(unsigned)((nthr + 127) / 128), 128, 0, c->stream>>>(a);
+    a.pk_ld = p->n_abs + 2 * p->n_scat + p->n_photo;
+    if (!p->pk) {
+        VK_CUDA(cudaMalloc((void **)&p->pk, sizeof(double) * (size_t)c->ncol * c->nz * a.pk_ld));
+        p->allocs.push_back(p->pk);
+    }
+    a.pk = p->pk;
+    const size_t npk = (size_t)c->ncol * c->nz * a.pk_ld;
+    photo_pack_kernel<<<(unsigned)((npk + 255) / 256), 256, 0, c->stream>>>(a);
+    const size_t smem = sizeof(double) * FLUX_TB * (size_t)(p->n_abs + p->n_scat + p->n_photo);
+    if (smem > 200 * 1024) { set_error("too many absorbing species for the flux kernel's shared-memory tile"); return VK_ERR_UNSUPPORTED; }
+    { int rc = ensure_smem((const void *)flux_kernel, c->net->device, smem); if (rc) return rc; }
+    flux_kernel<<<dim3((unsigned)((p->nbin + FLUX_TB - 1) / FLUX_TB), (unsigned)c->ncol), FLUX_TB, smem, c->stream>>>(a);
     VK_CUDA(cudaGetLastError());
     JArgs ja;
     ja.nz = c->nz; ja.nbin = p->nbin; ja.i12 = p->i12; ja.n_br = p->n_br; ja.ncol = c->ncol; ja.nr = c->nr;

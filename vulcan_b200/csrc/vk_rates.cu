@@ -180,6 +180,7 @@ int vk_compute_k(vk_column *c, const double *Tco, const double *M, int shared)
     cudaFree(dM);
     if (e != cudaSuccess) return cuda_fail(e, "vk_compute_k");
     c->k_set = true;
+    c->k_static_shared = false;
     return VK_OK;
 }
 

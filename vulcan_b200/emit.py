@@ -88,6 +88,7 @@ def emit_negjac(t, h, w):
     rows = [[] for _ in range(ni)]
     for e in range(len(jr)):
         rows[int(jr[e])].append(e)
+    dyn = set(int(x) for x in np.asarray(t.get("dyn_k", [])).ravel())
     # hot species live in registers, cold ones (least used by the Jacobian terms) behind the thread's row buffer in shared memory; the row
     # stride is chosen so that JAC_TB threads x JAC_BLOCKS blocks fit the shared memory of an SM
     use = np.bincount(jfac[jfac < ni].ravel(), minlength=ni)
@@ -129,7 +130,7 @@ def emit_negjac(t, h, w):
                 first = True
                 for qq in range(int(jp[e]), int(jp[e + 1])):
                     c = float(jcoef[qq])
-                    kx = "K(%d)" % int(jk[qq])
+                    kx = ("KG(%d)" if int(jk[qq]) in dyn else "K(%d)") % int(jk[qq])
                     head = kx if c == 1.0 else ("-" + kx if c == -1.0 else "%s%s * %s" % ("-" if c < 0 else "", _coef_lit(c), kx))
                     stm = ["t = %s;" % head]
                     for f in range(mjf):
@@ -169,6 +170,7 @@ def emit_chemdf(t, name):
     rhs_ptr, rhs_pair, rhs_coef = t["rhs_ptr"], t["rhs_pair"], t["rhs_coef"]
     h = _fnv_fast(t)
     npair = nr // 2
+    dyn = set(int(x) for x in np.asarray(t.get("dyn_k", [])).ravel())
     # terms of every pair in the order they are applied: (species, coef), species' own order preserved (their lists are sorted by reaction)
     terms = [[] for _ in range(npair + 1)]
     for s in range(ni):
@@ -202,7 +204,7 @@ def emit_chemdf(t, name):
                 continue
             w("    {")
             for hname, i in (("rf", 2 * p + 1), ("rr", 2 * p + 2)):
-                expr = "K(%d)" % i
+                expr = ("KG(%d)" if i in dyn else "K(%d)") % i
                 stmts = []
                 first = True
                 for q in range(maxf):
@@ -242,15 +244,17 @@ def emit_chemdf(t, name):
     w("    return 0;")
     w("}")
     have_jac = emit_negjac(t, h, w)
-    w("const EmitRegistrar reg_%016x(0x%016xull, %d, %d, \"%s\", launch_%016x, %s);" % (
-        h, h, ni, nr, name, h, ("launch_jac_%016x" % h) if have_jac else "nullptr"))
+    dl = sorted(dyn)
+    w("const int dyn_%016x[] = {%s};" % (h, ", ".join(str(x) for x in dl) if dl else "0"))
+    w("const EmitRegistrar reg_%016x(0x%016xull, %d, %d, \"%s\", launch_%016x, %s, dyn_%016x, %d);" % (
+        h, h, ni, nr, name, h, ("launch_jac_%016x" % h) if have_jac else "nullptr", h, len(dl)))
     w("}  // namespace")
     w("}}  // namespace vk::emitted")
     return "\n".join(out) + "\n", h
 
 
 TABLE_KEYS = ("ni", "nr", "maxf", "rate_fac", "rate_pow", "rhs_ptr", "rhs_pair", "rhs_coef",
-              "maxjf", "jac_ptr", "jac_row", "jac_col", "jac_k", "jac_coef", "jac_fac")
+              "maxjf", "jac_ptr", "jac_row", "jac_col", "jac_k", "jac_coef", "jac_fac", "dyn_k")
 HASH_KEYS = TABLE_KEYS[:8]
 
 

@@ -51,7 +51,7 @@ def synthetic_columns(y_base, n_0, compo, atom_names, kzz_scale, met_scale, c_to
     return y, atom_ini
 
 
-def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine, compo=None):
+def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine, compo=None, k_static_rows_shared=False):
     """a vk_column handle for `ncol` columns of a sweep: per-column Kzz, everything else of the atmosphere replicated."""
     col = _abi.Columns(devnet, nz, ncol)
     rep = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (ncol,) + np.shape(a)))
@@ -62,7 +62,7 @@ def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine, compo=None)
                 bot_vdep=rep(a["bot_vdep"]), use_moldiff=a["use_moldiff"], use_settling=a["use_settling"],
                 use_topflux=a["use_topflux"], use_botflux=a["use_botflux"], gas_indx=a.get("gas_indx"),
                 gas_indx_lhs=a.get("gas_indx_lhs"), shared=False)
-    col.set_k(k)                                        # thermal + photolysis rates shared by the sweep (same T-P, same star)
+    col.set_k(k, static_rows_shared=k_static_rows_shared and np.ndim(k) == 3)   # thermal rates shared by the sweep (same T-P, same star)
     if refine < 0 and compo is None:
         raise ValueError("refine = -1 (auto) needs the element composition `compo` [ni, na]")
     col.set_step_opts(cfg["mtol"], cfg["atol"], refine=refine, compo=compo)
@@ -72,10 +72,10 @@ def _make_columns(devnet, nz, ncol, atm_common, kzz, k, cfg, refine, compo=None)
 class EnsembleRunner(object):
     """The columns [lo, hi) of an ensemble resident on one GPU, advanced by the device-resident controller."""
 
-    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=-1):
+    def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=0, refine=-1, k_static_rows_shared=False):
         self.ncol = y.shape[0]
         self.devnet = _abi.DeviceNetwork(network, device)
-        self.col = _make_columns(self.devnet, nz, self.ncol, atm_common, kzz, k, cfg, refine, compo)
+        self.col = _make_columns(self.devnet, nz, self.ncol, atm_common, kzz, k, cfg, refine, compo, k_static_rows_shared)
         self.col.ens_setup(cfg["rtol"], cfg["loss_eps"], cfg["dt_min"], cfg["dt_max"], cfg["dt_var_min"], cfg["dt_var_max"],
                            cfg["pos_cut"], cfg["nega_cut"], compo, atom_ini, np.broadcast_to(n_0, (self.ncol, nz)))
         self.col.ens_set_state(y, dt)
@@ -215,9 +215,13 @@ class SteadyEnsemble(EnsembleRunner):
     def __init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, grid, photo=None, device=0, refine=-1,
                  hist_cap=None, hist_stride=None, diff_esc_idx=(), conv_ignore_sp=None):
         ncol = y.shape[0]
+        replicated = False
         if photo is not None and ncol > 1 and np.ndim(k) == 2:
+            # one T-P profile: the thermal rows are the same in every column, the J rows are rewritten per column by the photolysis update
             k = np.ascontiguousarray(np.broadcast_to(np.asarray(k, dtype=np.float64), (ncol,) + np.shape(k)))
-        EnsembleRunner.__init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=device, refine=refine)
+            replicated = True
+        EnsembleRunner.__init__(self, network, nz, y, dt, atm_common, kzz, k, cfg, compo, atom_ini, n_0, device=device, refine=refine,
+                                k_static_rows_shared=replicated)
         if photo is not None:
             self.col.photo_setup(**photo)
         conv_step = int(cfg["conv_step"])

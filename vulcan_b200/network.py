@@ -244,6 +244,10 @@ class Network(object):
             jac_ptr=np.array(jac_ptr, dtype=np.int32), jac_row=np.array(jac_row, dtype=np.int32),
             jac_col=np.array(jac_col, dtype=np.int32), jac_k=np.array(jac_k, dtype=np.int32),
             jac_coef=np.array(jac_coef, dtype=np.float64), jac_fac=jac_fac,
+            # k indices (forward and reverse) that the run itself rewrites per column: photolysis / ionisation rates (compute_J, compute_Jion)
+            # and condensation growth rates (Integration.conden) - everything else is set once from the T-P profile
+            dyn_k=np.array(sorted({r.id + d for r in self.reactions if r.section in (SECTION_PHOTO, SECTION_ION, SECTION_CONDEN)
+                                   for d in (0, 1)}), dtype=np.int32),
         )
         return self._tables
 
