@@ -447,6 +447,14 @@ int launch_refine(vk_column *c, const double *D, const double *up, const double 
                       VK_REFINE_BUDGET_TOL, act, c->refine_kept, c->refine_tried};
         refine_select_kernel<<<c->ncol, 256, 0, c->stream>>>(sa);
         VK_CUDA(cudaGetLastError());
+        // ONE column (the latency path): a further pass is ~30 launches of the cyclic-reduction solve whether or not the column is still
+        // being refined - ask the flag back (4 bytes, ~10 us) and stop launching once it is done (typically after the first pass)
+        if (c->ncol == 1 && it + 1 < passes) {
+            int still = 1;
+            VK_CUDA(cudaMemcpyAsync(&still, act, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            VK_CUDA(cudaStreamSynchronize(c->stream));
+            if (!still) break;
+        }
     }
     return VK_OK;
 }
