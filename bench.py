@@ -525,7 +525,7 @@ def main():
             col1.ros2_solve(y1, m1, case.dt)
         e2e1 = 20 / (time.time() - t0)
         line["single_column"] = {"steps_per_s": 30 / (ms1 * 1e-3), "ms_per_step": ms1 / 30, "e2e_steps_per_s": e2e1,
-                                 "note": "attempted Ros2 steps of ONE HD189 column (latency-bound: one SM runs the block-Thomas recurrence)"}
+                                 "note": "attempted Ros2 steps of ONE HD189 column (latency path: block cyclic reduction over the layers, vk_cr.inl)"}
         # time-to-steady-state: ONE HD189 column from the reference's own initial state to the reference's own stopping rule, the whole
         # loop device-resident (vk_ens_run_steady: steps, accept / reject, conv against the on-device history, photolysis cadence,
         # update_mu_dz); reference numbers from tests/golden/HD189_full.npz (unmodified reference, 1 core, build container)

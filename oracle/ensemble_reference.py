@@ -25,9 +25,10 @@ REPO = os.path.dirname(HERE)
 sys.path.insert(0, HERE)
 sys.path.insert(0, REPO)
 
-# (Kzz scale, metallicity scale, C/O) of the sampled columns; column 2 is the unmodified HD189 cfg
+# (Kzz scale, metallicity scale, C/O) of the sampled columns; column 2 is the unmodified HD189 cfg.  Column 3 (C/O 0.8 at twice solar
+# metallicity) had not converged after two hours of the reference and is not part of the fixture; column 8 was added in its place
 PARAMS = np.array([[0.1, 1.0, 0.55], [0.3, 1.0, 0.55], [1.0, 1.0, 0.55], [1.0, 2.0, 0.8], [3.0, 1.0, 0.3], [10.0, 0.5, 0.55],
-                   [0.5, 3.0, 1.0], [2.0, 0.3, 0.4]])
+                   [0.5, 3.0, 1.0], [2.0, 0.3, 0.4], [5.0, 1.5, 0.45]])
 
 
 def run_one(refdir, index, out):
