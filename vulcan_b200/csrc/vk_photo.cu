@@ -23,6 +23,7 @@ struct PhotoState {
     double *dz, *J;                            // [ncol][nz], [ncol][n_br][nz]
     unsigned long long *change_bits;           // [ncol]
     double *pk;                                // [ncol][nz][n_abs + 2 n_scat + n_photo] packed y dz / ymix of the species the sweeps read
+    int photo_same;                            // the photo species and their cross sections are the absorbers' (the usual case): one tile
     std::vector<void *> allocs;
 };
 
@@ -44,9 +45,11 @@ struct FluxArgs {
     // reads at the same address (one cached broadcast) instead of three dependent loads (index, y, cross section) per species and layer
     double *pk;
     int pk_ld;
+    int photo_same;
 };
 
 #define FLUX_TB 128
+#define FLUX_NZMAX 192
 struct Coef { double chi, xi, phi, i_u, i_d; };
 
 __device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double *ym_photo, const double *ym_scat, const double *xs_photo,
@@ -108,12 +111,18 @@ __global__ void __launch_bounds__(FLUX_TB) flux_kernel(FluxArgs a)
     const int b = blockIdx.x * FLUX_TB + tid;
     const bool live = b < nbin;
     const int bb = live ? b : nbin - 1;
-    double *xs_abs = xs + tid, *xs_scat = xs_abs + (size_t)a.n_abs * FLUX_TB, *xs_photo = xs_scat + (size_t)a.n_scat * FLUX_TB;
+    double *xs_abs = xs + tid, *xs_scat = xs_abs + (size_t)a.n_abs * FLUX_TB;
+    double *xs_photo = a.photo_same ? xs_abs : xs_scat + (size_t)a.n_scat * FLUX_TB;
     for (int s = 0; s < a.n_abs; s++) xs_abs[s * FLUX_TB] = a.cross_abs[(size_t)s * nbin + bb];
     for (int s = 0; s < a.n_scat; s++) xs_scat[s * FLUX_TB] = a.cross_scat[(size_t)s * nbin + bb];
-    for (int s = 0; s < a.n_photo; s++) xs_photo[s * FLUX_TB] = a.cross_photo[(size_t)s * nbin + bb];
+    if (!a.photo_same) for (int s = 0; s < a.n_photo; s++) xs_photo[s * FLUX_TB] = a.cross_photo[(size_t)s * nbin + bb];
     double change = 0.0;
     bool has = false;
+    // two-stream coefficients of the downward sweep, kept for the upward sweep (same inputs, same values: tau / sflux of the layer and the one
+    // above) in thread-local memory - 4 doubles per layer, coalesced across the warp, sized by the RESIDENT threads (2.4 GB on a B200) rather
+    // than by columns x bins; saves the second evaluation (an exp, a sqrt, 4 divisions and the albedo sums per bin and layer)
+    double cst[FLUX_NZMAX][4];
+    const bool keep = nz <= FLUX_NZMAX;
     if (live) {
         const int PL = a.pk_ld;
         const double *pkc = a.pk + (size_t)col * nz * PL;
@@ -130,13 +139,20 @@ __global__ void __launch_bounds__(FLUX_TB) flux_kernel(FluxArgs a)
         double s_above = top * exp(-1. * tau_above / cosz);
         sfl[(size_t)nz * nbin] = s_above;
         double dd_above = dd[(size_t)nz * nbin];          // stays as left by the caller (zero): dflux_d[nz] is never written
+        bool any_T = false;                               // temperature-dependent cross sections (Earth: per-layer tables) - rare
+        if (a.abs_is_T) for (int s = 0; s < a.n_abs; s++) any_T = any_T || a.abs_is_T[s];
         for (int j = nz - 1; j >= 0; j--) {
             const double *pj = pkc + (size_t)j * PL;      // [n_abs] y dz | [n_scat] y dz | [n_photo] ymix | [n_scat] ymix
+            const double du_j = du[(size_t)j * nbin];     // (issued before the sums: its latency hides behind them)
             double tj = 0.0;
-            for (int s = 0; s < a.n_abs; s++) {
-                const double f = pj[s];
-                const double cs = (a.abs_is_T && a.abs_is_T[s]) ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : xs_abs[s * FLUX_TB];
-                tj += f * cs;
+            if (!any_T) {
+                for (int s = 0; s < a.n_abs; s++) tj += pj[s] * xs_abs[s * FLUX_TB];
+            } else {
+                for (int s = 0; s < a.n_abs; s++) {
+                    const double f = pj[s];
+                    const double cs = a.abs_is_T[s] ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : xs_abs[s * FLUX_TB];
+                    tj += f * cs;
+                }
             }
             for (int s = 0; s < a.n_scat; s++) tj += pj[a.n_abs + s] * xs_scat[s * FLUX_TB];
             tj += tau_above;
@@ -145,19 +161,25 @@ __global__ void __launch_bounds__(FLUX_TB) flux_kernel(FluxArgs a)
             sfl[(size_t)j * nbin] = sj;
             Coef c = two_stream_coef(a, pj + a.n_abs + a.n_scat, pj + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, tj, tau_above,
                                      sj * cosz, s_above * cosz, mu_ang);
-            double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du[(size_t)j * nbin] + c.i_d / mu_ang);   // op.py:2692
+            double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du_j + c.i_d / mu_ang);   // op.py:2692
             dd[(size_t)j * nbin] = ddj;
             dd_above = ddj; tau_above = tj; s_above = sj;
+            if (keep) { cst[j][0] = c.chi; cst[j][1] = c.xi; cst[j][2] = c.phi; cst[j][3] = c.i_u; }
         }
         // ---- pass 2: bottom -> top (dflux_u[0] keeps its value: zero upward flux at the bottom)
         double du_below = du[0];
         for (int j = 1; j <= nz; j++) {
             const int m = j - 1;
-            const double *pm = pkc + (size_t)m * PL;
-            double t_m = tau[(size_t)m * nbin], t_j = tau[(size_t)j * nbin];
-            double s_m = sfl[(size_t)m * nbin], s_j = sfl[(size_t)j * nbin];
-            Coef c = two_stream_coef(a, pm + a.n_abs + a.n_scat, pm + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, t_m, t_j,
-                                     s_m * cosz, s_j * cosz, mu_ang);
+            Coef c;
+            if (keep) {
+                c.chi = cst[m][0]; c.xi = cst[m][1]; c.phi = cst[m][2]; c.i_u = cst[m][3];
+            } else {
+                const double *pm = pkc + (size_t)m * PL;
+                double t_m = tau[(size_t)m * nbin], t_j = tau[(size_t)j * nbin];
+                double s_m = sfl[(size_t)m * nbin], s_j = sfl[(size_t)j * nbin];
+                c = two_stream_coef(a, pm + a.n_abs + a.n_scat, pm + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, t_m, t_j,
+                                    s_m * cosz, s_j * cosz, mu_ang);
+            }
             double duj = 1. / c.chi * (c.phi * du_below - c.xi * dd[(size_t)j * nbin] + c.i_u / mu_ang);   // op.py:2694
             du[(size_t)j * nbin] = duj;
             du_below = duj;
@@ -267,6 +289,8 @@ int vk_photo_setup(vk_column *c, const vk_photo_view *v)
     PC(bins, nb); PC(sflux_top, nb);
     PC(abs_idx, v->n_abs); PC(cross_abs, v->n_abs * nb);
     PC(photo_idx, v->n_photo); PC(cross_photo, v->n_photo * nb);
+    p->photo_same = (v->n_abs == v->n_photo && memcmp(v->abs_idx, v->photo_idx, sizeof(int) * v->n_abs) == 0 &&
+                     memcmp(v->cross_abs, v->cross_photo, sizeof(double) * (size_t)v->n_abs * nb) == 0) ? 1 : 0;
     PC(scat_idx, v->n_scat); PC(cross_scat, v->n_scat * nb);
     PC(cross_J, v->n_br * nb); PC(br_rate_index, v->n_br);
 #undef PC
@@ -347,7 +371,8 @@ int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_de
     a.pk = p->pk;
     const size_t npk = (size_t)c->ncol * c->nz * a.pk_ld;
     photo_pack_kernel<<<(unsigned)((npk + 255) / 256), 256, 0, c->stream>>>(a);
-    const size_t smem = sizeof(double) * FLUX_TB * (size_t)(p->n_abs + p->n_scat + p->n_photo);
+    a.photo_same = p->photo_same;
+    const size_t smem = sizeof(double) * FLUX_TB * (size_t)(p->n_abs + p->n_scat + (p->photo_same ? 0 : p->n_photo));
     if (smem > 200 * 1024) { set_error("too many absorbing species for the flux kernel's shared-memory tile"); return VK_ERR_UNSUPPORTED; }
     { int rc = ensure_smem((const void *)flux_kernel, c->net->device, smem); if (rc) return rc; }
     flux_kernel<<<dim3((unsigned)((p->nbin + FLUX_TB - 1) / FLUX_TB), (unsigned)c->ncol), FLUX_TB, smem, c->stream>>>(a);
