@@ -50,6 +50,7 @@ struct FluxArgs {
 
 #define FLUX_TB 128
 #define FLUX_NZMAX 192
+#define FLUX_PKT 16
 struct Coef { double chi, xi, phi, i_u, i_d; };
 
 __device__ __forceinline__ Coef two_stream_coef(const FluxArgs &a, const double *ym_photo, const double *ym_scat, const double *xs_photo,
@@ -123,49 +124,64 @@ __global__ void __launch_bounds__(FLUX_TB) flux_kernel(FluxArgs a)
     // than by columns x bins; saves the second evaluation (an exp, a sqrt, 4 divisions and the albedo sums per bin and layer)
     double cst[FLUX_NZMAX][4];
     const bool keep = nz <= FLUX_NZMAX;
-    if (live) {
-        const int PL = a.pk_ld;
-        const double *pkc = a.pk + (size_t)col * nz * PL;
-        double *tau = a.tau + (size_t)col * (nz + 1) * nbin + b;
-        double *sfl = a.sflux + (size_t)col * (nz + 1) * nbin + b;
-        double *du = a.dflux_u + (size_t)col * (nz + 1) * nbin + b;
-        double *dd = a.dflux_d + (size_t)col * (nz + 1) * nbin + b;
-        double *af = a.aflux + (size_t)col * nz * nbin + b;
-        const double cosz = cos(a.sl_angle), mu_ang = -1. * cos(a.sl_angle);
-        const double top = a.sflux_top[b];
+    const int PL = a.pk_ld;
+    const double *pkc = a.pk + (size_t)col * nz * PL;
+    // pass 1 reads the packed y rows of FLUX_PKT layers at a time from shared memory (the same 464 bytes per layer for every thread of
+    // the block: a broadcast, no global-load latency inside the species loops).  Every thread of the block walks the loop (barriers);
+    // threads beyond the last bin compute on the last bin's data and store nothing
+    double *pkt = xs + (size_t)FLUX_TB * (a.n_abs + a.n_scat + (a.photo_same ? 0 : a.n_photo));
+    double *tau = a.tau + (size_t)col * (nz + 1) * nbin + bb;
+    double *sfl = a.sflux + (size_t)col * (nz + 1) * nbin + bb;
+    double *du = a.dflux_u + (size_t)col * (nz + 1) * nbin + bb;
+    double *dd = a.dflux_d + (size_t)col * (nz + 1) * nbin + bb;
+    double *af = a.aflux + (size_t)col * nz * nbin + bb;
+    const double cosz = cos(a.sl_angle), mu_ang = -1. * cos(a.sl_angle);
+    const double top = a.sflux_top[bb];
+    {
         // ---- pass 1: top -> bottom
         double tau_above = 0.0;
-        tau[(size_t)nz * nbin] = 0.0;
+        if (live) tau[(size_t)nz * nbin] = 0.0;
         double s_above = top * exp(-1. * tau_above / cosz);
-        sfl[(size_t)nz * nbin] = s_above;
+        if (live) sfl[(size_t)nz * nbin] = s_above;
         double dd_above = dd[(size_t)nz * nbin];          // stays as left by the caller (zero): dflux_d[nz] is never written
         bool any_T = false;                               // temperature-dependent cross sections (Earth: per-layer tables) - rare
         if (a.abs_is_T) for (int s = 0; s < a.n_abs; s++) any_T = any_T || a.abs_is_T[s];
-        for (int j = nz - 1; j >= 0; j--) {
-            const double *pj = pkc + (size_t)j * PL;      // [n_abs] y dz | [n_scat] y dz | [n_photo] ymix | [n_scat] ymix
-            const double du_j = du[(size_t)j * nbin];     // (issued before the sums: its latency hides behind them)
-            double tj = 0.0;
-            if (!any_T) {
-                for (int s = 0; s < a.n_abs; s++) tj += pj[s] * xs_abs[s * FLUX_TB];
-            } else {
-                for (int s = 0; s < a.n_abs; s++) {
-                    const double f = pj[s];
-                    const double cs = a.abs_is_T[s] ? a.cross_abs_T[((size_t)s * nz + j) * nbin + b] : xs_abs[s * FLUX_TB];
-                    tj += f * cs;
-                }
+        for (int j0 = nz - 1; j0 >= 0; j0 -= FLUX_PKT) {
+            __syncthreads();                              // the previous tile is consumed
+            for (int q = tid; q < FLUX_PKT * PL; q += FLUX_TB) {
+                const int l = q / PL, e = q - l * PL;
+                if (j0 - l >= 0) pkt[q] = pkc[(size_t)(j0 - l) * PL + e];
             }
-            for (int s = 0; s < a.n_scat; s++) tj += pj[a.n_abs + s] * xs_scat[s * FLUX_TB];
-            tj += tau_above;
-            tau[(size_t)j * nbin] = tj;
-            double sj = top * exp(-1. * tj / cosz);
-            sfl[(size_t)j * nbin] = sj;
-            Coef c = two_stream_coef(a, pj + a.n_abs + a.n_scat, pj + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, tj, tau_above,
-                                     sj * cosz, s_above * cosz, mu_ang);
-            double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du_j + c.i_d / mu_ang);   // op.py:2692
-            dd[(size_t)j * nbin] = ddj;
-            dd_above = ddj; tau_above = tj; s_above = sj;
-            if (keep) { cst[j][0] = c.chi; cst[j][1] = c.xi; cst[j][2] = c.phi; cst[j][3] = c.i_u; }
+            __syncthreads();
+            for (int l = 0; l < FLUX_PKT && j0 - l >= 0; l++) {
+                const int j = j0 - l;
+                const double *pj = pkt + l * PL;          // [n_abs] y dz | [n_scat] y dz | [n_photo] ymix | [n_scat] ymix
+                const double du_j = du[(size_t)j * nbin]; // (issued before the sums: its latency hides behind them)
+                double tj = 0.0;
+                if (!any_T) {
+                    for (int s = 0; s < a.n_abs; s++) tj += pj[s] * xs_abs[s * FLUX_TB];
+                } else {
+                    for (int s = 0; s < a.n_abs; s++) {
+                        const double f = pj[s];
+                        const double cs = a.abs_is_T[s] ? a.cross_abs_T[((size_t)s * nz + j) * nbin + bb] : xs_abs[s * FLUX_TB];
+                        tj += f * cs;
+                    }
+                }
+                for (int s = 0; s < a.n_scat; s++) tj += pj[a.n_abs + s] * xs_scat[s * FLUX_TB];
+                tj += tau_above;
+                if (live) tau[(size_t)j * nbin] = tj;
+                double sj = top * exp(-1. * tj / cosz);
+                if (live) sfl[(size_t)j * nbin] = sj;
+                Coef c = two_stream_coef(a, pj + a.n_abs + a.n_scat, pj + a.n_abs + a.n_scat + a.n_photo, xs_photo, xs_scat, tj, tau_above,
+                                         sj * cosz, s_above * cosz, mu_ang);
+                double ddj = 1. / c.chi * (c.phi * dd_above - c.xi * du_j + c.i_d / mu_ang);   // op.py:2692
+                if (live) dd[(size_t)j * nbin] = ddj;
+                dd_above = ddj; tau_above = tj; s_above = sj;
+                if (keep) { cst[j][0] = c.chi; cst[j][1] = c.xi; cst[j][2] = c.phi; cst[j][3] = c.i_u; }
+            }
         }
+    }
+    if (live) {
         // ---- pass 2: bottom -> top (dflux_u[0] keeps its value: zero upward flux at the bottom)
         double du_below = du[0];
         for (int j = 1; j <= nz; j++) {
@@ -372,7 +388,7 @@ int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_de
     const size_t npk = (size_t)c->ncol * c->nz * a.pk_ld;
     photo_pack_kernel<<<(unsigned)((npk + 255) / 256), 256, 0, c->stream>>>(a);
     a.photo_same = p->photo_same;
-    const size_t smem = sizeof(double) * FLUX_TB * (size_t)(p->n_abs + p->n_scat + (p->photo_same ? 0 : p->n_photo));
+    const size_t smem = sizeof(double) * (FLUX_TB * (size_t)(p->n_abs + p->n_scat + (p->photo_same ? 0 : p->n_photo)) + (size_t)FLUX_PKT * a.pk_ld);
     if (smem > 200 * 1024) { set_error("too many absorbing species for the flux kernel's shared-memory tile"); return VK_ERR_UNSUPPORTED; }
     { int rc = ensure_smem((const void *)flux_kernel, c->net->device, smem); if (rc) return rc; }
     flux_kernel<<<dim3((unsigned)((p->nbin + FLUX_TB - 1) / FLUX_TB), (unsigned)c->ncol), FLUX_TB, smem, c->stream>>>(a);
