@@ -399,6 +399,49 @@ def test_photolysis(tag, step):
         assert np.max(np.abs(J[0] - ref) / np.maximum(np.abs(ref), 1e-300 + 1e-12 * np.abs(ref).max(axis=1, keepdims=True))) < 1e-9
 
 
+@pytest.mark.parametrize("tag,step", [p for p in [("HD189", 0), ("Earth", 0)] if have(p[0], "photo%04d.npz" % p[1])])
+def test_photolysis_batch_matches_one_column(tag, step):
+    """a batch of 20 columns (per-column k; the layer x branch tiled J kernel, block-per-column flux kernel) against the same columns one
+    at a time: tau, fluxes and J bit-identical (every lane adds its bins in the same order in both J kernels), J also lands in the k rows"""
+    c = Case(tag, step)
+    st, cfg = c.st, c.cfg
+    px = np.load("%s/%s_photo%04d.npz" % (GOLD, tag, step))
+    pt = photo_tables(st)
+    ncol = 20
+    scale = np.linspace(0.7, 1.4, ncol)[:, None, None]
+    y = px["y"][None] * scale
+    ymix = np.repeat(px["ymix"][None], ncol, axis=0)
+    dz = np.repeat(px["dz"][None], ncol, axis=0)
+
+    def setup(n):
+        col = _columns(c, n)
+        if n > 1:
+            col.set_k(np.repeat(c.k[None], n, axis=0))
+        col.photo_setup(st["bins"], st["sflux_top"], int(st["sflux_din12_indx"]), float(st["dbin1"]), float(st["dbin2"]),
+                        cfg["sl_angle"], cfg["edd"], cfg["flux_atol"], cfg["f_diurnal"], st["photo_sp_idx"], pt["cross"],
+                        st["photo_sp_idx"], pt["cross"], st["scat_sp_idx"], st["cross_scat"], st["cross_J"],
+                        st["branch_rate_index"], abs_is_T=pt["abs_is_T"], cross_abs_T=pt["cross_T"], br_is_T=pt["br_is_T"],
+                        cross_J_T=pt["cross_J_T"])
+        return col
+    bat = setup(ncol)
+    for it in (1, 2):
+        Jb, chb = bat.photo_update(y, ymix, dz)
+    fb = bat.photo_read()
+    kb = bat.get_k()
+    for q in (0, 7, 19):
+        one = setup(1)
+        for it in (1, 2):
+            J1, ch1 = one.photo_update(y[q], ymix[q], dz[q])
+        f1 = one.photo_read()
+        assert np.array_equal(Jb[q], J1[0]) and chb[q] == ch1[0], q
+        for name in ("tau", "sflux", "dflux_u", "dflux_d", "aflux"):
+            assert np.array_equal(fb[name][q], f1[name][0]), (q, name)
+        k1 = one.get_k()
+        rid = np.asarray(st["branch_rate_index"])
+        rid = rid[rid > 0]
+        assert np.array_equal(kb[q][:, rid], k1.reshape(c.nz, -1)[:, rid])
+
+
 def test_device_resident_loop_vs_reference_trajectory():
     """vk_ens_run (solver -> clip -> accept/reject -> rescale -> step_size entirely on the device) started from the
     reference state at step 10 must reproduce the reference's own (dt, delta) trajectory of steps 10..99 (same photolysis

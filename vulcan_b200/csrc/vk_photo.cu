@@ -234,6 +234,7 @@ struct JArgs {
     const int *pred;
 };
 
+// one warp per (column, branch, layer): the latency version for a few columns (7200 warps for one HD189 column)
 __global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
 {
     const int lane = threadIdx.x & 31;
@@ -259,6 +260,87 @@ __global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
         a.J[((size_t)col * a.n_br + br) * a.nz + j] = v;
         const int rid = a.br_rate_index[br];
         if (rid > 0) a.k[(size_t)col * a.k_cs + (size_t)j * (a.nr + 1) + rid] = v * a.f_diurnal;   // op.py:2785-2786
+    }
+}
+
+// One warp per (column, tile of JR_LT layers, tile of JR_BT branches): lanes stride over the wavelength bins; the cross section of a branch
+// at a bin is loaded once for the JR_LT layers, the actinic flux of a layer at a bin once for the JR_BT branches (the first version - one warp
+// per (column, branch, layer) - moved 18 GB through L1 / L2 per 64 columns).  Every lane adds its bins in increasing order exactly as before,
+// so J has the same bits.
+#define JR_LT 4
+#define JR_BT 16
+__global__ void __launch_bounds__(256) jrate_tile_kernel(JArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const int nlt = (a.nz + JR_LT - 1) / JR_LT, nbt = (a.n_br + JR_BT - 1) / JR_BT;
+    const size_t nw = (size_t)a.ncol * nlt * nbt;
+    if (w >= nw) return;
+    const int bt = (int)(w % nbt), lt = (int)((w / nbt) % nlt), col = (int)(w / ((size_t)nbt * nlt));
+    if (a.pred && !a.pred[col]) return;
+    const int j0 = lt * JR_LT, br0 = bt * JR_BT;
+    const int nl = min(JR_LT, a.nz - j0), nb = min(JR_BT, a.n_br - br0);
+    const double *f[JR_LT];
+#pragma unroll
+    for (int l = 0; l < JR_LT; l++) f[l] = a.aflux + ((size_t)col * a.nz + j0 + (l < nl ? l : 0)) * a.nbin;
+    bool tileT = false;
+    if (a.br_is_T) for (int q = 0; q < nb; q++) tileT = tileT || a.br_is_T[br0 + q];
+    auto cptr = [&](int q, int l) -> const double * {      // cross section row of branch br0 + q (at layer j0 + l when temperature dependent)
+        const int br = br0 + (q < nb ? q : 0);
+        return (a.br_is_T && a.br_is_T[br]) ? a.cross_J_T + ((size_t)br * a.nz + j0 + (l < nl ? l : 0)) * a.nbin : a.cross_J + (size_t)br * a.nbin;
+    };
+    double v[JR_LT][JR_BT];
+    for (int region = 0; region < 2; region++) {
+        const int lo = region ? a.i12 : 0, hi = region ? a.nbin : a.i12;
+        const double db = region ? a.dbin2 : a.dbin1;
+        double acc[JR_LT][JR_BT];
+#pragma unroll
+        for (int l = 0; l < JR_LT; l++)
+#pragma unroll
+            for (int q = 0; q < JR_BT; q++) acc[l][q] = 0.0;
+        if (!tileT) {
+            const double *c[JR_BT];
+#pragma unroll
+            for (int q = 0; q < JR_BT; q++) c[q] = cptr(q, 0);
+            for (int b = lo + lane; b < hi; b += 32) {
+                double fv[JR_LT];
+#pragma unroll
+                for (int l = 0; l < JR_LT; l++) fv[l] = f[l][b];
+#pragma unroll
+                for (int q = 0; q < JR_BT; q++) {
+                    const double cv = c[q][b];
+#pragma unroll
+                    for (int l = 0; l < JR_LT; l++) acc[l][q] += fv[l] * cv * db;
+                }
+            }
+        } else {
+            for (int b = lo + lane; b < hi; b += 32)
+#pragma unroll
+                for (int q = 0; q < JR_BT; q++)
+#pragma unroll
+                    for (int l = 0; l < JR_LT; l++) acc[l][q] += f[l][b] * cptr(q, l)[b] * db;
+        }
+#pragma unroll
+        for (int l = 0; l < JR_LT; l++)
+#pragma unroll
+            for (int q = 0; q < JR_BT; q++) {
+                double s = acc[l][q];
+                for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+                // trapezoid on the uniform grid of the region: the end points count half (op.py:2766-2786)
+                const double *cc = cptr(q, l);
+                const double e = 0.5 * (f[l][lo] * cc[lo] + f[l][hi - 1] * cc[hi - 1]) * db;
+                if (region == 0) v[l][q] = s - e;
+                else { v[l][q] += s; v[l][q] -= e; }
+            }
+    }
+    if (lane == 0) {
+        for (int l = 0; l < nl; l++)
+            for (int q = 0; q < nb; q++) {
+                const int br = br0 + q, j = j0 + l;
+                a.J[((size_t)col * a.n_br + br) * a.nz + j] = v[l][q];
+                const int rid = a.br_rate_index[br];
+                if (rid > 0) a.k[(size_t)col * a.k_cs + (size_t)j * (a.nr + 1) + rid] = v[l][q] * a.f_diurnal;   // op.py:2785-2786
+            }
     }
 }
 
@@ -398,8 +480,13 @@ int photo_update_device(vk_column *c, const double *y_dev, const double *ymix_de
     ja.dbin1 = p->dbin1; ja.dbin2 = p->dbin2; ja.f_diurnal = p->f_diurnal;
     ja.aflux = p->aflux; ja.cross_J = p->cross_J; ja.cross_J_T = p->cross_J_T; ja.br_is_T = p->br_is_T;
     ja.br_rate_index = p->br_rate_index; ja.J = p->J; ja.k = c->k; ja.k_cs = c->k_cs; ja.pred = pred;
-    const size_t nwarp = (size_t)c->ncol * p->n_br * c->nz;
-    jrate_kernel<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, c->stream>>>(ja);
+    if (c->ncol >= 16) {       // batches: layer x branch tiles per warp (fewer, longer warps); a few columns: one warp per (branch, layer)
+        const size_t nwarp = (size_t)c->ncol * ((c->nz + JR_LT - 1) / JR_LT) * ((p->n_br + JR_BT - 1) / JR_BT);
+        jrate_tile_kernel<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, c->stream>>>(ja);
+    } else {
+        const size_t nwarp = (size_t)c->ncol * p->n_br * c->nz;
+        jrate_kernel<<<(unsigned)((nwarp * 32 + 255) / 256), 256, 0, c->stream>>>(ja);
+    }
     if (aflux_change_out) photo_end_kernel<<<nb, 128, 0, c->stream>>>(c->ncol, pred, p->change_bits, aflux_change_out);
     VK_CUDA(cudaGetLastError());
     return VK_OK;
