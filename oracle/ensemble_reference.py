@@ -69,12 +69,21 @@ def run_one(refdir, index, out):
         index, kz, met, co, para.count, var.t, para.end_case, var.longdy, wall), flush=True)
 
 
-def pack(src):
+def pack(src, src2=None):
+    """src: one run per column; src2 (optional): second runs of some columns under another PYTHONHASHSEED (another summation order of tau /
+    omega_0 inside the reference) - the reference's spread against ITSELF on those columns"""
     files = sorted(glob.glob(os.path.join(src, "col*.npz")))
     d = [dict(np.load(f)) for f in files]
     d.sort(key=lambda x: int(x["index"]))
     out = os.path.join(REPO, "tests", "golden", "HD189_ens8_reference.npz")
-    np.savez_compressed(out, params=np.array([x["params"] for x in d]), ymix=np.array([x["ymix"] for x in d]),
+    extra = {}
+    if src2:
+        d2 = [dict(np.load(f)) for f in sorted(glob.glob(os.path.join(src2, "col*.npz")))]
+        d2.sort(key=lambda x: int(x["index"]))
+        pos = {int(x["index"]): q for q, x in enumerate(d)}
+        extra = dict(seed2_column=np.array([pos[int(x["index"])] for x in d2]), seed2_ymix=np.array([x["ymix"] for x in d2]),
+                     seed2_count=np.array([int(x["count"]) for x in d2]), seed2_t=np.array([float(x["t"]) for x in d2]))
+    np.savez_compressed(out, **extra, params=np.array([x["params"] for x in d]), ymix=np.array([x["ymix"] for x in d]),
                         t=np.array([float(x["t"]) for x in d]), count=np.array([int(x["count"]) for x in d]),
                         end_case=np.array([int(x["end_case"]) for x in d]), longdy=np.array([float(x["longdy"]) for x in d]),
                         n_reject=np.array([int(x["n_reject"]) for x in d]), wall_s=np.array([float(x["wall_s"]) for x in d]),
@@ -89,8 +98,9 @@ if __name__ == "__main__":
     ap.add_argument("--index", type=int)
     ap.add_argument("--out")
     ap.add_argument("--pack")
+    ap.add_argument("--pack2", help="directory with second-seed runs of some columns")
     a = ap.parse_args()
     if a.pack:
-        pack(a.pack)
+        pack(a.pack, a.pack2)
     else:
         run_one(a.refdir, a.index, a.out)

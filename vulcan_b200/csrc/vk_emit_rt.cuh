@@ -109,6 +109,7 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     double *ks = ys + ((NI) + 1) * VK_EMIT_LD;                                                                           \
     const int j = (int)(blockIdx.x % (unsigned)a.nz), col0 = (int)(blockIdx.x / (unsigned)a.nz) * VK_EMIT_TB;            \
     const int ncb = min(VK_EMIT_TB, a.ncol - col0);                                                                      \
+    if (a.act && !__syncthreads_or(tid < ncb && a.act[col0 + tid])) return;   /* every column of the block has stopped */  \
     for (int i = tid; i <= (NR); i += VK_EMIT_TB) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];       \
     const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
     {                                                                                                                    \
@@ -166,6 +167,7 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     double *ks = rb + (TB) * (RLD);                                                                                      \
     const int j = (int)(blockIdx.x % (unsigned)a.nz), col0 = (int)(blockIdx.x / (unsigned)a.nz) * (TB);                  \
     const int ncb = min((TB), a.ncol - col0);                                                                            \
+    if (a.act && !__syncthreads_or(tid < ncb && a.act[col0 + tid])) return;   /* every column of the block has stopped */  \
     for (int i = tid; i <= (NR); i += (TB)) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];             \
     const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
     for (int cc = wrp; cc < (TB); cc += (TB) / 32) {                                                                     \
