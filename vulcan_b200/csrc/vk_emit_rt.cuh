@@ -111,7 +111,8 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     const int ncb = min(VK_EMIT_TB, a.ncol - col0);                                                                      \
     if (a.act && !__syncthreads_or(tid < ncb && a.act[col0 + tid])) return;   /* every column of the block has stopped */  \
     for (int i = tid; i <= (NR); i += VK_EMIT_TB) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];       \
-    const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
+    /* rows the run rewrites per column (KG): the thread's own column; with one shared k they are in the block's copy too */ \
+    const double *const kg = a.k_cs ? a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1) : ks; \
     {                                                                                                                    \
         const double rr = 1. + 1. / sqrt(2.);                                                                            \
         for (int cc = wrp; cc < VK_EMIT_TB; cc += VK_EMIT_TB / 32) {                                                     \
@@ -169,7 +170,8 @@ __device__ __forceinline__ double emit_row_sum(const double *yT, int n, int n_ga
     const int ncb = min((TB), a.ncol - col0);                                                                            \
     if (a.act && !__syncthreads_or(tid < ncb && a.act[col0 + tid])) return;   /* every column of the block has stopped */  \
     for (int i = tid; i <= (NR); i += (TB)) ks[i] = a.k[(size_t)col0 * a.k_cs + (size_t)j * ((NR) + 1) + i];             \
-    const double *const kg = a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1);             \
+    /* rows the run rewrites per column (KG): the thread's own column; with one shared k they are in the block's copy too */ \
+    const double *const kg = a.k_cs ? a.k + (size_t)(col0 + (tid < ncb ? tid : 0)) * a.k_cs + (size_t)j * ((NR) + 1) : ks; \
     for (int cc = wrp; cc < (TB); cc += (TB) / 32) {                                                                     \
         const size_t base = ((size_t)(col0 + cc) * a.nz + j) * (NI);                                                     \
         for (int s = lane; s < (NI); s += 32) rb[cc * (RLD) + s] = (cc < ncb) ? a.y[base + s] : 0.0;                     \
