@@ -464,6 +464,9 @@ def main():
                             "frac": flops / (fms * 1e-3) / 1e12 / peak, "traffic": traffic,
                             "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                             "flops_per_column_step": FLOP_FACTOR(nz, ni), "kernel_ms": fms, "kernel_ms_how": factor_how,
+                            "note": "since round 2 the kernel also forms the forward elimination of the first solve for columns with dt < 1e3 s "
+                                    "(z = W t, 2 nz ni^2 flop per column, NOT counted in the algorithmic flops; +1.3 ms of kernel time that saves a "
+                                    "4.2 ms sweep of lu_solve_kernel)",
                             "share_of_step": fms / (ms_max / args.steps)}
         # HBM roofline of the streaming kernels (north_star: "achieved HBM GB/s for the rate/RHS/diffusion kernels"), algorithmic bytes
         # per column as DESIGN.md section 4 states them; peak = MEASURED_PEAKS.json (driver-written copy bandwidth) or the recipe's fallback
