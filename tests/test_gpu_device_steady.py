@@ -172,3 +172,31 @@ def test_ensemble_columns_against_reference_runs():
             print("column %d: the reference against itself (second hash seed: %d steps, t %.3e): > 1e-4 %.2e, > 1e-8 %.2e | device against the "
                   "reference: %.2e, %.2e" % (q, n2, t2, s4, s8, rel[yr > 1e-4].max(), rel[yr > 1e-8].max()))
             assert rel[yr > 1e-4].max() < 6 * s4 and rel[yr > 1e-8].max() < 6 * s8, q
+
+
+def test_steady_ensemble_on_the_emitted_kernels(monkeypatch):
+    """a steady-state ensemble of 40 columns (per-column k with shared thermal rows -> the emitted chemistry kernels with KG rows, `act`
+    flags, a partial block of 128) against the same ensemble on the table-driven kernels over the first 300 loop iterations (photolysis
+    updates, accept / reject, mu / dz updates included): same accepted / rejected counts, states equal to the rounding of the Jacobian"""
+    from vulcan_b200 import ensemble
+    c = Case("HD189", 0)
+    ncol = 40
+    kz, met, co = [a[:ncol] for a in ensemble.sweep_grid()]
+    y, atom_ini = ensemble.synthetic_columns(c.st["y_ini"], c.st["n_0"], c.st["compo"], c.cfg["atom_list"], kz, met, co)
+    outs = []
+    for emitted in (True, False):
+        if not emitted:
+            monkeypatch.setenv("VK_EMIT", "0")
+            monkeypatch.setenv("VK_EMIT_JAC", "0")
+        r = steady_ensemble_from_fixture(c, y, atom_ini, kz)
+        r.col.ens_run_steady(300)
+        outs.append(r.state())
+        r.col.close()
+    a, b = outs
+    assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["n_reject"], b["n_reject"])
+    assert a["n_accept"].min() > 200
+    assert np.allclose(a["t"], b["t"], rtol=1e-9)
+    m = b["y"] > 1e-12 * b["y"].sum(axis=2, keepdims=True)
+    err = np.max(np.abs(a["y"] - b["y"])[m] / b["y"][m])
+    print("40-column steady ensemble, 300 iterations: emitted vs table-driven kernels, max rel diff of y %.2e" % err)
+    assert err < 1e-6
