@@ -163,3 +163,15 @@ def test_terms_out_of_reaction_order_are_refused():
     t["rhs_pair"] = pair
     with pytest.raises(ValueError):
         emit.emit_chemdf(t, "broken")
+
+
+def test_registered_tables_round_trip(tmp_path, monkeypatch):
+    """python -m vulcan_b200.emit <network>: the tables written under networks/ are the ones the emitter and the hash read back"""
+    c = Case("HD189", 0)
+    monkeypatch.setattr(emit, "NET_DIR", str(tmp_path))
+    out = emit.register_network(c.net, "roundtrip")
+    z = np.load(out)
+    t = c.net.tables()
+    for key in emit.TABLE_KEYS:
+        assert np.array_equal(np.asarray(z[key]), np.asarray(t[key])), key
+    assert emit.has_kernel(c.net)          # found by hash in the (temporary) registry directory

@@ -17,3 +17,9 @@ def test_group_bounds_cover_the_columns_once():
         assert all(b[g][1] == b[g + 1][0] for g in range(G - 1))
         sizes = np.array([hi - lo for lo, hi in b])
         assert sizes.min() >= 32 and sizes.max() - sizes.min() <= 1      # every group takes the emitted kernels
+
+
+def test_numa_binding_is_best_effort():
+    """no GPU / no NVML / a single-node VM: the helper reports what it found and never raises (bench.py calls it on every rank)"""
+    info = ensemble.bind_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and info["device"] == 0 and "node" in info
