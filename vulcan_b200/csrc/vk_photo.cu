@@ -263,13 +263,14 @@ __global__ void __launch_bounds__(256) jrate_kernel(JArgs a)
     }
 }
 
+// (4 layers x 8 branches per warp: 32 accumulators, two blocks of 8 warps per SM)
 // One warp per (column, tile of JR_LT layers, tile of JR_BT branches): lanes stride over the wavelength bins; the cross section of a branch
 // at a bin is loaded once for the JR_LT layers, the actinic flux of a layer at a bin once for the JR_BT branches (the first version - one warp
 // per (column, branch, layer) - moved 18 GB through L1 / L2 per 64 columns).  Every lane adds its bins in increasing order exactly as before,
 // so J has the same bits.
 #define JR_LT 4
-#define JR_BT 16
-__global__ void __launch_bounds__(256) jrate_tile_kernel(JArgs a)
+#define JR_BT 8
+__global__ void __launch_bounds__(256, 2) jrate_tile_kernel(JArgs a)
 {
     const int lane = threadIdx.x & 31;
     const size_t w = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(256) jrate_tile_kernel(JArgs a)
         const int br = br0 + (q < nb ? q : 0);
         return (a.br_is_T && a.br_is_T[br]) ? a.cross_J_T + ((size_t)br * a.nz + j0 + (l < nl ? l : 0)) * a.nbin : a.cross_J + (size_t)br * a.nbin;
     };
-    double v[JR_LT][JR_BT];
+    __shared__ double vs[8][JR_LT][JR_BT];      // region-0 part of every J of the warp's tile (keeps 64 doubles out of the registers)
+    double (*v)[JR_BT] = vs[threadIdx.x >> 5];
     for (int region = 0; region < 2; region++) {
         const int lo = region ? a.i12 : 0, hi = region ? a.nbin : a.i12;
         const double db = region ? a.dbin2 : a.dbin1;
@@ -329,8 +331,10 @@ __global__ void __launch_bounds__(256) jrate_tile_kernel(JArgs a)
                 // trapezoid on the uniform grid of the region: the end points count half (op.py:2766-2786)
                 const double *cc = cptr(q, l);
                 const double e = 0.5 * (f[l][lo] * cc[lo] + f[l][hi - 1] * cc[hi - 1]) * db;
-                if (region == 0) v[l][q] = s - e;
-                else { v[l][q] += s; v[l][q] -= e; }
+                if (lane == 0) {
+                    if (region == 0) v[l][q] = s - e;
+                    else { double t = v[l][q]; t += s; t -= e; v[l][q] = t; }
+                }
             }
     }
     if (lane == 0) {
